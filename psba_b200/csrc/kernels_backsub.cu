@@ -1,0 +1,287 @@
+// kernels_backsub.cu -- point back-substitution, parameter update and cost of the candidate, fused
+// per point chunk; plus the small vector kernels of the trust-region driver.
+//
+// Replaces kern_compute_eb (CL_files/compute_eb.cl:6-41), kern_compute_dpb (compute_dpb.cl:6-35),
+// kern_compute_newp (compute_newp.cl:6-26), the re-evaluation kern_compute_exQT
+// (compute_exQT.cl:18-71) and the host reductions compute_L2_sq / compute_rho
+// (PSBA/misc.cpp:151-157, PSBA/levmar.cpp:271-280).  kern_update_p (update_p.cl:6-25) is a
+// pointer swap of the two parameter sets.
+#include "dev_math.cuh"
+
+// candidate cameras = cams + dpa, plus the camera part of the step scalars
+__global__ void k_newcams(int N, const double *__restrict__ cams, const double *__restrict__ dpa, const double *__restrict__ ga,
+                          double mu, double *__restrict__ newcams, double *__restrict__ scal2)
+{
+    __shared__ double s0[256], s1[256];
+    double a = 0.0, b = 0.0;
+    for (int k = threadIdx.x; k < N; k += 256) {
+        const double d = dpa[k];
+        newcams[k] = cams[k] + d;
+        a += d * d;
+        b += d * (mu * d + ga[k]);
+    }
+    s0[threadIdx.x] = a; s1[threadIdx.x] = b;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) { s0[threadIdx.x] += s0[threadIdx.x + w]; s1[threadIdx.x] += s1[threadIdx.x + w]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { scal2[0] = s0[0]; scal2[1] = s1[0]; }
+}
+
+// CTA = one chunk of whole points (same chunks as k_lin_points).
+//  phase A (thread per observation): t = W_ij^T dpa_j -> shared
+//  phase B (owner thread per point): eb = gb - sum_j t (ascending camera, compute_eb.cl:27-37),
+//           dpb = Vinv eb (compute_dpb.cl:23-32), candidate point, |dpb|^2, dpb.(mu dpb + gb)
+//  phase C (thread per observation): residual of the candidate -> ||e||^2
+// EVAL=false stops after phase B (trust region: the step is formed on the host side first).
+template <bool EVAL>
+__global__ void __launch_bounds__(PT_CTA) k_backsub(const int *__restrict__ ptchunk, const int *__restrict__ pt_ptr,
+                                                   const int *__restrict__ iidx, const int *__restrict__ jidx,
+                                                   const double *__restrict__ impts, const double *__restrict__ W,
+                                                   const double *__restrict__ Vinv, const double *__restrict__ gb,
+                                                   const double *__restrict__ dpa, const double *__restrict__ pts,
+                                                   const double *__restrict__ newcache, double mu,
+                                                   double *__restrict__ eb, double *__restrict__ dpb, double *__restrict__ newpts,
+                                                   double *__restrict__ part)
+{
+    __shared__ double sh[3][PT_CTA];
+    __shared__ double shx[3][PT_CTA];
+    __shared__ double red[3][8];
+    const int tid = threadIdx.x;
+    const int p0 = ptchunk[blockIdx.x], p1 = ptchunk[blockIdx.x + 1];
+    const int o0 = pt_ptr[p0], o1 = pt_ptr[p1];
+    const int np = p1 - p0;
+    double acc0 = 0, acc1 = 0, acc2 = 0;
+    int my_a = 0, my_b = 0;
+    if (tid < np) { my_a = pt_ptr[p0 + tid]; my_b = pt_ptr[p0 + tid + 1]; }
+
+    for (int base = o0; base < o1; base += PT_CTA) {
+        const int k = base + tid;
+        if (k < o1) {
+            const double2 *wp = reinterpret_cast<const double2 *>(W + (size_t)k * 18);
+            const double *d = dpa + jidx[k] * 6;
+            double w[18];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { double2 w2 = __ldg(wp + q); w[2 * q] = w2.x; w[2 * q + 1] = w2.y; }
+            double t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { const double dr = __ldg(d + r); t0 += w[r * 3] * dr; t1 += w[r * 3 + 1] * dr; t2 += w[r * 3 + 2] * dr; }
+            sh[0][tid] = t0; sh[1][tid] = t1; sh[2][tid] = t2;
+        }
+        __syncthreads();
+        if (tid < np) {
+            const int a = max(my_a, base), b = min(my_b, base + PT_CTA);
+            for (int q = a; q < b; ++q) { acc0 += sh[0][q - base]; acc1 += sh[1][q - base]; acc2 += sh[2][q - base]; }
+        }
+        __syncthreads();
+    }
+    double s_dp2 = 0.0, s_dpg = 0.0, s_e2 = 0.0;
+    if (tid < np) {
+        const int p = p0 + tid;
+        const double g0 = gb[(size_t)p * 3], g1 = gb[(size_t)p * 3 + 1], g2 = gb[(size_t)p * 3 + 2];
+        const double e0 = g0 - acc0, e1 = g1 - acc1, e2 = g2 - acc2;
+        const double *vi = Vinv + (size_t)p * 6;
+        const double i00 = vi[0], i10 = vi[1], i20 = vi[2], i11 = vi[3], i21 = vi[4], i22 = vi[5];
+        const double d0 = i00 * e0 + i10 * e1 + i20 * e2;
+        const double d1 = i10 * e0 + i11 * e1 + i21 * e2;
+        const double d2 = i20 * e0 + i21 * e1 + i22 * e2;
+        eb[(size_t)p * 3] = e0; eb[(size_t)p * 3 + 1] = e1; eb[(size_t)p * 3 + 2] = e2;
+        dpb[(size_t)p * 3] = d0; dpb[(size_t)p * 3 + 1] = d1; dpb[(size_t)p * 3 + 2] = d2;
+        if (EVAL) {
+            const double x0 = pts[(size_t)p * 3] + d0, x1 = pts[(size_t)p * 3 + 1] + d1, x2 = pts[(size_t)p * 3 + 2] + d2;
+            newpts[(size_t)p * 3] = x0; newpts[(size_t)p * 3 + 1] = x1; newpts[(size_t)p * 3 + 2] = x2;
+            shx[0][tid] = x0; shx[1][tid] = x1; shx[2][tid] = x2;
+            s_dp2 = d0 * d0 + d1 * d1 + d2 * d2;
+            s_dpg = d0 * (mu * d0 + g0) + d1 * (mu * d1 + g1) + d2 * (mu * d2 + g2);
+        }
+    }
+    if (!EVAL) return;
+    __syncthreads();
+    for (int base = o0; base < o1; base += PT_CTA) {
+        const int k = base + tid;
+        if (k < o1) {
+            CamProj cam;
+            load_cam_proj(newcache + (size_t)jidx[k] * CAMC, cam);
+            const int lp = iidx[k] - p0;
+            double2 mm = __ldg(reinterpret_cast<const double2 *>(impts) + k);
+            double e0, e1;
+            residual(cam, shx[0][lp], shx[1][lp], shx[2][lp], mm.x, mm.y, e0, e1);
+            s_e2 += e0 * e0 + e1 * e1;
+        }
+    }
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) {
+        s_e2 += __shfl_down_sync(0xffffffffu, s_e2, w);
+        s_dp2 += __shfl_down_sync(0xffffffffu, s_dp2, w);
+        s_dpg += __shfl_down_sync(0xffffffffu, s_dpg, w);
+    }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = s_e2; red[1][tid >> 5] = s_dp2; red[2][tid >> 5] = s_dpg; }
+    __syncthreads();
+    if (tid < 3) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < PT_CTA / 32; ++w) s += red[tid][w];
+        part[(size_t)blockIdx.x * 3 + tid] = s;
+    }
+}
+
+__global__ void k_final_reduce3(const double *__restrict__ part, int nparts, double *__restrict__ out);
+
+// out[v] = sum_p part[p*3+v], v<3, fixed order
+__global__ void k_final_reduce3(const double *__restrict__ part, int nparts, double *__restrict__ out)
+{
+    __shared__ double sh[3][256];
+    double s[3] = {0, 0, 0};
+    for (int p = threadIdx.x; p < nparts; p += 256) { s[0] += part[(size_t)p * 3]; s[1] += part[(size_t)p * 3 + 1]; s[2] += part[(size_t)p * 3 + 2]; }
+    sh[0][threadIdx.x] = s[0]; sh[1][threadIdx.x] = s[1]; sh[2][threadIdx.x] = s[2];
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) { sh[0][threadIdx.x] += sh[0][threadIdx.x + w]; sh[1][threadIdx.x] += sh[1][threadIdx.x + w]; sh[2][threadIdx.x] += sh[2][threadIdx.x + w]; }
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) out[threadIdx.x] = sh[threadIdx.x][0];
+}
+
+// evaluate=true : dp (cams+points), candidate parameters, candidate cost, step scalars (LM try)
+// evaluate=false: eb and dpb only (trust region / compat)
+void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result *res)
+{
+    const int cur = c->cur, nw = 1 - cur;
+    double *gb = c->g + c->N, *ebp = c->eab + c->N, *dpbp = c->dp + c->N;
+    if (evaluate) {
+        k_newcams<<<1, 256, 0, c->stream>>>(c->N, c->cams[cur], c->dp, c->g, mu, c->cams[nw], c->d_scal + 4);
+        psba_launch_cam_prep(c, nw);
+        if (c->n_ptchunk > 0)
+            k_backsub<true><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptchunk, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
+                                                                   gb, c->dp, c->pts[cur], c->camcache[nw], mu, ebp, dpbp,
+                                                                   c->pts[nw], c->d_part);
+        k_final_reduce3<<<1, 256, 0, c->stream>>>(c->d_part, c->n_ptchunk, c->d_scal);
+        c->st_launches += 3; c->st_exqt += 1;
+        if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal, 3);
+        CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (res) {
+            res->cost_new = c->h_scal[0];
+            res->dp_L2 = c->h_scal[4] + c->h_scal[1];      // cameras first, then points (misc.cpp:151-157 order)
+            res->dp_dot = c->h_scal[5] + c->h_scal[2];
+        }
+    } else {
+        if (c->n_ptchunk > 0)
+            k_backsub<false><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptchunk, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
+                                                                    gb, c->dp, c->pts[cur], c->camcache[cur], mu, ebp, dpbp,
+                                                                    c->pts[nw], c->d_part);
+        c->st_launches += 1;
+    }
+}
+
+// new = cur + dp for an externally supplied step in c->dp (compute_newp.cl:6-26)
+__global__ void k_newp(int n, const double *__restrict__ a, const double *__restrict__ d, double *__restrict__ out)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = a[k] + d[k];
+}
+
+void psba_launch_newp(psba_ctx *c)
+{
+    const int cur = c->cur, nw = 1 - cur;
+    k_newp<<<cdiv(c->N, 256), 256, 0, c->stream>>>(c->N, c->cams[cur], c->dp, c->cams[nw]);
+    if (c->n > 0) k_newp<<<cdiv(3 * c->n, 256), 256, 0, c->stream>>>(3 * c->n, c->pts[cur], c->dp + c->N, c->pts[nw]);
+    c->cache_valid[nw] = false;
+    c->st_launches += 2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// all pairwise dot products of up to three [N | 3n] vectors: out = {xx, xy, xz, yy, yz, zz}.
+// Camera part (replicated across ranks) and point part (sharded) are reduced separately.
+__global__ void __launch_bounds__(256) k_dots(int n, const double *__restrict__ x, const double *__restrict__ y,
+                                              const double *__restrict__ z, double *__restrict__ part)
+{
+    __shared__ double sh[16 * (256 + 4)];
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = blockIdx.x * 256 + threadIdx.x; k < n; k += gridDim.x * 256) {
+        const double a = x[k], b = y[k], cc = z[k];
+        v[0] += a * a; v[1] += a * b; v[2] += a * cc; v[3] += b * b; v[4] += b * cc; v[5] += cc * cc;
+    }
+    block_reduce_to<6, 256, 16>(v, sh, part + (size_t)blockIdx.x * 6);
+}
+
+__global__ void k_final_reduce6(const double *__restrict__ part, int nparts, double *__restrict__ out)
+{
+    int v = threadIdx.x;
+    if (v >= 6) return;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += part[(size_t)p * 6 + v];
+    out[v] = s;
+}
+
+void psba_launch_dots(psba_ctx *c, const double *x, const double *y, const double *z, double out[6])
+{
+    // camera part
+    k_dots<<<1, 256, 0, c->stream>>>(c->N, x, y, z, c->d_part);
+    k_final_reduce6<<<1, 32, 0, c->stream>>>(c->d_part, 1, c->d_scal);
+    // point part
+    const int np = 3 * c->n;
+    int nb = np > 0 ? std::min(cdiv(np, 256), 296) : 0;
+    if (nb > 0) k_dots<<<nb, 256, 0, c->stream>>>(np, x + c->N, y + c->N, z + c->N, c->d_part + 8);
+    k_final_reduce6<<<1, 32, 0, c->stream>>>(c->d_part + 8, nb, c->d_scal + 6);
+    c->st_launches += 4;
+    if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal + 6, 6);
+    CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, 12 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int v = 0; v < 6; ++v) out[v] = c->h_scal[v] + c->h_scal[6 + v];
+}
+
+__global__ void k_axpby(int n, double a, const double *__restrict__ x, double b, const double *__restrict__ y, double *__restrict__ out)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = a * x[k] + b * y[k];
+}
+
+void psba_launch_axpby(psba_ctx *c, double a, const double *x, double b, const double *y, double *out)
+{
+    const int n = c->N + 3 * c->n;
+    k_axpby<<<cdiv(n, 256), 256, 0, c->stream>>>(n, a, x, b, y, out);
+    c->st_launches += 1;
+}
+
+// max over the diagonals of U and V (maxElmOfUV, sba_func.cpp:422-444; only positive values count)
+__global__ void k_maxdiag(int m, int n, const double *__restrict__ U, const double *__restrict__ V, double *__restrict__ part)
+{
+    __shared__ double sh[256];
+    double mx = 0.0;
+    const int tot = 6 * m + 3 * n;
+    for (int k = blockIdx.x * 256 + threadIdx.x; k < tot; k += gridDim.x * 256) {
+        double v;
+        if (k < 6 * m) { const int j = k / 6, r = k - j * 6; v = U[j * 36 + r * 7]; }
+        else { const int q = k - 6 * m, i = q / 3, r = q - i * 3; v = V[(size_t)i * 6 + (r == 0 ? 0 : (r == 1 ? 3 : 5))]; }
+        if (v > mx) mx = v;
+    }
+    sh[threadIdx.x] = mx;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + w]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+
+__global__ void k_final_max(const double *__restrict__ part, int nparts, double *__restrict__ out)
+{
+    double mx = 0.0;
+    for (int p = 0; p < nparts; ++p) mx = fmax(mx, part[p]);
+    out[0] = mx;
+}
+
+double psba_launch_maxdiag(psba_ctx *c)
+{
+    const int tot = c->N + 3 * c->n;
+    const int nb = std::min(cdiv(tot, 256), 296);
+    k_maxdiag<<<nb, 256, 0, c->stream>>>(c->m, c->n, c->U, c->V, c->d_part);
+    k_final_max<<<1, 1, 0, c->stream>>>(c->d_part, nb, c->d_scal);
+    c->st_launches += 2;
+    if (c->nranks > 1) psba_allreduce_max(c, c->d_scal, 1);
+    CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return c->h_scal[0];
+}

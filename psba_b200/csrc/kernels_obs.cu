@@ -1,0 +1,372 @@
+// kernels_obs.cu -- per-observation kernels: camera cache, residual / cost, fused linearisation
+// (point-major pass: W, V, gb; camera-major pass: U, ga), materialised Jacobian (compat only)
+// and J*x products with fused dot products (trust region).
+//
+// Replaces kern_compute_exQT (CL_files/compute_exQT.cl:18-71), kern_compute_jacobiQT
+// (compute_jacobiQT.cl:7-141), kern_compute_U/V/Wblks/g (compute_U.cl:5-35, compute_V.cl:6-38,
+// compute_Wblks.cl:7-34, compute_g.cl:6-60) and kern_compute_Jmultiply (compute_Jmultiply.cl:6-52).
+// The Jacobian never reaches HBM: both passes recompute it from 17+27 cached doubles per camera.
+// All cross-thread sums have a fixed order (no atomics) => bit-reproducible run to run.
+#include "dev_math.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// per-camera cache: M(q), t, K, G_k = dM/dv_k
+__global__ void k_cam_prep(int m, const double *__restrict__ K, const double *__restrict__ initcams,
+                           const double *__restrict__ cams, double *__restrict__ cache)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const double s0 = initcams[j * 4], a1 = initcams[j * 4 + 1], a2 = initcams[j * 4 + 2], a3 = initcams[j * 4 + 3];
+    const double v1 = cams[j * 6], v2 = cams[j * 6 + 1], v3 = cams[j * 6 + 2];
+    const double sl = sqrt(1 - v1 * v1 - v2 * v2 - v3 * v3);
+    // q = ql (x) q0, same operation order as compute_exQT.cl:46-49
+    const double s = sl * s0 - (a1 * v1 + a2 * v2 + a3 * v3);
+    const double x = s0 * v1 + sl * a1 + a3 * v2 - a2 * v3;
+    const double y = s0 * v2 + sl * a2 + a1 * v3 - a3 * v1;
+    const double z = s0 * v3 + sl * a3 + a2 * v1 - a1 * v2;
+    double *c = cache + (size_t)j * CAMC;
+    c[CC_R + 0] = s * s + x * x - y * y - z * z; c[CC_R + 1] = 2 * (x * y - s * z); c[CC_R + 2] = 2 * (x * z + s * y);
+    c[CC_R + 3] = 2 * (x * y + s * z); c[CC_R + 4] = s * s - x * x + y * y - z * z; c[CC_R + 5] = 2 * (y * z - s * x);
+    c[CC_R + 6] = 2 * (x * z - s * y); c[CC_R + 7] = 2 * (y * z + s * x); c[CC_R + 8] = s * s - x * x - y * y + z * z;
+    c[CC_T + 0] = cams[j * 6 + 3]; c[CC_T + 1] = cams[j * 6 + 4]; c[CC_T + 2] = cams[j * 6 + 5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) c[CC_K + k] = K[j * 5 + k];
+    const double vv[3] = {v1, v2, v3};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        // d ql / d v_k = (-v_k/sl, e_k);  dq = dql (x) q0
+        const double ds_l = -vv[k] / sl;
+        const double e1 = (k == 0), e2 = (k == 1), e3 = (k == 2);
+        const double ds = ds_l * s0 - (a1 * e1 + a2 * e2 + a3 * e3);
+        const double dx = s0 * e1 + ds_l * a1 + a3 * e2 - a2 * e3;
+        const double dy = s0 * e2 + ds_l * a2 + a1 * e3 - a3 * e1;
+        const double dz = s0 * e3 + ds_l * a3 + a2 * e1 - a1 * e2;
+        double *G = c + CC_G + 9 * k;
+        G[0] = 2 * (s * ds + x * dx - y * dy - z * dz);
+        G[1] = 2 * (dx * y + x * dy - ds * z - s * dz);
+        G[2] = 2 * (dx * z + x * dz + ds * y + s * dy);
+        G[3] = 2 * (dx * y + x * dy + ds * z + s * dz);
+        G[4] = 2 * (s * ds - x * dx + y * dy - z * dz);
+        G[5] = 2 * (dy * z + y * dz - ds * x - s * dx);
+        G[6] = 2 * (dx * z + x * dz - ds * y - s * dy);
+        G[7] = 2 * (dy * z + y * dz + ds * x + s * dx);
+        G[8] = 2 * (s * ds - x * dx - y * dy + z * dz);
+    }
+    for (int k = 44; k < CAMC; ++k) c[k] = 0.0;
+}
+
+void psba_launch_cam_prep(psba_ctx *c, int set)
+{
+    k_cam_prep<<<cdiv(c->m, 128), 128, 0, c->stream>>>(c->m, c->K, c->initcams, c->cams[set], c->camcache[set]);
+    c->cache_valid[set] = true;
+    c->st_launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// final deterministic reduction of per-CTA partials: out[v] = sum_p part[p*stride + v]
+__global__ void k_final_reduce(const double *__restrict__ part, int nparts, int stride, int nv, double *__restrict__ out)
+{
+    __shared__ double sh[256];
+    for (int v = 0; v < nv; ++v) {
+        double s = 0.0;
+        for (int p = threadIdx.x; p < nparts; p += 256) s += part[(size_t)p * stride + v];
+        sh[threadIdx.x] = s;
+        __syncthreads();
+        for (int w = 128; w > 0; w >>= 1) {
+            if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[v] = sh[0];
+        __syncthreads();
+    }
+}
+
+// residual + cost. One thread per observation (coalesced impts / idx loads, cached gathers).
+__global__ void __launch_bounds__(256) k_cost(int o, const int *__restrict__ iidx, const int *__restrict__ jidx,
+                                              const double *__restrict__ impts, const double *__restrict__ cache,
+                                              const double *__restrict__ pts, double *__restrict__ ex,
+                                              double *__restrict__ part)
+{
+    __shared__ double sh[8];
+    int k = blockIdx.x * 256 + threadIdx.x;
+    double e2 = 0.0;
+    if (k < o) {
+        CamProj cam;
+        load_cam_proj(cache + (size_t)jidx[k] * CAMC, cam);
+        const double *X = pts + (size_t)iidx[k] * 3;
+        double2 mm = __ldg(reinterpret_cast<const double2 *>(impts) + k);
+        double e0, e1;
+        residual(cam, __ldg(X), __ldg(X + 1), __ldg(X + 2), mm.x, mm.y, e0, e1);
+        if (ex) reinterpret_cast<double2 *>(ex)[k] = make_double2(e0, e1);
+        e2 = e0 * e0 + e1 * e1;
+    }
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) e2 += __shfl_down_sync(0xffffffffu, e2, w);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = e2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += sh[w];
+        part[blockIdx.x] = s;
+    }
+}
+
+static void read_scalars(psba_ctx *c, int off, int n)
+{
+    CUDA_CHECK(cudaMemcpyAsync(c->h_scal + off, c->d_scal + off, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+double psba_launch_cost(psba_ctx *c, int set, double *ex_dev)
+{
+    if (!c->cache_valid[set]) psba_launch_cam_prep(c, set);
+    int nb = cdiv(c->o, 256);
+    if (nb > 0)
+        k_cost<<<nb, 256, 0, c->stream>>>(c->o, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set], ex_dev, c->d_part);
+    k_final_reduce<<<1, 256, 0, c->stream>>>(c->d_part, nb, 1, 1, c->d_scal);
+    c->st_launches += 2; c->st_exqt += 1;
+    if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal, 1);
+    read_scalars(c, 0, 1);
+    return c->h_scal[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// point-major linearisation pass.  CTA = one chunk of whole points (<= PT_CTA observations per
+// wave).  Thread k: observation -> e, A, B in registers; W = c*A^T B written straight to HBM
+// (144 B per observation, the only per-observation product that persists); B^T B (6) and B^T e (3)
+// go through shared memory to the point's owner thread, which sums them in ascending camera
+// order (the order of compute_V.cl:24-31 / compute_g.cl:43-54).
+__global__ void __launch_bounds__(PT_CTA) k_lin_points(const int *__restrict__ ptchunk, const int *__restrict__ pt_ptr,
+                                                      const int *__restrict__ iidx, const int *__restrict__ jidx,
+                                                      const double *__restrict__ impts, const double *__restrict__ cache,
+                                                      const double *__restrict__ pts, double coeff, double coeff_g,
+                                                      double *__restrict__ W, double *__restrict__ V, double *__restrict__ gb)
+{
+    __shared__ double sh[9][PT_CTA];
+    const int tid = threadIdx.x;
+    const int p0 = ptchunk[blockIdx.x], p1 = ptchunk[blockIdx.x + 1];
+    const int o0 = pt_ptr[p0], o1 = pt_ptr[p1];
+    const int np = p1 - p0;
+    double acc[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+    int my_a = 0, my_b = 0;
+    if (tid < np) { my_a = pt_ptr[p0 + tid]; my_b = pt_ptr[p0 + tid + 1]; }
+
+    for (int base = o0; base < o1; base += PT_CTA) {
+        const int k = base + tid;
+        if (k < o1) {
+            CamReg cam;
+            load_cam(cache + (size_t)jidx[k] * CAMC, cam);
+            const double *X = pts + (size_t)iidx[k] * 3;
+            double2 mm = __ldg(reinterpret_cast<const double2 *>(impts) + k);
+            double e0, e1, A[12], B[6];
+            residual_jac(cam, __ldg(X), __ldg(X + 1), __ldg(X + 2), mm.x, mm.y, e0, e1, A, B);
+            double2 *Wk = reinterpret_cast<double2 *>(W + (size_t)k * 18);
+            double w[18];
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) w[r * 3 + cc] = coeff * (A[r] * B[cc] + A[6 + r] * B[3 + cc]);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) Wk[q] = make_double2(w[2 * q], w[2 * q + 1]);
+            sh[0][tid] = B[0] * B[0] + B[3] * B[3];
+            sh[1][tid] = B[0] * B[1] + B[3] * B[4];
+            sh[2][tid] = B[0] * B[2] + B[3] * B[5];
+            sh[3][tid] = B[1] * B[1] + B[4] * B[4];
+            sh[4][tid] = B[1] * B[2] + B[4] * B[5];
+            sh[5][tid] = B[2] * B[2] + B[5] * B[5];
+            sh[6][tid] = B[0] * e0 + B[3] * e1;
+            sh[7][tid] = B[1] * e0 + B[4] * e1;
+            sh[8][tid] = B[2] * e0 + B[5] * e1;
+        }
+        __syncthreads();
+        if (tid < np) {
+            const int a = max(my_a, base), b = min(my_b, base + PT_CTA);
+            for (int q = a; q < b; ++q) {
+#pragma unroll
+                for (int v = 0; v < 9; ++v) acc[v] += sh[v][q - base];
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < np) {
+        double *Vp = V + (size_t)(p0 + tid) * 6;
+#pragma unroll
+        for (int v = 0; v < 6; ++v) Vp[v] = coeff * acc[v];
+        double *gp = gb + (size_t)(p0 + tid) * 3;
+        gp[0] = coeff_g * acc[6]; gp[1] = coeff_g * acc[7]; gp[2] = coeff_g * acc[8];
+    }
+}
+
+// camera-major pass: chunk = up to CAM_CTA*CAM_OPT observations of ONE camera (ascending point).
+// The camera cache entry is uniform per CTA; points and measurements are gathered (L2-resident).
+// Each thread accumulates A^T A (21 upper entries) and A^T e (6) over its observations, then one
+// deterministic block reduction per chunk writes 27 partials.
+__global__ void __launch_bounds__(CAM_CTA) k_lin_cams(const int *__restrict__ cchunk_cam, const int *__restrict__ cchunk_beg,
+                                                     const int *__restrict__ cchunk_end, const int *__restrict__ cam_obs,
+                                                     const int *__restrict__ iidx, const double *__restrict__ impts,
+                                                     const double *__restrict__ cache, const double *__restrict__ pts,
+                                                     double *__restrict__ part)
+{
+    __shared__ double sh[16 * (CAM_CTA + 4)];
+    const int ch = blockIdx.x;
+    const int beg = cchunk_beg[ch], end = cchunk_end[ch];
+    CamReg cam;
+    load_cam(cache + (size_t)cchunk_cam[ch] * CAMC, cam);
+    double acc[27];
+#pragma unroll
+    for (int q = 0; q < 27; ++q) acc[q] = 0.0;
+#pragma unroll 1
+    for (int t = beg + threadIdx.x; t < end; t += CAM_CTA) {
+        const int k = cam_obs[t];
+        const double *X = pts + (size_t)iidx[k] * 3;
+        double2 mm = __ldg(reinterpret_cast<const double2 *>(impts) + k);
+        double e0, e1, A[12], B[6];
+        residual_jac(cam, __ldg(X), __ldg(X + 1), __ldg(X + 2), mm.x, mm.y, e0, e1, A, B);
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int cc = r; cc < 6; ++cc) acc[q++] += A[r] * A[cc] + A[6 + r] * A[6 + cc];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) acc[21 + r] += A[r] * e0 + A[6 + r] * e1;
+    }
+    block_reduce_to<27, CAM_CTA, 16>(acc, sh, part + (size_t)ch * 27);
+}
+
+// per camera: sum chunk partials in order; expand the 21 upper entries to the full 6x6 block
+__global__ void k_cam_reduce(int m, const int *__restrict__ cam_cchunk_ptr, const double *__restrict__ part,
+                             double coeff, double coeff_g, double *__restrict__ U, double *__restrict__ ga)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = t / 27, v = t - j * 27;
+    if (j >= m) return;
+    double s = 0.0;
+    for (int ch = cam_cchunk_ptr[j]; ch < cam_cchunk_ptr[j + 1]; ++ch) s += part[(size_t)ch * 27 + v];
+    if (v < 21) {
+        int r = 0, rem = v;
+        while (rem >= 6 - r) { rem -= 6 - r; ++r; }
+        int cc = r + rem;
+        s *= coeff;
+        U[j * 36 + r * 6 + cc] = s;
+        U[j * 36 + cc * 6 + r] = s;
+    } else ga[j * 6 + (v - 21)] = coeff_g * s;
+}
+
+void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
+{
+    const int set = c->cur;
+    if (!c->cache_valid[set]) psba_launch_cam_prep(c, set);
+    if (c->n_ptchunk > 0)
+        k_lin_points<<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptchunk, c->pt_ptr, c->iidx, c->jidx, c->impts,
+                                                            c->camcache[set], c->pts[set], coeff_uvw, coeff_g,
+                                                            c->W, c->V, c->g + c->N);
+    if (c->n_cchunk > 0)
+        k_lin_cams<<<c->n_cchunk, CAM_CTA, 0, c->stream>>>(c->cchunk_cam, c->cchunk_beg, c->cchunk_end, c->cam_obs,
+                                                          c->iidx, c->impts, c->camcache[set], c->pts[set], c->cam_part);
+    k_cam_reduce<<<cdiv(c->m * 27, 128), 128, 0, c->stream>>>(c->m, c->cam_cchunk_ptr, c->cam_part, coeff_uvw, coeff_g,
+                                                             c->U, c->g);
+    c->st_launches += 3; c->st_lin += 1;
+    if (c->nranks > 1) {
+        psba_allreduce_sum(c, c->U, (size_t)c->m * 36);
+        psba_allreduce_sum(c, c->g, (size_t)c->N);
+    }
+    c->coeff_uvw = coeff_uvw; c->coeff_g = coeff_g;
+    c->lin_valid = true; c->S_valid = false; c->factor_valid = false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compat only: materialise JA (o x 2 x 6) and JB (o x 2 x 3) in the reference's layout
+__global__ void k_jac_materialize(int o, const int *__restrict__ iidx, const int *__restrict__ jidx,
+                                  const double *__restrict__ impts, const double *__restrict__ cache,
+                                  const double *__restrict__ pts, double *__restrict__ JA, double *__restrict__ JB)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= o) return;
+    CamReg cam;
+    load_cam(cache + (size_t)jidx[k] * CAMC, cam);
+    const double *X = pts + (size_t)iidx[k] * 3;
+    double e0, e1, A[12], B[6];
+    residual_jac(cam, X[0], X[1], X[2], impts[2 * k], impts[2 * k + 1], e0, e1, A, B);
+    for (int q = 0; q < 12; ++q) JA[(size_t)k * 12 + q] = A[q];
+    for (int q = 0; q < 6; ++q) JB[(size_t)k * 6 + q] = B[q];
+}
+
+void psba_launch_jac_materialize(psba_ctx *c, double *JA, double *JB)
+{
+    const int set = c->cur;
+    if (!c->cache_valid[set]) psba_launch_cam_prep(c, set);
+    if (c->o > 0)
+        k_jac_materialize<<<cdiv(c->o, 128), 128, 0, c->stream>>>(c->o, c->iidx, c->jidx, c->impts, c->camcache[set],
+                                                                 c->pts[set], JA, JB);
+    c->st_launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// J*x and J*y per observation with fused <Jx,Jx>, <Jx,Jy>, <Jy,Jy> (trust_region.cpp:125-126,
+// 166-176, 208-210).  x, y are [N | 3n] vectors; y may alias x.
+__global__ void __launch_bounds__(256) k_Jdot(int o, int N, const int *__restrict__ iidx, const int *__restrict__ jidx,
+                                              const double *__restrict__ impts, const double *__restrict__ cache,
+                                              const double *__restrict__ pts, const double *__restrict__ x,
+                                              const double *__restrict__ y, double *__restrict__ Jx_out,
+                                              double *__restrict__ part)
+{
+    __shared__ double sh[3][8];
+    int k = blockIdx.x * 256 + threadIdx.x;
+    double r0 = 0, r1 = 0, r2 = 0;
+    if (k < o) {
+        const int i = iidx[k], j = jidx[k];
+        CamReg cam;
+        load_cam(cache + (size_t)j * CAMC, cam);
+        const double *X = pts + (size_t)i * 3;
+        double e0, e1, A[12], B[6];
+        residual_jac(cam, __ldg(X), __ldg(X + 1), __ldg(X + 2), 0.0, 0.0, e0, e1, A, B);
+        const double *xa = x + j * 6, *xb = x + N + (size_t)i * 3;
+        const double *ya = y + j * 6, *yb = y + N + (size_t)i * 3;
+        double jx[2], jy[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            double sx = 0.0, sy = 0.0;
+#pragma unroll
+            for (int t = 0; t < 6; ++t) { sx += A[r * 6 + t] * xa[t]; sy += A[r * 6 + t] * ya[t]; }
+#pragma unroll
+            for (int t = 0; t < 3; ++t) { sx += B[r * 3 + t] * xb[t]; sy += B[r * 3 + t] * yb[t]; }
+            jx[r] = sx; jy[r] = sy;
+        }
+        if (Jx_out) { Jx_out[2 * (size_t)k] = jx[0]; Jx_out[2 * (size_t)k + 1] = jx[1]; }
+        r0 = jx[0] * jx[0] + jx[1] * jx[1];
+        r1 = jx[0] * jy[0] + jx[1] * jy[1];
+        r2 = jy[0] * jy[0] + jy[1] * jy[1];
+    }
+#pragma unroll
+    for (int w = 16; w > 0; w >>= 1) {
+        r0 += __shfl_down_sync(0xffffffffu, r0, w);
+        r1 += __shfl_down_sync(0xffffffffu, r1, w);
+        r2 += __shfl_down_sync(0xffffffffu, r2, w);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = r0; sh[1][threadIdx.x >> 5] = r1; sh[2][threadIdx.x >> 5] = r2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += sh[threadIdx.x][w];
+        part[(size_t)blockIdx.x * 3 + threadIdx.x] = s;
+    }
+}
+
+void psba_launch_Jdot(psba_ctx *c, const double *x, const double *y, double *Jx_out, double res[3])
+{
+    const int set = c->cur;
+    if (!c->cache_valid[set]) psba_launch_cam_prep(c, set);
+    int nb = cdiv(c->o, 256);
+    if (nb > 0)
+        k_Jdot<<<nb, 256, 0, c->stream>>>(c->o, c->N, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set],
+                                         x, y, Jx_out, c->d_part);
+    k_final_reduce<<<1, 256, 0, c->stream>>>(c->d_part, nb, 3, 3, c->d_scal);
+    c->st_launches += 2;
+    if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal, 3);
+    read_scalars(c, 0, 3);
+    res[0] = c->h_scal[0]; res[1] = c->h_scal[1]; res[2] = c->h_scal[2];
+}

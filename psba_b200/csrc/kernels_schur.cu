@@ -1,0 +1,224 @@
+// kernels_schur.cu -- damping + Schur complement build.
+//
+// Replaces kern_update_UV / kern_restore_UVdiag (CL_files/update_UV.cl, restore_UVdiag.cl: the
+// damping term is a kernel argument, U and V are never modified), kern_compute_Vinv
+// (compute_Vinv.cl:6-90), kern_compute_Yblks (compute_Yblks.cl:6-39: Y stays in registers),
+// kern_compute_S (compute_S.cl:6-78) and kern_compute_ea (compute_ea.cl:6-37).
+//
+// S_kl = delta_kl (U_k + mu I) - sum_{i in common(k,l)} Y_ik W_il^T is built only for k >= l (the
+// reference's solvers read only that part, SPD_inv.cl:43-57) from a list of (obs_k, obs_l) triples
+// sorted by camera pair with ascending point index -- the order of comm3DIdx (misc.cpp:199-209).
+// Partial sums per chunk of triples, then a fixed-order sum per pair block: no atomics.
+#include "dev_math.cuh"
+
+// packed symmetric storage: V = (v00,v01,v02,v11,v12,v22); Vinv = (i00,i10,i20,i11,i21,i22)
+__global__ void k_vinv(int n, const double *__restrict__ V, double mu, double *__restrict__ Vinv, int *__restrict__ flag)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *v = V + (size_t)i * 6;
+    const double a11 = v[0] + mu, a12 = v[1], a13 = v[2], a22 = v[3] + mu, a23 = v[4], a33 = v[5] + mu;
+    double T = (a33 * a12 * a12 - 2 * a12 * a13 * a23 + a22 * a13 * a13 + a11 * a23 * a23 - a11 * a22 * a33);
+    double *o = Vinv + (size_t)i * 6;
+    if (fabs(T) < 1e-16) {
+        // compute_Vinv.cl:31-73 : determinant by pivoted LU, adjugate of the (symmetric) block
+        *flag = 1;
+        double a[3][3] = {{a11, a12, a13}, {a12, a22, a23}, {a13, a23, a33}};
+        int mx = 0;
+        if (a[0][0] < a[1][0]) mx = 1;
+        if (a[mx][0] < a[2][0]) mx = 2;
+        if (mx != 0) for (int q = 0; q < 3; ++q) { double t = a[0][q]; a[0][q] = a[mx][q]; a[mx][q] = t; }
+        a[1][0] = a[1][0] / a[0][0]; a[2][0] = a[2][0] / a[0][0];
+        a[1][1] = a[1][1] - a[1][0] * a[0][1]; a[1][2] = a[1][2] - a[1][0] * a[0][2];
+        a[2][1] = a[2][1] - a[2][0] * a[0][1]; a[2][2] = a[2][2] - a[2][0] * a[0][2];
+        if (a[1][1] < a[2][1]) for (int q = 0; q < 3; ++q) { double t = a[1][q]; a[1][q] = a[2][q]; a[2][q] = t; }
+        if (a[1][1] != 0.0) { a[2][1] = a[2][1] / a[1][1]; a[2][2] = a[2][2] - a[2][1] * a[1][2]; }
+        T = a[0][0] * a[1][1] * a[2][2];
+        o[0] = (a22 * a33 - a23 * a23) / T;
+        o[1] = -(a12 * a33 - a23 * a13) / T;
+        o[3] = (a11 * a33 - a13 * a13) / T;
+        o[2] = (a12 * a23 - a22 * a13) / T;
+        o[4] = -(a11 * a23 - a12 * a13) / T;
+        o[5] = (a11 * a22 - a12 * a12) / T;
+        return;
+    }
+    o[0] = -(-a23 * a23 + a22 * a33) / T;
+    o[1] = -(a13 * a23 - a12 * a33) / T;
+    o[3] = -(-a13 * a13 + a11 * a33) / T;
+    o[2] = -(a12 * a23 - a13 * a22) / T;
+    o[4] = -(a12 * a13 - a11 * a23) / T;
+    o[5] = -(-a12 * a12 + a11 * a22) / T;
+}
+
+double psba_launch_vinv(psba_ctx *c, double mu)
+{
+    CUDA_CHECK(cudaMemsetAsync(c->d_status + 1, 0, sizeof(int), c->stream));
+    if (c->n > 0) k_vinv<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->V, mu, c->Vinv, c->d_status + 1);
+    c->st_launches += 1;
+    return 0.0;
+}
+
+// one CTA per chunk of triples of ONE camera pair (k >= l).  Thread: Y = W_a * Vinv_i row by row,
+// acc[r][c] += Y_r . W_b[c];  diagonal pairs also accumulate Y * gb_i (the ea sum).
+template <bool DIAG>
+__device__ __forceinline__ void pair_accumulate(long long beg, long long end, const int *__restrict__ tri_oa,
+                                                const int *__restrict__ tri_ob, const int *__restrict__ iidx,
+                                                const double *__restrict__ W, const double *__restrict__ Vinv,
+                                                const double *__restrict__ gb, double *acc)
+{
+#pragma unroll 1
+    for (long long t = beg + threadIdx.x; t < end; t += PAIR_CTA) {
+        const int a = tri_oa[t];
+        const int b = DIAG ? a : tri_ob[t];
+        const int i = iidx[a];
+        const double2 *vp = reinterpret_cast<const double2 *>(Vinv + (size_t)i * 6);
+        const double2 v01 = __ldg(vp), v23 = __ldg(vp + 1), v45 = __ldg(vp + 2);
+        const double i00 = v01.x, i10 = v01.y, i20 = v23.x, i11 = v23.y, i21 = v45.x, i22 = v45.y;
+        double wb[18];
+        const double2 *wbp = reinterpret_cast<const double2 *>(W + (size_t)b * 18);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) { double2 w2 = __ldg(wbp + q); wb[2 * q] = w2.x; wb[2 * q + 1] = w2.y; }
+        double g0 = 0, g1 = 0, g2 = 0;
+        if (DIAG) { const double *gp = gb + (size_t)i * 3; g0 = __ldg(gp); g1 = __ldg(gp + 1); g2 = __ldg(gp + 2); }
+        const double *wa = DIAG ? wb : nullptr;
+        double wabuf[18];
+        if (!DIAG) {
+            const double2 *wap = reinterpret_cast<const double2 *>(W + (size_t)a * 18);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { double2 w2 = __ldg(wap + q); wabuf[2 * q] = w2.x; wabuf[2 * q + 1] = w2.y; }
+            wa = wabuf;
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const double w0 = wa[r * 3], w1 = wa[r * 3 + 1], w2 = wa[r * 3 + 2];
+            // compute_Yblks.cl:26-37
+            const double y0 = w0 * i00 + w1 * i10 + w2 * i20;
+            const double y1 = w0 * i10 + w1 * i11 + w2 * i21;
+            const double y2 = w0 * i20 + w1 * i21 + w2 * i22;
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc)
+                acc[r * 6 + cc] += y0 * wb[cc * 3] + y1 * wb[cc * 3 + 1] + y2 * wb[cc * 3 + 2];
+            if (DIAG) acc[36 + r] += y0 * g0 + y1 * g1 + y2 * g2;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PAIR_CTA) k_schur_pairs(const int *__restrict__ pchunk_pair, const long long *__restrict__ pchunk_beg,
+                                                         const long long *__restrict__ pchunk_end, const int *__restrict__ pair_k,
+                                                         const int *__restrict__ pair_l, const int *__restrict__ tri_oa,
+                                                         const int *__restrict__ tri_ob, const int *__restrict__ iidx,
+                                                         const double *__restrict__ W, const double *__restrict__ Vinv,
+                                                         const double *__restrict__ gb, double *__restrict__ part)
+{
+    __shared__ double sh[16 * (PAIR_CTA + 4)];
+    const int ch = blockIdx.x;
+    const int pr = pchunk_pair[ch];
+    const bool diag = pair_k[pr] == pair_l[pr];
+    double acc[42];
+#pragma unroll
+    for (int q = 0; q < 42; ++q) acc[q] = 0.0;
+    if (diag) pair_accumulate<true>(pchunk_beg[ch], pchunk_end[ch], tri_oa, tri_ob, iidx, W, Vinv, gb, acc);
+    else pair_accumulate<false>(pchunk_beg[ch], pchunk_end[ch], tri_oa, tri_ob, iidx, W, Vinv, gb, acc);
+    if (diag) block_reduce_to<42, PAIR_CTA, 16>(acc, sh, part + (size_t)ch * 42);
+    else block_reduce_to<36, PAIR_CTA, 16>(acc, sh, part + (size_t)ch * 42);
+}
+
+// per pair block: fixed-order sum of its chunk partials, S_kl = [k==l](U_k + mu I) - sum, written
+// into the 48x48 tile pool; ea_k = ga_k - sum_e.  with_U=0 writes only the (negated) local sums
+// (multi-GPU: all-reduce first, then k_add_U).
+__global__ void k_S_finalize(int n_pair, const int *__restrict__ pair_k, const int *__restrict__ pair_l,
+                             const int *__restrict__ pair_chunk_ptr, const double *__restrict__ part,
+                             const double *__restrict__ U, const double *__restrict__ ga, double mu, int with_U,
+                             const int *__restrict__ tile_index, int nt, double *__restrict__ Stiles, double *__restrict__ ea)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int pr = t / 42, v = t - pr * 42;
+    if (pr >= n_pair) return;
+    const int k = pair_k[pr], l = pair_l[pr];
+    if (v >= 36 && k != l) return;
+    double s = 0.0;
+    for (int ch = pair_chunk_ptr[pr]; ch < pair_chunk_ptr[pr + 1]; ++ch) s += part[(size_t)ch * 42 + v];
+    if (v < 36) {
+        const int r = v / 6, cc = v - r * 6;
+        double val = -s;
+        if (k == l && with_U) { val = U[k * 36 + r * 6 + cc] - s; if (r == cc) val = (U[k * 36 + r * 6 + cc] + mu) - s; }
+        const int I = k / 8, J = l / 8;
+        const int slot = tile_index[I * nt + J];
+        Stiles[(size_t)slot * TS * TS + ((k % 8) * 6 + r) * TS + (l % 8) * 6 + cc] = val;
+    } else {
+        const int r = v - 36;
+        ea[k * 6 + r] = with_U ? ga[k * 6 + r] - s : -s;
+    }
+}
+
+// multi-GPU second half: add U_k + mu I to the diagonal blocks and ga to ea (after the all-reduce)
+__global__ void k_add_U(int m, const double *__restrict__ U, const double *__restrict__ ga, double mu,
+                        const int *__restrict__ tile_index, int nt, double *__restrict__ Stiles, double *__restrict__ ea)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int k = t / 42, v = t - k * 42;
+    if (k >= m) return;
+    if (v < 36) {
+        const int r = v / 6, cc = v - r * 6;
+        const int slot = tile_index[(k / 8) * nt + (k / 8)];
+        double *p = Stiles + (size_t)slot * TS * TS + ((k % 8) * 6 + r) * TS + (k % 8) * 6 + cc;
+        double u = U[k * 36 + v];
+        if (r == cc) u += mu;
+        *p = u + *p;
+    } else ea[k * 6 + (v - 36)] += ga[k * 6 + (v - 36)];
+}
+
+// identity on the padded tail of the last diagonal tile so that the factorisation is well defined
+__global__ void k_pad_diag(int N, int nt, const int *__restrict__ tile_index, double *__restrict__ Stiles)
+{
+    int r = N + threadIdx.x;
+    if (r >= nt * TS) return;
+    int I = r / TS;
+    Stiles[(size_t)tile_index[I * nt + I] * TS * TS + (r % TS) * TS + (r % TS)] = 1.0;
+}
+
+void psba_launch_schur(psba_ctx *c, double mu)
+{
+    psba_launch_vinv(c, mu);
+    CUDA_CHECK(cudaMemsetAsync(c->Stiles, 0, (size_t)c->n_tiles * TS * TS * sizeof(double), c->stream));
+    if (c->n_pchunk > 0)
+        k_schur_pairs<<<c->n_pchunk, PAIR_CTA, 0, c->stream>>>(c->pchunk_pair, c->pchunk_beg, c->pchunk_end, c->pair_k, c->pair_l,
+                                                              c->tri_oa, c->tri_ob, c->iidx, c->W, c->Vinv, c->g + c->N, c->pair_part);
+    const int single = c->nranks == 1;
+    k_S_finalize<<<cdiv((long long)c->n_pair * 42, 128), 128, 0, c->stream>>>(c->n_pair, c->pair_k, c->pair_l, c->pair_chunk_ptr,
+                                                                             c->pair_part, c->U, c->g, mu, single, c->tile_index,
+                                                                             c->nt, c->Stiles, c->eab);
+    c->st_launches += 3;
+    if (!single) {
+        // the tile pool and ea are contiguous-by-construction only separately: two all-reduces
+        psba_allreduce_sum(c, c->Stiles, (size_t)c->n_tiles * TS * TS);
+        psba_allreduce_sum(c, c->eab, (size_t)c->N);
+        k_add_U<<<cdiv(c->m * 42, 128), 128, 0, c->stream>>>(c->m, c->U, c->g, mu, c->tile_index, c->nt, c->Stiles, c->eab);
+        c->st_launches += 1;
+    }
+    if (c->nt * TS > c->N) { k_pad_diag<<<1, TS, 0, c->stream>>>(c->N, c->nt, c->tile_index, c->Stiles); c->st_launches += 1; }
+    c->S_valid = true; c->factor_valid = false;
+}
+
+// compat only: Y_ij = W_ij * Vinv_i materialised in the reference's layout (compute_Yblks.cl:6-39)
+__global__ void k_Y_materialize(int o, const int *__restrict__ iidx, const double *__restrict__ W,
+                                const double *__restrict__ Vinv, double *__restrict__ Y)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= o) return;
+    const double *vi = Vinv + (size_t)iidx[k] * 6;
+    const double i00 = vi[0], i10 = vi[1], i20 = vi[2], i11 = vi[3], i21 = vi[4], i22 = vi[5];
+    for (int r = 0; r < 6; ++r) {
+        const double *w = W + (size_t)k * 18 + r * 3;
+        double *y = Y + (size_t)k * 18 + r * 3;
+        y[0] = w[0] * i00 + w[1] * i10 + w[2] * i20;
+        y[1] = w[0] * i10 + w[1] * i11 + w[2] * i21;
+        y[2] = w[0] * i20 + w[1] * i21 + w[2] * i22;
+    }
+}
+
+void psba_launch_Y_materialize(psba_ctx *c, double *Y)
+{
+    if (c->o > 0) k_Y_materialize<<<cdiv(c->o, 128), 128, 0, c->stream>>>(c->o, c->iidx, c->W, c->Vinv, Y);
+    c->st_launches += 1;
+}

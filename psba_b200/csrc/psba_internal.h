@@ -1,0 +1,134 @@
+// psba_internal.h -- internal state of libpsba_b200 (not part of the ABI).
+//
+// Data layout in HBM (all FP64 / int32, device-resident for the whole solve):
+//   per camera  : K[5], initcams[4], cams[2 sets][6], camcache[2 sets][CAMC]  (replicated on every GPU)
+//   per point   : pts[2 sets][3], V[6] (packed symmetric), Vinv[6], gb = g[N+3i..], dpb = dp[N+3i..]
+//   per obs     : impts[2], iidx, jidx, W[18]  -- point-major, cameras ascending (misc.cpp:189-217)
+//   camera sys  : S as a pool of 48x48 lower tiles (only tiles of the symbolic Cholesky factor),
+//                 ea / dpa in eab[0..N) / dp[0..N)
+// The two parameter sets (current / candidate) are swapped by pointer, never copied.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+#include "../../include/psba_b200.h"
+
+#define PSBA_CNP 6
+#define PSBA_PNP 3
+#define PSBA_MNP 2
+#define CAMC 48            // doubles per camera-cache entry (44 used, padded to 384 B)
+#define TS 48              // tile size of the camera system (8 cameras)
+#define PT_CTA 256         // observations per point-major CTA wave
+#define CAM_CTA 128        // threads per camera-major CTA
+#define CAM_OPT 4          // observations per thread in the camera-major pass
+#define PAIR_CTA 128       // threads per pair-pass CTA
+#define PAIR_TPT 2         // triples per thread in the pair pass
+#define NSCAL 16           // size of the device scalar block
+
+#define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+    fprintf(stderr, "psba_b200: CUDA error %d (%s) at %s(%d)\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    exit(EXIT_FAILURE); } } while (0)
+
+struct psba_comm;   // NCCL communicator wrapper (comm.cu)
+
+struct psba_ctx {
+    // global sizes
+    int m, n_glob, o_glob, N, T_glob;
+    // local (this rank's) point / observation range; equal to global on one GPU
+    int n, o, p_off, o_off;
+    int rank, nranks;
+    cudaStream_t stream;
+
+    // ---- parameters
+    double *K, *initcams, *impts;
+    double *cams[2], *pts[2], *camcache[2];
+    int cur;                        // index of the "current" parameter set
+    bool cache_valid[2];
+    // ---- structure
+    int *iidx, *jidx;               // local obs -> LOCAL point id, camera id
+    int *pt_ptr;                    // n+1
+    int *ptchunk; int n_ptchunk;    // point-major CTA chunks (point boundaries)
+    int *cam_obs;                   // o: local obs ids in camera-major order (ascending point)
+    int *cchunk_cam, *cchunk_beg, *cchunk_end; int n_cchunk;   // camera-major chunks
+    int *cam_cchunk_ptr;            // m+1: chunk range of each camera
+    // pair structure (lower triangle k>=l), triples sorted by (k,l), ascending point
+    long long ntri;
+    int *tri_oa, *tri_ob;
+    int n_pair; int *pair_k, *pair_l;          // pair blocks present GLOBALLY (all ranks agree)
+    int *pair_chunk_ptr;                        // n_pair+1
+    int n_pchunk; int *pchunk_pair; long long *pchunk_beg, *pchunk_end;
+    // ---- linearisation products
+    double *W, *V, *Vinv, *U, *g, *UVdiag_scr;
+    double coeff_uvw, coeff_g;
+    bool lin_valid;
+    double *cam_part;               // n_cchunk * 27
+    double *pair_part;              // n_pchunk * 42
+    // ---- camera system
+    int nt;                         // tiles per dimension
+    int n_tiles; int *tile_index;   // nt*nt -> slot or -1 (device + host copy)
+    std::vector<int> h_tile_index;
+    double *Stiles;                 // n_tiles * TS*TS  (factor overwrites it)
+    double *Linv;                   // nt * TS*TS   inverse of the diagonal factor tiles
+    double *eab, *dp;               // T_loc-sized vectors laid out [N | 3n]
+    int *d_status;                  // device int: 0 ok, 1 not PD
+    // per-panel task lists (host + device)
+    std::vector<int> panel_row_ptr, panel_rows;      // rows I>K with tile (I,K)
+    std::vector<int> panel_upd_ptr;                  // update tasks per panel
+    int *d_panel_rows; int *d_upd_I, *d_upd_J;
+    int *d_rowtile_ptr, *d_rowtile_col, *d_rowtile_slot;   // CSR of L tiles by row (for the solves)
+    int *d_coltile_ptr, *d_coltile_row, *d_coltile_slot;   // CSC (for the backward solve)
+    cudaGraphExec_t chol_graph; bool chol_graph_ok;
+    bool S_valid, factor_valid;
+    double *Sdense, *Sdense_aux;    // N*N, only allocated on demand (compat / cholmod)
+    double *chol_aux, *chol_diag, *chol_E;
+    // ---- scalars
+    double *d_part;                 // per-chunk partial sums (n_ptchunk * 4)
+    double *d_scal; double *h_scal; // NSCAL doubles (h_scal pinned)
+    // ---- TR vectors (local layout [N | 3n])
+    double *P_U, *P_B, *P;
+    // ---- compat state
+    double mu_pending;              // update_UV / restore_UVdiag
+    double *tmpA, *tmpB;            // on-demand o*12 / o*18 scratch for materialised J / Y
+    // ---- driver state (globals of PSBA/main.cpp:22-37)
+    int itno, max_iter, verbose, lm_only;
+    double initErr;
+    std::vector<psba_trace_rec> trace;
+    std::vector<double> force_lambda; int n_cholmod_events;
+    // stats
+    double st_tries, st_exqt, st_lin, st_launches;
+    psba_comm *comm;
+};
+
+// ---- kernels_obs.cu
+void psba_launch_cam_prep(psba_ctx *c, int set);
+double psba_launch_cost(psba_ctx *c, int set, double *ex_dev /*may be null*/);
+void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g);
+void psba_launch_jac_materialize(psba_ctx *c, double *JA, double *JB);
+void psba_launch_Jdot(psba_ctx *c, const double *x, const double *y, double *Jx_out /*may be null*/, double res[3]);
+// ---- kernels_schur.cu
+double psba_launch_vinv(psba_ctx *c, double mu);
+void psba_launch_schur(psba_ctx *c, double mu);
+void psba_launch_Y_materialize(psba_ctx *c, double *Y);
+// ---- kernels_solve.cu
+void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int,int>> &camera_pairs);
+double psba_launch_factor(psba_ctx *c);      // returns 0.0 / 1.0 (syncs)
+void psba_launch_solve(psba_ctx *c);         // dp[0..N) = S^-1 eab[0..N)
+void psba_tiles_to_dense(psba_ctx *c, double *dense_dev, bool mirror);
+void psba_launch_explicit_inverse(psba_ctx *c, double *out_dev);
+double psba_launch_cholmod(psba_ctx *c, double *delta, double *beta, int *nscalar);
+// ---- kernels_backsub.cu
+void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result *res);
+void psba_launch_newp(psba_ctx *c);
+// ---- vector helpers (kernels_backsub.cu)
+void psba_launch_dots(psba_ctx *c, const double *x, const double *y, const double *z, double out[6]);
+void psba_launch_axpby(psba_ctx *c, double a, const double *x, double b, const double *y, double *out);
+double psba_launch_maxdiag(psba_ctx *c);
+// ---- comm.cu
+void psba_allreduce_sum(psba_ctx *c, double *buf, size_t count);
+void psba_allreduce_max(psba_ctx *c, double *buf, size_t count);
+bool psba_comm_active();
+int psba_comm_rank();
+int psba_comm_size();
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
