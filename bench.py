@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- LM iterations/sec and reprojections/sec of the PSBA hot path on B200 (device-timed).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+A "step" is one Levenberg-Marquardt iteration of the reference's driver (PSBA/levmar.cpp:100-248):
+fused linearisation + >= 1 damped solve (Schur build, camera solve, back-substitution, candidate
+reprojection).  Default workload (BASELINE.json configs[4], the largest that fits one GPU): the seeded
+synthetic ring problem 2000 cameras / 1M points / 5M observations, window 64 (psba_b200/synth.py);
+inputs (~1.3 GB on the device) exceed the 126 MB L2, so no L2 flush is needed between steps.
+N > 1 (torchrun): the SAME problem sharded by points across ranks (strong scaling), one NCCL
+all-reduce of the camera system per damped solve.
+
+--impl reference: the reference's own CPU implementation (oracle/_ref = its kernel bodies compiled in
+place, else the C restatement) on a bounded sample of the same workload, all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reprojections/sec during LM iterations (device-timed); LM iterations/sec in lm_iters_per_sec"
+UNIT = "reprojections/s"
+
+WORKLOADS = {
+    # name: (m, n, d, w)
+    "ring-2000-1M-5M-w64": (2000, 1_000_000, 5, 64),
+    "ring-500-250k-1.25M-w64": (500, 250_000, 5, 64),
+    "ring-64-20k-100k": (64, 20_000, 5, 64),          # bounded CPU sample of the same generator
+    "ring-16-2k-10k": (16, 2_000, 5, 16),             # smoke-sized
+}
+CPU_SAMPLE = "ring-64-20k-100k"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def window(self, t0, t1):
+        """keep only the samples taken inside [t0, t1] (the timed region), padded by one sample period"""
+        self.t0, self.t1 = t0 - 0.1, t1 + 0.1
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if getattr(self, "t0", 0) <= t <= getattr(self, "t1", 1e300)] or [r for (t, r) in self.rows[-3:]]
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def kernel_bytes(G, prob_sizes):
+    """Algorithmic bytes per launch of the memory-bound kernels (DESIGN.md 'Kernels and rooflines'):
+    every distinct global array a kernel must read or write, counted once."""
+    o, n, m = prob_sizes
+    st = lambda k: G.stat(k)
+    ntri, npch, ncch = st("ntriples"), st("n_pchunk"), st("n_cchunk")
+    return {
+        "k_lin_points": 168 * o + 96 * n + 352 * m,           # R impts16 jidx4 iidx4 P24n C352m | W W144 V48n gb24n
+        "k_lin_cams": 24 * o + 24 * n + 352 * m + 216 * ncch,  # R cam_obs4 iidx4 impts16 P C | W partials
+        "k_schur_pairs": 148 * o + 72 * n + 8 * ntri + 336 * npch,   # R W144 iidx4 Vinv48n gb24n triples8 | W partials
+        "k_backsub": 168 * o + 168 * n + 136 * m + 48 * m,    # R W144 jidx4 iidx4 impts16 Vinv gb pts dpa C' | W eb dpb newpts
+        "k_cost": 24 * o + 24 * n + 136 * m,
+        "k_Jdot": 8 * o + 24 * n + 352 * m + 16 * (6 * m + 3 * n),
+    }
+
+
+def make_problem(name):
+    from psba_b200 import synth
+    m, n, d, w = WORKLOADS[name]
+    return synth.ring_problem(m=m, n=n, d=d, w=w, seed=20262000)
+
+
+def run_cpu(kind_pref, threads, sample, lm_passes):
+    """Oracle on the bounded sample; returns (reproj/s, lm it/s, seconds, kind, description)."""
+    import oracle
+    kind = "reference" if (kind_pref == "reference" and oracle.have_ref()) else "restatement"
+    prob = make_problem(sample)
+    P = oracle.Problem(prob, kind=kind)
+    P.set("nthreads", threads)
+    cams0, pts0 = prob["cams"].copy(), prob["pts"].copy()
+    t_tot, tries, its = 0.0, 0, 0
+    for _ in range(lm_passes):
+        P.buf("cams")[:] = cams0
+        P.buf("pts")[:] = pts0
+        P.set("itno", 0)
+        n0 = P.get("n_tries")
+        t0 = time.perf_counter()
+        P.levmar()                                        # 5 accepted LM iterations, then it would hand over to TR
+        t_tot += time.perf_counter() - t0
+        tries += int(P.get("n_tries") - n0)
+        its += int(P.get("itno"))
+    P.close()
+    desc = "%s: %d LM passes x %d iterations on %s (o=%d), %d threads" % (
+        "reference kernel bodies (oracle/_ref)" if kind == "reference" else "oracle C restatement",
+        lm_passes, its // max(lm_passes, 1), sample, prob["o"], threads)
+    return tries * prob["o"] / t_tot, its / t_tot, t_tot, ("reference" if kind == "reference" else "port"), desc, prob["o"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ring-2000-1M-5M-w64", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    K, W = args.steps, max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    m, n, d, w = WORKLOADS[args.workload]
+    o = n * d
+    cores = len(os.sched_getaffinity(0))
+    config = {"workload": args.workload, "cams": m, "points": n, "observations": o, "window": w,
+              "sharding": "points x%d" % world if world > 1 else "none", "l2": "inputs (>1 GB) exceed L2; no flush"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        passes = max(1, min(K, 3))
+        run_cpu("reference", cores, CPU_SAMPLE, 1)        # warm-up (page-in, thread pool)
+        v, its, secs, kind, desc, o_s = run_cpu("reference", cores, CPU_SAMPLE, passes)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+                "ms_per_step": 1e3 / its * (o / o_s), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config, "lm_iters_per_sec": its * (o_s / o),
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "ms_per_step / lm_iters_per_sec are scaled from the sample to the full workload by the observation ratio"}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import psba_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    L = psba_b200.lib()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl")
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            import ctypes
+            buf = ctypes.create_string_buffer(128)
+            L.psba_comm_unique_id(buf)
+            idt.copy_(torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        L.psba_comm_init(rank, world, bytes(idt.cpu().numpy().tobytes()))
+    prob = make_problem(args.workload)
+    t0 = time.perf_counter()
+    G = psba_b200.PSBA(prob)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    cams0, pts0 = prob["cams"], prob["pts"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def lm_run(steps):
+        """restart from the initial estimate and run `steps` LM iterations; returns device ms, tries"""
+        G.set_params(cams0, pts0)
+        G.set_option("itno", 0); G.set_option("max_iter", steps); G.set_option("lm_only", 1)
+        G.set_option("stats_reset", 0)
+        barrier()
+        G.set_option("timer_start", 0)
+        flag, fe = G.levmar()
+        ms = G.stat("timer_ms")
+        barrier()
+        return ms, int(G.stat("tries")), int(G.stat("itno")), fe, int(G.stat("launches"))
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                                   # runs through warm-up; only timed-region samples are kept
+    lm_run(W)                                             # warm-up (graph instantiation, clocks)
+    tw0 = time.perf_counter()
+    ms, tries, its, final_cost, launches = lm_run(K)
+    tw1 = time.perf_counter()
+    if rank == 0:
+        sampler.window(tw0, tw1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = tries * o / (ms * 1e-3)
+
+    # ---- per-kernel device times (CUDA events on the engine's stream), same K steps, profiled pass
+    G.set_option("profile", 1); G.set_option("profile_reset", 0)
+    lm_run(K)
+    hbm_peak, peak_src = peaks()
+    kb = kernel_bytes(G, (G.o_loc, G.n_loc, m))
+    names = ["k_cam_prep", "k_cost", "k_lin_points", "k_lin_cams", "k_cam_reduce", "k_vinv", "memset_S", "k_schur_pairs",
+             "k_S_finalize", "chol_graph", "k_tri_solve", "k_newcams", "k_backsub", "k_reduce", "k_vec", "allreduce"]
+    ktab, tot_ms = {}, 0.0
+    for kn in names:
+        kms, cnt = G.stat("ms." + kn), G.stat("n." + kn)
+        if cnt > 0:
+            ktab[kn] = {"launches": int(cnt), "ms_total": round(kms, 4), "ms_avg": round(kms / cnt, 5)}
+            tot_ms += kms
+            if kn in kb:
+                gbs = kb[kn] / (kms / cnt * 1e-3) / 1e9
+                ktab[kn].update({"alg_bytes": int(kb[kn]), "GBps": round(gbs, 1), "frac_hbm": round(gbs / hbm_peak, 4)})
+    for kn in ktab:
+        ktab[kn]["share"] = round(ktab[kn]["ms_total"] / tot_ms, 4)
+    G.set_option("profile", 0)
+    mem_kernels = [k for k in ktab if "alg_bytes" in ktab[k]]
+    dom = max(mem_kernels, key=lambda k: ktab[k]["ms_total"])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload, {}).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ktab[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": ktab[dom]["frac_hbm"], "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": ktab[dom]["alg_bytes"], "ms_per_launch": ktab[dom]["ms_avg"]}
+
+    # ---- end to end through the C ABI with HOST buffers: upload + structure build + K iterations + download
+    e2e = None
+    if not args.no_e2e:
+        G.close()
+        barrier()
+        t0 = time.perf_counter()
+        G = psba_b200.PSBA(prob)                          # setup_cl + fill_initBuffer2 + fill_idxBuffer (H2D inside)
+        G.set_option("itno", 0); G.set_option("max_iter", K); G.set_option("lm_only", 1)
+        G.levmar()
+        e_tries = int(G.stat("tries"))
+        cams_out, pts_out = G.get_params()                # D2H of the refined parameters
+        barrier()
+        e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_s = float(t.item())
+        h2d = (prob["K"].nbytes + prob["initrot"].nbytes + prob["cams"].nbytes) + (G.o_loc * 16 + G.n_loc * 24) + G.o_loc * 8
+        h2d += int(G.stat("ntriples")) * 8                # pair lists built on the host and uploaded
+        d2h = cams_out.nbytes + pts_out.nbytes + e_tries * 48
+        e2e = {"value": e_tries * o / e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),
+               "seconds": round(e_s, 3), "includes": "setup_cl + fill buffers (H2D) + host structure build + K LM iterations + get_params (D2H)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        run_cpu("port", cores, CPU_SAMPLE, 1)
+        v, cits, secs, kind, desc, o_s = run_cpu("port", cores, CPU_SAMPLE, 3)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc,
+               "lm_iters_per_sec_scaled_to_workload": cits * o_s / o}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / max(its, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "lm_iters_per_sec": its / (ms * 1e-3), "tries": tries, "lm_iterations": its, "final_cost": final_cost,
+                "gpu_launches": launches, "setup_seconds": round(setup_s, 3),
+                "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "kernels": ktab}
+        print(json.dumps(line))
+    G.close()
+    if world > 1:
+        L.psba_comm_finalize()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

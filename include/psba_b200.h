@@ -149,6 +149,9 @@ void psba_force_lambda(psba_ctx *ctx, const double *lam, int n);
 /* copy current parameters to the host: cams[m*6], pts[n*3] (either may be NULL) */
 void psba_get_params(psba_ctx *ctx, int params, double *cams, double *pts);
 
+/* restart from host parameters: cams[m*6], pts[n3Dpts*3] (global arrays; either may be NULL) */
+void psba_set_params(psba_ctx *ctx, const double *cams, const double *pts);
+
 /* fused hot-path steps used by the drivers and by bench.py (device-resident, no host arrays):
  * linearise at the current parameters; one damped solve + candidate evaluation. */
 typedef struct {

@@ -94,6 +94,7 @@ def lib():
     L.psba_get_stat.argtypes = [vp, C.c_char_p]
     L.psba_force_lambda.argtypes = [vp, _dp, i]
     L.psba_get_params.argtypes = [vp, i, _dp, _dp]
+    L.psba_set_params.argtypes = [vp, _dp, _dp]
     L.psba_linearize.argtypes = [vp, d, d]
     L.psba_try_step.argtypes = [vp, d, C.POINTER(TryResult)]
     L.psba_readInitialSBAEstimate.argtypes = [C.c_char_p, C.c_char_p, i, _dp, _ip, _ip, _ip,
@@ -320,6 +321,11 @@ class PSBA:
         pts = np.zeros((self.n_loc, 3))
         self.L.psba_get_params(self.h, params, _d(cams), _d(pts))
         return cams, pts
+
+    def set_params(self, cams=None, pts=None):
+        a = None if cams is None else np.ascontiguousarray(cams, dtype=np.float64)
+        b = None if pts is None else np.ascontiguousarray(pts, dtype=np.float64)
+        self.L.psba_set_params(self.h, _d(a), _d(b))
 
     def close(self):
         if self.h:

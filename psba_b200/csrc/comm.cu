@@ -45,7 +45,7 @@ extern "C" void psba_comm_finalize(void)
 void psba_allreduce_sum(psba_ctx *c, double *buf, size_t count)
 {
     if (!g_active) return;
-    NCCL_CHECK(ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, g_comm, c->stream));
+    PROF(c, KID_ALLREDUCE) NCCL_CHECK(ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, g_comm, c->stream));
 }
 
 void psba_allreduce_max(psba_ctx *c, double *buf, size_t count)

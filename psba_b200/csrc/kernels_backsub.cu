@@ -7,6 +7,7 @@
 // (PSBA/misc.cpp:151-157, PSBA/levmar.cpp:271-280).  kern_update_p (update_p.cl:6-25) is a
 // pointer swap of the two parameter sets.
 #include "dev_math.cuh"
+#include <algorithm>
 
 // candidate cameras = cams + dpa, plus the camera part of the step scalars
 __global__ void k_newcams(int N, const double *__restrict__ cams, const double *__restrict__ dpa, const double *__restrict__ ga,
@@ -150,13 +151,13 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
     const int cur = c->cur, nw = 1 - cur;
     double *gb = c->g + c->N, *ebp = c->eab + c->N, *dpbp = c->dp + c->N;
     if (evaluate) {
-        k_newcams<<<1, 256, 0, c->stream>>>(c->N, c->cams[cur], c->dp, c->g, mu, c->cams[nw], c->d_scal + 4);
+        PROF(c, KID_NEWCAMS) k_newcams<<<1, 256, 0, c->stream>>>(c->N, c->cams[cur], c->dp, c->g, mu, c->cams[nw], c->d_scal + 4);
         psba_launch_cam_prep(c, nw);
         if (c->n_ptchunk > 0)
-            k_backsub<true><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptchunk, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
+            PROF(c, KID_BACKSUB) k_backsub<true><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptchunk, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
                                                                    gb, c->dp, c->pts[cur], c->camcache[nw], mu, ebp, dpbp,
                                                                    c->pts[nw], c->d_part);
-        k_final_reduce3<<<1, 256, 0, c->stream>>>(c->d_part, c->n_ptchunk, c->d_scal);
+        PROF(c, KID_REDUCE) k_final_reduce3<<<1, 256, 0, c->stream>>>(c->d_part, c->n_ptchunk, c->d_scal);
         c->st_launches += 3; c->st_exqt += 1;
         if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal, 3);
         CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -168,7 +169,7 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
         }
     } else {
         if (c->n_ptchunk > 0)
-            k_backsub<false><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptchunk, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
+            PROF(c, KID_BACKSUB) k_backsub<false><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptchunk, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
                                                                     gb, c->dp, c->pts[cur], c->camcache[cur], mu, ebp, dpbp,
                                                                     c->pts[nw], c->d_part);
         c->st_launches += 1;
@@ -241,7 +242,7 @@ __global__ void k_axpby(int n, double a, const double *__restrict__ x, double b,
 void psba_launch_axpby(psba_ctx *c, double a, const double *x, double b, const double *y, double *out)
 {
     const int n = c->N + 3 * c->n;
-    k_axpby<<<cdiv(n, 256), 256, 0, c->stream>>>(n, a, x, b, y, out);
+    PROF(c, KID_VEC) k_axpby<<<cdiv(n, 256), 256, 0, c->stream>>>(n, a, x, b, y, out);
     c->st_launches += 1;
 }
 

@@ -57,7 +57,7 @@ __global__ void k_cam_prep(int m, const double *__restrict__ K, const double *__
 
 void psba_launch_cam_prep(psba_ctx *c, int set)
 {
-    k_cam_prep<<<cdiv(c->m, 128), 128, 0, c->stream>>>(c->m, c->K, c->initcams, c->cams[set], c->camcache[set]);
+    PROF(c, KID_CAM_PREP) k_cam_prep<<<cdiv(c->m, 128), 128, 0, c->stream>>>(c->m, c->K, c->initcams, c->cams[set], c->camcache[set]);
     c->cache_valid[set] = true;
     c->st_launches += 1;
 }
@@ -123,8 +123,8 @@ double psba_launch_cost(psba_ctx *c, int set, double *ex_dev)
     if (!c->cache_valid[set]) psba_launch_cam_prep(c, set);
     int nb = cdiv(c->o, 256);
     if (nb > 0)
-        k_cost<<<nb, 256, 0, c->stream>>>(c->o, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set], ex_dev, c->d_part);
-    k_final_reduce<<<1, 256, 0, c->stream>>>(c->d_part, nb, 1, 1, c->d_scal);
+        PROF(c, KID_COST) k_cost<<<nb, 256, 0, c->stream>>>(c->o, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set], ex_dev, c->d_part);
+    PROF(c, KID_REDUCE) k_final_reduce<<<1, 256, 0, c->stream>>>(c->d_part, nb, 1, 1, c->d_scal);
     c->st_launches += 2; c->st_exqt += 1;
     if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal, 1);
     read_scalars(c, 0, 1);
@@ -260,13 +260,13 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
     const int set = c->cur;
     if (!c->cache_valid[set]) psba_launch_cam_prep(c, set);
     if (c->n_ptchunk > 0)
-        k_lin_points<<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptchunk, c->pt_ptr, c->iidx, c->jidx, c->impts,
+        PROF(c, KID_LIN_POINTS) k_lin_points<<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptchunk, c->pt_ptr, c->iidx, c->jidx, c->impts,
                                                             c->camcache[set], c->pts[set], coeff_uvw, coeff_g,
                                                             c->W, c->V, c->g + c->N);
     if (c->n_cchunk > 0)
-        k_lin_cams<<<c->n_cchunk, CAM_CTA, 0, c->stream>>>(c->cchunk_cam, c->cchunk_beg, c->cchunk_end, c->cam_obs,
+        PROF(c, KID_LIN_CAMS) k_lin_cams<<<c->n_cchunk, CAM_CTA, 0, c->stream>>>(c->cchunk_cam, c->cchunk_beg, c->cchunk_end, c->cam_obs,
                                                           c->iidx, c->impts, c->camcache[set], c->pts[set], c->cam_part);
-    k_cam_reduce<<<cdiv(c->m * 27, 128), 128, 0, c->stream>>>(c->m, c->cam_cchunk_ptr, c->cam_part, coeff_uvw, coeff_g,
+    PROF(c, KID_CAM_REDUCE) k_cam_reduce<<<cdiv(c->m * 27, 128), 128, 0, c->stream>>>(c->m, c->cam_cchunk_ptr, c->cam_part, coeff_uvw, coeff_g,
                                                              c->U, c->g);
     c->st_launches += 3; c->st_lin += 1;
     if (c->nranks > 1) {
@@ -362,9 +362,9 @@ void psba_launch_Jdot(psba_ctx *c, const double *x, const double *y, double *Jx_
     if (!c->cache_valid[set]) psba_launch_cam_prep(c, set);
     int nb = cdiv(c->o, 256);
     if (nb > 0)
-        k_Jdot<<<nb, 256, 0, c->stream>>>(c->o, c->N, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set],
+        PROF(c, KID_JDOT) k_Jdot<<<nb, 256, 0, c->stream>>>(c->o, c->N, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set],
                                          x, y, Jx_out, c->d_part);
-    k_final_reduce<<<1, 256, 0, c->stream>>>(c->d_part, nb, 3, 3, c->d_scal);
+    PROF(c, KID_REDUCE) k_final_reduce<<<1, 256, 0, c->stream>>>(c->d_part, nb, 3, 3, c->d_scal);
     c->st_launches += 2;
     if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal, 3);
     read_scalars(c, 0, 3);

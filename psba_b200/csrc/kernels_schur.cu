@@ -53,7 +53,7 @@ __global__ void k_vinv(int n, const double *__restrict__ V, double mu, double *_
 double psba_launch_vinv(psba_ctx *c, double mu)
 {
     CUDA_CHECK(cudaMemsetAsync(c->d_status + 1, 0, sizeof(int), c->stream));
-    if (c->n > 0) k_vinv<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->V, mu, c->Vinv, c->d_status + 1);
+    if (c->n > 0) PROF(c, KID_VINV) k_vinv<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->V, mu, c->Vinv, c->d_status + 1);
     c->st_launches += 1;
     return 0.0;
 }
@@ -180,12 +180,12 @@ __global__ void k_pad_diag(int N, int nt, const int *__restrict__ tile_index, do
 void psba_launch_schur(psba_ctx *c, double mu)
 {
     psba_launch_vinv(c, mu);
-    CUDA_CHECK(cudaMemsetAsync(c->Stiles, 0, (size_t)c->n_tiles * TS * TS * sizeof(double), c->stream));
+    PROF(c, KID_MEMSET_S) CUDA_CHECK(cudaMemsetAsync(c->Stiles, 0, (size_t)c->n_tiles * TS * TS * sizeof(double), c->stream));
     if (c->n_pchunk > 0)
-        k_schur_pairs<<<c->n_pchunk, PAIR_CTA, 0, c->stream>>>(c->pchunk_pair, c->pchunk_beg, c->pchunk_end, c->pair_k, c->pair_l,
+        PROF(c, KID_SCHUR_PAIRS) k_schur_pairs<<<c->n_pchunk, PAIR_CTA, 0, c->stream>>>(c->pchunk_pair, c->pchunk_beg, c->pchunk_end, c->pair_k, c->pair_l,
                                                               c->tri_oa, c->tri_ob, c->iidx, c->W, c->Vinv, c->g + c->N, c->pair_part);
     const int single = c->nranks == 1;
-    k_S_finalize<<<cdiv((long long)c->n_pair * 42, 128), 128, 0, c->stream>>>(c->n_pair, c->pair_k, c->pair_l, c->pair_chunk_ptr,
+    PROF(c, KID_S_FINALIZE) k_S_finalize<<<cdiv((long long)c->n_pair * 42, 128), 128, 0, c->stream>>>(c->n_pair, c->pair_k, c->pair_l, c->pair_chunk_ptr,
                                                                              c->pair_part, c->U, c->g, mu, single, c->tile_index,
                                                                              c->nt, c->Stiles, c->eab);
     c->st_launches += 3;

@@ -221,7 +221,7 @@ double psba_launch_factor(psba_ctx *c)
         CUDA_CHECK(cudaGraphDestroy(graph));
         c->chol_graph_ok = true;
     }
-    CUDA_CHECK(cudaGraphLaunch(c->chol_graph, c->stream));
+    PROF(c, KID_FACTOR) CUDA_CHECK(cudaGraphLaunch(c->chol_graph, c->stream));
     c->st_launches += 3 * c->nt;
     int st = 0;
     CUDA_CHECK(cudaMemcpyAsync(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(512) k_tri_solve(int N, int nt, const int *__r
 
 void psba_launch_solve(psba_ctx *c)
 {
-    k_tri_solve<<<1, 512, 0, c->stream>>>(c->N, c->nt, c->tile_index, c->d_rowtile_ptr, c->d_rowtile_col, c->d_rowtile_slot,
+    PROF(c, KID_TRI_SOLVE) k_tri_solve<<<1, 512, 0, c->stream>>>(c->N, c->nt, c->tile_index, c->d_rowtile_ptr, c->d_rowtile_col, c->d_rowtile_slot,
                                          c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot, c->Stiles, c->Linv,
                                          c->eab, c->chol_aux, c->dp);
     c->st_launches += 1;
@@ -555,7 +555,7 @@ double psba_launch_cholmod(psba_ctx *c, double *delta_out, double *beta_out, int
     double beta = fmax(gamma, 1e-15);
     beta = fmax(beta, xi / sqrt((double)N * N - 1));
     beta = sqrt(beta);
-    k_cholmod<<<1, 1024, 0, c->stream>>>(N, c->Sdense, c->chol_aux, c->chol_diag, c->chol_E, beta, delta, c->d_status + 2);
+    PROF(c, KID_CHOLMOD) k_cholmod<<<1, 1024, 0, c->stream>>>(N, c->Sdense, c->chol_aux, c->chol_diag, c->chol_E, beta, delta, c->d_status + 2);
     k_cholmod_E<<<cdiv(N, 128), 128, 0, c->stream>>>(N, c->Sdense, c->chol_E);
     c->st_launches += 3;
     std::vector<double> E(N);

@@ -67,6 +67,8 @@ extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3D
     c->itno = 0; c->max_iter = 50; c->verbose = 0; c->lm_only = 0; c->initErr = 0.0;
     c->n_cholmod_events = 0;
     c->st_tries = c->st_exqt = c->st_lin = c->st_launches = 0;
+    c->profile = false; c->timer_init = false;
+    for (int k = 0; k < KID_COUNT; ++k) { c->prof_ms[k] = 0; c->prof_n[k] = 0; }
     c->comm = nullptr;
     c->K = dalloc<double>((size_t)nCams * 5);
     c->initcams = dalloc<double>((size_t)nCams * 4);
@@ -508,6 +510,16 @@ extern "C" void psba_get_params(psba_ctx *c, int params, double *cams, double *p
     if (pts) d2h(c, pts, c->pts[set], 3 * (size_t)c->n);
 }
 
+extern "C" void psba_set_params(psba_ctx *c, const double *cams, const double *pts_global)
+{
+    // restart from given parameters: cams[m*6] (all cameras), pts_global[n3Dpts*3] (this rank takes its slice)
+    if (cams) CUDA_CHECK(cudaMemcpyAsync(c->cams[c->cur], cams, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->stream));
+    if (pts_global && c->n) CUDA_CHECK(cudaMemcpyAsync(c->pts[c->cur], pts_global + (size_t)c->p_off * 3, (size_t)c->n * 24, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->cache_valid[0] = c->cache_valid[1] = false;
+    c->lin_valid = false; c->S_valid = false; c->factor_valid = false; c->mu_pending = 0.0;
+}
+
 extern "C" void psba_set_option(psba_ctx *c, const char *name, double v)
 {
     std::string s(name);
@@ -515,6 +527,14 @@ extern "C" void psba_set_option(psba_ctx *c, const char *name, double v)
     else if (s == "max_iter") c->max_iter = (int)v;
     else if (s == "itno") c->itno = (int)v;
     else if (s == "lm_only") c->lm_only = (int)v;
+    else if (s == "profile") { psba_prof_collect(c); c->profile = v != 0; }
+    else if (s == "profile_reset") { psba_prof_collect(c); for (int k = 0; k < KID_COUNT; ++k) { c->prof_ms[k] = 0; c->prof_n[k] = 0; } }
+    else if (s == "stats_reset") { c->st_tries = c->st_exqt = c->st_lin = c->st_launches = 0; }
+    else if (s == "timer_start") {
+        if (!c->timer_init) { CUDA_CHECK(cudaEventCreate(&c->timer_e0)); CUDA_CHECK(cudaEventCreate(&c->timer_e1)); c->timer_init = true; }
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        CUDA_CHECK(cudaEventRecord(c->timer_e0, c->stream));
+    }
     else die("set_option: unknown option");
 }
 
@@ -539,8 +559,36 @@ extern "C" double psba_get_stat(psba_ctx *c, const char *name)
     if (s == "n_cchunk") return c->n_cchunk;
     if (s == "n_pchunk") return c->n_pchunk;
     if (s == "cholmod_events") return c->n_cholmod_events;
+    if (s == "timer_ms") {   // device time since "timer_start" on the engine's stream
+        if (!c->timer_init) die("timer_ms before timer_start");
+        float ms = 0;
+        CUDA_CHECK(cudaEventRecord(c->timer_e1, c->stream));
+        CUDA_CHECK(cudaEventSynchronize(c->timer_e1));
+        CUDA_CHECK(cudaEventElapsedTime(&ms, c->timer_e0, c->timer_e1));
+        return ms;
+    }
+    if (s.rfind("ms.", 0) == 0 || s.rfind("n.", 0) == 0) {
+        psba_prof_collect(c);
+        const bool want_ms = s[0] == 'm';
+        const std::string kn = s.substr(want_ms ? 3 : 2);
+        for (int k = 0; k < KID_COUNT; ++k) if (kn == psba_kid_name[k]) return want_ms ? c->prof_ms[k] : c->prof_n[k];
+        die("get_stat: unknown kernel name");
+    }
     die("get_stat: unknown name");
     return 0;
+}
+
+void psba_prof_collect(psba_ctx *c)
+{
+    if (c->prof_pending.empty()) return;
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (auto &r : c->prof_pending) {
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+        c->prof_ms[r.id] += ms; c->prof_n[r.id] += 1;
+        c->prof_pool.push_back(r.e0); c->prof_pool.push_back(r.e1);
+    }
+    c->prof_pending.clear();
 }
 
 extern "C" void psba_force_lambda(psba_ctx *c, const double *lam, int n)

@@ -32,6 +32,16 @@
 
 struct psba_comm;   // NCCL communicator wrapper (comm.cu)
 
+// per-kernel device timing (CUDA events on the launching stream), enabled by option "profile"
+enum psba_kid { KID_CAM_PREP = 0, KID_COST, KID_LIN_POINTS, KID_LIN_CAMS, KID_CAM_REDUCE, KID_VINV, KID_MEMSET_S,
+                KID_SCHUR_PAIRS, KID_S_FINALIZE, KID_FACTOR, KID_TRI_SOLVE, KID_NEWCAMS, KID_BACKSUB, KID_REDUCE,
+                KID_JDOT, KID_VEC, KID_CHOLMOD, KID_ALLREDUCE, KID_COUNT };
+static const char *const psba_kid_name[KID_COUNT] = {
+    "k_cam_prep", "k_cost", "k_lin_points", "k_lin_cams", "k_cam_reduce", "k_vinv", "memset_S", "k_schur_pairs",
+    "k_S_finalize", "chol_graph", "k_tri_solve", "k_newcams", "k_backsub", "k_reduce", "k_Jdot", "k_vec", "k_cholmod",
+    "allreduce" };
+struct psba_prof_rec { int id; cudaEvent_t e0, e1; };
+
 struct psba_ctx {
     // global sizes
     int m, n_glob, o_glob, N, T_glob;
@@ -97,6 +107,11 @@ struct psba_ctx {
     std::vector<double> force_lambda; int n_cholmod_events;
     // stats
     double st_tries, st_exqt, st_lin, st_launches;
+    bool profile;
+    std::vector<psba_prof_rec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[KID_COUNT]; double prof_n[KID_COUNT];
+    cudaEvent_t timer_e0, timer_e1; bool timer_init;
     psba_comm *comm;
 };
 
@@ -130,5 +145,24 @@ void psba_allreduce_max(psba_ctx *c, double *buf, size_t count);
 bool psba_comm_active();
 int psba_comm_rank();
 int psba_comm_size();
+
+// scoped kernel timer: PROF(c, KID_x) { launch...; }
+struct psba_prof_scope {
+    psba_ctx *c; int id; cudaEvent_t e0, e1; bool on;
+    psba_prof_scope(psba_ctx *c_, int id_) : c(c_), id(id_), on(c_->profile) {
+        if (!on) return;
+        auto get = [&]() { cudaEvent_t e; if (c->prof_pool.empty()) { CUDA_CHECK(cudaEventCreate(&e)); } else { e = c->prof_pool.back(); c->prof_pool.pop_back(); } return e; };
+        e0 = get(); e1 = get();
+        CUDA_CHECK(cudaEventRecord(e0, c->stream));
+    }
+    ~psba_prof_scope() {
+        if (!on) return;
+        CUDA_CHECK(cudaEventRecord(e1, c->stream));
+        c->prof_pending.push_back({id, e0, e1});
+    }
+    explicit operator bool() const { return true; }
+};
+#define PROF(c, id) if (psba_prof_scope prof_scope_##id{c, id})
+void psba_prof_collect(psba_ctx *c);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
