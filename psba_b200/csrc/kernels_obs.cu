@@ -137,7 +137,7 @@ double psba_launch_cost(psba_ctx *c, int set, double *ex_dev)
 // (144 B per observation, the only per-observation product that persists); B^T B (6) and B^T e (3)
 // go through shared memory to the point's owner thread, which sums them in ascending camera
 // order (the order of compute_V.cl:24-31 / compute_g.cl:43-54).
-__global__ void __launch_bounds__(PT_CTA) k_lin_points(const int *__restrict__ ptchunk, const int *__restrict__ pt_ptr,
+__global__ void __launch_bounds__(PT_CTA, 2) k_lin_points(const int *__restrict__ ptchunk, const int *__restrict__ pt_ptr,
                                                       const int *__restrict__ iidx, const int *__restrict__ jidx,
                                                       const double *__restrict__ impts, const double *__restrict__ cache,
                                                       const double *__restrict__ pts, double coeff, double coeff_g,

@@ -58,19 +58,22 @@ double psba_launch_vinv(psba_ctx *c, double mu)
     return 0.0;
 }
 
-// one CTA per chunk of triples of ONE camera pair (k >= l).  Thread: Y = W_a * Vinv_i row by row,
-// acc[r][c] += Y_r . W_b[c];  diagonal pairs also accumulate Y * gb_i (the ea sum).
-template <bool DIAG>
-__device__ __forceinline__ void pair_accumulate(long long beg, long long end, const int *__restrict__ tri_oa,
+// Pair pass.  A group of G lanes (G = 1..32, chosen on the host from the mean run length) owns one chunk
+// of triples of ONE camera pair (k >= l); lanes stride the chunk.  Per triple: Y = W_a * Vinv_i row by
+// row (compute_Yblks.cl:26-37), acc[r][c] += Y_r . W_b[c] (compute_S.cl:44-52); diagonal pairs also
+// accumulate Y * gb_i (compute_ea.cl:27-33).  The group's 36 (+6) sums are combined by an xor butterfly
+// (bit-identical in every lane, fixed order) and written as the chunk's partial.
+template <bool DIAG, int G>
+__device__ __forceinline__ void pair_accumulate(long long beg, long long end, int lane, const int *__restrict__ tri_oa,
                                                 const int *__restrict__ tri_ob, const int *__restrict__ iidx,
                                                 const double *__restrict__ W, const double *__restrict__ Vinv,
                                                 const double *__restrict__ gb, double *acc)
 {
 #pragma unroll 1
-    for (long long t = beg + threadIdx.x; t < end; t += PAIR_CTA) {
-        const int a = tri_oa[t];
-        const int b = DIAG ? a : tri_ob[t];
-        const int i = iidx[a];
+    for (long long t = beg + lane; t < end; t += G) {
+        const int a = __ldg(tri_oa + t);
+        const int b = DIAG ? a : __ldg(tri_ob + t);
+        const int i = __ldg(iidx + a);
         const double2 *vp = reinterpret_cast<const double2 *>(Vinv + (size_t)i * 6);
         const double2 v01 = __ldg(vp), v23 = __ldg(vp + 1), v45 = __ldg(vp + 2);
         const double i00 = v01.x, i10 = v01.y, i20 = v23.x, i11 = v23.y, i21 = v45.x, i22 = v45.y;
@@ -80,47 +83,75 @@ __device__ __forceinline__ void pair_accumulate(long long beg, long long end, co
         for (int q = 0; q < 9; ++q) { double2 w2 = __ldg(wbp + q); wb[2 * q] = w2.x; wb[2 * q + 1] = w2.y; }
         double g0 = 0, g1 = 0, g2 = 0;
         if (DIAG) { const double *gp = gb + (size_t)i * 3; g0 = __ldg(gp); g1 = __ldg(gp + 1); g2 = __ldg(gp + 2); }
-        const double *wa = DIAG ? wb : nullptr;
-        double wabuf[18];
-        if (!DIAG) {
-            const double2 *wap = reinterpret_cast<const double2 *>(W + (size_t)a * 18);
+        const double2 *wap = reinterpret_cast<const double2 *>(W + (size_t)a * 18);
 #pragma unroll
-            for (int q = 0; q < 9; ++q) { double2 w2 = __ldg(wap + q); wabuf[2 * q] = w2.x; wabuf[2 * q + 1] = w2.y; }
-            wa = wabuf;
-        }
+        for (int rp = 0; rp < 3; ++rp) {              // two rows of W_a (6 doubles = 3 double2) at a time
+            double wa[6];
+            if (DIAG) {
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            const double w0 = wa[r * 3], w1 = wa[r * 3 + 1], w2 = wa[r * 3 + 2];
-            // compute_Yblks.cl:26-37
-            const double y0 = w0 * i00 + w1 * i10 + w2 * i20;
-            const double y1 = w0 * i10 + w1 * i11 + w2 * i21;
-            const double y2 = w0 * i20 + w1 * i21 + w2 * i22;
+                for (int q = 0; q < 6; ++q) wa[q] = wb[rp * 6 + q];
+            } else {
 #pragma unroll
-            for (int cc = 0; cc < 6; ++cc)
-                acc[r * 6 + cc] += y0 * wb[cc * 3] + y1 * wb[cc * 3 + 1] + y2 * wb[cc * 3 + 2];
-            if (DIAG) acc[36 + r] += y0 * g0 + y1 * g1 + y2 * g2;
+                for (int q = 0; q < 3; ++q) { double2 w2 = __ldg(wap + rp * 3 + q); wa[2 * q] = w2.x; wa[2 * q + 1] = w2.y; }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = rp * 2 + h;
+                const double w0 = wa[h * 3], w1 = wa[h * 3 + 1], w2 = wa[h * 3 + 2];
+                const double y0 = w0 * i00 + w1 * i10 + w2 * i20;
+                const double y1 = w0 * i10 + w1 * i11 + w2 * i21;
+                const double y2 = w0 * i20 + w1 * i21 + w2 * i22;
+#pragma unroll
+                for (int cc = 0; cc < 6; ++cc)
+                    acc[r * 6 + cc] += y0 * wb[cc * 3] + y1 * wb[cc * 3 + 1] + y2 * wb[cc * 3 + 2];
+                if (DIAG) acc[36 + r] += y0 * g0 + y1 * g1 + y2 * g2;
+            }
         }
     }
 }
 
-__global__ void __launch_bounds__(PAIR_CTA) k_schur_pairs(const int *__restrict__ pchunk_pair, const long long *__restrict__ pchunk_beg,
-                                                         const long long *__restrict__ pchunk_end, const int *__restrict__ pair_k,
-                                                         const int *__restrict__ pair_l, const int *__restrict__ tri_oa,
-                                                         const int *__restrict__ tri_ob, const int *__restrict__ iidx,
-                                                         const double *__restrict__ W, const double *__restrict__ Vinv,
-                                                         const double *__restrict__ gb, double *__restrict__ part)
+template <int G>
+__global__ void __launch_bounds__(PAIR_CTA) k_schur_pairs(int n_pchunk, const int *__restrict__ pchunk_pair,
+                                                         const long long *__restrict__ pchunk_beg, const long long *__restrict__ pchunk_end,
+                                                         const int *__restrict__ pair_k, const int *__restrict__ pair_l,
+                                                         const int *__restrict__ tri_oa, const int *__restrict__ tri_ob,
+                                                         const int *__restrict__ iidx, const double *__restrict__ W,
+                                                         const double *__restrict__ Vinv, const double *__restrict__ gb,
+                                                         double *__restrict__ part)
 {
-    __shared__ double sh[16 * (PAIR_CTA + 4)];
-    const int ch = blockIdx.x;
-    const int pr = pchunk_pair[ch];
-    const bool diag = pair_k[pr] == pair_l[pr];
+    const int lane = threadIdx.x % G;
+    const int ch = blockIdx.x * (PAIR_CTA / G) + threadIdx.x / G;
     double acc[42];
 #pragma unroll
     for (int q = 0; q < 42; ++q) acc[q] = 0.0;
-    if (diag) pair_accumulate<true>(pchunk_beg[ch], pchunk_end[ch], tri_oa, tri_ob, iidx, W, Vinv, gb, acc);
-    else pair_accumulate<false>(pchunk_beg[ch], pchunk_end[ch], tri_oa, tri_ob, iidx, W, Vinv, gb, acc);
-    if (diag) block_reduce_to<42, PAIR_CTA, 16>(acc, sh, part + (size_t)ch * 42);
-    else block_reduce_to<36, PAIR_CTA, 16>(acc, sh, part + (size_t)ch * 42);
+    bool diag = false;
+    if (ch < n_pchunk) {
+        const int pr = pchunk_pair[ch];
+        diag = pair_k[pr] == pair_l[pr];
+        if (diag) pair_accumulate<true, G>(pchunk_beg[ch], pchunk_end[ch], lane, tri_oa, tri_ob, iidx, W, Vinv, gb, acc);
+        else pair_accumulate<false, G>(pchunk_beg[ch], pchunk_end[ch], lane, tri_oa, tri_ob, iidx, W, Vinv, gb, acc);
+    }
+#pragma unroll
+    for (int w = G / 2; w > 0; w >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 42; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], w);
+    }
+    if (ch < n_pchunk) {
+        double *out = part + (size_t)ch * 42;
+        const int nv = diag ? 42 : 36;
+#pragma unroll
+        for (int q = 0; q < 42; ++q)
+            if ((q % G) == lane && q < nv) out[q] = acc[q];
+    }
+}
+
+template <int G>
+static void launch_pairs(psba_ctx *c)
+{
+    const int per_cta = PAIR_CTA / G;
+    k_schur_pairs<G><<<cdiv(c->n_pchunk, per_cta), PAIR_CTA, 0, c->stream>>>(c->n_pchunk, c->pchunk_pair, c->pchunk_beg, c->pchunk_end,
+                                                                          c->pair_k, c->pair_l, c->tri_oa, c->tri_ob, c->iidx, c->W,
+                                                                          c->Vinv, c->g + c->N, c->pair_part);
 }
 
 // per pair block: fixed-order sum of its chunk partials, S_kl = [k==l](U_k + mu I) - sum, written
@@ -182,8 +213,16 @@ void psba_launch_schur(psba_ctx *c, double mu)
     psba_launch_vinv(c, mu);
     PROF(c, KID_MEMSET_S) CUDA_CHECK(cudaMemsetAsync(c->Stiles, 0, (size_t)c->n_tiles * TS * TS * sizeof(double), c->stream));
     if (c->n_pchunk > 0)
-        PROF(c, KID_SCHUR_PAIRS) k_schur_pairs<<<c->n_pchunk, PAIR_CTA, 0, c->stream>>>(c->pchunk_pair, c->pchunk_beg, c->pchunk_end, c->pair_k, c->pair_l,
-                                                              c->tri_oa, c->tri_ob, c->iidx, c->W, c->Vinv, c->g + c->N, c->pair_part);
+        PROF(c, KID_SCHUR_PAIRS) {
+            switch (c->pair_G) {
+            case 1: launch_pairs<1>(c); break;
+            case 2: launch_pairs<2>(c); break;
+            case 4: launch_pairs<4>(c); break;
+            case 8: launch_pairs<8>(c); break;
+            case 16: launch_pairs<16>(c); break;
+            default: launch_pairs<32>(c); break;
+            }
+        }
     const int single = c->nranks == 1;
     PROF(c, KID_S_FINALIZE) k_S_finalize<<<cdiv((long long)c->n_pair * 42, 128), 128, 0, c->stream>>>(c->n_pair, c->pair_k, c->pair_l, c->pair_chunk_ptr,
                                                                              c->pair_part, c->U, c->g, mu, single, c->tile_index,

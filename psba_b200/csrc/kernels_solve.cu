@@ -19,306 +19,17 @@
 #define LDT (TS + 1)   // padded leading dimension in shared memory
 
 // ---------------------------------------------------------------------------------------------
-void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int>> &pairs)
-{
-    const int nt = (c->m + 7) / 8;
-    c->nt = nt;
-    std::vector<char> present((size_t)nt * nt, 0);
-    for (int I = 0; I < nt; ++I) present[(size_t)I * nt + I] = 1;
-    for (auto &p : pairs) present[(size_t)(p.first / 8) * nt + p.second / 8] = 1;
-    c->panel_row_ptr.assign(1, 0); c->panel_rows.clear();
-    c->panel_upd_ptr.assign(1, 0);
-    std::vector<int> updI, updJ;
-    for (int K = 0; K < nt; ++K) {
-        std::vector<int> rows;
-        for (int I = K + 1; I < nt; ++I) if (present[(size_t)I * nt + K]) rows.push_back(I);
-        for (size_t a = 0; a < rows.size(); ++a)
-            for (size_t b = 0; b <= a; ++b) {
-                present[(size_t)rows[a] * nt + rows[b]] = 1;
-                updI.push_back(rows[a]); updJ.push_back(rows[b]);
-            }
-        c->panel_rows.insert(c->panel_rows.end(), rows.begin(), rows.end());
-        c->panel_row_ptr.push_back((int)c->panel_rows.size());
-        c->panel_upd_ptr.push_back((int)updI.size());
-    }
-    c->h_tile_index.assign((size_t)nt * nt, -1);
-    int slot = 0;
-    std::vector<int> rptr(1, 0), rcol, rslot;
-    for (int I = 0; I < nt; ++I) {
-        for (int J = 0; J <= I; ++J)
-            if (present[(size_t)I * nt + J]) {
-                c->h_tile_index[(size_t)I * nt + J] = slot;
-                if (J < I) { rcol.push_back(J); rslot.push_back(slot); }
-                ++slot;
-            }
-        rptr.push_back((int)rcol.size());
-    }
-    std::vector<int> cptr(1, 0), crow, cslot;
-    for (int J = 0; J < nt; ++J) {
-        for (int I = J + 1; I < nt; ++I)
-            if (present[(size_t)I * nt + J]) { crow.push_back(I); cslot.push_back(c->h_tile_index[(size_t)I * nt + J]); }
-        cptr.push_back((int)crow.size());
-    }
-    c->n_tiles = slot;
-    auto up = [&](int **d, const std::vector<int> &h) {
-        CUDA_CHECK(cudaMalloc(d, std::max<size_t>(1, h.size()) * sizeof(int)));
-        if (!h.empty()) CUDA_CHECK(cudaMemcpy(*d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
-    };
-    up(&c->tile_index, c->h_tile_index);
-    up(&c->d_panel_rows, c->panel_rows);
-    up(&c->d_upd_I, updI); up(&c->d_upd_J, updJ);
-    up(&c->d_rowtile_ptr, rptr); up(&c->d_rowtile_col, rcol); up(&c->d_rowtile_slot, rslot);
-    up(&c->d_coltile_ptr, cptr); up(&c->d_coltile_row, crow); up(&c->d_coltile_slot, cslot);
-    CUDA_CHECK(cudaMalloc(&c->Stiles, (size_t)c->n_tiles * TS * TS * sizeof(double)));
-    CUDA_CHECK(cudaMalloc(&c->Linv, (size_t)nt * TS * TS * sizeof(double)));
-    c->chol_graph_ok = false;
-}
-
-// ---------------------------------------------------------------------------------------------
-// potrf of the diagonal tile K (in shared memory) + inverse of its factor
-__global__ void __launch_bounds__(256) k_potrf_diag(int K, int nt, const int *__restrict__ tile_index,
-                                                    double *__restrict__ Stiles, double *__restrict__ Linv, int *__restrict__ status)
-{
-    __shared__ double A[TS * LDT];
-    __shared__ int bad;
-    if (*status != 0) return;
-    const int tid = threadIdx.x;
-    double *tile = Stiles + (size_t)tile_index[K * nt + K] * TS * TS;
-    for (int e = tid; e < TS * TS; e += 256) A[(e / TS) * LDT + (e % TS)] = tile[e];
-    if (tid == 0) bad = 0;
-    __syncthreads();
-    for (int j = 0; j < TS; ++j) {
-        if (tid == 0) {
-            double d = A[j * LDT + j];
-            if (!(d > 0.0) || !isfinite(d)) bad = 1;
-            A[j * LDT + j] = sqrt(d);
-        }
-        __syncthreads();
-        if (bad) break;
-        const double djj = A[j * LDT + j];
-        if (tid > j && tid < TS) A[tid * LDT + j] /= djj;
-        __syncthreads();
-        // trailing lower triangle: (r,c), j < c <= r
-        const int rem = TS - 1 - j;
-        for (int e = tid; e < rem * rem; e += 256) {
-            const int r = j + 1 + e / rem, cc = j + 1 + e % rem;
-            if (cc <= r) A[r * LDT + cc] -= A[r * LDT + j] * A[cc * LDT + j];
-        }
-        __syncthreads();
-    }
-    if (bad) { if (tid == 0) *status = 1; return; }
-    for (int e = tid; e < TS * TS; e += 256) {
-        const int r = e / TS, cc = e % TS;
-        tile[e] = (cc <= r) ? A[r * LDT + cc] : 0.0;
-    }
-    // column cidx of L^-1 by forward substitution (one thread per column)
-    double *inv = Linv + (size_t)K * TS * TS;
-    if (tid < TS) {
-        const int cidx = tid;
-        double x[TS];
-#pragma unroll 1
-        for (int r = 0; r < TS; ++r) {
-            double v;
-            if (r < cidx) v = 0.0;
-            else if (r == cidx) v = 1.0 / A[r * LDT + r];
-            else {
-                double s = 0.0;
-                for (int k = cidx; k < r; ++k) s += A[r * LDT + k] * x[k];
-                v = -s / A[r * LDT + r];
-            }
-            x[r] = v;
-            inv[r * TS + cidx] = v;
-        }
-    }
-}
-
-// L_IK = A_IK * Linv_KK^T for the tiles below the diagonal of panel K
-__global__ void __launch_bounds__(256) k_trsm_tiles(int K, int nt, const int *__restrict__ rows, const int *__restrict__ tile_index,
-                                                    double *__restrict__ Stiles, const double *__restrict__ Linv, const int *__restrict__ status)
-{
-    __shared__ double A[TS * LDT];
-    __shared__ double Li[TS * LDT];
-    if (*status != 0) return;
-    const int tid = threadIdx.x;
-    const int I = rows[blockIdx.x];
-    double *tile = Stiles + (size_t)tile_index[I * nt + K] * TS * TS;
-    const double *inv = Linv + (size_t)K * TS * TS;
-    for (int e = tid; e < TS * TS; e += 256) { A[(e / TS) * LDT + (e % TS)] = tile[e]; Li[(e / TS) * LDT + (e % TS)] = inv[e]; }
-    __syncthreads();
-    const int tr = tid / 16, tc = tid % 16;
-    double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int k = 0; k < TS; ++k) {
-        double a[3], b[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) { a[q] = A[(tr * 3 + q) * LDT + k]; b[q] = Li[(tc * 3 + q) * LDT + k]; }
-#pragma unroll
-        for (int p = 0; p < 3; ++p)
-#pragma unroll
-            for (int q = 0; q < 3; ++q) acc[p][q] += a[p] * b[q];
-    }
-#pragma unroll
-    for (int p = 0; p < 3; ++p)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) tile[(tr * 3 + p) * TS + tc * 3 + q] = acc[p][q];
-}
-
-// A_IJ -= L_IK * L_JK^T for the trailing tiles of panel K
-__global__ void __launch_bounds__(256) k_update_tiles(int K, int nt, const int *__restrict__ updI, const int *__restrict__ updJ,
-                                                      const int *__restrict__ tile_index, double *__restrict__ Stiles,
-                                                      const int *__restrict__ status)
-{
-    __shared__ double A[TS * LDT];
-    __shared__ double B[TS * LDT];
-    if (*status != 0) return;
-    const int tid = threadIdx.x;
-    const int I = updI[blockIdx.x], J = updJ[blockIdx.x];
-    const double *ta = Stiles + (size_t)tile_index[I * nt + K] * TS * TS;
-    const double *tb = Stiles + (size_t)tile_index[J * nt + K] * TS * TS;
-    double *tcij = Stiles + (size_t)tile_index[I * nt + J] * TS * TS;
-    for (int e = tid; e < TS * TS; e += 256) { A[(e / TS) * LDT + (e % TS)] = ta[e]; B[(e / TS) * LDT + (e % TS)] = tb[e]; }
-    __syncthreads();
-    const int tr = tid / 16, tc = tid % 16;
-    double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int k = 0; k < TS; ++k) {
-        double a[3], b[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) { a[q] = A[(tr * 3 + q) * LDT + k]; b[q] = B[(tc * 3 + q) * LDT + k]; }
-#pragma unroll
-        for (int p = 0; p < 3; ++p)
-#pragma unroll
-            for (int q = 0; q < 3; ++q) acc[p][q] += a[p] * b[q];
-    }
-#pragma unroll
-    for (int p = 0; p < 3; ++p)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) tcij[(tr * 3 + p) * TS + tc * 3 + q] -= acc[p][q];
-}
-
-static void enqueue_factor(psba_ctx *c)
-{
-    for (int K = 0; K < c->nt; ++K) {
-        k_potrf_diag<<<1, 256, 0, c->stream>>>(K, c->nt, c->tile_index, c->Stiles, c->Linv, c->d_status);
-        const int nr = c->panel_row_ptr[K + 1] - c->panel_row_ptr[K];
-        if (nr > 0)
-            k_trsm_tiles<<<nr, 256, 0, c->stream>>>(K, c->nt, c->d_panel_rows + c->panel_row_ptr[K], c->tile_index, c->Stiles,
-                                                   c->Linv, c->d_status);
-        const int nu = c->panel_upd_ptr[K + 1] - c->panel_upd_ptr[K];
-        if (nu > 0)
-            k_update_tiles<<<nu, 256, 0, c->stream>>>(K, c->nt, c->d_upd_I + c->panel_upd_ptr[K], c->d_upd_J + c->panel_upd_ptr[K],
-                                                     c->tile_index, c->Stiles, c->d_status);
-    }
-}
-
-double psba_launch_factor(psba_ctx *c)
-{
-    CUDA_CHECK(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream));
-    if (!c->chol_graph_ok) {
-        cudaGraph_t graph;
-        CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        enqueue_factor(c);
-        CUDA_CHECK(cudaStreamEndCapture(c->stream, &graph));
-        CUDA_CHECK(cudaGraphInstantiate(&c->chol_graph, graph, 0));
-        CUDA_CHECK(cudaGraphDestroy(graph));
-        c->chol_graph_ok = true;
-    }
-    PROF(c, KID_FACTOR) CUDA_CHECK(cudaGraphLaunch(c->chol_graph, c->stream));
-    c->st_launches += 3 * c->nt;
-    int st = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    c->factor_valid = (st == 0);
-    c->S_valid = false;      // the factor overwrote the tile pool
-    return st ? 1.0 : 0.0;
-}
-
-// ---------------------------------------------------------------------------------------------
-// dpa = S^-1 ea with the tiled factor: forward then backward substitution, one persistent CTA.
-// 16 warps; warp w owns rows w, w+16, w+32 of the current tile row, lanes stride the columns.
-__global__ void __launch_bounds__(512) k_tri_solve(int N, int nt, const int *__restrict__ tile_index,
-                                                   const int *__restrict__ rptr, const int *__restrict__ rcol, const int *__restrict__ rslot,
-                                                   const int *__restrict__ cptr, const int *__restrict__ crow, const int *__restrict__ cslot,
-                                                   const double *__restrict__ Stiles, const double *__restrict__ Linv,
-                                                   const double *__restrict__ rhs, double *__restrict__ ywork, double *__restrict__ sol)
-{
-    __shared__ double acc[TS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // forward: y_I = Linv_II (b_I - sum_{J<I} L_IJ y_J)
-    for (int I = 0; I < nt; ++I) {
-        for (int r = warp; r < TS; r += 16) {
-            double s = 0.0;
-            for (int t = rptr[I]; t < rptr[I + 1]; ++t) {
-                const double *L = Stiles + (size_t)rslot[t] * TS * TS + r * TS;
-                const double *y = ywork + rcol[t] * TS;
-                for (int cc = lane; cc < TS; cc += 32) s += L[cc] * y[cc];
-            }
-#pragma unroll
-            for (int w = 16; w > 0; w >>= 1) s += __shfl_down_sync(0xffffffffu, s, w);
-            if (lane == 0) { const int gr = I * TS + r; acc[r] = (gr < N ? rhs[gr] : 0.0) - s; }
-        }
-        __syncthreads();
-        if (tid < TS) {
-            const double *inv = Linv + (size_t)I * TS * TS + tid * TS;
-            double s = 0.0;
-            for (int cc = 0; cc <= tid; ++cc) s += inv[cc] * acc[cc];
-            ywork[I * TS + tid] = s;
-        }
-        __syncthreads();
-    }
-    // backward: x_I = Linv_II^T (y_I - sum_{J>I} L_JI^T x_J); x overwrites ywork
-    for (int I = nt - 1; I >= 0; --I) {
-        if (tid < TS) acc[tid] = 0.0;
-        __syncthreads();
-        // thread (col = tid % 48, part = tid / 48): partial sums over tile rows r = part, part+10, ...
-        {
-            const int col = tid % TS, part = tid / TS;    // 512 threads -> parts 0..9 (+ 32 idle)
-            if (part < 10) {
-                double s = 0.0;
-                for (int t = cptr[I]; t < cptr[I + 1]; ++t) {
-                    const double *L = Stiles + (size_t)cslot[t] * TS * TS;
-                    const double *x = ywork + crow[t] * TS;
-                    for (int r = part; r < TS; r += 10) s += L[r * TS + col] * x[r];
-                }
-                // fixed-order combination of the 10 parts
-                for (int p = 0; p < 10; ++p) {
-                    if (part == p) acc[col] += s;
-                    __syncthreads();
-                }
-            } else {
-                for (int p = 0; p < 10; ++p) __syncthreads();
-            }
-        }
-        if (tid < TS) acc[tid] = ywork[I * TS + tid] - acc[tid];
-        __syncthreads();
-        if (tid < TS) {
-            const double *inv = Linv + (size_t)I * TS * TS;
-            double s = 0.0;
-            for (int r = tid; r < TS; ++r) s += inv[r * TS + tid] * acc[r];
-            ywork[I * TS + tid] = s;
-            const int gr = I * TS + tid;
-            if (gr < N) sol[gr] = s;
-        }
-        __syncthreads();
-    }
-}
-
-void psba_launch_solve(psba_ctx *c)
-{
-    PROF(c, KID_TRI_SOLVE) k_tri_solve<<<1, 512, 0, c->stream>>>(c->N, c->nt, c->tile_index, c->d_rowtile_ptr, c->d_rowtile_col, c->d_rowtile_slot,
-                                         c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot, c->Stiles, c->Linv,
-                                         c->eab, c->chol_aux, c->dp);
-    c->st_launches += 1;
-}
-
 // ---------------------------------------------------------------------------------------------
 // tile pool -> dense N x N row-major (lower triangle; mirror fills the upper one)
 __global__ void k_tiles_to_dense(int N, int nt, const int *__restrict__ tile_index, const double *__restrict__ Stiles,
-                                 double *__restrict__ dense, int mirror)
+                                 double *__restrict__ dense, int mirror, const double *__restrict__ Ldiag)
 {
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long long)N * N) return;
     const int r = (int)(e / N), cc = (int)(e % N);
     int rr = r, c2 = cc;
     if (cc > r) { if (!mirror) { dense[e] = 0.0; return; } rr = cc; c2 = r; }
+    if (Ldiag && rr / TS == c2 / TS) { dense[e] = Ldiag[(size_t)(rr / TS) * TS * TS + (rr % TS) * TS + c2 % TS]; return; }
     const int slot = tile_index[(rr / TS) * nt + c2 / TS];
     dense[e] = slot < 0 ? 0.0 : Stiles[(size_t)slot * TS * TS + (rr % TS) * TS + c2 % TS];
 }
@@ -326,7 +37,15 @@ __global__ void k_tiles_to_dense(int N, int nt, const int *__restrict__ tile_ind
 void psba_tiles_to_dense(psba_ctx *c, double *dense_dev, bool mirror)
 {
     long long tot = (long long)c->N * c->N;
-    k_tiles_to_dense<<<cdiv(tot, 256), 256, 0, c->stream>>>(c->N, c->nt, c->tile_index, c->Stiles, dense_dev, mirror ? 1 : 0);
+    k_tiles_to_dense<<<cdiv(tot, 256), 256, 0, c->stream>>>(c->N, c->nt, c->tile_index, c->Stiles, dense_dev, mirror ? 1 : 0, nullptr);
+    c->st_launches += 1;
+}
+
+// the factor L as a dense lower-triangular matrix (diagonal tiles live in their own pool)
+static void psba_factor_to_dense(psba_ctx *c, double *dense_dev)
+{
+    long long tot = (long long)c->N * c->N;
+    k_tiles_to_dense<<<cdiv(tot, 256), 256, 0, c->stream>>>(c->N, c->nt, c->tile_index, c->Stiles, dense_dev, 0, c->Ldiag);
     c->st_launches += 1;
 }
 
@@ -355,7 +74,7 @@ void psba_launch_explicit_inverse(psba_ctx *c, double *out_dev)
     const size_t nn = (size_t)c->N * c->N;
     if (!c->Sdense) CUDA_CHECK(cudaMalloc(&c->Sdense, nn * sizeof(double)));
     if (!c->Sdense_aux) CUDA_CHECK(cudaMalloc(&c->Sdense_aux, nn * sizeof(double)));
-    psba_tiles_to_dense(c, c->Sdense, false);
+    psba_factor_to_dense(c, c->Sdense);
     k_explicit_inverse<<<cdiv(c->N, 64), 64, 0, c->stream>>>(c->N, c->Sdense, c->Sdense_aux, out_dev);
     c->st_launches += 1;
 }

@@ -214,7 +214,18 @@ extern "C" void psba_fill_idxBuffer(psba_ctx *c, int nCams, int n3Dpts, int n2Dp
     c->tri_oa = dupload(toa); c->tri_ob = dupload(tob);
     std::vector<int> pc_pair, pc_ptr(1, 0);
     std::vector<long long> pc_beg, pc_end;
-    const long long PCH = (long long)PAIR_CTA * PAIR_TPT;
+    // lane-group size of the pair pass: every group of G lanes owns one chunk of <= G*PAIR_TPL triples of
+    // one camera pair; G follows the mean run length so that a lane streams ~PAIR_TPL triples before the
+    // (shuffle) reduction -- 4 for the synthetic ring (117 triples / pair), 32 for BAL (~10^3 / pair)
+    {
+        long long nonempty = 0;
+        for (int p = 0; p < c->n_pair; ++p) if (tptr[p + 1] > tptr[p]) ++nonempty;
+        const double avg = nonempty ? (double)c->ntri / (double)nonempty : 1.0;
+        int G = 1;
+        while (G < 32 && avg > (double)G * PAIR_TPL) G *= 2;
+        c->pair_G = G;
+    }
+    const long long PCH = (long long)c->pair_G * PAIR_TPL;
     for (int p = 0; p < c->n_pair; ++p) {
         for (long long b = tptr[p]; b < tptr[p + 1]; b += PCH) { pc_pair.push_back(p); pc_beg.push_back(b); pc_end.push_back(std::min(b + PCH, tptr[p + 1])); }
         pc_ptr.push_back((int)pc_pair.size());
@@ -251,7 +262,7 @@ extern "C" void psba_release_buffer(psba_ctx *c)
                     c->iidx, c->jidx, c->pt_ptr, c->ptchunk, c->cam_obs, c->cchunk_cam, c->cchunk_beg, c->cchunk_end,
                     c->cam_cchunk_ptr, c->tri_oa, c->tri_ob, c->pair_k, c->pair_l, c->pair_chunk_ptr, c->pchunk_pair,
                     c->pchunk_beg, c->pchunk_end, c->W, c->V, c->Vinv, c->U, c->g, c->UVdiag_scr, c->cam_part, c->pair_part,
-                    c->tile_index, c->Stiles, c->Linv, c->eab, c->dp, c->d_status, c->d_panel_rows, c->d_upd_I, c->d_upd_J,
+                    c->tile_index, c->Stiles, c->Linv, c->eab, c->dp, c->d_status, c->d_crit_rows, c->d_ncr_I, c->d_ncr_J, c->Ldiag,
                     c->d_rowtile_ptr, c->d_rowtile_col, c->d_rowtile_slot, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
                     c->Sdense, c->Sdense_aux, c->chol_aux, c->chol_diag, c->chol_E, c->d_part, c->d_scal, c->P_U, c->P_B, c->P,
                     c->tmpA, c->tmpB};
@@ -558,6 +569,7 @@ extern "C" double psba_get_stat(psba_ctx *c, const char *name)
     if (s == "n_ptchunk") return c->n_ptchunk;
     if (s == "n_cchunk") return c->n_cchunk;
     if (s == "n_pchunk") return c->n_pchunk;
+    if (s == "pair_G") return c->pair_G;
     if (s == "cholmod_events") return c->n_cholmod_events;
     if (s == "timer_ms") {   // device time since "timer_start" on the engine's stream
         if (!c->timer_init) die("timer_ms before timer_start");

@@ -23,7 +23,7 @@
 #define CAM_CTA 128        // threads per camera-major CTA
 #define CAM_OPT 4          // observations per thread in the camera-major pass
 #define PAIR_CTA 128       // threads per pair-pass CTA
-#define PAIR_TPT 2         // triples per thread in the pair pass
+#define PAIR_TPL 24        // target triples per lane in the pair pass
 #define NSCAL 16           // size of the device scalar block
 
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
@@ -67,6 +67,7 @@ struct psba_ctx {
     int *tri_oa, *tri_ob;
     int n_pair; int *pair_k, *pair_l;          // pair blocks present GLOBALLY (all ranks agree)
     int *pair_chunk_ptr;                        // n_pair+1
+    int pair_G;                                 // lanes per chunk in the pair pass (1..32)
     int n_pchunk; int *pchunk_pair; long long *pchunk_beg, *pchunk_end;
     // ---- linearisation products
     double *W, *V, *Vinv, *U, *g, *UVdiag_scr;
@@ -82,10 +83,11 @@ struct psba_ctx {
     double *Linv;                   // nt * TS*TS   inverse of the diagonal factor tiles
     double *eab, *dp;               // T_loc-sized vectors laid out [N | 3n]
     int *d_status;                  // device int: 0 ok, 1 not PD
-    // per-panel task lists (host + device)
-    std::vector<int> panel_row_ptr, panel_rows;      // rows I>K with tile (I,K)
-    std::vector<int> panel_upd_ptr;                  // update tasks per panel
-    int *d_panel_rows; int *d_upd_I, *d_upd_J;
+    // per-panel task lists (host + device): critical CTAs of panel K = {K} + rows I>K with tile (I,K);
+    // deferred updates of panel K = trailing tiles (I,J), J>K, touched by panel K-1
+    std::vector<int> crit_ptr, ncr_ptr;
+    int *d_crit_rows; int *d_ncr_I, *d_ncr_J;
+    double *Ldiag;                  // nt * TS*TS   factor of the diagonal tiles (kept out of the tile pool)
     int *d_rowtile_ptr, *d_rowtile_col, *d_rowtile_slot;   // CSR of L tiles by row (for the solves)
     int *d_coltile_ptr, *d_coltile_row, *d_coltile_slot;   // CSC (for the backward solve)
     cudaGraphExec_t chol_graph; bool chol_graph_ok;

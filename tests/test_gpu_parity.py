@@ -168,5 +168,8 @@ def test_cholmod_matches_oracle():
     sum_o = O.call("cholmod")
     res = G.cholmod_blk()
     assert res["n_scalar_blocks"] == int(O.get("ret"))
-    assert relerr(res["E"], O.buf("E")) < 1e-6
+    # E_i = sum_k L_ik^2 - S_ii is a difference of O(S_ii) numbers: compare at the scale of
+    # the diagonal, not of E itself (nvcc contracts a*b+c into FMA, the oracle is built without)
+    scale = float(np.max(np.abs(np.diag(S))))
+    assert float(np.max(np.abs(res["E"] - O.buf("E")))) < 1e-9 * scale
     G.close(); O.close()
