@@ -24,7 +24,7 @@
 
 #define LDT (TS + 1)            // padded leading dimension in shared memory
 #define TILE_SM (TS * LDT)      // doubles per shared tile
-#define CHOL_SMEM (5 * TILE_SM * sizeof(double))
+#define CHOL_SMEM (3 * TILE_SM * sizeof(double))
 
 // ---------------------------------------------------------------------------------------------
 void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int>> &pairs)
@@ -81,104 +81,126 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
 }
 
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_tile(double *sm, const double *__restrict__ g)
+// a 48x48 tile travels global -> registers (all loads in flight at once) -> padded shared memory
+template <int NT> struct TileRegs { double2 v[(TS * TS / 2 + NT - 1) / NT]; };
+template <int NT>
+__device__ __forceinline__ void tile_ldg(TileRegs<NT> &t, const double *__restrict__ g)
 {
-    for (int e = threadIdx.x; e < TS * TS / 2; e += 256) {
-        const double2 v = reinterpret_cast<const double2 *>(g)[e];
-        const int r = (2 * e) / TS, cc = (2 * e) % TS;
-        sm[r * LDT + cc] = v.x; sm[r * LDT + cc + 1] = v.y;
+    constexpr int Q = (TS * TS / 2 + NT - 1) / NT;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int e = threadIdx.x + q * NT;
+        t.v[q] = e < TS * TS / 2 ? reinterpret_cast<const double2 *>(g)[e] : make_double2(0.0, 0.0);
+    }
+}
+template <int NT>
+__device__ __forceinline__ void tile_sts(double *sm, const TileRegs<NT> &t)
+{
+    constexpr int Q = (TS * TS / 2 + NT - 1) / NT;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int e = threadIdx.x + q * NT;
+        if (e < TS * TS / 2) { const int r = (2 * e) / TS, cc = (2 * e) % TS; sm[r * LDT + cc] = t.v[q].x; sm[r * LDT + cc + 1] = t.v[q].y; }
+    }
+}
+// lower_only: entries above the diagonal are written as zero (diagonal factor tiles)
+template <int NT>
+__device__ __forceinline__ void tile_stg(double *__restrict__ g, const double *sm, bool lower_only = false)
+{
+    constexpr int Q = (TS * TS / 2 + NT - 1) / NT;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int e = threadIdx.x + q * NT;
+        if (e < TS * TS / 2) {
+            const int r = (2 * e) / TS, cc = (2 * e) % TS;
+            double x = sm[r * LDT + cc], y = sm[r * LDT + cc + 1];
+            if (lower_only) { if (cc > r) x = 0.0; if (cc + 1 > r) y = 0.0; }
+            reinterpret_cast<double2 *>(g)[e] = make_double2(x, y);
+        }
     }
 }
 
-// C (48x48 in smem) -= A * B^T, A and B 48x48 in smem; 256 threads, 3x3 register blocks
-__device__ __forceinline__ void tile_syrk_sub(double *C, const double *A, const double *B)
+// 128 threads as an 8 x 16 grid: thread (tr = tid % 8, tc = tid / 8) owns rows 6tr..6tr+5, columns
+// 3tc..3tc+2 of a tile (a warp covers four adjacent column triples, so warps retire as the sweep advances).
+// acc = A * B^T (and acc2 = A2 * B^T when TWO) for 48x48 tiles in smem.
+template <bool TWO>
+__device__ __forceinline__ void tile_abt(const double *A, const double *A2, const double *B, double acc[6][3], double acc2[6][3])
 {
-    const int tr = threadIdx.x / 16, tc = threadIdx.x % 16;
-    double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    const int tr = threadIdx.x % 8, tc = threadIdx.x / 8;
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { acc[p][q] = 0.0; if (TWO) acc2[p][q] = 0.0; }
 #pragma unroll 4
     for (int k = 0; k < TS; ++k) {
-        double a[3], b[3];
+        double a[6], a2[6], b[3];
 #pragma unroll
-        for (int q = 0; q < 3; ++q) { a[q] = A[(tr * 3 + q) * LDT + k]; b[q] = B[(tc * 3 + q) * LDT + k]; }
+        for (int p = 0; p < 6; ++p) { a[p] = A[(tr * 6 + p) * LDT + k]; if (TWO) a2[p] = A2[(tr * 6 + p) * LDT + k]; }
 #pragma unroll
-        for (int p = 0; p < 3; ++p)
+        for (int q = 0; q < 3; ++q) b[q] = B[(tc * 3 + q) * LDT + k];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) acc[p][q] += a[p] * b[q];
+        for (int p = 0; p < 6; ++p)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { acc[p][q] += a[p] * b[q]; if (TWO) acc2[p][q] += a2[p] * b[q]; }
     }
-#pragma unroll
-    for (int p = 0; p < 3; ++p)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) C[(tr * 3 + p) * LDT + tc * 3 + q] -= acc[p][q];
 }
 
-// in-smem Cholesky of the 48x48 tile D (lower part), factor written to Lo; one barrier per column.
-// Right-looking with the scaling folded into the update: D_ic -= D_ij D_cj / D_jj.  Returns false
-// (in every thread) when a pivot is <= 0 or not finite.
-__device__ __forceinline__ bool tile_potrf(double *D, double *Lo, int *bad)
+// X = L^-1 for the lower-triangular 48x48 factor in smem, by recursive doubling: the eight 6x6 diagonal
+// blocks are inverted by substitution (one thread per column, <= 5 dependent steps), then blocks are
+// merged pairwise (h = 6, 12, 24):  inv [[A,0],[B,C]] = [[A^-1,0],[-C^-1 B A^-1, C^-1]].  The h x h
+// scratch T = B A^-1 lives in the upper-right corner of the pair, which is zero in the result.
+template <int H>
+__device__ __forceinline__ void tri_inverse_merge(const double *L, double *X)
 {
     const int tid = threadIdx.x;
-    if (tid == 0) *bad = 0;
-    __syncthreads();
-#pragma unroll 1
-    for (int j = 0; j < TS; ++j) {
-        const double djj = D[j * LDT + j];
-        if (!(djj > 0.0) || !isfinite(djj)) { if (tid == 0) *bad = 1; break; }     // uniform: all threads read the same value
-        const double inv = 1.0 / djj;
-        if (tid >= j && tid < TS) Lo[tid * LDT + j] = (tid == j) ? sqrt(djj) : D[tid * LDT + j] * (sqrt(djj) * inv);
-        if (tid < j) Lo[tid * LDT + j] = 0.0;
-        const int rem = TS - 1 - j;
-        // trailing lower triangle (j < c <= i): linear index over the rem x rem square, upper half skipped
-        for (int e = tid; e < rem * rem; e += 256) {
-            const int i = j + 1 + e / rem, cc = j + 1 + e % rem;
-            if (cc <= i) D[i * LDT + cc] -= D[i * LDT + j] * D[cc * LDT + j] * inv;
-        }
-        __syncthreads();
+    constexpr int NP = TS / (2 * H), PER = H * H;
+    for (int e = tid; e < NP * PER; e += 256) {               // T = L21 * X11
+        const int o = (e / PER) * 2 * H, r = (e % PER) / H, cc = e % H;
+        double s = 0.0;
+        for (int k = cc; k < H; ++k) s += L[(o + H + r) * LDT + o + k] * X[(o + k) * LDT + o + cc];
+        X[(o + r) * LDT + o + H + cc] = s;
     }
     __syncthreads();
-    return *bad == 0;
+    for (int e = tid; e < NP * PER; e += 256) {               // X21 = -X22 * T
+        const int o = (e / PER) * 2 * H, r = (e % PER) / H, cc = e % H;
+        double s = 0.0;
+        for (int k = 0; k <= r; ++k) s += X[(o + H + r) * LDT + o + H + k] * X[(o + k) * LDT + o + H + cc];
+        X[(o + H + r) * LDT + o + cc] = -s;
+    }
+    __syncthreads();
+    for (int e = tid; e < NP * PER; e += 256) {
+        const int o = (e / PER) * 2 * H, r = (e % PER) / H, cc = e % H;
+        X[(o + r) * LDT + o + H + cc] = 0.0;
+    }
+    __syncthreads();
 }
 
-// X = L^-1 for the lower-triangular 48x48 factor in smem (two 24x24 diagonal blocks inverted by
-// substitution, one thread per column; off-diagonal block X21 = -X22 * L21 * X11 by two small GEMMs;
-// T is a 24x24 scratch inside X's upper-right corner, which is zero in the result and cleared last).
 __device__ __forceinline__ void tile_tri_inverse(const double *L, double *X)
 {
     const int tid = threadIdx.x;
-    constexpr int H = TS / 2;
     for (int e = tid; e < TS * LDT; e += 256) X[e] = 0.0;
     __syncthreads();
     if (tid < TS) {
-        const int b0 = (tid / H) * H, cidx = tid % H;          // block origin, column inside the block
-        const int gc = b0 + cidx;
-        X[gc * LDT + gc] = 1.0 / L[gc * LDT + gc];
-        for (int r = cidx + 1; r < H; ++r) {
-            const int gr = b0 + r;
-            double s0 = 0.0, s1 = 0.0;
-            int k = cidx;
-            for (; k + 1 < r; k += 2) { s0 += L[gr * LDT + b0 + k] * X[(b0 + k) * LDT + gc]; s1 += L[gr * LDT + b0 + k + 1] * X[(b0 + k + 1) * LDT + gc]; }
-            if (k < r) s0 += L[gr * LDT + b0 + k] * X[(b0 + k) * LDT + gc];
-            X[gr * LDT + gc] = -(s0 + s1) / L[gr * LDT + gr];
+        const int b0 = (tid / 6) * 6, cidx = tid % 6, gc = b0 + cidx;
+        double x[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            double v = 0.0;
+            if (r == cidx) v = 1.0 / L[gc * LDT + gc];
+            else if (r > cidx) {
+                double sum = 0.0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) if (k >= cidx && k < r) sum += L[(b0 + r) * LDT + b0 + k] * x[k];
+                v = -sum / L[(b0 + r) * LDT + b0 + r];
+            }
+            x[r] = v;
+            X[(b0 + r) * LDT + gc] = v;
         }
     }
     __syncthreads();
-    // T = L21 * X11  (24x24), stored in the upper-right corner X[0..H)[H..TS)
-    for (int e = tid; e < H * H; e += 256) {
-        const int r = e / H, cc = e % H;
-        double s = 0.0;
-        for (int k = cc; k < H; ++k) s += L[(H + r) * LDT + k] * X[k * LDT + cc];
-        X[r * LDT + H + cc] = s;
-    }
-    __syncthreads();
-    // X21 = -X22 * T
-    for (int e = tid; e < H * H; e += 256) {
-        const int r = e / H, cc = e % H;
-        double s = 0.0;
-        for (int k = 0; k <= r; ++k) s += X[(H + r) * LDT + H + k] * X[k * LDT + H + cc];
-        X[(H + r) * LDT + cc] = -s;
-    }
-    __syncthreads();
-    for (int e = tid; e < H * H; e += 256) X[(e / H) * LDT + H + e % H] = 0.0;
-    __syncthreads();
+    tri_inverse_merge<6>(L, X);
+    tri_inverse_merge<12>(L, X);
+    tri_inverse_merge<24>(L, X);
 }
 
 __global__ void k_init_rhs(int N, int npad, const double *__restrict__ ea, double *__restrict__ b)
@@ -187,90 +209,169 @@ __global__ void k_init_rhs(int N, int npad, const double *__restrict__ ea, doubl
     if (k < npad) b[k] = k < N ? ea[k] : 0.0;
 }
 
-__global__ void __launch_bounds__(256) k_panel(int K, int nt, int ncrit, const int *__restrict__ crit_rows,
-                                               const int *__restrict__ ncrI, const int *__restrict__ ncrJ,
-                                               const int *__restrict__ tile_index, double *__restrict__ Stiles,
-                                               double *__restrict__ Linv, double *__restrict__ Ldiag,
-                                               double *__restrict__ bwork, double *__restrict__ ywork, int *__restrict__ status)
+#define PANEL_NT 128
+// One kernel per panel K (128 threads per CTA).
+//  critical CTA for tile row I (I = K: the diagonal CTA): loads D = A_KK, A_IK and the factor tiles of
+//  panel K-1, applies the deferred updates, then ONE column sweep factors the stacked panel
+//  [D ; A_IK ; b_K^T] (97 x 48): l_ij = d_ij * rsqrt(d_jj), d_ic -= l_ij l_cj.  Rows of D become L_KK,
+//  rows of A_IK become L_IK = A_IK L_KK^-T (no explicit inverse, no separate trsm) and the extra row
+//  b_K^T becomes y_K^T = (L_KK^-1 b_K)^T, the forward substitution.  Every thread keeps one 6x3 block
+//  of D and one of A_IK in registers; per column only the 97 column entries go through shared memory
+//  (double-buffered, one barrier per column); the loop body is branch-free (dead entries are updated
+//  too, a non-positive pivot poisons the panel with NaN and is reported once at the end).
+//  deferred CTAs: A_IJ -= L_I,K-1 L_J,K-1^T for the trailing tiles (J > K) of panel K-1.
+__global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, const int *__restrict__ crit_rows,
+                                                    const int *__restrict__ ncrI, const int *__restrict__ ncrJ,
+                                                    const int *__restrict__ tile_index, double *__restrict__ Stiles,
+                                                    double *__restrict__ Ldiag, double *__restrict__ bwork,
+                                                    double *__restrict__ ywork, int *__restrict__ status)
 {
     extern __shared__ double smem[];
-    __shared__ int bad;
-    __shared__ double yk[TS];
+    __shared__ double colbuf[2][2 * TS + 2];
     if (*status != 0) return;
-    const int tid = threadIdx.x;
-    double *B0 = smem, *B1 = smem + TILE_SM, *B2 = smem + 2 * TILE_SM, *B3 = smem + 3 * TILE_SM, *B4 = smem + 4 * TILE_SM;
+    const int tid = threadIdx.x, tr = tid % 8, tc = tid / 8;
+    double *B0 = smem, *B1 = smem + TILE_SM, *B2 = smem + 2 * TILE_SM;
 
     if ((int)blockIdx.x >= ncrit) {
         // ---- deferred trailing update of panel K-1:  A_IJ -= L_I,K-1 L_J,K-1^T
         const int t = blockIdx.x - ncrit;
         const int I = ncrI[t], J = ncrJ[t];
         double *tij = Stiles + (size_t)tile_index[I * nt + J] * TS * TS;
-        load_tile(B0, Stiles + (size_t)tile_index[I * nt + (K - 1)] * TS * TS);
-        load_tile(B1, Stiles + (size_t)tile_index[J * nt + (K - 1)] * TS * TS);
-        load_tile(B2, tij);
+        TileRegs<PANEL_NT> ra, rb;
+        tile_ldg(ra, Stiles + (size_t)tile_index[I * nt + (K - 1)] * TS * TS);
+        tile_ldg(rb, Stiles + (size_t)tile_index[J * nt + (K - 1)] * TS * TS);
+        double c18[6][3];
+#pragma unroll
+        for (int p = 0; p < 6; ++p)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) c18[p][q] = tij[(tr * 6 + p) * TS + tc * 3 + q];
+        tile_sts(B0, ra); tile_sts(B1, rb);
         __syncthreads();
-        tile_syrk_sub(B2, B0, B1);
-        __syncthreads();
-        for (int e = tid; e < TS * TS; e += 256) tij[e] = B2[(e / TS) * LDT + e % TS];
+        double acc[6][3];
+        tile_abt<false>(B0, B0, B1, acc, acc);
+#pragma unroll
+        for (int p = 0; p < 6; ++p)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) tij[(tr * 6 + p) * TS + tc * 3 + q] = c18[p][q] - acc[p][q];
         return;
     }
 
     // ---- critical path of panel K for tile row I
     const int I = crit_rows[blockIdx.x];
+    const bool diagcta = I == K;
     const bool have_prev = K > 0 && tile_index[K * nt + (K - 1)] >= 0;
-    load_tile(B0, Stiles + (size_t)tile_index[K * nt + K] * TS * TS);          // D = A_KK (partially updated)
-    if (have_prev) load_tile(B2, Stiles + (size_t)tile_index[K * nt + (K - 1)] * TS * TS);   // L_K,K-1
-    __syncthreads();
-    if (have_prev) { tile_syrk_sub(B0, B2, B2); __syncthreads(); }
-    if (!tile_potrf(B0, B1, &bad)) { if (tid == 0) *status = 1; return; }     // B1 = L_KK
-    tile_tri_inverse(B1, B0);                                                  // B0 = L_KK^-1
-    // forward substitution piece: y_K = L_KK^-1 b_K
-    if (tid < TS) {
-        double s = 0.0;
-        for (int cc = 0; cc <= tid; ++cc) s += B0[tid * LDT + cc] * bwork[K * TS + cc];
-        yk[tid] = s;
+    const bool upd = !diagcta && have_prev && tile_index[I * nt + (K - 1)] >= 0;
+    double *tik = Stiles + (size_t)tile_index[I * nt + K] * TS * TS;
+    const double *tkk = Stiles + (size_t)tile_index[K * nt + K] * TS * TS;
+    // all global loads are issued before anything waits on them
+    TileRegs<PANEL_NT> rp, ri;
+    if (have_prev) tile_ldg(rp, Stiles + (size_t)tile_index[K * nt + (K - 1)] * TS * TS);    // L_K,K-1
+    if (upd) tile_ldg(ri, Stiles + (size_t)tile_index[I * nt + (K - 1)] * TS * TS);          // L_I,K-1
+    double d[6][3], a[6][3], bq[3] = {0, 0, 0};
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            d[p][q] = tkk[(tr * 6 + p) * TS + tc * 3 + q];
+            a[p][q] = diagcta ? 0.0 : tik[(tr * 6 + p) * TS + tc * 3 + q];
+        }
+    if (tr == 0) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) bq[q] = bwork[K * TS + tc * 3 + q];
+    }
+    if (have_prev) {
+        tile_sts(B0, rp);
+        if (upd) tile_sts(B1, ri);
+        __syncthreads();
+        double acc[6][3], acc2[6][3];
+        if (upd) tile_abt<true>(B0, B1, B0, acc, acc2);
+        else tile_abt<false>(B0, B0, B0, acc, acc2);
+#pragma unroll
+        for (int p = 0; p < 6; ++p)
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { d[p][q] -= acc[p][q]; if (upd) a[p][q] -= acc2[p][q]; }
+    }
+    // ---- column sweep over the stacked panel; B2 collects the factor rows of this CTA
+    bool bad = false;
+    double yk[3] = {0, 0, 0};
+    const double *pli = colbuf[0] + (diagcta ? 0 : TS) + tr * 6, *plc = colbuf[0] + tc * 3;
+    double *pout = B2 + (tr * 6) * LDT;
+    constexpr int CBS = 2 * TS + 2;
+#pragma unroll 1
+    const int warp_tc_max = (tid | 31) / 8;                 // last column triple owned by this warp
+    for (int jb = 0; jb < TS / 3; ++jb) {
+        const bool owner = tc == jb;
+        const bool live = warp_tc_max >= jb;                // warp-uniform: every entry of a retired warp is dead
+#pragma unroll
+        for (int jq = 0; jq < 3; ++jq) {
+            const int j = jb * 3 + jq, par = j & 1;
+            double *cb = colbuf[par];
+            if (owner) {
+#pragma unroll
+                for (int p = 0; p < 6; ++p) { cb[tr * 6 + p] = d[p][jq]; cb[TS + tr * 6 + p] = a[p][jq]; }
+                if (tr == 0) cb[2 * TS] = bq[jq];
+            }
+            __syncthreads();
+            if (!live) continue;
+            const double piv = cb[j];
+            bad |= !(piv > 0.0 && piv < 1e300);
+            const double rs = rsqrt(piv);
+            double lrow[6], ld[6], lc[3];
+            // lrow: this CTA's own factor rows (L_KK rows for the diagonal CTA, L_IK rows otherwise);
+            // ld: always the D rows (they keep being eliminated so that the pivots stay correct)
+#pragma unroll
+            for (int p = 0; p < 6; ++p) { ld[p] = cb[tr * 6 + p] * rs; lrow[p] = pli[par * CBS + p] * rs; }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) lc[q] = plc[par * CBS + q] * rs;
+            const double lb = cb[2 * TS] * rs;
+            if (owner) {
+#pragma unroll
+                for (int p = 0; p < 6; ++p) pout[p * LDT + j] = lrow[p];
+                if (tr == 0) yk[jq] = lb;
+            }
+#pragma unroll
+            for (int p = 0; p < 6; ++p)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { d[p][q] -= ld[p] * lc[q]; a[p][q] -= lrow[p] * lc[q]; }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) bq[q] -= lb * lc[q];
+        }
+    }
+    if (__syncthreads_or(bad)) { if (tid == 0) *status = 1; return; }
+    // y_K (held by the threads of grid row 0) -> shared
+    double *ysh = colbuf[0];
+    if (tr == 0) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) ysh[tc * 3 + q] = yk[q];
     }
     __syncthreads();
-    if (I == K) {
-        double *ld = Ldiag + (size_t)K * TS * TS, *li = Linv + (size_t)K * TS * TS;
-        for (int e = tid; e < TS * TS; e += 256) { ld[e] = B1[(e / TS) * LDT + e % TS]; li[e] = B0[(e / TS) * LDT + e % TS]; }
-        if (tid < TS) ywork[K * TS + tid] = yk[tid];
+    if (diagcta) {
+        tile_stg<PANEL_NT>(Ldiag + (size_t)K * TS * TS, B2, true);
+        if (tid < TS) ywork[K * TS + tid] = ysh[tid];
         return;
     }
-    // ---- off-diagonal tile: A_IK (deferred update from panel K-1), then L_IK = A_IK L_KK^-T
-    double *tik = Stiles + (size_t)tile_index[I * nt + K] * TS * TS;
-    load_tile(B3, tik);
-    const bool upd = have_prev && tile_index[I * nt + (K - 1)] >= 0;
-    if (upd) load_tile(B4, Stiles + (size_t)tile_index[I * nt + (K - 1)] * TS * TS);
-    __syncthreads();
-    if (upd) { tile_syrk_sub(B3, B4, B2); __syncthreads(); }
-    {
-        const int tr = tid / 16, tc = tid % 16;
-        double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-        const int kmax = tc * 3 + 3;                     // Linv is lower triangular: k <= column index
-#pragma unroll 4
-        for (int k = 0; k < kmax; ++k) {
-            double a[3], b[3];
-#pragma unroll
-            for (int q = 0; q < 3; ++q) { a[q] = B3[(tr * 3 + q) * LDT + k]; b[q] = B0[(tc * 3 + q) * LDT + k]; }
-#pragma unroll
-            for (int p = 0; p < 3; ++p)
-#pragma unroll
-                for (int q = 0; q < 3; ++q) acc[p][q] += a[p] * b[q];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int p = 0; p < 3; ++p)
-#pragma unroll
-            for (int q = 0; q < 3; ++q) B4[(tr * 3 + p) * LDT + tc * 3 + q] = acc[p][q];
-    }
-    __syncthreads();
-    for (int e = tid; e < TS * TS; e += 256) tik[e] = B4[(e / TS) * LDT + e % TS];
+    tile_stg<PANEL_NT>(tik, B2);
     if (tid < TS) {                                       // b_I -= L_IK y_K
         double s = 0.0;
-        for (int cc = 0; cc < TS; ++cc) s += B4[tid * LDT + cc] * yk[cc];
+#pragma unroll 8
+        for (int cc = 0; cc < TS; ++cc) s += B2[tid * LDT + cc] * ysh[cc];
         bwork[I * TS + tid] -= s;
     }
+}
+
+// L_KK^-1 for every diagonal tile (needed by the backward substitution only): one CTA per tile,
+// all tiles in parallel, off the critical path of the factorisation
+__global__ void __launch_bounds__(256) k_diag_inverse(const double *__restrict__ Ldiag, double *__restrict__ Linv, const int *__restrict__ status)
+{
+    extern __shared__ double smem[];
+    if (*status != 0) return;
+    double *B0 = smem, *B1 = smem + TILE_SM;
+    TileRegs<256> r;
+    tile_ldg(r, Ldiag + (size_t)blockIdx.x * TS * TS);
+    tile_sts(B0, r);
+    __syncthreads();
+    tile_tri_inverse(B0, B1);
+    tile_stg<256>(Linv + (size_t)blockIdx.x * TS * TS, B1);
 }
 
 static void enqueue_factor(psba_ctx *c)
@@ -280,13 +381,13 @@ static void enqueue_factor(psba_ctx *c)
     for (int K = 0; K < c->nt; ++K) {
         const int ncrit = c->crit_ptr[K + 1] - c->crit_ptr[K];
         const int nncr = c->ncr_ptr[K + 1] - c->ncr_ptr[K];
-        k_panel<<<ncrit + nncr, 256, CHOL_SMEM, c->stream>>>(K, c->nt, ncrit, c->d_crit_rows + c->crit_ptr[K],
-                                                            c->d_ncr_I + c->ncr_ptr[K], c->d_ncr_J + c->ncr_ptr[K], c->tile_index,
-                                                            c->Stiles, c->Linv, c->Ldiag, c->chol_aux, c->chol_diag, c->d_status);
+        k_panel<<<ncrit + nncr, PANEL_NT, CHOL_SMEM, c->stream>>>(K, c->nt, ncrit, c->d_crit_rows + c->crit_ptr[K],
+                                                                 c->d_ncr_I + c->ncr_ptr[K], c->d_ncr_J + c->ncr_ptr[K], c->tile_index,
+                                                                 c->Stiles, c->Ldiag, c->chol_aux, c->chol_diag, c->d_status);
     }
+    k_diag_inverse<<<c->nt, 256, 2 * TILE_SM * sizeof(double), c->stream>>>(c->Ldiag, c->Linv, c->d_status);
 }
 
-// factorise S (tile pool) and forward-substitute ea; returns 0.0 / 1.0 (synchronises)
 double psba_launch_factor(psba_ctx *c)
 {
     CUDA_CHECK(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream));
@@ -301,7 +402,7 @@ double psba_launch_factor(psba_ctx *c)
         c->chol_graph_ok = true;
     }
     PROF(c, KID_FACTOR) CUDA_CHECK(cudaGraphLaunch(c->chol_graph, c->stream));
-    c->st_launches += c->nt + 1;
+    c->st_launches += c->nt + 2;
     int st = 0;
     CUDA_CHECK(cudaMemcpyAsync(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -320,14 +421,20 @@ __global__ void __launch_bounds__(480) k_backward(int N, int nt, const int *__re
 {
     __shared__ double part[10][TS];
     __shared__ double acc[TS];
+    __shared__ double invs[TS * TS];
     const int tid = threadIdx.x, col = tid % TS, slotid = tid / TS;
     for (int I = nt - 1; I >= 0; --I) {
+        // L_II^-1 does not depend on x: fetch it while the tile column streams
+        for (int e = tid; e < TS * TS; e += 480) invs[e] = __ldg(Linv + (size_t)I * TS * TS + e);
         double s = 0.0;
         for (int t = cptr[I] + slotid; t < cptr[I + 1]; t += 10) {
             const double *L = Stiles + (size_t)cslot[t] * TS * TS + col;
             const double *x = ywork + crow[t] * TS;
-#pragma unroll 8
-            for (int r = 0; r < TS; ++r) s += L[r * TS] * x[r];
+            double lv[TS];
+#pragma unroll
+            for (int r = 0; r < TS; ++r) lv[r] = __ldg(L + r * TS);      // 48 independent coalesced loads in flight
+#pragma unroll
+            for (int r = 0; r < TS; ++r) s += lv[r] * x[r];
         }
         part[slotid][col] = s;
         __syncthreads();
@@ -339,7 +446,7 @@ __global__ void __launch_bounds__(480) k_backward(int N, int nt, const int *__re
         }
         __syncthreads();
         if (tid < TS) {
-            const double *inv = Linv + (size_t)I * TS * TS + tid;     // column tid of L_II^-1 = row of its transpose
+            const double *inv = invs + tid;                           // column tid of L_II^-1 = row of its transpose
             double a = 0.0;
 #pragma unroll 8
             for (int r = tid; r < TS; ++r) a += inv[r * TS] * acc[r];
