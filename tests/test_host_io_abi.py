@@ -1,0 +1,183 @@
+"""CPU tests (no GPU): host-side code of the product (readers, partitioning) and the C-ABI surface.
+
+The product library is LOADED here (its host functions run on the CPU) but no compute entry point is
+called -- those need a CUDA device and have no fallback.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+import psba_b200
+from util import HERE, data_file, dataset_paths
+
+ROOT = os.path.dirname(HERE)
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "psba_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(psba_[a-zA-Z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 40
+    L = psba_b200.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert b"sm_100a" in L.psba_version()
+
+
+def test_library_has_sm100a_code_only():
+    """the shipped kernels are sm_100a SASS (no PTX-JIT fallback, no other architectures)"""
+    out = subprocess.run(["cuobjdump", "-lelf", psba_b200.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, out
+
+
+@pytest.mark.parametrize("key", ["7", "9", "54", "54KD", "T21"])
+def test_product_reader_matches_oracle_reader(key):
+    c, p, cnp = dataset_paths(key)
+    a = psba_b200.read_sba(c, p, cnp)
+    b = oracle.read_sba(c, p, cnp, kind="restatement")
+    assert (a["m"], a["n"], a["o"]) == (b["m"], b["n"], b["o"])
+    for k in ("K", "initrot", "cams", "pts", "impts", "iidx", "jidx"):
+        assert np.array_equal(a[k], b[k]), k        # bit-exact: same text -> same doubles, same index lists
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("key", ["7", "54KD", "T21"])
+def test_product_reader_matches_reference_reader(key):
+    """against readInitialSBAEstimate + quat2vec + generate_idxs compiled from the reference sources"""
+    c, p, cnp = dataset_paths(key)
+    a = psba_b200.read_sba(c, p, cnp)
+    b = oracle.read_sba(c, p, cnp, kind="reference")
+    for k in ("K", "initrot", "cams", "pts", "impts", "iidx", "jidx"):
+        assert np.array_equal(a[k], b[k]), k
+    # the reference's dense tables say the same thing as our lists
+    blk = b["blk_idx"]
+    assert np.array_equal(blk[a["iidx"], a["jidx"]], np.arange(a["o"]))
+    assert int((blk >= 0).sum()) == a["o"]
+
+
+def test_varKD_equals_varK():
+    """the 17-column file carries five zero distortion coefficients; results must equal varK"""
+    a = psba_b200.read_sba(*dataset_paths("54"))
+    b = psba_b200.read_sba(*dataset_paths("54KD"))
+    for k in ("K", "initrot", "cams", "pts", "impts", "iidx", "jidx"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_seven_column_cameras_need_default_K():
+    c, p = data_file("7cams.txt"), data_file("7pts.txt")
+    with pytest.raises(RuntimeError):
+        psba_b200.read_sba(c, p, 6)
+    K = [851.57945, 330.24755, 262.19500, 1.00169, 0.0]          # SURVEY F6 (data/7camsvarK.txt)
+    a = psba_b200.read_sba(c, p, 6, Kdefault=K)
+    b = psba_b200.read_sba(*dataset_paths("7"))
+    assert np.allclose(a["K"], b["K"]) and np.array_equal(a["impts"], b["impts"])
+    assert np.allclose(a["initrot"], b["initrot"], atol=1e-6) and np.allclose(a["cams"], b["cams"], atol=1e-6)
+
+
+def test_reader_edge_cases(tmp_path):
+    cams = tmp_path / "c.txt"
+    pts = tmp_path / "p.txt"
+    # (the reference only recognises a camera-file comment at the start of the file or after another
+    #  comment: after a data record its fgetc sees the newline, readparams.cpp:203-219; the points loader
+    #  consumes the newline, :418, so comments may appear between point lines)
+    cams.write_text("# comment\n# another\n1000 0 0 1 0  1 0 0 0  0 0 5\n900 1 2 1 0  0.9 0.1 0 0  1 2 3\n")
+    # frames out of order in the second point; comment line in between
+    pts.write_text("0 0 1 2 0 10 20 1 30 40\n# c\n1 1 2 2 1 5 6 0 7 8\n")
+    a = psba_b200.read_sba(str(cams), str(pts), 11)
+    assert (a["m"], a["n"], a["o"]) == (2, 2, 4)
+    assert a["jidx"].tolist() == [0, 1, 0, 1]                 # generate_idxs: cameras ascending
+    assert a["impts"].tolist() == [[10, 20], [30, 40], [5, 6], [7, 8]]   # image points stay in file order
+    b = oracle.read_sba(str(cams), str(pts), 11)
+    for k in ("K", "initrot", "cams", "pts", "impts", "iidx", "jidx"):
+        assert np.array_equal(a[k], b[k]), k
+    q = a["initrot"][1]
+    assert abs(np.dot(q, q) - 1.0) < 1e-15 and q[0] > 0
+    # the product reader is line based and also accepts a comment between camera lines
+    cams.write_text("1000 0 0 1 0  1 0 0 0  0 0 5\n# mid\n900 1 2 1 0  0.9 0.1 0 0  1 2 3\n")
+    a2 = psba_b200.read_sba(str(cams), str(pts), 11)
+    assert np.array_equal(a2["K"], a["K"]) and np.array_equal(a2["initrot"], a["initrot"])
+    # wrong column count on the first line -> error code, no crash (readparams.cpp:189-192)
+    cams.write_text("1000 0 0 1 0  1 0 0 0  0 0\n")
+    with pytest.raises(RuntimeError):
+        psba_b200.read_sba(str(cams), str(pts), 11)
+    # frame index beyond the camera count (readparams.cpp:366-370)
+    cams.write_text("1000 0 0 1 0  1 0 0 0  0 0 5\n")
+    with pytest.raises(RuntimeError):
+        psba_b200.read_sba(str(cams), str(pts), 11)
+    # covariances are detected from the first line and skipped
+    cams.write_text("1000 0 0 1 0  1 0 0 0  0 0 5\n")
+    pts.write_text("0 0 1 1 0 10 20 1 0 0 1\n")
+    a = psba_b200.read_sba(str(cams), str(pts), 11)
+    assert a["impts"].tolist() == [[10, 20]] and a["o"] == 1
+
+
+def test_quat2vec_matches():
+    L = psba_b200.lib()
+    rng = np.random.default_rng(0)
+    for nin in (7, 12, 17):
+        x = rng.normal(size=nin)
+        a = np.zeros(nin - 1); b = np.zeros(nin - 1)
+        L.psba_quat2vec(psba_b200._d(x), nin, psba_b200._d(a), nin - 1)
+        oracle.lib().orc_quat2vec(oracle._d(x), nin, oracle._d(b), nin - 1)
+        assert np.array_equal(a, b)
+        q = x[nin - 7:nin - 3]
+        v = a[nin - 7:nin - 4]
+        assert abs(np.linalg.norm(v) ** 2 + (q[0] / np.linalg.norm(q)) ** 2 - 1) < 1e-14
+
+
+def test_synthetic_problem_through_the_text_reader(tmp_path):
+    """a text dump of the synthetic generator goes through the reader as a format check"""
+    from psba_b200 import synth
+    prob = synth.ring_problem(m=12, n=300, d=4, w=8, seed=7)
+    c, p = str(tmp_path / "c.txt"), str(tmp_path / "p.txt")
+    synth.write_sba_text(prob, c, p)
+    a = psba_b200.read_sba(c, p, 11)
+    assert np.array_equal(a["iidx"], prob["iidx"]) and np.array_equal(a["jidx"], prob["jidx"])
+    assert np.allclose(a["impts"], prob["impts"], rtol=0, atol=0)
+    assert np.allclose(a["pts"], prob["pts"], rtol=0, atol=0)
+    assert np.allclose(a["initrot"], prob["initrot"], atol=1e-15)
+    assert np.all(np.diff(a["jidx"].reshape(-1, 4), axis=1) > 0)
+
+
+def test_local_range_partitions_points_by_observation_count():
+    rng = np.random.default_rng(1)
+    n = 1000
+    d = rng.integers(1, 9, n)
+    iidx = np.repeat(np.arange(n, dtype=np.int32), d)
+    o = int(d.sum())
+    for R in (1, 2, 3, 8):
+        prev_p, prev_o, sizes = 0, 0, []
+        for r in range(R):
+            p0, p1, o0, o1 = psba_b200.local_range(n, o, iidx, r, R)
+            assert p0 == prev_p and o0 == prev_o and p1 >= p0
+            assert o1 - o0 == int(d[p0:p1].sum())
+            prev_p, prev_o = p1, o1
+            sizes.append(o1 - o0)
+        assert prev_p == n and prev_o == o
+        assert max(sizes) - min(sizes) <= 2 * 8          # balanced to within one point's track
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    monkeypatch.setattr(psba_b200, "_lib", None)
+    monkeypatch.setattr(psba_b200, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        psba_b200.lib()
+
+
+def test_product_never_imports_the_oracle():
+    """the oracle is test infrastructure: nothing under psba_b200/ may reference it"""
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "psba_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh", "Makefile")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"import oracle|from oracle|liboracle|psba_oracle\.h|orc_[a-z]", txt):
+                    bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
