@@ -2,74 +2,84 @@
 //
 // Camera j: fixed K = {fu,u0,v0,ar,s}, fixed unit quaternion q0, optimised {v(3), t(3)} with the
 // local rotation ql = (sqrt(1-|v|^2), v) and q = ql (x) q0 (CL_files/compute_exQT.cl:33-49).
-// Point in the camera frame: Xc = q X q* + t = M(q) X + t (compute_exQT.cl:51-65);
+// Point in the camera frame: Xc = q X q* + t (compute_exQT.cl:51-65);
 // projection x = (fu*Xc + s*Yc + u0*Zc)/Zc, y = (fu*ar*Yc + v0*Zc)/Zc (compute_exQT.cl:68-69);
 // residual e = measured - projected.
 //
-// Everything that depends on the camera only is hoisted into a per-camera cache entry
-// (k_cam_prep): M(q), t, K and the three matrices G_k = dM/dv_k, so that the per-observation
-// work is 9 FMA for Xc, 27 FMA for dXc/dv and a 2x3 projection derivative -- about a third of
-// the flops of the machine-generated Jacobian in compute_jacobiQT.cl:7-141, same quantity.
+// Everything that depends on the camera only is hoisted into a 24-double cache entry (k_cam_prep):
+// q (4), t (3), K (5) and the three quaternions D_k = d q / d v_k (12).  With b = X (x) q*,
+//   Xc        = vec(q (x) b) + t,
+//   dXc/dv_k  = 2 vec(D_k (x) b),        dXc/dX = M(q),
+// so an observation costs ~150 FP64 operations instead of the ~455 of the machine-generated
+// Jacobian in compute_jacobiQT.cl:7-141 (same quantity), and gathers 192 B of camera data.
 #pragma once
 #include "psba_internal.h"
 
-// camera-cache layout (doubles)
-#define CC_R 0     // 9  M(q) row-major
-#define CC_T 9     // 3  t
-#define CC_K 12    // 5  fu,u0,v0,ar,s
-#define CC_G 17    // 27 G_0,G_1,G_2 row-major
+// camera-cache layout (doubles); CAMC = 24
+#define CC_Q 0     // 4  total quaternion (s, x, y, z)
+#define CC_T 4     // 3  t
+#define CC_K 7     // 5  fu,u0,v0,ar,s
+#define CC_D 12    // 12 D_0, D_1, D_2 (each s,x,y,z)
 
-struct CamReg {            // camera cache entry held in registers
-    double R[9], t[3], K[5], G[27];
-};
+struct CamReg { double q[4], t[3], K[5], D[12]; };      // full entry (Jacobian)
+struct CamProj { double q[4], t[3], K[5]; };            // first 12 doubles (residual only)
 
+// entry -> registers from any 16-byte aligned source (global through the read-only path, or shared)
+template <bool GLOBAL>
 __device__ __forceinline__ void load_cam(const double *__restrict__ cc, CamReg &c)
 {
     const double2 *p = reinterpret_cast<const double2 *>(cc);
-    double buf[44];
+    double buf[24];
 #pragma unroll
-    for (int i = 0; i < 22; ++i) { double2 v = __ldg(p + i); buf[2 * i] = v.x; buf[2 * i + 1] = v.y; }
+    for (int i = 0; i < 12; ++i) { double2 v = GLOBAL ? __ldg(p + i) : p[i]; buf[2 * i] = v.x; buf[2 * i + 1] = v.y; }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) c.R[i] = buf[CC_R + i];
+    for (int i = 0; i < 4; ++i) c.q[i] = buf[CC_Q + i];
 #pragma unroll
     for (int i = 0; i < 3; ++i) c.t[i] = buf[CC_T + i];
 #pragma unroll
     for (int i = 0; i < 5; ++i) c.K[i] = buf[CC_K + i];
 #pragma unroll
-    for (int i = 0; i < 27; ++i) c.G[i] = buf[CC_G + i];
+    for (int i = 0; i < 12; ++i) c.D[i] = buf[CC_D + i];
 }
-
-// residual only needs R, t, K (17 doubles)
-struct CamProj { double R[9], t[3], K[5]; };
+template <bool GLOBAL>
 __device__ __forceinline__ void load_cam_proj(const double *__restrict__ cc, CamProj &c)
 {
     const double2 *p = reinterpret_cast<const double2 *>(cc);
-    double buf[18];
+    double buf[12];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { double2 v = __ldg(p + i); buf[2 * i] = v.x; buf[2 * i + 1] = v.y; }
+    for (int i = 0; i < 6; ++i) { double2 v = GLOBAL ? __ldg(p + i) : p[i]; buf[2 * i] = v.x; buf[2 * i + 1] = v.y; }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) c.R[i] = buf[i];
+    for (int i = 0; i < 4; ++i) c.q[i] = buf[CC_Q + i];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) c.t[i] = buf[9 + i];
+    for (int i = 0; i < 3; ++i) c.t[i] = buf[CC_T + i];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) c.K[i] = buf[12 + i];
+    for (int i = 0; i < 5; ++i) c.K[i] = buf[CC_K + i];
 }
 
+// b = X (x) q* = (w.X, sX + w x X);  Xc = vec(q (x) b) + t  (the two quaternion products of
+// compute_exQT.cl:51-65)
 template <class CAM>
-__device__ __forceinline__ void cam_transform(const CAM &c, double X, double Y, double Z, double &xc, double &yc, double &zc)
+__device__ __forceinline__ void cam_transform(const CAM &c, double X, double Y, double Z,
+                                              double &b0, double &b1, double &b2, double &b3,
+                                              double &xc, double &yc, double &zc)
 {
-    xc = c.R[0] * X + c.R[1] * Y + c.R[2] * Z + c.t[0];
-    yc = c.R[3] * X + c.R[4] * Y + c.R[5] * Z + c.t[1];
-    zc = c.R[6] * X + c.R[7] * Y + c.R[8] * Z + c.t[2];
+    const double s = c.q[0], w1 = c.q[1], w2 = c.q[2], w3 = c.q[3];
+    b0 = X * w1 + w2 * Y + w3 * Z;
+    b1 = s * X + w2 * Z - w3 * Y;
+    b2 = Y * s + w3 * X - Z * w1;
+    b3 = s * Z + Y * w1 - w2 * X;
+    xc = w1 * b0 + s * b1 - b2 * w3 + w2 * b3 + c.t[0];
+    yc = w2 * b0 + s * b2 - b3 * w1 + w3 * b1 + c.t[1];
+    zc = b0 * w3 + s * b3 - w2 * b1 + w1 * b2 + c.t[2];
 }
 
 // e = measured - projected
 template <class CAM>
 __device__ __forceinline__ void residual(const CAM &c, double X, double Y, double Z, double mx, double my, double &e0, double &e1)
 {
-    double xc, yc, zc;
-    cam_transform(c, X, Y, Z, xc, yc, zc);
-    double iz = 1.0 / zc;
+    double b0, b1, b2, b3, xc, yc, zc;
+    cam_transform(c, X, Y, Z, b0, b1, b2, b3, xc, yc, zc);
+    const double iz = 1.0 / zc;
     e0 = mx - (c.K[0] * xc + c.K[4] * yc + c.K[1] * zc) * iz;
     e1 = my - (c.K[0] * c.K[3] * yc + c.K[2] * zc) * iz;
 }
@@ -78,8 +88,8 @@ __device__ __forceinline__ void residual(const CAM &c, double X, double Y, doubl
 __device__ __forceinline__ void residual_jac(const CamReg &c, double X, double Y, double Z, double mx, double my,
                                              double &e0, double &e1, double *A, double *B)
 {
-    double xc, yc, zc;
-    cam_transform(c, X, Y, Z, xc, yc, zc);
+    double b0, b1, b2, b3, xc, yc, zc;
+    cam_transform(c, X, Y, Z, b0, b1, b2, b3, xc, yc, zc);
     const double iz = 1.0 / zc;
     const double fa = c.K[0] * c.K[3];
     e0 = mx - (c.K[0] * xc + c.K[4] * yc + c.K[1] * zc) * iz;
@@ -89,20 +99,27 @@ __device__ __forceinline__ void residual_jac(const CamReg &c, double X, double Y
     const double p11 = fa * iz, p12 = -(fa * yc) * iz * iz;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const double *G = c.G + 9 * k;
-        double d0 = G[0] * X + G[1] * Y + G[2] * Z;
-        double d1 = G[3] * X + G[4] * Y + G[5] * Z;
-        double d2 = G[6] * X + G[7] * Y + G[8] * Z;
+        // dXc/dv_k = 2 vec(D_k (x) b)
+        const double ds = c.D[4 * k], dx = c.D[4 * k + 1], dy = c.D[4 * k + 2], dz = c.D[4 * k + 3];
+        const double d0 = 2.0 * (ds * b1 + b0 * dx + dy * b3 - dz * b2);
+        const double d1 = 2.0 * (ds * b2 + b0 * dy + dz * b1 - dx * b3);
+        const double d2 = 2.0 * (ds * b3 + b0 * dz + dx * b2 - dy * b1);
         A[k] = p00 * d0 + p01 * d1 + p02 * d2;
         A[6 + k] = p11 * d1 + p12 * d2;
     }
     A[3] = p00; A[4] = p01; A[5] = p02;
     A[9] = 0.0; A[10] = p11; A[11] = p12;
-#pragma unroll
-    for (int cidx = 0; cidx < 3; ++cidx) {
-        B[cidx] = p00 * c.R[cidx] + p01 * c.R[3 + cidx] + p02 * c.R[6 + cidx];
-        B[3 + cidx] = p11 * c.R[3 + cidx] + p12 * c.R[6 + cidx];
-    }
+    // B = P * M(q)  (general, non-normalised form as compute_jacobiQT.cl:117-140)
+    const double s = c.q[0], x = c.q[1], y = c.q[2], z = c.q[3];
+    const double m00 = s * s + x * x - y * y - z * z, m01 = 2 * (x * y - s * z), m02 = 2 * (x * z + s * y);
+    const double m10 = 2 * (x * y + s * z), m11 = s * s - x * x + y * y - z * z, m12 = 2 * (y * z - s * x);
+    const double m20 = 2 * (x * z - s * y), m21 = 2 * (y * z + s * x), m22 = s * s - x * x - y * y + z * z;
+    B[0] = p00 * m00 + p01 * m10 + p02 * m20;
+    B[1] = p00 * m01 + p01 * m11 + p02 * m21;
+    B[2] = p00 * m02 + p01 * m12 + p02 * m22;
+    B[3] = p11 * m10 + p12 * m20;
+    B[4] = p11 * m11 + p12 * m21;
+    B[5] = p11 * m12 + p12 * m22;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -30,25 +30,30 @@ __global__ void k_newcams(int N, const double *__restrict__ cams, const double *
     if (threadIdx.x == 0) { scal2[0] = s0[0]; scal2[1] = s1[0]; }
 }
 
-// CTA = one chunk of whole points (same chunks as k_lin_points).
-//  phase A (thread per observation): t = W_ij^T dpa_j -> shared
+// CTA (128 threads) = one chunk of whole points (same chunks as k_lin_points).
+//  phase A: the wave's W tile (contiguous in HBM) is copied to shared memory with coalesced 16-byte
+//           loads; thread per observation: t = W_ij^T dpa_j -> shared
 //  phase B (owner thread per point): eb = gb - sum_j t (ascending camera, compute_eb.cl:27-37),
 //           dpb = Vinv eb (compute_dpb.cl:23-32), candidate point, |dpb|^2, dpb.(mu dpb + gb)
-//  phase C (thread per observation): residual of the candidate -> ||e||^2
+//  phase C: the candidate cameras' projection entries (96 B each) are staged the same way; thread per
+//           observation: residual of the candidate -> ||e||^2
 // EVAL=false stops after phase B (trust region: the step is formed on the host side first).
+#define PROJ_LD 14         // doubles per staged projection entry (12 + pad: conflict-free LDS.128)
 template <bool EVAL>
-__global__ void __launch_bounds__(PT_CTA) k_backsub(const int *__restrict__ ptchunk, const int *__restrict__ pt_ptr,
-                                                   const int *__restrict__ iidx, const int *__restrict__ jidx,
-                                                   const double *__restrict__ impts, const double *__restrict__ W,
-                                                   const double *__restrict__ Vinv, const double *__restrict__ gb,
-                                                   const double *__restrict__ dpa, const double *__restrict__ pts,
-                                                   const double *__restrict__ newcache, double mu,
-                                                   double *__restrict__ eb, double *__restrict__ dpb, double *__restrict__ newpts,
-                                                   double *__restrict__ part)
+__global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ ptchunk, const int *__restrict__ pt_ptr,
+                                                      const int *__restrict__ iidx, const int *__restrict__ jidx,
+                                                      const double *__restrict__ impts, const double *__restrict__ W,
+                                                      const double *__restrict__ Vinv, const double *__restrict__ gb,
+                                                      const double *__restrict__ dpa, const double *__restrict__ pts,
+                                                      const double *__restrict__ newcache, double mu,
+                                                      double *__restrict__ eb, double *__restrict__ dpb, double *__restrict__ newpts,
+                                                      double *__restrict__ part)
 {
+    __shared__ __align__(16) double stage[PT_CTA * 18];      // W tile, then the projection entries (128*14 <= 128*18)
     __shared__ double sh[3][PT_CTA];
     __shared__ double shx[3][PT_CTA];
-    __shared__ double red[3][8];
+    __shared__ double red[3][PT_CTA / 32];
+    __shared__ int sj[PT_CTA];
     const int tid = threadIdx.x;
     const int p0 = ptchunk[blockIdx.x], p1 = ptchunk[blockIdx.x + 1];
     const int o0 = pt_ptr[p0], o1 = pt_ptr[p1];
@@ -59,15 +64,24 @@ __global__ void __launch_bounds__(PT_CTA) k_backsub(const int *__restrict__ ptch
 
     for (int base = o0; base < o1; base += PT_CTA) {
         const int k = base + tid;
+        const int cnt = min(PT_CTA, o1 - base);
+        {
+            const double2 *wg = reinterpret_cast<const double2 *>(W + (size_t)base * 18);
+            double2 *ws = reinterpret_cast<double2 *>(stage);
+            for (int p = tid; p < cnt * 9; p += PT_CTA) ws[p] = __ldg(wg + p);
+        }
+        __syncthreads();
         if (k < o1) {
-            const double2 *wp = reinterpret_cast<const double2 *>(W + (size_t)k * 18);
-            const double *d = dpa + jidx[k] * 6;
-            double w[18];
+            const double2 *wp = reinterpret_cast<const double2 *>(stage + tid * 18);
+            const double2 *dq = reinterpret_cast<const double2 *>(dpa + jidx[k] * 6);
+            double w[18], d[6];
 #pragma unroll
-            for (int q = 0; q < 9; ++q) { double2 w2 = __ldg(wp + q); w[2 * q] = w2.x; w[2 * q + 1] = w2.y; }
+            for (int q = 0; q < 9; ++q) { double2 w2 = wp[q]; w[2 * q] = w2.x; w[2 * q + 1] = w2.y; }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { double2 d2 = __ldg(dq + q); d[2 * q] = d2.x; d[2 * q + 1] = d2.y; }
             double t0 = 0, t1 = 0, t2 = 0;
 #pragma unroll
-            for (int r = 0; r < 6; ++r) { const double dr = __ldg(d + r); t0 += w[r * 3] * dr; t1 += w[r * 3 + 1] * dr; t2 += w[r * 3 + 2] * dr; }
+            for (int r = 0; r < 6; ++r) { t0 += w[r * 3] * d[r]; t1 += w[r * 3 + 1] * d[r]; t2 += w[r * 3 + 2] * d[r]; }
             sh[0][tid] = t0; sh[1][tid] = t1; sh[2][tid] = t2;
         }
         __syncthreads();
@@ -98,12 +112,21 @@ __global__ void __launch_bounds__(PT_CTA) k_backsub(const int *__restrict__ ptch
         }
     }
     if (!EVAL) return;
-    __syncthreads();
     for (int base = o0; base < o1; base += PT_CTA) {
         const int k = base + tid;
+        const int cnt = min(PT_CTA, o1 - base);
+        __syncthreads();                                   // shx written / previous wave's stage consumed
+        sj[tid] = k < o1 ? jidx[k] : 0;
+        __syncthreads();
+        for (int p = tid; p < cnt * 6; p += PT_CTA) {      // 6 x 16 B = q, t, K of the candidate camera
+            const int ob = p / 6, piece = p - ob * 6;
+            const double2 v = __ldg(reinterpret_cast<const double2 *>(newcache + (size_t)sj[ob] * CAMC) + piece);
+            *reinterpret_cast<double2 *>(stage + ob * PROJ_LD + piece * 2) = v;
+        }
+        __syncthreads();
         if (k < o1) {
             CamProj cam;
-            load_cam_proj(newcache + (size_t)jidx[k] * CAMC, cam);
+            load_cam_proj<false>(stage + tid * PROJ_LD, cam);
             const int lp = iidx[k] - p0;
             double2 mm = __ldg(reinterpret_cast<const double2 *>(impts) + k);
             double e0, e1;

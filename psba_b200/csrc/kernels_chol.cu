@@ -291,52 +291,70 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
 #pragma unroll
             for (int q = 0; q < 3; ++q) { d[p][q] -= acc[p][q]; if (upd) a[p][q] -= acc2[p][q]; }
     }
-    // ---- column sweep over the stacked panel; B2 collects the factor rows of this CTA
+    // ---- column sweep over the stacked panel; B2 collects the factor rows of this CTA.
+    // Software-pipelined: step j first updates only the NEXT column (the one the next pivot needs) and
+    // publishes it; the bulk of step j's rank-1 update (the thread's other two columns) is executed
+    // after the next barrier, where it overlaps the LDS -> rsqrt -> scale latency chain of step j+1.
     bool bad = false;
     double yk[3] = {0, 0, 0};
-    const double *pli = colbuf[0] + (diagcta ? 0 : TS) + tr * 6, *plc = colbuf[0] + tc * 3;
+    const double *pli = colbuf[0] + (diagcta ? 0 : TS) + tr * 6, *pld = colbuf[0] + tr * 6, *plc = colbuf[0] + tc * 3;
     double *pout = B2 + (tr * 6) * LDT;
     constexpr int CBS = 2 * TS + 2;
-#pragma unroll 1
-    const int warp_tc_max = (tid | 31) / 8;                 // last column triple owned by this warp
-    for (int jb = 0; jb < TS / 3; ++jb) {
-        const bool owner = tc == jb;
-        const bool live = warp_tc_max >= jb;                // warp-uniform: every entry of a retired warp is dead
+    double lrow_p[6], ld_p[6], lc_p[3], lb_p = 0.0;            // scaled column of the previous step (deferred bulk)
 #pragma unroll
-        for (int jq = 0; jq < 3; ++jq) {
-            const int j = jb * 3 + jq, par = j & 1;
-            double *cb = colbuf[par];
-            if (owner) {
+    for (int p = 0; p < 6; ++p) { lrow_p[p] = 0.0; ld_p[p] = 0.0; }
 #pragma unroll
-                for (int p = 0; p < 6; ++p) { cb[tr * 6 + p] = d[p][jq]; cb[TS + tr * 6 + p] = a[p][jq]; }
-                if (tr == 0) cb[2 * TS] = bq[jq];
-            }
-            __syncthreads();
-            if (!live) continue;
-            const double piv = cb[j];
-            bad |= !(piv > 0.0 && piv < 1e300);
-            const double rs = rsqrt(piv);
-            double lrow[6], ld[6], lc[3];
-            // lrow: this CTA's own factor rows (L_KK rows for the diagonal CTA, L_IK rows otherwise);
-            // ld: always the D rows (they keep being eliminated so that the pivots stay correct)
+    for (int q = 0; q < 3; ++q) lc_p[q] = 0.0;
+    if (tc == 0) {                                             // publish column 0
 #pragma unroll
-            for (int p = 0; p < 6; ++p) { ld[p] = cb[tr * 6 + p] * rs; lrow[p] = pli[par * CBS + p] * rs; }
-#pragma unroll
-            for (int q = 0; q < 3; ++q) lc[q] = plc[par * CBS + q] * rs;
-            const double lb = cb[2 * TS] * rs;
-            if (owner) {
-#pragma unroll
-                for (int p = 0; p < 6; ++p) pout[p * LDT + j] = lrow[p];
-                if (tr == 0) yk[jq] = lb;
-            }
-#pragma unroll
-            for (int p = 0; p < 6; ++p)
-#pragma unroll
-                for (int q = 0; q < 3; ++q) { d[p][q] -= ld[p] * lc[q]; a[p][q] -= lrow[p] * lc[q]; }
-#pragma unroll
-            for (int q = 0; q < 3; ++q) bq[q] -= lb * lc[q];
-        }
+        for (int p = 0; p < 6; ++p) { colbuf[0][tr * 6 + p] = d[p][0]; colbuf[0][TS + tr * 6 + p] = a[p][0]; }
+        if (tr == 0) colbuf[0][2 * TS] = bq[0];
     }
+#define SWEEP_STEP(JQ)                                                                                         \
+    {                                                                                                          \
+        constexpr int QN = (JQ + 1) % 3;          /* column (inside a triple) that the next pivot lives in */  \
+        constexpr int QP = JQ;                    /* column that was critical in the previous step */          \
+        const int j = jb * 3 + JQ, par = j & 1;                                                                \
+        __syncthreads();                                                                                       \
+        const double piv = colbuf[par][j];                                                                     \
+        bad |= !(piv > 0.0 && piv < 1e300);                                                                    \
+        const double rs = rsqrt(piv);                                                                          \
+        double lrow[6], ld[6], lc[3];                                                                          \
+        _Pragma("unroll") for (int p = 0; p < 6; ++p) { ld[p] = pld[par * CBS + p] * rs; lrow[p] = pli[par * CBS + p] * rs; } \
+        _Pragma("unroll") for (int q = 0; q < 3; ++q) lc[q] = plc[par * CBS + q] * rs;                         \
+        const double lb = colbuf[par][2 * TS] * rs;                                                            \
+        /* deferred bulk of the previous step on the next-pivot column (independent of this step's rsqrt chain) */ \
+        _Pragma("unroll") for (int p = 0; p < 6; ++p) { d[p][QN] -= ld_p[p] * lc_p[QN]; a[p][QN] -= lrow_p[p] * lc_p[QN]; } \
+        bq[QN] -= lb_p * lc_p[QN];                                                                             \
+        /* critical part of this step: the next column, then publish it */                                     \
+        _Pragma("unroll") for (int p = 0; p < 6; ++p) { d[p][QN] -= ld[p] * lc[QN]; a[p][QN] -= lrow[p] * lc[QN]; } \
+        bq[QN] -= lb * lc[QN];                                                                                 \
+        if (tc == (JQ == 2 ? jb + 1 : jb)) {                                                                   \
+            double *cbn = colbuf[par ^ 1];                                                                     \
+            _Pragma("unroll") for (int p = 0; p < 6; ++p) { cbn[tr * 6 + p] = d[p][QN]; cbn[TS + tr * 6 + p] = a[p][QN]; } \
+            if (tr == 0) cbn[2 * TS] = bq[QN];                                                                 \
+        }                                                                                                      \
+        /* rest of the previous step's bulk: the third column (neither QP nor QN) */                           \
+        {                                                                                                      \
+            constexpr int Q3 = 3 - QP - QN;                                                                    \
+            _Pragma("unroll") for (int p = 0; p < 6; ++p) { d[p][Q3] -= ld_p[p] * lc_p[Q3]; a[p][Q3] -= lrow_p[p] * lc_p[Q3]; } \
+            bq[Q3] -= lb_p * lc_p[Q3];                                                                         \
+        }                                                                                                      \
+        if (tc == jb) {                                                                                        \
+            _Pragma("unroll") for (int p = 0; p < 6; ++p) pout[p * LDT + j] = lrow[p];                         \
+            if (tr == 0) yk[JQ] = lb;                                                                          \
+        }                                                                                                      \
+        _Pragma("unroll") for (int p = 0; p < 6; ++p) { ld_p[p] = ld[p]; lrow_p[p] = lrow[p]; }                \
+        _Pragma("unroll") for (int q = 0; q < 3; ++q) lc_p[q] = lc[q];                                         \
+        lb_p = lb;                                                                                             \
+    }
+#pragma unroll 1
+    for (int jb = 0; jb < TS / 3; ++jb) {
+        SWEEP_STEP(0)
+        SWEEP_STEP(1)
+        SWEEP_STEP(2)
+    }
+#undef SWEEP_STEP
     if (__syncthreads_or(bad)) { if (tid == 0) *status = 1; return; }
     // y_K (held by the threads of grid row 0) -> shared
     double *ysh = colbuf[0];

@@ -5,12 +5,18 @@
 // Replaces kern_compute_exQT (CL_files/compute_exQT.cl:18-71), kern_compute_jacobiQT
 // (compute_jacobiQT.cl:7-141), kern_compute_U/V/Wblks/g (compute_U.cl:5-35, compute_V.cl:6-38,
 // compute_Wblks.cl:7-34, compute_g.cl:6-60) and kern_compute_Jmultiply (compute_Jmultiply.cl:6-52).
-// The Jacobian never reaches HBM: both passes recompute it from 17+27 cached doubles per camera.
+// The Jacobian never reaches HBM: both passes recompute it from a 192-byte cache entry per camera.
 // All cross-thread sums have a fixed order (no atomics) => bit-reproducible run to run.
+//
+// Memory access: per-observation gathers (camera entry 192 B, W block 144 B) are turned into
+// coalesced 16-byte-per-lane transfers staged through shared memory: a warp moves 512 contiguous
+// bytes per instruction instead of 32 scattered sectors (ncu r01: 23 sectors/request before).
 #include "dev_math.cuh"
 
+#define CAM_LD 26          // doubles per staged camera entry in shared memory (24 + pad: conflict-free LDS.128)
+
 // ------------------------------------------------------------------------------------------------
-// per-camera cache: M(q), t, K, G_k = dM/dv_k
+// per-camera cache: q = ql (x) q0, t, K, D_k = d q / d v_k
 __global__ void k_cam_prep(int m, const double *__restrict__ K, const double *__restrict__ initcams,
                            const double *__restrict__ cams, double *__restrict__ cache)
 {
@@ -19,40 +25,26 @@ __global__ void k_cam_prep(int m, const double *__restrict__ K, const double *__
     const double s0 = initcams[j * 4], a1 = initcams[j * 4 + 1], a2 = initcams[j * 4 + 2], a3 = initcams[j * 4 + 3];
     const double v1 = cams[j * 6], v2 = cams[j * 6 + 1], v3 = cams[j * 6 + 2];
     const double sl = sqrt(1 - v1 * v1 - v2 * v2 - v3 * v3);
-    // q = ql (x) q0, same operation order as compute_exQT.cl:46-49
-    const double s = sl * s0 - (a1 * v1 + a2 * v2 + a3 * v3);
-    const double x = s0 * v1 + sl * a1 + a3 * v2 - a2 * v3;
-    const double y = s0 * v2 + sl * a2 + a1 * v3 - a3 * v1;
-    const double z = s0 * v3 + sl * a3 + a2 * v1 - a1 * v2;
     double *c = cache + (size_t)j * CAMC;
-    c[CC_R + 0] = s * s + x * x - y * y - z * z; c[CC_R + 1] = 2 * (x * y - s * z); c[CC_R + 2] = 2 * (x * z + s * y);
-    c[CC_R + 3] = 2 * (x * y + s * z); c[CC_R + 4] = s * s - x * x + y * y - z * z; c[CC_R + 5] = 2 * (y * z - s * x);
-    c[CC_R + 6] = 2 * (x * z - s * y); c[CC_R + 7] = 2 * (y * z + s * x); c[CC_R + 8] = s * s - x * x - y * y + z * z;
+    // q = ql (x) q0, same operation order as compute_exQT.cl:46-49
+    c[CC_Q + 0] = sl * s0 - (a1 * v1 + a2 * v2 + a3 * v3);
+    c[CC_Q + 1] = s0 * v1 + sl * a1 + a3 * v2 - a2 * v3;
+    c[CC_Q + 2] = s0 * v2 + sl * a2 + a1 * v3 - a3 * v1;
+    c[CC_Q + 3] = s0 * v3 + sl * a3 + a2 * v1 - a1 * v2;
     c[CC_T + 0] = cams[j * 6 + 3]; c[CC_T + 1] = cams[j * 6 + 4]; c[CC_T + 2] = cams[j * 6 + 5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) c[CC_K + k] = K[j * 5 + k];
     const double vv[3] = {v1, v2, v3};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        // d ql / d v_k = (-v_k/sl, e_k);  dq = dql (x) q0
+        // d ql / d v_k = (-v_k/sl, e_k);  D_k = dql (x) q0
         const double ds_l = -vv[k] / sl;
         const double e1 = (k == 0), e2 = (k == 1), e3 = (k == 2);
-        const double ds = ds_l * s0 - (a1 * e1 + a2 * e2 + a3 * e3);
-        const double dx = s0 * e1 + ds_l * a1 + a3 * e2 - a2 * e3;
-        const double dy = s0 * e2 + ds_l * a2 + a1 * e3 - a3 * e1;
-        const double dz = s0 * e3 + ds_l * a3 + a2 * e1 - a1 * e2;
-        double *G = c + CC_G + 9 * k;
-        G[0] = 2 * (s * ds + x * dx - y * dy - z * dz);
-        G[1] = 2 * (dx * y + x * dy - ds * z - s * dz);
-        G[2] = 2 * (dx * z + x * dz + ds * y + s * dy);
-        G[3] = 2 * (dx * y + x * dy + ds * z + s * dz);
-        G[4] = 2 * (s * ds - x * dx + y * dy - z * dz);
-        G[5] = 2 * (dy * z + y * dz - ds * x - s * dx);
-        G[6] = 2 * (dx * z + x * dz - ds * y - s * dy);
-        G[7] = 2 * (dy * z + y * dz + ds * x + s * dx);
-        G[8] = 2 * (s * ds - x * dx - y * dy + z * dz);
+        c[CC_D + 4 * k + 0] = ds_l * s0 - (a1 * e1 + a2 * e2 + a3 * e3);
+        c[CC_D + 4 * k + 1] = s0 * e1 + ds_l * a1 + a3 * e2 - a2 * e3;
+        c[CC_D + 4 * k + 2] = s0 * e2 + ds_l * a2 + a1 * e3 - a3 * e1;
+        c[CC_D + 4 * k + 3] = s0 * e3 + ds_l * a3 + a2 * e1 - a1 * e2;
     }
-    for (int k = 44; k < CAMC; ++k) c[k] = 0.0;
 }
 
 void psba_launch_cam_prep(psba_ctx *c, int set)
@@ -92,7 +84,7 @@ __global__ void __launch_bounds__(256) k_cost(int o, const int *__restrict__ iid
     double e2 = 0.0;
     if (k < o) {
         CamProj cam;
-        load_cam_proj(cache + (size_t)jidx[k] * CAMC, cam);
+        load_cam_proj<true>(cache + (size_t)jidx[k] * CAMC, cam);
         const double *X = pts + (size_t)iidx[k] * 3;
         double2 mm = __ldg(reinterpret_cast<const double2 *>(impts) + k);
         double e0, e1;
@@ -132,18 +124,24 @@ double psba_launch_cost(psba_ctx *c, int set, double *ex_dev)
 }
 
 // ------------------------------------------------------------------------------------------------
-// point-major linearisation pass.  CTA = one chunk of whole points (<= PT_CTA observations per
-// wave).  Thread k: observation -> e, A, B in registers; W = c*A^T B written straight to HBM
-// (144 B per observation, the only per-observation product that persists); B^T B (6) and B^T e (3)
-// go through shared memory to the point's owner thread, which sums them in ascending camera
-// order (the order of compute_V.cl:24-31 / compute_g.cl:43-54).
-__global__ void __launch_bounds__(PT_CTA, 2) k_lin_points(const int *__restrict__ ptchunk, const int *__restrict__ pt_ptr,
-                                                      const int *__restrict__ iidx, const int *__restrict__ jidx,
-                                                      const double *__restrict__ impts, const double *__restrict__ cache,
-                                                      const double *__restrict__ pts, double coeff, double coeff_g,
-                                                      double *__restrict__ W, double *__restrict__ V, double *__restrict__ gb)
+// point-major linearisation pass.  CTA (128 threads) = one chunk of whole points (<= 128
+// observations per wave).
+//   1. the wave's camera entries are copied global -> shared cooperatively (12 x 16 B pieces per
+//      entry, consecutive lanes take consecutive pieces: coalesced);
+//   2. thread k: observation -> e, A, B in registers, W = c * A^T B into a shared tile;
+//      B^T B (6) and B^T e (3) go to shared for the point's owner thread, which sums them in
+//      ascending camera order (the order of compute_V.cl:24-31 / compute_g.cl:43-54);
+//   3. the W tile (128 x 144 B, contiguous in HBM because observations are point-major) is written
+//      with fully coalesced 16-byte stores.
+__global__ void __launch_bounds__(PT_CTA, 4) k_lin_points(const int *__restrict__ ptchunk, const int *__restrict__ pt_ptr,
+                                                         const int *__restrict__ iidx, const int *__restrict__ jidx,
+                                                         const double *__restrict__ impts, const double *__restrict__ cache,
+                                                         const double *__restrict__ pts, double coeff, double coeff_g,
+                                                         double *__restrict__ W, double *__restrict__ V, double *__restrict__ gb)
 {
+    __shared__ __align__(16) double stage[PT_CTA * CAM_LD];      // camera entries, then the W tile (128*18 <= 128*26)
     __shared__ double sh[9][PT_CTA];
+    __shared__ int sj[PT_CTA];
     const int tid = threadIdx.x;
     const int p0 = ptchunk[blockIdx.x], p1 = ptchunk[blockIdx.x + 1];
     const int o0 = pt_ptr[p0], o1 = pt_ptr[p1];
@@ -156,21 +154,28 @@ __global__ void __launch_bounds__(PT_CTA, 2) k_lin_points(const int *__restrict_
 
     for (int base = o0; base < o1; base += PT_CTA) {
         const int k = base + tid;
+        const int cnt = min(PT_CTA, o1 - base);
+        sj[tid] = k < o1 ? jidx[k] : 0;
+        __syncthreads();
+        // 1. stage camera entries: piece p = (observation p/12, 16-byte part p%12)
+        for (int p = tid; p < cnt * 12; p += PT_CTA) {
+            const int ob = p / 12, part = p - ob * 12;
+            const double2 v = __ldg(reinterpret_cast<const double2 *>(cache + (size_t)sj[ob] * CAMC) + part);
+            *reinterpret_cast<double2 *>(stage + ob * CAM_LD + part * 2) = v;
+        }
+        __syncthreads();
+        double w[18];
         if (k < o1) {
             CamReg cam;
-            load_cam(cache + (size_t)jidx[k] * CAMC, cam);
+            load_cam<false>(stage + tid * CAM_LD, cam);
             const double *X = pts + (size_t)iidx[k] * 3;
             double2 mm = __ldg(reinterpret_cast<const double2 *>(impts) + k);
             double e0, e1, A[12], B[6];
             residual_jac(cam, __ldg(X), __ldg(X + 1), __ldg(X + 2), mm.x, mm.y, e0, e1, A, B);
-            double2 *Wk = reinterpret_cast<double2 *>(W + (size_t)k * 18);
-            double w[18];
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) w[r * 3 + cc] = coeff * (A[r] * B[cc] + A[6 + r] * B[3 + cc]);
-#pragma unroll
-            for (int q = 0; q < 9; ++q) Wk[q] = make_double2(w[2 * q], w[2 * q + 1]);
             sh[0][tid] = B[0] * B[0] + B[3] * B[3];
             sh[1][tid] = B[0] * B[1] + B[3] * B[4];
             sh[2][tid] = B[0] * B[2] + B[3] * B[5];
@@ -181,13 +186,25 @@ __global__ void __launch_bounds__(PT_CTA, 2) k_lin_points(const int *__restrict_
             sh[7][tid] = B[1] * e0 + B[4] * e1;
             sh[8][tid] = B[2] * e0 + B[5] * e1;
         }
-        __syncthreads();
+        __syncthreads();                               // every thread has consumed its camera entry
+        if (k < o1) {
+            double2 *ws = reinterpret_cast<double2 *>(stage + tid * 18);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) ws[q] = make_double2(w[2 * q], w[2 * q + 1]);
+        }
         if (tid < np) {
             const int a = max(my_a, base), b = min(my_b, base + PT_CTA);
             for (int q = a; q < b; ++q) {
 #pragma unroll
                 for (int v = 0; v < 9; ++v) acc[v] += sh[v][q - base];
             }
+        }
+        __syncthreads();
+        // 3. coalesced store of the W tile
+        {
+            double2 *wg = reinterpret_cast<double2 *>(W + (size_t)base * 18);
+            const double2 *ws = reinterpret_cast<const double2 *>(stage);
+            for (int p = tid; p < cnt * 9; p += PT_CTA) wg[p] = ws[p];
         }
         __syncthreads();
     }
@@ -204,17 +221,17 @@ __global__ void __launch_bounds__(PT_CTA, 2) k_lin_points(const int *__restrict_
 // The camera cache entry is uniform per CTA; points and measurements are gathered (L2-resident).
 // Each thread accumulates A^T A (21 upper entries) and A^T e (6) over its observations, then one
 // deterministic block reduction per chunk writes 27 partials.
-__global__ void __launch_bounds__(CAM_CTA) k_lin_cams(const int *__restrict__ cchunk_cam, const int *__restrict__ cchunk_beg,
-                                                     const int *__restrict__ cchunk_end, const int *__restrict__ cam_obs,
-                                                     const int *__restrict__ iidx, const double *__restrict__ impts,
-                                                     const double *__restrict__ cache, const double *__restrict__ pts,
-                                                     double *__restrict__ part)
+__global__ void __launch_bounds__(CAM_CTA, 4) k_lin_cams(const int *__restrict__ cchunk_cam, const int *__restrict__ cchunk_beg,
+                                                        const int *__restrict__ cchunk_end, const int *__restrict__ cam_obs,
+                                                        const int *__restrict__ iidx, const double *__restrict__ impts,
+                                                        const double *__restrict__ cache, const double *__restrict__ pts,
+                                                        double *__restrict__ part)
 {
     __shared__ double sh[16 * (CAM_CTA + 4)];
     const int ch = blockIdx.x;
     const int beg = cchunk_beg[ch], end = cchunk_end[ch];
     CamReg cam;
-    load_cam(cache + (size_t)cchunk_cam[ch] * CAMC, cam);
+    load_cam<true>(cache + (size_t)cchunk_cam[ch] * CAMC, cam);
     double acc[27];
 #pragma unroll
     for (int q = 0; q < 27; ++q) acc[q] = 0.0;
@@ -286,7 +303,7 @@ __global__ void k_jac_materialize(int o, const int *__restrict__ iidx, const int
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= o) return;
     CamReg cam;
-    load_cam(cache + (size_t)jidx[k] * CAMC, cam);
+    load_cam<true>(cache + (size_t)jidx[k] * CAMC, cam);
     const double *X = pts + (size_t)iidx[k] * 3;
     double e0, e1, A[12], B[6];
     residual_jac(cam, X[0], X[1], X[2], impts[2 * k], impts[2 * k + 1], e0, e1, A, B);
@@ -319,7 +336,7 @@ __global__ void __launch_bounds__(256) k_Jdot(int o, int N, const int *__restric
     if (k < o) {
         const int i = iidx[k], j = jidx[k];
         CamReg cam;
-        load_cam(cache + (size_t)j * CAMC, cam);
+        load_cam<true>(cache + (size_t)j * CAMC, cam);
         const double *X = pts + (size_t)i * 3;
         double e0, e1, A[12], B[6];
         residual_jac(cam, __ldg(X), __ldg(X + 1), __ldg(X + 2), 0.0, 0.0, e0, e1, A, B);

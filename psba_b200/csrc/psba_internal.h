@@ -17,9 +17,9 @@
 #define PSBA_CNP 6
 #define PSBA_PNP 3
 #define PSBA_MNP 2
-#define CAMC 48            // doubles per camera-cache entry (44 used, padded to 384 B)
+#define CAMC 24            // doubles per camera-cache entry: q(4) t(3) K(5) dq/dv(12) = 192 B
 #define TS 48              // tile size of the camera system (8 cameras)
-#define PT_CTA 256         // observations per point-major CTA wave
+#define PT_CTA 128         // observations per point-major CTA wave
 #define CAM_CTA 128        // threads per camera-major CTA
 #define CAM_OPT 4          // observations per thread in the camera-major pass
 #define PAIR_CTA 128       // threads per pair-pass CTA
