@@ -24,7 +24,7 @@
 
 #define LDT (TS + 1)            // padded leading dimension in shared memory
 #define TILE_SM (TS * LDT)      // doubles per shared tile
-#define CHOL_SMEM (3 * TILE_SM * sizeof(double))
+#define CHOL_SMEM ((2 * TILE_SM + TS * (TS + 2)) * sizeof(double))   // two staged tiles + the transposed output tile
 
 // ---------------------------------------------------------------------------------------------
 void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int>> &pairs)
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
                                                     double *__restrict__ ywork, int *__restrict__ status)
 {
     extern __shared__ double smem[];
-    __shared__ double colbuf[2][2 * TS + 2];
+    __shared__ __align__(16) double colbuf[2][2 * TS + 2];
     if (*status != 0) return;
     const int tid = threadIdx.x, tr = tid % 8, tc = tid / 8;
     double *B0 = smem, *B1 = smem + TILE_SM, *B2 = smem + 2 * TILE_SM;
@@ -298,16 +298,18 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
     bool bad = false;
     double yk[3] = {0, 0, 0};
     const double *pli = colbuf[0] + (diagcta ? 0 : TS) + tr * 6, *pld = colbuf[0] + tr * 6, *plc = colbuf[0] + tc * 3;
-    double *pout = B2 + (tr * 6) * LDT;
+    constexpr int LDO = TS + 2;                                // B2 holds the factor rows TRANSPOSED: B2[j * LDO + row]
+    double *pout = B2 + tr * 6;
     constexpr int CBS = 2 * TS + 2;
     double lrow_p[6], ld_p[6], lc_p[3], lb_p = 0.0;            // scaled column of the previous step (deferred bulk)
 #pragma unroll
     for (int p = 0; p < 6; ++p) { lrow_p[p] = 0.0; ld_p[p] = 0.0; }
 #pragma unroll
     for (int q = 0; q < 3; ++q) lc_p[q] = 0.0;
-    if (tc == 0) {                                             // publish column 0
+    if (tc == 0) {                                             // publish column 0 (16-byte stores)
+        double2 *cd = reinterpret_cast<double2 *>(colbuf[0] + tr * 6), *ca = reinterpret_cast<double2 *>(colbuf[0] + TS + tr * 6);
 #pragma unroll
-        for (int p = 0; p < 6; ++p) { colbuf[0][tr * 6 + p] = d[p][0]; colbuf[0][TS + tr * 6 + p] = a[p][0]; }
+        for (int p = 0; p < 3; ++p) { cd[p] = make_double2(d[2 * p][0], d[2 * p + 1][0]); ca[p] = make_double2(a[2 * p][0], a[2 * p + 1][0]); }
         if (tr == 0) colbuf[0][2 * TS] = bq[0];
     }
 #define SWEEP_STEP(JQ)                                                                                         \
@@ -320,7 +322,13 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
         bad |= !(piv > 0.0 && piv < 1e300);                                                                    \
         const double rs = rsqrt(piv);                                                                          \
         double lrow[6], ld[6], lc[3];                                                                          \
-        _Pragma("unroll") for (int p = 0; p < 6; ++p) { ld[p] = pld[par * CBS + p] * rs; lrow[p] = pli[par * CBS + p] * rs; } \
+        {                                                                                                      \
+            const double2 *vd = reinterpret_cast<const double2 *>(pld + par * CBS), *vr = reinterpret_cast<const double2 *>(pli + par * CBS); \
+            _Pragma("unroll") for (int p = 0; p < 3; ++p) {                                                    \
+                const double2 x = vd[p], y = vr[p];                                                            \
+                ld[2 * p] = x.x * rs; ld[2 * p + 1] = x.y * rs; lrow[2 * p] = y.x * rs; lrow[2 * p + 1] = y.y * rs; \
+            }                                                                                                  \
+        }                                                                                                      \
         _Pragma("unroll") for (int q = 0; q < 3; ++q) lc[q] = plc[par * CBS + q] * rs;                         \
         const double lb = colbuf[par][2 * TS] * rs;                                                            \
         /* deferred bulk of the previous step on the next-pivot column (independent of this step's rsqrt chain) */ \
@@ -331,7 +339,10 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
         bq[QN] -= lb * lc[QN];                                                                                 \
         if (tc == (JQ == 2 ? jb + 1 : jb)) {                                                                   \
             double *cbn = colbuf[par ^ 1];                                                                     \
-            _Pragma("unroll") for (int p = 0; p < 6; ++p) { cbn[tr * 6 + p] = d[p][QN]; cbn[TS + tr * 6 + p] = a[p][QN]; } \
+            double2 *cd = reinterpret_cast<double2 *>(cbn + tr * 6), *ca = reinterpret_cast<double2 *>(cbn + TS + tr * 6); \
+            _Pragma("unroll") for (int p = 0; p < 3; ++p) {                                                    \
+                cd[p] = make_double2(d[2 * p][QN], d[2 * p + 1][QN]); ca[p] = make_double2(a[2 * p][QN], a[2 * p + 1][QN]); \
+            }                                                                                                  \
             if (tr == 0) cbn[2 * TS] = bq[QN];                                                                 \
         }                                                                                                      \
         /* rest of the previous step's bulk: the third column (neither QP nor QN) */                           \
@@ -341,7 +352,8 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
             bq[Q3] -= lb_p * lc_p[Q3];                                                                         \
         }                                                                                                      \
         if (tc == jb) {                                                                                        \
-            _Pragma("unroll") for (int p = 0; p < 6; ++p) pout[p * LDT + j] = lrow[p];                         \
+            double2 *po = reinterpret_cast<double2 *>(pout + j * LDO);                                         \
+            _Pragma("unroll") for (int p = 0; p < 3; ++p) po[p] = make_double2(lrow[2 * p], lrow[2 * p + 1]);  \
             if (tr == 0) yk[JQ] = lb;                                                                          \
         }                                                                                                      \
         _Pragma("unroll") for (int p = 0; p < 6; ++p) { ld_p[p] = ld[p]; lrow_p[p] = lrow[p]; }                \
@@ -363,16 +375,28 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
         for (int q = 0; q < 3; ++q) ysh[tc * 3 + q] = yk[q];
     }
     __syncthreads();
+    // B2 is transposed (B2[col * LDO + row]); write the tile row-major, zero above the diagonal for L_KK
+    {
+        double *dst = diagcta ? Ldiag + (size_t)K * TS * TS : tik;
+#pragma unroll
+        for (int q = 0; q < (TS * TS / 2 + PANEL_NT - 1) / PANEL_NT; ++q) {
+            const int e = tid + q * PANEL_NT;
+            if (e < TS * TS / 2) {
+                const int r = (2 * e) / TS, cc = (2 * e) % TS;
+                double x = B2[cc * LDO + r], y = B2[(cc + 1) * LDO + r];
+                if (diagcta) { if (cc > r) x = 0.0; if (cc + 1 > r) y = 0.0; }
+                reinterpret_cast<double2 *>(dst)[e] = make_double2(x, y);
+            }
+        }
+    }
     if (diagcta) {
-        tile_stg<PANEL_NT>(Ldiag + (size_t)K * TS * TS, B2, true);
         if (tid < TS) ywork[K * TS + tid] = ysh[tid];
         return;
     }
-    tile_stg<PANEL_NT>(tik, B2);
     if (tid < TS) {                                       // b_I -= L_IK y_K
         double s = 0.0;
 #pragma unroll 8
-        for (int cc = 0; cc < TS; ++cc) s += B2[tid * LDT + cc] * ysh[cc];
+        for (int cc = 0; cc < TS; ++cc) s += B2[cc * LDO + tid] * ysh[cc];
         bwork[I * TS + tid] -= s;
     }
 }
@@ -430,44 +454,62 @@ double psba_launch_factor(psba_ctx *c)
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward substitution x_I = L_II^-T (y_I - sum_{J>I} L_JI^T x_J), one persistent CTA.  Threads are
-// laid out as 48 columns x 10 tile slots: every thread streams one tile column (48 independent
-// coalesced loads in flight), partial sums are combined in a fixed order.
-__global__ void __launch_bounds__(480) k_backward(int N, int nt, const int *__restrict__ cptr, const int *__restrict__ crow,
-                                                  const int *__restrict__ cslot, const double *__restrict__ Stiles,
-                                                  const double *__restrict__ Linv, double *__restrict__ ywork, double *__restrict__ sol)
+// backward substitution x_I = L_II^-T (y_I - sum_{J>I} L_JI^T x_J), one persistent CTA of 960 threads
+// = 48 columns x 20 tile slots: every thread streams one tile column (48 independent coalesced loads in
+// flight, four independent FMA chains), partial sums are combined in a fixed order.  L_II^-1 does not
+// depend on x and is prefetched into shared memory while the tile column streams.
+#define BW_SLOTS 20
+__global__ void __launch_bounds__(TS * BW_SLOTS) k_backward(int N, int nt, const int *__restrict__ cptr, const int *__restrict__ crow,
+                                                           const int *__restrict__ cslot, const double *__restrict__ Stiles,
+                                                           const double *__restrict__ Linv, double *__restrict__ ywork, double *__restrict__ sol)
 {
-    __shared__ double part[10][TS];
+    __shared__ double part[BW_SLOTS][TS];
     __shared__ double acc[TS];
     __shared__ double invs[TS * TS];
+    __shared__ double mv[4][TS];
     const int tid = threadIdx.x, col = tid % TS, slotid = tid / TS;
+    // tile indices of a column do not depend on x: they are fetched one step ahead so that the only
+    // dependent global accesses inside a step are the tile column itself and the x vectors
+    int nbeg = cptr[nt - 1], nend = cptr[nt];
+    int nslot = -1, nrow = 0;
+    if (nbeg + slotid < nend) { nslot = cslot[nbeg + slotid]; nrow = crow[nbeg + slotid]; }
     for (int I = nt - 1; I >= 0; --I) {
-        // L_II^-1 does not depend on x: fetch it while the tile column streams
-        for (int e = tid; e < TS * TS; e += 480) invs[e] = __ldg(Linv + (size_t)I * TS * TS + e);
-        double s = 0.0;
-        for (int t = cptr[I] + slotid; t < cptr[I + 1]; t += 10) {
-            const double *L = Stiles + (size_t)cslot[t] * TS * TS + col;
-            const double *x = ywork + crow[t] * TS;
+        const int beg = nbeg, end = nend, myslot = nslot, myrow = nrow;
+        if (I > 0) {
+            nbeg = cptr[I - 1]; nend = beg;
+            nslot = -1;
+            if (nbeg + slotid < nend) { nslot = cslot[nbeg + slotid]; nrow = crow[nbeg + slotid]; }
+        }
+        for (int e = tid; e < TS * TS; e += TS * BW_SLOTS) invs[e] = __ldg(Linv + (size_t)I * TS * TS + e);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        for (int t = beg + slotid; t < end; t += BW_SLOTS) {
+            const bool first = t == beg + slotid;
+            const double *L = Stiles + (size_t)(first ? myslot : cslot[t]) * TS * TS + col;
+            const double *x = ywork + (first ? myrow : crow[t]) * TS;
             double lv[TS];
 #pragma unroll
-            for (int r = 0; r < TS; ++r) lv[r] = __ldg(L + r * TS);      // 48 independent coalesced loads in flight
+            for (int r = 0; r < TS; ++r) lv[r] = __ldg(L + r * TS);
 #pragma unroll
-            for (int r = 0; r < TS; ++r) s += lv[r] * x[r];
+            for (int r = 0; r < TS; r += 4) { s0 += lv[r] * x[r]; s1 += lv[r + 1] * x[r + 1]; s2 += lv[r + 2] * x[r + 2]; s3 += lv[r + 3] * x[r + 3]; }
         }
-        part[slotid][col] = s;
+        part[slotid][col] = (s0 + s1) + (s2 + s3);
         __syncthreads();
         if (tid < TS) {
             double a = 0.0;
 #pragma unroll
-            for (int p = 0; p < 10; ++p) a += part[p][tid];
+            for (int p = 0; p < BW_SLOTS; ++p) a += part[p][tid];
             acc[tid] = ywork[I * TS + tid] - a;
         }
         __syncthreads();
-        if (tid < TS) {
-            const double *inv = invs + tid;                           // column tid of L_II^-1 = row of its transpose
+        if (tid < 4 * TS) {          // x_I[c] = sum_{r >= c} Linv[r][c] acc[r], rows split over 4 partial sums
+            const int cidx = tid % TS, q = tid / TS;
             double a = 0.0;
-#pragma unroll 8
-            for (int r = tid; r < TS; ++r) a += inv[r * TS] * acc[r];
+            for (int r = cidx + q; r < TS; r += 4) a += invs[r * TS + cidx] * acc[r];
+            mv[q][cidx] = a;
+        }
+        __syncthreads();
+        if (tid < TS) {
+            const double a = (mv[0][tid] + mv[1][tid]) + (mv[2][tid] + mv[3][tid]);
             ywork[I * TS + tid] = a;
             const int gr = I * TS + tid;
             if (gr < N) sol[gr] = a;
@@ -478,7 +520,7 @@ __global__ void __launch_bounds__(480) k_backward(int N, int nt, const int *__re
 
 void psba_launch_solve(psba_ctx *c)
 {
-    PROF(c, KID_TRI_SOLVE) k_backward<<<1, 480, 0, c->stream>>>(c->N, c->nt, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
+    PROF(c, KID_TRI_SOLVE) k_backward<<<1, TS * BW_SLOTS, 0, c->stream>>>(c->N, c->nt, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
                                                                c->Stiles, c->Linv, c->chol_diag, c->dp);
     c->st_launches += 1;
 }
