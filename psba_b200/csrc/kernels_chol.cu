@@ -24,7 +24,7 @@
 
 #define LDT (TS + 1)            // padded leading dimension in shared memory
 #define TILE_SM (TS * LDT)      // doubles per shared tile
-#define CHOL_SMEM ((2 * TILE_SM + TS * (TS + 2)) * sizeof(double))   // two staged tiles + the transposed output tile
+#define CHOL_SMEM (2 * TILE_SM * sizeof(double))   // two staged tiles (factor tiles of panel K-1, then D and A_IK)
 
 // ---------------------------------------------------------------------------------------------
 void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int>> &pairs)
@@ -227,10 +227,10 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
                                                     double *__restrict__ ywork, int *__restrict__ status)
 {
     extern __shared__ double smem[];
-    __shared__ __align__(16) double colbuf[2][2 * TS + 2];
+    __shared__ __align__(16) double colbuf[2][2 * TS + 4];
     if (*status != 0) return;
     const int tid = threadIdx.x, tr = tid % 8, tc = tid / 8;
-    double *B0 = smem, *B1 = smem + TILE_SM, *B2 = smem + 2 * TILE_SM;
+    double *B0 = smem, *B1 = smem + TILE_SM;
 
     if ((int)blockIdx.x >= ncrit) {
         // ---- deferred trailing update of panel K-1:  A_IJ -= L_I,K-1 L_J,K-1^T
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
     TileRegs<PANEL_NT> rp, ri;
     if (have_prev) tile_ldg(rp, Stiles + (size_t)tile_index[K * nt + (K - 1)] * TS * TS);    // L_K,K-1
     if (upd) tile_ldg(ri, Stiles + (size_t)tile_index[I * nt + (K - 1)] * TS * TS);          // L_I,K-1
-    double d[6][3], a[6][3], bq[3] = {0, 0, 0};
+    double d[6][3], a[6][3];
 #pragma unroll
     for (int p = 0; p < 6; ++p)
 #pragma unroll
@@ -275,10 +275,6 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
             d[p][q] = tkk[(tr * 6 + p) * TS + tc * 3 + q];
             a[p][q] = diagcta ? 0.0 : tik[(tr * 6 + p) * TS + tc * 3 + q];
         }
-    if (tr == 0) {
-#pragma unroll
-        for (int q = 0; q < 3; ++q) bq[q] = bwork[K * TS + tc * 3 + q];
-    }
     if (have_prev) {
         tile_sts(B0, rp);
         if (upd) tile_sts(B1, ri);
@@ -291,116 +287,76 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
 #pragma unroll
             for (int q = 0; q < 3; ++q) { d[p][q] -= acc[p][q]; if (upd) a[p][q] -= acc2[p][q]; }
     }
-    // ---- column sweep over the stacked panel; B2 collects the factor rows of this CTA.
-    // Software-pipelined: step j first updates only the NEXT column (the one the next pivot needs) and
-    // publishes it; the bulk of step j's rank-1 update (the thread's other two columns) is executed
-    // after the next barrier, where it overlaps the LDS -> rsqrt -> scale latency chain of step j+1.
-    bool bad = false;
-    double yk[3] = {0, 0, 0};
-    const double *pli = colbuf[0] + (diagcta ? 0 : TS) + tr * 6, *pld = colbuf[0] + tr * 6, *plc = colbuf[0] + tc * 3;
-    constexpr int LDO = TS + 2;                                // B2 holds the factor rows TRANSPOSED: B2[j * LDO + row]
-    double *pout = B2 + tr * 6;
-    constexpr int CBS = 2 * TS + 2;
-    double lrow_p[6], ld_p[6], lc_p[3], lb_p = 0.0;            // scaled column of the previous step (deferred bulk)
+    // ---- hand the updated blocks over to the ROW-OWNER layout of the sweep: thread t < 48 owns row t of
+    // D, thread 48+r owns row r of A_IK, thread 96 owns the right-hand-side row b_K^T
+    __syncthreads();                                           // the factor tiles in B0/B1 are consumed
 #pragma unroll
-    for (int p = 0; p < 6; ++p) { lrow_p[p] = 0.0; ld_p[p] = 0.0; }
+    for (int p = 0; p < 6; ++p)
 #pragma unroll
-    for (int q = 0; q < 3; ++q) lc_p[q] = 0.0;
-    if (tc == 0) {                                             // publish column 0 (16-byte stores)
-        double2 *cd = reinterpret_cast<double2 *>(colbuf[0] + tr * 6), *ca = reinterpret_cast<double2 *>(colbuf[0] + TS + tr * 6);
-#pragma unroll
-        for (int p = 0; p < 3; ++p) { cd[p] = make_double2(d[2 * p][0], d[2 * p + 1][0]); ca[p] = make_double2(a[2 * p][0], a[2 * p + 1][0]); }
-        if (tr == 0) colbuf[0][2 * TS] = bq[0];
-    }
-#define SWEEP_STEP(JQ)                                                                                         \
-    {                                                                                                          \
-        constexpr int QN = (JQ + 1) % 3;          /* column (inside a triple) that the next pivot lives in */  \
-        constexpr int QP = JQ;                    /* column that was critical in the previous step */          \
-        const int j = jb * 3 + JQ, par = j & 1;                                                                \
-        __syncthreads();                                                                                       \
-        const double piv = colbuf[par][j];                                                                     \
-        bad |= !(piv > 0.0 && piv < 1e300);                                                                    \
-        const double rs = rsqrt(piv);                                                                          \
-        double lrow[6], ld[6], lc[3];                                                                          \
-        {                                                                                                      \
-            const double2 *vd = reinterpret_cast<const double2 *>(pld + par * CBS), *vr = reinterpret_cast<const double2 *>(pli + par * CBS); \
-            _Pragma("unroll") for (int p = 0; p < 3; ++p) {                                                    \
-                const double2 x = vd[p], y = vr[p];                                                            \
-                ld[2 * p] = x.x * rs; ld[2 * p + 1] = x.y * rs; lrow[2 * p] = y.x * rs; lrow[2 * p + 1] = y.y * rs; \
-            }                                                                                                  \
-        }                                                                                                      \
-        _Pragma("unroll") for (int q = 0; q < 3; ++q) lc[q] = plc[par * CBS + q] * rs;                         \
-        const double lb = colbuf[par][2 * TS] * rs;                                                            \
-        /* deferred bulk of the previous step on the next-pivot column (independent of this step's rsqrt chain) */ \
-        _Pragma("unroll") for (int p = 0; p < 6; ++p) { d[p][QN] -= ld_p[p] * lc_p[QN]; a[p][QN] -= lrow_p[p] * lc_p[QN]; } \
-        bq[QN] -= lb_p * lc_p[QN];                                                                             \
-        /* critical part of this step: the next column, then publish it */                                     \
-        _Pragma("unroll") for (int p = 0; p < 6; ++p) { d[p][QN] -= ld[p] * lc[QN]; a[p][QN] -= lrow[p] * lc[QN]; } \
-        bq[QN] -= lb * lc[QN];                                                                                 \
-        if (tc == (JQ == 2 ? jb + 1 : jb)) {                                                                   \
-            double *cbn = colbuf[par ^ 1];                                                                     \
-            double2 *cd = reinterpret_cast<double2 *>(cbn + tr * 6), *ca = reinterpret_cast<double2 *>(cbn + TS + tr * 6); \
-            _Pragma("unroll") for (int p = 0; p < 3; ++p) {                                                    \
-                cd[p] = make_double2(d[2 * p][QN], d[2 * p + 1][QN]); ca[p] = make_double2(a[2 * p][QN], a[2 * p + 1][QN]); \
-            }                                                                                                  \
-            if (tr == 0) cbn[2 * TS] = bq[QN];                                                                 \
-        }                                                                                                      \
-        /* rest of the previous step's bulk: the third column (neither QP nor QN) */                           \
-        {                                                                                                      \
-            constexpr int Q3 = 3 - QP - QN;                                                                    \
-            _Pragma("unroll") for (int p = 0; p < 6; ++p) { d[p][Q3] -= ld_p[p] * lc_p[Q3]; a[p][Q3] -= lrow_p[p] * lc_p[Q3]; } \
-            bq[Q3] -= lb_p * lc_p[Q3];                                                                         \
-        }                                                                                                      \
-        if (tc == jb) {                                                                                        \
-            double2 *po = reinterpret_cast<double2 *>(pout + j * LDO);                                         \
-            _Pragma("unroll") for (int p = 0; p < 3; ++p) po[p] = make_double2(lrow[2 * p], lrow[2 * p + 1]);  \
-            if (tr == 0) yk[JQ] = lb;                                                                          \
-        }                                                                                                      \
-        _Pragma("unroll") for (int p = 0; p < 6; ++p) { ld_p[p] = ld[p]; lrow_p[p] = lrow[p]; }                \
-        _Pragma("unroll") for (int q = 0; q < 3; ++q) lc_p[q] = lc[q];                                         \
-        lb_p = lb;                                                                                             \
-    }
-#pragma unroll 1
-    for (int jb = 0; jb < TS / 3; ++jb) {
-        SWEEP_STEP(0)
-        SWEEP_STEP(1)
-        SWEEP_STEP(2)
-    }
-#undef SWEEP_STEP
-    if (__syncthreads_or(bad)) { if (tid == 0) *status = 1; return; }
-    // y_K (held by the threads of grid row 0) -> shared
-    double *ysh = colbuf[0];
-    if (tr == 0) {
-#pragma unroll
-        for (int q = 0; q < 3; ++q) ysh[tc * 3 + q] = yk[q];
-    }
+        for (int q = 0; q < 3; ++q) { B0[(tr * 6 + p) * LDT + tc * 3 + q] = d[p][q]; B1[(tr * 6 + p) * LDT + tc * 3 + q] = a[p][q]; }
     __syncthreads();
-    // B2 is transposed (B2[col * LDO + row]); write the tile row-major, zero above the diagonal for L_KK
-    {
-        double *dst = diagcta ? Ldiag + (size_t)K * TS * TS : tik;
+    const bool active = tid < TS || (tid < 2 * TS && !diagcta) || tid == 2 * TS;
+    double row[TS];
+    if (tid == 2 * TS) {
 #pragma unroll
-        for (int q = 0; q < (TS * TS / 2 + PANEL_NT - 1) / PANEL_NT; ++q) {
-            const int e = tid + q * PANEL_NT;
-            if (e < TS * TS / 2) {
-                const int r = (2 * e) / TS, cc = (2 * e) % TS;
-                double x = B2[cc * LDO + r], y = B2[(cc + 1) * LDO + r];
-                if (diagcta) { if (cc > r) x = 0.0; if (cc + 1 > r) y = 0.0; }
-                reinterpret_cast<double2 *>(dst)[e] = make_double2(x, y);
+        for (int c = 0; c < TS; ++c) row[c] = bwork[K * TS + c];
+    } else {
+        const double *src = tid < TS ? B0 + tid * LDT : B1 + (tid - TS) * LDT;
+#pragma unroll
+        for (int c = 0; c < TS; ++c) row[c] = active ? src[c] : 0.0;
+    }
+    // ---- column sweep over the stacked panel [D ; A_IK ; b^T] (97 x 48), one row per thread in registers.
+    // Step j: every thread publishes its entry of column j (ONE 8-byte shared store per thread: the
+    // barrier drains pending stores at ~19 cycles each, see tools/microbench/sweep_bench.cu), then
+    //   inv = 1/d_jj,  f = row[j]*inv,  row[c] -= f * col[c]  (c > j; the next column first),
+    // and finally row[j] *= rsqrt(d_jj) turns the entry into the factor value (off the critical chain).
+    bool bad = false;
+    if (active) colbuf[0][tid] = row[0];
+#pragma unroll
+    for (int j = 0; j < TS; ++j) {
+        __syncthreads();
+        if (active) {
+            const double *cb = colbuf[j & 1];
+            const double piv = cb[j];
+            bad |= !(piv > 0.0 && piv < 1e300);
+            const double f = row[j] * __drcp_rn(piv);
+            if (j + 1 < TS) {
+                row[j + 1] -= f * cb[j + 1];
+                colbuf[(j + 1) & 1][tid] = row[j + 1];         // publish the next column before the bulk update
             }
+#pragma unroll
+            for (int c = j + 2; c < TS; ++c) row[c] -= f * cb[c];
+            row[j] *= rsqrt(piv);
+        }
+    }
+    if (__syncthreads_or(bad)) { if (tid == 0) *status = 1; return; }
+    // ---- results: factor rows to global, y_K to shared, then b_I -= L_IK y_K
+    double *ysh = colbuf[0];
+    if (tid == 2 * TS) {
+#pragma unroll
+        for (int c = 0; c < TS; ++c) ysh[c] = row[c];
+        if (diagcta) {
+#pragma unroll
+            for (int c = 0; c < TS; ++c) ywork[K * TS + c] = row[c];
         }
     }
     if (diagcta) {
-        if (tid < TS) ywork[K * TS + tid] = ysh[tid];
+        if (tid < TS) {
+            double2 *dst = reinterpret_cast<double2 *>(Ldiag + (size_t)K * TS * TS + tid * TS);
+#pragma unroll
+            for (int c = 0; c < TS; c += 2) dst[c / 2] = make_double2(c <= tid ? row[c] : 0.0, c + 1 <= tid ? row[c + 1] : 0.0);
+        }
         return;
     }
-    if (tid < TS) {                                       // b_I -= L_IK y_K
+    __syncthreads();
+    if (tid >= TS && tid < 2 * TS) {
+        double2 *dst = reinterpret_cast<double2 *>(tik + (tid - TS) * TS);
         double s = 0.0;
-#pragma unroll 8
-        for (int cc = 0; cc < TS; ++cc) s += B2[cc * LDO + tid] * ysh[cc];
-        bwork[I * TS + tid] -= s;
+#pragma unroll
+        for (int c = 0; c < TS; c += 2) { dst[c / 2] = make_double2(row[c], row[c + 1]); s += row[c] * ysh[c] + row[c + 1] * ysh[c + 1]; }
+        bwork[I * TS + (tid - TS)] -= s;
     }
 }
-
 // L_KK^-1 for every diagonal tile (needed by the backward substitution only): one CTA per tile,
 // all tiles in parallel, off the critical path of the factorisation
 __global__ void __launch_bounds__(256) k_diag_inverse(const double *__restrict__ Ldiag, double *__restrict__ Linv, const int *__restrict__ status)
