@@ -78,3 +78,95 @@ def write_sba_text(prob, cams_path, pts_path, max_points=None):
             for k in range(a, b):
                 parts.append("%d %.17g %.17g" % (prob["jidx"][k], prob["impts"][k, 0], prob["impts"][k, 1]))
             f.write(" ".join(parts) + "\n")
+
+
+BAL_OBS = {"Ladybug-138-19878": 85217, "Venice-52-64053": 347173, "Dubrovnik-88-64298": 383937}
+
+
+def _quat2vec_rows(raw):
+    """PSBA/misc.cpp:21-49 + readparams.cpp:222-226 on a (m, 12) camera table -> K, initrot, t"""
+    q = raw[:, 5:9]
+    mag = np.sqrt((q * q).sum(1))
+    sg = np.where(q[:, 0] >= 0.0, 1.0, -1.0) / mag
+    v = q[:, 1:4] * sg[:, None]
+    initrot = np.concatenate([np.sqrt(1.0 - (v * v).sum(1, keepdims=True)), v], axis=1)
+    return raw[:, 0:5].copy(), initrot, raw[:, 9:12].copy()
+
+
+def _rotmats(q):
+    s0, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = np.empty((len(q), 3, 3))
+    R[:, 0, 0] = s0 * s0 + x * x - y * y - z * z; R[:, 0, 1] = 2 * (x * y - s0 * z); R[:, 0, 2] = 2 * (x * z + s0 * y)
+    R[:, 1, 0] = 2 * (x * y + s0 * z); R[:, 1, 1] = s0 * s0 - x * x + y * y - z * z; R[:, 1, 2] = 2 * (y * z - s0 * x)
+    R[:, 2, 0] = 2 * (x * z - s0 * y); R[:, 2, 1] = 2 * (y * z + s0 * x); R[:, 2, 2] = s0 * s0 - x * x - y * y + z * z
+    return R
+
+
+def bal_structure_problem(cams_txt, n, o, seed=None, name="bal-synth"):
+    """Synthetic structure on REAL shipped BAL cameras: the six BAL `-pts.txt` files are
+    missing from the reference checkout, so points and observations are generated on the shipped
+    `*-cams.txt`:  track lengths d_i = 2 + Poisson(o/n - 2) clipped to [2, m] with sum exactly o; first
+    camera uniform; X_i = back-projection of a pixel (u,v) ~ U(-0.4 fu, 0.4 fu)^2 at depth z ~ logU(2, 20);
+    the other d_i - 1 cameras uniform among those that see X_i (depth > 0.1, |u|,|v| <= fu), cameras of a
+    track ascending; observation = reference projection + N(0, 0.5^2) px; initial point = truth +
+    N(0, (0.01 z)^2); initial cameras = shipped.  Label results "synthetic structure on real BAL cameras"."""
+    raw = np.loadtxt(cams_txt)
+    m = raw.shape[0]
+    rng = np.random.Generator(np.random.PCG64(20260000 + m if seed is None else seed))
+    K, initrot, t = _quat2vec_rows(raw)
+    R = _rotmats(initrot)
+    fu, ar = K[:, 0], K[:, 3]
+    # track lengths
+    d = 2 + rng.poisson(max(o / n - 2.0, 0.0), n)
+    d = np.clip(d, 2, m)
+    diff = o - int(d.sum())
+    i = n - 1
+    while diff != 0:
+        step = 1 if diff > 0 else -1
+        if 2 <= d[i] + step <= m:
+            d[i] += step; diff -= step
+        i = i - 1 if i > 0 else n - 1
+    X = np.empty((n, 3)); zdepth = np.empty(n); first = np.empty(n, dtype=np.int64)
+    cand = np.zeros((n, m), dtype=bool)
+    todo = np.arange(n)
+    for _ in range(200):
+        c = len(todo)
+        if c == 0:
+            break
+        a = rng.integers(0, m, c)
+        u = rng.uniform(-0.4, 0.4, c) * fu[a]; v = rng.uniform(-0.4, 0.4, c) * fu[a]
+        z = np.exp(rng.uniform(np.log(2.0), np.log(20.0), c))
+        Xc = np.stack([u / fu[a] * z, v / (fu[a] * ar[a]) * z, z], axis=1)
+        Xw = np.einsum("cji,cj->ci", R[a], Xc - t[a])                      # R^T (Xc - t)
+        P = np.einsum("mij,cj->cmi", R, Xw) + t[None, :, :]               # all cameras
+        dep = P[:, :, 2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            uu = fu[None, :] * P[:, :, 0] / dep; vv = fu[None, :] * ar[None, :] * P[:, :, 1] / dep
+        ok = (dep > 0.1) & (np.abs(uu) <= fu[None, :]) & (np.abs(vv) <= fu[None, :])
+        ok[np.arange(c), a] = False
+        good = ok.sum(1) >= d[todo] - 1
+        g = todo[good]
+        X[g] = Xw[good]; zdepth[g] = z[good]; first[g] = a[good]; cand[g] = ok[good]
+        todo = todo[~good]
+    if len(todo):
+        raise RuntimeError("bal_structure_problem: %d points could not be placed" % len(todo))
+    # choose the other d_i - 1 cameras uniformly among the candidates
+    key = rng.random((n, m))
+    key[~cand] = 2.0
+    order = np.argsort(key, axis=1)
+    take = np.arange(m)[None, :] < (d - 1)[:, None]
+    sel = np.zeros((n, m), dtype=bool)
+    rows = np.repeat(np.arange(n), m).reshape(n, m)
+    sel[rows[take], order[take]] = True
+    sel[np.arange(n), first] = True
+    iidx, jidx = np.nonzero(sel)                                            # point-major, cameras ascending
+    iidx = iidx.astype(np.int32); jidx = jidx.astype(np.int32)
+    assert len(iidx) == o
+    Xc = np.einsum("oij,oj->oi", R[jidx], X[iidx]) + t[jidx]
+    px = (K[jidx, 0] * Xc[:, 0] + K[jidx, 4] * Xc[:, 1] + K[jidx, 1] * Xc[:, 2]) / Xc[:, 2]
+    py = (K[jidx, 0] * K[jidx, 3] * Xc[:, 1] + K[jidx, 2] * Xc[:, 2]) / Xc[:, 2]
+    impts = np.stack([px, py], axis=1) + rng.normal(0.0, 0.5, (o, 2))
+    pts0 = X + rng.normal(size=(n, 3)) * (0.01 * zdepth)[:, None]
+    cams = np.zeros((m, 6)); cams[:, 3:6] = t
+    return dict(m=m, n=n, o=o, K=K, initrot=initrot, cams=cams, pts=pts0, impts=impts, iidx=iidx, jidx=jidx,
+                pts_true=X, name=name, label="synthetic structure on real BAL cameras")

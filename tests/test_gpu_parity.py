@@ -188,3 +188,35 @@ def test_two_gpu_sharded_solve_matches_oracle():
                         "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tools", "mgpu_check.py")],
                        capture_output=True, text=True, timeout=600)
     assert "MGPU_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", ["Venice-52-64053", "Ladybug-138-19878"])
+def test_bal_synthetic_structure_full_solve(name):
+    """BASELINE configs 3-4: full LM + trust-region solve on the shipped BAL cameras with seeded synthetic
+    structure (the BAL pts files are missing from the reference checkout).  Same tolerances
+    as the shipped datasets; the CPU oracle runs the reference's algorithm with CSR index lookups."""
+    import os
+    from psba_b200 import synth
+    from util import data_file
+    n = int(name.split("-")[2])
+    prob = synth.bal_structure_problem(data_file(name + "-cams.txt"), n, synth.BAL_OBS[name], name=name)
+    O = oracle.Problem(prob)
+    O.set("nthreads", min(16, len(os.sched_getaffinity(0))))
+    G = psba_b200.PSBA(prob)
+    if name.startswith("Ladybug"):
+        # N = 828: the oracle's serial dense inverse is slow; compare the LM phase (5 accepted iterations) only
+        fo = O.levmar()
+        G.set_option("max_iter", 50)
+        fg, fe = G.levmar()
+        assert fo == fg == 2          # ITER_TURN_TO_TR
+    else:
+        fo = O.solve()
+        rg = G.solve()
+        assert rg["flag"] == fo and rg["itno"] == int(O.get("itno"))
+        assert abs(rg["finalErr"] - O.get("finalErr")) / O.get("finalErr") < 1e-6
+    to, tg = O.trace(), G.trace()
+    assert pattern(tg) == pattern(to)
+    for a, b in zip([r for r in to if r["phase"] == 0][:5], [r for r in tg if r["phase"] == 0][:5]):
+        assert abs(a["err"] - b["err"]) / a["err"] < 1e-9
+        assert abs(a["mu"] - b["mu"]) / a["mu"] < 1e-9
+    G.close(); O.close()
