@@ -139,6 +139,44 @@ def run_cpu(kind_pref, threads, sample, lm_passes):
     return tries * prob["o"] / t_tot, its / t_tot, t_tot, ("reference" if kind == "reference" else "port"), desc, prob["o"]
 
 
+def bal_full_solves(cores):
+    """Whole solves `while(true){levmar(); trust_region();}` (PSBA/main.cpp:192-209) on GPU and on the CPU
+    oracle: Trafalgar-21 (the only complete BAL set in the reference checkout) and Venice-52 with synthetic
+    structure on the shipped cameras.  Reported next to the headline, not part of it."""
+    import oracle
+    import psba_b200
+    from psba_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import data_file, dataset_paths
+    out = {}
+    probs = {"Trafalgar-21-11315 (real)": psba_b200.read_sba(*dataset_paths("T21")),
+             "Venice-52-64053 (synthetic structure on real BAL cameras)":
+                 synth.bal_structure_problem(data_file("Venice-52-64053-cams.txt"), 64053, synth.BAL_OBS["Venice-52-64053"])}
+    for name, prob in probs.items():
+        G = psba_b200.PSBA(prob)
+        G.solve()                                        # warm-up (graph instantiation)
+        G.set_params(prob["cams"], prob["pts"])
+        G.set_option("stats_reset", 0)
+        G.set_option("timer_start", 0)
+        r = G.solve()
+        ms = G.stat("timer_ms")
+        tries, nex = int(G.stat("tries")), int(G.stat("exqt"))
+        G.close()
+        O = oracle.Problem(prob)
+        O.set("nthreads", cores)
+        t0 = time.perf_counter()
+        fo = O.solve()
+        cpu_s = time.perf_counter() - t0
+        out[name] = {"cams": prob["m"], "points": prob["n"], "observations": prob["o"],
+                     "gpu_ms": round(ms, 3), "gpu_outer_iterations": r["itno"], "gpu_tries": tries,
+                     "gpu_reprojections_per_s": nex * prob["o"] / (ms * 1e-3), "gpu_final_cost": r["finalErr"],
+                     "cpu_s": round(cpu_s, 3), "cpu_threads": cores, "cpu_outer_iterations": int(O.get("itno")),
+                     "cpu_final_cost": O.get("finalErr"), "same_exit_flag": bool(fo == r["flag"]),
+                     "final_cost_rel_diff": abs(r["finalErr"] - O.get("finalErr")) / O.get("finalErr")}
+        O.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -296,13 +334,19 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc,
                "lm_iters_per_sec_scaled_to_workload": cits * o_s / o}
 
+    # ---- informational: FULL LM + trust-region solves (the reference's main loop) on BAL-size problems
+    bal = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        bal = bal_full_solves(cores)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / max(its, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
                 "lm_iters_per_sec": its / (ms * 1e-3), "tries": tries, "lm_iterations": its, "final_cost": final_cost,
                 "gpu_launches": launches, "setup_seconds": round(setup_s, 3),
-                "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "kernels": ktab}
+                "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "kernels": ktab,
+                "bal_full_solves": bal}
         print(json.dumps(line))
     G.close()
     if world > 1:

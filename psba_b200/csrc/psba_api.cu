@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <chrono>
 
 static void die(const char *msg)
 {
@@ -119,6 +120,15 @@ extern "C" void psba_fill_idxBuffer(psba_ctx *c, int nCams, int n3Dpts, int n2Dp
     psba_stage *st = g_stage_of(c);
     if (st->pts.size() != (size_t)n3Dpts * 3) die("fill_idxBuffer called before fill_initBuffer2");
     const int m = c->m;
+    const bool timing = getenv("PSBA_SETUP_TIMING") != nullptr;
+    auto tprev = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        CUDA_CHECK(cudaDeviceSynchronize());
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "psba setup: %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tprev).count());
+        tprev = now;
+    };
     // observations must be point-major, cameras ascending (generate_idxs, misc.cpp:189-217)
     for (int k = 1; k < n2Dprojs; ++k) {
         if (iidx[k] < iidx[k - 1] || (iidx[k] == iidx[k - 1] && jidx[k] <= jidx[k - 1]))
@@ -129,6 +139,7 @@ extern "C" void psba_fill_idxBuffer(psba_ctx *c, int nCams, int n3Dpts, int n2Dp
     c->p_off = p0; c->o_off = o0; c->n = p1 - p0; c->o = o1 - o0;
     const int n = c->n, o = c->o;
 
+    lap("validate + partition");
     // ---- parameters
     CUDA_CHECK(cudaMemcpy(c->K, st->K.data(), (size_t)m * 5 * 8, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(c->initcams, st->initcams.data(), (size_t)m * 4 * 8, cudaMemcpyHostToDevice));
@@ -139,6 +150,7 @@ extern "C" void psba_fill_idxBuffer(psba_ctx *c, int nCams, int n3Dpts, int n2Dp
     if (n) CUDA_CHECK(cudaMemcpy(c->pts[0], st->pts.data() + (size_t)p0 * 3, (size_t)n * 24, cudaMemcpyHostToDevice));
     g_stage.erase(c);
 
+    lap("parameter upload");
     // ---- local CSR
     std::vector<int> li(o), lj(o), ptr((size_t)n + 1, 0);
     for (int k = 0; k < o; ++k) { li[k] = iidx[o0 + k] - p0; lj[k] = jidx[o0 + k]; ptr[li[k] + 1]++; }
@@ -176,6 +188,7 @@ extern "C" void psba_fill_idxBuffer(psba_ctx *c, int nCams, int n3Dpts, int n2Dp
     c->cchunk_cam = dupload(cc_cam); c->cchunk_beg = dupload(cc_beg); c->cchunk_end = dupload(cc_end);
     c->cam_cchunk_ptr = dupload(cc_ptr);
 
+    lap("CSR + chunks");
     // ---- camera-pair structure: GLOBAL set of pairs (k >= l) so that every rank builds the same S layout
     std::vector<int> pair_id((size_t)m * m, -1);
     {
@@ -194,6 +207,7 @@ extern "C" void psba_fill_idxBuffer(psba_ctx *c, int nCams, int n3Dpts, int n2Dp
             if (pair_id[(size_t)k * m + l] == 0) { pair_id[(size_t)k * m + l] = (int)pk.size(); pk.push_back(k); pl.push_back(l); pairs.push_back({k, l}); }
     c->n_pair = (int)pk.size();
     c->pair_k = dupload(pk); c->pair_l = dupload(pl);
+    lap("global pair set");
     // local triples, counting sort by pair (points ascending inside a pair)
     std::vector<long long> tptr((size_t)c->n_pair + 1, 0);
     for (int i = 0; i < n; ++i)
@@ -234,9 +248,11 @@ extern "C" void psba_fill_idxBuffer(psba_ctx *c, int nCams, int n3Dpts, int n2Dp
     c->pchunk_pair = dupload(pc_pair); c->pchunk_beg = dupload(pc_beg); c->pchunk_end = dupload(pc_end);
     c->pair_chunk_ptr = dupload(pc_ptr);
 
+    lap("triple sort + upload");
     // ---- camera system tiles
     psba_build_tile_structure(c, pairs);
 
+    lap("tile structure");
     // ---- work buffers
     const size_t Tl = (size_t)c->N + 3 * (size_t)n;
     c->W = dalloc<double>((size_t)o * 18);
@@ -252,6 +268,7 @@ extern "C" void psba_fill_idxBuffer(psba_ctx *c, int nCams, int n3Dpts, int n2Dp
     c->chol_E = dalloc<double>((size_t)c->N + TS);
     c->UVdiag_scr = dalloc<double>(Tl);
     CUDA_CHECK(cudaDeviceSynchronize());
+    lap("work buffers");
 }
 
 extern "C" void psba_release_buffer(psba_ctx *c)
