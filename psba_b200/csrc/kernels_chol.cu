@@ -27,57 +27,225 @@
 #define CHOL_SMEM (2 * TILE_SM * sizeof(double))   // two staged tiles (factor tiles of panel K-1, then D and A_IK)
 
 // ---------------------------------------------------------------------------------------------
+// Symbolic phase (host, once per problem).
+//
+// Ordering: nested dissection of the TILE graph (tile = 8 consecutive cameras) by BFS level
+// structures (George's automatic nested dissection): a connected subgraph is rooted at a
+// pseudo-peripheral tile, the level that balances the two sides is the separator, the two sides
+// are ordered recursively and the separator goes last.  Subgraphs whose level structure has fewer
+// than three levels (every dense BAL system) keep their natural order.  For the block-banded ring
+// (250 tile columns, half band width 8 tiles) this turns a dependent chain of 250 panels into ~50
+// steps of independent panels.
+struct nd_ctx {
+    const std::vector<std::vector<int>> *adj;
+    std::vector<int> mark, dist;
+    int tag;
+    int min_size;
+    std::vector<int> order;
+};
+
+static void nd_bfs(nd_ctx &x, int root, int tag, std::vector<int> &visit, int &nlev)
+{
+    // BFS inside the subset {v : mark[v] == tag}; dist doubles as the visited flag (-1 = unseen)
+    visit.clear();
+    visit.push_back(root);
+    x.dist[root] = 0;
+    for (size_t h = 0; h < visit.size(); ++h) {
+        const int v = visit[h];
+        for (int w : (*x.adj)[v])
+            if (x.mark[w] == tag && x.dist[w] < 0) { x.dist[w] = x.dist[v] + 1; visit.push_back(w); }
+    }
+    nlev = x.dist[visit.back()] + 1;
+}
+
+static void nd_recurse(nd_ctx &x, std::vector<int> nodes)
+{
+    std::sort(nodes.begin(), nodes.end());
+    if ((int)nodes.size() <= x.min_size) { x.order.insert(x.order.end(), nodes.begin(), nodes.end()); return; }
+    const int tag = ++x.tag;
+    for (int v : nodes) { x.mark[v] = tag; x.dist[v] = -1; }
+    std::vector<int> visit;
+    int nlev = 0;
+    nd_bfs(x, nodes[0], tag, visit, nlev);
+    if (visit.size() < nodes.size()) {
+        // disconnected: every component is an independent subtree of the elimination forest
+        std::vector<std::vector<int>> comps;
+        comps.push_back(visit);
+        for (int v : nodes)
+            if (x.dist[v] < 0) { nd_bfs(x, v, tag, visit, nlev); comps.push_back(visit); }
+        for (auto &cmp : comps) nd_recurse(x, cmp);
+        return;
+    }
+    // pseudo-peripheral root: restart from the lowest-degree tile of the last level while the depth grows
+    int root = nodes[0];
+    for (int it = 0; it < 4; ++it) {
+        int best = -1;
+        size_t bdeg = (size_t)-1;
+        for (int v : visit)
+            if (x.dist[v] == nlev - 1 && (*x.adj)[v].size() < bdeg) { bdeg = (*x.adj)[v].size(); best = v; }
+        for (int v : nodes) x.dist[v] = -1;
+        int nl2 = 0;
+        nd_bfs(x, best, tag, visit, nl2);
+        const bool grew = nl2 > nlev;
+        root = best; nlev = nl2;
+        if (!grew) break;
+    }
+    (void)root;
+    if (nlev < 3) { x.order.insert(x.order.end(), nodes.begin(), nodes.end()); return; }
+    std::vector<int> cnt(nlev, 0);
+    for (int v : nodes) cnt[x.dist[v]]++;
+    int best_l = 1;
+    long long best_score = -1;
+    {
+        long long below = cnt[0];
+        for (int l = 1; l <= nlev - 2; ++l) {
+            const long long above = (long long)nodes.size() - below - cnt[l];
+            const long long score = std::max(below, above) + cnt[l];      // longest remaining chain
+            if (best_score < 0 || score < best_score) { best_score = score; best_l = l; }
+            below += cnt[l];
+        }
+    }
+    std::vector<int> A, B, S;
+    for (int v : nodes) (x.dist[v] < best_l ? A : x.dist[v] > best_l ? B : S).push_back(v);
+    nd_recurse(x, A);
+    nd_recurse(x, B);
+    std::sort(S.begin(), S.end());
+    x.order.insert(x.order.end(), S.begin(), S.end());
+}
+
+template <class T> static void up_vec(T **d, const std::vector<T> &h)
+{
+    CUDA_CHECK(cudaMalloc(d, std::max<size_t>(1, h.size()) * sizeof(T)));
+    if (!h.empty()) CUDA_CHECK(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+}
+
 void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int>> &pairs)
 {
     const int nt = (c->m + 7) / 8;
     c->nt = nt;
+    // ---- tile graph in natural numbering
+    std::vector<char> nat((size_t)nt * nt, 0);
+    for (auto &p : pairs) { const int a = p.first / 8, b = p.second / 8; nat[(size_t)a * nt + b] = 1; nat[(size_t)b * nt + a] = 1; }
+    std::vector<std::vector<int>> adj(nt);
+    for (int a = 0; a < nt; ++a)
+        for (int b = 0; b < nt; ++b)
+            if (a != b && nat[(size_t)a * nt + b]) adj[a].push_back(b);
+    // ---- ordering
+    std::vector<int> tpos(nt);                       // natural tile -> position
+    {
+        const char *e = getenv("PSBA_ND_MIN");
+        int min_size = e ? atoi(e) : 12;
+        nd_ctx x;
+        x.adj = &adj; x.mark.assign(nt, 0); x.dist.assign(nt, -1); x.tag = 0; x.min_size = std::max(1, min_size);
+        std::vector<int> all(nt);
+        for (int t = 0; t < nt; ++t) all[t] = t;
+        if (min_size <= 0 || min_size >= nt) x.order = all;      // natural order
+        else nd_recurse(x, all);
+        if ((int)x.order.size() != nt) { fprintf(stderr, "psba_b200: internal error in the tile ordering\n"); exit(EXIT_FAILURE); }
+        for (int p = 0; p < nt; ++p) tpos[x.order[p]] = p;
+    }
+    c->h_cam2pos.resize(c->m);
+    std::vector<int> pos2cam((size_t)nt * 8, -1);
+    for (int j = 0; j < c->m; ++j) { c->h_cam2pos[j] = tpos[j / 8] * 8 + j % 8; pos2cam[c->h_cam2pos[j]] = j; }
+    up_vec(&c->cam2pos, c->h_cam2pos);
+    up_vec(&c->pos2cam, pos2cam);
+    // ---- pattern in permuted numbering + symbolic factorisation at tile granularity
     std::vector<char> present((size_t)nt * nt, 0);
     for (int I = 0; I < nt; ++I) present[(size_t)I * nt + I] = 1;
-    for (auto &p : pairs) present[(size_t)(p.first / 8) * nt + p.second / 8] = 1;
-    // symbolic factorisation at tile granularity
-    std::vector<std::vector<int>> rows(nt);
+    for (int a = 0; a < nt; ++a)
+        for (int b : adj[a]) { const int I = std::max(tpos[a], tpos[b]), J = std::min(tpos[a], tpos[b]); present[(size_t)I * nt + J] = 1; }
+    std::vector<std::vector<int>> rows(nt);          // rows[K]: tile rows I > K of the factor column K
     for (int K = 0; K < nt; ++K) {
         for (int I = K + 1; I < nt; ++I) if (present[(size_t)I * nt + K]) rows[K].push_back(I);
         for (size_t a = 0; a < rows[K].size(); ++a)
             for (size_t b = 0; b <= a; ++b) present[(size_t)rows[K][a] * nt + rows[K][b]] = 1;
-    }
-    std::vector<int> crit_rows, ncrI, ncrJ;
-    c->crit_ptr.assign(1, 0); c->ncr_ptr.assign(1, 0);
-    for (int K = 0; K < nt; ++K) {
-        crit_rows.push_back(K);
-        crit_rows.insert(crit_rows.end(), rows[K].begin(), rows[K].end());
-        c->crit_ptr.push_back((int)crit_rows.size());
-        if (K > 0)
-            for (size_t a = 0; a < rows[K - 1].size(); ++a)
-                for (size_t b = 0; b <= a; ++b)
-                    if (rows[K - 1][b] > K) { ncrI.push_back(rows[K - 1][a]); ncrJ.push_back(rows[K - 1][b]); }
-        c->ncr_ptr.push_back((int)ncrI.size());
     }
     c->h_tile_index.assign((size_t)nt * nt, -1);
     int slot = 0;
     for (int I = 0; I < nt; ++I)
         for (int J = 0; J <= I; ++J)
             if (present[(size_t)I * nt + J]) c->h_tile_index[(size_t)I * nt + J] = slot++;
+    c->n_tiles = slot;
+    // ---- steps: a panel runs one step after the last panel it depends on
+    std::vector<int> step(nt, 0);
+    std::vector<std::vector<int>> cols(nt);          // cols[K]: panels P < K with a factor tile (K,P), ascending
+    for (int P = 0; P < nt; ++P) for (int I : rows[P]) cols[I].push_back(P);
+    int n_steps = 0;
+    for (int K = 0; K < nt; ++K) {
+        int s = 0;
+        for (int P : cols[K]) s = std::max(s, step[P] + 1);
+        step[K] = s;
+        n_steps = std::max(n_steps, s + 1);
+    }
+    c->n_steps = n_steps;
+    std::vector<std::vector<int>> by_step(n_steps);
+    for (int K = 0; K < nt; ++K) by_step[step[K]].push_back(K);
+    c->chain_schedule = true;
+    for (auto &v : by_step) if (v.size() != 1) c->chain_schedule = false;
+    // ---- task lists
+    std::vector<int> critI, critK, psrc_ptr(1, 0), psrc, rowl_ptr(1, 0), rowl_slot;
+    std::vector<int> defI, defJ, def_sptr(1, 0), def_src, step_panels;
+    std::vector<std::vector<int>> psrc_of(nt);
+    for (int K = 0; K < nt; ++K) {
+        for (int P : cols[K]) {
+            if (step[P] == step[K] - 1) psrc_of[K].push_back(P);
+            rowl_slot.push_back(c->h_tile_index[(size_t)K * nt + P]);
+        }
+        psrc.insert(psrc.end(), psrc_of[K].begin(), psrc_of[K].end());
+        psrc_ptr.push_back((int)psrc.size());
+        rowl_ptr.push_back((int)rowl_slot.size());
+    }
+    c->step_crit_ptr.assign(1, 0); c->step_def_ptr.assign(1, 0); c->step_panel_ptr.assign(1, 0);
+    std::vector<int> stamp((size_t)nt * nt, -1), def_of((size_t)nt * nt, -1);
+    for (int s = 0; s < n_steps; ++s) {
+        for (int K : by_step[s]) {
+            critI.push_back(K); critK.push_back(K);
+            for (int I : rows[K]) { critI.push_back(I); critK.push_back(K); }
+            step_panels.push_back(K);
+        }
+        c->step_crit_ptr.push_back((int)critI.size());
+        c->step_panel_ptr.push_back((int)step_panels.size());
+        // deferred targets of the panels of step s-1: tiles (I,J) with J in a later step than s
+        if (s > 0) {
+            std::vector<std::vector<int>> srcs;
+            std::vector<std::pair<int, int>> tgt;
+            for (int P : by_step[s - 1])
+                for (size_t a = 0; a < rows[P].size(); ++a)
+                    for (size_t b = 0; b <= a; ++b) {
+                        const int I = rows[P][a], J = rows[P][b];
+                        if (step[J] == s) continue;              // handled by the critical CTAs of panel J
+                        const size_t key = (size_t)I * nt + J;
+                        if (stamp[key] != s) { stamp[key] = s; def_of[key] = (int)tgt.size(); tgt.push_back({I, J}); srcs.emplace_back(); }
+                        srcs[def_of[key]].push_back(P);
+                    }
+            for (size_t t = 0; t < tgt.size(); ++t) {
+                defI.push_back(tgt[t].first); defJ.push_back(tgt[t].second);
+                def_src.insert(def_src.end(), srcs[t].begin(), srcs[t].end());
+                def_sptr.push_back((int)def_src.size());
+            }
+        }
+        c->step_def_ptr.push_back((int)defI.size());
+    }
     std::vector<int> cptr(1, 0), crow, cslot;
     for (int J = 0; J < nt; ++J) {
-        for (int I = J + 1; I < nt; ++I)
-            if (present[(size_t)I * nt + J]) { crow.push_back(I); cslot.push_back(c->h_tile_index[(size_t)I * nt + J]); }
+        for (int I : rows[J]) { crow.push_back(I); cslot.push_back(c->h_tile_index[(size_t)I * nt + J]); }
         cptr.push_back((int)crow.size());
     }
-    c->n_tiles = slot;
-    auto up = [&](int **d, const std::vector<int> &h) {
-        CUDA_CHECK(cudaMalloc(d, std::max<size_t>(1, h.size()) * sizeof(int)));
-        if (!h.empty()) CUDA_CHECK(cudaMemcpy(*d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
-    };
-    up(&c->tile_index, c->h_tile_index);
-    up(&c->d_crit_rows, crit_rows);
-    up(&c->d_ncr_I, ncrI); up(&c->d_ncr_J, ncrJ);
-    up(&c->d_coltile_ptr, cptr); up(&c->d_coltile_row, crow); up(&c->d_coltile_slot, cslot);
-    c->d_rowtile_ptr = c->d_rowtile_col = c->d_rowtile_slot = nullptr;
+    up_vec(&c->tile_index, c->h_tile_index);
+    up_vec(&c->d_crit_I, critI); up_vec(&c->d_crit_K, critK);
+    up_vec(&c->d_psrc_ptr, psrc_ptr); up_vec(&c->d_psrc, psrc);
+    up_vec(&c->d_rowl_ptr, rowl_ptr); up_vec(&c->d_rowl_slot, rowl_slot);
+    up_vec(&c->d_def_I, defI); up_vec(&c->d_def_J, defJ); up_vec(&c->d_def_sptr, def_sptr); up_vec(&c->d_def_src, def_src);
+    up_vec(&c->d_step_panels, step_panels);
+    up_vec(&c->d_coltile_ptr, cptr); up_vec(&c->d_coltile_row, crow); up_vec(&c->d_coltile_slot, cslot);
     CUDA_CHECK(cudaMalloc(&c->Stiles, (size_t)c->n_tiles * TS * TS * sizeof(double)));
+    CUDA_CHECK(cudaMalloc(&c->contrib, (size_t)c->n_tiles * TS * sizeof(double)));
     CUDA_CHECK(cudaMalloc(&c->Linv, (size_t)nt * TS * TS * sizeof(double)));
     CUDA_CHECK(cudaMalloc(&c->Ldiag, (size_t)nt * TS * TS * sizeof(double)));
-    c->chol_graph_ok = false;
+    c->chol_graph_ok = false; c->bw_graph_ok = false;
+    if (getenv("PSBA_SETUP_TIMING"))
+        fprintf(stderr, "psba setup: camera system %d tiles/edge, %d factor tiles, %d steps, %zu critical + %zu deferred tasks\n",
+                nt, c->n_tiles, n_steps, critI.size(), defI.size());
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -203,28 +371,27 @@ __device__ __forceinline__ void tile_tri_inverse(const double *L, double *X)
     tri_inverse_merge<24>(L, X);
 }
 
-__global__ void k_init_rhs(int N, int npad, const double *__restrict__ ea, double *__restrict__ b)
-{
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < npad) b[k] = k < N ? ea[k] : 0.0;
-}
-
 #define PANEL_NT 128
-// One kernel per panel K (128 threads per CTA).
-//  critical CTA for tile row I (I = K: the diagonal CTA): loads D = A_KK, A_IK and the factor tiles of
-//  panel K-1, applies the deferred updates, then ONE column sweep factors the stacked panel
-//  [D ; A_IK ; b_K^T] (97 x 48): l_ij = d_ij * rsqrt(d_jj), d_ic -= l_ij l_cj.  Rows of D become L_KK,
-//  rows of A_IK become L_IK = A_IK L_KK^-T (no explicit inverse, no separate trsm) and the extra row
-//  b_K^T becomes y_K^T = (L_KK^-1 b_K)^T, the forward substitution.  Every thread keeps one 6x3 block
-//  of D and one of A_IK in registers; per column only the 97 column entries go through shared memory
-//  (double-buffered, one barrier per column); the loop body is branch-free (dead entries are updated
-//  too, a non-positive pivot poisons the panel with NaN and is reported once at the end).
-//  deferred CTAs: A_IJ -= L_I,K-1 L_J,K-1^T for the trailing tiles (J > K) of panel K-1.
-__global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, const int *__restrict__ crit_rows,
-                                                    const int *__restrict__ ncrI, const int *__restrict__ ncrJ,
-                                                    const int *__restrict__ tile_index, double *__restrict__ Stiles,
-                                                    double *__restrict__ Ldiag, double *__restrict__ bwork,
-                                                    double *__restrict__ ywork, int *__restrict__ status)
+// One kernel per STEP (128 threads per CTA); a step holds every panel whose dependencies are met.
+//  critical CTA for tile row I of panel K (I = K: the diagonal CTA): loads D = A_KK and A_IK, applies the
+//  pending updates of the source panels P of the previous step (D -= L_KP L_KP^T, A_IK -= L_IP L_KP^T), then
+//  ONE column sweep factors the stacked panel [D ; A_IK ; b_K^T] (97 x 48): l_ij = d_ij * rsqrt(d_jj),
+//  d_ic -= l_ij l_cj.  Rows of D become L_KK, rows of A_IK become L_IK = A_IK L_KK^-T (no explicit inverse, no
+//  separate trsm) and the extra row b_K^T becomes y_K^T = (L_KK^-1 b_K)^T, the forward substitution; b_K is the
+//  right-hand side minus the contributions L_KP y_P that the CTAs of the tiles (K,P) left behind (summed in
+//  ascending P: fixed order, no atomics).  Every thread keeps one 6x3 block of D and one of A_IK in registers
+//  for the updates and one row of the stacked panel for the sweep; per column only the 97 column entries go
+//  through shared memory (double-buffered, one barrier per column); the loop body is branch-free (dead
+//  entries are updated too, a non-positive pivot poisons the panel with NaN and is reported once at the end).
+//  deferred CTAs: A_IJ -= sum_P L_IP L_JP^T for trailing tiles whose panel J runs in a later step.
+__global__ void __launch_bounds__(PANEL_NT) k_panel_step(int nt, int ncrit, const int *__restrict__ critI, const int *__restrict__ critK,
+                                                         const int *__restrict__ psrc_ptr, const int *__restrict__ psrc,
+                                                         const int *__restrict__ rowl_ptr, const int *__restrict__ rowl_slot,
+                                                         const int *__restrict__ defI, const int *__restrict__ defJ,
+                                                         const int *__restrict__ def_sptr, const int *__restrict__ def_src,
+                                                         const int *__restrict__ tile_index, double *__restrict__ Stiles,
+                                                         double *__restrict__ Ldiag, const double *__restrict__ b0,
+                                                         double *__restrict__ ywork, double *__restrict__ contrib, int *__restrict__ status)
 {
     extern __shared__ double smem[];
     __shared__ __align__(16) double colbuf[2][2 * TS + 4];
@@ -233,40 +400,61 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
     double *B0 = smem, *B1 = smem + TILE_SM;
 
     if ((int)blockIdx.x >= ncrit) {
-        // ---- deferred trailing update of panel K-1:  A_IJ -= L_I,K-1 L_J,K-1^T
+        // ---- deferred trailing update:  A_IJ -= sum_P L_IP L_JP^T
         const int t = blockIdx.x - ncrit;
-        const int I = ncrI[t], J = ncrJ[t];
+        const int I = defI[t], J = defJ[t];
+        const int sb = def_sptr[t], se = def_sptr[t + 1];
         double *tij = Stiles + (size_t)tile_index[I * nt + J] * TS * TS;
         TileRegs<PANEL_NT> ra, rb;
-        tile_ldg(ra, Stiles + (size_t)tile_index[I * nt + (K - 1)] * TS * TS);
-        tile_ldg(rb, Stiles + (size_t)tile_index[J * nt + (K - 1)] * TS * TS);
+        {
+            const int P = def_src[sb];
+            tile_ldg(ra, Stiles + (size_t)tile_index[I * nt + P] * TS * TS);
+            tile_ldg(rb, Stiles + (size_t)tile_index[J * nt + P] * TS * TS);
+        }
         double c18[6][3];
 #pragma unroll
         for (int p = 0; p < 6; ++p)
 #pragma unroll
             for (int q = 0; q < 3; ++q) c18[p][q] = tij[(tr * 6 + p) * TS + tc * 3 + q];
-        tile_sts(B0, ra); tile_sts(B1, rb);
-        __syncthreads();
-        double acc[6][3];
-        tile_abt<false>(B0, B0, B1, acc, acc);
+        for (int s = sb; s < se; ++s) {
+            if (s > sb) __syncthreads();
+            tile_sts(B0, ra); tile_sts(B1, rb);
+            __syncthreads();
+            if (s + 1 < se) {                                  // next source's tiles fly during the product
+                const int P = def_src[s + 1];
+                tile_ldg(ra, Stiles + (size_t)tile_index[I * nt + P] * TS * TS);
+                tile_ldg(rb, Stiles + (size_t)tile_index[J * nt + P] * TS * TS);
+            }
+            double acc[6][3];
+            tile_abt<false>(B0, B0, B1, acc, acc);
+#pragma unroll
+            for (int p = 0; p < 6; ++p)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) c18[p][q] -= acc[p][q];
+        }
 #pragma unroll
         for (int p = 0; p < 6; ++p)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) tij[(tr * 6 + p) * TS + tc * 3 + q] = c18[p][q] - acc[p][q];
+            for (int q = 0; q < 3; ++q) tij[(tr * 6 + p) * TS + tc * 3 + q] = c18[p][q];
         return;
     }
 
     // ---- critical path of panel K for tile row I
-    const int I = crit_rows[blockIdx.x];
+    const int I = critI[blockIdx.x], K = critK[blockIdx.x];
     const bool diagcta = I == K;
-    const bool have_prev = K > 0 && tile_index[K * nt + (K - 1)] >= 0;
-    const bool upd = !diagcta && have_prev && tile_index[I * nt + (K - 1)] >= 0;
+    const int sb = psrc_ptr[K], se = psrc_ptr[K + 1];
     double *tik = Stiles + (size_t)tile_index[I * nt + K] * TS * TS;
     const double *tkk = Stiles + (size_t)tile_index[K * nt + K] * TS * TS;
     // all global loads are issued before anything waits on them
     TileRegs<PANEL_NT> rp, ri;
-    if (have_prev) tile_ldg(rp, Stiles + (size_t)tile_index[K * nt + (K - 1)] * TS * TS);    // L_K,K-1
-    if (upd) tile_ldg(ri, Stiles + (size_t)tile_index[I * nt + (K - 1)] * TS * TS);          // L_I,K-1
+    bool upd = false;
+    if (sb < se) {
+        const int P = psrc[sb];
+        tile_ldg(rp, Stiles + (size_t)tile_index[K * nt + P] * TS * TS);                         // L_KP
+        const int sl = diagcta ? -1 : tile_index[I * nt + P];
+        upd = sl >= 0;
+        if (upd) tile_ldg(ri, Stiles + (size_t)sl * TS * TS);                                     // L_IP
+    }
     double d[6][3], a[6][3];
 #pragma unroll
     for (int p = 0; p < 6; ++p)
@@ -275,17 +463,32 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
             d[p][q] = tkk[(tr * 6 + p) * TS + tc * 3 + q];
             a[p][q] = diagcta ? 0.0 : tik[(tr * 6 + p) * TS + tc * 3 + q];
         }
-    if (have_prev) {
+    // right-hand side of the panel: b_K = b0_K - sum_P L_KP y_P (ascending P, two interleaved partial sums)
+    double bpart = 0.0;
+    if (tid < 2 * TS) {
+        const int cidx = tid % TS, half = tid / TS;
+        for (int r = rowl_ptr[K] + half; r < rowl_ptr[K + 1]; r += 2) bpart += contrib[(size_t)rowl_slot[r] * TS + cidx];
+    }
+    for (int s = sb; s < se; ++s) {
+        if (s > sb) __syncthreads();
         tile_sts(B0, rp);
         if (upd) tile_sts(B1, ri);
         __syncthreads();
+        const bool upd_now = upd;
+        if (s + 1 < se) {
+            const int P = psrc[s + 1];
+            tile_ldg(rp, Stiles + (size_t)tile_index[K * nt + P] * TS * TS);
+            const int sl = diagcta ? -1 : tile_index[I * nt + P];
+            upd = sl >= 0;
+            if (upd) tile_ldg(ri, Stiles + (size_t)sl * TS * TS);
+        }
         double acc[6][3], acc2[6][3];
-        if (upd) tile_abt<true>(B0, B1, B0, acc, acc2);
+        if (upd_now) tile_abt<true>(B0, B1, B0, acc, acc2);
         else tile_abt<false>(B0, B0, B0, acc, acc2);
 #pragma unroll
         for (int p = 0; p < 6; ++p)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { d[p][q] -= acc[p][q]; if (upd) a[p][q] -= acc2[p][q]; }
+            for (int q = 0; q < 3; ++q) { d[p][q] -= acc[p][q]; if (upd_now) a[p][q] -= acc2[p][q]; }
     }
     // ---- hand the updated blocks over to the ROW-OWNER layout of the sweep: thread t < 48 owns row t of
     // D, thread 48+r owns row r of A_IK, thread 96 owns the right-hand-side row b_K^T
@@ -294,17 +497,19 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
     for (int p = 0; p < 6; ++p)
 #pragma unroll
         for (int q = 0; q < 3; ++q) { B0[(tr * 6 + p) * LDT + tc * 3 + q] = d[p][q]; B1[(tr * 6 + p) * LDT + tc * 3 + q] = a[p][q]; }
+    if (tid < 2 * TS) colbuf[0][tid] = bpart;
     __syncthreads();
     const bool active = tid < TS || (tid < 2 * TS && !diagcta) || tid == 2 * TS;
     double row[TS];
     if (tid == 2 * TS) {
 #pragma unroll
-        for (int c = 0; c < TS; ++c) row[c] = bwork[K * TS + c];
+        for (int c = 0; c < TS; ++c) row[c] = b0[K * TS + c] - (colbuf[0][c] + colbuf[0][TS + c]);
     } else {
         const double *src = tid < TS ? B0 + tid * LDT : B1 + (tid - TS) * LDT;
 #pragma unroll
         for (int c = 0; c < TS; ++c) row[c] = active ? src[c] : 0.0;
     }
+    __syncthreads();                                           // colbuf[0] is reused by the sweep
     // ---- column sweep over the stacked panel [D ; A_IK ; b^T] (97 x 48), one row per thread in registers.
     // Step j: every thread publishes its entry of column j (ONE 8-byte shared store per thread: the
     // barrier drains pending stores at ~19 cycles each, see tools/microbench/sweep_bench.cu), then
@@ -330,7 +535,7 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
         }
     }
     if (__syncthreads_or(bad)) { if (tid == 0) *status = 1; return; }
-    // ---- results: factor rows to global, y_K to shared, then b_I -= L_IK y_K
+    // ---- results: factor rows to global, y_K to shared, then the contribution L_IK y_K of this tile
     double *ysh = colbuf[0];
     if (tid == 2 * TS) {
 #pragma unroll
@@ -354,7 +559,7 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel(int K, int nt, int ncrit, co
         double s = 0.0;
 #pragma unroll
         for (int c = 0; c < TS; c += 2) { dst[c / 2] = make_double2(row[c], row[c + 1]); s += row[c] * ysh[c] + row[c + 1] * ysh[c + 1]; }
-        bwork[I * TS + (tid - TS)] -= s;
+        contrib[(size_t)tile_index[I * nt + K] * TS + (tid - TS)] = s;
     }
 }
 // L_KK^-1 for every diagonal tile (needed by the backward substitution only): one CTA per tile,
@@ -372,16 +577,26 @@ __global__ void __launch_bounds__(256) k_diag_inverse(const double *__restrict__
     tile_stg<256>(Linv + (size_t)blockIdx.x * TS * TS, B1);
 }
 
+// b0 = ea in the camera ordering of S (zero on the padding)
+__global__ void k_init_rhs(int npad, const int *__restrict__ pos2cam, const double *__restrict__ ea, double *__restrict__ b)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= npad) return;
+    const int cam = pos2cam[k / 6];
+    b[k] = cam >= 0 ? ea[cam * 6 + k % 6] : 0.0;
+}
+
 static void enqueue_factor(psba_ctx *c)
 {
     const int npad = c->nt * TS;
-    k_init_rhs<<<cdiv(npad, 256), 256, 0, c->stream>>>(c->N, npad, c->eab, c->chol_aux);
-    for (int K = 0; K < c->nt; ++K) {
-        const int ncrit = c->crit_ptr[K + 1] - c->crit_ptr[K];
-        const int nncr = c->ncr_ptr[K + 1] - c->ncr_ptr[K];
-        k_panel<<<ncrit + nncr, PANEL_NT, CHOL_SMEM, c->stream>>>(K, c->nt, ncrit, c->d_crit_rows + c->crit_ptr[K],
-                                                                 c->d_ncr_I + c->ncr_ptr[K], c->d_ncr_J + c->ncr_ptr[K], c->tile_index,
-                                                                 c->Stiles, c->Ldiag, c->chol_aux, c->chol_diag, c->d_status);
+    k_init_rhs<<<cdiv(npad, 256), 256, 0, c->stream>>>(npad, c->pos2cam, c->eab, c->chol_aux);
+    for (int s = 0; s < c->n_steps; ++s) {
+        const int cb = c->step_crit_ptr[s], ncrit = c->step_crit_ptr[s + 1] - cb;
+        const int db = c->step_def_ptr[s], ndef = c->step_def_ptr[s + 1] - db;
+        k_panel_step<<<ncrit + ndef, PANEL_NT, CHOL_SMEM, c->stream>>>(c->nt, ncrit, c->d_crit_I + cb, c->d_crit_K + cb, c->d_psrc_ptr, c->d_psrc,
+                                                                      c->d_rowl_ptr, c->d_rowl_slot, c->d_def_I + db, c->d_def_J + db,
+                                                                      c->d_def_sptr + db, c->d_def_src, c->tile_index, c->Stiles, c->Ldiag,
+                                                                      c->chol_aux, c->chol_diag, c->contrib, c->d_status);
     }
     k_diag_inverse<<<c->nt, 256, 2 * TILE_SM * sizeof(double), c->stream>>>(c->Ldiag, c->Linv, c->d_status);
 }
@@ -390,7 +605,7 @@ double psba_launch_factor(psba_ctx *c)
 {
     CUDA_CHECK(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream));
     if (!c->chol_graph_ok) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(k_panel_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_SMEM));
         cudaGraph_t graph;
         CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         enqueue_factor(c);
@@ -400,7 +615,7 @@ double psba_launch_factor(psba_ctx *c)
         c->chol_graph_ok = true;
     }
     PROF(c, KID_FACTOR) CUDA_CHECK(cudaGraphLaunch(c->chol_graph, c->stream));
-    c->st_launches += c->nt + 2;
+    c->st_launches += c->n_steps + 2;
     int st = 0;
     CUDA_CHECK(cudaMemcpyAsync(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -410,20 +625,71 @@ double psba_launch_factor(psba_ctx *c)
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward substitution x_I = L_II^-T (y_I - sum_{J>I} L_JI^T x_J), one persistent CTA of 960 threads
-// = 48 columns x 20 tile slots: every thread streams one tile column (48 independent coalesced loads in
-// flight, four independent FMA chains), partial sums are combined in a fixed order.  L_II^-1 does not
-// depend on x and is prefetched into shared memory while the tile column streams.
+// backward substitution x_I = L_II^-T (y_I - sum_{J>I} L_JI^T x_J).  A CTA of 960 threads = 48 columns x 20
+// tile slots handles one panel: every thread streams one tile column (48 independent coalesced loads in
+// flight, four independent FMA chains), partial sums are combined in a fixed order; L_II^-1 does not depend
+// on x and is prefetched into shared memory while the tile column streams.  The solution leaves in the
+// callers' camera order (pos2cam).
+//   chain schedule (dense S): ONE persistent CTA walks the panels from last to first;
+//   otherwise: one launch per step in reverse order, one CTA per panel of the step (all in one CUDA graph).
 #define BW_SLOTS 20
-__global__ void __launch_bounds__(TS * BW_SLOTS) k_backward(int N, int nt, const int *__restrict__ cptr, const int *__restrict__ crow,
-                                                           const int *__restrict__ cslot, const double *__restrict__ Stiles,
-                                                           const double *__restrict__ Linv, double *__restrict__ ywork, double *__restrict__ sol)
+struct bw_smem {
+    double part[BW_SLOTS][TS];
+    double acc[TS];
+    double invs[TS * TS];
+    double mv[4][TS];
+};
+
+__device__ __forceinline__ void backward_panel(bw_smem &sm, int I, int beg, int end, int myslot, int myrow, const int *__restrict__ crow,
+                                               const int *__restrict__ cslot, const double *__restrict__ Stiles,
+                                               const double *__restrict__ Linv, double *__restrict__ ywork,
+                                               const int *__restrict__ pos2cam, double *__restrict__ sol)
 {
-    __shared__ double part[BW_SLOTS][TS];
-    __shared__ double acc[TS];
-    __shared__ double invs[TS * TS];
-    __shared__ double mv[4][TS];
     const int tid = threadIdx.x, col = tid % TS, slotid = tid / TS;
+    for (int e = tid; e < TS * TS; e += TS * BW_SLOTS) sm.invs[e] = __ldg(Linv + (size_t)I * TS * TS + e);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int t = beg + slotid; t < end; t += BW_SLOTS) {
+        const bool first = t == beg + slotid;
+        const double *L = Stiles + (size_t)(first ? myslot : cslot[t]) * TS * TS + col;
+        const double *x = ywork + (first ? myrow : crow[t]) * TS;
+        double lv[TS];
+#pragma unroll
+        for (int r = 0; r < TS; ++r) lv[r] = __ldg(L + r * TS);
+#pragma unroll
+        for (int r = 0; r < TS; r += 4) { s0 += lv[r] * x[r]; s1 += lv[r + 1] * x[r + 1]; s2 += lv[r + 2] * x[r + 2]; s3 += lv[r + 3] * x[r + 3]; }
+    }
+    sm.part[slotid][col] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (tid < TS) {
+        double a = 0.0;
+#pragma unroll
+        for (int p = 0; p < BW_SLOTS; ++p) a += sm.part[p][tid];
+        sm.acc[tid] = ywork[I * TS + tid] - a;
+    }
+    __syncthreads();
+    if (tid < 4 * TS) {          // x_I[c] = sum_{r >= c} Linv[r][c] acc[r], rows split over 4 partial sums
+        const int cidx = tid % TS, q = tid / TS;
+        double a = 0.0;
+        for (int r = cidx + q; r < TS; r += 4) a += sm.invs[r * TS + cidx] * sm.acc[r];
+        sm.mv[q][cidx] = a;
+    }
+    __syncthreads();
+    if (tid < TS) {
+        const double a = (sm.mv[0][tid] + sm.mv[1][tid]) + (sm.mv[2][tid] + sm.mv[3][tid]);
+        ywork[I * TS + tid] = a;
+        const int pos = I * TS + tid, cam = pos2cam[pos / 6];
+        if (cam >= 0) sol[cam * 6 + pos % 6] = a;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TS * BW_SLOTS) k_backward(int nt, const int *__restrict__ cptr, const int *__restrict__ crow,
+                                                           const int *__restrict__ cslot, const double *__restrict__ Stiles,
+                                                           const double *__restrict__ Linv, double *__restrict__ ywork,
+                                                           const int *__restrict__ pos2cam, double *__restrict__ sol)
+{
+    __shared__ bw_smem sm;
+    const int slotid = threadIdx.x / TS;
     // tile indices of a column do not depend on x: they are fetched one step ahead so that the only
     // dependent global accesses inside a step are the tile column itself and the x vectors
     int nbeg = cptr[nt - 1], nend = cptr[nt];
@@ -436,47 +702,46 @@ __global__ void __launch_bounds__(TS * BW_SLOTS) k_backward(int N, int nt, const
             nslot = -1;
             if (nbeg + slotid < nend) { nslot = cslot[nbeg + slotid]; nrow = crow[nbeg + slotid]; }
         }
-        for (int e = tid; e < TS * TS; e += TS * BW_SLOTS) invs[e] = __ldg(Linv + (size_t)I * TS * TS + e);
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        for (int t = beg + slotid; t < end; t += BW_SLOTS) {
-            const bool first = t == beg + slotid;
-            const double *L = Stiles + (size_t)(first ? myslot : cslot[t]) * TS * TS + col;
-            const double *x = ywork + (first ? myrow : crow[t]) * TS;
-            double lv[TS];
-#pragma unroll
-            for (int r = 0; r < TS; ++r) lv[r] = __ldg(L + r * TS);
-#pragma unroll
-            for (int r = 0; r < TS; r += 4) { s0 += lv[r] * x[r]; s1 += lv[r + 1] * x[r + 1]; s2 += lv[r + 2] * x[r + 2]; s3 += lv[r + 3] * x[r + 3]; }
-        }
-        part[slotid][col] = (s0 + s1) + (s2 + s3);
-        __syncthreads();
-        if (tid < TS) {
-            double a = 0.0;
-#pragma unroll
-            for (int p = 0; p < BW_SLOTS; ++p) a += part[p][tid];
-            acc[tid] = ywork[I * TS + tid] - a;
-        }
-        __syncthreads();
-        if (tid < 4 * TS) {          // x_I[c] = sum_{r >= c} Linv[r][c] acc[r], rows split over 4 partial sums
-            const int cidx = tid % TS, q = tid / TS;
-            double a = 0.0;
-            for (int r = cidx + q; r < TS; r += 4) a += invs[r * TS + cidx] * acc[r];
-            mv[q][cidx] = a;
-        }
-        __syncthreads();
-        if (tid < TS) {
-            const double a = (mv[0][tid] + mv[1][tid]) + (mv[2][tid] + mv[3][tid]);
-            ywork[I * TS + tid] = a;
-            const int gr = I * TS + tid;
-            if (gr < N) sol[gr] = a;
-        }
-        __syncthreads();
+        backward_panel(sm, I, beg, end, myslot, myrow, crow, cslot, Stiles, Linv, ywork, pos2cam, sol);
     }
+}
+
+__global__ void __launch_bounds__(TS * BW_SLOTS) k_backward_step(const int *__restrict__ panels, const int *__restrict__ cptr,
+                                                                const int *__restrict__ crow, const int *__restrict__ cslot,
+                                                                const double *__restrict__ Stiles, const double *__restrict__ Linv,
+                                                                double *__restrict__ ywork, const int *__restrict__ pos2cam,
+                                                                double *__restrict__ sol)
+{
+    __shared__ bw_smem sm;
+    const int slotid = threadIdx.x / TS;
+    const int I = panels[blockIdx.x];
+    const int beg = cptr[I], end = cptr[I + 1];
+    int myslot = -1, myrow = 0;
+    if (beg + slotid < end) { myslot = cslot[beg + slotid]; myrow = crow[beg + slotid]; }
+    backward_panel(sm, I, beg, end, myslot, myrow, crow, cslot, Stiles, Linv, ywork, pos2cam, sol);
 }
 
 void psba_launch_solve(psba_ctx *c)
 {
-    PROF(c, KID_TRI_SOLVE) k_backward<<<1, TS * BW_SLOTS, 0, c->stream>>>(c->N, c->nt, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
-                                                               c->Stiles, c->Linv, c->chol_diag, c->dp);
-    c->st_launches += 1;
+    if (c->chain_schedule) {
+        PROF(c, KID_TRI_SOLVE) k_backward<<<1, TS * BW_SLOTS, 0, c->stream>>>(c->nt, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
+                                                                   c->Stiles, c->Linv, c->chol_diag, c->pos2cam, c->dp);
+        c->st_launches += 1;
+        return;
+    }
+    if (!c->bw_graph_ok) {
+        cudaGraph_t graph;
+        CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        for (int s = c->n_steps - 1; s >= 0; --s) {
+            const int pb = c->step_panel_ptr[s], np = c->step_panel_ptr[s + 1] - pb;
+            k_backward_step<<<np, TS * BW_SLOTS, 0, c->stream>>>(c->d_step_panels + pb, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
+                                                               c->Stiles, c->Linv, c->chol_diag, c->pos2cam, c->dp);
+        }
+        CUDA_CHECK(cudaStreamEndCapture(c->stream, &graph));
+        CUDA_CHECK(cudaGraphInstantiate(&c->bw_graph, graph, 0));
+        CUDA_CHECK(cudaGraphDestroy(graph));
+        c->bw_graph_ok = true;
+    }
+    PROF(c, KID_TRI_SOLVE) CUDA_CHECK(cudaGraphLaunch(c->bw_graph, c->stream));
+    c->st_launches += c->n_steps;
 }

@@ -154,13 +154,23 @@ static void launch_pairs(psba_ctx *c)
                                                                           c->Vinv, c->g + c->N, c->pair_part);
 }
 
+// position of entry (r,cc) of the camera block (k,l) inside the tile pool: the camera system is stored in
+// the solver's camera ordering (cam2pos); a block that lands above the diagonal is stored transposed
+__device__ __forceinline__ double *s_entry(double *Stiles, const int *__restrict__ tile_index, int nt, int pk, int pl, int r, int cc)
+{
+    if (pk < pl) { int t = pk; pk = pl; pl = t; t = r; r = cc; cc = t; }
+    const int slot = tile_index[(pk / 8) * nt + pl / 8];
+    return Stiles + (size_t)slot * TS * TS + ((pk % 8) * 6 + r) * TS + (pl % 8) * 6 + cc;
+}
+
 // per pair block: fixed-order sum of its chunk partials, S_kl = [k==l](U_k + mu I) - sum, written
 // into the 48x48 tile pool; ea_k = ga_k - sum_e.  with_U=0 writes only the (negated) local sums
 // (multi-GPU: all-reduce first, then k_add_U).
 __global__ void k_S_finalize(int n_pair, const int *__restrict__ pair_k, const int *__restrict__ pair_l,
                              const int *__restrict__ pair_chunk_ptr, const double *__restrict__ part,
                              const double *__restrict__ U, const double *__restrict__ ga, double mu, int with_U,
-                             const int *__restrict__ tile_index, int nt, double *__restrict__ Stiles, double *__restrict__ ea)
+                             const int *__restrict__ tile_index, const int *__restrict__ cam2pos, int nt,
+                             double *__restrict__ Stiles, double *__restrict__ ea)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int pr = t / 42, v = t - pr * 42;
@@ -173,9 +183,7 @@ __global__ void k_S_finalize(int n_pair, const int *__restrict__ pair_k, const i
         const int r = v / 6, cc = v - r * 6;
         double val = -s;
         if (k == l && with_U) { val = U[k * 36 + r * 6 + cc] - s; if (r == cc) val = (U[k * 36 + r * 6 + cc] + mu) - s; }
-        const int I = k / 8, J = l / 8;
-        const int slot = tile_index[I * nt + J];
-        Stiles[(size_t)slot * TS * TS + ((k % 8) * 6 + r) * TS + (l % 8) * 6 + cc] = val;
+        *s_entry(Stiles, tile_index, nt, cam2pos[k], cam2pos[l], r, cc) = val;
     } else {
         const int r = v - 36;
         ea[k * 6 + r] = with_U ? ga[k * 6 + r] - s : -s;
@@ -184,26 +192,26 @@ __global__ void k_S_finalize(int n_pair, const int *__restrict__ pair_k, const i
 
 // multi-GPU second half: add U_k + mu I to the diagonal blocks and ga to ea (after the all-reduce)
 __global__ void k_add_U(int m, const double *__restrict__ U, const double *__restrict__ ga, double mu,
-                        const int *__restrict__ tile_index, int nt, double *__restrict__ Stiles, double *__restrict__ ea)
+                        const int *__restrict__ tile_index, const int *__restrict__ cam2pos, int nt,
+                        double *__restrict__ Stiles, double *__restrict__ ea)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int k = t / 42, v = t - k * 42;
     if (k >= m) return;
     if (v < 36) {
         const int r = v / 6, cc = v - r * 6;
-        const int slot = tile_index[(k / 8) * nt + (k / 8)];
-        double *p = Stiles + (size_t)slot * TS * TS + ((k % 8) * 6 + r) * TS + (k % 8) * 6 + cc;
+        double *p = s_entry(Stiles, tile_index, nt, cam2pos[k], cam2pos[k], r, cc);
         double u = U[k * 36 + v];
         if (r == cc) u += mu;
         *p = u + *p;
     } else ea[k * 6 + (v - 36)] += ga[k * 6 + (v - 36)];
 }
 
-// identity on the padded tail of the last diagonal tile so that the factorisation is well defined
-__global__ void k_pad_diag(int N, int nt, const int *__restrict__ tile_index, double *__restrict__ Stiles)
+// identity on the padding rows (block positions without a camera) so that the factorisation is well defined
+__global__ void k_pad_diag(int nt, const int *__restrict__ pos2cam, const int *__restrict__ tile_index, double *__restrict__ Stiles)
 {
-    int r = N + threadIdx.x;
-    if (r >= nt * TS) return;
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nt * TS || pos2cam[r / 6] >= 0) return;
     int I = r / TS;
     Stiles[(size_t)tile_index[I * nt + I] * TS * TS + (r % TS) * TS + (r % TS)] = 1.0;
 }
@@ -226,16 +234,16 @@ void psba_launch_schur(psba_ctx *c, double mu)
     const int single = c->nranks == 1;
     PROF(c, KID_S_FINALIZE) k_S_finalize<<<cdiv((long long)c->n_pair * 42, 128), 128, 0, c->stream>>>(c->n_pair, c->pair_k, c->pair_l, c->pair_chunk_ptr,
                                                                              c->pair_part, c->U, c->g, mu, single, c->tile_index,
-                                                                             c->nt, c->Stiles, c->eab);
+                                                                             c->cam2pos, c->nt, c->Stiles, c->eab);
     c->st_launches += 3;
     if (!single) {
         // the tile pool and ea are contiguous-by-construction only separately: two all-reduces
         psba_allreduce_sum(c, c->Stiles, (size_t)c->n_tiles * TS * TS);
         psba_allreduce_sum(c, c->eab, (size_t)c->N);
-        k_add_U<<<cdiv(c->m * 42, 128), 128, 0, c->stream>>>(c->m, c->U, c->g, mu, c->tile_index, c->nt, c->Stiles, c->eab);
+        k_add_U<<<cdiv(c->m * 42, 128), 128, 0, c->stream>>>(c->m, c->U, c->g, mu, c->tile_index, c->cam2pos, c->nt, c->Stiles, c->eab);
         c->st_launches += 1;
     }
-    if (c->nt * TS > c->N) { k_pad_diag<<<1, TS, 0, c->stream>>>(c->N, c->nt, c->tile_index, c->Stiles); c->st_launches += 1; }
+    if (c->nt * TS > c->N) { k_pad_diag<<<cdiv(c->nt * TS, 256), 256, 0, c->stream>>>(c->nt, c->pos2cam, c->tile_index, c->Stiles); c->st_launches += 1; }
     c->S_valid = true; c->factor_valid = false;
 }
 

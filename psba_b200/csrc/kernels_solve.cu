@@ -20,15 +20,19 @@
 
 // ---------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------
-// tile pool -> dense N x N row-major (lower triangle; mirror fills the upper one)
-__global__ void k_tiles_to_dense(int N, int nt, const int *__restrict__ tile_index, const double *__restrict__ Stiles,
-                                 double *__restrict__ dense, int mirror, const double *__restrict__ Ldiag)
+// tile pool -> dense N x N row-major.  cam2pos != null: rows/columns in the CALLERS' camera order (S of the
+// ABI and of the modified Cholesky; mirror fills the upper triangle); cam2pos == null: the solver's own
+// ordering (the factor L, lower triangle, diagonal tiles from Ldiag).
+__global__ void k_tiles_to_dense(int N, int nt, const int *__restrict__ tile_index, const int *__restrict__ cam2pos,
+                                 const double *__restrict__ Stiles, double *__restrict__ dense, int mirror, const double *__restrict__ Ldiag)
 {
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long long)N * N) return;
     const int r = (int)(e / N), cc = (int)(e % N);
+    if (cc > r && !mirror) { dense[e] = 0.0; return; }
     int rr = r, c2 = cc;
-    if (cc > r) { if (!mirror) { dense[e] = 0.0; return; } rr = cc; c2 = r; }
+    if (cam2pos) { rr = cam2pos[r / 6] * 6 + r % 6; c2 = cam2pos[cc / 6] * 6 + cc % 6; }
+    if (c2 > rr) { const int t = rr; rr = c2; c2 = t; }
     if (Ldiag && rr / TS == c2 / TS) { dense[e] = Ldiag[(size_t)(rr / TS) * TS * TS + (rr % TS) * TS + c2 % TS]; return; }
     const int slot = tile_index[(rr / TS) * nt + c2 / TS];
     dense[e] = slot < 0 ? 0.0 : Stiles[(size_t)slot * TS * TS + (rr % TS) * TS + c2 % TS];
@@ -37,46 +41,54 @@ __global__ void k_tiles_to_dense(int N, int nt, const int *__restrict__ tile_ind
 void psba_tiles_to_dense(psba_ctx *c, double *dense_dev, bool mirror)
 {
     long long tot = (long long)c->N * c->N;
-    k_tiles_to_dense<<<cdiv(tot, 256), 256, 0, c->stream>>>(c->N, c->nt, c->tile_index, c->Stiles, dense_dev, mirror ? 1 : 0, nullptr);
+    k_tiles_to_dense<<<cdiv(tot, 256), 256, 0, c->stream>>>(c->N, c->nt, c->tile_index, c->cam2pos, c->Stiles, dense_dev, mirror ? 1 : 0, nullptr);
     c->st_launches += 1;
 }
 
-// the factor L as a dense lower-triangular matrix (diagonal tiles live in their own pool)
+// the factor L as a dense lower-triangular matrix of size npad = nt*TS in the solver's ordering
+// (diagonal tiles live in their own pool)
 static void psba_factor_to_dense(psba_ctx *c, double *dense_dev)
 {
-    long long tot = (long long)c->N * c->N;
-    k_tiles_to_dense<<<cdiv(tot, 256), 256, 0, c->stream>>>(c->N, c->nt, c->tile_index, c->Stiles, dense_dev, 0, c->Ldiag);
+    const int npad = c->nt * TS;
+    long long tot = (long long)npad * npad;
+    k_tiles_to_dense<<<cdiv(tot, 256), 256, 0, c->stream>>>(npad, c->nt, c->tile_index, nullptr, c->Stiles, dense_dev, 0, c->Ldiag);
     c->st_launches += 1;
 }
 
-// ABI parity only (SPDinv's explicit inverse, cl_spdinv.cpp:18-40): column cidx of S^-1 by one
-// forward and one backward substitution on the dense factor.  O(N^2) per thread; small N only.
-__global__ void k_explicit_inverse(int N, const double *__restrict__ L, double *__restrict__ work, double *__restrict__ out)
+// ABI parity only (SPDinv's explicit inverse, cl_spdinv.cpp:18-40): column of S^-1 for (camera, component)
+// cidx by one forward and one backward substitution on the dense factor (solver's ordering, padded size
+// NP), written back in the callers' camera order.  O(NP^2) per thread; small N only.
+__global__ void k_explicit_inverse(int N, int NP, const int *__restrict__ cam2pos, const double *__restrict__ L,
+                                   double *__restrict__ work, double *__restrict__ out)
 {
     int cidx = blockIdx.x * blockDim.x + threadIdx.x;
     if (cidx >= N) return;
-    double *x = work + (size_t)cidx * N;
-    for (int r = 0; r < N; ++r) {
-        double s = (r == cidx) ? 1.0 : 0.0;
-        for (int k = 0; k < r; ++k) s -= L[(size_t)r * N + k] * x[k];
-        x[r] = s / L[(size_t)r * N + r];
+    const int pc = cam2pos[cidx / 6] * 6 + cidx % 6;
+    double *x = work + (size_t)cidx * NP;
+    for (int r = 0; r < NP; ++r) {
+        double s = (r == pc) ? 1.0 : 0.0;
+        for (int k = 0; k < r; ++k) s -= L[(size_t)r * NP + k] * x[k];
+        x[r] = s / L[(size_t)r * NP + r];
     }
-    for (int r = N - 1; r >= 0; --r) {
+    for (int r = NP - 1; r >= 0; --r) {
         double s = x[r];
-        for (int k = r + 1; k < N; ++k) s -= L[(size_t)k * N + r] * x[k];
-        x[r] = s / L[(size_t)r * N + r];
+        for (int k = r + 1; k < NP; ++k) s -= L[(size_t)k * NP + r] * x[k];
+        x[r] = s / L[(size_t)r * NP + r];
     }
-    for (int r = 0; r < N; ++r) out[(size_t)r * N + cidx] = x[r];
+    for (int r = 0; r < N; ++r) out[(size_t)r * N + cidx] = x[cam2pos[r / 6] * 6 + r % 6];
 }
 
 void psba_launch_explicit_inverse(psba_ctx *c, double *out_dev)
 {
-    const size_t nn = (size_t)c->N * c->N;
-    if (!c->Sdense) CUDA_CHECK(cudaMalloc(&c->Sdense, nn * sizeof(double)));
-    if (!c->Sdense_aux) CUDA_CHECK(cudaMalloc(&c->Sdense_aux, nn * sizeof(double)));
-    psba_factor_to_dense(c, c->Sdense);
-    k_explicit_inverse<<<cdiv(c->N, 64), 64, 0, c->stream>>>(c->N, c->Sdense, c->Sdense_aux, out_dev);
+    const size_t NP = (size_t)c->nt * TS;
+    double *Ld = nullptr, *work = nullptr;
+    CUDA_CHECK(cudaMalloc(&Ld, NP * NP * sizeof(double)));
+    CUDA_CHECK(cudaMalloc(&work, NP * NP * sizeof(double)));
+    psba_factor_to_dense(c, Ld);
+    k_explicit_inverse<<<cdiv(c->N, 64), 64, 0, c->stream>>>(c->N, (int)NP, c->cam2pos, Ld, work, out_dev);
     c->st_launches += 1;
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    CUDA_CHECK(cudaFree(Ld)); CUDA_CHECK(cudaFree(work));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -62,7 +62,7 @@ extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3D
     c->nranks = psba_comm_active() ? psba_comm_size() : 1;
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->cur = 0; c->cache_valid[0] = c->cache_valid[1] = false;
-    c->lin_valid = false; c->S_valid = false; c->factor_valid = false; c->chol_graph_ok = false;
+    c->lin_valid = false; c->S_valid = false; c->factor_valid = false; c->chol_graph_ok = false; c->bw_graph_ok = false;
     c->Sdense = c->Sdense_aux = nullptr; c->tmpA = c->tmpB = nullptr;
     c->mu_pending = 0.0; c->coeff_uvw = 1.0; c->coeff_g = 1.0;
     c->itno = 0; c->max_iter = 50; c->verbose = 0; c->lm_only = 0; c->initErr = 0.0;
@@ -279,12 +279,14 @@ extern "C" void psba_release_buffer(psba_ctx *c)
                     c->iidx, c->jidx, c->pt_ptr, c->ptchunk, c->cam_obs, c->cchunk_cam, c->cchunk_beg, c->cchunk_end,
                     c->cam_cchunk_ptr, c->tri_oa, c->tri_ob, c->pair_k, c->pair_l, c->pair_chunk_ptr, c->pchunk_pair,
                     c->pchunk_beg, c->pchunk_end, c->W, c->V, c->Vinv, c->U, c->g, c->UVdiag_scr, c->cam_part, c->pair_part,
-                    c->tile_index, c->Stiles, c->Linv, c->eab, c->dp, c->d_status, c->d_crit_rows, c->d_ncr_I, c->d_ncr_J, c->Ldiag,
-                    c->d_rowtile_ptr, c->d_rowtile_col, c->d_rowtile_slot, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
+                    c->tile_index, c->Stiles, c->Linv, c->eab, c->dp, c->d_status, c->Ldiag, c->cam2pos, c->pos2cam, c->d_crit_I, c->d_crit_K,
+                    c->d_psrc_ptr, c->d_psrc, c->d_rowl_ptr, c->d_rowl_slot, c->d_def_I, c->d_def_J, c->d_def_sptr, c->d_def_src,
+                    c->d_step_panels, c->contrib, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
                     c->Sdense, c->Sdense_aux, c->chol_aux, c->chol_diag, c->chol_E, c->d_part, c->d_scal, c->P_U, c->P_B, c->P,
                     c->tmpA, c->tmpB};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->chol_graph_ok) cudaGraphExecDestroy(c->chol_graph);
+    if (c->bw_graph_ok) cudaGraphExecDestroy(c->bw_graph);
     cudaFreeHost(c->h_scal);
     cudaStreamDestroy(c->stream);
     g_stage.erase(c);
@@ -583,6 +585,7 @@ extern "C" double psba_get_stat(psba_ctx *c, const char *name)
     if (s == "n_pairs") return c->n_pair;
     if (s == "n_tiles") return c->n_tiles;
     if (s == "nt") return c->nt;
+    if (s == "n_steps") return c->n_steps;
     if (s == "n_ptchunk") return c->n_ptchunk;
     if (s == "n_cchunk") return c->n_cchunk;
     if (s == "n_pchunk") return c->n_pchunk;

@@ -83,13 +83,23 @@ struct psba_ctx {
     double *Linv;                   // nt * TS*TS   inverse of the diagonal factor tiles
     double *eab, *dp;               // T_loc-sized vectors laid out [N | 3n]
     int *d_status;                  // device int: 0 ok, 1 not PD
-    // per-panel task lists (host + device): critical CTAs of panel K = {K} + rows I>K with tile (I,K);
-    // deferred updates of panel K = trailing tiles (I,J), J>K, touched by panel K-1
-    std::vector<int> crit_ptr, ncr_ptr;
-    int *d_crit_rows; int *d_ncr_I, *d_ncr_J;
+    // camera ordering of S (nested dissection at tile granularity): cam2pos[j] = block position of camera j,
+    // pos2cam[p] = camera at block position p (-1: padding).  tile_index is in permuted coordinates.
+    int *cam2pos, *pos2cam;
+    std::vector<int> h_cam2pos;
+    // step schedule of the factorisation: panels whose dependencies are met run in the same launch.
+    //   critical task (I,K): tile row I of panel K (I == K: the diagonal CTA)
+    //   panel sources      : panels P of the previous step with a tile (K,P) (their updates are still pending)
+    //   row list of K      : slots of the tiles (K,P), P < K (forward-substitution contributions)
+    //   deferred task (I,J): trailing tile touched by panels of the previous step, J in a later step
+    int n_steps; bool chain_schedule;          // chain: one panel per step (dense S)
+    std::vector<int> step_crit_ptr, step_def_ptr, step_panel_ptr;
+    int *d_crit_I, *d_crit_K, *d_psrc_ptr, *d_psrc, *d_rowl_ptr, *d_rowl_slot;
+    int *d_def_I, *d_def_J, *d_def_sptr, *d_def_src, *d_step_panels;
+    double *contrib;                // n_tiles * TS: L_IK y_K per factor tile
     double *Ldiag;                  // nt * TS*TS   factor of the diagonal tiles (kept out of the tile pool)
-    int *d_rowtile_ptr, *d_rowtile_col, *d_rowtile_slot;   // CSR of L tiles by row (for the solves)
-    int *d_coltile_ptr, *d_coltile_row, *d_coltile_slot;   // CSC (for the backward solve)
+    int *d_coltile_ptr, *d_coltile_row, *d_coltile_slot;   // CSC of the factor tiles (backward solve)
+    cudaGraphExec_t bw_graph; bool bw_graph_ok;
     cudaGraphExec_t chol_graph; bool chol_graph_ok;
     bool S_valid, factor_valid;
     double *Sdense, *Sdense_aux;    // N*N, only allocated on demand (compat / cholmod)

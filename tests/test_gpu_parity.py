@@ -220,3 +220,45 @@ def test_bal_synthetic_structure_full_solve(name):
         assert abs(a["err"] - b["err"]) / a["err"] < 1e-9
         assert abs(a["mu"] - b["mu"]) / a["mu"] < 1e-9
     G.close(); O.close()
+
+
+@pytest.mark.parametrize("nd_min", ["0", "2", "12"])
+def test_banded_ring_nested_dissection_solve(nd_min, monkeypatch):
+    """Block-banded camera system (ring of 160 cameras, window 12): the solver orders the 48x48 tiles by nested
+    dissection and runs independent panels in the same step.  Every ordering (natural, deepest, default) must
+    give the reference's S, S^-1, dpa and LM costs."""
+    from psba_b200 import synth
+    monkeypatch.setenv("PSBA_ND_MIN", nd_min)
+    prob = synth.ring_problem(m=160, n=6000, d=4, w=12, seed=7)
+    O = oracle.Problem(prob)
+    O.set("nthreads", 8)
+    G = psba_b200.PSBA(prob)
+    nsteps, nt = int(G.stat("n_steps")), int(G.stat("nt"))
+    assert nt == 20
+    assert nsteps == nt if nd_min == "0" else nsteps < nt
+    O.call("exQT"); O.call("jacobiQT"); O.call("U", 1); O.call("V", 1); O.call("Wblks", 1); O.call("g", 1)
+    mu = 1e-3 * float(np.max(O.buf("UVdiag")))
+    O.call("update_UV", mu); O.call("Vinv"); O.call("Yblks"); O.call("S"); O.call("ea")
+    So = O.buf("S").copy()
+    G.compute_jacobiQT(); G.compute_U(1.0); G.update_UV(mu); G.compute_Vinv()
+    S = G.compute_S()
+    assert relerr(np.tril(S), np.tril(So)) < 1e-10
+    ea = G.compute_ea()
+    ret, Sinv = G.SPDinv(want=True)
+    assert ret == 0.0
+    Sfull = np.tril(So) + np.tril(So, -1).T
+    ref_inv = np.linalg.inv(Sfull)
+    assert relerr(Sinv, ref_inv) < 1e-8
+    dpa = G.matVec_mul()
+    assert relerr(dpa, ref_inv @ ea) < 1e-8
+    G.restore_UVdiag()
+    G.close()
+    # LM iterations: costs and damping sequence against the oracle
+    G = psba_b200.PSBA(prob)
+    assert O.levmar() == G.levmar()[0]          # 5 accepted LM iterations, then ITER_TURN_TO_TR
+    to, tg = O.trace(), G.trace()
+    assert pattern(tg) == pattern(to) and len(to) >= 5
+    for a, b in zip(to, tg):
+        assert abs(a["err"] - b["err"]) / a["err"] < 1e-9
+        assert abs(a["mu"] - b["mu"]) / a["mu"] < 1e-9
+    G.close(); O.close()
