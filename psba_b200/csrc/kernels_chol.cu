@@ -183,19 +183,17 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
     c->chain_schedule = true;
     for (auto &v : by_step) if (v.size() != 1) c->chain_schedule = false;
     // ---- task lists
-    std::vector<int> critI, critK, psrc_ptr(1, 0), psrc, rowl_ptr(1, 0), rowl_slot;
+    std::vector<int> critI, critK, psrc_ptr(1, 0), psrc;
     std::vector<int> defI, defJ, def_sptr(1, 0), def_src, step_panels;
+    std::vector<int> bJ, b_sptr(1, 0), b_slot;
     std::vector<std::vector<int>> psrc_of(nt);
     for (int K = 0; K < nt; ++K) {
-        for (int P : cols[K]) {
+        for (int P : cols[K])
             if (step[P] == step[K] - 1) psrc_of[K].push_back(P);
-            rowl_slot.push_back(c->h_tile_index[(size_t)K * nt + P]);
-        }
         psrc.insert(psrc.end(), psrc_of[K].begin(), psrc_of[K].end());
         psrc_ptr.push_back((int)psrc.size());
-        rowl_ptr.push_back((int)rowl_slot.size());
     }
-    c->step_crit_ptr.assign(1, 0); c->step_def_ptr.assign(1, 0); c->step_panel_ptr.assign(1, 0);
+    c->step_crit_ptr.assign(1, 0); c->step_def_ptr.assign(1, 0); c->step_panel_ptr.assign(1, 0); c->step_b_ptr.assign(1, 0);
     std::vector<int> stamp((size_t)nt * nt, -1), def_of((size_t)nt * nt, -1);
     for (int s = 0; s < n_steps; ++s) {
         for (int K : by_step[s]) {
@@ -225,6 +223,24 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
             }
         }
         c->step_def_ptr.push_back((int)defI.size());
+        // right-hand-side tasks: b_J -= sum_P L_JP y_P for the panels P of step s-1 and rows J of later steps
+        if (s > 0) {
+            std::vector<int> tg;
+            std::vector<std::vector<int>> sl;
+            std::vector<int> at(nt, -1);
+            for (int P : by_step[s - 1])
+                for (int J : rows[P]) {
+                    if (step[J] == s) continue;                  // summed by the critical CTAs of panel J
+                    if (at[J] < 0) { at[J] = (int)tg.size(); tg.push_back(J); sl.emplace_back(); }
+                    sl[at[J]].push_back(c->h_tile_index[(size_t)J * nt + P]);
+                }
+            for (size_t t = 0; t < tg.size(); ++t) {
+                bJ.push_back(tg[t]);
+                b_slot.insert(b_slot.end(), sl[t].begin(), sl[t].end());
+                b_sptr.push_back((int)b_slot.size());
+            }
+        }
+        c->step_b_ptr.push_back((int)bJ.size());
     }
     std::vector<int> cptr(1, 0), crow, cslot;
     for (int J = 0; J < nt; ++J) {
@@ -234,7 +250,7 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
     up_vec(&c->tile_index, c->h_tile_index);
     up_vec(&c->d_crit_I, critI); up_vec(&c->d_crit_K, critK);
     up_vec(&c->d_psrc_ptr, psrc_ptr); up_vec(&c->d_psrc, psrc);
-    up_vec(&c->d_rowl_ptr, rowl_ptr); up_vec(&c->d_rowl_slot, rowl_slot);
+    up_vec(&c->d_b_J, bJ); up_vec(&c->d_b_sptr, b_sptr); up_vec(&c->d_b_slot, b_slot);
     up_vec(&c->d_def_I, defI); up_vec(&c->d_def_J, defJ); up_vec(&c->d_def_sptr, def_sptr); up_vec(&c->d_def_src, def_src);
     up_vec(&c->d_step_panels, step_panels);
     up_vec(&c->d_coltile_ptr, cptr); up_vec(&c->d_coltile_row, crow); up_vec(&c->d_coltile_slot, cslot);
@@ -244,8 +260,8 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
     CUDA_CHECK(cudaMalloc(&c->Ldiag, (size_t)nt * TS * TS * sizeof(double)));
     c->chol_graph_ok = false; c->bw_graph_ok = false;
     if (getenv("PSBA_SETUP_TIMING"))
-        fprintf(stderr, "psba setup: camera system %d tiles/edge, %d factor tiles, %d steps, %zu critical + %zu deferred tasks\n",
-                nt, c->n_tiles, n_steps, critI.size(), defI.size());
+        fprintf(stderr, "psba setup: camera system %d tiles/edge, %d factor tiles, %d steps, %zu critical + %zu deferred + %zu rhs tasks\n",
+                nt, c->n_tiles, n_steps, critI.size(), defI.size(), bJ.size());
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -372,6 +388,9 @@ __device__ __forceinline__ void tile_tri_inverse(const double *L, double *X)
 }
 
 #define PANEL_NT 128
+// optional phase stamps of the diagonal CTA of every step (PSBA_PANEL_DEBUG=1): clock64 at phase boundaries
+__device__ long long *g_panel_dbg = nullptr;
+#define PANEL_STAMP(i) do { if (dbg && tid == 0) dbg[i] = clock64(); } while (0)
 // One kernel per STEP (128 threads per CTA); a step holds every panel whose dependencies are met.
 //  critical CTA for tile row I of panel K (I = K: the diagonal CTA): loads D = A_KK and A_IK, applies the
 //  pending updates of the source panels P of the previous step (D -= L_KP L_KP^T, A_IK -= L_IP L_KP^T), then
@@ -386,11 +405,11 @@ __device__ __forceinline__ void tile_tri_inverse(const double *L, double *X)
 //  deferred CTAs: A_IJ -= sum_P L_IP L_JP^T for trailing tiles whose panel J runs in a later step.
 __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int nt, int ncrit, const int *__restrict__ critI, const int *__restrict__ critK,
                                                          const int *__restrict__ psrc_ptr, const int *__restrict__ psrc,
-                                                         const int *__restrict__ rowl_ptr, const int *__restrict__ rowl_slot,
-                                                         const int *__restrict__ defI, const int *__restrict__ defJ,
+                                                         int ndef, const int *__restrict__ defI, const int *__restrict__ defJ,
                                                          const int *__restrict__ def_sptr, const int *__restrict__ def_src,
+                                                         const int *__restrict__ bJ, const int *__restrict__ b_sptr, const int *__restrict__ b_slot,
                                                          const int *__restrict__ tile_index, double *__restrict__ Stiles,
-                                                         double *__restrict__ Ldiag, const double *__restrict__ b0,
+                                                         double *__restrict__ Ldiag, double *__restrict__ bwork,
                                                          double *__restrict__ ywork, double *__restrict__ contrib, int *__restrict__ status)
 {
     extern __shared__ double smem[];
@@ -399,6 +418,16 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int nt, int ncrit, cons
     const int tid = threadIdx.x, tr = tid % 8, tc = tid / 8;
     double *B0 = smem, *B1 = smem + TILE_SM;
 
+    if ((int)blockIdx.x >= ncrit + ndef) {
+        // ---- right-hand side of a later panel:  b_J -= sum_P L_JP y_P  (ascending P)
+        const int t = blockIdx.x - ncrit - ndef;
+        if (tid < TS) {
+            double sum = 0.0;
+            for (int q = b_sptr[t]; q < b_sptr[t + 1]; ++q) sum += contrib[(size_t)b_slot[q] * TS + tid];
+            bwork[bJ[t] * TS + tid] -= sum;
+        }
+        return;
+    }
     if ((int)blockIdx.x >= ncrit) {
         // ---- deferred trailing update:  A_IJ -= sum_P L_IP L_JP^T
         const int t = blockIdx.x - ncrit;
@@ -442,6 +471,8 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int nt, int ncrit, cons
     // ---- critical path of panel K for tile row I
     const int I = critI[blockIdx.x], K = critK[blockIdx.x];
     const bool diagcta = I == K;
+    long long *dbg = (g_panel_dbg && blockIdx.x == 0) ? g_panel_dbg + (size_t)K * 8 : nullptr;
+    PANEL_STAMP(0);
     const int sb = psrc_ptr[K], se = psrc_ptr[K + 1];
     double *tik = Stiles + (size_t)tile_index[I * nt + K] * TS * TS;
     const double *tkk = Stiles + (size_t)tile_index[K * nt + K] * TS * TS;
@@ -463,33 +494,36 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int nt, int ncrit, cons
             d[p][q] = tkk[(tr * 6 + p) * TS + tc * 3 + q];
             a[p][q] = diagcta ? 0.0 : tik[(tr * 6 + p) * TS + tc * 3 + q];
         }
-    // right-hand side of the panel: b_K = b0_K - sum_P L_KP y_P (ascending P, two interleaved partial sums)
-    double bpart = 0.0;
-    if (tid < 2 * TS) {
-        const int cidx = tid % TS, half = tid / TS;
-        for (int r = rowl_ptr[K] + half; r < rowl_ptr[K + 1]; r += 2) bpart += contrib[(size_t)rowl_slot[r] * TS + cidx];
+    // right-hand side of the panel: what the rhs tasks of earlier steps left in bwork minus the
+    // contributions of the source panels (ascending P)
+    PANEL_STAMP(1);
+    double bk = 0.0;
+    if (tid < TS) {
+        double sum = 0.0;
+        for (int s = sb; s < se; ++s) sum += contrib[(size_t)tile_index[K * nt + psrc[s]] * TS + tid];
+        bk = bwork[K * TS + tid] - sum;
     }
     for (int s = sb; s < se; ++s) {
-        if (s > sb) __syncthreads();
-        tile_sts(B0, rp);
-        if (upd) tile_sts(B1, ri);
-        __syncthreads();
-        const bool upd_now = upd;
-        if (s + 1 < se) {
-            const int P = psrc[s + 1];
+        if (s > sb) {                                          // further sources (first panel of a separator)
+            __syncthreads();
+            const int P = psrc[s];
             tile_ldg(rp, Stiles + (size_t)tile_index[K * nt + P] * TS * TS);
             const int sl = diagcta ? -1 : tile_index[I * nt + P];
             upd = sl >= 0;
             if (upd) tile_ldg(ri, Stiles + (size_t)sl * TS * TS);
         }
+        tile_sts(B0, rp);
+        if (upd) tile_sts(B1, ri);
+        __syncthreads();
         double acc[6][3], acc2[6][3];
-        if (upd_now) tile_abt<true>(B0, B1, B0, acc, acc2);
+        if (upd) tile_abt<true>(B0, B1, B0, acc, acc2);
         else tile_abt<false>(B0, B0, B0, acc, acc2);
 #pragma unroll
         for (int p = 0; p < 6; ++p)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { d[p][q] -= acc[p][q]; if (upd_now) a[p][q] -= acc2[p][q]; }
+            for (int q = 0; q < 3; ++q) { d[p][q] -= acc[p][q]; if (upd) a[p][q] -= acc2[p][q]; }
     }
+    PANEL_STAMP(2);
     // ---- hand the updated blocks over to the ROW-OWNER layout of the sweep: thread t < 48 owns row t of
     // D, thread 48+r owns row r of A_IK, thread 96 owns the right-hand-side row b_K^T
     __syncthreads();                                           // the factor tiles in B0/B1 are consumed
@@ -497,43 +531,111 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int nt, int ncrit, cons
     for (int p = 0; p < 6; ++p)
 #pragma unroll
         for (int q = 0; q < 3; ++q) { B0[(tr * 6 + p) * LDT + tc * 3 + q] = d[p][q]; B1[(tr * 6 + p) * LDT + tc * 3 + q] = a[p][q]; }
-    if (tid < 2 * TS) colbuf[0][tid] = bpart;
+    if (tid < TS) colbuf[0][tid] = bk;
     __syncthreads();
     const bool active = tid < TS || (tid < 2 * TS && !diagcta) || tid == 2 * TS;
     double row[TS];
     if (tid == 2 * TS) {
 #pragma unroll
-        for (int c = 0; c < TS; ++c) row[c] = b0[K * TS + c] - (colbuf[0][c] + colbuf[0][TS + c]);
+        for (int c = 0; c < TS; ++c) row[c] = colbuf[0][c];
     } else {
         const double *src = tid < TS ? B0 + tid * LDT : B1 + (tid - TS) * LDT;
 #pragma unroll
         for (int c = 0; c < TS; ++c) row[c] = active ? src[c] : 0.0;
     }
-    __syncthreads();                                           // colbuf[0] is reused by the sweep
-    // ---- column sweep over the stacked panel [D ; A_IK ; b^T] (97 x 48), one row per thread in registers.
-    // Step j: every thread publishes its entry of column j (ONE 8-byte shared store per thread: the
-    // barrier drains pending stores at ~19 cycles each, see tools/microbench/sweep_bench.cu), then
-    //   inv = 1/d_jj,  f = row[j]*inv,  row[c] -= f * col[c]  (c > j; the next column first),
-    // and finally row[j] *= rsqrt(d_jj) turns the entry into the factor value (off the critical chain).
+    __syncthreads();                                           // colbuf[0] is reused below
+    PANEL_STAMP(3);
+    // ---- blocked sweep over the stacked panel [D ; A_IK ; b^T] (97 x 48), one row per thread in registers,
+    // SB = 6 columns per block step (8 steps, two barriers each instead of one barrier per column):
+    //   A  every thread factors the current 6x6 diagonal block redundantly in registers (the only truly
+    //      sequential part: 6 dependent rsqrt) and runs its own row through it (l_i = row_i L_bb^-T);
+    //   B  the rows of D publish their six factor entries;
+    //   C1 every thread updates the six columns of the NEXT block, whose owners publish the next diagonal
+    //      block immediately;
+    //   C2 the remaining columns are updated at the top of the next step, in the same basic block as the
+    //      latency-bound factorisation A so that the FMA stream hides under the rsqrt chain.
+    // Dead entries (above the diagonal of D) are updated too: the loop is branch-free; a non-positive pivot
+    // poisons the panel with NaN and is reported once at the end.
+    constexpr int SB = 6, NB = TS / SB;
+    double *pubD = colbuf[0];                                  // [2][SB*SB]
+    double *pubL = smem;                                       // [2][TS*SB]  (the tiles in B0 are consumed)
     bool bad = false;
-    if (active) colbuf[0][tid] = row[0];
+    if (tid < SB) {
 #pragma unroll
-    for (int j = 0; j < TS; ++j) {
+        for (int k = 0; k < SB; ++k) pubD[tid * SB + k] = row[k];
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
         __syncthreads();
-        if (active) {
-            const double *cb = colbuf[j & 1];
-            const double piv = cb[j];
-            bad |= !(piv > 0.0 && piv < 1e300);
-            const double f = row[j] * __drcp_rn(piv);
-            if (j + 1 < TS) {
-                row[j + 1] -= f * cb[j + 1];
-                colbuf[(j + 1) & 1][tid] = row[j + 1];         // publish the next column before the bulk update
-            }
+        // A: 6x6 diagonal block, redundantly, fused with this thread's own row.  C2 of the previous block step
+        // (columns beyond the current block) is dealt out in six chunks, one in front of every rsqrt, so
+        // that its FMA stream runs under the latency of the MUFU + Newton chain (same basic block).
+        {
+            const double *pd = pubD + (b & 1) * SB * SB;
+            const double *pl = pubL + ((b + 1) & 1) * TS * SB;         // l-values of block b-1
+            double dd[SB][SB];
 #pragma unroll
-            for (int c = j + 2; c < TS; ++c) row[c] -= f * cb[c];
-            row[j] *= rsqrt(piv);
+            for (int i = 0; i < SB; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) dd[i][j] = pd[i * SB + j];
+            double *x = row + b * SB;
+#pragma unroll
+            for (int j = 0; j < SB; ++j) {
+                const double piv = dd[j][j];
+                if (b > 0) {
+                    const double *xp = row + (b - 1) * SB;
+#pragma unroll
+                    for (int c = (b + 1) * SB + j; c < TS; c += SB) {
+                        const double2 l01 = *reinterpret_cast<const double2 *>(pl + c * SB);
+                        const double2 l23 = *reinterpret_cast<const double2 *>(pl + c * SB + 2);
+                        const double2 l45 = *reinterpret_cast<const double2 *>(pl + c * SB + 4);
+                        double r = row[c];
+                        r = fma(-xp[0], l01.x, r); r = fma(-xp[1], l01.y, r); r = fma(-xp[2], l23.x, r);
+                        r = fma(-xp[3], l23.y, r); r = fma(-xp[4], l45.x, r); r = fma(-xp[5], l45.y, r);
+                        row[c] = r;
+                    }
+                }
+                bad |= !(piv > 0.0 && piv < 1e300);
+                const double inv = rsqrt(piv);
+                x[j] *= inv;
+#pragma unroll
+                for (int i = j + 1; i < SB; ++i) dd[i][j] *= inv;
+#pragma unroll
+                for (int i = j + 1; i < SB; ++i) {
+                    x[i] -= x[j] * dd[i][j];
+#pragma unroll
+                    for (int k = j + 1; k <= i; ++k) dd[i][k] -= dd[i][j] * dd[k][j];
+                }
+            }
+        }
+        if (b == NB - 1) break;
+        // B: publish the factor entries of the rows of D
+        double *plw = pubL + (b & 1) * TS * SB;
+        if (tid < TS) {
+            const double *x = row + b * SB;
+            *reinterpret_cast<double2 *>(plw + tid * SB) = make_double2(x[0], x[1]);
+            *reinterpret_cast<double2 *>(plw + tid * SB + 2) = make_double2(x[2], x[3]);
+            *reinterpret_cast<double2 *>(plw + tid * SB + 4) = make_double2(x[4], x[5]);
+        }
+        __syncthreads();
+        // C1: the columns of the next block, then its diagonal block goes out
+        {
+            const double *x = row + b * SB;
+#pragma unroll
+            for (int c = (b + 1) * SB; c < (b + 2) * SB; ++c) {
+                const double2 l01 = *reinterpret_cast<const double2 *>(plw + c * SB);
+                const double2 l23 = *reinterpret_cast<const double2 *>(plw + c * SB + 2);
+                const double2 l45 = *reinterpret_cast<const double2 *>(plw + c * SB + 4);
+                row[c] -= (x[0] * l01.x + x[1] * l01.y) + (x[2] * l23.x + x[3] * l23.y) + (x[4] * l45.x + x[5] * l45.y);
+            }
+            if (tid >= (b + 1) * SB && tid < (b + 2) * SB) {
+                double *pdw = pubD + ((b + 1) & 1) * SB * SB + (tid - (b + 1) * SB) * SB;
+#pragma unroll
+                for (int k = 0; k < SB; ++k) pdw[k] = row[(b + 1) * SB + k];
+            }
         }
     }
+    PANEL_STAMP(4);
     if (__syncthreads_or(bad)) { if (tid == 0) *status = 1; return; }
     // ---- results: factor rows to global, y_K to shared, then the contribution L_IK y_K of this tile
     double *ysh = colbuf[0];
@@ -551,6 +653,7 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int nt, int ncrit, cons
 #pragma unroll
             for (int c = 0; c < TS; c += 2) dst[c / 2] = make_double2(c <= tid ? row[c] : 0.0, c + 1 <= tid ? row[c + 1] : 0.0);
         }
+        PANEL_STAMP(5);
         return;
     }
     __syncthreads();
@@ -593,10 +696,11 @@ static void enqueue_factor(psba_ctx *c)
     for (int s = 0; s < c->n_steps; ++s) {
         const int cb = c->step_crit_ptr[s], ncrit = c->step_crit_ptr[s + 1] - cb;
         const int db = c->step_def_ptr[s], ndef = c->step_def_ptr[s + 1] - db;
-        k_panel_step<<<ncrit + ndef, PANEL_NT, CHOL_SMEM, c->stream>>>(c->nt, ncrit, c->d_crit_I + cb, c->d_crit_K + cb, c->d_psrc_ptr, c->d_psrc,
-                                                                      c->d_rowl_ptr, c->d_rowl_slot, c->d_def_I + db, c->d_def_J + db,
-                                                                      c->d_def_sptr + db, c->d_def_src, c->tile_index, c->Stiles, c->Ldiag,
-                                                                      c->chol_aux, c->chol_diag, c->contrib, c->d_status);
+        const int bb = c->step_b_ptr[s], nb = c->step_b_ptr[s + 1] - bb;
+        k_panel_step<<<ncrit + ndef + nb, PANEL_NT, CHOL_SMEM, c->stream>>>(c->nt, ncrit, c->d_crit_I + cb, c->d_crit_K + cb, c->d_psrc_ptr, c->d_psrc,
+                                                                           ndef, c->d_def_I + db, c->d_def_J + db, c->d_def_sptr + db, c->d_def_src,
+                                                                           c->d_b_J + bb, c->d_b_sptr + bb, c->d_b_slot, c->tile_index, c->Stiles,
+                                                                           c->Ldiag, c->chol_aux, c->chol_diag, c->contrib, c->d_status);
     }
     k_diag_inverse<<<c->nt, 256, 2 * TILE_SM * sizeof(double), c->stream>>>(c->Ldiag, c->Linv, c->d_status);
 }
@@ -614,7 +718,28 @@ double psba_launch_factor(psba_ctx *c)
         CUDA_CHECK(cudaGraphDestroy(graph));
         c->chol_graph_ok = true;
     }
+    static int dbg_runs = getenv("PSBA_PANEL_DEBUG") ? 2 : 0;
+    long long *dbg_dev = nullptr;
+    if (dbg_runs > 0) {
+        CUDA_CHECK(cudaMalloc(&dbg_dev, (size_t)c->nt * 8 * sizeof(long long)));
+        CUDA_CHECK(cudaMemset(dbg_dev, 0, (size_t)c->nt * 8 * sizeof(long long)));
+        CUDA_CHECK(cudaMemcpyToSymbol(g_panel_dbg, &dbg_dev, sizeof(dbg_dev)));
+    }
     PROF(c, KID_FACTOR) CUDA_CHECK(cudaGraphLaunch(c->chol_graph, c->stream));
+    if (dbg_dev) {
+        std::vector<long long> h((size_t)c->nt * 8);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        CUDA_CHECK(cudaMemcpy(h.data(), dbg_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        long long *nul = nullptr;
+        CUDA_CHECK(cudaMemcpyToSymbol(g_panel_dbg, &nul, sizeof(nul)));
+        CUDA_CHECK(cudaFree(dbg_dev));
+        if (--dbg_runs == 0)
+            for (int K = 0; K < c->nt; ++K)
+                if (h[(size_t)K * 8])
+                    fprintf(stderr, "panel %4d: loads %6lld  update %6lld  handover %6lld  sweep %6lld  store %6lld  total %6lld clk\n", K,
+                            h[K * 8 + 1] - h[K * 8], h[K * 8 + 2] - h[K * 8 + 1], h[K * 8 + 3] - h[K * 8 + 2], h[K * 8 + 4] - h[K * 8 + 3],
+                            h[K * 8 + 5] - h[K * 8 + 4], h[K * 8 + 5] - h[K * 8]);
+    }
     c->st_launches += c->n_steps + 2;
     int st = 0;
     CUDA_CHECK(cudaMemcpyAsync(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

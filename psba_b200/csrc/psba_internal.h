@@ -90,11 +90,11 @@ struct psba_ctx {
     // step schedule of the factorisation: panels whose dependencies are met run in the same launch.
     //   critical task (I,K): tile row I of panel K (I == K: the diagonal CTA)
     //   panel sources      : panels P of the previous step with a tile (K,P) (their updates are still pending)
-    //   row list of K      : slots of the tiles (K,P), P < K (forward-substitution contributions)
+    //   rhs task J         : b_J -= sum_P L_JP y_P over the panels P of the previous step (J in a later step)
     //   deferred task (I,J): trailing tile touched by panels of the previous step, J in a later step
     int n_steps; bool chain_schedule;          // chain: one panel per step (dense S)
-    std::vector<int> step_crit_ptr, step_def_ptr, step_panel_ptr;
-    int *d_crit_I, *d_crit_K, *d_psrc_ptr, *d_psrc, *d_rowl_ptr, *d_rowl_slot;
+    std::vector<int> step_crit_ptr, step_def_ptr, step_panel_ptr, step_b_ptr;
+    int *d_crit_I, *d_crit_K, *d_psrc_ptr, *d_psrc, *d_b_J, *d_b_sptr, *d_b_slot;
     int *d_def_I, *d_def_J, *d_def_sptr, *d_def_src, *d_step_panels;
     double *contrib;                // n_tiles * TS: L_IK y_K per factor tile
     double *Ldiag;                  // nt * TS*TS   factor of the diagonal tiles (kept out of the tile pool)
