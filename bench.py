@@ -321,11 +321,11 @@ def main():
             t = torch.tensor([e_s], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_s = float(t.item())
-        h2d = (prob["K"].nbytes + prob["initrot"].nbytes + prob["cams"].nbytes) + (G.o_loc * 16 + G.n_loc * 24) + G.o_loc * 8
-        h2d += int(G.stat("ntriples")) * 8                # pair lists built on the host and uploaded
+        # every rank uploads the whole problem (it cuts its slice on the device) + the two index arrays
+        h2d = (prob["K"].nbytes + prob["initrot"].nbytes + prob["cams"].nbytes) + (o * 16 + prob["n"] * 24) + o * 8
         d2h = cams_out.nbytes + pts_out.nbytes + e_tries * 48
         e2e = {"value": e_tries * o / e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),
-               "seconds": round(e_s, 3), "includes": "setup_cl + fill buffers (H2D) + host structure build + K LM iterations + get_params (D2H)"}
+               "seconds": round(e_s, 3), "includes": "setup_cl + fill_initBuffer2 (H2D) + fill_idxBuffer (H2D + device-built index structure) + K LM iterations + get_params (D2H)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -108,7 +108,7 @@ static bool compute_PB(psba_ctx *c, double *lambda)
             // it from Saux, trust_region.cpp:345-346), then the modified Cholesky picks lambda
             psba_launch_schur(c, 0.0);
             const size_t nn = (size_t)c->N * c->N;
-            if (!c->Sdense) CUDA_CHECK(cudaMalloc(&c->Sdense, nn * sizeof(double)));
+            if (!c->Sdense) c->Sdense = (double *)psba_dev_alloc(c, nn * sizeof(double), true);
             psba_tiles_to_dense(c, c->Sdense, true);
             double delta, beta; int nscalar = 0;
             const double sum = psba_launch_cholmod(c, &delta, &beta, &nscalar);

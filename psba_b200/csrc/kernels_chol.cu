@@ -113,10 +113,10 @@ static void nd_recurse(nd_ctx &x, std::vector<int> nodes)
     x.order.insert(x.order.end(), S.begin(), S.end());
 }
 
-template <class T> static void up_vec(T **d, const std::vector<T> &h)
+template <class T> static void up_vec(psba_ctx *c, T **d, const std::vector<T> &h)
 {
-    CUDA_CHECK(cudaMalloc(d, std::max<size_t>(1, h.size()) * sizeof(T)));
-    if (!h.empty()) CUDA_CHECK(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *d = (T *)psba_dev_alloc(c, std::max<size_t>(1, h.size()) * sizeof(T), false);
+    if (!h.empty()) CUDA_CHECK(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
 }
 
 void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int>> &pairs)
@@ -147,8 +147,8 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
     c->h_cam2pos.resize(c->m);
     std::vector<int> pos2cam((size_t)nt * 8, -1);
     for (int j = 0; j < c->m; ++j) { c->h_cam2pos[j] = tpos[j / 8] * 8 + j % 8; pos2cam[c->h_cam2pos[j]] = j; }
-    up_vec(&c->cam2pos, c->h_cam2pos);
-    up_vec(&c->pos2cam, pos2cam);
+    up_vec(c, &c->cam2pos, c->h_cam2pos);
+    up_vec(c, &c->pos2cam, pos2cam);
     // ---- pattern in permuted numbering + symbolic factorisation at tile granularity
     std::vector<char> present((size_t)nt * nt, 0);
     for (int I = 0; I < nt; ++I) present[(size_t)I * nt + I] = 1;
@@ -247,17 +247,18 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
         for (int I : rows[J]) { crow.push_back(I); cslot.push_back(c->h_tile_index[(size_t)I * nt + J]); }
         cptr.push_back((int)crow.size());
     }
-    up_vec(&c->tile_index, c->h_tile_index);
-    up_vec(&c->d_crit_I, critI); up_vec(&c->d_crit_K, critK);
-    up_vec(&c->d_psrc_ptr, psrc_ptr); up_vec(&c->d_psrc, psrc);
-    up_vec(&c->d_b_J, bJ); up_vec(&c->d_b_sptr, b_sptr); up_vec(&c->d_b_slot, b_slot);
-    up_vec(&c->d_def_I, defI); up_vec(&c->d_def_J, defJ); up_vec(&c->d_def_sptr, def_sptr); up_vec(&c->d_def_src, def_src);
-    up_vec(&c->d_step_panels, step_panels);
-    up_vec(&c->d_coltile_ptr, cptr); up_vec(&c->d_coltile_row, crow); up_vec(&c->d_coltile_slot, cslot);
-    CUDA_CHECK(cudaMalloc(&c->Stiles, (size_t)c->n_tiles * TS * TS * sizeof(double)));
-    CUDA_CHECK(cudaMalloc(&c->contrib, (size_t)c->n_tiles * TS * sizeof(double)));
-    CUDA_CHECK(cudaMalloc(&c->Linv, (size_t)nt * TS * TS * sizeof(double)));
-    CUDA_CHECK(cudaMalloc(&c->Ldiag, (size_t)nt * TS * TS * sizeof(double)));
+    up_vec(c, &c->tile_index, c->h_tile_index);
+    up_vec(c, &c->d_crit_I, critI); up_vec(c, &c->d_crit_K, critK);
+    up_vec(c, &c->d_psrc_ptr, psrc_ptr); up_vec(c, &c->d_psrc, psrc);
+    up_vec(c, &c->d_b_J, bJ); up_vec(c, &c->d_b_sptr, b_sptr); up_vec(c, &c->d_b_slot, b_slot);
+    up_vec(c, &c->d_def_I, defI); up_vec(c, &c->d_def_J, defJ); up_vec(c, &c->d_def_sptr, def_sptr); up_vec(c, &c->d_def_src, def_src);
+    up_vec(c, &c->d_step_panels, step_panels);
+    up_vec(c, &c->d_coltile_ptr, cptr); up_vec(c, &c->d_coltile_row, crow); up_vec(c, &c->d_coltile_slot, cslot);
+    c->Stiles = (double *)psba_dev_alloc(c, (size_t)c->n_tiles * TS * TS * sizeof(double), true);
+    c->contrib = (double *)psba_dev_alloc(c, (size_t)c->n_tiles * TS * sizeof(double), true);
+    c->Linv = (double *)psba_dev_alloc(c, (size_t)nt * TS * TS * sizeof(double), true);
+    c->Ldiag = (double *)psba_dev_alloc(c, (size_t)nt * TS * TS * sizeof(double), true);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));            // the host vectors above go out of scope
     c->chol_graph_ok = false; c->bw_graph_ok = false;
     if (getenv("PSBA_SETUP_TIMING"))
         fprintf(stderr, "psba setup: camera system %d tiles/edge, %d factor tiles, %d steps, %zu critical + %zu deferred + %zu rhs tasks\n",

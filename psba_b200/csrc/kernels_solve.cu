@@ -82,13 +82,13 @@ void psba_launch_explicit_inverse(psba_ctx *c, double *out_dev)
 {
     const size_t NP = (size_t)c->nt * TS;
     double *Ld = nullptr, *work = nullptr;
-    CUDA_CHECK(cudaMalloc(&Ld, NP * NP * sizeof(double)));
-    CUDA_CHECK(cudaMalloc(&work, NP * NP * sizeof(double)));
+    Ld = (double *)psba_dev_alloc(c, NP * NP * sizeof(double), false);
+    work = (double *)psba_dev_alloc(c, NP * NP * sizeof(double), false);
     psba_factor_to_dense(c, Ld);
     k_explicit_inverse<<<cdiv(c->N, 64), 64, 0, c->stream>>>(c->N, (int)NP, c->cam2pos, Ld, work, out_dev);
     c->st_launches += 1;
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    CUDA_CHECK(cudaFree(Ld)); CUDA_CHECK(cudaFree(work));
+    psba_dev_free(c, Ld); psba_dev_free(c, work);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -22,29 +22,34 @@ static void check_dims(int cnp, int pnp, int mnp)
         die("only cnp=6, pnp=3, mnp=2 are supported (CL_files/PSBA.cl:5-7)");
 }
 
-template <class T> static T *dalloc(size_t n)
+// Device memory comes from the stream-ordered allocator; the pool keeps what a released context gives back
+// (release threshold = never), so a service that opens one problem after another pays for page mapping once.
+void *psba_dev_alloc(psba_ctx *c, size_t bytes, bool zero)
 {
-    T *p = nullptr;
-    CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-    CUDA_CHECK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    static bool pool_ready = false;
+    if (!pool_ready) {
+        int dev = 0;
+        cudaMemPool_t pool;
+        CUDA_CHECK(cudaGetDevice(&dev));
+        CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long keep = ~0ull;
+        CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_ready = true;
+    }
+    void *p = nullptr;
+    bytes = std::max<size_t>(bytes, 16);
+    CUDA_CHECK(cudaMallocAsync(&p, bytes, c->stream));
+    if (zero) CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, c->stream));
     return p;
 }
-template <class T> static T *dupload(const std::vector<T> &h)
+void psba_dev_free(psba_ctx *c, void *p)
 {
-    T *p = dalloc<T>(h.size());
-    if (!h.empty()) CUDA_CHECK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
-    return p;
+    if (p) CUDA_CHECK(cudaFreeAsync(p, c->stream));
 }
-
-// host staging between fill_initBuffer2 and fill_idxBuffer (the local slice is only known once
-// the observation -> point map arrives)
-struct psba_stage {
-    std::vector<double> K, impts, initcams, cams, pts;
-};
-static psba_stage *g_stage_of(psba_ctx *c);
-#include <map>
-static std::map<psba_ctx *, psba_stage> g_stage;
-static psba_stage *g_stage_of(psba_ctx *c) { return &g_stage[c]; }
+template <class T> static T *dalloc(psba_ctx *c, size_t n)
+{
+    return (T *)psba_dev_alloc(c, std::max<size_t>(n, 1) * sizeof(T), true);
+}
 
 extern "C" const char *psba_version(void) { return "psba_b200 0.1 (sm_100a, FP64)"; }
 
@@ -71,15 +76,16 @@ extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3D
     c->profile = false; c->timer_init = false;
     for (int k = 0; k < KID_COUNT; ++k) { c->prof_ms[k] = 0; c->prof_n[k] = 0; }
     c->comm = nullptr;
-    c->K = dalloc<double>((size_t)nCams * 5);
-    c->initcams = dalloc<double>((size_t)nCams * 4);
+    c->stage_impts = c->stage_pts = nullptr;
+    c->K = dalloc<double>(c, (size_t)nCams * 5);
+    c->initcams = dalloc<double>(c, (size_t)nCams * 4);
     for (int s = 0; s < 2; ++s) {
-        c->cams[s] = dalloc<double>((size_t)nCams * 6);
-        c->camcache[s] = dalloc<double>((size_t)nCams * CAMC);
+        c->cams[s] = dalloc<double>(c, (size_t)nCams * 6);
+        c->camcache[s] = dalloc<double>(c, (size_t)nCams * CAMC);
     }
-    c->U = dalloc<double>((size_t)nCams * 36);
-    c->d_status = dalloc<int>(4);
-    c->d_scal = dalloc<double>(NSCAL);
+    c->U = dalloc<double>(c, (size_t)nCams * 36);
+    c->d_status = dalloc<int>(c, 4);
+    c->d_scal = dalloc<double>(c, NSCAL);
     CUDA_CHECK(cudaMallocHost(&c->h_scal, NSCAL * sizeof(double)));
     return c;
 }
@@ -90,18 +96,25 @@ extern "C" void psba_fill_initBuffer2(psba_ctx *c, int cnp, int pnp, int mnp, in
 {
     check_dims(cnp, pnp, mnp);
     if (nCams != c->m || n3Dpts != c->n_glob || n2Dprojs != c->o_glob) die("fill_initBuffer2: sizes differ from setup_cl");
-    psba_stage *st = g_stage_of(c);
-    st->K.assign(Kparas, Kparas + (size_t)nCams * 5);
-    st->impts.assign(impts, impts + (size_t)n2Dprojs * 2);
-    st->initcams.assign(initcams, initcams + (size_t)nCams * 4);
-    st->cams.assign(camsEx, camsEx + (size_t)nCams * 6);
-    st->pts.assign(pts3Ds, pts3Ds + (size_t)n3Dpts * 3);
+    // the caller keeps its arrays: everything is copied to the device here (the local slice of the
+    // per-observation / per-point arrays is cut out once fill_idxBuffer knows this rank's range)
+    cudaStream_t st = c->stream;
+    CUDA_CHECK(cudaMemcpyAsync(c->K, Kparas, (size_t)nCams * 5 * 8, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(c->initcams, initcams, (size_t)nCams * 4 * 8, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(c->cams[0], camsEx, (size_t)nCams * 6 * 8, cudaMemcpyHostToDevice, st));
+    psba_dev_free(c, c->stage_impts); psba_dev_free(c, c->stage_pts);
+    c->stage_impts = (double *)psba_dev_alloc(c, (size_t)n2Dprojs * 16, false);
+    c->stage_pts = (double *)psba_dev_alloc(c, (size_t)n3Dpts * 24, false);
+    if (n2Dprojs) CUDA_CHECK(cudaMemcpyAsync(c->stage_impts, impts, (size_t)n2Dprojs * 16, cudaMemcpyHostToDevice, st));
+    if (n3Dpts) CUDA_CHECK(cudaMemcpyAsync(c->stage_pts, pts3Ds, (size_t)n3Dpts * 24, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
 extern "C" void psba_local_range(int n, int o, const int *iidx, int rank, int nranks, int *p0, int *p1, int *o0, int *o1)
 {
     // contiguous point ranges balanced by observation count: rank r owns the points whose first
-    // observation index lies in [r*o/R, (r+1)*o/R)
+    // observation index lies in [r*o/R, (r+1)*o/R)   (host helper; the engine derives the same range
+    // from the device-built CSR in structure.cu)
     std::vector<int> ptr((size_t)n + 1, 0);
     for (int k = 0; k < o; ++k) ptr[iidx[k] + 1]++;
     for (int i = 0; i < n; ++i) ptr[i + 1] += ptr[i];
@@ -117,158 +130,42 @@ extern "C" void psba_local_range(int n, int o, const int *iidx, int rank, int nr
 extern "C" void psba_fill_idxBuffer(psba_ctx *c, int nCams, int n3Dpts, int n2Dprojs, const int *iidx, const int *jidx)
 {
     if (nCams != c->m || n3Dpts != c->n_glob || n2Dprojs != c->o_glob) die("fill_idxBuffer: sizes differ from setup_cl");
-    psba_stage *st = g_stage_of(c);
-    if (st->pts.size() != (size_t)n3Dpts * 3) die("fill_idxBuffer called before fill_initBuffer2");
-    const int m = c->m;
+    if (!c->stage_pts) die("fill_idxBuffer called before fill_initBuffer2");
     const bool timing = getenv("PSBA_SETUP_TIMING") != nullptr;
-    auto tprev = std::chrono::steady_clock::now();
-    auto lap = [&](const char *what) {
-        if (!timing) return;
-        CUDA_CHECK(cudaDeviceSynchronize());
-        auto now = std::chrono::steady_clock::now();
-        fprintf(stderr, "psba setup: %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tprev).count());
-        tprev = now;
-    };
-    // observations must be point-major, cameras ascending (generate_idxs, misc.cpp:189-217)
-    for (int k = 1; k < n2Dprojs; ++k) {
-        if (iidx[k] < iidx[k - 1] || (iidx[k] == iidx[k - 1] && jidx[k] <= jidx[k - 1]))
-            die("fill_idxBuffer: observations are not point-major with ascending cameras");
-    }
-    int p0, p1, o0, o1;
-    psba_local_range(n3Dpts, n2Dprojs, iidx, c->rank, c->nranks, &p0, &p1, &o0, &o1);
-    c->p_off = p0; c->o_off = o0; c->n = p1 - p0; c->o = o1 - o0;
+    auto t0 = std::chrono::steady_clock::now();
+    // ---- index structure (device-built: CSR, camera order, camera-pair triples, tile structure of S)
+    psba_build_structure(c, iidx, jidx);
     const int n = c->n, o = c->o;
-
-    lap("validate + partition");
-    // ---- parameters
-    CUDA_CHECK(cudaMemcpy(c->K, st->K.data(), (size_t)m * 5 * 8, cudaMemcpyHostToDevice));
-    CUDA_CHECK(cudaMemcpy(c->initcams, st->initcams.data(), (size_t)m * 4 * 8, cudaMemcpyHostToDevice));
-    CUDA_CHECK(cudaMemcpy(c->cams[0], st->cams.data(), (size_t)m * 6 * 8, cudaMemcpyHostToDevice));
-    c->impts = dalloc<double>((size_t)o * 2);
-    if (o) CUDA_CHECK(cudaMemcpy(c->impts, st->impts.data() + (size_t)o0 * 2, (size_t)o * 16, cudaMemcpyHostToDevice));
-    for (int s = 0; s < 2; ++s) c->pts[s] = dalloc<double>((size_t)n * 3);
-    if (n) CUDA_CHECK(cudaMemcpy(c->pts[0], st->pts.data() + (size_t)p0 * 3, (size_t)n * 24, cudaMemcpyHostToDevice));
-    g_stage.erase(c);
-
-    lap("parameter upload");
-    // ---- local CSR
-    std::vector<int> li(o), lj(o), ptr((size_t)n + 1, 0);
-    for (int k = 0; k < o; ++k) { li[k] = iidx[o0 + k] - p0; lj[k] = jidx[o0 + k]; ptr[li[k] + 1]++; }
-    for (int i = 0; i < n; ++i) ptr[i + 1] += ptr[i];
-    c->iidx = dupload(li); c->jidx = dupload(lj); c->pt_ptr = dupload(ptr);
-    // point chunks
-    std::vector<int> pch(1, 0);
-    {
-        int cnt_o = 0, cnt_p = 0;
-        for (int i = 0; i < n; ++i) {
-            const int d = ptr[i + 1] - ptr[i];
-            if (cnt_p > 0 && (cnt_o + d > PT_CTA || cnt_p == PT_CTA)) { pch.push_back(i); cnt_o = 0; cnt_p = 0; }
-            cnt_o += d; cnt_p++;
-        }
-        if (n > 0) pch.push_back(n);
+    // ---- this rank's slice of the per-observation / per-point inputs
+    cudaStream_t st = c->stream;
+    if (c->nranks == 1) { c->impts = c->stage_impts; c->pts[0] = c->stage_pts; }
+    else {
+        c->impts = (double *)psba_dev_alloc(c, (size_t)o * 16, false);
+        c->pts[0] = (double *)psba_dev_alloc(c, (size_t)n * 24, false);
+        if (o) CUDA_CHECK(cudaMemcpyAsync(c->impts, c->stage_impts + (size_t)c->o_off * 2, (size_t)o * 16, cudaMemcpyDeviceToDevice, st));
+        if (n) CUDA_CHECK(cudaMemcpyAsync(c->pts[0], c->stage_pts + (size_t)c->p_off * 3, (size_t)n * 24, cudaMemcpyDeviceToDevice, st));
+        psba_dev_free(c, c->stage_impts); psba_dev_free(c, c->stage_pts);
     }
-    c->n_ptchunk = (int)pch.size() - 1;
-    c->ptchunk = dupload(pch);
-    // camera-major lists + chunks
-    std::vector<int> cptr((size_t)m + 1, 0), cobs(o);
-    for (int k = 0; k < o; ++k) cptr[lj[k] + 1]++;
-    for (int j = 0; j < m; ++j) cptr[j + 1] += cptr[j];
-    {
-        std::vector<int> fill(m, 0);
-        for (int k = 0; k < o; ++k) cobs[cptr[lj[k]] + fill[lj[k]]++] = k;
-    }
-    c->cam_obs = dupload(cobs);
-    std::vector<int> cc_cam, cc_beg, cc_end, cc_ptr(1, 0);
-    const int CCH = CAM_CTA * CAM_OPT;
-    for (int j = 0; j < m; ++j) {
-        for (int b = cptr[j]; b < cptr[j + 1]; b += CCH) { cc_cam.push_back(j); cc_beg.push_back(b); cc_end.push_back(std::min(b + CCH, cptr[j + 1])); }
-        cc_ptr.push_back((int)cc_cam.size());
-    }
-    c->n_cchunk = (int)cc_cam.size();
-    c->cchunk_cam = dupload(cc_cam); c->cchunk_beg = dupload(cc_beg); c->cchunk_end = dupload(cc_end);
-    c->cam_cchunk_ptr = dupload(cc_ptr);
-
-    lap("CSR + chunks");
-    // ---- camera-pair structure: GLOBAL set of pairs (k >= l) so that every rank builds the same S layout
-    std::vector<int> pair_id((size_t)m * m, -1);
-    {
-        std::vector<int> gptr((size_t)n3Dpts + 1, 0);
-        for (int k = 0; k < n2Dprojs; ++k) gptr[iidx[k] + 1]++;
-        for (int i = 0; i < n3Dpts; ++i) gptr[i + 1] += gptr[i];
-        for (int i = 0; i < n3Dpts; ++i)
-            for (int a = gptr[i]; a < gptr[i + 1]; ++a)
-                for (int b = gptr[i]; b <= a; ++b) pair_id[(size_t)jidx[a] * m + jidx[b]] = 0;
-    }
-    for (int j = 0; j < m; ++j) pair_id[(size_t)j * m + j] = 0;   // every diagonal block exists (U_k)
-    std::vector<int> pk, pl;
-    std::vector<std::pair<int, int>> pairs;
-    for (int k = 0; k < m; ++k)
-        for (int l = 0; l <= k; ++l)
-            if (pair_id[(size_t)k * m + l] == 0) { pair_id[(size_t)k * m + l] = (int)pk.size(); pk.push_back(k); pl.push_back(l); pairs.push_back({k, l}); }
-    c->n_pair = (int)pk.size();
-    c->pair_k = dupload(pk); c->pair_l = dupload(pl);
-    lap("global pair set");
-    // local triples, counting sort by pair (points ascending inside a pair)
-    std::vector<long long> tptr((size_t)c->n_pair + 1, 0);
-    for (int i = 0; i < n; ++i)
-        for (int a = ptr[i]; a < ptr[i + 1]; ++a)
-            for (int b = ptr[i]; b <= a; ++b) tptr[pair_id[(size_t)lj[a] * m + lj[b]] + 1]++;
-    for (int p = 0; p < c->n_pair; ++p) tptr[p + 1] += tptr[p];
-    c->ntri = tptr[c->n_pair];
-    std::vector<int> toa((size_t)c->ntri), tob((size_t)c->ntri);
-    {
-        std::vector<long long> fill(tptr.begin(), tptr.end() - 1);
-        for (int i = 0; i < n; ++i)
-            for (int a = ptr[i]; a < ptr[i + 1]; ++a)
-                for (int b = ptr[i]; b <= a; ++b) {
-                    long long at = fill[pair_id[(size_t)lj[a] * m + lj[b]]]++;
-                    toa[at] = a; tob[at] = b;
-                }
-    }
-    c->tri_oa = dupload(toa); c->tri_ob = dupload(tob);
-    std::vector<int> pc_pair, pc_ptr(1, 0);
-    std::vector<long long> pc_beg, pc_end;
-    // lane-group size of the pair pass: every group of G lanes owns one chunk of <= G*PAIR_TPL triples of
-    // one camera pair; G follows the mean run length so that a lane streams ~PAIR_TPL triples before the
-    // (shuffle) reduction -- 4 for the synthetic ring (117 triples / pair), 32 for BAL (~10^3 / pair)
-    {
-        long long nonempty = 0;
-        for (int p = 0; p < c->n_pair; ++p) if (tptr[p + 1] > tptr[p]) ++nonempty;
-        const double avg = nonempty ? (double)c->ntri / (double)nonempty : 1.0;
-        int G = 1;
-        while (G < 32 && avg > (double)G * PAIR_TPL) G *= 2;
-        c->pair_G = G;
-    }
-    const long long PCH = (long long)c->pair_G * PAIR_TPL;
-    for (int p = 0; p < c->n_pair; ++p) {
-        for (long long b = tptr[p]; b < tptr[p + 1]; b += PCH) { pc_pair.push_back(p); pc_beg.push_back(b); pc_end.push_back(std::min(b + PCH, tptr[p + 1])); }
-        pc_ptr.push_back((int)pc_pair.size());
-    }
-    c->n_pchunk = (int)pc_pair.size();
-    c->pchunk_pair = dupload(pc_pair); c->pchunk_beg = dupload(pc_beg); c->pchunk_end = dupload(pc_end);
-    c->pair_chunk_ptr = dupload(pc_ptr);
-
-    lap("triple sort + upload");
-    // ---- camera system tiles
-    psba_build_tile_structure(c, pairs);
-
-    lap("tile structure");
+    c->stage_impts = c->stage_pts = nullptr;
+    c->pts[1] = dalloc<double>(c, (size_t)n * 3);
     // ---- work buffers
     const size_t Tl = (size_t)c->N + 3 * (size_t)n;
-    c->W = dalloc<double>((size_t)o * 18);
-    c->V = dalloc<double>((size_t)n * 6);
-    c->Vinv = dalloc<double>((size_t)n * 6);
-    c->g = dalloc<double>(Tl); c->dp = dalloc<double>(Tl); c->eab = dalloc<double>(Tl);
-    c->P_U = dalloc<double>(Tl); c->P_B = dalloc<double>(Tl); c->P = dalloc<double>(Tl);
-    c->cam_part = dalloc<double>((size_t)c->n_cchunk * 27);
-    c->pair_part = dalloc<double>((size_t)c->n_pchunk * 42);
-    c->d_part = dalloc<double>(((size_t)cdiv(o, 128) + c->n_ptchunk + 512) * 8);
-    c->chol_aux = dalloc<double>((size_t)3 * c->N + 2 * TS);
-    c->chol_diag = dalloc<double>((size_t)3 * c->N + 2 * TS);
-    c->chol_E = dalloc<double>((size_t)c->N + TS);
-    c->UVdiag_scr = dalloc<double>(Tl);
-    CUDA_CHECK(cudaDeviceSynchronize());
-    lap("work buffers");
+    c->W = dalloc<double>(c, (size_t)o * 18);
+    c->V = dalloc<double>(c, (size_t)n * 6);
+    c->Vinv = dalloc<double>(c, (size_t)n * 6);
+    c->g = dalloc<double>(c, Tl); c->dp = dalloc<double>(c, Tl); c->eab = dalloc<double>(c, Tl);
+    c->P_U = dalloc<double>(c, Tl); c->P_B = dalloc<double>(c, Tl); c->P = dalloc<double>(c, Tl);
+    c->cam_part = dalloc<double>(c, (size_t)c->n_cchunk * 27);
+    c->pair_part = dalloc<double>(c, (size_t)c->n_pchunk * 42);
+    c->d_part = dalloc<double>(c, ((size_t)cdiv(o, 128) + c->n_ptchunk + 512) * 8);
+    c->chol_aux = dalloc<double>(c, (size_t)3 * c->N + 2 * TS);
+    c->chol_diag = dalloc<double>(c, (size_t)3 * c->N + 2 * TS);
+    c->chol_E = dalloc<double>(c, (size_t)c->N + TS);
+    c->UVdiag_scr = dalloc<double>(c, Tl);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (timing)
+        fprintf(stderr, "psba setup: fill_idxBuffer total          %8.2f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 }
 
 extern "C" void psba_release_buffer(psba_ctx *c)
@@ -284,12 +181,13 @@ extern "C" void psba_release_buffer(psba_ctx *c)
                     c->d_step_panels, c->contrib, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
                     c->Sdense, c->Sdense_aux, c->chol_aux, c->chol_diag, c->chol_E, c->d_part, c->d_scal, c->P_U, c->P_B, c->P,
                     c->tmpA, c->tmpB};
-    for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *p : ptrs) psba_dev_free(c, p);
+    psba_dev_free(c, c->stage_impts); psba_dev_free(c, c->stage_pts);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (c->chol_graph_ok) cudaGraphExecDestroy(c->chol_graph);
     if (c->bw_graph_ok) cudaGraphExecDestroy(c->bw_graph);
     cudaFreeHost(c->h_scal);
     cudaStreamDestroy(c->stream);
-    g_stage.erase(c);
     delete c;
 }
 
@@ -310,7 +208,7 @@ extern "C" double psba_compute_exQT(psba_ctx *c, int cnp, int pnp, int mnp, int 
     check_dims(cnp, pnp, mnp); (void)n3Dpts; (void)nCams; (void)n2Dprojs;
     const int set = params == PSBA_PARAMS_CUR ? c->cur : 1 - c->cur;
     double *exd = nullptr;
-    if (ex) { if (!c->tmpA) c->tmpA = dalloc<double>((size_t)c->o * 18); exd = c->tmpA; }
+    if (ex) { if (!c->tmpA) c->tmpA = dalloc<double>(c, (size_t)c->o * 18); exd = c->tmpA; }
     const double cost = psba_launch_cost(c, set, exd);
     if (ex) d2h(c, ex, exd, (size_t)c->o * 2);
     return cost;
@@ -321,8 +219,8 @@ extern "C" void psba_compute_jacobiQT(psba_ctx *c, int cnp, int pnp, int mnp, in
     check_dims(cnp, pnp, mnp); (void)n3Dpts; (void)nCams; (void)n2Dprojs;
     c->lin_valid = false;            // a new linearisation point; products are rebuilt on demand
     if (jac_A || jac_B) {
-        if (!c->tmpA) c->tmpA = dalloc<double>((size_t)c->o * 18);
-        if (!c->tmpB) c->tmpB = dalloc<double>((size_t)c->o * 18);
+        if (!c->tmpA) c->tmpA = dalloc<double>(c, (size_t)c->o * 18);
+        if (!c->tmpB) c->tmpB = dalloc<double>(c, (size_t)c->o * 18);
         psba_launch_jac_materialize(c, c->tmpA, c->tmpB);
         if (jac_A) d2h(c, jac_A, c->tmpA, (size_t)c->o * 12);
         if (jac_B) d2h(c, jac_B, c->tmpB, (size_t)c->o * 6);
@@ -419,7 +317,7 @@ extern "C" void psba_compute_Yblks(psba_ctx *c, int cnp, int pnp, int mnp, int n
 {
     check_dims(cnp, pnp, mnp); (void)n3Dpts; (void)nCams; (void)n2Dprojs; (void)iidx; (void)jidx;
     if (Yblks) {
-        if (!c->tmpB) c->tmpB = dalloc<double>((size_t)c->o * 18);
+        if (!c->tmpB) c->tmpB = dalloc<double>(c, (size_t)c->o * 18);
         psba_launch_Y_materialize(c, c->tmpB);
         d2h(c, Yblks, c->tmpB, (size_t)c->o * 18);
     }
@@ -428,8 +326,8 @@ extern "C" void psba_compute_Yblks(psba_ctx *c, int cnp, int pnp, int mnp, int n
 static void ensure_dense(psba_ctx *c)
 {
     const size_t nn = (size_t)c->N * c->N;
-    if (!c->Sdense) c->Sdense = dalloc<double>(nn);
-    if (!c->Sdense_aux) c->Sdense_aux = dalloc<double>(nn);
+    if (!c->Sdense) c->Sdense = dalloc<double>(c, nn);
+    if (!c->Sdense_aux) c->Sdense_aux = dalloc<double>(c, nn);
 }
 
 extern "C" void psba_compute_S(psba_ctx *c, int cnp, int pnp, int mnp, int n3Dpts, int nCams, int n2Dprojs, double *S)
@@ -458,10 +356,11 @@ extern "C" double psba_SPDinv(psba_ctx *c, int matSize, double *outMat)
     const double ret = psba_launch_factor(c);
     if (ret == 0.0 && outMat) {
         ensure_dense(c);
-        double *tmp = dalloc<double>((size_t)c->N * c->N);
+        double *tmp = dalloc<double>(c, (size_t)c->N * c->N);
         psba_launch_explicit_inverse(c, tmp);
         d2h(c, outMat, tmp, (size_t)c->N * c->N);
-        cudaFree(tmp);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        psba_dev_free(c, tmp);
     }
     return ret;
 }
@@ -509,7 +408,7 @@ extern "C" double psba_compute_Jmultiply(psba_ctx *c, int mnp, int n3Dpts, int n
     const double *xv = x == PSBA_VEC_G ? c->g : c->dp;
     double res[3];
     double *jx = nullptr;
-    if (out) { if (!c->tmpA) c->tmpA = dalloc<double>((size_t)c->o * 18); jx = c->tmpA; }
+    if (out) { if (!c->tmpA) c->tmpA = dalloc<double>(c, (size_t)c->o * 18); jx = c->tmpA; }
     psba_launch_Jdot(c, xv, xv, jx, res);
     if (out) d2h(c, out, jx, (size_t)c->o * 2);
     return res[0];

@@ -52,6 +52,7 @@ struct psba_ctx {
 
     // ---- parameters
     double *K, *initcams, *impts;
+    double *stage_impts, *stage_pts;  // whole-problem uploads of fill_initBuffer2 until fill_idxBuffer slices them
     double *cams[2], *pts[2], *camcache[2];
     int cur;                        // index of the "current" parameter set
     bool cache_valid[2];
@@ -127,6 +128,11 @@ struct psba_ctx {
     psba_comm *comm;
 };
 
+// ---- psba_api.cu: stream-ordered pool allocator
+void *psba_dev_alloc(psba_ctx *c, size_t bytes, bool zero);
+void psba_dev_free(psba_ctx *c, void *p);
+// ---- structure.cu
+void psba_build_structure(psba_ctx *c, const int *iidx_host, const int *jidx_host);
 // ---- kernels_obs.cu
 void psba_launch_cam_prep(psba_ctx *c, int set);
 double psba_launch_cost(psba_ctx *c, int set, double *ex_dev /*may be null*/);
