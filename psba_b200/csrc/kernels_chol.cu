@@ -253,6 +253,12 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
     up_vec(c, &c->d_b_J, bJ); up_vec(c, &c->d_b_sptr, b_sptr); up_vec(c, &c->d_b_slot, b_slot);
     up_vec(c, &c->d_def_I, defI); up_vec(c, &c->d_def_J, defJ); up_vec(c, &c->d_def_sptr, def_sptr); up_vec(c, &c->d_def_src, def_src);
     up_vec(c, &c->d_step_panels, step_panels);
+    {
+        std::vector<int> order(step_panels.rbegin(), step_panels.rend());        // last step first
+        up_vec(c, &c->d_bw_order, order);
+        c->d_xdone = (int *)psba_dev_alloc(c, (size_t)nt * 32 * sizeof(int), true);
+        c->bw_epoch = 0;
+    }
     up_vec(c, &c->d_coltile_ptr, cptr); up_vec(c, &c->d_coltile_row, crow); up_vec(c, &c->d_coltile_slot, cslot);
     c->Stiles = (double *)psba_dev_alloc(c, (size_t)c->n_tiles * TS * TS * sizeof(double), true);
     c->contrib = (double *)psba_dev_alloc(c, (size_t)c->n_tiles * TS * sizeof(double), true);
@@ -832,19 +838,123 @@ __global__ void __launch_bounds__(TS * BW_SLOTS) k_backward(int nt, const int *_
     }
 }
 
-__global__ void __launch_bounds__(TS * BW_SLOTS) k_backward_step(const int *__restrict__ panels, const int *__restrict__ cptr,
-                                                                const int *__restrict__ crow, const int *__restrict__ cslot,
-                                                                const double *__restrict__ Stiles, const double *__restrict__ Linv,
-                                                                double *__restrict__ ywork, const int *__restrict__ pos2cam,
-                                                                double *__restrict__ sol)
+// ---- dataflow variant for tree schedules: ONE launch, one CTA per panel in reverse step order.  A CTA
+// prefetches everything that does not depend on x (its tile column into registers, L_II^-1 into shared
+// memory), then waits for the x_J it needs on per-panel flags (release / acquire, epoch-stamped: no reset
+// between solves).  Forward progress: a CTA only waits for CTAs with a smaller block index, which the
+// hardware dispatches first; a bounded spin turns a broken schedule into an error instead of a hang.
+#define BWD_SLOTS 10
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define BW_STAMP(i) do { if (dbg && threadIdx.x == 0) dbg[i] = gtimer(); } while (0)
+#define FLAG_STRIDE 32        // ints between two flags (128 bytes)
+__device__ __forceinline__ int ld_acquire(const int *p)
 {
-    __shared__ bw_smem sm;
-    const int slotid = threadIdx.x / TS;
-    const int I = panels[blockIdx.x];
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_relaxed(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(TS * BWD_SLOTS, 1) k_backward_flow(const int *__restrict__ order, const int *__restrict__ cptr,
+                                                                    const int *__restrict__ crow, const int *__restrict__ cslot,
+                                                                    const double *__restrict__ Stiles, const double *__restrict__ Linv,
+                                                                    double *ywork, const int *__restrict__ pos2cam, double *__restrict__ sol,
+                                                                    int *xdone, int epoch, int *__restrict__ status)
+{
+    __shared__ double part[BWD_SLOTS][TS];
+    __shared__ double xs[BWD_SLOTS][TS];
+    __shared__ double acc[TS];
+    __shared__ double invs[TS * TS];
+    __shared__ double mv[4][TS];
+    const int tid = threadIdx.x, col = tid % TS, slotid = tid / TS;
+    const int I = order[blockIdx.x];
     const int beg = cptr[I], end = cptr[I + 1];
-    int myslot = -1, myrow = 0;
-    if (beg + slotid < end) { myslot = cslot[beg + slotid]; myrow = crow[beg + slotid]; }
-    backward_panel(sm, I, beg, end, myslot, myrow, crow, cslot, Stiles, Linv, ywork, pos2cam, sol);
+    long long *dbg = g_panel_dbg ? g_panel_dbg + (size_t)I * 8 : nullptr;
+    BW_STAMP(0);
+    // independent of x: first tile column of this slot, L_II^-1, y_I
+    double lv[TS];
+    int myrow = -1;
+    if (beg + slotid < end) {
+        myrow = crow[beg + slotid];
+        const double *L = Stiles + (size_t)cslot[beg + slotid] * TS * TS + col;
+#pragma unroll
+        for (int r = 0; r < TS; ++r) lv[r] = __ldg(L + r * TS);
+    }
+    for (int e = tid; e < TS * TS; e += TS * BWD_SLOTS) invs[e] = __ldg(Linv + (size_t)I * TS * TS + e);
+    const double yI = tid < TS ? __ldcg(ywork + I * TS + tid) : 0.0;
+    BW_STAMP(1);
+    // wait for the x_J of this column: ONE lane per dependency polls (relaxed load + back-off; flags are 128
+    // bytes apart so that the pollers of the whole grid do not queue up on one L2 slice), then the CTA
+    // synchronises and a single fence orders the x loads behind the flags
+    for (int t = beg + tid; t < end; t += TS * BWD_SLOTS) {
+        const int *f = xdone + (size_t)crow[t] * FLAG_STRIDE;
+        int spins = 0;
+        while (ld_relaxed(f) != epoch) {
+            __nanosleep(64);
+            if (++spins > (1 << 20)) { *status = 3; break; }
+        }
+    }
+    BW_STAMP(2);
+    __threadfence();
+    __syncthreads();
+    BW_STAMP(3);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int t0 = beg; t0 < end; t0 += BWD_SLOTS) {
+        // x_J of this slot's tile: ONE coherent load per thread into shared memory (L2-coherent loads are
+        // not pipelined by the hardware: 48 of them in a row cost 48 round trips)
+        const int t = t0 + slotid;
+        if (t < end) {
+            const int J = t0 == beg ? myrow : crow[t];
+            xs[slotid][col] = __ldcg(ywork + J * TS + col);
+            if (t0 != beg) {
+                const double *L = Stiles + (size_t)cslot[t] * TS * TS + col;
+#pragma unroll
+                for (int r = 0; r < TS; ++r) lv[r] = __ldg(L + r * TS);
+            }
+        }
+        __syncthreads();
+        if (t < end) {
+            const double *x = xs[slotid];
+#pragma unroll
+            for (int r = 0; r < TS; r += 4) { s0 += lv[r] * x[r]; s1 += lv[r + 1] * x[r + 1]; s2 += lv[r + 2] * x[r + 2]; s3 += lv[r + 3] * x[r + 3]; }
+        }
+        __syncthreads();
+    }
+    part[slotid][col] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (tid < TS) {
+        double a = 0.0;
+#pragma unroll
+        for (int p = 0; p < BWD_SLOTS; ++p) a += part[p][tid];
+        acc[tid] = yI - a;
+    }
+    __syncthreads();
+    if (tid < 4 * TS) {          // x_I[c] = sum_{r >= c} Linv[r][c] acc[r], rows split over 4 partial sums
+        const int cidx = tid % TS, q = tid / TS;
+        double a = 0.0;
+        for (int r = cidx + q; r < TS; r += 4) a += invs[r * TS + cidx] * acc[r];
+        mv[q][cidx] = a;
+    }
+    __syncthreads();
+    if (tid < TS) {
+        const double a = (mv[0][tid] + mv[1][tid]) + (mv[2][tid] + mv[3][tid]);
+        __stcg(ywork + I * TS + tid, a);
+        const int pos = I * TS + tid, cam = pos2cam[pos / 6];
+        if (cam >= 0) sol[cam * 6 + pos % 6] = a;
+    }
+    __syncthreads();
+    BW_STAMP(4);
+    if (tid == 0) st_release(xdone + (size_t)I * FLAG_STRIDE, epoch);
+    BW_STAMP(5);
 }
 
 void psba_launch_solve(psba_ctx *c)
@@ -855,19 +965,34 @@ void psba_launch_solve(psba_ctx *c)
         c->st_launches += 1;
         return;
     }
-    if (!c->bw_graph_ok) {
-        cudaGraph_t graph;
-        CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        for (int s = c->n_steps - 1; s >= 0; --s) {
-            const int pb = c->step_panel_ptr[s], np = c->step_panel_ptr[s + 1] - pb;
-            k_backward_step<<<np, TS * BW_SLOTS, 0, c->stream>>>(c->d_step_panels + pb, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
-                                                               c->Stiles, c->Linv, c->chol_diag, c->pos2cam, c->dp);
-        }
-        CUDA_CHECK(cudaStreamEndCapture(c->stream, &graph));
-        CUDA_CHECK(cudaGraphInstantiate(&c->bw_graph, graph, 0));
-        CUDA_CHECK(cudaGraphDestroy(graph));
-        c->bw_graph_ok = true;
+    c->bw_epoch += 1;
+    static int dbg_runs = getenv("PSBA_BW_DEBUG") ? 3 : 0;
+    long long *dbg_dev = nullptr;
+    if (dbg_runs > 0) {
+        CUDA_CHECK(cudaMalloc(&dbg_dev, (size_t)c->nt * 8 * sizeof(long long)));
+        CUDA_CHECK(cudaMemset(dbg_dev, 0, (size_t)c->nt * 8 * sizeof(long long)));
+        CUDA_CHECK(cudaMemcpyToSymbol(g_panel_dbg, &dbg_dev, sizeof(dbg_dev)));
     }
-    PROF(c, KID_TRI_SOLVE) CUDA_CHECK(cudaGraphLaunch(c->bw_graph, c->stream));
-    c->st_launches += c->n_steps;
+    PROF(c, KID_TRI_SOLVE) k_backward_flow<<<c->nt, TS * BWD_SLOTS, 0, c->stream>>>(c->d_bw_order, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
+                                                                        c->Stiles, c->Linv, c->chol_diag, c->pos2cam, c->dp, c->d_xdone, c->bw_epoch,
+                                                                        c->d_status);
+    c->st_launches += 1;
+    if (dbg_dev) {
+        std::vector<long long> h((size_t)c->nt * 8), ord(c->nt);
+        std::vector<int> order(c->nt);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        CUDA_CHECK(cudaMemcpy(h.data(), dbg_dev, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(order.data(), c->d_bw_order, c->nt * sizeof(int), cudaMemcpyDeviceToHost));
+        long long *nul = nullptr;
+        CUDA_CHECK(cudaMemcpyToSymbol(g_panel_dbg, &nul, sizeof(nul)));
+        CUDA_CHECK(cudaFree(dbg_dev));
+        if (--dbg_runs == 0) {
+            long long t0 = h[(size_t)order[0] * 8];
+            for (int b = 0; b < c->nt; ++b) {
+                const long long *q = &h[(size_t)order[b] * 8];
+                fprintf(stderr, "bw blk %3d panel %3d: start %7lld prefetched %7lld flags %7lld fenced %7lld computed %7lld released %7lld ns\n", b, order[b],
+                        q[0] - t0, q[1] - t0, q[2] - t0, q[3] - t0, q[4] - t0, q[5] - t0);
+            }
+        }
+    }
 }
