@@ -110,7 +110,8 @@ def kernel_bytes(G, prob_sizes):
 def make_problem(name):
     from psba_b200 import synth
     m, n, d, w = WORKLOADS[name]
-    return synth.ring_problem(m=m, n=n, d=d, w=w, seed=20262000)
+    prob = synth.ring_problem(m=m, n=n, d=d, w=w, seed=20262000)
+    return prob
 
 
 def run_cpu(kind_pref, threads, sample, lm_passes):

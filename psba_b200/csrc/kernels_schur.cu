@@ -65,15 +65,19 @@ double psba_launch_vinv(psba_ctx *c, double mu)
 // (bit-identical in every lane, fixed order) and written as the chunk's partial.
 template <bool DIAG, int G>
 __device__ __forceinline__ void pair_accumulate(long long beg, long long end, int lane, const int *__restrict__ tri_oa,
-                                                const int *__restrict__ tri_ob, const int *__restrict__ iidx,
+                                                const int *__restrict__ tri_ob, const int *__restrict__ tri_pt,
                                                 const double *__restrict__ W, const double *__restrict__ Vinv,
                                                 const double *__restrict__ gb, double *acc)
 {
+    long long t = beg + lane;
+    int a_n = 0, b_n = 0, i_n = 0;
+    if (t < end) { a_n = __ldg(tri_oa + t); b_n = DIAG ? a_n : __ldg(tri_ob + t); i_n = __ldg(tri_pt + t); }
 #pragma unroll 1
-    for (long long t = beg + lane; t < end; t += G) {
-        const int a = __ldg(tri_oa + t);
-        const int b = DIAG ? a : __ldg(tri_ob + t);
-        const int i = __ldg(iidx + a);
+    for (; t < end; t += G) {
+        const int a = a_n, b = b_n, i = i_n;
+        if (t + G < end) {                              // indices of the next triple fly with this triple's blocks
+            a_n = __ldg(tri_oa + t + G); b_n = DIAG ? a_n : __ldg(tri_ob + t + G); i_n = __ldg(tri_pt + t + G);
+        }
         const double2 *vp = reinterpret_cast<const double2 *>(Vinv + (size_t)i * 6);
         const double2 v01 = __ldg(vp), v23 = __ldg(vp + 1), v45 = __ldg(vp + 2);
         const double i00 = v01.x, i10 = v01.y, i20 = v23.x, i11 = v23.y, i21 = v45.x, i22 = v45.y;
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(PAIR_CTA, 3) k_schur_pairs(int n_pchunk, const
                                                          const long long *__restrict__ pchunk_beg, const long long *__restrict__ pchunk_end,
                                                          const int *__restrict__ pair_k, const int *__restrict__ pair_l,
                                                          const int *__restrict__ tri_oa, const int *__restrict__ tri_ob,
-                                                         const int *__restrict__ iidx, const double *__restrict__ W,
+                                                         const int *__restrict__ tri_pt, const double *__restrict__ W,
                                                          const double *__restrict__ Vinv, const double *__restrict__ gb,
                                                          double *__restrict__ part)
 {
@@ -128,8 +132,8 @@ __global__ void __launch_bounds__(PAIR_CTA, 3) k_schur_pairs(int n_pchunk, const
     if (ch < n_pchunk) {
         const int pr = pchunk_pair[ch];
         diag = pair_k[pr] == pair_l[pr];
-        if (diag) pair_accumulate<true, G>(pchunk_beg[ch], pchunk_end[ch], lane, tri_oa, tri_ob, iidx, W, Vinv, gb, acc);
-        else pair_accumulate<false, G>(pchunk_beg[ch], pchunk_end[ch], lane, tri_oa, tri_ob, iidx, W, Vinv, gb, acc);
+        if (diag) pair_accumulate<true, G>(pchunk_beg[ch], pchunk_end[ch], lane, tri_oa, tri_ob, tri_pt, W, Vinv, gb, acc);
+        else pair_accumulate<false, G>(pchunk_beg[ch], pchunk_end[ch], lane, tri_oa, tri_ob, tri_pt, W, Vinv, gb, acc);
     }
 #pragma unroll
     for (int w = G / 2; w > 0; w >>= 1) {
@@ -150,7 +154,7 @@ static void launch_pairs(psba_ctx *c)
 {
     const int per_cta = PAIR_CTA / G;
     k_schur_pairs<G><<<cdiv(c->n_pchunk, per_cta), PAIR_CTA, 0, c->stream>>>(c->n_pchunk, c->pchunk_pair, c->pchunk_beg, c->pchunk_end,
-                                                                          c->pair_k, c->pair_l, c->tri_oa, c->tri_ob, c->iidx, c->W,
+                                                                          c->pair_k, c->pair_l, c->tri_oa, c->tri_ob, c->tri_pt, c->W,
                                                                           c->Vinv, c->g + c->N, c->pair_part);
 }
 

@@ -65,7 +65,7 @@ struct psba_ctx {
     int *cam_cchunk_ptr;            // m+1: chunk range of each camera
     // pair structure (lower triangle k>=l), triples sorted by (k,l), ascending point
     long long ntri;
-    int *tri_oa, *tri_ob;
+    int *tri_oa, *tri_ob, *tri_pt;   // observation of camera k, of camera l, local point
     int n_pair; int *pair_k, *pair_l;          // pair blocks present GLOBALLY (all ranks agree)
     int *pair_chunk_ptr;                        // n_pair+1
     int pair_G;                                 // lanes per chunk in the pair pass (1..32)

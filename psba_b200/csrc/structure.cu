@@ -86,12 +86,14 @@ __global__ void k_triple_emit(int np, int p0, int o0, int m, const int *__restri
     }
 }
 
-__global__ void k_split_vals(long long cnt, const u64 *__restrict__ val, int *__restrict__ oa, int *__restrict__ ob)
+__global__ void k_split_vals(long long cnt, const u64 *__restrict__ val, const int *__restrict__ iidx_loc, int *__restrict__ oa,
+                             int *__restrict__ ob, int *__restrict__ pt)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= cnt) return;
     const u64 v = val[t];
     oa[t] = (int)(v >> 32); ob[t] = (int)(v & 0xffffffffu);
+    pt[t] = iidx_loc[(int)(v >> 32)];                 // local point of the triple: the pair pass never gathers iidx
 }
 
 // tptr[p] = first triple whose key is >= the key of pair p (binary search in the sorted local keys)
@@ -269,8 +271,8 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
     // ---- triples of the local points, sorted by camera pair
     u64 *lkeys = nullptr, *lvals = nullptr;
     sorted_triples(c, n, p0, o0, gptr, gj, true, &lkeys, &lvals, &c->ntri);
-    c->tri_oa = salloc<int>(c, (size_t)c->ntri); c->tri_ob = salloc<int>(c, (size_t)c->ntri);
-    if (c->ntri) k_split_vals<<<cdiv(c->ntri, 256), 256, 0, st>>>(c->ntri, lvals, c->tri_oa, c->tri_ob);
+    c->tri_oa = salloc<int>(c, (size_t)c->ntri); c->tri_ob = salloc<int>(c, (size_t)c->ntri); c->tri_pt = salloc<int>(c, (size_t)c->ntri);
+    if (c->ntri) k_split_vals<<<cdiv(c->ntri, 256), 256, 0, st>>>(c->ntri, lvals, c->iidx, c->tri_oa, c->tri_ob, c->tri_pt);
     psba_dev_free(c, lvals);
     T.lap("triple sort");
     // ---- global pair set (all ranks agree): unique keys of ALL points' triples + every diagonal block (U_k)
