@@ -40,7 +40,7 @@ __global__ void k_newcams(int N, const double *__restrict__ cams, const double *
 // EVAL=false stops after phase B (trust region: the step is formed on the host side first).
 #define PROJ_LD 14         // doubles per staged projection entry (12 + pad: conflict-free LDS.128)
 template <bool EVAL>
-__global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ ptchunk, const int *__restrict__ pt_ptr,
+__global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int4 *__restrict__ ptdesc, const int *__restrict__ pt_ptr,
                                                       const int *__restrict__ iidx, const int *__restrict__ jidx,
                                                       const double *__restrict__ impts, const double *__restrict__ W,
                                                       const double *__restrict__ Vinv, const double *__restrict__ gb,
@@ -49,18 +49,34 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ p
                                                       double *__restrict__ eb, double *__restrict__ dpb, double *__restrict__ newpts,
                                                       double *__restrict__ part)
 {
-    __shared__ __align__(16) double stage[PT_CTA * 18];      // W tile, then the projection entries (128*14 <= 128*18)
+    __shared__ __align__(16) double stage[PT_CTA * 18];      // W tile of the wave, then the projection entries (128*14 <= 128*18)
+    double *pstage = stage;
     __shared__ double sh[3][PT_CTA];
     __shared__ double shx[3][PT_CTA];
     __shared__ double red[3][PT_CTA / 32];
     __shared__ int sj[PT_CTA];
     const int tid = threadIdx.x;
-    const int p0 = ptchunk[blockIdx.x], p1 = ptchunk[blockIdx.x + 1];
-    const int o0 = pt_ptr[p0], o1 = pt_ptr[p1];
+    // a CTA is a chain of dependent L2 / HBM round trips: one 16-byte chunk descriptor, then every
+    // independent load of the chunk (W tile, indices, measurements, the owner's point data) at once, then
+    // the loads that need a camera index (dpa, projection entries)
+    const int4 ds = __ldg(ptdesc + blockIdx.x);
+    const int p0 = ds.x, p1 = ds.y, o0 = ds.z, o1 = ds.w;
     const int np = p1 - p0;
+    const bool single = o1 - o0 <= PT_CTA;                   // the common case: the whole chunk is one wave
     double acc0 = 0, acc1 = 0, acc2 = 0;
     int my_a = 0, my_b = 0;
-    if (tid < np) { my_a = pt_ptr[p0 + tid]; my_b = pt_ptr[p0 + tid + 1]; }
+    double g0 = 0, g1 = 0, g2 = 0, i00 = 0, i10 = 0, i20 = 0, i11 = 0, i21 = 0, i22 = 0, px = 0, py = 0, pz = 0;
+    if (tid < np) {
+        const int p = p0 + tid;
+        my_a = __ldg(pt_ptr + p); my_b = __ldg(pt_ptr + p + 1);
+        g0 = __ldg(gb + (size_t)p * 3); g1 = __ldg(gb + (size_t)p * 3 + 1); g2 = __ldg(gb + (size_t)p * 3 + 2);
+        const double2 *vi = reinterpret_cast<const double2 *>(Vinv + (size_t)p * 6);
+        const double2 v01 = __ldg(vi), v23 = __ldg(vi + 1), v45 = __ldg(vi + 2);
+        i00 = v01.x; i10 = v01.y; i20 = v23.x; i11 = v23.y; i21 = v45.x; i22 = v45.y;
+        if (EVAL) { px = __ldg(pts + (size_t)p * 3); py = __ldg(pts + (size_t)p * 3 + 1); pz = __ldg(pts + (size_t)p * 3 + 2); }
+    }
+    int lp1 = 0;
+    double2 mm1 = make_double2(0.0, 0.0);
 
     for (int base = o0; base < o1; base += PT_CTA) {
         const int k = base + tid;
@@ -68,23 +84,50 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ p
         {
             const double2 *wg = reinterpret_cast<const double2 *>(W + (size_t)base * 18);
             double2 *ws = reinterpret_cast<double2 *>(stage);
-            for (int p = tid; p < cnt * 9; p += PT_CTA) ws[p] = __ldg(wg + p);
-        }
-        __syncthreads();
-        if (k < o1) {
-            const double2 *wp = reinterpret_cast<const double2 *>(stage + tid * 18);
-            const double2 *dq = reinterpret_cast<const double2 *>(dpa + jidx[k] * 6);
-            double w[18], d[6];
+            double2 wv[9];                                   // all nine 16-byte pieces in flight at once
 #pragma unroll
-            for (int q = 0; q < 9; ++q) { double2 w2 = wp[q]; w[2 * q] = w2.x; w[2 * q + 1] = w2.y; }
+            for (int q = 0; q < 9; ++q) { const int p = tid + q * PT_CTA; wv[q] = p < cnt * 9 ? __ldg(wg + p) : make_double2(0.0, 0.0); }
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { const int p = tid + q * PT_CTA; if (p < cnt * 9) ws[p] = wv[q]; }
+        }
+        const int ji = k < o1 ? __ldg(jidx + k) : 0;
+        if (EVAL && single) {
+            sj[tid] = ji;
+            if (k < o1) { lp1 = __ldg(iidx + k) - p0; mm1 = __ldg(reinterpret_cast<const double2 *>(impts) + k); }
+        }
+        double d[6];
+        if (k < o1) {
+            const double2 *dq = reinterpret_cast<const double2 *>(dpa + ji * 6);
 #pragma unroll
             for (int q = 0; q < 3; ++q) { double2 d2 = __ldg(dq + q); d[2 * q] = d2.x; d[2 * q + 1] = d2.y; }
+        }
+        __syncthreads();
+        double2 pv[6];                                       // 6 x 16 B = q, t, K of the candidate camera
+        if (EVAL && single) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int p = tid + q * PT_CTA, ob = p / 6, piece = p - ob * 6;
+                pv[q] = p < cnt * 6 ? __ldg(reinterpret_cast<const double2 *>(newcache + (size_t)sj[ob] * CAMC) + piece) : make_double2(0.0, 0.0);
+            }
+        }
+        if (k < o1) {
+            const double2 *wp = reinterpret_cast<const double2 *>(stage + tid * 18);
+            double w[18];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { double2 w2 = wp[q]; w[2 * q] = w2.x; w[2 * q + 1] = w2.y; }
             double t0 = 0, t1 = 0, t2 = 0;
 #pragma unroll
             for (int r = 0; r < 6; ++r) { t0 += w[r * 3] * d[r]; t1 += w[r * 3 + 1] * d[r]; t2 += w[r * 3 + 2] * d[r]; }
             sh[0][tid] = t0; sh[1][tid] = t1; sh[2][tid] = t2;
         }
-        __syncthreads();
+        __syncthreads();                                     // the W tile has been consumed
+        if (EVAL && single) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int p = tid + q * PT_CTA, ob = p / 6, piece = p - ob * 6;
+                if (p < cnt * 6) *reinterpret_cast<double2 *>(pstage + ob * PROJ_LD + piece * 2) = pv[q];
+            }
+        }
         if (tid < np) {
             const int a = max(my_a, base), b = min(my_b, base + PT_CTA);
             for (int q = a; q < b; ++q) { acc0 += sh[0][q - base]; acc1 += sh[1][q - base]; acc2 += sh[2][q - base]; }
@@ -94,17 +137,14 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ p
     double s_dp2 = 0.0, s_dpg = 0.0, s_e2 = 0.0;
     if (tid < np) {
         const int p = p0 + tid;
-        const double g0 = gb[(size_t)p * 3], g1 = gb[(size_t)p * 3 + 1], g2 = gb[(size_t)p * 3 + 2];
         const double e0 = g0 - acc0, e1 = g1 - acc1, e2 = g2 - acc2;
-        const double *vi = Vinv + (size_t)p * 6;
-        const double i00 = vi[0], i10 = vi[1], i20 = vi[2], i11 = vi[3], i21 = vi[4], i22 = vi[5];
         const double d0 = i00 * e0 + i10 * e1 + i20 * e2;
         const double d1 = i10 * e0 + i11 * e1 + i21 * e2;
         const double d2 = i20 * e0 + i21 * e1 + i22 * e2;
         eb[(size_t)p * 3] = e0; eb[(size_t)p * 3 + 1] = e1; eb[(size_t)p * 3 + 2] = e2;
         dpb[(size_t)p * 3] = d0; dpb[(size_t)p * 3 + 1] = d1; dpb[(size_t)p * 3 + 2] = d2;
         if (EVAL) {
-            const double x0 = pts[(size_t)p * 3] + d0, x1 = pts[(size_t)p * 3 + 1] + d1, x2 = pts[(size_t)p * 3 + 2] + d2;
+            const double x0 = px + d0, x1 = py + d1, x2 = pz + d2;
             newpts[(size_t)p * 3] = x0; newpts[(size_t)p * 3 + 1] = x1; newpts[(size_t)p * 3 + 2] = x2;
             shx[0][tid] = x0; shx[1][tid] = x1; shx[2][tid] = x2;
             s_dp2 = d0 * d0 + d1 * d1 + d2 * d2;
@@ -112,26 +152,38 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ p
         }
     }
     if (!EVAL) return;
-    for (int base = o0; base < o1; base += PT_CTA) {
-        const int k = base + tid;
-        const int cnt = min(PT_CTA, o1 - base);
-        __syncthreads();                                   // shx written / previous wave's stage consumed
-        sj[tid] = k < o1 ? jidx[k] : 0;
-        __syncthreads();
-        for (int p = tid; p < cnt * 6; p += PT_CTA) {      // 6 x 16 B = q, t, K of the candidate camera
-            const int ob = p / 6, piece = p - ob * 6;
-            const double2 v = __ldg(reinterpret_cast<const double2 *>(newcache + (size_t)sj[ob] * CAMC) + piece);
-            *reinterpret_cast<double2 *>(stage + ob * PROJ_LD + piece * 2) = v;
-        }
-        __syncthreads();
+    if (single) {
+        __syncthreads();                                   // shx and pstage are complete
+        const int k = o0 + tid;
         if (k < o1) {
             CamProj cam;
-            load_cam_proj<false>(stage + tid * PROJ_LD, cam);
-            const int lp = iidx[k] - p0;
-            double2 mm = __ldg(reinterpret_cast<const double2 *>(impts) + k);
+            load_cam_proj<false>(pstage + tid * PROJ_LD, cam);
             double e0, e1;
-            residual(cam, shx[0][lp], shx[1][lp], shx[2][lp], mm.x, mm.y, e0, e1);
+            residual(cam, shx[0][lp1], shx[1][lp1], shx[2][lp1], mm1.x, mm1.y, e0, e1);
             s_e2 += e0 * e0 + e1 * e1;
+        }
+    } else {
+        for (int base = o0; base < o1; base += PT_CTA) {
+            const int k = base + tid;
+            const int cnt = min(PT_CTA, o1 - base);
+            __syncthreads();                               // shx written / previous wave's entries consumed
+            sj[tid] = k < o1 ? jidx[k] : 0;
+            __syncthreads();
+            for (int p = tid; p < cnt * 6; p += PT_CTA) {
+                const int ob = p / 6, piece = p - ob * 6;
+                const double2 v = __ldg(reinterpret_cast<const double2 *>(newcache + (size_t)sj[ob] * CAMC) + piece);
+                *reinterpret_cast<double2 *>(pstage + ob * PROJ_LD + piece * 2) = v;
+            }
+            __syncthreads();
+            if (k < o1) {
+                CamProj cam;
+                load_cam_proj<false>(pstage + tid * PROJ_LD, cam);
+                const int lp = iidx[k] - p0;
+                double2 mm = __ldg(reinterpret_cast<const double2 *>(impts) + k);
+                double e0, e1;
+                residual(cam, shx[0][lp], shx[1][lp], shx[2][lp], mm.x, mm.y, e0, e1);
+                s_e2 += e0 * e0 + e1 * e1;
+            }
         }
     }
 #pragma unroll
@@ -177,7 +229,7 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
         PROF(c, KID_NEWCAMS) k_newcams<<<1, 256, 0, c->stream>>>(c->N, c->cams[cur], c->dp, c->g, mu, c->cams[nw], c->d_scal + 4);
         psba_launch_cam_prep(c, nw);
         if (c->n_ptchunk > 0)
-            PROF(c, KID_BACKSUB) k_backsub<true><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptchunk, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
+            PROF(c, KID_BACKSUB) k_backsub<true><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
                                                                    gb, c->dp, c->pts[cur], c->camcache[nw], mu, ebp, dpbp,
                                                                    c->pts[nw], c->d_part);
         PROF(c, KID_REDUCE) k_final_reduce3<<<1, 256, 0, c->stream>>>(c->d_part, c->n_ptchunk, c->d_scal);
@@ -192,7 +244,7 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
         }
     } else {
         if (c->n_ptchunk > 0)
-            PROF(c, KID_BACKSUB) k_backsub<false><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptchunk, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
+            PROF(c, KID_BACKSUB) k_backsub<false><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
                                                                     gb, c->dp, c->pts[cur], c->camcache[cur], mu, ebp, dpbp,
                                                                     c->pts[nw], c->d_part);
         c->st_launches += 1;

@@ -133,7 +133,7 @@ double psba_launch_cost(psba_ctx *c, int set, double *ex_dev)
 //      ascending camera order (the order of compute_V.cl:24-31 / compute_g.cl:43-54);
 //   3. the W tile (128 x 144 B, contiguous in HBM because observations are point-major) is written
 //      with fully coalesced 16-byte stores.
-__global__ void __launch_bounds__(PT_CTA, 4) k_lin_points(const int *__restrict__ ptchunk, const int *__restrict__ pt_ptr,
+__global__ void __launch_bounds__(PT_CTA, 4) k_lin_points(const int4 *__restrict__ ptdesc, const int *__restrict__ pt_ptr,
                                                          const int *__restrict__ iidx, const int *__restrict__ jidx,
                                                          const double *__restrict__ impts, const double *__restrict__ cache,
                                                          const double *__restrict__ pts, double coeff, double coeff_g,
@@ -143,35 +143,49 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_lin_points(const int *__restrict_
     __shared__ double sh[9][PT_CTA];
     __shared__ int sj[PT_CTA];
     const int tid = threadIdx.x;
-    const int p0 = ptchunk[blockIdx.x], p1 = ptchunk[blockIdx.x + 1];
-    const int o0 = pt_ptr[p0], o1 = pt_ptr[p1];
+    // one 16-byte descriptor per chunk {p0, p1, o0, o1}; every independent load of a wave is issued before
+    // anything waits (a CTA is a chain of dependent L2 / HBM round trips: the fewer links, the better)
+    const int4 ds = __ldg(ptdesc + blockIdx.x);
+    const int p0 = ds.x, p1 = ds.y, o0 = ds.z, o1 = ds.w;
     const int np = p1 - p0;
     double acc[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) acc[q] = 0.0;
     int my_a = 0, my_b = 0;
-    if (tid < np) { my_a = pt_ptr[p0 + tid]; my_b = pt_ptr[p0 + tid + 1]; }
+    if (tid < np) { my_a = __ldg(pt_ptr + p0 + tid); my_b = __ldg(pt_ptr + p0 + tid + 1); }
 
     for (int base = o0; base < o1; base += PT_CTA) {
         const int k = base + tid;
         const int cnt = min(PT_CTA, o1 - base);
-        sj[tid] = k < o1 ? jidx[k] : 0;
+        int ji = 0, ii = 0;
+        double2 mm = make_double2(0.0, 0.0);
+        if (k < o1) { ji = __ldg(jidx + k); ii = __ldg(iidx + k); mm = __ldg(reinterpret_cast<const double2 *>(impts) + k); }
+        sj[tid] = ji;
+        double X0 = 0, X1 = 0, X2 = 0;
+        if (k < o1) { const double *X = pts + (size_t)ii * 3; X0 = __ldg(X); X1 = __ldg(X + 1); X2 = __ldg(X + 2); }
         __syncthreads();
         // 1. stage camera entries: piece p = (observation p/12, 16-byte part p%12)
-        for (int p = tid; p < cnt * 12; p += PT_CTA) {
-            const int ob = p / 12, part = p - ob * 12;
-            const double2 v = __ldg(reinterpret_cast<const double2 *>(cache + (size_t)sj[ob] * CAMC) + part);
-            *reinterpret_cast<double2 *>(stage + ob * CAM_LD + part * 2) = v;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                       // two batches of six loads in flight (register budget)
+            double2 cv[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int p = tid + (h * 6 + q) * PT_CTA, ob = p / 12, part = p - ob * 12;
+                cv[q] = p < cnt * 12 ? __ldg(reinterpret_cast<const double2 *>(cache + (size_t)sj[ob] * CAMC) + part) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int p = tid + (h * 6 + q) * PT_CTA, ob = p / 12, part = p - ob * 12;
+                if (p < cnt * 12) *reinterpret_cast<double2 *>(stage + ob * CAM_LD + part * 2) = cv[q];
+            }
         }
         __syncthreads();
         double w[18];
         if (k < o1) {
             CamReg cam;
             load_cam<false>(stage + tid * CAM_LD, cam);
-            const double *X = pts + (size_t)iidx[k] * 3;
-            double2 mm = __ldg(reinterpret_cast<const double2 *>(impts) + k);
             double e0, e1, A[12], B[6];
-            residual_jac(cam, __ldg(X), __ldg(X + 1), __ldg(X + 2), mm.x, mm.y, e0, e1, A, B);
+            residual_jac(cam, X0, X1, X2, mm.x, mm.y, e0, e1, A, B);
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -277,7 +291,7 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
     const int set = c->cur;
     if (!c->cache_valid[set]) psba_launch_cam_prep(c, set);
     if (c->n_ptchunk > 0)
-        PROF(c, KID_LIN_POINTS) k_lin_points<<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptchunk, c->pt_ptr, c->iidx, c->jidx, c->impts,
+        PROF(c, KID_LIN_POINTS) k_lin_points<<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts,
                                                             c->camcache[set], c->pts[set], coeff_uvw, coeff_g,
                                                             c->W, c->V, c->g + c->N);
     if (c->n_cchunk > 0)

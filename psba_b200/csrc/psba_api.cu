@@ -173,7 +173,7 @@ extern "C" void psba_release_buffer(psba_ctx *c)
     if (!c) return;
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     void *ptrs[] = {c->K, c->initcams, c->impts, c->cams[0], c->cams[1], c->pts[0], c->pts[1], c->camcache[0], c->camcache[1],
-                    c->iidx, c->jidx, c->pt_ptr, c->ptchunk, c->cam_obs, c->cchunk_cam, c->cchunk_beg, c->cchunk_end,
+                    c->iidx, c->jidx, c->pt_ptr, c->ptchunk, c->ptdesc, c->cam_obs, c->cchunk_cam, c->cchunk_beg, c->cchunk_end,
                     c->cam_cchunk_ptr, c->tri_oa, c->tri_ob, c->tri_pt, c->pair_k, c->pair_l, c->pair_chunk_ptr, c->pchunk_pair,
                     c->pchunk_beg, c->pchunk_end, c->W, c->V, c->Vinv, c->U, c->g, c->UVdiag_scr, c->cam_part, c->pair_part,
                     c->tile_index, c->Stiles, c->Linv, c->eab, c->dp, c->d_status, c->Ldiag, c->cam2pos, c->pos2cam, c->d_crit_I, c->d_crit_K,

@@ -59,7 +59,7 @@ struct psba_ctx {
     // ---- structure
     int *iidx, *jidx;               // local obs -> LOCAL point id, camera id
     int *pt_ptr;                    // n+1
-    int *ptchunk; int n_ptchunk;    // point-major CTA chunks (point boundaries)
+    int *ptchunk; int n_ptchunk;    int4 *ptdesc;    // point-major CTA chunks (point boundaries)
     int *cam_obs;                   // o: local obs ids in camera-major order (ascending point)
     int *cchunk_cam, *cchunk_beg, *cchunk_end; int n_cchunk;   // camera-major chunks
     int *cam_cchunk_ptr;            // m+1: chunk range of each camera

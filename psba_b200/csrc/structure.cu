@@ -240,6 +240,12 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
     }
     c->n_ptchunk = (int)pch.size() - 1;
     c->ptchunk = supload(c, pch);
+    {
+        std::vector<int4> desc(c->n_ptchunk);            // {p0, p1, o0, o1}: one 16-byte load per CTA
+        for (int q = 0; q < c->n_ptchunk; ++q)
+            desc[q] = make_int4(pch[q], pch[q + 1], hptr[p0 + pch[q]] - o0, hptr[p0 + pch[q + 1]] - o0);
+        c->ptdesc = supload(c, desc);
+    }
     // ---- camera-major order: stable radix sort of the local observations by camera
     c->cam_obs = salloc<int>(c, o);
     std::vector<int> cptr((size_t)m + 1, 0);
