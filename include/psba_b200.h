@@ -144,6 +144,12 @@ void psba_trace_get(psba_ctx *ctx, int k, psba_trace_rec *rec);
  * "force_lambda_count"; unknown names abort. */
 void psba_set_option(psba_ctx *ctx, const char *name, double value);
 double psba_get_stat(psba_ctx *ctx, const char *name);
+/* index-structure readback (test hook, like the `out` pointers of the operators): copies the named
+ * device-built table to `out` (at most max_count 64-bit-or-narrower elements) and returns its length.
+ * int32: "pt_ptr" (n+1), "cam_obs" (o), "pair_k"/"pair_l" (n_pairs), "tri_oa"/"tri_ob"/"tri_pt" (ntriples),
+ * "pchunk_pair" (n_pchunk), "cam2pos" (m); int64: "pchunk_beg"/"pchunk_end" (n_pchunk).  These replace
+ * blk_idx / comm3DIdx / comm3DIdxCnt of generate_idxs (PSBA/misc.cpp:178-218). */
+long long psba_get_index(psba_ctx *ctx, const char *name, void *out, long long max_count);
 /* lambda-follow hook for parity runs: the k-th modified-Cholesky event uses lam[k] */
 void psba_force_lambda(psba_ctx *ctx, const double *lam, int n);
 /* copy current parameters to the host: cams[m*6], pts[n*3] (either may be NULL) */

@@ -92,6 +92,8 @@ def lib():
     L.psba_set_option.argtypes = [vp, C.c_char_p, d]
     L.psba_get_stat.restype = d
     L.psba_get_stat.argtypes = [vp, C.c_char_p]
+    L.psba_get_index.restype = C.c_longlong
+    L.psba_get_index.argtypes = [vp, C.c_char_p, vp, C.c_longlong]
     L.psba_force_lambda.argtypes = [vp, _dp, i]
     L.psba_get_params.argtypes = [vp, i, _dp, _dp]
     L.psba_set_params.argtypes = [vp, _dp, _dp]
@@ -308,6 +310,14 @@ class PSBA:
 
     def set_option(self, name, v):
         self.L.psba_set_option(self.h, name.encode(), float(v))
+
+    def index(self, name):
+        """device-built index table by name (include/psba_b200.h: psba_get_index)"""
+        cnt = self.L.psba_get_index(self.h, name.encode(), None, 0)
+        out = np.zeros(cnt, dtype=np.int64 if name in ("pchunk_beg", "pchunk_end") else np.int32)
+        if cnt:
+            self.L.psba_get_index(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), cnt)
+        return out
 
     def stat(self, name):
         return self.L.psba_get_stat(self.h, name.encode())

@@ -509,6 +509,29 @@ extern "C" double psba_get_stat(psba_ctx *c, const char *name)
     return 0;
 }
 
+extern "C" long long psba_get_index(psba_ctx *c, const char *name, void *out, long long max_count)
+{
+    const std::string s(name);
+    const void *src = nullptr; long long cnt = 0; size_t esz = 4;
+    if (s == "pt_ptr") { src = c->pt_ptr; cnt = c->n + 1; }
+    else if (s == "cam_obs") { src = c->cam_obs; cnt = c->o; }
+    else if (s == "pair_k") { src = c->pair_k; cnt = c->n_pair; }
+    else if (s == "pair_l") { src = c->pair_l; cnt = c->n_pair; }
+    else if (s == "tri_oa") { src = c->tri_oa; cnt = c->ntri; }
+    else if (s == "tri_ob") { src = c->tri_ob; cnt = c->ntri; }
+    else if (s == "tri_pt") { src = c->tri_pt; cnt = c->ntri; }
+    else if (s == "pchunk_pair") { src = c->pchunk_pair; cnt = c->n_pchunk; }
+    else if (s == "pchunk_beg") { src = c->pchunk_beg; cnt = c->n_pchunk; esz = 8; }
+    else if (s == "pchunk_end") { src = c->pchunk_end; cnt = c->n_pchunk; esz = 8; }
+    else if (s == "cam2pos") { src = c->cam2pos; cnt = c->m; }
+    else die("get_index: unknown table");
+    if (out && cnt > 0) {
+        CUDA_CHECK(cudaMemcpyAsync(out, src, (size_t)std::min(cnt, max_count) * esz, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    return cnt;
+}
+
 void psba_prof_collect(psba_ctx *c)
 {
     if (c->prof_pending.empty()) return;

@@ -262,3 +262,46 @@ def test_banded_ring_nested_dissection_solve(nd_min, monkeypatch):
         assert abs(a["err"] - b["err"]) / a["err"] < 1e-9
         assert abs(a["mu"] - b["mu"]) / a["mu"] < 1e-9
     G.close(); O.close()
+
+
+@pytest.mark.parametrize("key", ["7", "54"])
+def test_device_built_index_structure_is_bit_exact(key):
+    """The index structure is built on the device (structure.cu).  It must reproduce the reference's tables of
+    generate_idxs (PSBA/misc.cpp:178-218) exactly: blk_idx (observation of point i in camera j), comm3DIdx /
+    comm3DIdxCnt (common points of every camera pair, ascending), and the camera-major scan order of compute_U."""
+    c, p, cnp = dataset_paths(key)
+    prob = psba_b200.read_sba(c, p, cnp)
+    O = oracle.Problem(prob, kind="restatement", dense=True)
+    G = psba_b200.PSBA(prob)
+    m, n, o = prob["m"], prob["n"], prob["o"]
+    blk = O.ibuf("blk_idx", n * m).reshape(n, m)
+    comm = O.ibuf("comm3DIdx", n * m * m).reshape(m, m, n)
+    cnt = O.ibuf("comm3DIdxCnt", m * m).reshape(m, m)
+    # CSR by point and camera-major order
+    ptr = G.index("pt_ptr")
+    assert np.array_equal(ptr, np.concatenate([[0], np.cumsum(np.bincount(prob["iidx"], minlength=n))]))
+    assert np.array_equal(G.index("cam_obs"), np.argsort(prob["jidx"], kind="stable"))
+    # camera pairs k >= l: every pair with a common point + every diagonal, sorted by (k, l)
+    pk, pl = G.index("pair_k"), G.index("pair_l")
+    want = [(k, l) for k in range(m) for l in range(k + 1) if cnt[k, l] > 0 or k == l]
+    assert list(zip(pk.tolist(), pl.tolist())) == want
+    # triples of every pair = the rows of comm3DIdx, with the observation ids blk_idx gives
+    oa, ob, pt = G.index("tri_oa"), G.index("tri_ob"), G.index("tri_pt")
+    cp, cb, ce = G.index("pchunk_pair"), G.index("pchunk_beg"), G.index("pchunk_end")
+    beg = {}; end = {}
+    for q in range(len(cp)):
+        beg.setdefault(int(cp[q]), int(cb[q])); end[int(cp[q])] = int(ce[q])
+    assert len(oa) == sum(int(cnt[k, l]) for k, l in want)
+    for pid, (k, l) in enumerate(want):
+        c_kl = int(cnt[k, l])
+        assert cnt[l, k] == c_kl
+        if c_kl == 0:
+            assert pid not in beg
+            continue
+        b, e = beg[pid], end[pid]
+        assert e - b == c_kl
+        pts_kl = comm[k, l, :c_kl]
+        assert np.array_equal(pts_kl, comm[l, k, :c_kl]) and np.all(np.diff(pts_kl) > 0)
+        assert np.array_equal(pt[b:e], pts_kl)
+        assert np.array_equal(oa[b:e], blk[pts_kl, k]) and np.array_equal(ob[b:e], blk[pts_kl, l])
+    G.close(); O.close()
