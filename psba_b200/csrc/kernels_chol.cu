@@ -249,6 +249,29 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
     }
     up_vec(c, &c->tile_index, c->h_tile_index);
     up_vec(c, &c->d_crit_I, critI); up_vec(c, &c->d_crit_K, critK);
+    {
+        // flat task descriptors: everything a CTA needs to find its tiles in ONE dependent load
+        //   critical: {I, K, slot(I,K), slot(K,K)} {src_begin, src_end}  + per source {slot(K,P), slot(I,P) or -1}
+        //   deferred: {slot(I,J), src_begin, src_end, -}                + per source {slot(I,P), slot(J,P)}
+        auto slot_of = [&](int A, int B) { return c->h_tile_index[(size_t)A * nt + B]; };
+        std::vector<int4> cd; std::vector<int2> cs;
+        for (size_t t = 0; t < critI.size(); ++t) {
+            const int I = critI[t], K = critK[t];
+            const int b0 = (int)cs.size();
+            for (int P : psrc_of[K]) cs.push_back(make_int2(slot_of(K, P), I == K ? -1 : slot_of(I, P)));
+            cd.push_back(make_int4(I, K, slot_of(I, K), slot_of(K, K)));
+            cd.push_back(make_int4(b0, (int)cs.size(), 0, 0));
+        }
+        std::vector<int4> dd; std::vector<int2> dsrc;
+        for (size_t t = 0; t < defI.size(); ++t) {
+            const int I = defI[t], J = defJ[t];
+            const int b0 = (int)dsrc.size();
+            for (int q = def_sptr[t]; q < def_sptr[t + 1]; ++q) dsrc.push_back(make_int2(slot_of(I, def_src[q]), slot_of(J, def_src[q])));
+            dd.push_back(make_int4(slot_of(I, J), b0, (int)dsrc.size(), 0));
+        }
+        up_vec(c, &c->d_crit_desc, cd); up_vec(c, &c->d_crit_src, cs);
+        up_vec(c, &c->d_def_desc, dd); up_vec(c, &c->d_def_srcs, dsrc);
+    }
     up_vec(c, &c->d_psrc_ptr, psrc_ptr); up_vec(c, &c->d_psrc, psrc);
     up_vec(c, &c->d_b_J, bJ); up_vec(c, &c->d_b_sptr, b_sptr); up_vec(c, &c->d_b_slot, b_slot);
     up_vec(c, &c->d_def_I, defI); up_vec(c, &c->d_def_J, defJ); up_vec(c, &c->d_def_sptr, def_sptr); up_vec(c, &c->d_def_src, def_src);
@@ -410,17 +433,21 @@ __device__ long long *g_panel_dbg = nullptr;
 //  through shared memory (double-buffered, one barrier per column); the loop body is branch-free (dead
 //  entries are updated too, a non-positive pivot poisons the panel with NaN and is reported once at the end).
 //  deferred CTAs: A_IJ -= sum_P L_IP L_JP^T for trailing tiles whose panel J runs in a later step.
-__global__ void __launch_bounds__(PANEL_NT) k_panel_step(int nt, int ncrit, const int *__restrict__ critI, const int *__restrict__ critK,
-                                                         const int *__restrict__ psrc_ptr, const int *__restrict__ psrc,
-                                                         int ndef, const int *__restrict__ defI, const int *__restrict__ defJ,
-                                                         const int *__restrict__ def_sptr, const int *__restrict__ def_src,
+__global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *__restrict__ crit_desc, const int2 *__restrict__ crit_src,
+                                                         int ndef, const int4 *__restrict__ def_desc, const int2 *__restrict__ def_srcs,
                                                          const int *__restrict__ bJ, const int *__restrict__ b_sptr, const int *__restrict__ b_slot,
-                                                         const int *__restrict__ tile_index, double *__restrict__ Stiles,
-                                                         double *__restrict__ Ldiag, double *__restrict__ bwork,
+                                                         double *__restrict__ Stiles, double *__restrict__ Ldiag, double *__restrict__ bwork,
                                                          double *__restrict__ ywork, double *__restrict__ contrib, int *__restrict__ status)
 {
     extern __shared__ double smem[];
     __shared__ __align__(16) double colbuf[2][2 * TS + 4];
+    // programmatic dependent launch: the CTAs of step s+1 are scheduled while step s drains; they fetch
+    // their (static) task descriptors and then wait for the previous step's memory to become visible
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    int4 cd0 = make_int4(0, 0, 0, 0), cd1 = cd0;
+    if ((int)blockIdx.x < ncrit) { cd0 = __ldg(crit_desc + 2 * blockIdx.x); cd1 = __ldg(crit_desc + 2 * blockIdx.x + 1); }
+    else if ((int)blockIdx.x < ncrit + ndef) cd0 = __ldg(def_desc + (blockIdx.x - ncrit));
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (*status != 0) return;
     const int tid = threadIdx.x, tr = tid % 8, tc = tid / 8;
     double *B0 = smem, *B1 = smem + TILE_SM;
@@ -437,15 +464,14 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int nt, int ncrit, cons
     }
     if ((int)blockIdx.x >= ncrit) {
         // ---- deferred trailing update:  A_IJ -= sum_P L_IP L_JP^T
-        const int t = blockIdx.x - ncrit;
-        const int I = defI[t], J = defJ[t];
-        const int sb = def_sptr[t], se = def_sptr[t + 1];
-        double *tij = Stiles + (size_t)tile_index[I * nt + J] * TS * TS;
+        const int4 dd = cd0;
+        const int sb = dd.y, se = dd.z;
+        double *tij = Stiles + (size_t)dd.x * TS * TS;
         TileRegs<PANEL_NT> ra, rb;
         {
-            const int P = def_src[sb];
-            tile_ldg(ra, Stiles + (size_t)tile_index[I * nt + P] * TS * TS);
-            tile_ldg(rb, Stiles + (size_t)tile_index[J * nt + P] * TS * TS);
+            const int2 sl = __ldg(def_srcs + sb);
+            tile_ldg(ra, Stiles + (size_t)sl.x * TS * TS);
+            tile_ldg(rb, Stiles + (size_t)sl.y * TS * TS);
         }
         double c18[6][3];
 #pragma unroll
@@ -457,9 +483,9 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int nt, int ncrit, cons
             tile_sts(B0, ra); tile_sts(B1, rb);
             __syncthreads();
             if (s + 1 < se) {                                  // next source's tiles fly during the product
-                const int P = def_src[s + 1];
-                tile_ldg(ra, Stiles + (size_t)tile_index[I * nt + P] * TS * TS);
-                tile_ldg(rb, Stiles + (size_t)tile_index[J * nt + P] * TS * TS);
+                const int2 sl = __ldg(def_srcs + s + 1);
+                tile_ldg(ra, Stiles + (size_t)sl.x * TS * TS);
+                tile_ldg(rb, Stiles + (size_t)sl.y * TS * TS);
             }
             double acc[6][3];
             tile_abt<false>(B0, B0, B1, acc, acc);
@@ -476,22 +502,22 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int nt, int ncrit, cons
     }
 
     // ---- critical path of panel K for tile row I
-    const int I = critI[blockIdx.x], K = critK[blockIdx.x];
+    const int I = cd0.x, K = cd0.y;
     const bool diagcta = I == K;
     long long *dbg = (g_panel_dbg && blockIdx.x == 0) ? g_panel_dbg + (size_t)K * 8 : nullptr;
     PANEL_STAMP(0);
-    const int sb = psrc_ptr[K], se = psrc_ptr[K + 1];
-    double *tik = Stiles + (size_t)tile_index[I * nt + K] * TS * TS;
-    const double *tkk = Stiles + (size_t)tile_index[K * nt + K] * TS * TS;
+    const int sb = cd1.x, se = cd1.y;
+    const int slot_ik = cd0.z;
+    double *tik = Stiles + (size_t)slot_ik * TS * TS;
+    const double *tkk = Stiles + (size_t)cd0.w * TS * TS;
     // all global loads are issued before anything waits on them
     TileRegs<PANEL_NT> rp, ri;
     bool upd = false;
     if (sb < se) {
-        const int P = psrc[sb];
-        tile_ldg(rp, Stiles + (size_t)tile_index[K * nt + P] * TS * TS);                         // L_KP
-        const int sl = diagcta ? -1 : tile_index[I * nt + P];
-        upd = sl >= 0;
-        if (upd) tile_ldg(ri, Stiles + (size_t)sl * TS * TS);                                     // L_IP
+        const int2 sl = __ldg(crit_src + sb);
+        tile_ldg(rp, Stiles + (size_t)sl.x * TS * TS);                                            // L_KP
+        upd = sl.y >= 0;
+        if (upd) tile_ldg(ri, Stiles + (size_t)sl.y * TS * TS);                                   // L_IP
     }
     double d[6][3], a[6][3];
 #pragma unroll
@@ -507,17 +533,16 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int nt, int ncrit, cons
     double bk = 0.0;
     if (tid < TS) {
         double sum = 0.0;
-        for (int s = sb; s < se; ++s) sum += contrib[(size_t)tile_index[K * nt + psrc[s]] * TS + tid];
+        for (int s = sb; s < se; ++s) sum += contrib[(size_t)__ldg(crit_src + s).x * TS + tid];
         bk = bwork[K * TS + tid] - sum;
     }
     for (int s = sb; s < se; ++s) {
         if (s > sb) {                                          // further sources (first panel of a separator)
             __syncthreads();
-            const int P = psrc[s];
-            tile_ldg(rp, Stiles + (size_t)tile_index[K * nt + P] * TS * TS);
-            const int sl = diagcta ? -1 : tile_index[I * nt + P];
-            upd = sl >= 0;
-            if (upd) tile_ldg(ri, Stiles + (size_t)sl * TS * TS);
+            const int2 sl = __ldg(crit_src + s);
+            tile_ldg(rp, Stiles + (size_t)sl.x * TS * TS);
+            upd = sl.y >= 0;
+            if (upd) tile_ldg(ri, Stiles + (size_t)sl.y * TS * TS);
         }
         tile_sts(B0, rp);
         if (upd) tile_sts(B1, ri);
@@ -669,7 +694,7 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int nt, int ncrit, cons
         double s = 0.0;
 #pragma unroll
         for (int c = 0; c < TS; c += 2) { dst[c / 2] = make_double2(row[c], row[c + 1]); s += row[c] * ysh[c] + row[c + 1] * ysh[c + 1]; }
-        contrib[(size_t)tile_index[I * nt + K] * TS + (tid - TS)] = s;
+        contrib[(size_t)slot_ik * TS + (tid - TS)] = s;
     }
 }
 // L_KK^-1 for every diagonal tile (needed by the backward substitution only): one CTA per tile,
@@ -704,10 +729,16 @@ static void enqueue_factor(psba_ctx *c)
         const int cb = c->step_crit_ptr[s], ncrit = c->step_crit_ptr[s + 1] - cb;
         const int db = c->step_def_ptr[s], ndef = c->step_def_ptr[s + 1] - db;
         const int bb = c->step_b_ptr[s], nb = c->step_b_ptr[s + 1] - bb;
-        k_panel_step<<<ncrit + ndef + nb, PANEL_NT, CHOL_SMEM, c->stream>>>(c->nt, ncrit, c->d_crit_I + cb, c->d_crit_K + cb, c->d_psrc_ptr, c->d_psrc,
-                                                                           ndef, c->d_def_I + db, c->d_def_J + db, c->d_def_sptr + db, c->d_def_src,
-                                                                           c->d_b_J + bb, c->d_b_sptr + bb, c->d_b_slot, c->tile_index, c->Stiles,
-                                                                           c->Ldiag, c->chol_aux, c->chol_diag, c->contrib, c->d_status);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ncrit + ndef + nb); cfg.blockDim = dim3(PANEL_NT); cfg.dynamicSmemBytes = CHOL_SMEM; cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = c->chol_pdl ? 1 : 0;
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_panel_step, ncrit, (const int4 *)(c->d_crit_desc + 2 * cb), (const int2 *)c->d_crit_src, ndef,
+                                      (const int4 *)(c->d_def_desc + db), (const int2 *)c->d_def_srcs, (const int *)(c->d_b_J + bb),
+                                      (const int *)(c->d_b_sptr + bb), (const int *)c->d_b_slot, c->Stiles, c->Ldiag, c->chol_aux,
+                                      c->chol_diag, c->contrib, c->d_status));
     }
     k_diag_inverse<<<c->nt, 256, 2 * TILE_SM * sizeof(double), c->stream>>>(c->Ldiag, c->Linv, c->d_status);
 }

@@ -93,10 +93,12 @@ struct psba_ctx {
     //   panel sources      : panels P of the previous step with a tile (K,P) (their updates are still pending)
     //   rhs task J         : b_J -= sum_P L_JP y_P over the panels P of the previous step (J in a later step)
     //   deferred task (I,J): trailing tile touched by panels of the previous step, J in a later step
+    bool chol_pdl;                             // programmatic dependent launch between the step kernels
     int n_steps; bool chain_schedule;          // chain: one panel per step (dense S)
     std::vector<int> step_crit_ptr, step_def_ptr, step_panel_ptr, step_b_ptr;
     int *d_crit_I, *d_crit_K, *d_psrc_ptr, *d_psrc, *d_b_J, *d_b_sptr, *d_b_slot;
     int *d_def_I, *d_def_J, *d_def_sptr, *d_def_src, *d_step_panels;
+    int4 *d_crit_desc, *d_def_desc; int2 *d_crit_src, *d_def_srcs;   // flat task descriptors (one load per CTA)
     double *contrib;                // n_tiles * TS: L_IK y_K per factor tile
     double *Ldiag;                  // nt * TS*TS   factor of the diagonal tiles (kept out of the tile pool)
     int *d_coltile_ptr, *d_coltile_row, *d_coltile_slot;   // CSC of the factor tiles (backward solve)
