@@ -19,6 +19,8 @@ if mode == "launches":
         if len(r) <= vi:
             continue
         name = r[ki].split("(")[0].replace("void ", "")
+        if name.startswith("cub::"):
+            name = name.split("<")[0] + "<...> (setup)"
         v = float(r[vi].replace(",", ""))
         v_us = v / 1e3 if r[ui] == "ns" else (v * 1e3 if r[ui] == "ms" else v)
         t = tot.setdefault(name, [0, 0.0])
@@ -26,7 +28,7 @@ if mode == "launches":
     total = sum(t[1] for t in tot.values())
     with open(dst, "w") as f:
         f.write("# ncu launch list summary (%s)\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over `python bench.py --steps 2 --warmup 3 "
-                "--no-e2e --no-cpu-baseline` (cold-cache, serialised launches: compare SHARES, not absolutes).\n\n" % src)
+                "--no-e2e --no-cpu-baseline` (includes the one-off device structure build) (cold-cache, serialised launches: compare SHARES, not absolutes).\n\n" % src)
         f.write("| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|\n")
         for k, (n, us) in sorted(tot.items(), key=lambda x: -x[1][1]):
             f.write("| %s | %d | %.1f | %.2f | %.1f%% |\n" % (k, n, us, us / n, 100 * us / total))
