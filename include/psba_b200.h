@@ -165,6 +165,7 @@ typedef struct {
     double dp_L2;         /* ||dp||^2                                   */
     double dp_dot;        /* sum dp_i (mu dp_i + g_i)   (levmar.cpp:271) */
     double solve_status;  /* 0.0 ok, 1.0 S not positive definite        */
+    double p_new_L2;      /* ||p + dp||^2 (levmar.cpp:214: p_L2 after an accepted step) */
 } psba_try_result;
 void psba_linearize(psba_ctx *ctx, double coeff_uvw, double coeff_g);
 void psba_try_step(psba_ctx *ctx, double mu, psba_try_result *res);

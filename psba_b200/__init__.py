@@ -32,7 +32,7 @@ class TraceRec(C.Structure):
 
 
 class TryResult(C.Structure):
-    _fields_ = [("cost_new", C.c_double), ("dp_L2", C.c_double), ("dp_dot", C.c_double), ("solve_status", C.c_double)]
+    _fields_ = [("cost_new", C.c_double), ("dp_L2", C.c_double), ("dp_dot", C.c_double), ("solve_status", C.c_double), ("p_new_L2", C.c_double)]
 
 
 def build():

@@ -73,7 +73,7 @@ extern "C" int psba_levmar(psba_ctx *c, int cnp, int pnp, int mnp, int n3Dpts, i
                     nu = 2;
                     c->cur = 1 - c->cur;                          // update_p: pointer swap
                     c->lin_valid = false;
-                    p_L2 = param_norm_sq(c, c->cur);
+                    p_L2 = res.p_new_L2;                          // fused into the back-substitution pass
                     ex_L2 = new_ex_L2;
                     if (fabs(rho - 1) < (1.0 / 5.0)) {
                         gooditer_cnt++;

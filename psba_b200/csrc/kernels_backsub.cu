@@ -11,23 +11,24 @@
 
 // candidate cameras = cams + dpa, plus the camera part of the step scalars
 __global__ void k_newcams(int N, const double *__restrict__ cams, const double *__restrict__ dpa, const double *__restrict__ ga,
-                          double mu, double *__restrict__ newcams, double *__restrict__ scal2)
+                          double mu, double *__restrict__ newcams, double *__restrict__ scal3)
 {
-    __shared__ double s0[256], s1[256];
-    double a = 0.0, b = 0.0;
+    __shared__ double s0[256], s1[256], s2[256];
+    double a = 0.0, b = 0.0, p2 = 0.0;
     for (int k = threadIdx.x; k < N; k += 256) {
-        const double d = dpa[k];
-        newcams[k] = cams[k] + d;
+        const double d = dpa[k], x = cams[k] + d;
+        newcams[k] = x;
         a += d * d;
         b += d * (mu * d + ga[k]);
+        p2 += x * x;
     }
-    s0[threadIdx.x] = a; s1[threadIdx.x] = b;
+    s0[threadIdx.x] = a; s1[threadIdx.x] = b; s2[threadIdx.x] = p2;
     __syncthreads();
     for (int w = 128; w > 0; w >>= 1) {
-        if (threadIdx.x < w) { s0[threadIdx.x] += s0[threadIdx.x + w]; s1[threadIdx.x] += s1[threadIdx.x + w]; }
+        if (threadIdx.x < w) { s0[threadIdx.x] += s0[threadIdx.x + w]; s1[threadIdx.x] += s1[threadIdx.x + w]; s2[threadIdx.x] += s2[threadIdx.x + w]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { scal2[0] = s0[0]; scal2[1] = s1[0]; }
+    if (threadIdx.x == 0) { scal3[0] = s0[0]; scal3[1] = s1[0]; scal3[2] = s2[0]; }
 }
 
 // CTA (128 threads) = one chunk of whole points (same chunks as k_lin_points).
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int4 *__restrict__ 
     double *pstage = stage;
     __shared__ double sh[3][PT_CTA];
     __shared__ double shx[3][PT_CTA];
-    __shared__ double red[3][PT_CTA / 32];
+    __shared__ double red[4][PT_CTA / 32];
     __shared__ int sj[PT_CTA];
     const int tid = threadIdx.x;
     // a CTA is a chain of dependent L2 / HBM round trips: one 16-byte chunk descriptor, then every
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int4 *__restrict__ 
         }
         __syncthreads();
     }
-    double s_dp2 = 0.0, s_dpg = 0.0, s_e2 = 0.0;
+    double s_dp2 = 0.0, s_dpg = 0.0, s_e2 = 0.0, s_p2 = 0.0;
     if (tid < np) {
         const int p = p0 + tid;
         const double e0 = g0 - acc0, e1 = g1 - acc1, e2 = g2 - acc2;
@@ -148,6 +149,7 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int4 *__restrict__ 
             newpts[(size_t)p * 3] = x0; newpts[(size_t)p * 3 + 1] = x1; newpts[(size_t)p * 3 + 2] = x2;
             shx[0][tid] = x0; shx[1][tid] = x1; shx[2][tid] = x2;
             s_dp2 = d0 * d0 + d1 * d1 + d2 * d2;
+            s_p2 = x0 * x0 + x1 * x1 + x2 * x2;
             s_dpg = d0 * (mu * d0 + g0) + d1 * (mu * d1 + g1) + d2 * (mu * d2 + g2);
         }
     }
@@ -191,32 +193,51 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int4 *__restrict__ 
         s_e2 += __shfl_down_sync(0xffffffffu, s_e2, w);
         s_dp2 += __shfl_down_sync(0xffffffffu, s_dp2, w);
         s_dpg += __shfl_down_sync(0xffffffffu, s_dpg, w);
+        s_p2 += __shfl_down_sync(0xffffffffu, s_p2, w);
     }
-    if ((tid & 31) == 0) { red[0][tid >> 5] = s_e2; red[1][tid >> 5] = s_dp2; red[2][tid >> 5] = s_dpg; }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = s_e2; red[1][tid >> 5] = s_dp2; red[2][tid >> 5] = s_dpg; red[3][tid >> 5] = s_p2; }
     __syncthreads();
-    if (tid < 3) {
+    if (tid < 4) {
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < PT_CTA / 32; ++w) s += red[tid][w];
-        part[(size_t)blockIdx.x * 3 + tid] = s;
+        part[(size_t)blockIdx.x * 4 + tid] = s;
     }
 }
 
-__global__ void k_final_reduce3(const double *__restrict__ part, int nparts, double *__restrict__ out);
 
-// out[v] = sum_p part[p*3+v], v<3, fixed order
-__global__ void k_final_reduce3(const double *__restrict__ part, int nparts, double *__restrict__ out)
+// out[v] = sum_p part[p*4+v], v<4, fixed order.  1024 threads, four independent partial sums per thread and
+// value so that the loads of one CTA are in flight together (it is a single-CTA kernel on the critical path
+// of every try: 44 us with 256 threads and one dependent chain)
+__global__ void __launch_bounds__(1024) k_final_reduce4(const double *__restrict__ part, int nparts, double *__restrict__ out)
 {
-    __shared__ double sh[3][256];
-    double s[3] = {0, 0, 0};
-    for (int p = threadIdx.x; p < nparts; p += 256) { s[0] += part[(size_t)p * 3]; s[1] += part[(size_t)p * 3 + 1]; s[2] += part[(size_t)p * 3 + 2]; }
-    sh[0][threadIdx.x] = s[0]; sh[1][threadIdx.x] = s[1]; sh[2][threadIdx.x] = s[2];
+    __shared__ double sh[4][1024];
+    double s[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) s[u][v] = 0.0;
+    const double4 *p4 = reinterpret_cast<const double4 *>(part);
+    int p = threadIdx.x;
+    for (; p + 3 * 1024 < nparts; p += 4 * 1024) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double4 q = p4[p + u * 1024];
+            s[u][0] += q.x; s[u][1] += q.y; s[u][2] += q.z; s[u][3] += q.w;
+        }
+    }
+    for (; p < nparts; p += 1024) { const double4 q = p4[p]; s[0][0] += q.x; s[0][1] += q.y; s[0][2] += q.z; s[0][3] += q.w; }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) sh[v][threadIdx.x] = (s[0][v] + s[1][v]) + (s[2][v] + s[3][v]);
     __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {
-        if (threadIdx.x < w) { sh[0][threadIdx.x] += sh[0][threadIdx.x + w]; sh[1][threadIdx.x] += sh[1][threadIdx.x + w]; sh[2][threadIdx.x] += sh[2][threadIdx.x + w]; }
+    for (int w = 512; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) sh[v][threadIdx.x] += sh[v][threadIdx.x + w];
+        }
         __syncthreads();
     }
-    if (threadIdx.x < 3) out[threadIdx.x] = sh[threadIdx.x][0];
+    if (threadIdx.x < 4) out[threadIdx.x] = sh[threadIdx.x][0];
 }
 
 // evaluate=true : dp (cams+points), candidate parameters, candidate cost, step scalars (LM try)
@@ -232,15 +253,17 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
             PROF(c, KID_BACKSUB) k_backsub<true><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
                                                                    gb, c->dp, c->pts[cur], c->camcache[nw], mu, ebp, dpbp,
                                                                    c->pts[nw], c->d_part);
-        PROF(c, KID_REDUCE) k_final_reduce3<<<1, 256, 0, c->stream>>>(c->d_part, c->n_ptchunk, c->d_scal);
+        PROF(c, KID_REDUCE) k_final_reduce4<<<1, 1024, 0, c->stream>>>(c->d_part, c->n_ptchunk, c->d_scal);
         c->st_launches += 3; c->st_exqt += 1;
-        if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal, 3);
-        CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal, 4);
+        CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
         if (res) {
             res->cost_new = c->h_scal[0];
             res->dp_L2 = c->h_scal[4] + c->h_scal[1];      // cameras first, then points (misc.cpp:151-157 order)
             res->dp_dot = c->h_scal[5] + c->h_scal[2];
+            res->p_new_L2 = c->h_scal[6] + c->h_scal[3];   // ||candidate parameters||^2
         }
     } else {
         if (c->n_ptchunk > 0)

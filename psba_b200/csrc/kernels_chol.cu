@@ -743,7 +743,10 @@ static void enqueue_factor(psba_ctx *c)
     k_diag_inverse<<<c->nt, 256, 2 * TILE_SM * sizeof(double), c->stream>>>(c->Ldiag, c->Linv, c->d_status);
 }
 
-double psba_launch_factor(psba_ctx *c)
+// defer_status: do not wait for the outcome here (the fused try reads the status word together with the
+// step scalars after the back-substitution; the kernels behind a failed factorisation run on garbage and
+// their results are discarded)
+double psba_launch_factor(psba_ctx *c, bool defer_status)
 {
     CUDA_CHECK(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream));
     if (!c->chol_graph_ok) {
@@ -779,6 +782,8 @@ double psba_launch_factor(psba_ctx *c)
                             h[K * 8 + 5] - h[K * 8 + 4], h[K * 8 + 5] - h[K * 8]);
     }
     c->st_launches += c->n_steps + 2;
+    c->S_valid = false;      // the factor overwrote the tile pool
+    if (defer_status) { c->factor_valid = true; return 0.0; }
     int st = 0;
     CUDA_CHECK(cudaMemcpyAsync(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));

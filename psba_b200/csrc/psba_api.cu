@@ -88,6 +88,8 @@ extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3D
     c->d_status = dalloc<int>(c, 4);
     c->d_scal = dalloc<double>(c, NSCAL);
     CUDA_CHECK(cudaMallocHost(&c->h_scal, NSCAL * sizeof(double)));
+    CUDA_CHECK(cudaMallocHost(&c->h_status, 4 * sizeof(int)));
+    c->h_status[0] = 0;
     return c;
 }
 
@@ -187,7 +189,7 @@ extern "C" void psba_release_buffer(psba_ctx *c)
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (c->chol_graph_ok) cudaGraphExecDestroy(c->chol_graph);
     if (c->bw_graph_ok) cudaGraphExecDestroy(c->bw_graph);
-    cudaFreeHost(c->h_scal);
+    cudaFreeHost(c->h_scal); cudaFreeHost(c->h_status);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -565,9 +567,10 @@ extern "C" void psba_try_step(psba_ctx *c, double mu, psba_try_result *res)
     if (!c->lin_valid) die("try_step before linearize");
     c->st_tries += 1;
     psba_launch_schur(c, mu);
-    res->solve_status = psba_launch_factor(c);
-    res->cost_new = res->dp_L2 = res->dp_dot = NAN;
-    if (res->solve_status != 0.0) return;
+    psba_launch_factor(c, true);                     // no host round trip between factorisation and solves
+    res->cost_new = res->dp_L2 = res->dp_dot = res->p_new_L2 = NAN;
     psba_launch_solve(c);
-    psba_launch_backsub(c, mu, true, res);
+    psba_launch_backsub(c, mu, true, res);           // reads the status word with the step scalars
+    res->solve_status = c->h_status[0] ? 1.0 : 0.0;
+    if (res->solve_status != 0.0) { c->factor_valid = false; res->cost_new = res->dp_L2 = res->dp_dot = res->p_new_L2 = NAN; }
 }

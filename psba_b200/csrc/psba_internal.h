@@ -111,6 +111,7 @@ struct psba_ctx {
     // ---- scalars
     double *d_part;                 // per-chunk partial sums (n_ptchunk * 4)
     double *d_scal; double *h_scal; // NSCAL doubles (h_scal pinned)
+    int *h_status;                  // pinned copy of d_status[0] read with the step scalars
     // ---- TR vectors (local layout [N | 3n])
     double *P_U, *P_B, *P;
     // ---- compat state
@@ -148,7 +149,7 @@ void psba_launch_schur(psba_ctx *c, double mu);
 void psba_launch_Y_materialize(psba_ctx *c, double *Y);
 // ---- kernels_solve.cu
 void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int,int>> &camera_pairs);
-double psba_launch_factor(psba_ctx *c);      // returns 0.0 / 1.0 (syncs)
+double psba_launch_factor(psba_ctx *c, bool defer_status = false);      // returns 0.0 / 1.0 (syncs unless deferred)
 void psba_launch_solve(psba_ctx *c);         // dp[0..N) = S^-1 eab[0..N)
 void psba_tiles_to_dense(psba_ctx *c, double *dense_dev, bool mirror);
 void psba_launch_explicit_inverse(psba_ctx *c, double *out_dev);
