@@ -99,7 +99,7 @@ def kernel_bytes(G, prob_sizes):
     ntri, npch, ncch = st("ntriples"), st("n_pchunk"), st("n_cchunk")
     return {
         "k_lin_points": 168 * o + 96 * n + 192 * m,           # R impts16 jidx4 iidx4 P24n C192m | W W144 V48n gb24n
-        "k_lin_cams": 24 * o + 24 * n + 192 * m + 216 * ncch,  # R cam_obs4 iidx4 impts16 P C | W partials
+        "k_lin_cams": 20 * o + 24 * n + 192 * m + 216 * ncch,  # R cam_pt4 cam_impts16 P C | W partials
         "k_schur_pairs": 148 * o + 72 * n + 8 * ntri + 336 * npch,   # R W144 iidx4 Vinv48n gb24n triples8 | W partials
         "k_backsub": 168 * o + 168 * n + 96 * m + 48 * m,     # R W144 jidx4 iidx4 impts16 Vinv gb pts dpa C' | W eb dpb newpts
         "k_cost": 24 * o + 24 * n + 96 * m,

@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_lin_points(const int4 *__restrict
 // Each thread accumulates A^T A (21 upper entries) and A^T e (6) over its observations, then one
 // deterministic block reduction per chunk writes 27 partials.
 __global__ void __launch_bounds__(CAM_CTA, 4) k_lin_cams(const int *__restrict__ cchunk_cam, const int *__restrict__ cchunk_beg,
-                                                        const int *__restrict__ cchunk_end, const int *__restrict__ cam_obs,
-                                                        const int *__restrict__ iidx, const double *__restrict__ impts,
+                                                        const int *__restrict__ cchunk_end, const int *__restrict__ cam_pt,
+                                                        const double *__restrict__ cam_impts,
                                                         const double *__restrict__ cache, const double *__restrict__ pts,
                                                         double *__restrict__ part)
 {
@@ -249,11 +249,12 @@ __global__ void __launch_bounds__(CAM_CTA, 4) k_lin_cams(const int *__restrict__
     double acc[27];
 #pragma unroll
     for (int q = 0; q < 27; ++q) acc[q] = 0.0;
+    // point index and measurement come from camera-major copies made at set-up (coalesced streams); only the
+    // point itself, which changes every iteration, is gathered
 #pragma unroll 1
     for (int t = beg + threadIdx.x; t < end; t += CAM_CTA) {
-        const int k = cam_obs[t];
-        const double *X = pts + (size_t)iidx[k] * 3;
-        double2 mm = __ldg(reinterpret_cast<const double2 *>(impts) + k);
+        const double *X = pts + (size_t)__ldg(cam_pt + t) * 3;
+        double2 mm = __ldg(reinterpret_cast<const double2 *>(cam_impts) + t);
         double e0, e1, A[12], B[6];
         residual_jac(cam, __ldg(X), __ldg(X + 1), __ldg(X + 2), mm.x, mm.y, e0, e1, A, B);
         int q = 0;
@@ -295,8 +296,8 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
                                                             c->camcache[set], c->pts[set], coeff_uvw, coeff_g,
                                                             c->W, c->V, c->g + c->N);
     if (c->n_cchunk > 0)
-        PROF(c, KID_LIN_CAMS) k_lin_cams<<<c->n_cchunk, CAM_CTA, 0, c->stream>>>(c->cchunk_cam, c->cchunk_beg, c->cchunk_end, c->cam_obs,
-                                                          c->iidx, c->impts, c->camcache[set], c->pts[set], c->cam_part);
+        PROF(c, KID_LIN_CAMS) k_lin_cams<<<c->n_cchunk, CAM_CTA, 0, c->stream>>>(c->cchunk_cam, c->cchunk_beg, c->cchunk_end, c->cam_pt,
+                                                          c->cam_impts, c->camcache[set], c->pts[set], c->cam_part);
     PROF(c, KID_CAM_REDUCE) k_cam_reduce<<<cdiv(c->m * 27, 128), 128, 0, c->stream>>>(c->m, c->cam_cchunk_ptr, c->cam_part, coeff_uvw, coeff_g,
                                                              c->U, c->g);
     c->st_launches += 3; c->st_lin += 1;

@@ -115,7 +115,7 @@ __device__ __forceinline__ void pair_accumulate(long long beg, long long end, in
 }
 
 template <int G>
-__global__ void __launch_bounds__(PAIR_CTA, 3) k_schur_pairs(int n_pchunk, const int *__restrict__ pchunk_pair,
+__global__ void __launch_bounds__(PAIR_CTA, 2) k_schur_pairs(int n_pchunk, const int *__restrict__ pchunk_pair,
                                                          const long long *__restrict__ pchunk_beg, const long long *__restrict__ pchunk_end,
                                                          const int *__restrict__ pair_k, const int *__restrict__ pair_l,
                                                          const int *__restrict__ tri_oa, const int *__restrict__ tri_ob,

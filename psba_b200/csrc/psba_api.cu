@@ -151,6 +151,7 @@ extern "C" void psba_fill_idxBuffer(psba_ctx *c, int nCams, int n3Dpts, int n2Dp
     }
     c->stage_impts = c->stage_pts = nullptr;
     c->pts[1] = dalloc<double>(c, (size_t)n * 3);
+    psba_build_camera_major_copies(c);
     // ---- work buffers
     const size_t Tl = (size_t)c->N + 3 * (size_t)n;
     c->W = dalloc<double>(c, (size_t)o * 18);
@@ -176,7 +177,7 @@ extern "C" void psba_release_buffer(psba_ctx *c)
     if (!c) return;
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     void *ptrs[] = {c->K, c->initcams, c->impts, c->cams[0], c->cams[1], c->pts[0], c->pts[1], c->camcache[0], c->camcache[1],
-                    c->iidx, c->jidx, c->pt_ptr, c->ptchunk, c->ptdesc, c->cam_obs, c->cchunk_cam, c->cchunk_beg, c->cchunk_end,
+                    c->iidx, c->jidx, c->pt_ptr, c->ptchunk, c->ptdesc, c->cam_obs, c->cam_pt, c->cam_impts, c->cchunk_cam, c->cchunk_beg, c->cchunk_end,
                     c->cam_cchunk_ptr, c->tri_oa, c->tri_ob, c->tri_pt, c->pair_k, c->pair_l, c->pair_chunk_ptr, c->pchunk_pair,
                     c->pchunk_beg, c->pchunk_end, c->W, c->V, c->Vinv, c->U, c->g, c->UVdiag_scr, c->cam_part, c->pair_part,
                     c->tile_index, c->Stiles, c->Linv, c->eab, c->dp, c->d_status, c->Ldiag, c->cam2pos, c->pos2cam, c->d_crit_I, c->d_crit_K,

@@ -61,6 +61,7 @@ struct psba_ctx {
     int *pt_ptr;                    // n+1
     int *ptchunk; int n_ptchunk;    int4 *ptdesc;    // point-major CTA chunks (point boundaries)
     int *cam_obs;                   // o: local obs ids in camera-major order (ascending point)
+    int *cam_pt; double *cam_impts; // camera-major copies of the point index and of the measurements
     int *cchunk_cam, *cchunk_beg, *cchunk_end; int n_cchunk;   // camera-major chunks
     int *cam_cchunk_ptr;            // m+1: chunk range of each camera
     // pair structure (lower triangle k>=l), triples sorted by (k,l), ascending point
@@ -137,6 +138,7 @@ void *psba_dev_alloc(psba_ctx *c, size_t bytes, bool zero);
 void psba_dev_free(psba_ctx *c, void *p);
 // ---- structure.cu
 void psba_build_structure(psba_ctx *c, const int *iidx_host, const int *jidx_host);
+void psba_build_camera_major_copies(psba_ctx *c);   // cam_pt, cam_impts (needs impts on the device)
 // ---- kernels_obs.cu
 void psba_launch_cam_prep(psba_ctx *c, int set);
 double psba_launch_cost(psba_ctx *c, int set, double *ex_dev /*may be null*/);

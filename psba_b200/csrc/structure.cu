@@ -127,6 +127,16 @@ __global__ void k_chunk_fill(int n_pair, long long pch, const long long *__restr
     for (long long b = tptr[p]; b < tptr[p + 1]; b += pch, ++q) { ch_pair[q] = p; ch_beg[q] = b; ch_end[q] = min(b + pch, tptr[p + 1]); }
 }
 
+__global__ void k_camera_major_copy(int o, const int *__restrict__ cam_obs, const int *__restrict__ iidx, const double *__restrict__ impts,
+                                    int *__restrict__ cam_pt, double *__restrict__ cam_impts)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= o) return;
+    const int k = cam_obs[t];
+    cam_pt[t] = iidx[k];
+    reinterpret_cast<double2 *>(cam_impts)[t] = reinterpret_cast<const double2 *>(impts)[k];
+}
+
 // ---- helpers ---------------------------------------------------------------------------------------
 template <class T> static T *salloc(psba_ctx *c, size_t n)
 {
@@ -359,4 +369,12 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
     // ---- camera system tiles (symbolic factorisation, host)
     psba_build_tile_structure(c, pairs);
     T.lap("tile structure");
+}
+
+// camera-major copies of the per-observation constants the camera pass reads (point index, measurement)
+void psba_build_camera_major_copies(psba_ctx *c)
+{
+    c->cam_pt = salloc<int>(c, c->o);
+    c->cam_impts = salloc<double>(c, (size_t)c->o * 2);
+    if (c->o) k_camera_major_copy<<<cdiv(c->o, 256), 256, 0, c->stream>>>(c->o, c->cam_obs, c->iidx, c->impts, c->cam_pt, c->cam_impts);
 }
