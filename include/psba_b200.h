@@ -185,6 +185,21 @@ int psba_readInitialSBAEstimate(const char *camsfname, const char *ptsfname, int
 void psba_quat2vec(const double *inp, int nin, double *outp, int nout);   /* misc.cpp:21-49 */
 void psba_free(void *p);
 
+/* Result writers (the reference has only commented-out prototypes, PSBA/readparams.h:13-25,
+ * PSBA/misc.cpp:60-85).  vec2quat: q = q_local(v) (x) q_init, the inverse of the set-up of PSBA/main.cpp:131-149.
+ * write_sba_result writes the 12-column camera file and the points file that psba_readInitialSBAEstimate
+ * (origin_cnp = 11) reads back; write_ply writes points (white) and camera centres (red).  Return 0 on success. */
+/* Native BAL loader: problem-*.txt (Rodrigues r, t, f, k1, k2 per camera; p = -P/P.z) converted to
+ * PSBA's form: R' = diag(1,-1,-1) R, t' likewise, image y flipped, K = {f, 0, 0, 1, 0}; observations sorted point-major
+ * with ascending cameras.  kc[m*2] receives (k1, k2), which the reference's model ignores; may be NULL. */
+int psba_read_bal(const char *fname, int *ncams, int *n3Dpts, int *n2Dprojs, double **Kparas, double **initrot,
+                  double **camsEx, double **pts, double **imgpts, int **iidx, int **jidx, double **kc);
+void psba_vec2quat(const double *initrot4, const double *local3, double *q4);
+int psba_write_sba_result(const char *camsfname, const char *ptsfname, int ncams, int n3Dpts, int n2Dprojs,
+                          const double *Kparas, const double *initrot, const double *camsEx, const double *pts,
+                          const double *imgpts, const int *iidx, const int *jidx);
+int psba_write_ply(const char *fname, int ncams, int n3Dpts, const double *initrot, const double *camsEx, const double *pts);
+
 /* ------------------------------------------------------------------ multi-GPU --------- */
 
 /* One process per GPU.  unique_id is the 128-byte ncclUniqueId created by rank 0

@@ -104,6 +104,10 @@ def lib():
                                               C.POINTER(_dp), C.POINTER(_ip), C.POINTER(_ip)]
     L.psba_quat2vec.argtypes = [_dp, i, _dp, i]
     L.psba_free.argtypes = [vp]
+    L.psba_read_bal.argtypes = [C.c_char_p, _ip, _ip, _ip] + [C.POINTER(_dp)] * 5 + [C.POINTER(_ip)] * 2 + [C.POINTER(_dp)]
+    L.psba_vec2quat.argtypes = [_dp, _dp, _dp]
+    L.psba_write_sba_result.argtypes = [C.c_char_p, C.c_char_p, i, i, i, _dp, _dp, _dp, _dp, _dp, _ip, _ip]
+    L.psba_write_ply.argtypes = [C.c_char_p, i, i, _dp, _dp, _dp]
     L.psba_comm_unique_id.argtypes = [C.c_char_p]
     L.psba_comm_init.argtypes = [i, i, C.c_char_p]
     L.psba_local_range.argtypes = [i, i, _ip, i, i, _ip, _ip, _ip, _ip]
@@ -139,6 +143,41 @@ def read_sba(cams_path, pts_path, origin_cnp=11, Kdefault=None):
     for p in (K, rot, ex, pts, im, ii, jj):
         L.psba_free(p)
     return out
+
+
+def read_bal(path):
+    """Native BAL problem-*.txt loader (psba_read_bal): the same dict as read_sba plus kc[m,2] = (k1, k2)."""
+    L = lib()
+    m, n, o = C.c_int(), C.c_int(), C.c_int()
+    K, rot, ex, pts, im, kc = _dp(), _dp(), _dp(), _dp(), _dp(), _dp()
+    ii, jj = _ip(), _ip()
+    rc = L.psba_read_bal(path.encode(), C.byref(m), C.byref(n), C.byref(o), C.byref(K), C.byref(rot), C.byref(ex),
+                         C.byref(pts), C.byref(im), C.byref(ii), C.byref(jj), C.byref(kc))
+    if rc:
+        raise RuntimeError("psba_read_bal failed with code %d" % rc)
+    m, n, o = m.value, n.value, o.value
+    take = lambda p, k, shp: np.ctypeslib.as_array(p, shape=(k,)).copy().reshape(shp)
+    out = dict(m=m, n=n, o=o, K=take(K, m * 5, (m, 5)), initrot=take(rot, m * 4, (m, 4)), cams=take(ex, m * 6, (m, 6)),
+               pts=take(pts, n * 3, (n, 3)), impts=take(im, o * 2, (o, 2)), iidx=take(ii, o, (o,)), jidx=take(jj, o, (o,)),
+               kc=take(kc, m * 2, (m, 2)))
+    for p in (K, rot, ex, pts, im, ii, jj, kc):
+        L.psba_free(p)
+    return out
+
+
+def write_result(prob, cams, pts, cams_path, pts_path, ply_path=None):
+    """Save refined parameters (cams[m,6] local rotation | t, pts[n,3]) as SBA text files that read_sba loads
+    back (12-column cameras with the rotations recomposed by vec2quat) and optionally as a PLY cloud."""
+    L = lib()
+    a = lambda x, t=np.float64: np.ascontiguousarray(x, dtype=t)
+    K, rot, ce, p3, im = a(prob["K"]), a(prob["initrot"]), a(cams), a(pts), a(prob["impts"])
+    ii, jj = a(prob["iidx"], np.int32), a(prob["jidx"], np.int32)
+    rc = L.psba_write_sba_result(cams_path.encode(), pts_path.encode(), int(prob["m"]), int(prob["n"]), int(prob["o"]),
+                                 _d(K), _d(rot), _d(ce), _d(p3), _d(im), _i(ii), _i(jj))
+    if rc == 0 and ply_path:
+        rc = L.psba_write_ply(ply_path.encode(), int(prob["m"]), int(prob["n"]), _d(rot), _d(ce), _d(p3))
+    if rc:
+        raise RuntimeError("writing the result failed")
 
 
 def local_range(n, o, iidx, rank, nranks):

@@ -181,3 +181,96 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"import oracle|from oracle|liboracle|psba_oracle\.h|orc_[a-z]", txt):
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_result_writer_round_trip(tmp_path):
+    """refined parameters written as SBA text (rotations recomposed by vec2quat) and read
+    back by the reader describe the same cameras: the oracle's reprojection cost of the re-read problem equals
+    the cost of the parameters that were written."""
+    c, p, cnp = dataset_paths("7")
+    prob = psba_b200.read_sba(c, p, cnp)
+    rng = np.random.default_rng(3)
+    cams = prob["cams"].copy()
+    cams[:, :3] = rng.normal(0, 0.02, (prob["m"], 3))          # a refined local rotation
+    cams[:, 3:] += rng.normal(0, 0.01, (prob["m"], 3))
+    pts = prob["pts"] + rng.normal(0, 0.01, prob["pts"].shape)
+    moved = dict(prob, cams=cams, pts=pts)
+    O = oracle.Problem(moved)
+    cost = O.call("exQT")
+    O.close()
+    co, po, ply = str(tmp_path / "c_out.txt"), str(tmp_path / "p_out.txt"), str(tmp_path / "r.ply")
+    psba_b200.write_result(prob, cams, pts, co, po, ply)
+    back = psba_b200.read_sba(co, po, 11)
+    assert back["m"] == prob["m"] and back["n"] == prob["n"] and back["o"] == prob["o"]
+    assert np.array_equal(back["iidx"], prob["iidx"]) and np.array_equal(back["jidx"], prob["jidx"])
+    assert np.array_equal(back["impts"], prob["impts"]) and np.array_equal(back["pts"], pts)
+    assert np.all(back["cams"][:, :3] == 0) and np.array_equal(back["cams"][:, 3:], cams[:, 3:])
+    O2 = oracle.Problem(back)
+    cost2 = O2.call("exQT")
+    O2.close()
+    assert abs(cost2 - cost) / cost < 1e-12
+    # vec2quat is the operation of compute_exQT.cl:46-49 and gives unit quaternions
+    q = np.zeros(4)
+    psba_b200.lib().psba_vec2quat(psba_b200._d(np.ascontiguousarray(prob["initrot"][0])), psba_b200._d(np.ascontiguousarray(cams[0, :3])), psba_b200._d(q))
+    assert abs(np.linalg.norm(q) - 1) < 1e-14
+    head = open(ply).read().split("end_header")[0]
+    assert "element vertex %d" % (prob["n"] + prob["m"]) in head
+    assert len(open(ply).read().strip().splitlines()) == 10 + prob["n"] + prob["m"]
+
+
+def _rodrigues(r):
+    th = np.linalg.norm(r)
+    if th < 1e-300:
+        return np.eye(3)
+    k = r / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+
+
+def test_native_bal_loader(tmp_path):
+    """a BAL problem-*.txt (Rodrigues, p = -P/P.z, observations in arbitrary order) is converted
+    to PSBA's quaternion / pinhole form.  The oracle's reprojection cost of the loaded problem must equal the BAL
+    cost computed here from the BAL parameters with the BAL camera model (k1 = k2 = 0)."""
+    rng = np.random.default_rng(11)
+    m, n = 6, 40
+    rv = rng.normal(0, 0.4, (m, 3)); rv[0] = 0.0                 # one identity rotation
+    rv[1] = np.array([np.pi - 1e-3, 0.0, 0.0])                   # close to 180 degrees: exercises every quaternion branch
+    t = rng.normal(0, 0.3, (m, 3)); f = rng.uniform(500, 900, m); kc = np.zeros((m, 2))
+    X = rng.normal(0, 1.0, (n, 3)) + np.array([0, 0, -8.0])      # in front of BAL cameras (negative z)
+    obs = []
+    for i in range(n):
+        for j in rng.choice(m, size=rng.integers(2, m + 1), replace=False):
+            P = _rodrigues(rv[j]) @ X[i] + t[j]
+            p = -P[:2] / P[2]
+            obs.append((int(j), i, *(f[j] * p + rng.normal(0, 0.5, 2))))
+    order = rng.permutation(len(obs))                            # BAL files need not be sorted
+    path = str(tmp_path / "problem-6-40-pre.txt")
+    with open(path, "w") as fh:
+        fh.write("%d %d %d\n" % (m, n, len(obs)))
+        for q in order:
+            fh.write("%d %d %.17e %.17e\n" % obs[q])
+        for j in range(m):
+            for v in list(rv[j]) + list(t[j]) + [f[j], kc[j, 0], kc[j, 1]]:
+                fh.write("%.17e\n" % v)
+        for i in range(n):
+            for v in X[i]:
+                fh.write("%.17e\n" % v)
+    prob = psba_b200.read_bal(path)
+    assert (prob["m"], prob["n"], prob["o"]) == (m, n, len(obs))
+    key = prob["iidx"].astype(np.int64) * m + prob["jidx"]
+    assert np.all(np.diff(key) > 0)                              # point-major, cameras ascending
+    assert np.array_equal(prob["K"], np.stack([f, 0 * f, 0 * f, 0 * f + 1, 0 * f], axis=1))
+    assert np.all(prob["initrot"][:, 0] >= 0) and np.allclose(np.linalg.norm(prob["initrot"], axis=1), 1, atol=1e-14)
+    bal_cost = 0.0
+    for (j, i, x, y) in obs:
+        P = _rodrigues(rv[j]) @ X[i] + t[j]
+        e = np.array([x, y]) - f[j] * (-P[:2] / P[2])
+        bal_cost += e @ e
+    O = oracle.Problem(prob)
+    cost = O.call("exQT")
+    O.close()
+    assert abs(cost - bal_cost) / bal_cost < 1e-10
+    with open(path, "w") as fh:
+        fh.write("2 2 1\n0 5 1.0 1.0\n")
+    with pytest.raises(RuntimeError):
+        psba_b200.read_bal(path)
