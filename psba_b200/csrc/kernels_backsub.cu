@@ -41,7 +41,7 @@ __global__ void k_newcams(int N, const double *__restrict__ cams, const double *
 // EVAL=false stops after phase B (trust region: the step is formed on the host side first).
 #define PROJ_LD 14         // doubles per staged projection entry (12 + pad: conflict-free LDS.128)
 template <bool EVAL>
-__global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int4 *__restrict__ ptdesc, const int *__restrict__ pt_ptr,
+__global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ chunk_list, const int4 *__restrict__ ptdesc, const int *__restrict__ pt_ptr,
                                                       const int *__restrict__ iidx, const int *__restrict__ jidx,
                                                       const double *__restrict__ impts, const double *__restrict__ W,
                                                       const double *__restrict__ Vinv, const double *__restrict__ gb,
@@ -60,7 +60,8 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int4 *__restrict__ 
     // a CTA is a chain of dependent L2 / HBM round trips: one 16-byte chunk descriptor, then every
     // independent load of the chunk (W tile, indices, measurements, the owner's point data) at once, then
     // the loads that need a camera index (dpa, projection entries)
-    const int4 ds = __ldg(ptdesc + blockIdx.x);
+    const int cidx = chunk_list ? chunk_list[blockIdx.x] : blockIdx.x;
+    const int4 ds = __ldg(ptdesc + cidx);
     const int p0 = ds.x, p1 = ds.y, o0 = ds.z, o1 = ds.w;
     const int np = p1 - p0;
     const bool single = o1 - o0 <= PT_CTA;                   // the common case: the whole chunk is one wave
@@ -201,10 +202,154 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int4 *__restrict__ 
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < PT_CTA / 32; ++w) s += red[tid][w];
-        part[(size_t)blockIdx.x * 4 + tid] = s;
+        part[(size_t)cidx * 4 + tid] = s;
     }
 }
 
+
+// PERSISTENT, software-pipelined variant for the chunks that fit one wave (all of them unless a point has more
+// than PT_CTA observations).  A CTA is otherwise a chain of dependent L2 / HBM round trips -- descriptor, then
+// indices and per-point data, then the gathers that need a camera index -- and 3-4 resident CTAs per SM cannot
+// hide ~5 us of chain behind ~1 us of work.  Here the descriptor is fetched two chunks ahead, the W tile of the
+// next chunk arrives by ONE TMA bulk copy (cp.async.bulk -> mbarrier) into a double-buffered shared tile, and the
+// next chunk's indices, measurements and per-point data are prefetched into registers; the only exposed round
+// trip per chunk is the gather of dpa / candidate-camera entries (L2 hits).
+template <int DUMMY>
+__global__ void __launch_bounds__(PT_CTA, 3) k_backsub_pipe(int n_list, const int *__restrict__ chunk_list, const int4 *__restrict__ ptdesc,
+                                                           const int *__restrict__ pt_ptr, const int *__restrict__ iidx,
+                                                           const int *__restrict__ jidx, const double *__restrict__ impts,
+                                                           const double *__restrict__ W, const double *__restrict__ Vinv,
+                                                           const double *__restrict__ gb, const double *__restrict__ dpa,
+                                                           const double *__restrict__ pts, const double *__restrict__ newcache, double mu,
+                                                           double *__restrict__ eb, double *__restrict__ dpb, double *__restrict__ newpts,
+                                                           double *__restrict__ part)
+{
+    extern __shared__ __align__(128) double wtile_dyn[];       // two W tiles (TMA destinations)
+    __shared__ __align__(16) double pstage[PT_CTA * PROJ_LD];
+    __shared__ __align__(8) unsigned long long bar[2];
+    __shared__ double sh[3][PT_CTA];
+    __shared__ double shx[3][PT_CTA];
+    __shared__ double red[4][PT_CTA / 32];
+    __shared__ int sj[PT_CTA];
+    const int tid = threadIdx.x, G = gridDim.x;
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    struct pre {                                               // what is prefetched per chunk, per thread
+        int j, lp; double2 mm;                                 // observation: camera, local point, measurement
+        int a, b; double g0, g1, g2, i00, i10, i20, i11, i21, i22, px, py, pz;   // owner of a point
+    };
+    auto chunk_of = [&](int q) { return chunk_list ? __ldg(chunk_list + q) : q; };
+    auto prefetch = [&](const int4 &d, int stage, pre &r) {
+        const int np = d.y - d.x, k = d.z + tid;
+        if (tid == 0) {
+            const unsigned bytes = (unsigned)(d.w - d.z) * 144u;
+            mbar_expect_tx(&bar[stage], bytes);
+            bulk_g2s(wtile_dyn + stage * PT_CTA * 18, W + (size_t)d.z * 18, bytes, &bar[stage]);
+        }
+        r.j = 0; r.lp = 0; r.mm = make_double2(0.0, 0.0);
+        if (k < d.w) { r.j = __ldg(jidx + k); r.lp = __ldg(iidx + k) - d.x; r.mm = __ldg(reinterpret_cast<const double2 *>(impts) + k); }
+        if (tid < np) {
+            const int p = d.x + tid;
+            r.a = __ldg(pt_ptr + p); r.b = __ldg(pt_ptr + p + 1);
+            r.g0 = __ldg(gb + (size_t)p * 3); r.g1 = __ldg(gb + (size_t)p * 3 + 1); r.g2 = __ldg(gb + (size_t)p * 3 + 2);
+            const double2 *vi = reinterpret_cast<const double2 *>(Vinv + (size_t)p * 6);
+            const double2 v01 = __ldg(vi), v23 = __ldg(vi + 1), v45 = __ldg(vi + 2);
+            r.i00 = v01.x; r.i10 = v01.y; r.i20 = v23.x; r.i11 = v23.y; r.i21 = v45.x; r.i22 = v45.y;
+            r.px = __ldg(pts + (size_t)p * 3); r.py = __ldg(pts + (size_t)p * 3 + 1); r.pz = __ldg(pts + (size_t)p * 3 + 2);
+        }
+    };
+    int q = blockIdx.x;
+    if (q >= n_list) return;
+    int4 ds = __ldg(ptdesc + chunk_of(q));
+    int4 ds1 = q + G < n_list ? __ldg(ptdesc + chunk_of(q + G)) : make_int4(0, 0, 0, 0);
+    pre cur, nxt;
+    prefetch(ds, 0, nxt);
+    for (int it = 0; q < n_list; q += G, ++it) {
+        const int st = it & 1;
+        const int cidx = chunk_of(q);
+        cur = nxt;
+        // two chunks ahead: descriptor only; one chunk ahead: data (its descriptor arrived an iteration ago)
+        const int4 ds2 = q + 2 * G < n_list ? __ldg(ptdesc + chunk_of(q + 2 * G)) : make_int4(0, 0, 0, 0);
+        if (q + G < n_list) prefetch(ds1, st ^ 1, nxt);
+        const int p0 = ds.x, o0 = ds.z, o1 = ds.w, np = ds.y - ds.x, cnt = o1 - o0;
+        const int k = o0 + tid;
+        const double *stage = wtile_dyn + st * PT_CTA * 18;
+        sj[tid] = cur.j;
+        double d[6];
+        if (k < o1) {
+            const double2 *dq = reinterpret_cast<const double2 *>(dpa + cur.j * 6);
+#pragma unroll
+            for (int u = 0; u < 3; ++u) { double2 d2 = __ldg(dq + u); d[2 * u] = d2.x; d[2 * u + 1] = d2.y; }
+        }
+        __syncthreads();                                       // sj visible
+        double2 pv[6];                                         // 6 x 16 B = q, t, K of the candidate camera
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+            const int p = tid + u * PT_CTA, ob = p / 6, piece = p - ob * 6;
+            pv[u] = p < cnt * 6 ? __ldg(reinterpret_cast<const double2 *>(newcache + (size_t)sj[ob] * CAMC) + piece) : make_double2(0.0, 0.0);
+        }
+        mbar_wait(&bar[st], (it >> 1) & 1);                    // the TMA bytes of this chunk have landed
+        if (k < o1) {
+            const double2 *wp = reinterpret_cast<const double2 *>(stage + tid * 18);
+            double w[18];
+#pragma unroll
+            for (int u = 0; u < 9; ++u) { double2 w2 = wp[u]; w[2 * u] = w2.x; w[2 * u + 1] = w2.y; }
+            double t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { t0 += w[r * 3] * d[r]; t1 += w[r * 3 + 1] * d[r]; t2 += w[r * 3 + 2] * d[r]; }
+            sh[0][tid] = t0; sh[1][tid] = t1; sh[2][tid] = t2;
+        }
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+            const int p = tid + u * PT_CTA, ob = p / 6, piece = p - ob * 6;
+            if (p < cnt * 6) *reinterpret_cast<double2 *>(pstage + ob * PROJ_LD + piece * 2) = pv[u];
+        }
+        __syncthreads();
+        double s_dp2 = 0.0, s_dpg = 0.0, s_e2 = 0.0, s_p2 = 0.0;
+        if (tid < np) {
+            double acc0 = 0, acc1 = 0, acc2 = 0;
+            for (int u = cur.a; u < cur.b; ++u) { acc0 += sh[0][u - o0]; acc1 += sh[1][u - o0]; acc2 += sh[2][u - o0]; }
+            const int p = p0 + tid;
+            const double e0 = cur.g0 - acc0, e1 = cur.g1 - acc1, e2 = cur.g2 - acc2;
+            const double d0 = cur.i00 * e0 + cur.i10 * e1 + cur.i20 * e2;
+            const double d1 = cur.i10 * e0 + cur.i11 * e1 + cur.i21 * e2;
+            const double d2 = cur.i20 * e0 + cur.i21 * e1 + cur.i22 * e2;
+            eb[(size_t)p * 3] = e0; eb[(size_t)p * 3 + 1] = e1; eb[(size_t)p * 3 + 2] = e2;
+            dpb[(size_t)p * 3] = d0; dpb[(size_t)p * 3 + 1] = d1; dpb[(size_t)p * 3 + 2] = d2;
+            const double x0 = cur.px + d0, x1 = cur.py + d1, x2 = cur.pz + d2;
+            newpts[(size_t)p * 3] = x0; newpts[(size_t)p * 3 + 1] = x1; newpts[(size_t)p * 3 + 2] = x2;
+            shx[0][tid] = x0; shx[1][tid] = x1; shx[2][tid] = x2;
+            s_dp2 = d0 * d0 + d1 * d1 + d2 * d2;
+            s_p2 = x0 * x0 + x1 * x1 + x2 * x2;
+            s_dpg = d0 * (mu * d0 + cur.g0) + d1 * (mu * d1 + cur.g1) + d2 * (mu * d2 + cur.g2);
+        }
+        __syncthreads();                                       // shx and pstage are complete
+        if (k < o1) {
+            CamProj cam;
+            load_cam_proj<false>(pstage + tid * PROJ_LD, cam);
+            double e0, e1;
+            residual(cam, shx[0][cur.lp], shx[1][cur.lp], shx[2][cur.lp], cur.mm.x, cur.mm.y, e0, e1);
+            s_e2 = e0 * e0 + e1 * e1;
+        }
+#pragma unroll
+        for (int w = 16; w > 0; w >>= 1) {
+            s_e2 += __shfl_down_sync(0xffffffffu, s_e2, w);
+            s_dp2 += __shfl_down_sync(0xffffffffu, s_dp2, w);
+            s_dpg += __shfl_down_sync(0xffffffffu, s_dpg, w);
+            s_p2 += __shfl_down_sync(0xffffffffu, s_p2, w);
+        }
+        if ((tid & 31) == 0) { red[0][tid >> 5] = s_e2; red[1][tid >> 5] = s_dp2; red[2][tid >> 5] = s_dpg; red[3][tid >> 5] = s_p2; }
+        __syncthreads();
+        if (tid < 4) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < PT_CTA / 32; ++w) s += red[tid][w];
+            part[(size_t)cidx * 4 + tid] = s;
+        }
+        __syncthreads();                                       // every shared buffer of this chunk is free again
+        ds = ds1; ds1 = ds2;
+    }
+}
 
 // out[v] = sum_p part[p*4+v], v<4, fixed order.  1024 threads, four independent partial sums per thread and
 // value so that the loads of one CTA are in flight together (it is a single-CTA kernel on the critical path
@@ -249,10 +394,18 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
     if (evaluate) {
         PROF(c, KID_NEWCAMS) k_newcams<<<1, 256, 0, c->stream>>>(c->N, c->cams[cur], c->dp, c->g, mu, c->cams[nw], c->d_scal + 4);
         psba_launch_cam_prep(c, nw);
-        if (c->n_ptchunk > 0)
-            PROF(c, KID_BACKSUB) k_backsub<true><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
-                                                                   gb, c->dp, c->pts[cur], c->camcache[nw], mu, ebp, dpbp,
-                                                                   c->pts[nw], c->d_part);
+        PROF(c, KID_BACKSUB) {
+            static bool attr_set = false;
+            const int dyn = 2 * PT_CTA * 18 * (int)sizeof(double);
+            if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_backsub_pipe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)); attr_set = true; }
+            if (c->n_small > 0)
+                k_backsub_pipe<0><<<std::min(c->n_small, c->n_sm * 3), PT_CTA, dyn, c->stream>>>(c->n_small, c->d_small_list, c->ptdesc, c->pt_ptr, c->iidx,
+                                                                                             c->jidx, c->impts, c->W, c->Vinv, gb, c->dp, c->pts[cur],
+                                                                                             c->camcache[nw], mu, ebp, dpbp, c->pts[nw], c->d_part);
+            if (c->n_big > 0)      // points with more observations than one wave
+                k_backsub<true><<<c->n_big, PT_CTA, 0, c->stream>>>(c->d_big_list, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
+                                                                   gb, c->dp, c->pts[cur], c->camcache[nw], mu, ebp, dpbp, c->pts[nw], c->d_part);
+        }
         PROF(c, KID_REDUCE) k_final_reduce4<<<1, 1024, 0, c->stream>>>(c->d_part, c->n_ptchunk, c->d_scal);
         c->st_launches += 3; c->st_exqt += 1;
         if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal, 4);
@@ -267,7 +420,7 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
         }
     } else {
         if (c->n_ptchunk > 0)
-            PROF(c, KID_BACKSUB) k_backsub<false><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
+            PROF(c, KID_BACKSUB) k_backsub<false><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(nullptr, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
                                                                     gb, c->dp, c->pts[cur], c->camcache[cur], mu, ebp, dpbp,
                                                                     c->pts[nw], c->d_part);
         c->st_launches += 1;

@@ -76,6 +76,8 @@ extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3D
     c->profile = false; c->timer_init = false;
     for (int k = 0; k < KID_COUNT; ++k) { c->prof_ms[k] = 0; c->prof_n[k] = 0; }
     c->comm = nullptr;
+    { int dev = 0; CUDA_CHECK(cudaGetDevice(&dev)); CUDA_CHECK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, dev)); }
+    c->d_small_list = c->d_big_list = nullptr; c->n_small = c->n_big = 0;
     c->chol_pdl = !(getenv("PSBA_NO_PDL") && atoi(getenv("PSBA_NO_PDL")));
     c->stage_impts = c->stage_pts = nullptr;
     c->K = dalloc<double>(c, (size_t)nCams * 5);
@@ -177,7 +179,7 @@ extern "C" void psba_release_buffer(psba_ctx *c)
     if (!c) return;
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     void *ptrs[] = {c->K, c->initcams, c->impts, c->cams[0], c->cams[1], c->pts[0], c->pts[1], c->camcache[0], c->camcache[1],
-                    c->iidx, c->jidx, c->pt_ptr, c->ptchunk, c->ptdesc, c->cam_obs, c->cam_pt, c->cam_impts, c->cchunk_cam, c->cchunk_beg, c->cchunk_end,
+                    c->iidx, c->jidx, c->pt_ptr, c->ptchunk, c->ptdesc, c->d_small_list, c->d_big_list, c->cam_obs, c->cam_pt, c->cam_impts, c->cchunk_cam, c->cchunk_beg, c->cchunk_end,
                     c->cam_cchunk_ptr, c->tri_oa, c->tri_ob, c->tri_pt, c->pair_k, c->pair_l, c->pair_chunk_ptr, c->pchunk_pair,
                     c->pchunk_beg, c->pchunk_end, c->W, c->V, c->Vinv, c->U, c->g, c->UVdiag_scr, c->cam_part, c->pair_part,
                     c->tile_index, c->Stiles, c->Linv, c->eab, c->dp, c->d_status, c->Ldiag, c->cam2pos, c->pos2cam, c->d_crit_I, c->d_crit_K,

@@ -60,6 +60,8 @@ struct psba_ctx {
     int *iidx, *jidx;               // local obs -> LOCAL point id, camera id
     int *pt_ptr;                    // n+1
     int *ptchunk; int n_ptchunk;    int4 *ptdesc;    // point-major CTA chunks (point boundaries)
+    int n_small, n_big; int *d_small_list, *d_big_list;   // one-wave chunks (null list = all) / oversize chunks
+    int n_sm;                       // multiprocessors of the device (persistent grids)
     int *cam_obs;                   // o: local obs ids in camera-major order (ascending point)
     int *cam_pt; double *cam_impts; // camera-major copies of the point index and of the measurements
     int *cchunk_cam, *cchunk_beg, *cchunk_end; int n_cchunk;   // camera-major chunks

@@ -255,6 +255,13 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
         for (int q = 0; q < c->n_ptchunk; ++q)
             desc[q] = make_int4(pch[q], pch[q + 1], hptr[p0 + pch[q]] - o0, hptr[p0 + pch[q + 1]] - o0);
         c->ptdesc = supload(c, desc);
+        // chunks that fit one wave go through the pipelined kernels; a chunk that is one point with more than
+        // PT_CTA observations keeps the wave loop
+        std::vector<int> small, big;
+        for (int q = 0; q < c->n_ptchunk; ++q) (desc[q].w - desc[q].z <= PT_CTA ? small : big).push_back(q);
+        c->n_small = (int)small.size(); c->n_big = (int)big.size();
+        c->d_small_list = big.empty() ? nullptr : supload(c, small);
+        c->d_big_list = big.empty() ? nullptr : supload(c, big);
     }
     // ---- camera-major order: stable radix sort of the local observations by camera
     c->cam_obs = salloc<int>(c, o);
