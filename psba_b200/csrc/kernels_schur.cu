@@ -158,6 +158,103 @@ static void launch_pairs(psba_ctx *c)
                                                                           c->Vinv, c->g + c->N, c->pair_part);
 }
 
+
+// Quad variant of the pair pass (PSBA_PAIR_MODE=1; measured 1.23 ms against 1.03 ms: twice the sector look-ups).  The lane-per-triple kernel above keeps 42 sums and two 6x3
+// blocks per thread (~170 registers, 8 warps per SM) and is bound by the latency of its gathers, not by their
+// volume.  Here FOUR lanes share a triple: lane (qa, qb) owns the 3x3 quadrant rows 3qa.., columns 3qb.. of the
+// block and reads only rows 3qa.. of W_a and rows 3qb.. of W_b (lanes of a quad that read the same rows are
+// merged by the load unit), so a thread holds 12 sums and streams its operands row by row: three times the
+// resident warps, three times the gathers in flight.  A group of G lanes (G/4 quads) owns one chunk of
+// triples; the quads' sums are combined by an xor butterfly over the quad index (fixed order).
+template <bool DIAG, int G>
+__device__ __forceinline__ void pair_accumulate_q(long long beg, long long end, int quad, int qa, int qb, const int *__restrict__ tri_oa,
+                                                  const int *__restrict__ tri_ob, const int *__restrict__ tri_pt,
+                                                  const double *__restrict__ W, const double *__restrict__ Vinv,
+                                                  const double *__restrict__ gb, double *acc)
+{
+    constexpr int Q = G / 4;
+    long long t = beg + quad;
+    int a_n = 0, b_n = 0, i_n = 0;
+    if (t < end) { a_n = __ldg(tri_oa + t); b_n = DIAG ? a_n : __ldg(tri_ob + t); i_n = __ldg(tri_pt + t); }
+#pragma unroll 1
+    for (; t < end; t += Q) {
+        const int a = a_n, b = b_n, i = i_n;
+        if (t + Q < end) {                              // indices of the next triple fly with this triple's blocks
+            a_n = __ldg(tri_oa + t + Q); b_n = DIAG ? a_n : __ldg(tri_ob + t + Q); i_n = __ldg(tri_pt + t + Q);
+        }
+        const double2 *vp = reinterpret_cast<const double2 *>(Vinv + (size_t)i * 6);
+        const double2 v01 = __ldg(vp), v23 = __ldg(vp + 1), v45 = __ldg(vp + 2);
+        const double *wbp = W + (size_t)b * 18 + 9 * qb, *wap = W + (size_t)a * 18 + 9 * qa;
+        double wb[9], wa[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) wb[q] = __ldg(wbp + q);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) wa[q] = __ldg(wap + q);
+        double g0 = 0, g1 = 0, g2 = 0;
+        if (DIAG) { const double *gp = gb + (size_t)i * 3; g0 = __ldg(gp); g1 = __ldg(gp + 1); g2 = __ldg(gp + 2); }
+        const double i00 = v01.x, i10 = v01.y, i20 = v23.x, i11 = v23.y, i21 = v45.x, i22 = v45.y;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const double w0 = wa[r * 3], w1 = wa[r * 3 + 1], w2 = wa[r * 3 + 2];
+            const double y0 = w0 * i00 + w1 * i10 + w2 * i20;
+            const double y1 = w0 * i10 + w1 * i11 + w2 * i21;
+            const double y2 = w0 * i20 + w1 * i21 + w2 * i22;
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc)
+                acc[r * 3 + cc] += y0 * wb[cc * 3] + y1 * wb[cc * 3 + 1] + y2 * wb[cc * 3 + 2];
+            if (DIAG) acc[9 + r] += y0 * g0 + y1 * g1 + y2 * g2;
+        }
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(PAIR_CTA, 5) k_schur_pairs_q(int n_pchunk, const int *__restrict__ pchunk_pair,
+                                                           const long long *__restrict__ pchunk_beg, const long long *__restrict__ pchunk_end,
+                                                           const int *__restrict__ pair_k, const int *__restrict__ pair_l,
+                                                           const int *__restrict__ tri_oa, const int *__restrict__ tri_ob,
+                                                           const int *__restrict__ tri_pt, const double *__restrict__ W,
+                                                           const double *__restrict__ Vinv, const double *__restrict__ gb,
+                                                           double *__restrict__ part)
+{
+    const int lane = threadIdx.x % G, quad = lane >> 2, qa = (lane >> 1) & 1, qb = lane & 1;
+    const int ch = blockIdx.x * (PAIR_CTA / G) + threadIdx.x / G;
+    double acc[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) acc[q] = 0.0;
+    bool diag = false;
+    if (ch < n_pchunk) {
+        const int pr = pchunk_pair[ch];
+        diag = pair_k[pr] == pair_l[pr];
+        if (diag) pair_accumulate_q<true, G>(pchunk_beg[ch], pchunk_end[ch], quad, qa, qb, tri_oa, tri_ob, tri_pt, W, Vinv, gb, acc);
+        else pair_accumulate_q<false, G>(pchunk_beg[ch], pchunk_end[ch], quad, qa, qb, tri_oa, tri_ob, tri_pt, W, Vinv, gb, acc);
+    }
+#pragma unroll
+    for (int w = G / 2; w >= 4; w >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 12; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], w);
+    }
+    if (ch < n_pchunk && quad == 0) {
+        double *out = part + (size_t)ch * 42;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) out[(3 * qa + r) * 6 + 3 * qb + cc] = acc[r * 3 + cc];
+        if (diag && qb == 0) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) out[36 + 3 * qa + r] = acc[9 + r];
+        }
+    }
+}
+
+template <int G>
+static void launch_pairs_q(psba_ctx *c)
+{
+    const int per_cta = PAIR_CTA / G;
+    k_schur_pairs_q<G><<<cdiv(c->n_pchunk, per_cta), PAIR_CTA, 0, c->stream>>>(c->n_pchunk, c->pchunk_pair, c->pchunk_beg, c->pchunk_end,
+                                                                            c->pair_k, c->pair_l, c->tri_oa, c->tri_ob, c->tri_pt, c->W,
+                                                                            c->Vinv, c->g + c->N, c->pair_part);
+}
+
 // position of entry (r,cc) of the camera block (k,l) inside the tile pool: the camera system is stored in
 // the solver's camera ordering (cam2pos); a block that lands above the diagonal is stored transposed
 __device__ __forceinline__ double *s_entry(double *Stiles, const int *__restrict__ tile_index, int nt, int pk, int pl, int r, int cc)
@@ -183,6 +280,262 @@ __global__ void k_S_finalize(int n_pair, const int *__restrict__ pair_k, const i
     if (v >= 36 && k != l) return;
     double s = 0.0;
     for (int ch = pair_chunk_ptr[pr]; ch < pair_chunk_ptr[pr + 1]; ++ch) s += part[(size_t)ch * 42 + v];
+    if (v < 36) {
+        const int r = v / 6, cc = v - r * 6;
+        double val = -s;
+        if (k == l && with_U) { val = U[k * 36 + r * 6 + cc] - s; if (r == cc) val = (U[k * 36 + r * 6 + cc] + mu) - s; }
+        *s_entry(Stiles, tile_index, nt, cam2pos[k], cam2pos[l], r, cc) = val;
+    } else {
+        const int r = v - 36;
+        ea[k * 6 + r] = with_U ? ga[k * 6 + r] - s : -s;
+    }
+}
+
+
+// ---- Row sweep (PSBA_PAIR_MODE=2; measured 1.39 ms against 1.03 ms).  CTA = a segment of ONE camera row k; thread = one camera pair
+// (k, l) of that row, l < k, with its 36 sums in registers for the whole segment; warp 0 owns the diagonal
+// pair.  The segment is walked in chunks of visits (camera k looks at point i).  Per chunk:
+//   1. every block the chunk needs -- for each visit the observations of point i with camera <= k, a
+//      CONTIGUOUS prefix of the point's observations -- is copied into shared memory by 16-byte asynchronous
+//      copies (coalesced: consecutive lanes, consecutive 16-byte pieces), each block exactly once per visit;
+//   2. one thread per visit forms Y_ik = W_ik Vinv_i and Y_ik gb_i (compute_Yblks.cl:26-37, compute_ea.cl:27-33);
+//   3. every pair thread consumes its triples of the chunk (they are a contiguous piece of the pair's run in the
+//      pair-sorted triple list: ascending point, the order of comm3DIdx) reading Y_ik and W_il from shared memory
+//      (compute_S.cl:44-52); the lanes of warp 0 stride the visits for the diagonal block and ea.
+// The pair-major kernel gathers 336 B per triple from L2 in 16-byte pieces per lane (5.2 GB of sector traffic
+// for 15 M triples); here a point's prefix is fetched once per visit (2.4 GB, whole lines) and the 108-FMA block
+// product runs out of shared memory.  Fixed summation order: ascending point per pair, segments in order.
+template <int NT, int B>
+__global__ void __launch_bounds__(NT, (NT <= 256 && B <= 320 ? 2 : 1))
+k_schur_rows(const int *__restrict__ seg_row, const int2 *__restrict__ seg_chunks, const int *__restrict__ seg_slot_base,
+             const int *__restrict__ row_pair0, const int4 *__restrict__ chunk_desc, const int4 *__restrict__ vis_desc,
+             const int2 *__restrict__ runs, const unsigned *__restrict__ tri_meta, const double *__restrict__ W,
+             const double *__restrict__ Vinv, const double *__restrict__ gb, double *__restrict__ part)
+{
+    constexpr int POOL = ROW_POOL_BYTES(B);                    // blocks from the bottom (144 B), Y entries from the top (208 B)
+    constexpr int MAXV = (B + ROW_MAXLEN + 2) / 3 + 1;         // visits per chunk (<= NT)
+    constexpr int YENT = 26;                                   // doubles per Y entry: rows 0-2 at 0, rows 3-5 at 10, Y gb at 20
+    static_assert(MAXV <= NT, "one visit per thread");
+    extern __shared__ __align__(128) unsigned char pool[];     // two pools: chunk c+1 lands while chunk c is consumed
+    __shared__ unsigned short own_slot[MAXV];
+    __shared__ __align__(8) unsigned long long bar[2];         // bytes of the bulk copies of each pool
+    const int seg = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k = __ldg(seg_row + seg);
+    const int2 cr = __ldg(seg_chunks + seg);
+    const int pair0 = __ldg(row_pair0 + k), nslot = __ldg(row_pair0 + k + 1) - pair0;      // the diagonal is the last slot
+    const int sbase = __ldg(seg_slot_base + seg);
+    const bool diag_warp = warp == 0;
+    const int ve = lane * (NT / 32) + warp;                    // the visit of a chunk this thread holds: every warp has some
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    // pair threads: a group of four lanes per pair, lane (qa, qb) owns the 3x3 quadrant rows 3qa.., columns 3qb.. of
+    // the 6x6 block (a lane per pair leaves most of a warp idle: the runs of a chunk are 2-4 triples long and differ
+    // from pair to pair); a group serves the pairs grp, grp + NG and grp + 2 NG of the row.  Three triple records are always in
+    // flight per pair (they are the only global loads of the product phase).
+    constexpr int NG = (NT - 32) / 4;
+    const int grp = (tid - 32) >> 2, qa = (tid >> 1) & 1, qb = tid & 1;
+    constexpr int NH = 3;                                      // pairs per group
+    int cur[NH], rend[NH];
+    unsigned m0[NH], m1[NH], m2[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) { cur[h] = rend[h] = 0; m0[h] = m1[h] = m2[h] = 0xffffffffu; }   // never a chunk number
+    if (!diag_warp) {
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            const int slot = grp + h * NG;
+            if (slot < nslot - 1) {
+                const int2 r = __ldg(runs + sbase + slot);
+                cur[h] = r.x; rend[h] = r.y;
+                if (cur[h] < rend[h]) m0[h] = __ldg(tri_meta + cur[h]);
+                if (cur[h] + 1 < rend[h]) m1[h] = __ldg(tri_meta + cur[h] + 1);
+                if (cur[h] + 2 < rend[h]) m2[h] = __ldg(tri_meta + cur[h] + 2);
+            }
+        }
+    }
+    // every copy of a chunk: the thread that holds a visit sends its prefix as ONE bulk copy (the prefix is contiguous
+    // in W) and its Vinv_i / gb_i as 16- and 8-byte asynchronous copies into the visit's Y entry
+    auto issue = [&](const int4 &cd, const int4 &d, int buf) {
+        unsigned char *pl = pool + buf * POOL;
+        if (tid == 0) mbar_expect_tx(&bar[buf], (unsigned)cd.z * 144u);
+        if (ve < cd.y) {
+            fence_proxy_async();
+            bulk_g2s(pl + d.z * 144, W + (size_t)d.x * 18, (unsigned)d.y * 144u, &bar[buf]);
+            double *ent = reinterpret_cast<double *>(pl + POOL) - (ve + 1) * YENT;
+            const double *vp = Vinv + (size_t)d.w * 6, *gp = gb + (size_t)d.w * 3;
+            cp_async16(ent, vp); cp_async16(ent + 2, vp + 2); cp_async16(ent + 4, vp + 4);
+            cp_async8(ent + 6, gp); cp_async8(ent + 7, gp + 1); cp_async8(ent + 8, gp + 2);
+        }
+    };
+    double acc[27];                                            // pair lanes: 3 x 9; diagonal warp: 21 + 6
+#pragma unroll
+    for (int q = 0; q < 27; ++q) acc[q] = 0.0;
+    const int4 zero4 = make_int4(0, 0, 0, 0);
+    // cdN / dN: chunk record and this thread's visit record of the chunk N steps ahead (records beyond the segment: 0)
+    int4 cd0 = cr.x < cr.y ? __ldg(chunk_desc + cr.x) : zero4;
+    int4 cd1 = cr.x + 1 < cr.y ? __ldg(chunk_desc + cr.x + 1) : zero4;
+    int4 cd2 = cr.x + 2 < cr.y ? __ldg(chunk_desc + cr.x + 2) : zero4;
+    int4 d0 = ve < cd0.y ? __ldg(vis_desc + cd0.x + ve) : zero4;
+    int4 d1 = ve < cd1.y ? __ldg(vis_desc + cd1.x + ve) : zero4;
+    __syncthreads();                                           // barriers initialised
+    issue(cd0, d0, 0);
+    cp_async_commit();
+    for (int c = cr.x, crel = 0; c < cr.y; ++c, ++crel) {
+        const int buf = crel & 1;
+        unsigned char *pl = pool + buf * POOL;
+        if (c + 1 < cr.y) issue(cd1, d1, buf ^ 1);
+        cp_async_commit();
+        // two chunks ahead: visit records (their chunk record arrived an iteration ago); three ahead: the chunk record
+        const int4 d2 = ve < cd2.y ? __ldg(vis_desc + cd2.x + ve) : zero4;
+        const int4 cd3 = c + 3 < cr.y ? __ldg(chunk_desc + c + 3) : zero4;
+        const int nvc = cd0.y;
+        cp_async_wait<1>();
+        mbar_wait(&bar[buf], (crel >> 1) & 1);
+        __syncthreads();
+        double *stage = reinterpret_cast<double *>(pl);
+        double *ytop = reinterpret_cast<double *>(pl + POOL);
+        // Y entries: Y_ik = W_ik Vinv_i (compute_Yblks.cl:26-37), Y_ik gb_i (compute_ea.cl:27-33)
+        if (ve < nvc) {
+            const int own = d0.z + d0.y - 1;                                                // the visit's own block: last of its prefix
+            own_slot[ve] = (unsigned short)own;
+            const double2 *wp = reinterpret_cast<const double2 *>(stage + own * 18);
+            double2 *yp = reinterpret_cast<double2 *>(ytop - (ve + 1) * YENT);
+            double w[18];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { const double2 w2 = wp[q]; w[2 * q] = w2.x; w[2 * q + 1] = w2.y; }
+            const double2 a01 = yp[0], a23 = yp[1], a45 = yp[2], g01 = yp[3];
+            const double g2 = reinterpret_cast<const double *>(yp)[8];
+            const double i00 = a01.x, i10 = a01.y, i20 = a23.x, i11 = a23.y, i21 = a45.x, i22 = a45.y;
+            double y[26];
+            y[9] = 0.0; y[19] = 0.0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                const int o3 = r < 3 ? r * 3 : 10 + (r - 3) * 3;
+                const double w0 = w[r * 3], w1 = w[r * 3 + 1], w2 = w[r * 3 + 2];
+                y[o3] = w0 * i00 + w1 * i10 + w2 * i20;
+                y[o3 + 1] = w0 * i10 + w1 * i11 + w2 * i21;
+                y[o3 + 2] = w0 * i20 + w1 * i21 + w2 * i22;
+                y[20 + r] = y[o3] * g01.x + y[o3 + 1] * g01.y + y[o3 + 2] * g2;
+            }
+#pragma unroll
+            for (int q = 0; q < 13; ++q) yp[q] = make_double2(y[2 * q], y[2 * q + 1]);
+        }
+        __syncthreads();
+        // block products out of shared memory (compute_S.cl:44-52)
+        if (!diag_warp) {
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+                while ((m0[h] >> 18) == (unsigned)crel) {
+                    const unsigned mt = m0[h];
+                    m0[h] = m1[h]; m1[h] = m2[h];
+                    m2[h] = cur[h] + 3 < rend[h] ? __ldg(tri_meta + cur[h] + 3) : 0xffffffffu;
+                    ++cur[h];
+                    // rows 3qa..3qa+2 of Y (entry doubles 10qa..10qa+8: 16-byte aligned), rows 3qb..3qb+2 of W_il (doubles 9qb..)
+                    const double2 *yp = reinterpret_cast<const double2 *>(ytop - (((mt >> 10) & 255u) + 1) * YENT + 10 * qa);
+                    const double *wp = stage + (mt & 1023u) * 18 + 9 * qb;
+                    double y[10], w[9];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) { const double2 a = yp[q]; y[2 * q] = a.x; y[2 * q + 1] = a.y; }
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) w[q] = wp[q];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) {
+                            double t = acc[h * 9 + r * 3 + cc];
+                            t = fma(y[r * 3], w[cc * 3], t); t = fma(y[r * 3 + 1], w[cc * 3 + 1], t); t = fma(y[r * 3 + 2], w[cc * 3 + 2], t);
+                            acc[h * 9 + r * 3 + cc] = t;
+                        }
+                }
+            }
+        } else {
+            for (int e = lane; e < nvc; e += 32) {
+                const double2 *yp = reinterpret_cast<const double2 *>(ytop - (e + 1) * YENT);
+                const double2 *wp = reinterpret_cast<const double2 *>(stage + (int)own_slot[e] * 18);
+                double ye[26], w[18];
+#pragma unroll
+                for (int q = 0; q < 13; ++q) { const double2 a = yp[q]; ye[2 * q] = a.x; ye[2 * q + 1] = a.y; }
+#pragma unroll
+                for (int q = 0; q < 9; ++q) { const double2 b = wp[q]; w[2 * q] = b.x; w[2 * q + 1] = b.y; }
+                int q = 0;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    const int o3 = r < 3 ? r * 3 : 10 + (r - 3) * 3;
+#pragma unroll
+                    for (int cc = 0; cc <= r; ++cc, ++q)
+                        acc[q] += ye[o3] * w[cc * 3] + ye[o3 + 1] * w[cc * 3 + 1] + ye[o3 + 2] * w[cc * 3 + 2];
+                }
+#pragma unroll
+                for (int r = 0; r < 6; ++r) acc[21 + r] += ye[20 + r];
+            }
+        }
+        __syncthreads();                                                                    // this pool is free again
+        cd0 = cd1; cd1 = cd2; cd2 = cd3; d0 = d1; d1 = d2;
+    }
+    cp_async_wait<0>();
+    if (!diag_warp) {
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            const int slot = grp + h * NG;
+            if (slot < nslot - 1) {
+                double *out = part + (size_t)(sbase + slot) * 42;
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) out[(3 * qa + r) * 6 + 3 * qb + cc] = acc[h * 9 + r * 3 + cc];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int w = 16; w > 0; w >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 27; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], w);
+        }
+        double *out = part + (size_t)(sbase + nslot - 1) * 42;
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int cc = 0; cc <= r; ++cc, ++q)
+                if (lane == (q & 31)) { out[r * 6 + cc] = acc[q]; out[cc * 6 + r] = acc[q]; }
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+            if (lane == r) out[36 + r] = acc[21 + r];
+    }
+}
+
+template <int NT, int B>
+static void launch_rows(psba_ctx *c)
+{
+    static bool attr_set = false;
+    const int dyn = 2 * ROW_POOL_BYTES(B);
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_schur_rows<NT, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        if (getenv("PSBA_ROW_DEBUG")) {
+            int nb = 0;
+            CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_schur_rows<NT, B>, NT, dyn));
+            fprintf(stderr, "psba: k_schur_rows<%d,%d>: %d CTAs/SM, %d segments, %d chunks\n", NT, B, nb, c->n_rseg, c->n_rchunk);
+        }
+        attr_set = true;
+    }
+    k_schur_rows<NT, B><<<c->n_rseg, NT, dyn, c->stream>>>(c->rseg_row, c->rseg_chunks, c->rseg_slot_base, c->row_pair0, c->rchunk_desc,
+                                                          c->vis_desc, c->rseg_runs, c->tri_meta, c->W, c->Vinv, c->g + c->N, c->pair_part);
+}
+
+// per pair block of the row sweep: fixed-order sum over the segments of its row, then as k_S_finalize
+__global__ void k_S_finalize_rows(int n_pair, const int *__restrict__ pair_k, const int *__restrict__ pair_l,
+                                  const int *__restrict__ row_pair0, const int *__restrict__ row_seg_ptr,
+                                  const int *__restrict__ seg_slot_base, const double *__restrict__ part,
+                                  const double *__restrict__ U, const double *__restrict__ ga, double mu, int with_U,
+                                  const int *__restrict__ tile_index, const int *__restrict__ cam2pos, int nt,
+                                  double *__restrict__ Stiles, double *__restrict__ ea)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int pr = t / 42, v = t - pr * 42;
+    if (pr >= n_pair) return;
+    const int k = pair_k[pr], l = pair_l[pr];
+    if (v >= 36 && k != l) return;
+    const int slot = pr - row_pair0[k];
+    double s = 0.0;
+    for (int sg = row_seg_ptr[k]; sg < row_seg_ptr[k + 1]; ++sg) s += part[(size_t)(seg_slot_base[sg] + slot) * 42 + v];
     if (v < 36) {
         const int r = v / 6, cc = v - r * 6;
         double val = -s;
@@ -224,21 +577,44 @@ void psba_launch_schur(psba_ctx *c, double mu)
 {
     psba_launch_vinv(c, mu);
     PROF(c, KID_MEMSET_S) CUDA_CHECK(cudaMemsetAsync(c->Stiles, 0, (size_t)c->n_tiles * TS * TS * sizeof(double), c->stream));
-    if (c->n_pchunk > 0)
-        PROF(c, KID_SCHUR_PAIRS) {
-            switch (c->pair_G) {
-            case 1: launch_pairs<1>(c); break;
-            case 2: launch_pairs<2>(c); break;
-            case 4: launch_pairs<4>(c); break;
-            case 8: launch_pairs<8>(c); break;
-            case 16: launch_pairs<16>(c); break;
-            default: launch_pairs<32>(c); break;
+    const int single = c->nranks == 1;
+    if (c->rows_ok) {
+        if (c->n_rseg > 0)
+            PROF(c, KID_SCHUR_PAIRS) {
+                if (c->rows_nt == 256 && c->row_budget == 304) launch_rows<256, 304>(c);
+                else if (c->rows_nt == 256) launch_rows<256, 640>(c);
+                else if (c->row_budget == 304) launch_rows<544, 304>(c);
+                else launch_rows<544, 640>(c);
+            }
+        PROF(c, KID_S_FINALIZE) k_S_finalize_rows<<<cdiv((long long)c->n_pair * 42, 128), 128, 0, c->stream>>>(c->n_pair, c->pair_k, c->pair_l, c->row_pair0,
+                                                                             c->row_seg_ptr, c->rseg_slot_base, c->pair_part, c->U, c->g, mu, single,
+                                                                             c->tile_index, c->cam2pos, c->nt, c->Stiles, c->eab);
+    } else {
+        if (c->n_pchunk > 0) {
+            PROF(c, KID_SCHUR_PAIRS) {
+                if (c->pair_mode == 1) {
+                    switch (c->pair_G) {
+                    case 4: launch_pairs_q<4>(c); break;
+                    case 8: launch_pairs_q<8>(c); break;
+                    case 16: launch_pairs_q<16>(c); break;
+                    default: launch_pairs_q<32>(c); break;
+                    }
+                } else {
+                    switch (c->pair_G) {
+                    case 1: launch_pairs<1>(c); break;
+                    case 2: launch_pairs<2>(c); break;
+                    case 4: launch_pairs<4>(c); break;
+                    case 8: launch_pairs<8>(c); break;
+                    case 16: launch_pairs<16>(c); break;
+                    default: launch_pairs<32>(c); break;
+                    }
+                }
             }
         }
-    const int single = c->nranks == 1;
-    PROF(c, KID_S_FINALIZE) k_S_finalize<<<cdiv((long long)c->n_pair * 42, 128), 128, 0, c->stream>>>(c->n_pair, c->pair_k, c->pair_l, c->pair_chunk_ptr,
+        PROF(c, KID_S_FINALIZE) k_S_finalize<<<cdiv((long long)c->n_pair * 42, 128), 128, 0, c->stream>>>(c->n_pair, c->pair_k, c->pair_l, c->pair_chunk_ptr,
                                                                              c->pair_part, c->U, c->g, mu, single, c->tile_index,
                                                                              c->cam2pos, c->nt, c->Stiles, c->eab);
+    }
     c->st_launches += 3;
     if (!single) {
         // the tile pool and ea are contiguous-by-construction only separately: two all-reduces

@@ -78,6 +78,8 @@ extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3D
     c->comm = nullptr;
     { int dev = 0; CUDA_CHECK(cudaGetDevice(&dev)); CUDA_CHECK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, dev)); }
     c->d_small_list = c->d_big_list = nullptr; c->n_small = c->n_big = 0;
+    c->rows_ok = false; c->rchunk_desc = nullptr; c->rchunk_first = nullptr; c->vis_desc = nullptr; c->tri_meta = nullptr; c->rseg_row = nullptr; c->rseg_chunks = nullptr;
+    c->rseg_slot_base = nullptr; c->rseg_runs = nullptr; c->row_pair0 = nullptr; c->row_seg_ptr = nullptr; c->n_rchunk = c->n_rseg = c->n_rpart = 0;
     c->chol_pdl = !(getenv("PSBA_NO_PDL") && atoi(getenv("PSBA_NO_PDL")));
     c->stage_impts = c->stage_pts = nullptr;
     c->K = dalloc<double>(c, (size_t)nCams * 5);
@@ -162,7 +164,7 @@ extern "C" void psba_fill_idxBuffer(psba_ctx *c, int nCams, int n3Dpts, int n2Dp
     c->g = dalloc<double>(c, Tl); c->dp = dalloc<double>(c, Tl); c->eab = dalloc<double>(c, Tl);
     c->P_U = dalloc<double>(c, Tl); c->P_B = dalloc<double>(c, Tl); c->P = dalloc<double>(c, Tl);
     c->cam_part = dalloc<double>(c, (size_t)c->n_cchunk * 27);
-    c->pair_part = dalloc<double>(c, (size_t)c->n_pchunk * 42);
+    c->pair_part = dalloc<double>(c, (size_t)std::max(c->n_pchunk, c->n_rpart) * 42);
     c->d_part = dalloc<double>(c, ((size_t)cdiv(o, 128) + c->n_ptchunk + 512) * 8);
     c->chol_aux = dalloc<double>(c, (size_t)3 * c->N + 2 * TS);
     c->chol_diag = dalloc<double>(c, (size_t)3 * c->N + 2 * TS);
@@ -186,7 +188,8 @@ extern "C" void psba_release_buffer(psba_ctx *c)
                     c->d_psrc_ptr, c->d_psrc, c->d_b_J, c->d_b_sptr, c->d_b_slot, c->d_def_I, c->d_def_J, c->d_def_sptr, c->d_def_src,
                     c->d_step_panels, c->d_crit_desc, c->d_def_desc, c->d_crit_src, c->d_def_srcs, c->d_bw_order, c->d_xdone, c->contrib, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
                     c->Sdense, c->Sdense_aux, c->chol_aux, c->chol_diag, c->chol_E, c->d_part, c->d_scal, c->P_U, c->P_B, c->P,
-                    c->tmpA, c->tmpB};
+                    c->tmpA, c->tmpB, c->rchunk_desc, c->rchunk_first, c->vis_desc, c->tri_meta, c->rseg_row, c->rseg_chunks, c->rseg_slot_base, c->rseg_runs,
+                    c->row_pair0, c->row_seg_ptr};
     for (void *p : ptrs) psba_dev_free(c, p);
     psba_dev_free(c, c->stage_impts); psba_dev_free(c, c->stage_pts);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -495,6 +498,9 @@ extern "C" double psba_get_stat(psba_ctx *c, const char *name)
     if (s == "n_cchunk") return c->n_cchunk;
     if (s == "n_pchunk") return c->n_pchunk;
     if (s == "pair_G") return c->pair_G;
+    if (s == "rows_ok") return c->rows_ok ? 1 : 0;
+    if (s == "n_rseg") return c->n_rseg;
+    if (s == "n_rchunk") return c->n_rchunk;
     if (s == "cholmod_events") return c->n_cholmod_events;
     if (s == "timer_ms") {   // device time since "timer_start" on the engine's stream
         if (!c->timer_init) die("timer_ms before timer_start");

@@ -23,7 +23,10 @@
 #define CAM_CTA 128        // threads per camera-major CTA
 #define CAM_OPT 4          // observations per thread in the camera-major pass
 #define PAIR_CTA 128       // threads per pair-pass CTA
-#define PAIR_TPL 24        // target triples per lane in the pair pass
+#define PAIR_TPL 24        // target triples per lane in the pair pass (lane-per-triple variant)
+#define PAIR_TPQ 64        // target triples per quad (quad-per-triple variant)
+#define ROW_MAXLEN 64      // longest prefix (observations of one point) the row kernel stages
+#define ROW_POOL_BYTES(B) (((B) + ROW_MAXLEN + 2) * 144)   // chunk pool for budget B (cost of a chunk: prefix blocks + 2 per visit)
 #define NSCAL 16           // size of the device scalar block
 
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
@@ -72,7 +75,19 @@ struct psba_ctx {
     int n_pair; int *pair_k, *pair_l;          // pair blocks present GLOBALLY (all ranks agree)
     int *pair_chunk_ptr;                        // n_pair+1
     int pair_G;                                 // lanes per chunk in the pair pass (1..32)
+    int pair_mode;                              // 0: lane per triple, 1: quad per triple (default), 2: row sweep
     int n_pchunk; int *pchunk_pair; long long *pchunk_beg, *pchunk_end;
+    // ---- row-sweep pair pass (k_schur_rows): CTA = segment of one camera row, thread = pair of that row
+    bool rows_ok;                   // false: a prefix or a row exceeds the kernel's caps, the pair-major kernel runs
+    int row_budget;                 // chunk budget: 304 (two CTAs per SM) or 640
+    int rows_nt;                    // threads per CTA (288: <= 128 off-diagonal pairs per row, else 544)
+    int n_rchunk, n_rseg, n_rpart;  // chunks, segments (CTAs), partial slots (sum of pairs-per-row over segments)
+    int *rchunk_first;              // n_rchunk+1: first visit (camera-major position) of every chunk
+    int4 *rchunk_desc;              // per chunk: first visit, visits, staged blocks
+    int4 *vis_desc;                 // per visit: first observation of the point, prefix length, stage slot in the chunk, point
+    unsigned *tri_meta;             // per triple: chunk in segment << 18 | visit in chunk << 10 | stage slot
+    int *rseg_row; int2 *rseg_chunks; int *rseg_slot_base; int2 *rseg_runs;
+    int *row_pair0, *row_seg_ptr;   // m+1: first pair / first segment of every camera row
     // ---- linearisation products
     double *W, *V, *Vinv, *U, *g, *UVdiag_scr;
     double coeff_uvw, coeff_g;

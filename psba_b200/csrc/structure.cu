@@ -137,6 +137,111 @@ __global__ void k_camera_major_copy(int o, const int *__restrict__ cam_obs, cons
     reinterpret_cast<double2 *>(cam_impts)[t] = reinterpret_cast<const double2 *>(impts)[k];
 }
 
+
+// ---- row-sweep pair pass (kernels_schur.cu: k_schur_rows) -----------------------------------------
+// A "visit" is an observation in camera-major order: camera k looks at point i.  The blocks a visit needs are
+// the observations of point i with camera <= k: a contiguous prefix of the point's observations (cameras
+// ascend inside a point).  Visits of one camera are cut into chunks by a running cost (prefix length + 2 per
+// visit): chunk = floor(cost_prefix / ROW_BUDGET), computable per visit without a sequential pass.
+__global__ void k_visit_len(int o, const int *__restrict__ cam_obs, const int *__restrict__ iidx, const int *__restrict__ pt_ptr,
+                            int *__restrict__ len, int *__restrict__ cam_pos, int *__restrict__ maxlen)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= o) return;
+    const int a = cam_obs[v];
+    const int l = a - pt_ptr[iidx[a]] + 1;
+    len[v] = l; cam_pos[a] = v;
+    if (l > ROW_MAXLEN) atomicMax(maxlen, l);
+}
+
+__device__ __forceinline__ int row_chunk_of(int v, int row_first, const int *__restrict__ vis_off, int budget)
+{
+    return ((vis_off[v] + 2 * v) - (vis_off[row_first] + 2 * row_first)) / budget;
+}
+
+__global__ void k_row_chunks(int RB, int m, const int *__restrict__ cam_ptr, const int *__restrict__ vis_off, int *__restrict__ nch)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const int b = cam_ptr[k], e = cam_ptr[k + 1];
+    nch[k] = e > b ? row_chunk_of(e - 1, b, vis_off, RB) + 1 : 0;
+}
+
+__global__ void k_chunk_first(int RB, int o, const int *__restrict__ cam_obs, const int *__restrict__ jidx, const int *__restrict__ cam_ptr,
+                              const int *__restrict__ vis_off, const int *__restrict__ row_chunk_base, int n_rchunk, int *__restrict__ chunk_first)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= o) return;
+    const int k = jidx[cam_obs[v]], b = cam_ptr[k];
+    const int c = row_chunk_of(v, b, vis_off, RB);
+    if (v == b || row_chunk_of(v - 1, b, vis_off, RB) != c) chunk_first[row_chunk_base[k] + c] = v;
+    if (v == o - 1) chunk_first[n_rchunk] = o;
+}
+
+__global__ void k_vis_desc(int RB, int o, const int *__restrict__ cam_obs, const int *__restrict__ iidx, const int *__restrict__ jidx,
+                           const int *__restrict__ pt_ptr, const int *__restrict__ cam_ptr, const int *__restrict__ vis_off,
+                           const int *__restrict__ row_chunk_base, const int *__restrict__ chunk_first, int4 *__restrict__ desc)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= o) return;
+    const int a = cam_obs[v], i = iidx[a], k = jidx[a], b = cam_ptr[k];
+    const int vf = chunk_first[row_chunk_base[k] + row_chunk_of(v, b, vis_off, RB)];
+    desc[v] = make_int4(pt_ptr[i], vis_off[v + 1] - vis_off[v], vis_off[v] - vis_off[vf], i);
+}
+
+// one 16-byte record per chunk: first visit, visits, staged blocks
+__global__ void k_chunk_desc(int n_rchunk, const int *__restrict__ chunk_first, const int4 *__restrict__ desc, int4 *__restrict__ cdesc)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_rchunk) return;
+    const int v0 = chunk_first[c], v1 = chunk_first[c + 1];
+    const int4 l = desc[v1 - 1];
+    cdesc[c] = make_int4(v0, v1 - v0, l.z + l.y, 0);
+}
+
+// per triple (pair-sorted): where the row kernel finds its operands
+__global__ void k_tri_meta(int RB, long long ntri, int SC, const int *__restrict__ tri_oa, const int *__restrict__ tri_ob, const int *__restrict__ cam_pos,
+                           const int *__restrict__ jidx, const int *__restrict__ cam_ptr, const int *__restrict__ vis_off,
+                           const int *__restrict__ row_chunk_base, const int *__restrict__ chunk_first, const int4 *__restrict__ desc,
+                           unsigned *__restrict__ meta)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntri) return;
+    const int a = tri_oa[t], bo = tri_ob[t];
+    const int v = cam_pos[a], k = jidx[a], rb = cam_ptr[k];
+    const int cir = row_chunk_of(v, rb, vis_off, RB);
+    const int vf = chunk_first[row_chunk_base[k] + cir];
+    const int4 d = desc[v];
+    meta[t] = ((unsigned)(cir % SC) << 18) | ((unsigned)(v - vf) << 10) | (unsigned)(d.z + (bo - d.x));
+}
+
+// triple range of every (segment, off-diagonal slot): the triples of the pair whose visit lies in the segment
+__global__ void k_seg_runs(int RB, int SC, const int *__restrict__ seg_row, const int *__restrict__ seg_slot_base, const int *__restrict__ row_seg_ptr,
+                           const int *__restrict__ row_pair0, const long long *__restrict__ tptr, const int *__restrict__ tri_oa,
+                           const int *__restrict__ cam_pos, const int *__restrict__ cam_ptr, const int *__restrict__ vis_off,
+                           int2 *__restrict__ runs)
+{
+    const int s = blockIdx.x;
+    const int k = seg_row[s], j = s - row_seg_ptr[k], nseg = row_seg_ptr[k + 1] - row_seg_ptr[k];
+    const int pair0 = row_pair0[k], noff = row_pair0[k + 1] - pair0 - 1, rb = cam_ptr[k];
+    for (int slot = threadIdx.x; slot < noff; slot += blockDim.x) {
+        const long long t0 = tptr[pair0 + slot], t1 = tptr[pair0 + slot + 1];
+        long long be = t0, en = t1;
+        if (nseg > 1) {
+            auto lower = [&](int want) {         // first triple of the pair whose segment is >= want
+                long long lo = t0, hi = t1;
+                while (lo < hi) {
+                    const long long mid = (lo + hi) >> 1;
+                    if (row_chunk_of(cam_pos[tri_oa[mid]], rb, vis_off, RB) / SC < want) lo = mid + 1; else hi = mid;
+                }
+                return lo;
+            };
+            be = lower(j); en = lower(j + 1);
+        }
+        runs[seg_slot_base[s] + slot] = make_int2((int)be, (int)en);
+    }
+}
+
 // ---- helpers ---------------------------------------------------------------------------------------
 template <class T> static T *salloc(psba_ctx *c, size_t n)
 {
@@ -197,6 +302,90 @@ static void sorted_triples(psba_ctx *c, int np, int p0, int o0, const int *gptr,
     psba_dev_free(c, tmp); psba_dev_free(c, k0);
     if (v0) psba_dev_free(c, v0);
     *keys_out = k1; *vals_out = v1; *ntri_out = ntri;
+}
+
+
+// tables of the row-sweep pair pass; falls back (rows_ok = false) when a prefix or a row exceeds the kernel's caps
+static void build_row_sweep(psba_ctx *c, const long long *tptr, const std::vector<int> &cptr, const std::vector<int> &pk)
+{
+    cudaStream_t st = c->stream;
+    const int m = c->m, o = c->o;
+    c->rows_ok = false; c->n_rchunk = c->n_rseg = c->n_rpart = 0;
+    if (c->pair_mode != 2) return;
+    // pairs of a row are contiguous (sorted by k, then l; the diagonal is the last one)
+    std::vector<int> row_pair0((size_t)m + 1, 0);
+    {
+        size_t q = 0;
+        for (int k = 0; k <= m; ++k) { while (q < pk.size() && pk[q] < k) ++q; row_pair0[k] = (int)q; }
+    }
+    int max_off = 0;
+    for (int k = 0; k < m; ++k) max_off = std::max(max_off, row_pair0[k + 1] - row_pair0[k] - 1);
+    if (max_off > 384 || o == 0) return;
+    int RB = 304;
+    if (getenv("PSBA_ROW_BUDGET") && atoi(getenv("PSBA_ROW_BUDGET")) == 640) RB = 640;
+    c->row_budget = RB;
+    int *len = salloc<int>(c, (size_t)o + 1), *cam_pos = salloc<int>(c, o), *vis_off = salloc<int>(c, (size_t)o + 1);
+    int *maxlen = salloc<int>(c, 1), *cam_ptr = supload(c, cptr);
+    CUDA_CHECK(cudaMemsetAsync(maxlen, 0, sizeof(int), st));
+    CUDA_CHECK(cudaMemsetAsync(len + o, 0, sizeof(int), st));
+    k_visit_len<<<cdiv(o, 256), 256, 0, st>>>(o, c->cam_obs, c->iidx, c->pt_ptr, len, cam_pos, maxlen);
+    {
+        size_t tb = 0;
+        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tb, len, vis_off, o + 1, st));
+        void *tmp = psba_dev_alloc(c, std::max<size_t>(tb, 16), false);
+        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tb, len, vis_off, o + 1, st));
+        psba_dev_free(c, tmp);
+    }
+    int *nch = salloc<int>(c, m);
+    k_row_chunks<<<cdiv(m, 256), 256, 0, st>>>(RB, m, cam_ptr, vis_off, nch);
+    std::vector<int> hnch(m);
+    int hmax = 0;
+    CUDA_CHECK(cudaMemcpyAsync(hnch.data(), nch, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(&hmax, maxlen, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    psba_dev_free(c, nch); psba_dev_free(c, maxlen); psba_dev_free(c, len);
+    if (hmax > ROW_MAXLEN) { psba_dev_free(c, cam_pos); psba_dev_free(c, vis_off); psba_dev_free(c, cam_ptr); return; }
+    std::vector<int> chunk_base((size_t)m + 1, 0);
+    for (int k = 0; k < m; ++k) chunk_base[k + 1] = chunk_base[k] + hnch[k];
+    c->n_rchunk = chunk_base[m];
+    // segments (one CTA each): SC consecutive chunks of one row
+    int SC = std::max(1, cdiv(c->n_rchunk, 8 * c->n_sm));
+    if (getenv("PSBA_ROW_SEG")) SC = std::max(1, atoi(getenv("PSBA_ROW_SEG")));
+    SC = std::min(SC, 1 << 14);
+    std::vector<int> seg_row, seg_slot_base, row_seg_ptr((size_t)m + 1, 0);
+    std::vector<int2> seg_chunks;
+    int nslot_total = 0;
+    for (int k = 0; k < m; ++k) {
+        for (int b = 0; b < hnch[k]; b += SC) {
+            seg_row.push_back(k);
+            seg_chunks.push_back(make_int2(chunk_base[k] + b, chunk_base[k] + std::min(b + SC, hnch[k])));
+            seg_slot_base.push_back(nslot_total);
+            nslot_total += row_pair0[k + 1] - row_pair0[k];
+        }
+        row_seg_ptr[k + 1] = (int)seg_row.size();
+    }
+    c->n_rseg = (int)seg_row.size(); c->n_rpart = nslot_total;
+    c->rows_nt = max_off <= 168 ? 256 : 544;       // (NT - 32) / 4 groups of four lanes, three pairs per group
+    int *row_chunk_base = supload(c, chunk_base);
+    c->rchunk_first = salloc<int>(c, (size_t)c->n_rchunk + 1);
+    k_chunk_first<<<cdiv(o, 256), 256, 0, st>>>(RB, o, c->cam_obs, c->jidx, cam_ptr, vis_off, row_chunk_base, c->n_rchunk, c->rchunk_first);
+    c->vis_desc = salloc<int4>(c, o);
+    k_vis_desc<<<cdiv(o, 256), 256, 0, st>>>(RB, o, c->cam_obs, c->iidx, c->jidx, c->pt_ptr, cam_ptr, vis_off, row_chunk_base, c->rchunk_first, c->vis_desc);
+    c->rchunk_desc = salloc<int4>(c, (size_t)c->n_rchunk + 4);
+    CUDA_CHECK(cudaMemsetAsync(c->rchunk_desc, 0, ((size_t)c->n_rchunk + 4) * sizeof(int4), st));
+    if (c->n_rchunk) k_chunk_desc<<<cdiv(c->n_rchunk, 256), 256, 0, st>>>(c->n_rchunk, c->rchunk_first, c->vis_desc, c->rchunk_desc);
+    c->tri_meta = salloc<unsigned>(c, (size_t)c->ntri + 4);
+    if (c->ntri) k_tri_meta<<<cdiv(c->ntri, 256), 256, 0, st>>>(RB, c->ntri, SC, c->tri_oa, c->tri_ob, cam_pos, c->jidx, cam_ptr, vis_off, row_chunk_base,
+                                                              c->rchunk_first, c->vis_desc, c->tri_meta);
+    c->rseg_row = supload(c, seg_row); c->rseg_chunks = supload(c, seg_chunks); c->rseg_slot_base = supload(c, seg_slot_base);
+    c->row_pair0 = supload(c, row_pair0); c->row_seg_ptr = supload(c, row_seg_ptr);
+    c->rseg_runs = salloc<int2>(c, (size_t)nslot_total);
+    CUDA_CHECK(cudaMemsetAsync(c->rseg_runs, 0, std::max<size_t>(nslot_total, 1) * sizeof(int2), st));
+    if (c->n_rseg) k_seg_runs<<<c->n_rseg, 128, 0, st>>>(RB, SC, c->rseg_row, c->rseg_slot_base, c->row_seg_ptr, c->row_pair0, tptr, c->tri_oa, cam_pos,
+                                                        cam_ptr, vis_off, c->rseg_runs);
+    CUDA_CHECK(cudaStreamSynchronize(st));          // the host vectors above are read by the async uploads
+    psba_dev_free(c, cam_pos); psba_dev_free(c, vis_off); psba_dev_free(c, cam_ptr); psba_dev_free(c, row_chunk_base);
+    c->rows_ok = true;
 }
 
 // ---- the build ---------------------------------------------------------------------------------------
@@ -350,13 +539,26 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
     // lane-group size of the pair pass: every group of G lanes owns one chunk of <= G*PAIR_TPL triples of
     // one camera pair; G follows the mean run length so that a lane streams ~PAIR_TPL triples before the
     // (shuffle) reduction -- 4..8 for the synthetic ring (117 triples / pair), 32 for BAL (~10^3 / pair)
+    // pair_mode 0 (default): a lane per triple; 1: the lanes of a group work as quads (four lanes per triple, a 3x3
+    // quadrant of the block each), a chunk is <= (G/4)*PAIR_TPQ triples; 2: row sweep.  PSBA_PAIR_MODE selects
+    // the two measured-and-slower variants
+    c->pair_mode = 0;
+    if (getenv("PSBA_PAIR_MODE")) c->pair_mode = atoi(getenv("PSBA_PAIR_MODE"));
+    long long PCH;
     {
         const double avg = h_nonempty ? (double)c->ntri / (double)h_nonempty : 1.0;
-        int G = 1;
-        while (G < 32 && avg > (double)G * PAIR_TPL) G *= 2;
-        c->pair_G = G;
+        if (c->pair_mode == 1) {
+            int G = 4;
+            while (G < 32 && avg > (double)(G / 4) * PAIR_TPQ) G *= 2;
+            c->pair_G = G;
+            PCH = (long long)(G / 4) * PAIR_TPQ;
+        } else {
+            int G = 1;
+            while (G < 32 && avg > (double)G * PAIR_TPL) G *= 2;
+            c->pair_G = G;
+            PCH = (long long)G * PAIR_TPL;
+        }
     }
-    const long long PCH = (long long)c->pair_G * PAIR_TPL;
     k_chunk_count<<<cdiv(c->n_pair, 256), 256, 0, st>>>(c->n_pair, PCH, tptr, ccnt, nullptr);
     c->pair_chunk_ptr = salloc<int>(c, (size_t)c->n_pair + 1);
     {
@@ -371,8 +573,10 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
     c->pchunk_pair = salloc<int>(c, c->n_pchunk);
     c->pchunk_beg = salloc<long long>(c, c->n_pchunk); c->pchunk_end = salloc<long long>(c, c->n_pchunk);
     k_chunk_fill<<<cdiv(c->n_pair, 256), 256, 0, st>>>(c->n_pair, PCH, tptr, c->pair_chunk_ptr, c->pchunk_pair, c->pchunk_beg, c->pchunk_end);
-    psba_dev_free(c, tptr); psba_dev_free(c, ccnt); psba_dev_free(c, nonempty); psba_dev_free(c, lkeys);
     T.lap("pair set + chunks");
+    build_row_sweep(c, tptr, cptr, pk);
+    T.lap("row-sweep tables");
+    psba_dev_free(c, tptr); psba_dev_free(c, ccnt); psba_dev_free(c, nonempty); psba_dev_free(c, lkeys);
     // ---- camera system tiles (symbolic factorisation, host)
     psba_build_tile_structure(c, pairs);
     T.lap("tile structure");
