@@ -24,6 +24,9 @@ import time
 
 import numpy as np
 
+# NCCL prints its version banner on stdout when NCCL_DEBUG asks for it: rank 0 must print ONE JSON line
+os.environ["NCCL_DEBUG"] = os.environ.get("PSBA_NCCL_DEBUG", "WARN")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 

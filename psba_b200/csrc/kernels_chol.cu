@@ -154,6 +154,7 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
     for (int I = 0; I < nt; ++I) present[(size_t)I * nt + I] = 1;
     for (int a = 0; a < nt; ++a)
         for (int b : adj[a]) { const int I = std::max(tpos[a], tpos[b]), J = std::min(tpos[a], tpos[b]); present[(size_t)I * nt + J] = 1; }
+    const std::vector<char> presentS = present;      // tiles of S itself (before fill-in)
     std::vector<std::vector<int>> rows(nt);          // rows[K]: tile rows I > K of the factor column K
     for (int K = 0; K < nt; ++K) {
         for (int I = K + 1; I < nt; ++I) if (present[(size_t)I * nt + K]) rows[K].push_back(I);
@@ -161,10 +162,14 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
             for (size_t b = 0; b <= a; ++b) present[(size_t)rows[K][a] * nt + rows[K][b]] = 1;
     }
     c->h_tile_index.assign((size_t)nt * nt, -1);
+    // slots: the tiles of S first (the only ones the multi-GPU all-reduce has to move), then the fill-in
     int slot = 0;
-    for (int I = 0; I < nt; ++I)
-        for (int J = 0; J <= I; ++J)
-            if (present[(size_t)I * nt + J]) c->h_tile_index[(size_t)I * nt + J] = slot++;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int I = 0; I < nt; ++I)
+            for (int J = 0; J <= I; ++J)
+                if (present[(size_t)I * nt + J] && (presentS[(size_t)I * nt + J] != 0) == (pass == 0)) c->h_tile_index[(size_t)I * nt + J] = slot++;
+        if (pass == 0) c->n_tiles_S = slot;
+    }
     c->n_tiles = slot;
     // ---- steps: a panel runs one step after the last panel it depends on
     std::vector<int> step(nt, 0);

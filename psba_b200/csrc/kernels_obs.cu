@@ -291,15 +291,28 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
 {
     const int set = c->cur;
     if (!c->cache_valid[set]) psba_launch_cam_prep(c, set);
+    // the camera pass (FP64-bound) and the point pass (memory-bound) are independent: outside profile mode the
+    // camera pass runs on a second stream under the point pass
+    const bool fork = !c->profile && c->n_cchunk > 0 && c->n_ptchunk > 0;
+    cudaStream_t cs = c->stream;
+    if (fork) {
+        CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+        cs = c->stream2;
+    }
+    if (c->n_cchunk > 0)
+        PROF(c, KID_LIN_CAMS) k_lin_cams<<<c->n_cchunk, CAM_CTA, 0, cs>>>(c->cchunk_cam, c->cchunk_beg, c->cchunk_end, c->cam_pt,
+                                                          c->cam_impts, c->camcache[set], c->pts[set], c->cam_part);
+    PROF(c, KID_CAM_REDUCE) k_cam_reduce<<<cdiv(c->m * 27, 128), 128, 0, cs>>>(c->m, c->cam_cchunk_ptr, c->cam_part, coeff_uvw, coeff_g,
+                                                             c->U, c->g);
     if (c->n_ptchunk > 0)
         PROF(c, KID_LIN_POINTS) k_lin_points<<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts,
                                                             c->camcache[set], c->pts[set], coeff_uvw, coeff_g,
                                                             c->W, c->V, c->g + c->N);
-    if (c->n_cchunk > 0)
-        PROF(c, KID_LIN_CAMS) k_lin_cams<<<c->n_cchunk, CAM_CTA, 0, c->stream>>>(c->cchunk_cam, c->cchunk_beg, c->cchunk_end, c->cam_pt,
-                                                          c->cam_impts, c->camcache[set], c->pts[set], c->cam_part);
-    PROF(c, KID_CAM_REDUCE) k_cam_reduce<<<cdiv(c->m * 27, 128), 128, 0, c->stream>>>(c->m, c->cam_cchunk_ptr, c->cam_part, coeff_uvw, coeff_g,
-                                                             c->U, c->g);
+    if (fork) {
+        CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
+        CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    }
     c->st_launches += 3; c->st_lin += 1;
     if (c->nranks > 1) {
         psba_allreduce_sum(c, c->U, (size_t)c->m * 36);

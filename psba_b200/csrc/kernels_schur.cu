@@ -618,7 +618,7 @@ void psba_launch_schur(psba_ctx *c, double mu)
     c->st_launches += 3;
     if (!single) {
         // the tile pool and ea are contiguous-by-construction only separately: two all-reduces
-        psba_allreduce_sum(c, c->Stiles, (size_t)c->n_tiles * TS * TS);
+        psba_allreduce_sum(c, c->Stiles, (size_t)c->n_tiles_S * TS * TS);     // fill-in tiles are zero on every rank
         psba_allreduce_sum(c, c->eab, (size_t)c->N);
         k_add_U<<<cdiv(c->m * 42, 128), 128, 0, c->stream>>>(c->m, c->U, c->g, mu, c->tile_index, c->cam2pos, c->nt, c->Stiles, c->eab);
         c->st_launches += 1;

@@ -66,6 +66,9 @@ extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3D
     c->rank = psba_comm_active() ? psba_comm_rank() : 0;
     c->nranks = psba_comm_active() ? psba_comm_size() : 1;
     CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     c->cur = 0; c->cache_valid[0] = c->cache_valid[1] = false;
     c->lin_valid = false; c->S_valid = false; c->factor_valid = false; c->chol_graph_ok = false; c->bw_graph_ok = false;
     c->Sdense = c->Sdense_aux = nullptr; c->tmpA = c->tmpB = nullptr;
@@ -196,6 +199,8 @@ extern "C" void psba_release_buffer(psba_ctx *c)
     if (c->chol_graph_ok) cudaGraphExecDestroy(c->chol_graph);
     if (c->bw_graph_ok) cudaGraphExecDestroy(c->bw_graph);
     cudaFreeHost(c->h_scal); cudaFreeHost(c->h_status);
+    cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
+    cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -492,6 +497,7 @@ extern "C" double psba_get_stat(psba_ctx *c, const char *name)
     if (s == "ntriples") return (double)c->ntri;
     if (s == "n_pairs") return c->n_pair;
     if (s == "n_tiles") return c->n_tiles;
+    if (s == "n_tiles_S") return c->n_tiles_S;
     if (s == "nt") return c->nt;
     if (s == "n_steps") return c->n_steps;
     if (s == "n_ptchunk") return c->n_ptchunk;

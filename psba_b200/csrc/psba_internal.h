@@ -52,6 +52,7 @@ struct psba_ctx {
     int n, o, p_off, o_off;
     int rank, nranks;
     cudaStream_t stream;
+    cudaStream_t stream2; cudaEvent_t ev_fork, ev_join;   // side stream of the linearisation (camera pass under the point pass)
 
     // ---- parameters
     double *K, *initcams, *impts;
@@ -97,6 +98,7 @@ struct psba_ctx {
     // ---- camera system
     int nt;                         // tiles per dimension
     int n_tiles; int *tile_index;   // nt*nt -> slot or -1 (device + host copy)
+    int n_tiles_S;                  // the first n_tiles_S slots are the tiles of S itself, the rest is fill-in of the factor
     std::vector<int> h_tile_index;
     double *Stiles;                 // n_tiles * TS*TS  (factor overwrites it)
     double *Linv;                   // nt * TS*TS   inverse of the diagonal factor tiles
