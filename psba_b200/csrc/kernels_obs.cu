@@ -12,6 +12,7 @@
 // coalesced 16-byte-per-lane transfers staged through shared memory: a warp moves 512 contiguous
 // bytes per instruction instead of 32 scattered sectors (ncu r01: 23 sectors/request before).
 #include "dev_math.cuh"
+#include <algorithm>
 
 #define CAM_LD 26          // doubles per staged camera entry in shared memory (24 + pad: conflict-free LDS.128)
 
@@ -133,7 +134,7 @@ double psba_launch_cost(psba_ctx *c, int set, double *ex_dev)
 //      ascending camera order (the order of compute_V.cl:24-31 / compute_g.cl:43-54);
 //   3. the W tile (128 x 144 B, contiguous in HBM because observations are point-major) is written
 //      with fully coalesced 16-byte stores.
-__global__ void __launch_bounds__(PT_CTA, 4) k_lin_points(const int4 *__restrict__ ptdesc, const int *__restrict__ pt_ptr,
+__global__ void __launch_bounds__(PT_CTA, 4) k_lin_points(const int *__restrict__ chunk_list, const int4 *__restrict__ ptdesc, const int *__restrict__ pt_ptr,
                                                          const int *__restrict__ iidx, const int *__restrict__ jidx,
                                                          const double *__restrict__ impts, const double *__restrict__ cache,
                                                          const double *__restrict__ pts, double coeff, double coeff_g,
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_lin_points(const int4 *__restrict
     const int tid = threadIdx.x;
     // one 16-byte descriptor per chunk {p0, p1, o0, o1}; every independent load of a wave is issued before
     // anything waits (a CTA is a chain of dependent L2 / HBM round trips: the fewer links, the better)
-    const int4 ds = __ldg(ptdesc + blockIdx.x);
+    const int4 ds = __ldg(ptdesc + (chunk_list ? chunk_list[blockIdx.x] : blockIdx.x));
     const int p0 = ds.x, p1 = ds.y, o0 = ds.z, o1 = ds.w;
     const int np = p1 - p0;
     double acc[9];
@@ -231,6 +232,129 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_lin_points(const int4 *__restrict
     }
 }
 
+
+// PERSISTENT, software-pipelined variant for the chunks that fit one wave (all of them unless a point has more
+// than PT_CTA observations).  Nothing a chunk needs is waited for in the iteration that asks for it:
+//   three chunks ahead  the 16-byte chunk descriptor,
+//   two chunks ahead    indices, measurements, point ranges (registers),
+//   one chunk ahead     camera entries (12 x 16 B per observation) and the chunk's points as asynchronous copies
+//                       (LDGSTS) into the other half of a double-buffered stage,
+// and the W tile (contiguous in HBM: observations are point-major) leaves with ONE bulk store (TMA) out of the
+// stage half its camera entries came in, instead of a copy-out loop through the load/store unit.
+template <int DUMMY>
+__global__ void __launch_bounds__(PT_CTA, 3) k_lin_points_pipe(int n_list, const int *__restrict__ chunk_list, const int4 *__restrict__ ptdesc,
+                                                              const int *__restrict__ pt_ptr, const int *__restrict__ iidx,
+                                                              const int *__restrict__ jidx, const double *__restrict__ impts,
+                                                              const double *__restrict__ cache, const double *__restrict__ pts,
+                                                              double coeff, double coeff_g, double *__restrict__ W,
+                                                              double *__restrict__ V, double *__restrict__ gb)
+{
+    extern __shared__ __align__(128) double stage_dyn[];       // 2 x PT_CTA*CAM_LD: camera entries, then the W tile
+    __shared__ double sh[9][PT_CTA];
+    __shared__ double px[2][3][PT_CTA];
+    __shared__ int sj[2][PT_CTA];
+    const int tid = threadIdx.x, G = gridDim.x;
+    struct idx { int j, lp, a, b; double2 mm; };
+    auto chunk_of = [&](int q) { return chunk_list ? __ldg(chunk_list + q) : q; };
+    const int4 zero4 = make_int4(0, 0, 0, 0);
+    auto load_idx = [&](const int4 &d, idx &r) {
+        const int k = d.z + tid;
+        r.j = 0; r.lp = 0; r.a = 0; r.b = 0; r.mm = make_double2(0.0, 0.0);
+        if (k < d.w) { r.j = __ldg(jidx + k); r.lp = __ldg(iidx + k) - d.x; r.mm = __ldg(reinterpret_cast<const double2 *>(impts) + k); }
+        if (tid < d.y - d.x) { r.a = __ldg(pt_ptr + d.x + tid); r.b = __ldg(pt_ptr + d.x + tid + 1); }
+    };
+    auto issue = [&](const int4 &d, int buf) {               // camera entries (sj[buf] is visible) and points of a chunk
+        const int cnt = d.w - d.z, np = d.y - d.x;
+        double *st = stage_dyn + buf * PT_CTA * CAM_LD;
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            const int p = tid + q * PT_CTA, ob = p / 12, part = p - ob * 12;
+            if (p < cnt * 12) cp_async16(st + ob * CAM_LD + part * 2, cache + (size_t)sj[buf][ob] * CAMC + part * 2);
+        }
+        if (tid < np) {
+            const double *X = pts + (size_t)(d.x + tid) * 3;
+            cp_async8(&px[buf][0][tid], X); cp_async8(&px[buf][1][tid], X + 1); cp_async8(&px[buf][2][tid], X + 2);
+        }
+    };
+    int q = blockIdx.x;
+    if (q >= n_list) return;
+    int4 ds = __ldg(ptdesc + chunk_of(q));
+    int4 ds1 = q + G < n_list ? __ldg(ptdesc + chunk_of(q + G)) : zero4;
+    int4 ds2 = q + 2 * G < n_list ? __ldg(ptdesc + chunk_of(q + 2 * G)) : zero4;
+    idx cur, mid, far;
+    load_idx(ds, cur);
+    load_idx(ds1, mid);
+    sj[0][tid] = cur.j;
+    __syncthreads();
+    issue(ds, 0);
+    cp_async_commit();
+    for (int it = 0; q < n_list; q += G, ++it) {
+        const int buf = it & 1;
+        // 1. the store of the previous chunk has read its tile: that stage half takes the next chunk's entries
+        if (tid == 0) bulk_wait_read0();
+        sj[buf ^ 1][tid] = mid.j;
+        __syncthreads();
+        if (q + G < n_list) issue(ds1, buf ^ 1);
+        cp_async_commit();
+        // 2. two chunks ahead: indices; three ahead: the descriptor
+        load_idx(ds2, far);
+        const int4 ds3 = q + 3 * G < n_list ? __ldg(ptdesc + chunk_of(q + 3 * G)) : zero4;
+        cp_async_wait<1>();
+        __syncthreads();                                     // entries and points of this chunk have landed
+        const int p0 = ds.x, o0 = ds.z, o1 = ds.w, np = ds.y - ds.x, cnt = o1 - o0;
+        const int k = o0 + tid;
+        double *st = stage_dyn + buf * PT_CTA * CAM_LD;
+        CamReg cam;
+        load_cam<false>(st + tid * CAM_LD, cam);
+        const double X0 = px[buf][0][cur.lp], X1 = px[buf][1][cur.lp], X2 = px[buf][2][cur.lp];
+        __syncthreads();                                     // every thread holds its entry: the half is free for the W tile
+        if (k < o1) {
+            double e0, e1, A[12], B[6];
+            residual_jac(cam, X0, X1, X2, cur.mm.x, cur.mm.y, e0, e1, A, B);
+            double2 *ws = reinterpret_cast<double2 *>(st + tid * 18);
+#pragma unroll
+            for (int r = 0; r < 6; r += 2) {
+                double w[6];
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) w[h * 3 + cc] = coeff * (A[r + h] * B[cc] + A[6 + r + h] * B[3 + cc]);
+                ws[r / 2 * 3] = make_double2(w[0], w[1]); ws[r / 2 * 3 + 1] = make_double2(w[2], w[3]); ws[r / 2 * 3 + 2] = make_double2(w[4], w[5]);
+            }
+            sh[0][tid] = B[0] * B[0] + B[3] * B[3];
+            sh[1][tid] = B[0] * B[1] + B[3] * B[4];
+            sh[2][tid] = B[0] * B[2] + B[3] * B[5];
+            sh[3][tid] = B[1] * B[1] + B[4] * B[4];
+            sh[4][tid] = B[1] * B[2] + B[4] * B[5];
+            sh[5][tid] = B[2] * B[2] + B[5] * B[5];
+            sh[6][tid] = B[0] * e0 + B[3] * e1;
+            sh[7][tid] = B[1] * e0 + B[4] * e1;
+            sh[8][tid] = B[2] * e0 + B[5] * e1;
+        }
+        fence_proxy_async();                                 // the tile was written through the generic proxy
+        __syncthreads();
+        if (tid == 0) { bulk_s2g(W + (size_t)o0 * 18, st, (unsigned)cnt * 144u); bulk_commit(); }
+        if (tid < np) {                                      // owner: ascending camera order (compute_V.cl:24-31 / compute_g.cl:43-54)
+            double acc[9];
+#pragma unroll
+            for (int v = 0; v < 9; ++v) acc[v] = 0.0;
+            for (int u = cur.a; u < cur.b; ++u) {
+#pragma unroll
+                for (int v = 0; v < 9; ++v) acc[v] += sh[v][u - o0];
+            }
+            double *Vp = V + (size_t)(p0 + tid) * 6;
+#pragma unroll
+            for (int v = 0; v < 6; ++v) Vp[v] = coeff * acc[v];
+            double *gp = gb + (size_t)(p0 + tid) * 3;
+            gp[0] = coeff_g * acc[6]; gp[1] = coeff_g * acc[7]; gp[2] = coeff_g * acc[8];
+        }
+        cur = mid; mid = far;
+        ds = ds1; ds1 = ds2; ds2 = ds3;
+    }
+    cp_async_wait<0>();
+    if (tid == 0) bulk_wait0();
+}
+
 // camera-major pass: chunk = up to CAM_CTA*CAM_OPT observations of ONE camera (ascending point).
 // The camera cache entry is uniform per CTA; points and measurements are gathered (L2-resident).
 // Each thread accumulates A^T A (21 upper entries) and A^T e (6) over its observations, then one
@@ -306,9 +430,24 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
     PROF(c, KID_CAM_REDUCE) k_cam_reduce<<<cdiv(c->m * 27, 128), 128, 0, cs>>>(c->m, c->cam_cchunk_ptr, c->cam_part, coeff_uvw, coeff_g,
                                                              c->U, c->g);
     if (c->n_ptchunk > 0)
-        PROF(c, KID_LIN_POINTS) k_lin_points<<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts,
-                                                            c->camcache[set], c->pts[set], coeff_uvw, coeff_g,
-                                                            c->W, c->V, c->g + c->N);
+        PROF(c, KID_LIN_POINTS) {
+            static bool attr_set = false;
+            const int dyn = 2 * PT_CTA * CAM_LD * (int)sizeof(double);
+            if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_lin_points_pipe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)); attr_set = true; }
+            static const bool pipe = !(getenv("PSBA_LIN_PIPE") && atoi(getenv("PSBA_LIN_PIPE")) == 0);
+            if (!pipe)
+                k_lin_points<<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(nullptr, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set],
+                                                                    coeff_uvw, coeff_g, c->W, c->V, c->g + c->N);
+            else {
+                if (c->n_small > 0)
+                    k_lin_points_pipe<0><<<std::min(c->n_small, c->n_sm * 3), PT_CTA, dyn, c->stream>>>(c->n_small, c->d_small_list, c->ptdesc, c->pt_ptr, c->iidx, c->jidx,
+                                                                                                     c->impts, c->camcache[set], c->pts[set], coeff_uvw, coeff_g,
+                                                                                                     c->W, c->V, c->g + c->N);
+                if (c->n_big > 0)      // points with more observations than one wave
+                    k_lin_points<<<c->n_big, PT_CTA, 0, c->stream>>>(c->d_big_list, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set],
+                                                                    coeff_uvw, coeff_g, c->W, c->V, c->g + c->N);
+            }
+        }
     if (fork) {
         CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
         CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
