@@ -726,11 +726,12 @@ __global__ void k_init_rhs(int npad, const int *__restrict__ pos2cam, const doub
     b[k] = cam >= 0 ? ea[cam * 6 + k % 6] : 0.0;
 }
 
-static void enqueue_factor(psba_ctx *c)
+static void enqueue_factor(psba_ctx *c, std::vector<cudaEvent_t> *ev = nullptr)
 {
     const int npad = c->nt * TS;
     k_init_rhs<<<cdiv(npad, 256), 256, 0, c->stream>>>(npad, c->pos2cam, c->eab, c->chol_aux);
     for (int s = 0; s < c->n_steps; ++s) {
+        if (ev) CUDA_CHECK(cudaEventRecord((*ev)[s], c->stream));
         const int cb = c->step_crit_ptr[s], ncrit = c->step_crit_ptr[s + 1] - cb;
         const int db = c->step_def_ptr[s], ndef = c->step_def_ptr[s + 1] - db;
         const int bb = c->step_b_ptr[s], nb = c->step_b_ptr[s + 1] - bb;
@@ -745,6 +746,7 @@ static void enqueue_factor(psba_ctx *c)
                                       (const int *)(c->d_b_sptr + bb), (const int *)c->d_b_slot, c->Stiles, c->Ldiag, c->chol_aux,
                                       c->chol_diag, c->contrib, c->d_status));
     }
+    if (ev) CUDA_CHECK(cudaEventRecord((*ev)[c->n_steps], c->stream));
     k_diag_inverse<<<c->nt, 256, 2 * TILE_SM * sizeof(double), c->stream>>>(c->Ldiag, c->Linv, c->d_status);
 }
 
@@ -771,6 +773,21 @@ double psba_launch_factor(psba_ctx *c, bool defer_status)
         CUDA_CHECK(cudaMemset(dbg_dev, 0, (size_t)c->nt * 8 * sizeof(long long)));
         CUDA_CHECK(cudaMemcpyToSymbol(g_panel_dbg, &dbg_dev, sizeof(dbg_dev)));
     }
+    static int step_timing = getenv("PSBA_STEP_TIMING") ? 3 : 0;      // third factorisation: per-step device times, no graph
+    if (step_timing > 0 && --step_timing == 0) {
+        std::vector<cudaEvent_t> ev(c->n_steps + 1);
+        for (auto &e : ev) CUDA_CHECK(cudaEventCreate(&e));
+        const bool pdl = c->chol_pdl; c->chol_pdl = false;
+        enqueue_factor(c, &ev);
+        c->chol_pdl = pdl;
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        for (int s = 0; s < c->n_steps; ++s) {
+            float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, ev[s], ev[s + 1]));
+            fprintf(stderr, "step %3d: %7.1f us  crit %5d  deferred %5d  rhs %4d\n", s, ms * 1e3, c->step_crit_ptr[s + 1] - c->step_crit_ptr[s],
+                    c->step_def_ptr[s + 1] - c->step_def_ptr[s], c->step_b_ptr[s + 1] - c->step_b_ptr[s]);
+        }
+        for (auto &e : ev) cudaEventDestroy(e);
+    } else
     PROF(c, KID_FACTOR) CUDA_CHECK(cudaGraphLaunch(c->chol_graph, c->stream));
     if (dbg_dev) {
         std::vector<long long> h((size_t)c->nt * 8);

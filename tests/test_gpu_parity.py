@@ -305,3 +305,89 @@ def test_device_built_index_structure_is_bit_exact(key):
         assert np.array_equal(pt[b:e], pts_kl)
         assert np.array_equal(oa[b:e], blk[pts_kl, k]) and np.array_equal(ob[b:e], blk[pts_kl, l])
     G.close(); O.close()
+
+
+def _mixed_track_problem():
+    """160 ring cameras; 300 points seen by 150 cameras each (more observations than one 128-wide wave: the
+    'oversize chunk' path of the point-major kernels) followed by 2000 ordinary points with 4 observations."""
+    from psba_b200 import synth
+    a = synth.ring_problem(m=160, n=300, d=150, w=160, seed=11)
+    b = synth.ring_problem(m=160, n=2000, d=4, w=12, seed=12)
+    prob = dict(a)
+    prob["n"] = a["n"] + b["n"]; prob["o"] = a["o"] + b["o"]
+    prob["pts"] = np.concatenate([a["pts"], b["pts"]]); prob["impts"] = np.concatenate([a["impts"], b["impts"]])
+    prob["iidx"] = np.concatenate([a["iidx"], b["iidx"] + a["n"]]).astype(np.int32)
+    prob["jidx"] = np.concatenate([a["jidx"], b["jidx"]]).astype(np.int32)
+    prob["name"] = "ring-160-mixed-tracks"
+    return prob
+
+
+def _check_try_against_oracle(prob, G):
+    """one linearisation + one damped solve + LM trajectory against the oracle"""
+    O = oracle.Problem(prob)
+    O.set("nthreads", 8)
+    O.call("exQT"); O.call("jacobiQT"); O.call("U", 1); O.call("V", 1); O.call("Wblks", 1); O.call("g", 1)
+    G.compute_jacobiQT()
+    assert relerr(G.compute_U(1.0), O.buf("U")) < 1e-11
+    assert relerr(G.compute_V(1.0), O.buf("V")) < 1e-11
+    assert relerr(G.compute_Wblks(1.0), O.buf("W")) < 1e-11
+    assert relerr(G.compute_g(1.0), O.buf("g")) < 1e-11
+    mu = 1e-3 * float(np.max(O.buf("UVdiag")))
+    O.call("update_UV", mu); O.call("Vinv"); O.call("Yblks"); O.call("S"); O.call("ea")
+    So, eao = O.buf("S").copy(), O.buf("eab")[:O.N].copy()
+    G.update_UV(mu)
+    ret, Vmix = G.compute_Vinv()
+    assert ret == 0.0 and relerr(Vmix, O.buf("V")) < 1e-10
+    assert relerr(np.tril(G.compute_S()), np.tril(So)) < 1e-10
+    assert relerr(G.compute_ea(), eao) < 1e-10
+    assert G.SPDinv() == 0.0 and O.call("SPDinv") == 0.0
+    G.matVec_mul(); O.call("matVec")
+    O.call("eb"); O.call("dpb"); O.call("newp")
+    assert relerr(G.compute_eb()[O.N:], O.buf("eab")[O.N:]) < 1e-7
+    assert relerr(G.compute_dpb(), O.buf("dp")) < 1e-7
+    G.compute_newp()
+    cn_o, cn_g = O.call("exQT_new"), G.compute_exQT(psba_b200.PARAMS_NEW)
+    assert abs(cn_g - cn_o) / cn_o < 1e-9
+    G.restore_UVdiag()
+    return O
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_pair_pass_variants_agree_with_oracle(mode, monkeypatch):
+    """PSBA_PAIR_MODE selects the pair pass: lane per triple (default), quad per triple, row sweep.  All three must
+    give the reference's S and ea (compute_S.cl / compute_ea.cl) and the same LM trajectory."""
+    from psba_b200 import synth
+    monkeypatch.setenv("PSBA_PAIR_MODE", mode)
+    for prob in (synth.ring_problem(m=160, n=6000, d=4, w=12, seed=7), psba_b200.read_sba(*dataset_paths("54"))):
+        G = psba_b200.PSBA(prob)
+        if mode == "2":
+            assert int(G.stat("rows_ok")) == 1 and int(G.stat("n_rseg")) > 0
+        O = _check_try_against_oracle(prob, G)
+        G.close()
+        G = psba_b200.PSBA(prob)
+        assert O.levmar() == G.levmar()[0]
+        to, tg = O.trace(), G.trace()
+        assert pattern(tg) == pattern(to)
+        for a, b in zip(to, tg):
+            assert abs(a["err"] - b["err"]) / a["err"] < 1e-9
+        G.close(); O.close()
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_points_with_more_observations_than_one_wave(mode, monkeypatch):
+    """Tracks of 150 observations (> 128, one CTA wave) next to ordinary ones: the pipelined point-major kernels
+    take the one-wave chunks, the wave-loop kernels the oversize ones; the row sweep (mode 2) must notice that a
+    prefix of 150 blocks exceeds its stage and fall back to the pair-major kernel."""
+    monkeypatch.setenv("PSBA_PAIR_MODE", mode)
+    prob = _mixed_track_problem()
+    G = psba_b200.PSBA(prob)
+    assert int(G.stat("rows_ok")) == 0
+    O = _check_try_against_oracle(prob, G)
+    G.close()
+    G = psba_b200.PSBA(prob)
+    assert O.levmar() == G.levmar()[0]
+    to, tg = O.trace(), G.trace()
+    assert pattern(tg) == pattern(to)
+    for a, b in zip(to, tg):
+        assert abs(a["err"] - b["err"]) / a["err"] < 1e-9
+    G.close(); O.close()
