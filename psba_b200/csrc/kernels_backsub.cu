@@ -208,12 +208,14 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ c
 
 
 // PERSISTENT, software-pipelined variant for the chunks that fit one wave (all of them unless a point has more
-// than PT_CTA observations).  A CTA is otherwise a chain of dependent L2 / HBM round trips -- descriptor, then
+// than PT_CTA observations).  A one-shot CTA is a chain of dependent L2 / HBM round trips -- descriptor, then
 // indices and per-point data, then the gathers that need a camera index -- and 3-4 resident CTAs per SM cannot
-// hide ~5 us of chain behind ~1 us of work.  Here the descriptor is fetched two chunks ahead, the W tile of the
-// next chunk arrives by ONE TMA bulk copy (cp.async.bulk -> mbarrier) into a double-buffered shared tile, and the
-// next chunk's indices, measurements and per-point data are prefetched into registers; the only exposed round
-// trip per chunk is the gather of dpa / candidate-camera entries (L2 hits).
+// hide ~5 us of chain behind ~1 us of work.  Here nothing is waited for in the iteration that asks for it:
+//   three chunks ahead  the 16-byte chunk descriptor,
+//   two chunks ahead    camera index, local point, measurement of every observation (registers),
+//   one chunk ahead     the W tile by ONE TMA bulk copy (cp.async.bulk -> mbarrier), the candidate-camera entries
+//                       (6 x 16 B per observation) by asynchronous copies (LDGSTS) into a double-buffered stage,
+//                       the dpa rows and the per-point data (gb, Vinv, point) in registers.
 template <int DUMMY>
 __global__ void __launch_bounds__(PT_CTA, 3) k_backsub_pipe(int n_list, const int *__restrict__ chunk_list, const int4 *__restrict__ ptdesc,
                                                            const int *__restrict__ pt_ptr, const int *__restrict__ iidx,
@@ -224,30 +226,43 @@ __global__ void __launch_bounds__(PT_CTA, 3) k_backsub_pipe(int n_list, const in
                                                            double *__restrict__ eb, double *__restrict__ dpb, double *__restrict__ newpts,
                                                            double *__restrict__ part)
 {
-    extern __shared__ __align__(128) double wtile_dyn[];       // two W tiles (TMA destinations)
-    __shared__ __align__(16) double pstage[PT_CTA * PROJ_LD];
+    extern __shared__ __align__(128) double dyn[];             // two W tiles (TMA destinations), then two entry stages
+    double *wtile = dyn, *pstage = dyn + 2 * PT_CTA * 18;
     __shared__ __align__(8) unsigned long long bar[2];
     __shared__ double sh[3][PT_CTA];
     __shared__ double shx[3][PT_CTA];
     __shared__ double red[4][PT_CTA / 32];
-    __shared__ int sj[PT_CTA];
+    __shared__ int sj[2][PT_CTA];
     const int tid = threadIdx.x, G = gridDim.x;
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
-    __syncthreads();
-    struct pre {                                               // what is prefetched per chunk, per thread
-        int j, lp; double2 mm;                                 // observation: camera, local point, measurement
-        int a, b; double g0, g1, g2, i00, i10, i20, i11, i21, i22, px, py, pz;   // owner of a point
-    };
+    struct idx { int j, lp; double2 mm; };                     // observation: camera, local point, measurement
+    struct own { int a, b; double g0, g1, g2, i00, i10, i20, i11, i21, i22, px, py, pz; };   // owner of a point
     auto chunk_of = [&](int q) { return chunk_list ? __ldg(chunk_list + q) : q; };
-    auto prefetch = [&](const int4 &d, int stage, pre &r) {
-        const int np = d.y - d.x, k = d.z + tid;
-        if (tid == 0) {
-            const unsigned bytes = (unsigned)(d.w - d.z) * 144u;
-            mbar_expect_tx(&bar[stage], bytes);
-            bulk_g2s(wtile_dyn + stage * PT_CTA * 18, W + (size_t)d.z * 18, bytes, &bar[stage]);
-        }
+    const int4 zero4 = make_int4(0, 0, 0, 0);
+    auto load_idx = [&](const int4 &d, idx &r) {
+        const int k = d.z + tid;
         r.j = 0; r.lp = 0; r.mm = make_double2(0.0, 0.0);
         if (k < d.w) { r.j = __ldg(jidx + k); r.lp = __ldg(iidx + k) - d.x; r.mm = __ldg(reinterpret_cast<const double2 *>(impts) + k); }
+    };
+    // everything of a chunk that needs only its descriptor and (in sj[buf]) its camera indices
+    auto issue = [&](const int4 &d, int buf, int myj, own &r, double (&dq)[6]) {
+        const int np = d.y - d.x, cnt = d.w - d.z;
+        if (tid == 0) {
+            const unsigned bytes = (unsigned)cnt * 144u;
+            mbar_expect_tx(&bar[buf], bytes);
+            bulk_g2s(wtile + buf * PT_CTA * 18, W + (size_t)d.z * 18, bytes, &bar[buf]);
+        }
+        double *ps = pstage + buf * PT_CTA * PROJ_LD;
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+            const int p = tid + u * PT_CTA, ob = p / 6, piece = p - ob * 6;
+            if (p < cnt * 6) cp_async16(ps + ob * PROJ_LD + piece * 2, newcache + (size_t)sj[buf][ob] * CAMC + piece * 2);
+        }
+        if (tid < cnt) {
+            const double2 *dp2 = reinterpret_cast<const double2 *>(dpa + myj * 6);
+#pragma unroll
+            for (int u = 0; u < 3; ++u) { const double2 d2 = __ldg(dp2 + u); dq[2 * u] = d2.x; dq[2 * u + 1] = d2.y; }
+        }
         if (tid < np) {
             const int p = d.x + tid;
             r.a = __ldg(pt_ptr + p); r.b = __ldg(pt_ptr + p + 1);
@@ -261,36 +276,36 @@ __global__ void __launch_bounds__(PT_CTA, 3) k_backsub_pipe(int n_list, const in
     int q = blockIdx.x;
     if (q >= n_list) return;
     int4 ds = __ldg(ptdesc + chunk_of(q));
-    int4 ds1 = q + G < n_list ? __ldg(ptdesc + chunk_of(q + G)) : make_int4(0, 0, 0, 0);
-    pre cur, nxt;
-    prefetch(ds, 0, nxt);
+    int4 ds1 = q + G < n_list ? __ldg(ptdesc + chunk_of(q + G)) : zero4;
+    int4 ds2 = q + 2 * G < n_list ? __ldg(ptdesc + chunk_of(q + 2 * G)) : zero4;
+    idx cur, mid, far;
+    own oc, on;
+    double d[6], dn[6];
+    load_idx(ds, cur);
+    load_idx(ds1, mid);
+    sj[0][tid] = cur.j;
+    __syncthreads();                                           // barriers initialised, sj[0] visible
+    issue(ds, 0, cur.j, on, dn);
+    cp_async_commit();
     for (int it = 0; q < n_list; q += G, ++it) {
         const int st = it & 1;
         const int cidx = chunk_of(q);
-        cur = nxt;
-        // two chunks ahead: descriptor only; one chunk ahead: data (its descriptor arrived an iteration ago)
-        const int4 ds2 = q + 2 * G < n_list ? __ldg(ptdesc + chunk_of(q + 2 * G)) : make_int4(0, 0, 0, 0);
-        if (q + G < n_list) prefetch(ds1, st ^ 1, nxt);
-        const int p0 = ds.x, o0 = ds.z, o1 = ds.w, np = ds.y - ds.x, cnt = o1 - o0;
+        oc = on;
+#pragma unroll
+        for (int u = 0; u < 6; ++u) d[u] = dn[u];
+        sj[st ^ 1][tid] = mid.j;
+        __syncthreads();                                       // the other stage half is free, its camera indices are visible
+        if (q + G < n_list) issue(ds1, st ^ 1, mid.j, on, dn);
+        cp_async_commit();
+        load_idx(ds2, far);
+        const int4 ds3 = q + 3 * G < n_list ? __ldg(ptdesc + chunk_of(q + 3 * G)) : zero4;
+        const int p0 = ds.x, o0 = ds.z, o1 = ds.w, np = ds.y - ds.x;
         const int k = o0 + tid;
-        const double *stage = wtile_dyn + st * PT_CTA * 18;
-        sj[tid] = cur.j;
-        double d[6];
-        if (k < o1) {
-            const double2 *dq = reinterpret_cast<const double2 *>(dpa + cur.j * 6);
-#pragma unroll
-            for (int u = 0; u < 3; ++u) { double2 d2 = __ldg(dq + u); d[2 * u] = d2.x; d[2 * u + 1] = d2.y; }
-        }
-        __syncthreads();                                       // sj visible
-        double2 pv[6];                                         // 6 x 16 B = q, t, K of the candidate camera
-#pragma unroll
-        for (int u = 0; u < 6; ++u) {
-            const int p = tid + u * PT_CTA, ob = p / 6, piece = p - ob * 6;
-            pv[u] = p < cnt * 6 ? __ldg(reinterpret_cast<const double2 *>(newcache + (size_t)sj[ob] * CAMC) + piece) : make_double2(0.0, 0.0);
-        }
+        const double *wt = wtile + st * PT_CTA * 18;
+        cp_async_wait<1>();
         mbar_wait(&bar[st], (it >> 1) & 1);                    // the TMA bytes of this chunk have landed
         if (k < o1) {
-            const double2 *wp = reinterpret_cast<const double2 *>(stage + tid * 18);
+            const double2 *wp = reinterpret_cast<const double2 *>(wt + tid * 18);
             double w[18];
 #pragma unroll
             for (int u = 0; u < 9; ++u) { double2 w2 = wp[u]; w[2 * u] = w2.x; w[2 * u + 1] = w2.y; }
@@ -299,34 +314,29 @@ __global__ void __launch_bounds__(PT_CTA, 3) k_backsub_pipe(int n_list, const in
             for (int r = 0; r < 6; ++r) { t0 += w[r * 3] * d[r]; t1 += w[r * 3 + 1] * d[r]; t2 += w[r * 3 + 2] * d[r]; }
             sh[0][tid] = t0; sh[1][tid] = t1; sh[2][tid] = t2;
         }
-#pragma unroll
-        for (int u = 0; u < 6; ++u) {
-            const int p = tid + u * PT_CTA, ob = p / 6, piece = p - ob * 6;
-            if (p < cnt * 6) *reinterpret_cast<double2 *>(pstage + ob * PROJ_LD + piece * 2) = pv[u];
-        }
-        __syncthreads();
+        __syncthreads();                                       // sh complete; every thread's entry copies have landed
         double s_dp2 = 0.0, s_dpg = 0.0, s_e2 = 0.0, s_p2 = 0.0;
         if (tid < np) {
             double acc0 = 0, acc1 = 0, acc2 = 0;
-            for (int u = cur.a; u < cur.b; ++u) { acc0 += sh[0][u - o0]; acc1 += sh[1][u - o0]; acc2 += sh[2][u - o0]; }
+            for (int u = oc.a; u < oc.b; ++u) { acc0 += sh[0][u - o0]; acc1 += sh[1][u - o0]; acc2 += sh[2][u - o0]; }
             const int p = p0 + tid;
-            const double e0 = cur.g0 - acc0, e1 = cur.g1 - acc1, e2 = cur.g2 - acc2;
-            const double d0 = cur.i00 * e0 + cur.i10 * e1 + cur.i20 * e2;
-            const double d1 = cur.i10 * e0 + cur.i11 * e1 + cur.i21 * e2;
-            const double d2 = cur.i20 * e0 + cur.i21 * e1 + cur.i22 * e2;
+            const double e0 = oc.g0 - acc0, e1 = oc.g1 - acc1, e2 = oc.g2 - acc2;
+            const double d0 = oc.i00 * e0 + oc.i10 * e1 + oc.i20 * e2;
+            const double d1 = oc.i10 * e0 + oc.i11 * e1 + oc.i21 * e2;
+            const double d2 = oc.i20 * e0 + oc.i21 * e1 + oc.i22 * e2;
             eb[(size_t)p * 3] = e0; eb[(size_t)p * 3 + 1] = e1; eb[(size_t)p * 3 + 2] = e2;
             dpb[(size_t)p * 3] = d0; dpb[(size_t)p * 3 + 1] = d1; dpb[(size_t)p * 3 + 2] = d2;
-            const double x0 = cur.px + d0, x1 = cur.py + d1, x2 = cur.pz + d2;
+            const double x0 = oc.px + d0, x1 = oc.py + d1, x2 = oc.pz + d2;
             newpts[(size_t)p * 3] = x0; newpts[(size_t)p * 3 + 1] = x1; newpts[(size_t)p * 3 + 2] = x2;
             shx[0][tid] = x0; shx[1][tid] = x1; shx[2][tid] = x2;
             s_dp2 = d0 * d0 + d1 * d1 + d2 * d2;
             s_p2 = x0 * x0 + x1 * x1 + x2 * x2;
-            s_dpg = d0 * (mu * d0 + cur.g0) + d1 * (mu * d1 + cur.g1) + d2 * (mu * d2 + cur.g2);
+            s_dpg = d0 * (mu * d0 + oc.g0) + d1 * (mu * d1 + oc.g1) + d2 * (mu * d2 + oc.g2);
         }
-        __syncthreads();                                       // shx and pstage are complete
+        __syncthreads();                                       // shx complete
         if (k < o1) {
             CamProj cam;
-            load_cam_proj<false>(pstage + tid * PROJ_LD, cam);
+            load_cam_proj<false>(pstage + st * PT_CTA * PROJ_LD + tid * PROJ_LD, cam);
             double e0, e1;
             residual(cam, shx[0][cur.lp], shx[1][cur.lp], shx[2][cur.lp], cur.mm.x, cur.mm.y, e0, e1);
             s_e2 = e0 * e0 + e1 * e1;
@@ -346,9 +356,10 @@ __global__ void __launch_bounds__(PT_CTA, 3) k_backsub_pipe(int n_list, const in
             for (int w = 0; w < PT_CTA / 32; ++w) s += red[tid][w];
             part[(size_t)cidx * 4 + tid] = s;
         }
-        __syncthreads();                                       // every shared buffer of this chunk is free again
-        ds = ds1; ds1 = ds2;
+        cur = mid; mid = far;
+        ds = ds1; ds1 = ds2; ds2 = ds3;
     }
+    cp_async_wait<0>();
 }
 
 // out[v] = sum_p part[p*4+v], v<4, fixed order.  1024 threads, four independent partial sums per thread and
@@ -396,7 +407,7 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
         psba_launch_cam_prep(c, nw);
         PROF(c, KID_BACKSUB) {
             static bool attr_set = false;
-            const int dyn = 2 * PT_CTA * 18 * (int)sizeof(double);
+            const int dyn = 2 * PT_CTA * (18 + PROJ_LD) * (int)sizeof(double);
             if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_backsub_pipe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)); attr_set = true; }
             if (c->n_small > 0)
                 k_backsub_pipe<0><<<std::min(c->n_small, c->n_sm * 3), PT_CTA, dyn, c->stream>>>(c->n_small, c->d_small_list, c->ptdesc, c->pt_ptr, c->iidx,
