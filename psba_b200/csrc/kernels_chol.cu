@@ -24,7 +24,8 @@
 
 #define LDT (TS + 1)            // padded leading dimension in shared memory
 #define TILE_SM (TS * LDT)      // doubles per shared tile
-#define CHOL_SMEM (2 * TILE_SM * sizeof(double))   // two staged tiles (factor tiles of panel K-1, then D and A_IK)
+#define LDD (TS + 4)            // leading dimension of the tiles staged for the tensor-core product (8 rows x 32 B per fragment load: 2 wavefronts)
+#define CHOL_SMEM (2 * TS * LDD * sizeof(double))   // two staged tiles (factor tiles of panel K-1, then D and A_IK)
 
 // ---------------------------------------------------------------------------------------------
 // Symbolic phase (host, once per problem).
@@ -364,6 +365,68 @@ __device__ __forceinline__ void tile_abt(const double *A, const double *A2, cons
     }
 }
 
+
+// ---- FP64 tensor-core product for the deferred updates ------------------------------------------------
+// The 6x3 register-blocked product reads 9 doubles from shared memory per 18 FMA and thread; ncu shows the leaf
+// steps at 73 % of the L1 data pipe and 25 % of the FP64 pipe.  DMMA.8x8x4 (mma.sync m8n8k4 f64) takes one double
+// of A and one of B per lane for 256 FMA: a warp that owns a 24x24 block of the tile (3x3 fragments) loads 6
+// doubles per lane and k-step of 4 for 9 DMMA = 2 304 FMA.
+template <int NT>
+__device__ __forceinline__ void tile_sts_ldd(double *sm, const TileRegs<NT> &t)
+{
+    constexpr int Q = (TS * TS / 2 + NT - 1) / NT;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int e = threadIdx.x + q * NT;
+        if (e < TS * TS / 2) { const int r = (2 * e) / TS, cc = (2 * e) % TS; *reinterpret_cast<double2 *>(sm + r * LDD + cc) = t.v[q]; }
+    }
+}
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// c (3x3 fragments of the warp's 24x24 block, rows rb.., columns cb..) -= A[rb..][:] * B[cb..][:]^T, tiles staged with LDD
+__device__ __forceinline__ void tile_abt_dmma_sub(const double *A, const double *B, int rb, int cb, double c[3][3][2])
+{
+    const int lane = threadIdx.x & 31, fr = lane >> 2, fk = lane & 3;
+    const double *ap = A + (rb + fr) * LDD + fk, *bp = B + (cb + fr) * LDD + fk;
+#pragma unroll 4
+    for (int ks = 0; ks < TS / 4; ++ks) {
+        double a[3], b[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) { a[t] = -ap[t * 8 * LDD + ks * 4]; b[t] = bp[t * 8 * LDD + ks * 4]; }
+#pragma unroll
+        for (int ti = 0; ti < 3; ++ti)
+#pragma unroll
+            for (int tj = 0; tj < 3; ++tj) dmma884(c[ti][tj][0], c[ti][tj][1], a[ti], b[tj]);
+    }
+}
+
+// c1 -= A1[rb..] * B[cb..]^T and (TWO) c2 -= A2[rb..] * B[cb..]^T with the B fragments shared
+template <bool TWO>
+__device__ __forceinline__ void tile_abt_dmma_sub2(const double *A1, const double *A2, const double *B, int rb, int cb,
+                                                   double c1[3][3][2], double c2[3][3][2])
+{
+    const int lane = threadIdx.x & 31, fr = lane >> 2, fk = lane & 3;
+    const double *a1p = A1 + (rb + fr) * LDD + fk, *a2p = A2 + (rb + fr) * LDD + fk, *bp = B + (cb + fr) * LDD + fk;
+#pragma unroll 2
+    for (int ks = 0; ks < TS / 4; ++ks) {
+        double a1[3], a2[3], b[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            a1[t] = -a1p[t * 8 * LDD + ks * 4]; b[t] = bp[t * 8 * LDD + ks * 4];
+            if (TWO) a2[t] = -a2p[t * 8 * LDD + ks * 4];
+        }
+#pragma unroll
+        for (int ti = 0; ti < 3; ++ti)
+#pragma unroll
+            for (int tj = 0; tj < 3; ++tj) {
+                dmma884(c1[ti][tj][0], c1[ti][tj][1], a1[ti], b[tj]);
+                if (TWO) dmma884(c2[ti][tj][0], c2[ti][tj][1], a2[ti], b[tj]);
+            }
+    }
+}
+
 // X = L^-1 for the lower-triangular 48x48 factor in smem, by recursive doubling: the eight 6x6 diagonal
 // blocks are inverted by substitution (one thread per column, <= 5 dependent steps), then blocks are
 // merged pairwise (h = 6, 12, 24):  inv [[A,0],[B,C]] = [[A^-1,0],[-C^-1 B A^-1, C^-1]].  The h x h
@@ -472,37 +535,39 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
         const int4 dd = cd0;
         const int sb = dd.y, se = dd.z;
         double *tij = Stiles + (size_t)dd.x * TS * TS;
-        TileRegs<PANEL_NT> ra, rb;
+        TileRegs<PANEL_NT> ra, rb_;
         {
             const int2 sl = __ldg(def_srcs + sb);
             tile_ldg(ra, Stiles + (size_t)sl.x * TS * TS);
-            tile_ldg(rb, Stiles + (size_t)sl.y * TS * TS);
+            tile_ldg(rb_, Stiles + (size_t)sl.y * TS * TS);
         }
-        double c18[6][3];
+        // warp w owns the 24x24 block (w / 2, w % 2) of the target: 3x3 DMMA fragments, two doubles per lane each
+        const int wrp = tid >> 5, lane = tid & 31, rb = (wrp >> 1) * 24, cb = (wrp & 1) * 24;
+        double cf[3][3][2];
 #pragma unroll
-        for (int p = 0; p < 6; ++p)
+        for (int ti = 0; ti < 3; ++ti)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) c18[p][q] = tij[(tr * 6 + p) * TS + tc * 3 + q];
+            for (int tj = 0; tj < 3; ++tj) {
+                const double2 v = *reinterpret_cast<const double2 *>(tij + (rb + ti * 8 + (lane >> 2)) * TS + cb + tj * 8 + 2 * (lane & 3));
+                cf[ti][tj][0] = v.x; cf[ti][tj][1] = v.y;
+            }
+        double *D0 = smem, *D1 = smem + TS * LDD;
         for (int s = sb; s < se; ++s) {
             if (s > sb) __syncthreads();
-            tile_sts(B0, ra); tile_sts(B1, rb);
+            tile_sts_ldd(D0, ra); tile_sts_ldd(D1, rb_);
             __syncthreads();
             if (s + 1 < se) {                                  // next source's tiles fly during the product
                 const int2 sl = __ldg(def_srcs + s + 1);
                 tile_ldg(ra, Stiles + (size_t)sl.x * TS * TS);
-                tile_ldg(rb, Stiles + (size_t)sl.y * TS * TS);
+                tile_ldg(rb_, Stiles + (size_t)sl.y * TS * TS);
             }
-            double acc[6][3];
-            tile_abt<false>(B0, B0, B1, acc, acc);
-#pragma unroll
-            for (int p = 0; p < 6; ++p)
-#pragma unroll
-                for (int q = 0; q < 3; ++q) c18[p][q] -= acc[p][q];
+            tile_abt_dmma_sub(D0, D1, rb, cb, cf);
         }
 #pragma unroll
-        for (int p = 0; p < 6; ++p)
+        for (int ti = 0; ti < 3; ++ti)
 #pragma unroll
-            for (int q = 0; q < 3; ++q) tij[(tr * 6 + p) * TS + tc * 3 + q] = c18[p][q];
+            for (int tj = 0; tj < 3; ++tj)
+                *reinterpret_cast<double2 *>(tij + (rb + ti * 8 + (lane >> 2)) * TS + cb + tj * 8 + 2 * (lane & 3)) = make_double2(cf[ti][tj][0], cf[ti][tj][1]);
         return;
     }
 
@@ -524,13 +589,20 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
         upd = sl.y >= 0;
         if (upd) tile_ldg(ri, Stiles + (size_t)sl.y * TS * TS);                                   // L_IP
     }
-    double d[6][3], a[6][3];
+    // D and A_IK as DMMA accumulator fragments: warp w owns the 24x24 block (w / 2, w % 2), 3x3 fragments of 8x8,
+    // lane l holds the entries (l / 4, 2 (l % 4) + {0, 1}) of each
+    const int wrp = tid >> 5, lane = tid & 31, rb = (wrp >> 1) * 24, cb = (wrp & 1) * 24;
+    double d[3][3][2], a[3][3][2];
 #pragma unroll
-    for (int p = 0; p < 6; ++p)
+    for (int ti = 0; ti < 3; ++ti)
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            d[p][q] = tkk[(tr * 6 + p) * TS + tc * 3 + q];
-            a[p][q] = diagcta ? 0.0 : tik[(tr * 6 + p) * TS + tc * 3 + q];
+        for (int tj = 0; tj < 3; ++tj) {
+            const int off = (rb + ti * 8 + (lane >> 2)) * TS + cb + tj * 8 + 2 * (lane & 3);
+            const double2 dv = *reinterpret_cast<const double2 *>(tkk + off);
+            d[ti][tj][0] = dv.x; d[ti][tj][1] = dv.y;
+            double2 av = make_double2(0.0, 0.0);
+            if (!diagcta) av = *reinterpret_cast<const double2 *>(tik + off);
+            a[ti][tj][0] = av.x; a[ti][tj][1] = av.y;
         }
     // right-hand side of the panel: what the rhs tasks of earlier steps left in bwork minus the
     // contributions of the source panels (ascending P)
@@ -549,25 +621,24 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
             upd = sl.y >= 0;
             if (upd) tile_ldg(ri, Stiles + (size_t)sl.y * TS * TS);
         }
-        tile_sts(B0, rp);
-        if (upd) tile_sts(B1, ri);
+        tile_sts_ldd(B0, rp);
+        if (upd) tile_sts_ldd(B0 + TS * LDD, ri);
         __syncthreads();
-        double acc[6][3], acc2[6][3];
-        if (upd) tile_abt<true>(B0, B1, B0, acc, acc2);
-        else tile_abt<false>(B0, B0, B0, acc, acc2);
-#pragma unroll
-        for (int p = 0; p < 6; ++p)
-#pragma unroll
-            for (int q = 0; q < 3; ++q) { d[p][q] -= acc[p][q]; if (upd) a[p][q] -= acc2[p][q]; }
+        if (upd) tile_abt_dmma_sub2<true>(B0, B0 + TS * LDD, B0, rb, cb, d, a);
+        else tile_abt_dmma_sub2<false>(B0, B0, B0, rb, cb, d, a);
     }
     PANEL_STAMP(2);
     // ---- hand the updated blocks over to the ROW-OWNER layout of the sweep: thread t < 48 owns row t of
     // D, thread 48+r owns row r of A_IK, thread 96 owns the right-hand-side row b_K^T
     __syncthreads();                                           // the factor tiles in B0/B1 are consumed
 #pragma unroll
-    for (int p = 0; p < 6; ++p)
+    for (int ti = 0; ti < 3; ++ti)
 #pragma unroll
-        for (int q = 0; q < 3; ++q) { B0[(tr * 6 + p) * LDT + tc * 3 + q] = d[p][q]; B1[(tr * 6 + p) * LDT + tc * 3 + q] = a[p][q]; }
+        for (int tj = 0; tj < 3; ++tj) {
+            const int off = (rb + ti * 8 + (lane >> 2)) * LDT + cb + tj * 8 + 2 * (lane & 3);
+            B0[off] = d[ti][tj][0]; B0[off + 1] = d[ti][tj][1];
+            B1[off] = a[ti][tj][0]; B1[off + 1] = a[ti][tj][1];
+        }
     if (tid < TS) colbuf[0][tid] = bk;
     __syncthreads();
     const bool active = tid < TS || (tid < 2 * TS && !diagcta) || tid == 2 * TS;
