@@ -489,6 +489,8 @@ __device__ __forceinline__ void tile_tri_inverse(const double *L, double *X)
 // optional phase stamps of the diagonal CTA of every step (PSBA_PANEL_DEBUG=1): clock64 at phase boundaries
 __device__ long long *g_panel_dbg = nullptr;
 #define PANEL_STAMP(i) do { if (dbg && tid == 0) dbg[i] = clock64(); } while (0)
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PANEL_WALL(i) do { if (dbg && tid == 0) dbg[i] = global_ns(); } while (0)
 // One kernel per STEP (128 threads per CTA); a step holds every panel whose dependencies are met.
 //  critical CTA for tile row I of panel K (I = K: the diagonal CTA): loads D = A_KK and A_IK, applies the
 //  pending updates of the source panels P of the previous step (D -= L_KP L_KP^T, A_IK -= L_IP L_KP^T), then
@@ -575,7 +577,7 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
     const int I = cd0.x, K = cd0.y;
     const bool diagcta = I == K;
     long long *dbg = (g_panel_dbg && blockIdx.x == 0) ? g_panel_dbg + (size_t)K * 8 : nullptr;
-    PANEL_STAMP(0);
+    PANEL_STAMP(0); PANEL_WALL(6);
     const int sb = cd1.x, se = cd1.y;
     const int slot_ik = cd0.z;
     double *tik = Stiles + (size_t)slot_ik * TS * TS;
@@ -761,7 +763,7 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
 #pragma unroll
             for (int c = 0; c < TS; c += 2) dst[c / 2] = make_double2(c <= tid ? row[c] : 0.0, c + 1 <= tid ? row[c + 1] : 0.0);
         }
-        PANEL_STAMP(5);
+        PANEL_STAMP(5); PANEL_WALL(7);
         return;
     }
     __syncthreads();
@@ -870,9 +872,9 @@ double psba_launch_factor(psba_ctx *c, bool defer_status)
         if (--dbg_runs == 0)
             for (int K = 0; K < c->nt; ++K)
                 if (h[(size_t)K * 8])
-                    fprintf(stderr, "panel %4d: loads %6lld  update %6lld  handover %6lld  sweep %6lld  store %6lld  total %6lld clk\n", K,
+                    fprintf(stderr, "panel %4d: loads %6lld  update %6lld  handover %6lld  sweep %6lld  store %6lld  total %6lld clk   start %lld end %lld ns\n", K,
                             h[K * 8 + 1] - h[K * 8], h[K * 8 + 2] - h[K * 8 + 1], h[K * 8 + 3] - h[K * 8 + 2], h[K * 8 + 4] - h[K * 8 + 3],
-                            h[K * 8 + 5] - h[K * 8 + 4], h[K * 8 + 5] - h[K * 8]);
+                            h[K * 8 + 5] - h[K * 8 + 4], h[K * 8 + 5] - h[K * 8], h[K * 8 + 6] - h[7], h[K * 8 + 7] - h[7]);
     }
     c->st_launches += c->n_steps + 2;
     c->S_valid = false;      // the factor overwrote the tile pool
