@@ -391,3 +391,46 @@ def test_points_with_more_observations_than_one_wave(mode, monkeypatch):
     for a, b in zip(to, tg):
         assert abs(a["err"] - b["err"]) / a["err"] < 1e-9
     G.close(); O.close()
+
+
+def _ragged_problem():
+    """ring of 24 cameras where camera 5 sees nothing, every seventh point has ONE observation and the others two or
+    three: empty camera rows / pair runs, rank-deficient V_i (regularised by the damping only)"""
+    from psba_b200 import synth
+    a = synth.ring_problem(m=24, n=600, d=3, w=8, seed=5)
+    keep = np.ones(a["o"], dtype=bool)
+    keep[a["jidx"] == 5] = False
+    first = np.concatenate([[True], a["iidx"][1:] != a["iidx"][:-1]])
+    keep[(a["iidx"] % 7 == 0) & ~first] = False
+    # a point whose only remaining candidates were camera 5 keeps its first observation
+    cnt = np.bincount(a["iidx"][keep], minlength=a["n"])
+    for i in np.nonzero(cnt == 0)[0]:
+        keep[np.nonzero(a["iidx"] == i)[0][0]] = True
+    prob = dict(a)
+    prob["o"] = int(keep.sum())
+    prob["iidx"] = a["iidx"][keep].astype(np.int32); prob["jidx"] = a["jidx"][keep].astype(np.int32)
+    prob["impts"] = a["impts"][keep]
+    # observations kept "to save a point" may belong to camera 5: move them to camera 6 if that keeps cameras ascending
+    bad = prob["jidx"] == 5
+    prob["jidx"][bad] = 4
+    order_ok = np.all((prob["iidx"][1:] > prob["iidx"][:-1]) | ((prob["iidx"][1:] == prob["iidx"][:-1]) & (prob["jidx"][1:] > prob["jidx"][:-1])))
+    assert order_ok
+    prob["name"] = "ring-24-ragged"
+    return prob
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_ragged_structure_empty_camera_and_single_observation_points(mode, monkeypatch):
+    monkeypatch.setenv("PSBA_PAIR_MODE", mode)
+    prob = _ragged_problem()
+    assert not np.any(prob["jidx"] == 5) and np.bincount(prob["iidx"]).min() == 1
+    G = psba_b200.PSBA(prob)
+    O = _check_try_against_oracle(prob, G)
+    G.close()
+    G = psba_b200.PSBA(prob)
+    assert O.levmar() == G.levmar()[0]
+    to, tg = O.trace(), G.trace()
+    assert pattern(tg) == pattern(to) and len(to) >= 2
+    for a, b in zip(to, tg):
+        assert abs(a["err"] - b["err"]) / a["err"] < 1e-9
+    G.close(); O.close()
