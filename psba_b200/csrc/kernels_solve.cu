@@ -112,7 +112,7 @@ __global__ void k_mat_max(int N, const double *__restrict__ mat, double *__restr
     double xi = 0.0, ga = 0.0;
     for (int r = threadIdx.x; r < N; r += 256) {
         for (int k = 0; k < N; ++k) {
-            double t = fabs(mat[(size_t)r * N + k]);
+            double t = fabs(mat[(size_t)k * N + r]);           // symmetric input: column r = row r, coalesced
             if (k == r) { if (t > ga) ga = t; } else if (t > xi) xi = t;
         }
     }
@@ -125,6 +125,11 @@ __global__ void k_mat_max(int N, const double *__restrict__ mat, double *__restr
     if (threadIdx.x == 0) { out2[0] = sx[0]; out2[1] = sg[0]; }
 }
 
+// The working matrix is addressed TRANSPOSED, element (r, c) at mat[c * N + r]: the input is symmetric (dense S with
+// the mirrored upper triangle), the threads of a warp own consecutive rows r, so every access of the factor is
+// coalesced (row-major addressing made each lane pull its own 32-byte sector: 2.5 ms on N = 312).  Only E and the
+// number of scalar blocks leave this file.
+#define M(r, c) mat[(size_t)(c) * N + (r)]
 __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ mat, double *__restrict__ aux, double *__restrict__ diagInv,
                                                   double *__restrict__ diag, double beta, double delta, int *__restrict__ nscalar_out)
 {
@@ -134,13 +139,13 @@ __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ ma
     const int tid = threadIdx.x, nb = N / 3;
     int nscalar = 0;
     for (int j = 0; j < nb; ++j) {
-        double *d = mat + (size_t)(j * 3) * N + j * 3;
+        const int j3 = j * 3;
         if (tid < 9) {   // back up A_jj, diag; T_jj (cholmod_blk.cl:107-129)
             const int u = tid / 3, v = tid % 3;
-            double sum = d[(size_t)u * N + v];
+            double sum = M(j3 + u, j3 + v);
             aux[j * 9 + tid] = sum;
             if (u == v) diag[j * 3 + u] = sum;
-            for (int k = 0; k < j; ++k) sum -= dot3g(mat + (size_t)(j * 3 + u) * N + k * 3, mat + (size_t)(j * 3 + v) * N + k * 3);
+            for (int k = 0; k < j; ++k) sum -= M(j3 + u, k * 3) * M(j3 + v, k * 3) + M(j3 + u, k * 3 + 1) * M(j3 + v, k * 3 + 1) + M(j3 + u, k * 3 + 2) * M(j3 + v, k * 3 + 2);
             T[tid] = sum;
         }
         if (tid == 0) { fail = 0; over = 0; }
@@ -166,9 +171,9 @@ __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ ma
             if (!isfinite(L[5]) || L[5] <= 0) f = 1; else L[5] = sqrt(L[5]);
             fail = f;
             if (!f) {
-                d[0] = L[0]; d[1] = 0; d[2] = 0;
-                d[N] = L[1]; d[N + 1] = L[2]; d[N + 2] = 0;
-                d[2 * (size_t)N] = L[3]; d[2 * (size_t)N + 1] = L[4]; d[2 * (size_t)N + 2] = L[5];
+                M(j3, j3) = L[0]; M(j3, j3 + 1) = 0; M(j3, j3 + 2) = 0;
+                M(j3 + 1, j3) = L[1]; M(j3 + 1, j3 + 1) = L[2]; M(j3 + 1, j3 + 2) = 0;
+                M(j3 + 2, j3) = L[3]; M(j3 + 2, j3 + 1) = L[4]; M(j3 + 2, j3 + 2) = L[5];
                 tri3_inverse_dev(L, inv);
                 for (int k = 0; k < 9; ++k) diagInv[j * 9 + k] = inv[k];
             }
@@ -183,16 +188,16 @@ __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ ma
                 const int row = (j + 1) * 3 + rr;
                 const int i = row / 3, u = row % 3;
                 double Tij[3];
-                for (int v = 0; v < 3; ++v) {
-                    double sum = mat[(size_t)row * N + j * 3 + v];
-                    aux[i * 9 + u * 3 + v] = sum;
-                    for (int k = 0; k < j; ++k) sum -= dot3g(mat + (size_t)row * N + k * 3, mat + (size_t)(j * 3 + v) * N + k * 3);
-                    Tij[v] = sum;
+                for (int v = 0; v < 3; ++v) { Tij[v] = M(row, j3 + v); aux[i * 9 + u * 3 + v] = Tij[v]; }
+                for (int k = 0; k < j; ++k) {               // per entry the reference's order: ascending k (cholmod_blk.cl:318-331)
+                    const double a0 = M(row, k * 3), a1 = M(row, k * 3 + 1), a2 = M(row, k * 3 + 2);
+#pragma unroll
+                    for (int v = 0; v < 3; ++v) Tij[v] -= a0 * M(j3 + v, k * 3) + a1 * M(j3 + v, k * 3 + 1) + a2 * M(j3 + v, k * 3 + 2);
                 }
                 for (int v = 0; v < 3; ++v) {
                     const double sum = Tij[0] * inv[v * 3] + Tij[1] * inv[v * 3 + 1] + Tij[2] * inv[v * 3 + 2];
-                    mat[(size_t)row * N + j * 3 + v] = sum;
-                    mat[(size_t)(j * 3 + v) * N + row] = 0;
+                    M(row, j3 + v) = sum;
+                    M(j3 + v, row) = 0;
                     if (sum > beta) over = 1;          // signed compare, SURVEY A.4
                 }
             }
@@ -201,12 +206,12 @@ __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ ma
                 for (int rr = tid; rr < nrows; rr += 1024) {
                     const int row = (j + 1) * 3 + rr;
                     const int i = row / 3, u = row % 3;
-                    for (int v = 0; v < 3; ++v) mat[(size_t)row * N + j * 3 + v] = aux[i * 9 + u * 3 + v];
+                    for (int v = 0; v < 3; ++v) M(row, j3 + v) = aux[i * 9 + u * 3 + v];
                 }
                 if (tid == 0) {
-                    d[0] = aux[j * 9];
-                    d[N] = aux[j * 9 + 3]; d[N + 1] = aux[j * 9 + 4];
-                    d[2 * (size_t)N] = aux[j * 9 + 6]; d[2 * (size_t)N + 1] = aux[j * 9 + 7]; d[2 * (size_t)N + 2] = aux[j * 9 + 8];
+                    M(j3, j3) = aux[j * 9];
+                    M(j3 + 1, j3) = aux[j * 9 + 3]; M(j3 + 1, j3 + 1) = aux[j * 9 + 4];
+                    M(j3 + 2, j3) = aux[j * 9 + 6]; M(j3 + 2, j3 + 1) = aux[j * 9 + 7]; M(j3 + 2, j3 + 2) = aux[j * 9 + 8];
                 }
                 scalar = true;
             }
@@ -216,11 +221,11 @@ __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ ma
             ++nscalar;
             for (int col = 0; col < 3; ++col) {
                 const int x = j * 3 + col;
-                const size_t jj = (size_t)x * N + x;
+                const size_t jj = (size_t)x * N + x;              // the diagonal is where it was
                 __syncthreads();
                 if (tid == 0) {
                     double sum = mat[jj];
-                    for (int k = 0; k < x; ++k) { const double Lk = mat[(size_t)x * N + k]; sum -= Lk * Lk; }
+                    for (int k = 0; k < x; ++k) { const double Lk = M(x, k); sum -= Lk * Lk; }
                     sum = fabs(sum);
                     const double dj = fmax(sum, delta);
                     aux[x] = dj;
@@ -230,12 +235,12 @@ __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ ma
                 __syncthreads();
                 const double ljj = mat[jj];
                 for (int i = x + 1 + tid; i < N; i += 1024) {
-                    double C = mat[(size_t)i * N + x];
-                    for (int k = 0; k < x; ++k) C = C - (mat[(size_t)i * N + k] * mat[(size_t)x * N + k]);
+                    double C = M(i, x);
+                    for (int k = 0; k < x; ++k) C = C - (M(i, k) * M(x, k));
                     aux[N + i] = C;
                     const double lij = C / ljj;
-                    mat[(size_t)i * N + x] = lij;
-                    mat[(size_t)x * N + i] = 0;
+                    M(i, x) = lij;
+                    M(x, i) = 0;
                     if (lij > beta) flagged = 1;
                 }
                 __syncthreads();
@@ -248,13 +253,13 @@ __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ ma
                         aux[x] = theta_s * theta_s;
                     }
                     __syncthreads();
-                    for (int i = x + 1 + tid; i < N; i += 1024) mat[(size_t)i * N + x] = aux[N + i] / theta_s;
+                    for (int i = x + 1 + tid; i < N; i += 1024) M(i, x) = aux[N + i] / theta_s;
                 }
                 __syncthreads();
             }
             if (tid == 0) {   // kern_cholmod_diaginv (cholmod_blk.cl:703-763)
-                L[0] = d[0]; L[1] = d[N]; L[2] = d[N + 1];
-                L[3] = d[2 * (size_t)N]; L[4] = d[2 * (size_t)N + 1]; L[5] = d[2 * (size_t)N + 2];
+                L[0] = M(j3, j3); L[1] = M(j3 + 1, j3); L[2] = M(j3 + 1, j3 + 1);
+                L[3] = M(j3 + 2, j3); L[4] = M(j3 + 2, j3 + 1); L[5] = M(j3 + 2, j3 + 2);
                 tri3_inverse_dev(L, inv);
                 for (int k = 0; k < 9; ++k) diagInv[j * 9 + k] = inv[k];
             }
@@ -270,10 +275,11 @@ __global__ void k_cholmod_E(int N, const double *__restrict__ mat, double *__res
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     double sum = 0.0;
-    for (int k = 0; k <= i; ++k) sum += mat[(size_t)i * N + k] * mat[(size_t)i * N + k];
+    for (int k = 0; k <= i; ++k) sum += M(i, k) * M(i, k);
     diag[i] = sum - diag[i];
 }
 
+#undef M
 // runs on c->Sdense (dense S incl. mirrored upper triangle). Returns sum_i E_i (left-to-right).
 double psba_launch_cholmod(psba_ctx *c, double *delta_out, double *beta_out, int *nscalar_out)
 {
