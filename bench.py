@@ -24,8 +24,12 @@ import time
 
 import numpy as np
 
-# NCCL prints its version banner on stdout when NCCL_DEBUG asks for it: rank 0 must print ONE JSON line
-os.environ["NCCL_DEBUG"] = os.environ.get("PSBA_NCCL_DEBUG", "WARN")
+# NCCL prints its version banner / debug lines on stdout when NCCL_DEBUG is set (WARN and VERSION included): rank 0
+# must print ONE JSON line, so the variable is dropped (PSBA_NCCL_DEBUG re-enables it) and NCCL's log goes to stderr
+os.environ.pop("NCCL_DEBUG", None)
+if os.environ.get("PSBA_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = os.environ["PSBA_NCCL_DEBUG"]
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -181,7 +185,23 @@ def bal_full_solves(cores):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the process's original stdout; everything else any library prints was sent to stderr"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                                        # NCCL / CUDA libraries print banners on fd 1
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -214,7 +234,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "ms_per_step / lm_iters_per_sec are scaled from the sample to the full workload by the observation ratio"}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -351,7 +371,7 @@ def main():
                 "gpu_launches": launches, "setup_seconds": round(setup_s, 3),
                 "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "kernels": ktab,
                 "bal_full_solves": bal}
-        print(json.dumps(line))
+        emit(line)
     G.close()
     if world > 1:
         L.psba_comm_finalize()
