@@ -169,7 +169,7 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
         for (int I = 0; I < nt; ++I)
             for (int J = 0; J <= I; ++J)
                 if (present[(size_t)I * nt + J] && (presentS[(size_t)I * nt + J] != 0) == (pass == 0)) c->h_tile_index[(size_t)I * nt + J] = slot++;
-        if (pass == 0) c->n_tiles_S = slot;
+        if (pass == 0) { c->n_tiles_S = slot; slot += (c->N + TS * TS - 1) / (TS * TS); }   // room for ea behind the S tiles: one all-reduce for both
     }
     c->n_tiles = slot;
     // ---- steps: a panel runs one step after the last panel it depends on

@@ -427,8 +427,10 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
     if (c->n_cchunk > 0)
         PROF(c, KID_LIN_CAMS) k_lin_cams<<<c->n_cchunk, CAM_CTA, 0, cs>>>(c->cchunk_cam, c->cchunk_beg, c->cchunk_end, c->cam_pt,
                                                           c->cam_impts, c->camcache[set], c->pts[set], c->cam_part);
+    // N > 1 GPUs: ga goes right behind U so that ONE all-reduce sums both
+    double *ga_out = c->nranks > 1 ? c->U + (size_t)c->m * 36 : c->g;
     PROF(c, KID_CAM_REDUCE) k_cam_reduce<<<cdiv(c->m * 27, 128), 128, 0, cs>>>(c->m, c->cam_cchunk_ptr, c->cam_part, coeff_uvw, coeff_g,
-                                                             c->U, c->g);
+                                                             c->U, ga_out);
     if (c->n_ptchunk > 0)
         PROF(c, KID_LIN_POINTS) {
             static bool attr_set = false;
@@ -457,8 +459,8 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
     }
     c->st_launches += 3; c->st_lin += 1;
     if (c->nranks > 1) {
-        psba_allreduce_sum(c, c->U, (size_t)c->m * 36);
-        psba_allreduce_sum(c, c->g, (size_t)c->N);
+        psba_allreduce_sum(c, c->U, (size_t)c->m * 42);
+        CUDA_CHECK(cudaMemcpyAsync(c->g, c->U + (size_t)c->m * 36, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     }
     c->coeff_uvw = coeff_uvw; c->coeff_g = coeff_g;
     c->lin_valid = true; c->S_valid = false; c->factor_valid = false;

@@ -550,7 +550,7 @@ __global__ void k_S_finalize_rows(int n_pair, const int *__restrict__ pair_k, co
 // multi-GPU second half: add U_k + mu I to the diagonal blocks and ga to ea (after the all-reduce)
 __global__ void k_add_U(int m, const double *__restrict__ U, const double *__restrict__ ga, double mu,
                         const int *__restrict__ tile_index, const int *__restrict__ cam2pos, int nt,
-                        double *__restrict__ Stiles, double *__restrict__ ea)
+                        double *__restrict__ Stiles, const double *__restrict__ ea_red, double *__restrict__ ea)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int k = t / 42, v = t - k * 42;
@@ -561,7 +561,7 @@ __global__ void k_add_U(int m, const double *__restrict__ U, const double *__res
         double u = U[k * 36 + v];
         if (r == cc) u += mu;
         *p = u + *p;
-    } else ea[k * 6 + (v - 36)] += ga[k * 6 + (v - 36)];
+    } else ea[k * 6 + (v - 36)] = ea_red[k * 6 + (v - 36)] + ga[k * 6 + (v - 36)];
 }
 
 // identity on the padding rows (block positions without a camera) so that the factorisation is well defined
@@ -578,6 +578,9 @@ void psba_launch_schur(psba_ctx *c, double mu)
     psba_launch_vinv(c, mu);
     PROF(c, KID_MEMSET_S) CUDA_CHECK(cudaMemsetAsync(c->Stiles, 0, (size_t)c->n_tiles * TS * TS * sizeof(double), c->stream));
     const int single = c->nranks == 1;
+    // N > 1 GPUs: the local sums of ea go right behind the S tiles of the pool so that ONE all-reduce moves both
+    double *ea_red = c->Stiles + (size_t)c->n_tiles_S * TS * TS;
+    double *ea_out = single ? c->eab : ea_red;
     if (c->rows_ok) {
         if (c->n_rseg > 0)
             PROF(c, KID_SCHUR_PAIRS) {
@@ -588,7 +591,7 @@ void psba_launch_schur(psba_ctx *c, double mu)
             }
         PROF(c, KID_S_FINALIZE) k_S_finalize_rows<<<cdiv((long long)c->n_pair * 42, 128), 128, 0, c->stream>>>(c->n_pair, c->pair_k, c->pair_l, c->row_pair0,
                                                                              c->row_seg_ptr, c->rseg_slot_base, c->pair_part, c->U, c->g, mu, single,
-                                                                             c->tile_index, c->cam2pos, c->nt, c->Stiles, c->eab);
+                                                                             c->tile_index, c->cam2pos, c->nt, c->Stiles, ea_out);
     } else {
         if (c->n_pchunk > 0) {
             PROF(c, KID_SCHUR_PAIRS) {
@@ -613,14 +616,12 @@ void psba_launch_schur(psba_ctx *c, double mu)
         }
         PROF(c, KID_S_FINALIZE) k_S_finalize<<<cdiv((long long)c->n_pair * 42, 128), 128, 0, c->stream>>>(c->n_pair, c->pair_k, c->pair_l, c->pair_chunk_ptr,
                                                                              c->pair_part, c->U, c->g, mu, single, c->tile_index,
-                                                                             c->cam2pos, c->nt, c->Stiles, c->eab);
+                                                                             c->cam2pos, c->nt, c->Stiles, ea_out);
     }
     c->st_launches += 3;
     if (!single) {
-        // the tile pool and ea are contiguous-by-construction only separately: two all-reduces
-        psba_allreduce_sum(c, c->Stiles, (size_t)c->n_tiles_S * TS * TS);     // fill-in tiles are zero on every rank
-        psba_allreduce_sum(c, c->eab, (size_t)c->N);
-        k_add_U<<<cdiv(c->m * 42, 128), 128, 0, c->stream>>>(c->m, c->U, c->g, mu, c->tile_index, c->cam2pos, c->nt, c->Stiles, c->eab);
+        psba_allreduce_sum(c, c->Stiles, (size_t)c->n_tiles_S * TS * TS + (size_t)c->N);   // S tiles + ea; fill-in tiles are zero on every rank
+        k_add_U<<<cdiv(c->m * 42, 128), 128, 0, c->stream>>>(c->m, c->U, c->g, mu, c->tile_index, c->cam2pos, c->nt, c->Stiles, ea_red, c->eab);
         c->st_launches += 1;
     }
     if (c->nt * TS > c->N) { k_pad_diag<<<cdiv(c->nt * TS, 256), 256, 0, c->stream>>>(c->nt, c->pos2cam, c->tile_index, c->Stiles); c->st_launches += 1; }

@@ -91,7 +91,7 @@ extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3D
         c->cams[s] = dalloc<double>(c, (size_t)nCams * 6);
         c->camcache[s] = dalloc<double>(c, (size_t)nCams * CAMC);
     }
-    c->U = dalloc<double>(c, (size_t)nCams * 36);
+    c->U = dalloc<double>(c, (size_t)nCams * 42);          // [U | 6m doubles: ga as it comes out of the camera pass on N > 1 GPUs (one all-reduce for both)]
     c->d_status = dalloc<int>(c, 4);
     c->d_scal = dalloc<double>(c, NSCAL);
     CUDA_CHECK(cudaMallocHost(&c->h_scal, NSCAL * sizeof(double)));
