@@ -434,3 +434,26 @@ def test_ragged_structure_empty_camera_and_single_observation_points(mode, monke
     for a, b in zip(to, tg):
         assert abs(a["err"] - b["err"]) / a["err"] < 1e-9
     G.close(); O.close()
+
+
+@pytest.mark.parametrize("key", ["7", "T21"])
+def test_indefinite_camera_system_is_reported_not_factored(key):
+    """Failure semantics of the camera solve (SPD_inv.cl:66-107, cl_spdinv.cpp:18-40): a system that is not positive
+    definite makes SPDinv return 1.0 -- here forced with a NEGATIVE damping term -- and the fused try reports
+    solve_status 1 with NaN costs, so that levmar.cpp:227-244 can raise mu and try again.  A regular try on the same
+    context afterwards must still work."""
+    prob = psba_b200.read_sba(*dataset_paths(key))
+    O = oracle.Problem(prob); G = psba_b200.PSBA(prob)
+    O.call("exQT"); O.call("jacobiQT"); O.call("U", 1); O.call("V", 1); O.call("Wblks", 1); O.call("g", 1)
+    mx = float(np.max(O.buf("UVdiag")))
+    O.call("update_UV", -0.5 * mx); O.call("Vinv"); O.call("Yblks"); O.call("S"); O.call("ea")
+    assert O.call("SPDinv") == 1.0
+    G.compute_exQT(); G.linearize(1.0, 1.0)
+    G.update_UV(-0.5 * mx); G.compute_Vinv(); G.compute_S()
+    assert G.SPDinv() == 1.0
+    G.restore_UVdiag()
+    res = G.try_step(-0.5 * mx)
+    assert res["solve_status"] == 1.0 and np.isnan(res["cost_new"])
+    res = G.try_step(1e-3 * mx)
+    assert res["solve_status"] == 0.0 and np.isfinite(res["cost_new"]) and res["cost_new"] > 0
+    G.close(); O.close()
