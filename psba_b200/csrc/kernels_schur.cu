@@ -255,6 +255,155 @@ static void launch_pairs_q(psba_ctx *c)
                                                                             c->Vinv, c->g + c->N, c->pair_part);
 }
 
+// Staged variant of the pair-major pass (PSBA_PAIR_MODE=3; measured 1.19 ms against 1.03 ms: the line look-ups fall
+// from 21 to ~6 per triple, but two stages of 10.75 KB per warp allow only 8 warps per SM and one round in flight).  The lane-per-triple kernel is bound by the number of
+// cache lines its loads touch: every lane pulls its own 16-byte pieces (21 per triple), a warp instruction touches 32
+// different lines and the L1 serves about one line per cycle (an L1 prefetch of the next triple, five more requests
+// per triple, makes it 34 % slower; three times the occupancy does not help).  Here the warp fetches the operands
+// of its 32 triples COOPERATIVELY: the 21 x 16-byte pieces of a triple are consecutive pieces of the warp's copy
+// list, consecutive lanes take consecutive pieces (asynchronous copies, LDGSTS), so one instruction touches ~7
+// lines instead of 32; the copies of the next round fly during the products of this one; every lane then reads its
+// own 336 bytes from the warp's stage (stride 21 x 16 B: conflict-free).  No CTA-wide barrier anywhere.
+#define STG_PIECES 21                                          // 9 (W_a) + 9 (W_b) + 3 (Vinv) pieces of 16 B
+template <int G>
+__global__ void __launch_bounds__(PAIR_CTA, 2) k_schur_pairs_s(int n_pchunk, const int *__restrict__ pchunk_pair,
+                                                           const long long *__restrict__ pchunk_beg, const long long *__restrict__ pchunk_end,
+                                                           const int *__restrict__ pair_k, const int *__restrict__ pair_l,
+                                                           const int *__restrict__ tri_oa, const int *__restrict__ tri_ob,
+                                                           const int *__restrict__ tri_pt, const double *__restrict__ W,
+                                                           const double *__restrict__ Vinv, const double *__restrict__ gb,
+                                                           double *__restrict__ part)
+{
+    extern __shared__ __align__(16) unsigned char stg_dyn[];   // per warp: two stages of 32 x 336 B, two index tables
+    constexpr int NW = PAIR_CTA / 32;
+    constexpr int STAGE = 32 * STG_PIECES * 16;
+    const int tid = threadIdx.x, wrp = tid >> 5, ln = tid & 31;
+    unsigned char *stage = stg_dyn + (size_t)wrp * 2 * STAGE;
+    int *itab = reinterpret_cast<int *>(stg_dyn + (size_t)NW * 2 * STAGE) + wrp * 2 * 32 * 3;
+    const int lane = tid % G;
+    const int ch = blockIdx.x * (PAIR_CTA / G) + tid / G;
+    double acc[42];
+#pragma unroll
+    for (int q = 0; q < 42; ++q) acc[q] = 0.0;
+    bool diag = false;
+    long long t = 0, end = 0;
+    if (ch < n_pchunk) {
+        const int pr = pchunk_pair[ch];
+        diag = pair_k[pr] == pair_l[pr];
+        t = pchunk_beg[ch] + lane; end = pchunk_end[ch];
+    }
+    // indices of this lane's triple of the round being issued (a < 0: none)
+    auto load_idx = [&](long long tt, int &a, int &b, int &i) {
+        a = -1; b = 0; i = 0;
+        if (tt < end) { a = __ldg(tri_oa + tt); b = diag ? a : __ldg(tri_ob + tt); i = __ldg(tri_pt + tt); }
+    };
+    // the warp's copies of one round.  W blocks (9 pieces): eight lanes take the first eight pieces of a block (128
+    // contiguous bytes: one line, two at most), four blocks per instruction, eight instructions for the 32 blocks; one
+    // more instruction for the ninth piece of every block.  Vinv (3 pieces): eight blocks per instruction.
+    auto issue = [&](int buf, int a, int b, int i) {
+        int *tb = itab + buf * 96;
+        tb[ln * 3] = a; tb[ln * 3 + 1] = b; tb[ln * 3 + 2] = i;
+        __syncwarp();
+        unsigned char *st = stage + buf * STAGE;
+        const int sub8 = ln & 7, blk4 = ln >> 3;
+#pragma unroll 2
+        for (int u = 0; u < 8; ++u) {
+            const int trip = blk4 + 4 * u;
+            const int ta = tb[trip * 3], tbb = tb[trip * 3 + 1];
+            if (ta >= 0) {
+                unsigned char *dst = st + trip * (STG_PIECES * 16) + sub8 * 16;
+                if (ta != tbb) cp_async16(dst, reinterpret_cast<const char *>(W + (size_t)ta * 18) + sub8 * 16);   // diagonal triples: W_a is W_b
+                cp_async16(dst + 144, reinterpret_cast<const char *>(W + (size_t)tbb * 18) + sub8 * 16);
+            }
+        }
+        if (a >= 0) {                                          // ninth piece of this lane's own blocks
+            unsigned char *dst = st + ln * (STG_PIECES * 16) + 128;
+            if (a != b) cp_async16(dst, reinterpret_cast<const char *>(W + (size_t)a * 18) + 128);
+            cp_async16(dst + 144, reinterpret_cast<const char *>(W + (size_t)b * 18) + 128);
+        }
+        const int blk8 = ln / 3, sub3 = ln - blk8 * 3;          // lanes 0..23: eight Vinv blocks of three pieces
+        if (ln < 24) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int trip = blk8 + 8 * u;
+                const int ta = tb[trip * 3], ti = tb[trip * 3 + 2];
+                if (ta >= 0) cp_async16(st + trip * (STG_PIECES * 16) + 288 + sub3 * 16, reinterpret_cast<const char *>(Vinv + (size_t)ti * 6) + sub3 * 16);
+            }
+        }
+    };
+    int a0, b0, i0, a1, b1, i1;
+    load_idx(t, a0, b0, i0);
+    load_idx(t + G, a1, b1, i1);
+    issue(0, a0, b0, i0);
+    cp_async_commit();
+    for (int it = 0; __any_sync(0xffffffffu, a0 >= 0); ++it) {
+        const int buf = it & 1;
+        issue(buf ^ 1, a1, b1, i1);                            // next round's copies fly during this round's products
+        cp_async_commit();
+        int a2, b2, i2;
+        load_idx(t + 2 * (long long)G, a2, b2, i2);            // indices two rounds ahead
+        double g0 = 0, g1 = 0, g2 = 0;
+        if (diag && a0 >= 0) { const double *gp = gb + (size_t)i0 * 3; g0 = __ldg(gp); g1 = __ldg(gp + 1); g2 = __ldg(gp + 2); }
+        cp_async_wait<1>();
+        __syncwarp();
+        if (a0 >= 0) {
+            const double2 *sp = reinterpret_cast<const double2 *>(stage + buf * STAGE + ln * STG_PIECES * 16);
+            const double2 v01 = sp[18], v23 = sp[19], v45 = sp[20];
+            const double i00 = v01.x, i10 = v01.y, i20 = v23.x, i11 = v23.y, i21 = v45.x, i22 = v45.y;
+            double wb[18];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { const double2 w2 = sp[9 + q]; wb[2 * q] = w2.x; wb[2 * q + 1] = w2.y; }
+            const int ao = a0 == b0 ? 9 : 0;                   // diagonal triples read W_b again
+#pragma unroll
+            for (int rp = 0; rp < 3; ++rp) {
+                double wa[6];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { const double2 w2 = sp[ao + rp * 3 + q]; wa[2 * q] = w2.x; wa[2 * q + 1] = w2.y; }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = rp * 2 + h;
+                    const double w0 = wa[h * 3], w1 = wa[h * 3 + 1], w2 = wa[h * 3 + 2];
+                    const double y0 = w0 * i00 + w1 * i10 + w2 * i20;
+                    const double y1 = w0 * i10 + w1 * i11 + w2 * i21;
+                    const double y2 = w0 * i20 + w1 * i21 + w2 * i22;
+#pragma unroll
+                    for (int cc = 0; cc < 6; ++cc)
+                        acc[r * 6 + cc] += y0 * wb[cc * 3] + y1 * wb[cc * 3 + 1] + y2 * wb[cc * 3 + 2];
+                    acc[36 + r] += y0 * g0 + y1 * g1 + y2 * g2;
+                }
+            }
+        }
+        __syncwarp();                                          // the stage and its index table are free again
+        t += G;
+        a0 = a1; b0 = b1; i0 = i1; a1 = a2; b1 = b2; i1 = i2;
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int w = G / 2; w > 0; w >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 42; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], w);
+    }
+    if (ch < n_pchunk) {
+        double *out = part + (size_t)ch * 42;
+        const int nv = diag ? 42 : 36;
+#pragma unroll
+        for (int q = 0; q < 42; ++q)
+            if ((q % G) == lane && q < nv) out[q] = acc[q];
+    }
+}
+
+template <int G>
+static void launch_pairs_s(psba_ctx *c)
+{
+    const int per_cta = PAIR_CTA / G;
+    const int dyn = (PAIR_CTA / 32) * (2 * 32 * STG_PIECES * 16 + 2 * 96 * (int)sizeof(int));
+    static bool attr_set = false;
+    if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_schur_pairs_s<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)); attr_set = true; }
+    k_schur_pairs_s<G><<<cdiv(c->n_pchunk, per_cta), PAIR_CTA, dyn, c->stream>>>(c->n_pchunk, c->pchunk_pair, c->pchunk_beg, c->pchunk_end,
+                                                                              c->pair_k, c->pair_l, c->tri_oa, c->tri_ob, c->tri_pt, c->W,
+                                                                              c->Vinv, c->g + c->N, c->pair_part);
+}
+
 // position of entry (r,cc) of the camera block (k,l) inside the tile pool: the camera system is stored in
 // the solver's camera ordering (cam2pos); a block that lands above the diagonal is stored transposed
 __device__ __forceinline__ double *s_entry(double *Stiles, const int *__restrict__ tile_index, int nt, int pk, int pl, int r, int cc)
@@ -595,7 +744,16 @@ void psba_launch_schur(psba_ctx *c, double mu)
     } else {
         if (c->n_pchunk > 0) {
             PROF(c, KID_SCHUR_PAIRS) {
-                if (c->pair_mode == 1) {
+                if (c->pair_mode == 3) {
+                    switch (c->pair_G) {
+                    case 1: launch_pairs_s<1>(c); break;
+                    case 2: launch_pairs_s<2>(c); break;
+                    case 4: launch_pairs_s<4>(c); break;
+                    case 8: launch_pairs_s<8>(c); break;
+                    case 16: launch_pairs_s<16>(c); break;
+                    default: launch_pairs_s<32>(c); break;
+                    }
+                } else if (c->pair_mode == 1) {
                     switch (c->pair_G) {
                     case 4: launch_pairs_q<4>(c); break;
                     case 8: launch_pairs_q<8>(c); break;

@@ -540,8 +540,9 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
     // one camera pair; G follows the mean run length so that a lane streams ~PAIR_TPL triples before the
     // (shuffle) reduction -- 4..8 for the synthetic ring (117 triples / pair), 32 for BAL (~10^3 / pair)
     // pair_mode 0 (default): a lane per triple; 1: the lanes of a group work as quads (four lanes per triple, a 3x3
-    // quadrant of the block each), a chunk is <= (G/4)*PAIR_TPQ triples; 2: row sweep.  PSBA_PAIR_MODE selects
-    // the two measured-and-slower variants
+    // quadrant of the block each), a chunk is <= (G/4)*PAIR_TPQ triples; 2: row sweep; 3: lane per triple with the
+    // operands fetched cooperatively through a per-warp stage.  PSBA_PAIR_MODE selects the measured-and-slower
+    // variants
     c->pair_mode = 0;
     if (getenv("PSBA_PAIR_MODE")) c->pair_mode = atoi(getenv("PSBA_PAIR_MODE"));
     long long PCH;

@@ -352,9 +352,9 @@ def _check_try_against_oracle(prob, G):
     return O
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "2"])
+@pytest.mark.parametrize("mode", ["0", "1", "2", "3"])
 def test_pair_pass_variants_agree_with_oracle(mode, monkeypatch):
-    """PSBA_PAIR_MODE selects the pair pass: lane per triple (default), quad per triple, row sweep.  All three must
+    """PSBA_PAIR_MODE selects the pair pass: lane per triple, quad per triple, row sweep, staged cooperative fetch.  All must
     give the reference's S and ea (compute_S.cl / compute_ea.cl) and the same LM trajectory."""
     from psba_b200 import synth
     monkeypatch.setenv("PSBA_PAIR_MODE", mode)
