@@ -22,6 +22,7 @@
 #ifndef PSBA_B200_H
 #define PSBA_B200_H
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -211,6 +212,13 @@ void psba_comm_finalize(void);
  * whose per-point observation counts are given by iidx (balanced by observation count) */
 void psba_local_range(int n3Dpts, int n2Dprojs, const int *iidx, int rank, int nranks,
                       int *p0, int *p1, int *o0, int *o1);
+
+/* Page-locked host memory for the arrays handed to fill_initBuffer2 / fill_idxBuffer / get_params: the reference's
+ * reader mallocs them (PSBA/readparams.cpp:470-500, emalloc in PSBA/misc.cpp:135-146); uploads from pageable memory run
+ * at ~5 GB/s, from page-locked memory at the PCIe rate.  Any host pointer is accepted by the ABI; these two are a
+ * convenience for callers that own the allocation. */
+void *psba_host_alloc(size_t bytes);
+void psba_host_free(void *p);
 
 const char *psba_version(void);
 

@@ -57,6 +57,9 @@ def lib():
     L.psba_fill_initBuffer2.argtypes = dims + [_dp, _dp, _dp, _dp, _dp]
     L.psba_fill_idxBuffer.argtypes = [vp, i, i, i, _ip, _ip]
     L.psba_release_buffer.argtypes = [vp]
+    L.psba_host_alloc.restype = vp
+    L.psba_host_alloc.argtypes = [C.c_size_t]
+    L.psba_host_free.argtypes = [vp]
     L.psba_compute_exQT.restype = d
     L.psba_compute_exQT.argtypes = dims + [i, _dp]
     L.psba_compute_jacobiQT.argtypes = dims + [_dp, _dp]
@@ -186,6 +189,42 @@ def local_range(n, o, iidx, rank, nranks):
     a = np.ascontiguousarray(iidx, dtype=np.int32)
     L.psba_local_range(n, o, _i(a), rank, nranks, *[C.byref(x) for x in v])
     return tuple(x.value for x in v)
+
+
+class _Pinned(np.ndarray):
+    """numpy view of page-locked memory from psba_host_alloc; the block is freed with the last view"""
+
+
+_pinned_blocks = {}
+
+
+def pinned_array(src):
+    """Copy of `src` (C-contiguous) in page-locked host memory (psba_host_alloc): uploads and downloads through the
+    ABI then run at the PCIe rate instead of the pageable-memory rate."""
+    src = np.ascontiguousarray(src)
+    L = lib()
+    ptr = L.psba_host_alloc(max(src.nbytes, 16))
+    buf = (C.c_char * max(src.nbytes, 16)).from_address(ptr)
+    out = np.frombuffer(buf, dtype=src.dtype, count=src.size).reshape(src.shape)
+    out[...] = src
+    _pinned_blocks[ptr] = buf
+    return out
+
+
+def pinned_problem(prob):
+    """the problem dictionary with every array the engine uploads moved to page-locked memory"""
+    q = dict(prob)
+    for k, t in (("K", np.float64), ("impts", np.float64), ("initrot", np.float64), ("cams", np.float64), ("pts", np.float64),
+                 ("iidx", np.int32), ("jidx", np.int32)):
+        q[k] = pinned_array(np.ascontiguousarray(prob[k], dtype=t))
+    return q
+
+
+def free_pinned():
+    L = lib()
+    for ptr in list(_pinned_blocks):
+        del _pinned_blocks[ptr]
+        L.psba_host_free(ptr)
 
 
 class PSBA:
@@ -365,9 +404,10 @@ class PSBA:
         a = np.ascontiguousarray(lams, dtype=np.float64)
         self.L.psba_force_lambda(self.h, _d(a), a.size)
 
-    def get_params(self, params=PARAMS_CUR):
-        cams = np.zeros((self.m, 6))
-        pts = np.zeros((self.n_loc, 3))
+    def get_params(self, params=PARAMS_CUR, out=None):
+        """refined cameras (m x 6) and this rank's points; `out` = (cams, pts) arrays to fill (e.g. page-locked ones)"""
+        cams, pts = out if out is not None else (np.zeros((self.m, 6)), np.zeros((self.n_loc, 3)))
+        assert cams.shape == (self.m, 6) and pts.shape == (self.n_loc, 3) and cams.flags.c_contiguous and pts.flags.c_contiguous
         self.L.psba_get_params(self.h, params, _d(cams), _d(pts))
         return cams, pts
 

@@ -51,6 +51,14 @@ template <class T> static T *dalloc(psba_ctx *c, size_t n)
     return (T *)psba_dev_alloc(c, std::max<size_t>(n, 1) * sizeof(T), true);
 }
 
+extern "C" void *psba_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    CUDA_CHECK(cudaHostAlloc(&p, std::max<size_t>(bytes, 16), cudaHostAllocDefault));
+    return p;
+}
+extern "C" void psba_host_free(void *p) { if (p) CUDA_CHECK(cudaFreeHost(p)); }
+
 extern "C" const char *psba_version(void) { return "psba_b200 0.1 (sm_100a, FP64)"; }
 
 extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3Dpts, int n2Dprojs)
