@@ -669,6 +669,257 @@ static void launch_rows(psba_ctx *c)
                                                           c->vis_desc, c->rseg_runs, c->tri_meta, c->W, c->Vinv, c->g + c->N, c->pair_part);
 }
 
+
+// ---- Row sweep WITHOUT CTA-wide barriers (PSBA_PAIR_MODE=4; measured 0.99 ms against 1.03 ms).  Same tables and the same order of sums as
+// k_schur_rows; what changes is who waits for whom.  Warp 0 is the PRODUCER: it copies the blocks of the next chunk of
+// visits (eight lanes per block: 128 contiguous bytes, then the ninth piece), Vinv_i and gb_i of every visit into
+// the other half of a two-stage pool with asynchronous copies whose completion arrives on the stage's `full`
+// mbarrier, and accumulates the diagonal pair of the current chunk.  The seven PAIR warps wait on `full`, consume
+// their triples of the chunk at their own pace (Y_ik = W_ik Vinv_i is formed on the fly from the visit's own staged
+// block: no Y pass, no shared Y entries) and arrive on the stage's `empty` mbarrier; a fast warp is up to a chunk
+// ahead of a slow one.  Nothing in the loop is a __syncthreads.
+#define FLOW_NT 256
+#define FLOW_REC 10                                            // doubles per visit record at the top of a stage: Vinv (6), gb (3), pad
+template <int FLOW_B, int FLOW_S, int FLOW_ML>
+__global__ void __launch_bounds__(FLOW_NT, 2)
+k_schur_flow(const int *__restrict__ seg_row, const int2 *__restrict__ seg_chunks, const int *__restrict__ seg_slot_base,
+             const int *__restrict__ row_pair0, const int4 *__restrict__ chunk_desc, const int4 *__restrict__ vis_desc,
+             const int *__restrict__ blk_src, const int2 *__restrict__ runs, const unsigned *__restrict__ tri_meta,
+             const double *__restrict__ W, const double *__restrict__ Vinv, const double *__restrict__ gb, double *__restrict__ part)
+{
+    constexpr int MAXB = FLOW_B + FLOW_ML + 2;                 // staged blocks per chunk
+    constexpr int POOL = MAXB * 144;                           // blocks from the bottom, visit records from the top
+    constexpr int NBR = (MAXB + 31) / 32;                      // block-source registers per producer lane
+    constexpr int NVR = (MAXB / 3 + 1 + 31) / 32;              // visits per producer lane
+    constexpr int NPW = FLOW_NT / 32 - 2;                      // pair warps (warp 0: producer, warp 1: diagonal pair)
+    extern __shared__ __align__(128) unsigned char pool[];
+    __shared__ __align__(8) unsigned long long full[FLOW_S], empty[FLOW_S];
+    const int seg = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k = __ldg(seg_row + seg);
+    const int2 cr = __ldg(seg_chunks + seg);
+    const int nch = cr.y - cr.x;
+    const int pair0 = __ldg(row_pair0 + k), nslot = __ldg(row_pair0 + k + 1) - pair0;      // the diagonal is the last slot
+    const int sbase = __ldg(seg_slot_base + seg);
+    if (tid == 0) {
+        for (int q = 0; q < FLOW_S; ++q) { mbar_init(&full[q], 32); mbar_init(&empty[q], NPW + 1); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    double acc[27];
+#pragma unroll
+    for (int q = 0; q < 27; ++q) acc[q] = 0.0;
+    const int4 zero4 = make_int4(0, 0, 0, 0);
+
+    if (warp == 0) {
+        // ================= producer =================
+        int srcr[NBR];                                         // observation behind block lane + 32 r of the chunk to issue
+        int pt[NVR];                                           // point of visit lane + 32 r of the chunk to issue
+        auto fetch = [&](const int4 &cd) {                     // what the issue of a chunk needs, one chunk ahead
+#pragma unroll
+            for (int r = 0; r < NBR; ++r) srcr[r] = lane + 32 * r < cd.z ? __ldg(blk_src + cd.w + lane + 32 * r) : 0;
+#pragma unroll
+            for (int r = 0; r < NVR; ++r) pt[r] = lane + 32 * r < cd.y ? __ldg(vis_desc + cd.x + lane + 32 * r).w : 0;
+        };
+        auto issue = [&](const int4 &cd, int st) {
+            unsigned char *pl = pool + st * POOL;
+            const int sub8 = lane & 7, blk4 = lane >> 3;
+#pragma unroll
+            for (int r = 0; r < NBR; ++r) {                    // blocks 32 r .. 32 r + 31: eight instructions of four blocks
+                if (32 * r < cd.z) {
+#pragma unroll
+                    for (int gq = 0; gq < 8; ++gq) {
+                        const int b = 32 * r + 4 * gq + blk4;
+                        const int so = __shfl_sync(0xffffffffu, srcr[r], 4 * gq + blk4);
+                        if (b < cd.z) cp_async16(pl + b * 144 + sub8 * 16, reinterpret_cast<const char *>(W + (size_t)so * 18) + sub8 * 16);
+                    }
+                    const int b = 32 * r + lane;               // ninth piece of this lane's own block
+                    if (b < cd.z) cp_async16(pl + b * 144 + 128, reinterpret_cast<const char *>(W + (size_t)srcr[r] * 18) + 128);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < NVR; ++r) {
+                const int e = lane + 32 * r;
+                if (e < cd.y) {
+                    double *rec = reinterpret_cast<double *>(pl + POOL) - (e + 1) * FLOW_REC;
+                    const double *vp = Vinv + (size_t)pt[r] * 6, *gp = gb + (size_t)pt[r] * 3;
+                    cp_async16(rec, vp); cp_async16(rec + 2, vp + 2); cp_async16(rec + 4, vp + 4);
+                    cp_async8(rec + 6, gp); cp_async8(rec + 7, gp + 1); cp_async8(rec + 8, gp + 2);
+                }
+            }
+            cp_async_mbar_arrive(&full[st]);
+        };
+        int4 cd1 = nch > 0 ? __ldg(chunk_desc + cr.x) : zero4;
+        int4 cd2 = nch > 1 ? __ldg(chunk_desc + cr.x + 1) : zero4;
+        fetch(cd1);
+        for (int j = 0; j < nch; ++j) {                        // runs up to FLOW_S chunks ahead of the slowest consumer
+            const int st = j % FLOW_S;
+            if (j >= FLOW_S) mbar_wait(&empty[st], (j / FLOW_S - 1) & 1);                    // chunk j - FLOW_S has been consumed by every warp
+            issue(cd1, st);
+            const int4 cd3 = j + 2 < nch ? __ldg(chunk_desc + cr.x + j + 2) : zero4;
+            if (j + 1 < nch) fetch(cd2);
+            cd1 = cd2; cd2 = cd3;
+        }
+        cp_async_wait<0>();
+        return;
+    }
+    if (warp == 1) {
+        // ================= diagonal pair: lanes stride the visits of a chunk =================
+        int4 cdn = nch > 0 ? __ldg(chunk_desc + cr.x) : zero4;
+        int own_n[NVR], nv_n = cdn.y;
+#pragma unroll
+        for (int r = 0; r < NVR; ++r) { const int4 d = lane + 32 * r < cdn.y ? __ldg(vis_desc + cdn.x + lane + 32 * r) : zero4; own_n[r] = d.z + d.y - 1; }
+        for (int c = 0; c < nch; ++c) {
+            const int st = c % FLOW_S;
+            int own[NVR]; const int nv = nv_n;
+#pragma unroll
+            for (int r = 0; r < NVR; ++r) own[r] = own_n[r];
+            if (c + 1 < nch) {                                 // next chunk's own-block slots fly during this chunk
+                cdn = __ldg(chunk_desc + cr.x + c + 1); nv_n = cdn.y;
+#pragma unroll
+                for (int r = 0; r < NVR; ++r) { const int4 d = lane + 32 * r < cdn.y ? __ldg(vis_desc + cdn.x + lane + 32 * r) : zero4; own_n[r] = d.z + d.y - 1; }
+            }
+            mbar_wait(&full[st], (c / FLOW_S) & 1);
+            const unsigned char *pl = pool + st * POOL;
+            const double *stage = reinterpret_cast<const double *>(pl);
+            const double *top = reinterpret_cast<const double *>(pl + POOL);
+#pragma unroll 1
+            for (int r = 0; r < NVR; ++r) {
+                const int e = lane + 32 * r;
+                if (e < nv) {
+                    const double2 *rp = reinterpret_cast<const double2 *>(top - (e + 1) * FLOW_REC);
+                    const double2 a01 = rp[0], a23 = rp[1], a45 = rp[2], g01 = rp[3];
+                    const double g2 = reinterpret_cast<const double *>(rp)[8];
+                    const double i00 = a01.x, i10 = a01.y, i20 = a23.x, i11 = a23.y, i21 = a45.x, i22 = a45.y;
+                    const double2 *wp = reinterpret_cast<const double2 *>(stage + own[r] * 18);
+                    double w[18], y[18];
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) { const double2 b = wp[q]; w[2 * q] = b.x; w[2 * q + 1] = b.y; }
+#pragma unroll
+                    for (int rr = 0; rr < 6; ++rr) {
+                        const double w0 = w[rr * 3], w1 = w[rr * 3 + 1], w2 = w[rr * 3 + 2];
+                        y[rr * 3] = w0 * i00 + w1 * i10 + w2 * i20;
+                        y[rr * 3 + 1] = w0 * i10 + w1 * i11 + w2 * i21;
+                        y[rr * 3 + 2] = w0 * i20 + w1 * i21 + w2 * i22;
+                        acc[21 + rr] += y[rr * 3] * g01.x + y[rr * 3 + 1] * g01.y + y[rr * 3 + 2] * g2;
+                    }
+                    int q = 0;
+#pragma unroll
+                    for (int rr = 0; rr < 6; ++rr)
+#pragma unroll
+                        for (int cc = 0; cc <= rr; ++cc, ++q)
+                            acc[q] += y[rr * 3] * w[cc * 3] + y[rr * 3 + 1] * w[cc * 3 + 1] + y[rr * 3 + 2] * w[cc * 3 + 2];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+#pragma unroll
+        for (int w = 16; w > 0; w >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 27; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], w);
+        }
+        double *out = part + (size_t)(sbase + nslot - 1) * 42;
+        int q = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int cc = 0; cc <= r; ++cc, ++q)
+                if (lane == (q & 31)) { out[r * 6 + cc] = acc[q]; out[cc * 6 + r] = acc[q]; }
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+            if (lane == r) out[36 + r] = acc[21 + r];
+        return;
+    }
+
+    // ================= pair warps =================
+    constexpr int NG = (FLOW_NT - 64) / 4, NH = 3;
+    const int grp = (tid - 64) >> 2, qa = (tid >> 1) & 1, qb = tid & 1;
+    int cur[NH], rend[NH];
+    unsigned m0[NH], m1[NH], m2[NH];
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+        cur[h] = rend[h] = 0; m0[h] = m1[h] = m2[h] = 0xffffffffu;                            // never a chunk number
+        const int slot = grp + h * NG;
+        if (slot < nslot - 1) {
+            const int2 r = __ldg(runs + sbase + slot);
+            cur[h] = r.x; rend[h] = r.y;
+            if (cur[h] < rend[h]) m0[h] = __ldg(tri_meta + cur[h]);
+            if (cur[h] + 1 < rend[h]) m1[h] = __ldg(tri_meta + cur[h] + 1);
+            if (cur[h] + 2 < rend[h]) m2[h] = __ldg(tri_meta + cur[h] + 2);
+        }
+    }
+    for (int c = 0; c < nch; ++c) {
+        const int st = c % FLOW_S;
+        mbar_wait(&full[st], (c / FLOW_S) & 1);
+        const unsigned char *pl = pool + st * POOL;
+        const double *stage = reinterpret_cast<const double *>(pl);
+        const double *top = reinterpret_cast<const double *>(pl + POOL);
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+            while ((m0[h] >> 26) == (unsigned)c) {
+                const unsigned mt = m0[h];
+                m0[h] = m1[h]; m1[h] = m2[h];
+                m2[h] = cur[h] + 3 < rend[h] ? __ldg(tri_meta + cur[h] + 3) : 0xffffffffu;
+                ++cur[h];
+                const double2 *rp = reinterpret_cast<const double2 *>(top - (((mt >> 18) & 255u) + 1) * FLOW_REC);
+                const double2 a01 = rp[0], a23 = rp[1], a45 = rp[2];
+                const double i00 = a01.x, i10 = a01.y, i20 = a23.x, i11 = a23.y, i21 = a45.x, i22 = a45.y;
+                const double *wap = stage + (mt & 511u) * 18 + 9 * qa;                       // rows 3qa.. of the visit's own block
+                const double *wbp = stage + ((mt >> 9) & 511u) * 18 + 9 * qb;                // rows 3qb.. of W_il
+                double wa[9], wb[9];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) { wa[q] = wap[q]; wb[q] = wbp[q]; }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const double w0 = wa[r * 3], w1 = wa[r * 3 + 1], w2 = wa[r * 3 + 2];
+                    const double y0 = w0 * i00 + w1 * i10 + w2 * i20;
+                    const double y1 = w0 * i10 + w1 * i11 + w2 * i21;
+                    const double y2 = w0 * i20 + w1 * i21 + w2 * i22;
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) {
+                        double t = acc[h * 9 + r * 3 + cc];
+                        t = fma(y0, wb[cc * 3], t); t = fma(y1, wb[cc * 3 + 1], t); t = fma(y2, wb[cc * 3 + 2], t);
+                        acc[h * 9 + r * 3 + cc] = t;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+    }
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+        const int slot = grp + h * NG;
+        if (slot < nslot - 1) {
+            double *out = part + (size_t)(sbase + slot) * 42;
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) out[(3 * qa + r) * 6 + 3 * qb + cc] = acc[h * 9 + r * 3 + cc];
+        }
+    }
+}
+
+template <int FB, int FS, int FML>
+static void launch_flow_t(psba_ctx *c)
+{
+    static bool attr_set = false;
+    const int dyn = FS * (FB + FML + 2) * 144;
+    if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_schur_flow<FB, FS, FML>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)); attr_set = true; }
+    k_schur_flow<FB, FS, FML><<<c->n_rseg, FLOW_NT, dyn, c->stream>>>(c->rseg_row, c->rseg_chunks, c->rseg_slot_base, c->row_pair0, c->rchunk_desc, c->vis_desc,
+                                                       c->rblk_src, c->rseg_runs, c->tri_meta, c->W, c->Vinv, c->g + c->N, c->pair_part);
+}
+static void launch_flow(psba_ctx *c)
+{
+    static const int deep = getenv("PSBA_FLOW_DEEP") ? atoi(getenv("PSBA_FLOW_DEEP")) : 0;
+    if (c->row_budget == 304 && deep) launch_flow_t<304, 4, 64>(c);
+    else if (c->row_budget == 192 && deep) launch_flow_t<192, 6, 32>(c);
+    else if (c->row_budget == 304) launch_flow_t<304, 2, 64>(c);
+    else if (c->row_budget == 192) launch_flow_t<192, 3, 32>(c);
+    else if (c->row_budget == 144) launch_flow_t<144, 4, 32>(c);
+    else launch_flow_t<112, 5, 32>(c);
+}
+
 // per pair block of the row sweep: fixed-order sum over the segments of its row, then as k_S_finalize
 __global__ void k_S_finalize_rows(int n_pair, const int *__restrict__ pair_k, const int *__restrict__ pair_l,
                                   const int *__restrict__ row_pair0, const int *__restrict__ row_seg_ptr,
@@ -733,7 +984,8 @@ void psba_launch_schur(psba_ctx *c, double mu)
     if (c->rows_ok) {
         if (c->n_rseg > 0)
             PROF(c, KID_SCHUR_PAIRS) {
-                if (c->rows_nt == 256 && c->row_budget == 304) launch_rows<256, 304>(c);
+                if (c->pair_mode == 4) launch_flow(c);
+                else if (c->rows_nt == 256 && c->row_budget == 304) launch_rows<256, 304>(c);
                 else if (c->rows_nt == 256) launch_rows<256, 640>(c);
                 else if (c->row_budget == 304) launch_rows<544, 304>(c);
                 else launch_rows<544, 640>(c);

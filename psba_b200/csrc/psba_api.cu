@@ -88,7 +88,7 @@ extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3D
     for (int k = 0; k < KID_COUNT; ++k) { c->prof_ms[k] = 0; c->prof_n[k] = 0; }
     c->comm = nullptr;
     { int dev = 0; CUDA_CHECK(cudaGetDevice(&dev)); CUDA_CHECK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, dev)); }
-    c->d_small_list = c->d_big_list = nullptr; c->n_small = c->n_big = 0;
+    c->d_small_list = c->d_big_list = nullptr; c->n_small = c->n_big = 0; c->rblk_src = nullptr;
     c->rows_ok = false; c->rchunk_desc = nullptr; c->rchunk_first = nullptr; c->vis_desc = nullptr; c->tri_meta = nullptr; c->rseg_row = nullptr; c->rseg_chunks = nullptr;
     c->rseg_slot_base = nullptr; c->rseg_runs = nullptr; c->row_pair0 = nullptr; c->row_seg_ptr = nullptr; c->n_rchunk = c->n_rseg = c->n_rpart = 0;
     c->chol_pdl = !(getenv("PSBA_NO_PDL") && atoi(getenv("PSBA_NO_PDL")));
@@ -199,7 +199,7 @@ extern "C" void psba_release_buffer(psba_ctx *c)
                     c->d_psrc_ptr, c->d_psrc, c->d_b_J, c->d_b_sptr, c->d_b_slot, c->d_def_I, c->d_def_J, c->d_def_sptr, c->d_def_src,
                     c->d_step_panels, c->d_crit_desc, c->d_def_desc, c->d_crit_src, c->d_def_srcs, c->d_bw_order, c->d_xdone, c->contrib, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
                     c->Sdense, c->Sdense_aux, c->chol_aux, c->chol_diag, c->chol_E, c->d_part, c->d_scal, c->P_U, c->P_B, c->P,
-                    c->tmpA, c->tmpB, c->rchunk_desc, c->rchunk_first, c->vis_desc, c->tri_meta, c->rseg_row, c->rseg_chunks, c->rseg_slot_base, c->rseg_runs,
+                    c->tmpA, c->tmpB, c->rblk_src, c->rchunk_desc, c->rchunk_first, c->vis_desc, c->tri_meta, c->rseg_row, c->rseg_chunks, c->rseg_slot_base, c->rseg_runs,
                     c->row_pair0, c->row_seg_ptr};
     for (void *p : ptrs) psba_dev_free(c, p);
     psba_dev_free(c, c->stage_impts); psba_dev_free(c, c->stage_pts);

@@ -76,7 +76,7 @@ struct psba_ctx {
     int n_pair; int *pair_k, *pair_l;          // pair blocks present GLOBALLY (all ranks agree)
     int *pair_chunk_ptr;                        // n_pair+1
     int pair_G;                                 // lanes per chunk in the pair pass (1..32)
-    int pair_mode;                              // 0: lane per triple, 1: quad per triple (default), 2: row sweep
+    int pair_mode;                              // 0: lane per triple (default), 1: quad per triple, 2: row sweep, 3: staged fetch, 4: row sweep without CTA barriers
     int n_pchunk; int *pchunk_pair; long long *pchunk_beg, *pchunk_end;
     // ---- row-sweep pair pass (k_schur_rows): CTA = segment of one camera row, thread = pair of that row
     bool rows_ok;                   // false: a prefix or a row exceeds the kernel's caps, the pair-major kernel runs
@@ -84,6 +84,7 @@ struct psba_ctx {
     int rows_nt;                    // threads per CTA (288: <= 128 off-diagonal pairs per row, else 544)
     int n_rchunk, n_rseg, n_rpart;  // chunks, segments (CTAs), partial slots (sum of pairs-per-row over segments)
     int *rchunk_first;              // n_rchunk+1: first visit (camera-major position) of every chunk
+    int *rblk_src;                  // flow kernel: observation behind every staged block, staging order
     int4 *rchunk_desc;              // per chunk: first visit, visits, staged blocks
     int4 *vis_desc;                 // per visit: first observation of the point, prefix length, stage slot in the chunk, point
     unsigned *tri_meta;             // per triple: chunk in segment << 18 | visit in chunk << 10 | stage slot

@@ -151,7 +151,7 @@ __global__ void k_visit_len(int o, const int *__restrict__ cam_obs, const int *_
     const int a = cam_obs[v];
     const int l = a - pt_ptr[iidx[a]] + 1;
     len[v] = l; cam_pos[a] = v;
-    if (l > ROW_MAXLEN) atomicMax(maxlen, l);
+    atomicMax(maxlen, l);
 }
 
 __device__ __forceinline__ int row_chunk_of(int v, int row_first, const int *__restrict__ vis_off, int budget)
@@ -189,18 +189,29 @@ __global__ void k_vis_desc(int RB, int o, const int *__restrict__ cam_obs, const
     desc[v] = make_int4(pt_ptr[i], vis_off[v + 1] - vis_off[v], vis_off[v] - vis_off[vf], i);
 }
 
+// observation behind every staged block, in staging order (visit-major; the blocks of a visit are the observations
+// pt_ptr[i] .. own observation of its point)
+__global__ void k_block_src(int o, const int4 *__restrict__ desc, const int *__restrict__ vis_off, int *__restrict__ src)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= o) return;
+    const int4 d = desc[v];
+    const int b0 = vis_off[v];
+    for (int j = 0; j < d.y; ++j) src[b0 + j] = d.x + j;
+}
+
 // one 16-byte record per chunk: first visit, visits, staged blocks
-__global__ void k_chunk_desc(int n_rchunk, const int *__restrict__ chunk_first, const int4 *__restrict__ desc, int4 *__restrict__ cdesc)
+__global__ void k_chunk_desc(int n_rchunk, const int *__restrict__ chunk_first, const int4 *__restrict__ desc, const int *__restrict__ vis_off, int4 *__restrict__ cdesc)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_rchunk) return;
     const int v0 = chunk_first[c], v1 = chunk_first[c + 1];
     const int4 l = desc[v1 - 1];
-    cdesc[c] = make_int4(v0, v1 - v0, l.z + l.y, 0);
+    cdesc[c] = make_int4(v0, v1 - v0, l.z + l.y, vis_off[v0]);       // first visit, visits, staged blocks, rank of the first staged block
 }
 
 // per triple (pair-sorted): where the row kernel finds its operands
-__global__ void k_tri_meta(int RB, long long ntri, int SC, const int *__restrict__ tri_oa, const int *__restrict__ tri_ob, const int *__restrict__ cam_pos,
+__global__ void k_tri_meta(int packing, int RB, long long ntri, int SC, const int *__restrict__ tri_oa, const int *__restrict__ tri_ob, const int *__restrict__ cam_pos,
                            const int *__restrict__ jidx, const int *__restrict__ cam_ptr, const int *__restrict__ vis_off,
                            const int *__restrict__ row_chunk_base, const int *__restrict__ chunk_first, const int4 *__restrict__ desc,
                            unsigned *__restrict__ meta)
@@ -212,7 +223,9 @@ __global__ void k_tri_meta(int RB, long long ntri, int SC, const int *__restrict
     const int cir = row_chunk_of(v, rb, vis_off, RB);
     const int vf = chunk_first[row_chunk_base[k] + cir];
     const int4 d = desc[v];
-    meta[t] = ((unsigned)(cir % SC) << 18) | ((unsigned)(v - vf) << 10) | (unsigned)(d.z + (bo - d.x));
+    if (packing == 0) meta[t] = ((unsigned)(cir % SC) << 18) | ((unsigned)(v - vf) << 10) | (unsigned)(d.z + (bo - d.x));
+    else               // flow kernel: chunk in segment (6) | visit in chunk (8) | stage slot of W_il (9) | stage slot of the visit's own block (9)
+        meta[t] = ((unsigned)(cir % SC) << 26) | ((unsigned)(v - vf) << 18) | ((unsigned)(d.z + (bo - d.x)) << 9) | (unsigned)(d.z + d.y - 1);
 }
 
 // triple range of every (segment, off-diagonal slot): the triples of the pair whose visit lies in the segment
@@ -311,7 +324,7 @@ static void build_row_sweep(psba_ctx *c, const long long *tptr, const std::vecto
     cudaStream_t st = c->stream;
     const int m = c->m, o = c->o;
     c->rows_ok = false; c->n_rchunk = c->n_rseg = c->n_rpart = 0;
-    if (c->pair_mode != 2) return;
+    if (c->pair_mode != 2 && c->pair_mode != 4) return;
     // pairs of a row are contiguous (sorted by k, then l; the diagonal is the last one)
     std::vector<int> row_pair0((size_t)m + 1, 0);
     {
@@ -322,7 +335,14 @@ static void build_row_sweep(psba_ctx *c, const long long *tptr, const std::vecto
     for (int k = 0; k < m; ++k) max_off = std::max(max_off, row_pair0[k + 1] - row_pair0[k] - 1);
     if (max_off > 384 || o == 0) return;
     int RB = 304;
-    if (getenv("PSBA_ROW_BUDGET") && atoi(getenv("PSBA_ROW_BUDGET")) == 640) RB = 640;
+    if (getenv("PSBA_ROW_BUDGET") && atoi(getenv("PSBA_ROW_BUDGET")) == 640 && c->pair_mode == 2) RB = 640;
+    int maxlen_cap = ROW_MAXLEN;
+    if (c->pair_mode == 4) {                              // flow kernel: (budget, stages, longest prefix) = (304,2,64) (192,3,32) (144,4,32) (112,5,32)
+        RB = 192;
+        if (getenv("PSBA_FLOW_B")) RB = atoi(getenv("PSBA_FLOW_B"));
+        if (RB != 304 && RB != 192 && RB != 144 && RB != 112) RB = 192;
+        maxlen_cap = RB == 304 ? 64 : 32;
+    }
     c->row_budget = RB;
     int *len = salloc<int>(c, (size_t)o + 1), *cam_pos = salloc<int>(c, o), *vis_off = salloc<int>(c, (size_t)o + 1);
     int *maxlen = salloc<int>(c, 1), *cam_ptr = supload(c, cptr);
@@ -344,14 +364,14 @@ static void build_row_sweep(psba_ctx *c, const long long *tptr, const std::vecto
     CUDA_CHECK(cudaMemcpyAsync(&hmax, maxlen, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     psba_dev_free(c, nch); psba_dev_free(c, maxlen); psba_dev_free(c, len);
-    if (hmax > ROW_MAXLEN) { psba_dev_free(c, cam_pos); psba_dev_free(c, vis_off); psba_dev_free(c, cam_ptr); return; }
+    if (hmax > maxlen_cap) { psba_dev_free(c, cam_pos); psba_dev_free(c, vis_off); psba_dev_free(c, cam_ptr); return; }
     std::vector<int> chunk_base((size_t)m + 1, 0);
     for (int k = 0; k < m; ++k) chunk_base[k + 1] = chunk_base[k] + hnch[k];
     c->n_rchunk = chunk_base[m];
     // segments (one CTA each): SC consecutive chunks of one row
     int SC = std::max(1, cdiv(c->n_rchunk, 8 * c->n_sm));
     if (getenv("PSBA_ROW_SEG")) SC = std::max(1, atoi(getenv("PSBA_ROW_SEG")));
-    SC = std::min(SC, 1 << 14);
+    SC = std::min(SC, c->pair_mode == 4 ? 63 : (1 << 14));      // mode 4: 6 bits, 63 is the "no triple" mark
     std::vector<int> seg_row, seg_slot_base, row_seg_ptr((size_t)m + 1, 0);
     std::vector<int2> seg_chunks;
     int nslot_total = 0;
@@ -365,7 +385,9 @@ static void build_row_sweep(psba_ctx *c, const long long *tptr, const std::vecto
         row_seg_ptr[k + 1] = (int)seg_row.size();
     }
     c->n_rseg = (int)seg_row.size(); c->n_rpart = nslot_total;
-    c->rows_nt = max_off <= 168 ? 256 : 544;       // (NT - 32) / 4 groups of four lanes, three pairs per group
+    c->rows_nt = max_off <= 168 ? 256 : 544;
+    // (NT - 32) / 4 groups of four lanes, three pairs per group; the flow kernel (mode 4) exists in the small size only
+    if (c->pair_mode == 4 && max_off > 144) { c->n_rseg = c->n_rpart = 0; psba_dev_free(c, cam_pos); psba_dev_free(c, vis_off); psba_dev_free(c, cam_ptr); return; }
     int *row_chunk_base = supload(c, chunk_base);
     c->rchunk_first = salloc<int>(c, (size_t)c->n_rchunk + 1);
     k_chunk_first<<<cdiv(o, 256), 256, 0, st>>>(RB, o, c->cam_obs, c->jidx, cam_ptr, vis_off, row_chunk_base, c->n_rchunk, c->rchunk_first);
@@ -373,9 +395,15 @@ static void build_row_sweep(psba_ctx *c, const long long *tptr, const std::vecto
     k_vis_desc<<<cdiv(o, 256), 256, 0, st>>>(RB, o, c->cam_obs, c->iidx, c->jidx, c->pt_ptr, cam_ptr, vis_off, row_chunk_base, c->rchunk_first, c->vis_desc);
     c->rchunk_desc = salloc<int4>(c, (size_t)c->n_rchunk + 4);
     CUDA_CHECK(cudaMemsetAsync(c->rchunk_desc, 0, ((size_t)c->n_rchunk + 4) * sizeof(int4), st));
-    if (c->n_rchunk) k_chunk_desc<<<cdiv(c->n_rchunk, 256), 256, 0, st>>>(c->n_rchunk, c->rchunk_first, c->vis_desc, c->rchunk_desc);
+    if (c->n_rchunk) k_chunk_desc<<<cdiv(c->n_rchunk, 256), 256, 0, st>>>(c->n_rchunk, c->rchunk_first, c->vis_desc, vis_off, c->rchunk_desc);
+    c->rblk_src = nullptr;
+    if (c->pair_mode == 4) {
+        c->rblk_src = salloc<int>(c, (size_t)c->ntri + 512);
+        CUDA_CHECK(cudaMemsetAsync(c->rblk_src, 0, ((size_t)c->ntri + 512) * sizeof(int), st));
+        k_block_src<<<cdiv(o, 256), 256, 0, st>>>(o, c->vis_desc, vis_off, c->rblk_src);
+    }
     c->tri_meta = salloc<unsigned>(c, (size_t)c->ntri + 4);
-    if (c->ntri) k_tri_meta<<<cdiv(c->ntri, 256), 256, 0, st>>>(RB, c->ntri, SC, c->tri_oa, c->tri_ob, cam_pos, c->jidx, cam_ptr, vis_off, row_chunk_base,
+    if (c->ntri) k_tri_meta<<<cdiv(c->ntri, 256), 256, 0, st>>>(c->pair_mode == 4 ? 1 : 0, RB, c->ntri, SC, c->tri_oa, c->tri_ob, cam_pos, c->jidx, cam_ptr, vis_off, row_chunk_base,
                                                               c->rchunk_first, c->vis_desc, c->tri_meta);
     c->rseg_row = supload(c, seg_row); c->rseg_chunks = supload(c, seg_chunks); c->rseg_slot_base = supload(c, seg_slot_base);
     c->row_pair0 = supload(c, row_pair0); c->row_seg_ptr = supload(c, row_seg_ptr);

@@ -352,7 +352,7 @@ def _check_try_against_oracle(prob, G):
     return O
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("mode", ["0", "1", "2", "3", "4"])
 def test_pair_pass_variants_agree_with_oracle(mode, monkeypatch):
     """PSBA_PAIR_MODE selects the pair pass: lane per triple, quad per triple, row sweep, staged cooperative fetch.  All must
     give the reference's S and ea (compute_S.cl / compute_ea.cl) and the same LM trajectory."""
@@ -360,7 +360,7 @@ def test_pair_pass_variants_agree_with_oracle(mode, monkeypatch):
     monkeypatch.setenv("PSBA_PAIR_MODE", mode)
     for prob in (synth.ring_problem(m=160, n=6000, d=4, w=12, seed=7), psba_b200.read_sba(*dataset_paths("54"))):
         G = psba_b200.PSBA(prob)
-        if mode == "2":
+        if mode in ("2", "4"):
             assert int(G.stat("rows_ok")) == 1 and int(G.stat("n_rseg")) > 0
         O = _check_try_against_oracle(prob, G)
         G.close()
