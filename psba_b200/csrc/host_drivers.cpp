@@ -23,17 +23,6 @@ static void trace(psba_ctx *c, int phase, double err, double rho, double mu, dou
     c->trace.push_back(r);
 }
 
-// ||p||^2 of a parameter set: cameras (replicated) + points (sharded)
-static double param_norm_sq(psba_ctx *c, int set)
-{
-    // the [N | 3n] layout helper works on contiguous vectors; cams and pts are separate buffers,
-    // so stage them through the scratch vector
-    CUDA_CHECK(cudaMemcpyAsync(c->UVdiag_scr, c->cams[set], (size_t)c->N * 8, cudaMemcpyDeviceToDevice, c->stream));
-    if (c->n) CUDA_CHECK(cudaMemcpyAsync(c->UVdiag_scr + c->N, c->pts[set], (size_t)c->n * 24, cudaMemcpyDeviceToDevice, c->stream));
-    double d[6];
-    psba_launch_dots(c, c->UVdiag_scr, c->UVdiag_scr, c->UVdiag_scr, d);
-    return d[0];
-}
 
 extern "C" int psba_levmar(psba_ctx *c, int cnp, int pnp, int mnp, int n3Dpts, int nCams, int n2Dprojs, double *finalErr)
 {

@@ -340,34 +340,8 @@ __device__ __forceinline__ void tile_stg(double *__restrict__ g, const double *s
     }
 }
 
-// 128 threads as an 8 x 16 grid: thread (tr = tid % 8, tc = tid / 8) owns rows 6tr..6tr+5, columns
-// 3tc..3tc+2 of a tile (a warp covers four adjacent column triples, so warps retire as the sweep advances).
-// acc = A * B^T (and acc2 = A2 * B^T when TWO) for 48x48 tiles in smem.
-template <bool TWO>
-__device__ __forceinline__ void tile_abt(const double *A, const double *A2, const double *B, double acc[6][3], double acc2[6][3])
-{
-    const int tr = threadIdx.x % 8, tc = threadIdx.x / 8;
-#pragma unroll
-    for (int p = 0; p < 6; ++p)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) { acc[p][q] = 0.0; if (TWO) acc2[p][q] = 0.0; }
-#pragma unroll 4
-    for (int k = 0; k < TS; ++k) {
-        double a[6], a2[6], b[3];
-#pragma unroll
-        for (int p = 0; p < 6; ++p) { a[p] = A[(tr * 6 + p) * LDT + k]; if (TWO) a2[p] = A2[(tr * 6 + p) * LDT + k]; }
-#pragma unroll
-        for (int q = 0; q < 3; ++q) b[q] = B[(tc * 3 + q) * LDT + k];
-#pragma unroll
-        for (int p = 0; p < 6; ++p)
-#pragma unroll
-            for (int q = 0; q < 3; ++q) { acc[p][q] += a[p] * b[q]; if (TWO) acc2[p][q] += a2[p] * b[q]; }
-    }
-}
-
-
 // ---- FP64 tensor-core product for the deferred updates ------------------------------------------------
-// The 6x3 register-blocked product reads 9 doubles from shared memory per 18 FMA and thread; ncu shows the leaf
+// A 6x3 register-blocked product (rounds 1a-1c) reads 9 doubles from shared memory per 18 FMA and thread; ncu showed the leaf
 // steps at 73 % of the L1 data pipe and 25 % of the FP64 pipe.  DMMA.8x8x4 (mma.sync m8n8k4 f64) takes one double
 // of A and one of B per lane for 256 FMA: a warp that owns a 24x24 block of the tile (3x3 fragments) loads 6
 // doubles per lane and k-step of 4 for 9 DMMA = 2 304 FMA.
@@ -519,7 +493,7 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
     else if ((int)blockIdx.x < ncrit + ndef) cd0 = __ldg(def_desc + (blockIdx.x - ncrit));
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (*status != 0) return;
-    const int tid = threadIdx.x, tr = tid % 8, tc = tid / 8;
+    const int tid = threadIdx.x;
     double *B0 = smem, *B1 = smem + TILE_SM;
 
     if ((int)blockIdx.x >= ncrit + ndef) {
