@@ -457,3 +457,23 @@ def test_indefinite_camera_system_is_reported_not_factored(key):
     res = G.try_step(1e-3 * mx)
     assert res["solve_status"] == 0.0 and np.isfinite(res["cost_new"]) and res["cost_new"] > 0
     G.close(); O.close()
+
+
+def test_page_locked_host_arrays_give_the_same_solve():
+    """psba_host_alloc / psba_host_free: the same problem handed over in page-locked arrays, parameters read back into
+    page-locked arrays -- identical trajectory and parameters (the ABI takes any host pointer)."""
+    prob = psba_b200.read_sba(*dataset_paths("54"))
+    G = psba_b200.PSBA(prob)
+    flag_a, fe_a = G.levmar()
+    cams_a, pts_a = G.get_params()
+    G.close()
+    hp = psba_b200.pinned_problem(prob)
+    G = psba_b200.PSBA(hp)
+    flag_b, fe_b = G.levmar()
+    out = (psba_b200.pinned_array(np.zeros((prob["m"], 6))), psba_b200.pinned_array(np.zeros((G.n_loc, 3))))
+    cams_b, pts_b = G.get_params(out=out)
+    G.close()
+    assert flag_a == flag_b and fe_a == fe_b
+    assert np.array_equal(cams_a, cams_b) and np.array_equal(pts_a, pts_b)
+    del hp, out, cams_b, pts_b
+    psba_b200.free_pinned()
