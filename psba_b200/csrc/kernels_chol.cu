@@ -190,7 +190,7 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
     for (auto &v : by_step) if (v.size() != 1) c->chain_schedule = false;
     // ---- task lists
     std::vector<int> critI, critK, psrc_ptr(1, 0), psrc;
-    std::vector<int> defI, defJ, def_sptr(1, 0), def_src, step_panels;
+    std::vector<int> defI, defJ, def_sptr(1, 0), def_src, def_cnt, step_panels;
     std::vector<int> bJ, b_sptr(1, 0), b_slot;
     std::vector<std::vector<int>> psrc_of(nt);
     for (int K = 0; K < nt; ++K) {
@@ -211,22 +211,29 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
         c->step_panel_ptr.push_back((int)step_panels.size());
         // deferred targets of the panels of step s-1: tiles (I,J) with J in a later step than s
         if (s > 0) {
-            std::vector<std::vector<int>> srcs;
-            std::vector<std::pair<int, int>> tgt;
+            // two passes over the same loops (count, then fill) into flat arrays: no per-target allocation
+            const int t0 = (int)defI.size();
             for (int P : by_step[s - 1])
                 for (size_t a = 0; a < rows[P].size(); ++a)
                     for (size_t b = 0; b <= a; ++b) {
                         const int I = rows[P][a], J = rows[P][b];
                         if (step[J] == s) continue;              // handled by the critical CTAs of panel J
                         const size_t key = (size_t)I * nt + J;
-                        if (stamp[key] != s) { stamp[key] = s; def_of[key] = (int)tgt.size(); tgt.push_back({I, J}); srcs.emplace_back(); }
-                        srcs[def_of[key]].push_back(P);
+                        if (stamp[key] != s) { stamp[key] = s; def_of[key] = (int)defI.size(); defI.push_back(I); defJ.push_back(J); def_cnt.push_back(0); }
+                        def_cnt[def_of[key]] += 1;
                     }
-            for (size_t t = 0; t < tgt.size(); ++t) {
-                defI.push_back(tgt[t].first); defJ.push_back(tgt[t].second);
-                def_src.insert(def_src.end(), srcs[t].begin(), srcs[t].end());
-                def_sptr.push_back((int)def_src.size());
-            }
+            const int t1 = (int)defI.size();
+            for (int t = t0; t < t1; ++t) def_sptr.push_back(def_sptr.back() + def_cnt[t]);
+            def_src.resize(def_sptr.back());
+            for (int t = t0; t < t1; ++t) def_cnt[t] = 0;
+            for (int P : by_step[s - 1])
+                for (size_t a = 0; a < rows[P].size(); ++a)
+                    for (size_t b = 0; b <= a; ++b) {
+                        const int I = rows[P][a], J = rows[P][b];
+                        if (step[J] == s) continue;
+                        const int t = def_of[(size_t)I * nt + J];
+                        def_src[def_sptr[t] + def_cnt[t]++] = P;
+                    }
         }
         c->step_def_ptr.push_back((int)defI.size());
         // right-hand-side tasks: b_J -= sum_P L_JP y_P for the panels P of step s-1 and rows J of later steps
