@@ -499,12 +499,15 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
     if ((int)blockIdx.x < ncrit) { cd0 = __ldg(crit_desc + 2 * blockIdx.x); cd1 = __ldg(crit_desc + 2 * blockIdx.x + 1); }
     else if ((int)blockIdx.x < ncrit + ndef) cd0 = __ldg(def_desc + (blockIdx.x - ncrit));
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (*status != 0) return;
+    // the status word of the earlier steps is loaded here and tested after the first tile loads have been issued:
+    // one L2 round trip less in front of every step
+    const int failed = *reinterpret_cast<volatile int *>(status);
     const int tid = threadIdx.x;
     double *B0 = smem, *B1 = smem + TILE_SM;
 
     if ((int)blockIdx.x >= ncrit + ndef) {
         // ---- right-hand side of a later panel:  b_J -= sum_P L_JP y_P  (ascending P)
+        if (failed) return;
         const int t = blockIdx.x - ncrit - ndef;
         if (tid < TS) {
             double sum = 0.0;
@@ -524,6 +527,7 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
             tile_ldg(ra, Stiles + (size_t)sl.x * TS * TS);
             tile_ldg(rb_, Stiles + (size_t)sl.y * TS * TS);
         }
+        if (failed) return;
         // warp w owns the 24x24 block (w / 2, w % 2) of the target: 3x3 DMMA fragments, two doubles per lane each
         const int wrp = tid >> 5, lane = tid & 31, rb = (wrp >> 1) * 24, cb = (wrp & 1) * 24;
         double cf[3][3][2];
@@ -587,6 +591,7 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
             if (!diagcta) av = *reinterpret_cast<const double2 *>(tik + off);
             a[ti][tj][0] = av.x; a[ti][tj][1] = av.y;
         }
+    if (failed) return;
     // right-hand side of the panel: what the rhs tasks of earlier steps left in bwork minus the
     // contributions of the source panels (ascending P)
     PANEL_STAMP(1);
@@ -1010,13 +1015,11 @@ __global__ void __launch_bounds__(TS * BWD_SLOTS, 1) k_backward_flow(const int *
     for (int t = beg + tid; t < end; t += TS * BWD_SLOTS) {
         const int *f = xdone + (size_t)crow[t] * FLAG_STRIDE;
         int spins = 0;
-        while (ld_relaxed(f) != epoch) {
-            __nanosleep(64);
-            if (++spins > (1 << 20)) { *status = 3; break; }
+        while (ld_acquire(f) != epoch) {              // acquire by the polling lane + the barrier below order the x loads of every thread
+            if (++spins > (1 << 22)) { *status = 3; break; }
         }
     }
     BW_STAMP(2);
-    __threadfence();
     __syncthreads();
     BW_STAMP(3);
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
