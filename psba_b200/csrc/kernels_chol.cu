@@ -496,8 +496,14 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
     // their (static) task descriptors and then wait for the previous step's memory to become visible
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     int4 cd0 = make_int4(0, 0, 0, 0), cd1 = cd0;
-    if ((int)blockIdx.x < ncrit) { cd0 = __ldg(crit_desc + 2 * blockIdx.x); cd1 = __ldg(crit_desc + 2 * blockIdx.x + 1); }
-    else if ((int)blockIdx.x < ncrit + ndef) cd0 = __ldg(def_desc + (blockIdx.x - ncrit));
+    int2 sl0 = make_int2(-1, -1);                              // first source of the task: static data, fetched before the wait too
+    if ((int)blockIdx.x < ncrit) {
+        cd0 = __ldg(crit_desc + 2 * blockIdx.x); cd1 = __ldg(crit_desc + 2 * blockIdx.x + 1);
+        if (cd1.x < cd1.y) sl0 = __ldg(crit_src + cd1.x);
+    } else if ((int)blockIdx.x < ncrit + ndef) {
+        cd0 = __ldg(def_desc + (blockIdx.x - ncrit));
+        sl0 = __ldg(def_srcs + cd0.y);
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     // the status word of the earlier steps is loaded here and tested after the first tile loads have been issued:
     // one L2 round trip less in front of every step
@@ -522,11 +528,8 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
         const int sb = dd.y, se = dd.z;
         double *tij = Stiles + (size_t)dd.x * TS * TS;
         TileRegs<PANEL_NT> ra, rb_;
-        {
-            const int2 sl = __ldg(def_srcs + sb);
-            tile_ldg(ra, Stiles + (size_t)sl.x * TS * TS);
-            tile_ldg(rb_, Stiles + (size_t)sl.y * TS * TS);
-        }
+        tile_ldg(ra, Stiles + (size_t)sl0.x * TS * TS);
+        tile_ldg(rb_, Stiles + (size_t)sl0.y * TS * TS);
         if (failed) return;
         // warp w owns the 24x24 block (w / 2, w % 2) of the target: 3x3 DMMA fragments, two doubles per lane each
         const int wrp = tid >> 5, lane = tid & 31, rb = (wrp >> 1) * 24, cb = (wrp & 1) * 24;
@@ -571,10 +574,9 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
     TileRegs<PANEL_NT> rp, ri;
     bool upd = false;
     if (sb < se) {
-        const int2 sl = __ldg(crit_src + sb);
-        tile_ldg(rp, Stiles + (size_t)sl.x * TS * TS);                                            // L_KP
-        upd = sl.y >= 0;
-        if (upd) tile_ldg(ri, Stiles + (size_t)sl.y * TS * TS);                                   // L_IP
+        tile_ldg(rp, Stiles + (size_t)sl0.x * TS * TS);                                           // L_KP
+        upd = sl0.y >= 0;
+        if (upd) tile_ldg(ri, Stiles + (size_t)sl0.y * TS * TS);                                  // L_IP
     }
     // D and A_IK as DMMA accumulator fragments: warp w owns the 24x24 block (w / 2, w % 2), 3x3 fragments of 8x8,
     // lane l holds the entries (l / 4, 2 (l % 4) + {0, 1}) of each
