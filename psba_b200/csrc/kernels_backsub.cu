@@ -10,12 +10,14 @@
 #include <algorithm>
 
 // candidate cameras = cams + dpa, plus the camera part of the step scalars
-__global__ void k_newcams(int N, const double *__restrict__ cams, const double *__restrict__ dpa, const double *__restrict__ ga,
-                          double mu, double *__restrict__ newcams, double *__restrict__ scal3)
+__global__ void __launch_bounds__(1024) k_newcams(int N, const double *__restrict__ cams, const double *__restrict__ dpa, const double *__restrict__ ga,
+                                                  double mu, double *__restrict__ newcams, double *__restrict__ scal3)
 {
-    __shared__ double s0[256], s1[256], s2[256];
+    // one CTA on the critical path of every try: 1024 threads so that the N = 6m entries are a dozen independent
+    // loads per thread (25 us with 256 threads on 2 000 cameras); fixed-order tree
+    __shared__ double s0[1024], s1[1024], s2[1024];
     double a = 0.0, b = 0.0, p2 = 0.0;
-    for (int k = threadIdx.x; k < N; k += 256) {
+    for (int k = threadIdx.x; k < N; k += 1024) {
         const double d = dpa[k], x = cams[k] + d;
         newcams[k] = x;
         a += d * d;
@@ -24,7 +26,7 @@ __global__ void k_newcams(int N, const double *__restrict__ cams, const double *
     }
     s0[threadIdx.x] = a; s1[threadIdx.x] = b; s2[threadIdx.x] = p2;
     __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {
+    for (int w = 512; w > 0; w >>= 1) {
         if (threadIdx.x < w) { s0[threadIdx.x] += s0[threadIdx.x + w]; s1[threadIdx.x] += s1[threadIdx.x + w]; s2[threadIdx.x] += s2[threadIdx.x + w]; }
         __syncthreads();
     }
@@ -403,7 +405,7 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
     const int cur = c->cur, nw = 1 - cur;
     double *gb = c->g + c->N, *ebp = c->eab + c->N, *dpbp = c->dp + c->N;
     if (evaluate) {
-        PROF(c, KID_NEWCAMS) k_newcams<<<1, 256, 0, c->stream>>>(c->N, c->cams[cur], c->dp, c->g, mu, c->cams[nw], c->d_scal + 4);
+        PROF(c, KID_NEWCAMS) k_newcams<<<1, 1024, 0, c->stream>>>(c->N, c->cams[cur], c->dp, c->g, mu, c->cams[nw], c->d_scal + 4);
         psba_launch_cam_prep(c, nw);
         PROF(c, KID_BACKSUB) {
             static bool attr_set = false;
