@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ c
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < PT_CTA / 32; ++w) s += red[tid][w];
-        part[(size_t)cidx * 4 + tid] = s;
+        part[(size_t)(chunk_list ? (int)blockIdx.x : cidx) * 4 + tid] = s;      // listed launch: partials by CTA
     }
 }
 
@@ -289,9 +289,9 @@ __global__ void __launch_bounds__(PT_CTA, 3) k_backsub_pipe(int n_list, const in
     __syncthreads();                                           // barriers initialised, sj[0] visible
     issue(ds, 0, cur.j, on, dn);
     cp_async_commit();
+    double cta_sum = 0.0;
     for (int it = 0; q < n_list; q += G, ++it) {
         const int st = it & 1;
-        const int cidx = chunk_of(q);
         oc = on;
 #pragma unroll
         for (int u = 0; u < 6; ++u) d[u] = dn[u];
@@ -352,16 +352,17 @@ __global__ void __launch_bounds__(PT_CTA, 3) k_backsub_pipe(int n_list, const in
         }
         if ((tid & 31) == 0) { red[0][tid >> 5] = s_e2; red[1][tid >> 5] = s_dp2; red[2][tid >> 5] = s_dpg; red[3][tid >> 5] = s_p2; }
         __syncthreads();
-        if (tid < 4) {
+        if (tid < 4) {                                         // the CTA's own running sums (its chunks in order): one partial per CTA
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < PT_CTA / 32; ++w) s += red[tid][w];
-            part[(size_t)cidx * 4 + tid] = s;
+            cta_sum += s;
         }
         cur = mid; mid = far;
         ds = ds1; ds1 = ds2; ds2 = ds3;
     }
     cp_async_wait<0>();
+    if (tid < 4) part[(size_t)blockIdx.x * 4 + tid] = cta_sum;
 }
 
 // out[v] = sum_p part[p*4+v], v<4, fixed order.  1024 threads, four independent partial sums per thread and
@@ -407,19 +408,22 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
     if (evaluate) {
         PROF(c, KID_NEWCAMS) k_newcams<<<1, 1024, 0, c->stream>>>(c->N, c->cams[cur], c->dp, c->g, mu, c->cams[nw], c->d_scal + 4);
         psba_launch_cam_prep(c, nw);
+        int n_part = 0;
         PROF(c, KID_BACKSUB) {
             static bool attr_set = false;
             const int dyn = 2 * PT_CTA * (18 + PROJ_LD) * (int)sizeof(double);
             if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_backsub_pipe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)); attr_set = true; }
+            const int gs = std::min(c->n_small, c->n_sm * 3);      // persistent CTAs: one partial each
             if (c->n_small > 0)
-                k_backsub_pipe<0><<<std::min(c->n_small, c->n_sm * 3), PT_CTA, dyn, c->stream>>>(c->n_small, c->d_small_list, c->ptdesc, c->pt_ptr, c->iidx,
-                                                                                             c->jidx, c->impts, c->W, c->Vinv, gb, c->dp, c->pts[cur],
-                                                                                             c->camcache[nw], mu, ebp, dpbp, c->pts[nw], c->d_part);
-            if (c->n_big > 0)      // points with more observations than one wave
+                k_backsub_pipe<0><<<gs, PT_CTA, dyn, c->stream>>>(c->n_small, c->d_small_list, c->ptdesc, c->pt_ptr, c->iidx,
+                                                              c->jidx, c->impts, c->W, c->Vinv, gb, c->dp, c->pts[cur],
+                                                              c->camcache[nw], mu, ebp, dpbp, c->pts[nw], c->d_part);
+            if (c->n_big > 0)      // points with more observations than one wave: one partial per CTA behind the others
                 k_backsub<true><<<c->n_big, PT_CTA, 0, c->stream>>>(c->d_big_list, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
-                                                                   gb, c->dp, c->pts[cur], c->camcache[nw], mu, ebp, dpbp, c->pts[nw], c->d_part);
+                                                                   gb, c->dp, c->pts[cur], c->camcache[nw], mu, ebp, dpbp, c->pts[nw], c->d_part + (size_t)gs * 4);
+            n_part = gs + c->n_big;
         }
-        PROF(c, KID_REDUCE) k_final_reduce4<<<1, 1024, 0, c->stream>>>(c->d_part, c->n_ptchunk, c->d_scal);
+        PROF(c, KID_REDUCE) k_final_reduce4<<<1, 1024, 0, c->stream>>>(c->d_part, n_part, c->d_scal);
         c->st_launches += 3; c->st_exqt += 1;
         if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal, 4);
         CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
