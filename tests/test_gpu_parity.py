@@ -554,3 +554,28 @@ def test_full_size_properties_of_the_headline_workload():
         finals.append((flag, fe, tuple(r["err"] for r in G.trace())))
         G.close()
     assert finals[0] == finals[1] and finals[0][1] < res["cost_new"]
+
+
+def test_full_size_index_structure_against_numpy():
+    """The device-built index structure at the full size of the headline workload (15 M camera-pair triples; the
+    reference's comm3DIdx would be 14.6 TB): CSR by point, camera-major order and the pair-sorted triples are rebuilt
+    with numpy -- stable sorts in the enumeration order of generate_idxs (PSBA/misc.cpp:189-217) -- and compared
+    bit for bit."""
+    from psba_b200 import synth
+    prob = synth.ring_problem(m=2000, n=1_000_000, d=5, w=64, seed=20262000)
+    m, n, o, d = prob["m"], prob["n"], prob["o"], 5
+    G = psba_b200.PSBA(prob)
+    assert np.array_equal(G.index("pt_ptr"), np.arange(n + 1, dtype=np.int64) * d)
+    assert np.array_equal(G.index("cam_obs"), np.argsort(prob["jidx"], kind="stable"))
+    # triples of a point in emission order: a = 0..d-1, b = 0..a (cameras ascend inside a point)
+    la = np.concatenate([np.full(a + 1, a) for a in range(d)]); lb = np.concatenate([np.arange(a + 1) for a in range(d)])
+    base = (np.arange(n, dtype=np.int64) * d)[:, None]
+    oa, ob = (base + la[None, :]).ravel(), (base + lb[None, :]).ravel()
+    key = prob["jidx"][oa].astype(np.int64) * m + prob["jidx"][ob]
+    order = np.argsort(key, kind="stable")                  # by pair (k, l); ascending point inside a pair
+    assert int(G.stat("ntriples")) == len(order)
+    assert np.array_equal(G.index("tri_oa"), oa[order]) and np.array_equal(G.index("tri_ob"), ob[order])
+    assert np.array_equal(G.index("tri_pt"), prob["iidx"][oa[order]])
+    uk = np.unique(np.concatenate([key, np.arange(m, dtype=np.int64) * (m + 1)]))     # pairs present + every diagonal
+    assert np.array_equal(G.index("pair_k").astype(np.int64) * m + G.index("pair_l"), uk)
+    G.close()
