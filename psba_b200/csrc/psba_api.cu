@@ -169,9 +169,10 @@ extern "C" void psba_fill_idxBuffer(psba_ctx *c, int nCams, int n3Dpts, int n2Dp
     psba_build_camera_major_copies(c);
     // ---- work buffers
     const size_t Tl = (size_t)c->N + 3 * (size_t)n;
-    c->W = dalloc<double>(c, (size_t)o * 18);
-    c->V = dalloc<double>(c, (size_t)n * 6);
-    c->Vinv = dalloc<double>(c, (size_t)n * 6);
+    // W, V and Vinv are written in full (point pass, k_vinv) before anything reads them: no zero fill (0.9 GB at 5 M observations)
+    c->W = (double *)psba_dev_alloc(c, std::max<size_t>((size_t)o * 18, 1) * sizeof(double), false);
+    c->V = (double *)psba_dev_alloc(c, std::max<size_t>((size_t)n * 6, 1) * sizeof(double), false);
+    c->Vinv = (double *)psba_dev_alloc(c, std::max<size_t>((size_t)n * 6, 1) * sizeof(double), false);
     c->g = dalloc<double>(c, Tl); c->dp = dalloc<double>(c, Tl); c->eab = dalloc<double>(c, Tl);
     c->P_U = dalloc<double>(c, Tl); c->P_B = dalloc<double>(c, Tl); c->P = dalloc<double>(c, Tl);
     c->cam_part = dalloc<double>(c, (size_t)c->n_cchunk * 27);
