@@ -122,6 +122,10 @@ void psba_upload_vec(psba_ctx *ctx, int vec, const double *host, int n);
  * E (N doubles, may be NULL) receives E_i; returns sum_i E_i (trust_region.cpp:358-364). */
 double psba_cholmod_blk(psba_ctx *ctx, int matSize, double *E, double *delta, double *beta, int *n_scalar_blocks);
 
+/* the same on a caller-supplied HOST matrix (the reference's cholmod_blk takes matBuf itself, PSBA/cl_cholmod.h:10-12):
+ * mat (matSize x matSize, symmetric, row-major, matSize % 3 == 0) is replaced by the factor L (zero above the diagonal). */
+double psba_cholmod_blk_mat(psba_ctx *ctx, int matSize, double *mat, double *E, double *delta, double *beta, int *n_scalar_blocks);
+
 /* ------------------------------------------------------------------ drivers (L3) ------ */
 
 /* levmar, PSBA/levmar.cpp:45-256 ; trust_region, PSBA/trust_region.cpp:49-288 (blk_idx is not
@@ -142,7 +146,7 @@ typedef struct {
 int  psba_trace_count(psba_ctx *ctx);
 void psba_trace_get(psba_ctx *ctx, int k, psba_trace_rec *rec);
 /* options: "verbose" (0/1), "max_iter" (50), "itno", "lm_only" (stop instead of handing to TR),
- * "force_lambda_count"; unknown names abort. */
+ * "trace_reset" (forget the run log), "stats_reset", "profile" (per-kernel CUDA-event timing), "timer_start"; unknown names abort. */
 void psba_set_option(psba_ctx *ctx, const char *name, double value);
 double psba_get_stat(psba_ctx *ctx, const char *name);
 /* index-structure readback (test hook, like the `out` pointers of the operators): copies the named

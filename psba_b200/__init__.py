@@ -87,6 +87,8 @@ def lib():
     L.psba_upload_vec.argtypes = [vp, i, _dp, i]
     L.psba_cholmod_blk.restype = d
     L.psba_cholmod_blk.argtypes = [vp, i, _dp, _dp, _dp, _ip]
+    L.psba_cholmod_blk_mat.restype = d
+    L.psba_cholmod_blk_mat.argtypes = [vp, i, _dp, _dp, _dp, _dp, _ip]
     L.psba_levmar.argtypes = dims + [_dp]
     L.psba_trust_region.argtypes = dims + [_ip, _dp]
     L.psba_solve.argtypes = [vp, _dp, _dp, _ip]
@@ -352,6 +354,15 @@ class PSBA:
         delta, beta, ns = C.c_double(), C.c_double(), C.c_int()
         s = self.L.psba_cholmod_blk(self.h, self.N, _d(E), C.byref(delta), C.byref(beta), C.byref(ns))
         return dict(sumE=s, E=E, delta=delta.value, beta=beta.value, n_scalar_blocks=ns.value)
+
+    def cholmod_blk_mat(self, mat):
+        """modified Cholesky of a host matrix (psba_cholmod_blk_mat): returns dict(sumE, E, L, delta, beta, n_scalar_blocks)"""
+        A = np.ascontiguousarray(mat, dtype=np.float64).copy()
+        n = A.shape[0]
+        E = np.zeros(n)
+        delta, beta, ns = C.c_double(), C.c_double(), C.c_int()
+        s = self.L.psba_cholmod_blk_mat(self.h, n, _d(A), _d(E), C.byref(delta), C.byref(beta), C.byref(ns))
+        return dict(sumE=s, E=E, L=A, delta=delta.value, beta=beta.value, n_scalar_blocks=ns.value)
 
     # ---- fused steps and drivers -----------------------------------------------------------
     def linearize(self, coeff_uvw=1.0, coeff_g=1.0):

@@ -111,6 +111,12 @@ static bool compute_PB(psba_ctx *c, double *lambda)
         return false;
     }
     psba_launch_solve(c);                                         // dpa
+    {   // the dataflow backward solve reports a broken schedule (bounded spin) through the status word
+        int st = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (st != 0) { fprintf(stderr, "psba_b200: camera solve failed with status %d after a successful factorisation\n", st); exit(EXIT_FAILURE); }
+    }
     psba_launch_backsub(c, *lambda, false, nullptr);              // eb, dpb
     psba_launch_axpby(c, -1.0, c->dp, 0.0, c->dp, c->P_B);        // P_B = -dp
     return true;

@@ -97,15 +97,19 @@ extern "C" int psba_readInitialSBAEstimate(const char *camsfname, const char *pt
             return 4;
         }
     }
+    if (origin_cnp == 6 && !Kdefault) { fprintf(stderr, "psba_readInitialSBAEstimate: 7-column camera file needs Kdefault\n"); return 6; }
     double *K = (double *)malloc(sizeof(double) * m * 5), *rot = (double *)malloc(sizeof(double) * m * 4);
     double *ex = (double *)malloc(sizeof(double) * m * 6);
+    double *P = nullptr;
+    // every error return below gives back what was allocated so far (the reference exits instead)
+    auto fail = [&](int code) { free(K); free(rot); free(ex); free(P); return code; };
     std::vector<double> raw(filecnp), filt(origin_cnp);
     for (int j = 0; j < m; ++j) {
         const char *s = cl[j];
         char *e;
         for (int k = 0; k < filecnp; ++k) {
             raw[k] = strtod(s, &e);
-            if (e == s) { fprintf(stderr, "readCameraParams(): line %d contains %d parameters, expected %d!\n", j + 1, k, filecnp); return 5; }
+            if (e == s) { fprintf(stderr, "readCameraParams(): line %d contains %d parameters, expected %d!\n", j + 1, k, filecnp); return fail(5); }
             s = e;
         }
         psba_quat2vec(raw.data(), filecnp, filt.data(), origin_cnp);
@@ -119,7 +123,6 @@ extern "C" int psba_readInitialSBAEstimate(const char *camsfname, const char *pt
         ex[j * 6] = ex[j * 6 + 1] = ex[j * 6 + 2] = 0.0;
         for (int k = 0; k < 3; ++k) ex[j * 6 + 3 + k] = filt[origin_cnp - 3 + k];
     }
-    if (origin_cnp == 6 && !Kdefault) { fprintf(stderr, "psba_readInitialSBAEstimate: 7-column camera file needs Kdefault\n"); return 6; }
 
     // points: X Y Z nframes (frame x y [cov])*   (readparams.cpp:247-290, 332-423)
     int covvals = 0;
@@ -132,7 +135,7 @@ extern "C" int psba_readInitialSBAEstimate(const char *camsfname, const char *pt
         if (rest == nframes * (mnp + 1 + mnp * mnp)) covvals = mnp * mnp;
         else if (rest == nframes * (mnp + 1 + mnp * (mnp + 1) / 2)) covvals = mnp * (mnp + 1) / 2;
     }
-    double *P = (double *)malloc(sizeof(double) * (size_t)n * 3);
+    P = (double *)malloc(sizeof(double) * (size_t)n * 3);
     std::vector<double> im; std::vector<int> ii, jj;
     im.reserve((size_t)n * 10); ii.reserve((size_t)n * 5); jj.reserve((size_t)n * 5);
     bool warned = false;
@@ -141,35 +144,43 @@ extern "C" int psba_readInitialSBAEstimate(const char *camsfname, const char *pt
         char *e;
         for (int k = 0; k < pnp; ++k) {
             P[(size_t)i * 3 + k] = strtod(s, &e);
-            if (e == s) { fprintf(stderr, "readPointParamsAndProjections(): line %d: expecting %d parameters for 3D point\n", i, pnp); return 7; }
+            if (e == s) { fprintf(stderr, "readPointParamsAndProjections(): line %d: expecting %d parameters for 3D point\n", i, pnp); return fail(7); }
             s = e;
         }
         const long nframes = strtol(s, &e, 10);
-        if (e == s) { fprintf(stderr, "readPointParamsAndProjections(): line %d: expecting number of frames\n", i); return 8; }
+        if (e == s) { fprintf(stderr, "readPointParamsAndProjections(): line %d: expecting number of frames\n", i); return fail(8); }
         s = e;
         const size_t first = jj.size();
         for (long f = 0; f < nframes; ++f) {
             const long frameno = strtol(s, &e, 10);
-            if (e == s) { fprintf(stderr, "readPointParamsAndProjections(): line %d has fewer than %ld projections\n", i + 1, nframes); return 9; }
+            if (e == s) { fprintf(stderr, "readPointParamsAndProjections(): line %d has fewer than %ld projections\n", i + 1, nframes); return fail(9); }
             s = e;
             if (frameno >= m || frameno < 0) {
                 fprintf(stderr, "readPointParamsAndProjections(): line %d contains an image projection for frame %ld "
                                 "but only %d cameras have been specified!\n", i + 1, frameno, m);
-                return 10;
+                return fail(10);
             }
             for (int k = 0; k < mnp; ++k) {
                 const double v = strtod(s, &e);
-                if (e == s) { fprintf(stderr, "readPointParamsAndProjections(): error reading image projections from line %d\n", i + 1); return 11; }
+                if (e == s) { fprintf(stderr, "readPointParamsAndProjections(): error reading image projections from line %d\n", i + 1); return fail(11); }
                 im.push_back(v); s = e;
             }
             for (int k = 0; k < covvals; ++k) { strtod(s, &e); s = e; }   // covariances are parsed and dropped (never used by any kernel)
             ii.push_back(i); jj.push_back((int)frameno);
         }
-        // generate_idxs scans the visibility mask with cameras ascending (misc.cpp:191-196) while the
-        // image points stay in file order; identical when the frames of a point are listed ascending
+        // generate_idxs scans the visibility mask with cameras ascending (misc.cpp:191-196) while the reference leaves
+        // the image points in file order: a point that lists its frames out of order gets its measurements attached to
+        // the wrong cameras there.  Every shipped file is ascending; for anything else the (frame, x, y)
+        // tuples are sorted TOGETHER here, so that a measurement stays with its camera (documented deviation).
         if (!std::is_sorted(jj.begin() + first, jj.end())) {
-            if (!warned) { fprintf(stderr, "psba: point %d lists its frames out of order; indices follow generate_idxs (ascending)\n", i); warned = true; }
-            std::sort(jj.begin() + first, jj.end());
+            if (!warned) { fprintf(stderr, "psba: point %d lists its frames out of order; (frame, x, y) tuples are sorted by frame\n", i); warned = true; }
+            const size_t cnt = jj.size() - first;
+            std::vector<size_t> ord(cnt);
+            for (size_t q = 0; q < cnt; ++q) ord[q] = q;
+            std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return jj[first + a] < jj[first + b]; });
+            std::vector<int> js(cnt); std::vector<double> ms(cnt * mnp);
+            for (size_t q = 0; q < cnt; ++q) { js[q] = jj[first + ord[q]]; for (int k = 0; k < mnp; ++k) ms[q * mnp + k] = im[(first + ord[q]) * mnp + k]; }
+            for (size_t q = 0; q < cnt; ++q) { jj[first + q] = js[q]; for (int k = 0; k < mnp; ++k) im[(first + q) * mnp + k] = ms[q * mnp + k]; }
         }
     }
     const size_t o = jj.size();
@@ -311,9 +322,10 @@ extern "C" int psba_read_bal(const char *fname, int *ncams, int *n3Dpts, int *n2
     double *ex = (double *)malloc(sizeof(double) * m * 6), *X = (double *)malloc(sizeof(double) * n * 3);
     double *im = (double *)malloc(sizeof(double) * o * 2), *dist = (double *)malloc(sizeof(double) * m * 2);
     int *ii = (int *)malloc(sizeof(int) * o), *jj = (int *)malloc(sizeof(int) * o);
+    auto fail = [&](int code) { free(K); free(rot); free(ex); free(X); free(im); free(dist); free(ii); free(jj); return code; };
     for (int j = 0; j < m; ++j) {
         double c9[9];
-        for (int q = 0; q < 9; ++q) if (!next_d(c9[q])) { fprintf(stderr, "psba_b200: %s: camera %d is truncated\n", fname, j); return 5; }
+        for (int q = 0; q < 9; ++q) if (!next_d(c9[q])) { fprintf(stderr, "psba_b200: %s: camera %d is truncated\n", fname, j); return fail(5); }
         // Rodrigues vector -> rotation matrix
         const double th = std::sqrt(c9[0] * c9[0] + c9[1] * c9[1] + c9[2] * c9[2]);
         double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -336,7 +348,7 @@ extern "C" int psba_read_bal(const char *fname, int *ncams, int *n3Dpts, int *n2
         K[j * 5] = c9[6]; K[j * 5 + 1] = 0; K[j * 5 + 2] = 0; K[j * 5 + 3] = 1; K[j * 5 + 4] = 0;
         dist[j * 2] = c9[7]; dist[j * 2 + 1] = c9[8];
     }
-    for (int i = 0; i < n * 3; ++i) if (!next_d(X[i])) { fprintf(stderr, "psba_b200: %s: point %d is truncated\n", fname, i / 3); return 6; }
+    for (int i = 0; i < n * 3; ++i) if (!next_d(X[i])) { fprintf(stderr, "psba_b200: %s: point %d is truncated\n", fname, i / 3); return fail(6); }
     for (int k = 0; k < o; ++k) { ii[k] = ob[k].i; jj[k] = ob[k].j; im[k * 2] = ob[k].x; im[k * 2 + 1] = ob[k].y; }
     *ncams = m; *n3Dpts = n; *n2Dprojs = o;
     *Kparas = K; *initrot = rot; *camsEx = ex; *pts = X; *imgpts = im; *iidx = ii; *jidx = jj;

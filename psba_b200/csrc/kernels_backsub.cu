@@ -410,9 +410,8 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
         psba_launch_cam_prep(c, nw);
         int n_part = 0;
         PROF(c, KID_BACKSUB) {
-            static bool attr_set = false;
             const int dyn = 2 * PT_CTA * (18 + PROJ_LD) * (int)sizeof(double);
-            if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_backsub_pipe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)); attr_set = true; }
+            psba_set_smem((const void *)k_backsub_pipe<0>, dyn);
             const int gs = std::min(c->n_small, c->n_sm * 3);      // persistent CTAs: one partial each
             if (c->n_small > 0)
                 k_backsub_pipe<0><<<gs, PT_CTA, dyn, c->stream>>>(c->n_small, c->d_small_list, c->ptdesc, c->pt_ptr, c->iidx,
@@ -425,6 +424,7 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
         }
         PROF(c, KID_REDUCE) k_final_reduce4<<<1, 1024, 0, c->stream>>>(c->d_part, n_part, c->d_scal);
         c->st_launches += 3; c->st_exqt += 1;
+        LAUNCH_CHECK();
         if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal, 4);
         CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -441,6 +441,7 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
                                                                     gb, c->dp, c->pts[cur], c->camcache[cur], mu, ebp, dpbp,
                                                                     c->pts[nw], c->d_part);
         c->st_launches += 1;
+        LAUNCH_CHECK();
     }
 }
 
@@ -458,6 +459,7 @@ void psba_launch_newp(psba_ctx *c)
     if (c->n > 0) k_newp<<<cdiv(3 * c->n, 256), 256, 0, c->stream>>>(3 * c->n, c->pts[cur], c->dp + c->N, c->pts[nw]);
     c->cache_valid[nw] = false;
     c->st_launches += 2;
+    LAUNCH_CHECK();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -495,6 +497,7 @@ void psba_launch_dots(psba_ctx *c, const double *x, const double *y, const doubl
     if (nb > 0) k_dots<<<nb, 256, 0, c->stream>>>(np, x + c->N, y + c->N, z + c->N, c->d_part + 8);
     k_final_reduce6<<<1, 32, 0, c->stream>>>(c->d_part + 8, nb, c->d_scal + 6);
     c->st_launches += 4;
+    LAUNCH_CHECK();
     if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal + 6, 6);
     CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, 12 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -512,6 +515,7 @@ void psba_launch_axpby(psba_ctx *c, double a, const double *x, double b, const d
     const int n = c->N + 3 * c->n;
     PROF(c, KID_VEC) k_axpby<<<cdiv(n, 256), 256, 0, c->stream>>>(n, a, x, b, y, out);
     c->st_launches += 1;
+    LAUNCH_CHECK();
 }
 
 // max over the diagonals of U and V (maxElmOfUV, sba_func.cpp:422-444; only positive values count)
@@ -549,6 +553,7 @@ double psba_launch_maxdiag(psba_ctx *c)
     k_maxdiag<<<nb, 256, 0, c->stream>>>(c->m, c->n, c->U, c->V, c->d_part);
     k_final_max<<<1, 1, 0, c->stream>>>(c->d_part, nb, c->d_scal);
     c->st_launches += 2;
+    LAUNCH_CHECK();
     if (c->nranks > 1) psba_allreduce_max(c, c->d_scal, 1);
     CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));

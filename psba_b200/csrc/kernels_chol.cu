@@ -865,6 +865,7 @@ double psba_launch_factor(psba_ctx *c, bool defer_status)
                             h[K * 8 + 5] - h[K * 8 + 4], h[K * 8 + 5] - h[K * 8], h[K * 8 + 6] - h[7], h[K * 8 + 7] - h[7]);
     }
     c->st_launches += c->n_steps + 2;
+    LAUNCH_CHECK();
     c->S_valid = false;      // the factor overwrote the tile pool
     if (defer_status) { c->factor_valid = true; return 0.0; }
     int st = 0;
@@ -1080,6 +1081,7 @@ void psba_launch_solve(psba_ctx *c)
         PROF(c, KID_TRI_SOLVE) k_backward<<<1, TS * BW_SLOTS, 0, c->stream>>>(c->nt, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
                                                                    c->Stiles, c->Linv, c->chol_diag, c->pos2cam, c->dp);
         c->st_launches += 1;
+        LAUNCH_CHECK();
         return;
     }
     c->bw_epoch += 1;
@@ -1094,6 +1096,7 @@ void psba_launch_solve(psba_ctx *c)
                                                                         c->Stiles, c->Linv, c->chol_diag, c->pos2cam, c->dp, c->d_xdone, c->bw_epoch,
                                                                         c->d_status);
     c->st_launches += 1;
+    LAUNCH_CHECK();
     if (dbg_dev) {
         std::vector<long long> h((size_t)c->nt * 8), ord(c->nt);
         std::vector<int> order(c->nt);

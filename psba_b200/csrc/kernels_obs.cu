@@ -53,6 +53,7 @@ void psba_launch_cam_prep(psba_ctx *c, int set)
     PROF(c, KID_CAM_PREP) k_cam_prep<<<cdiv(c->m, 128), 128, 0, c->stream>>>(c->m, c->K, c->initcams, c->cams[set], c->camcache[set]);
     c->cache_valid[set] = true;
     c->st_launches += 1;
+    LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -119,6 +120,7 @@ double psba_launch_cost(psba_ctx *c, int set, double *ex_dev)
         PROF(c, KID_COST) k_cost<<<nb, 256, 0, c->stream>>>(c->o, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set], ex_dev, c->d_part);
     PROF(c, KID_REDUCE) k_final_reduce<<<1, 256, 0, c->stream>>>(c->d_part, nb, 1, 1, c->d_scal);
     c->st_launches += 2; c->st_exqt += 1;
+    LAUNCH_CHECK();
     if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal, 1);
     read_scalars(c, 0, 1);
     return c->h_scal[0];
@@ -433,9 +435,8 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
                                                              c->U, ga_out);
     if (c->n_ptchunk > 0)
         PROF(c, KID_LIN_POINTS) {
-            static bool attr_set = false;
             const int dyn = 2 * PT_CTA * CAM_LD * (int)sizeof(double);
-            if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_lin_points_pipe<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)); attr_set = true; }
+            psba_set_smem((const void *)k_lin_points_pipe<0>, dyn);
             // the persistent kernel pays for its three-stage prologue only when a CTA sees enough chunks (measured on
             // Venice-52, 2 700 chunks: 57 us against 31 us for the one-shot kernel)
             static const int pipe_env = getenv("PSBA_LIN_PIPE") ? atoi(getenv("PSBA_LIN_PIPE")) : -1;
@@ -458,6 +459,7 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
         CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     }
     c->st_launches += 3; c->st_lin += 1;
+    LAUNCH_CHECK();
     if (c->nranks > 1) {
         psba_allreduce_sum(c, c->U, (size_t)c->m * 42);
         CUDA_CHECK(cudaMemcpyAsync(c->g, c->U + (size_t)c->m * 36, (size_t)c->N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -491,6 +493,7 @@ void psba_launch_jac_materialize(psba_ctx *c, double *JA, double *JB)
         k_jac_materialize<<<cdiv(c->o, 128), 128, 0, c->stream>>>(c->o, c->iidx, c->jidx, c->impts, c->camcache[set],
                                                                  c->pts[set], JA, JB);
     c->st_launches += 1;
+    LAUNCH_CHECK();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -555,6 +558,7 @@ void psba_launch_Jdot(psba_ctx *c, const double *x, const double *y, double *Jx_
                                          x, y, Jx_out, c->d_part);
     PROF(c, KID_REDUCE) k_final_reduce<<<1, 256, 0, c->stream>>>(c->d_part, nb, 3, 3, c->d_scal);
     c->st_launches += 2;
+    LAUNCH_CHECK();
     if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal, 3);
     read_scalars(c, 0, 3);
     res[0] = c->h_scal[0]; res[1] = c->h_scal[1]; res[2] = c->h_scal[2];

@@ -55,6 +55,7 @@ double psba_launch_vinv(psba_ctx *c, double mu)
     CUDA_CHECK(cudaMemsetAsync(c->d_status + 1, 0, sizeof(int), c->stream));
     if (c->n > 0) PROF(c, KID_VINV) k_vinv<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->V, mu, c->Vinv, c->d_status + 1);
     c->st_launches += 1;
+    LAUNCH_CHECK();
     return 0.0;
 }
 
@@ -1029,10 +1030,12 @@ void psba_launch_schur(psba_ctx *c, double mu)
                                                                              c->cam2pos, c->nt, c->Stiles, ea_out);
     }
     c->st_launches += 3;
+    LAUNCH_CHECK();
     if (!single) {
         psba_allreduce_sum(c, c->Stiles, (size_t)c->n_tiles_S * TS * TS + (size_t)c->N);   // S tiles + ea; fill-in tiles are zero on every rank
         k_add_U<<<cdiv(c->m * 42, 128), 128, 0, c->stream>>>(c->m, c->U, c->g, mu, c->tile_index, c->cam2pos, c->nt, c->Stiles, ea_red, c->eab);
         c->st_launches += 1;
+        LAUNCH_CHECK();
     }
     if (c->nt * TS > c->N) { k_pad_diag<<<cdiv(c->nt * TS, 256), 256, 0, c->stream>>>(c->nt, c->pos2cam, c->tile_index, c->Stiles); c->st_launches += 1; }
     c->S_valid = true; c->factor_valid = false;
@@ -1059,4 +1062,5 @@ void psba_launch_Y_materialize(psba_ctx *c, double *Y)
 {
     if (c->o > 0) k_Y_materialize<<<cdiv(c->o, 128), 128, 0, c->stream>>>(c->o, c->iidx, c->W, c->Vinv, Y);
     c->st_launches += 1;
+    LAUNCH_CHECK();
 }

@@ -43,6 +43,7 @@ void psba_tiles_to_dense(psba_ctx *c, double *dense_dev, bool mirror)
     long long tot = (long long)c->N * c->N;
     k_tiles_to_dense<<<cdiv(tot, 256), 256, 0, c->stream>>>(c->N, c->nt, c->tile_index, c->cam2pos, c->Stiles, dense_dev, mirror ? 1 : 0, nullptr);
     c->st_launches += 1;
+    LAUNCH_CHECK();
 }
 
 // the factor L as a dense lower-triangular matrix of size npad = nt*TS in the solver's ordering
@@ -53,6 +54,7 @@ static void psba_factor_to_dense(psba_ctx *c, double *dense_dev)
     long long tot = (long long)npad * npad;
     k_tiles_to_dense<<<cdiv(tot, 256), 256, 0, c->stream>>>(npad, c->nt, c->tile_index, nullptr, c->Stiles, dense_dev, 0, c->Ldiag);
     c->st_launches += 1;
+    LAUNCH_CHECK();
 }
 
 // ABI parity only (SPDinv's explicit inverse, cl_spdinv.cpp:18-40): column of S^-1 for (camera, component)
@@ -87,6 +89,7 @@ void psba_launch_explicit_inverse(psba_ctx *c, double *out_dev)
     psba_factor_to_dense(c, Ld);
     k_explicit_inverse<<<cdiv(c->N, 64), 64, 0, c->stream>>>(c->N, (int)NP, c->cam2pos, Ld, work, out_dev);
     c->st_launches += 1;
+    LAUNCH_CHECK();
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     psba_dev_free(c, Ld); psba_dev_free(c, work);
 }
@@ -280,11 +283,12 @@ __global__ void k_cholmod_E(int N, const double *__restrict__ mat, double *__res
 }
 
 #undef M
-// runs on c->Sdense (dense S incl. mirrored upper triangle). Returns sum_i E_i (left-to-right).
-double psba_launch_cholmod(psba_ctx *c, double *delta_out, double *beta_out, int *nscalar_out)
+// runs on a dense symmetric matrix (S incl. mirrored upper triangle) of size N on the device; aux / diagInv / diag / E
+// are work arrays of 3N+2TS, 3N+2TS and N doubles.  Returns sum_i E_i (left-to-right, trust_region.cpp:358-362).
+double psba_launch_cholmod_dense(psba_ctx *c, int N, double *mat, double *aux, double *diagInv, double *E,
+                                 double *delta_out, double *beta_out, int *nscalar_out)
 {
-    const int N = c->N;
-    k_mat_max<<<1, 256, 0, c->stream>>>(N, c->Sdense, c->d_scal + 8);
+    k_mat_max<<<1, 256, 0, c->stream>>>(N, mat, c->d_scal + 8);
     CUDA_CHECK(cudaMemcpyAsync(c->h_scal + 8, c->d_scal + 8, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     const double xi = c->h_scal[8], gamma = c->h_scal[9];
@@ -292,18 +296,25 @@ double psba_launch_cholmod(psba_ctx *c, double *delta_out, double *beta_out, int
     double beta = fmax(gamma, 1e-15);
     beta = fmax(beta, xi / sqrt((double)N * N - 1));
     beta = sqrt(beta);
-    PROF(c, KID_CHOLMOD) k_cholmod<<<1, 1024, 0, c->stream>>>(N, c->Sdense, c->chol_aux, c->chol_diag, c->chol_E, beta, delta, c->d_status + 2);
-    k_cholmod_E<<<cdiv(N, 128), 128, 0, c->stream>>>(N, c->Sdense, c->chol_E);
+    PROF(c, KID_CHOLMOD) k_cholmod<<<1, 1024, 0, c->stream>>>(N, mat, aux, diagInv, E, beta, delta, c->d_status + 2);
+    k_cholmod_E<<<cdiv(N, 128), 128, 0, c->stream>>>(N, mat, E);
     c->st_launches += 3;
-    std::vector<double> E(N);
+    LAUNCH_CHECK();
+    std::vector<double> Eh(N);
     int ns = 0;
-    CUDA_CHECK(cudaMemcpyAsync(E.data(), c->chol_E, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(Eh.data(), E, N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaMemcpyAsync(&ns, c->d_status + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     double sum = 0.0;
-    for (int i = 0; i < N; ++i) sum += E[i];                      // trust_region.cpp:358-362
+    for (int i = 0; i < N; ++i) sum += Eh[i];                     // trust_region.cpp:358-362
     if (delta_out) *delta_out = delta;
     if (beta_out) *beta_out = beta;
     if (nscalar_out) *nscalar_out = ns;
     return sum;
+}
+
+// on c->Sdense (the S of the last compute_S in the callers' camera order)
+double psba_launch_cholmod(psba_ctx *c, double *delta_out, double *beta_out, int *nscalar_out)
+{
+    return psba_launch_cholmod_dense(c, c->N, c->Sdense, c->chol_aux, c->chol_diag, c->chol_E, delta_out, beta_out, nscalar_out);
 }

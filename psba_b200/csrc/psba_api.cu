@@ -26,15 +26,15 @@ static void check_dims(int cnp, int pnp, int mnp)
 // (release threshold = never), so a service that opens one problem after another pays for page mapping once.
 void *psba_dev_alloc(psba_ctx *c, size_t bytes, bool zero)
 {
-    static bool pool_ready = false;
-    if (!pool_ready) {
-        int dev = 0;
+    static bool pool_ready[64] = {false};
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    if (!pool_ready[dev & 63]) {
         cudaMemPool_t pool;
-        CUDA_CHECK(cudaGetDevice(&dev));
         CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
         unsigned long long keep = ~0ull;
         CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        pool_ready = true;
+        pool_ready[dev & 63] = true;
     }
     void *p = nullptr;
     bytes = std::max<size_t>(bytes, 16);
@@ -455,6 +455,25 @@ extern "C" double psba_cholmod_blk(psba_ctx *c, int matSize, double *E, double *
     return sum;
 }
 
+// the reference's cholmod_blk takes the matrix buffer itself (cl_cholmod.h:10-12): same here for a HOST matrix
+// (symmetric, row-major, matSize a multiple of 3); mat receives the factor (lower triangle, zero above), E the E_i.
+extern "C" double psba_cholmod_blk_mat(psba_ctx *c, int matSize, double *mat, double *E, double *delta, double *beta, int *n_scalar_blocks)
+{
+    if (matSize <= 0 || matSize % 3) die("cholmod_blk_mat: matSize must be a positive multiple of 3");
+    const size_t nn = (size_t)matSize * matSize;
+    double *d = (double *)psba_dev_alloc(c, nn * 8, false), *aux = (double *)psba_dev_alloc(c, ((size_t)3 * matSize + 2 * TS) * 8, true);
+    double *dinv = (double *)psba_dev_alloc(c, ((size_t)3 * matSize + 2 * TS) * 8, true), *Ed = (double *)psba_dev_alloc(c, ((size_t)matSize + TS) * 8, true);
+    CUDA_CHECK(cudaMemcpyAsync(d, mat, nn * 8, cudaMemcpyHostToDevice, c->stream));
+    const double sum = psba_launch_cholmod_dense(c, matSize, d, aux, dinv, Ed, delta, beta, n_scalar_blocks);
+    // the kernel addresses its matrix transposed (element (r, c) at [c * N + r]): hand the factor back row-major
+    std::vector<double> t(nn);
+    d2h(c, t.data(), d, nn);
+    for (int r = 0; r < matSize; ++r) for (int q = 0; q < matSize; ++q) mat[(size_t)r * matSize + q] = q <= r ? t[(size_t)q * matSize + r] : 0.0;
+    if (E) d2h(c, E, Ed, (size_t)matSize);
+    psba_dev_free(c, d); psba_dev_free(c, aux); psba_dev_free(c, dinv); psba_dev_free(c, Ed);
+    return sum;
+}
+
 extern "C" void psba_get_params(psba_ctx *c, int params, double *cams, double *pts)
 {
     const int set = params == PSBA_PARAMS_CUR ? c->cur : 1 - c->cur;
@@ -481,6 +500,7 @@ extern "C" void psba_set_option(psba_ctx *c, const char *name, double v)
     else if (s == "lm_only") c->lm_only = (int)v;
     else if (s == "profile") { psba_prof_collect(c); c->profile = v != 0; }
     else if (s == "profile_reset") { psba_prof_collect(c); for (int k = 0; k < KID_COUNT; ++k) { c->prof_ms[k] = 0; c->prof_n[k] = 0; } }
+    else if (s == "trace_reset") { c->trace.clear(); c->n_cholmod_events = 0; }
     else if (s == "stats_reset") { c->st_tries = c->st_exqt = c->st_lin = c->st_launches = 0; }
     else if (s == "timer_start") {
         if (!c->timer_init) { CUDA_CHECK(cudaEventCreate(&c->timer_e0)); CUDA_CHECK(cudaEventCreate(&c->timer_e1)); c->timer_init = true; }
@@ -595,6 +615,7 @@ extern "C" void psba_try_step(psba_ctx *c, double mu, psba_try_result *res)
     res->cost_new = res->dp_L2 = res->dp_dot = res->p_new_L2 = NAN;
     psba_launch_solve(c);
     psba_launch_backsub(c, mu, true, res);           // reads the status word with the step scalars
+    if (c->h_status[0] > 1) { fprintf(stderr, "psba_b200: camera solve failed with status %d (broken dataflow schedule)\n", c->h_status[0]); exit(EXIT_FAILURE); }
     res->solve_status = c->h_status[0] ? 1.0 : 0.0;
     if (res->solve_status != 0.0) { c->factor_valid = false; res->cost_new = res->dp_L2 = res->dp_dot = res->p_new_L2 = NAN; }
 }

@@ -33,6 +33,10 @@
     fprintf(stderr, "psba_b200: CUDA error %d (%s) at %s(%d)\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); \
     exit(EXIT_FAILURE); } } while (0)
 
+// every kernel launch is followed by this check (launch-configuration errors -- too much shared memory, too many
+// registers for the block size -- are reported by cudaGetLastError, not by the launch statement itself)
+#define LAUNCH_CHECK() CUDA_CHECK(cudaGetLastError())
+
 struct psba_comm;   // NCCL communicator wrapper (comm.cu)
 
 // per-kernel device timing (CUDA events on the launching stream), enabled by option "profile"
@@ -176,6 +180,8 @@ void psba_launch_solve(psba_ctx *c);         // dp[0..N) = S^-1 eab[0..N)
 void psba_tiles_to_dense(psba_ctx *c, double *dense_dev, bool mirror);
 void psba_launch_explicit_inverse(psba_ctx *c, double *out_dev);
 double psba_launch_cholmod(psba_ctx *c, double *delta, double *beta, int *nscalar);
+double psba_launch_cholmod_dense(psba_ctx *c, int N, double *mat, double *aux, double *diagInv, double *E,
+                                 double *delta, double *beta, int *nscalar);
 // ---- kernels_backsub.cu
 void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result *res);
 void psba_launch_newp(psba_ctx *c);
@@ -200,6 +206,7 @@ struct psba_prof_scope {
         CUDA_CHECK(cudaEventRecord(e0, c->stream));
     }
     ~psba_prof_scope() {
+        LAUNCH_CHECK();
         if (!on) return;
         CUDA_CHECK(cudaEventRecord(e1, c->stream));
         c->prof_pending.push_back({id, e0, e1});
@@ -208,5 +215,16 @@ struct psba_prof_scope {
 };
 #define PROF(c, id) if (psba_prof_scope prof_scope_##id{c, id})
 void psba_prof_collect(psba_ctx *c);
+
+// opt-in dynamic shared memory is an attribute per (function, device): remembered per pair, set once
+#include <set>
+#include <utility>
+static inline void psba_set_smem(const void *fn, int bytes)
+{
+    static std::set<std::pair<const void *, int>> done;
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    if (done.insert({fn, dev}).second) CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+}
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -42,7 +42,8 @@ __global__ void k_segment_ptr(int cnt, int nv, const int *__restrict__ key, int 
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cnt) return;
-    const int cur = key[k], prev = k > 0 ? key[k - 1] : -1;
+    // keys are clamped: the order check (k_check_order) runs in the same stream and its verdict is read afterwards
+    const int cur = min(max(key[k], 0), nv - 1), prev = k > 0 ? min(max(key[k - 1], 0), nv - 1) : -1;
     for (int v = prev + 1; v <= cur; ++v) ptr[v] = k;
     if (k == cnt - 1) for (int v = cur + 1; v <= nv; ++v) ptr[v] = cnt;
 }
