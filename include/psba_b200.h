@@ -66,6 +66,16 @@ void psba_fill_idxBuffer(psba_ctx *ctx, int nCams, int n3Dpts, int n2Dprojs, con
 /* release_buffer, PSBA/cl_psba.cpp:210-241 */
 void psba_release_buffer(psba_ctx *ctx);
 
+/* Extended camera model (neither is used by any reference kernel).
+ * set_distortion: fixed per-camera lens distortion kc[nCams*5] = (k1, k2, p1, p2, k3) of the sba "varKD" camera -- the
+ * columns 6-10 of data/54camsvarKD.txt that PSBA/misc.cpp:27-29 (quat2vec) copies through and CL_files/PSBA.cl:5-7
+ * (cnp = 6) then drops.  NULL / all zeros = the reference's projection.
+ * set_covariances: image-point covariances as readInitialSBAEstimate parses them (PSBA/readparams.cpp:272-283, 380-413;
+ * covsz = 4 full 2x2, 3 upper triangle), n2Dprojs * covsz doubles; residuals become W e with W^T W = Sigma^-1.
+ * Returns 1 if a covariance is not positive definite.  Both may be called any time after fill_idxBuffer. */
+void psba_set_distortion(psba_ctx *ctx, const double *kc);
+int psba_set_covariances(psba_ctx *ctx, const double *cov, int covsz);
+
 /* ------------------------------------------------------------------ operators (L2) ---- */
 
 /* compute_exQT, PSBA/sba_func.cpp:81-145 -> kern_compute_exQT, CL_files/compute_exQT.cl:18-71.
@@ -187,6 +197,14 @@ int psba_readInitialSBAEstimate(const char *camsfname, const char *ptsfname, int
                                 int *ncams, int *n3Dpts, int *n2Dprojs,
                                 double **Kparas, double **initrot, double **camsEx, double **pts,
                                 double **imgpts, int **iidx, int **jidx);
+/* the same reader, also returning what the reference parses and then drops: kc[m*5] (origin_cnp = 16, else NULL) for
+ * psba_set_distortion and the image-point covariances cov[o*covsz] (covsz 4 = FULLCOV, 3 = TRICOV, PSBA/readparams.cpp:272-283;
+ * NULL if the points file has none) for psba_set_covariances */
+int psba_readInitialSBAEstimate_ext(const char *camsfname, const char *ptsfname, int origin_cnp,
+                                    const double *Kdefault,
+                                    int *ncams, int *n3Dpts, int *n2Dprojs,
+                                    double **Kparas, double **initrot, double **camsEx, double **pts,
+                                    double **imgpts, int **iidx, int **jidx, double **kc, double **cov, int *covsz);
 void psba_quat2vec(const double *inp, int nin, double *outp, int nout);   /* misc.cpp:21-49 */
 void psba_free(void *p);
 

@@ -62,6 +62,7 @@ def lib(kind="restatement"):
     L.orc_call.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     L.orc_trace_get.argtypes = [C.c_void_p, C.c_int, _dp]
     L.orc_force_lambda.argtypes = [C.c_void_p, _dp, C.c_int]
+    L.orc_set_ext.argtypes = [C.c_void_p, _dp, _dp]
     L.orc_solve.argtypes = [C.c_void_p]
     L.orc_levmar.argtypes = [C.c_void_p]
     L.orc_trust_region.argtypes = [C.c_void_p]
@@ -191,6 +192,12 @@ class Problem:
 
     def call(self, op, arg=0.0):
         return self.L.orc_call(self.h, op.encode(), float(arg))
+
+    def set_ext(self, kc=None, wgt=None):
+        """extended camera model: kc[m,5] distortion (sba varKD), wgt[o,3] lower-triangular residual weights"""
+        a = None if kc is None else np.ascontiguousarray(kc, dtype=np.float64)
+        b = None if wgt is None else np.ascontiguousarray(wgt, dtype=np.float64)
+        self.L.orc_set_ext(self.h, None if a is None else _d(a), None if b is None else _d(b))
 
     def force_lambda(self, lams):
         a = np.ascontiguousarray(lams, dtype=np.float64)

@@ -46,6 +46,32 @@ static void transform_point(const double *q, const double *t, const double *X, d
     Xc[2] = -b0 * w3 + s * a3 - w2 * a1 + w1 * a2 + t[2];
 }
 
+/* Extended projection (not in the reference: SURVEY F7, 8(f) rank 3): the distortion of Lourakis' sba "varKD"
+ * camera (Bouguet model, kc = k1 k2 p1 p2 k3) applied to the normalised point, then the reference's affine K:
+ *   xn = Xc/Zc, yn = Yc/Zc, r2 = xn^2 + yn^2, c = 1 + k1 r2 + k2 r2^2 + k3 r2^3,
+ *   xd = c xn + 2 p1 xn yn + p2 (r2 + 2 xn^2),   yd = c yn + p1 (r2 + 2 yn^2) + 2 p2 xn yn,
+ *   x = fu xd + s yd + u0,   y = fu ar yd + v0        (kc = 0: compute_exQT.cl:68-69).
+ * P (optional) receives d(x, y) / d Xc. */
+static void ext_project(const double *K, const double *kc, const double *Xc, double *px, double *py, double P[2][3])
+{
+    static const double zero5[5] = {0, 0, 0, 0, 0};
+    const double *k = kc ? kc : zero5;
+    double iz = 1 / Xc[2], xn = Xc[0] * iz, yn = Xc[1] * iz, r2 = xn * xn + yn * yn;
+    double c = 1 + r2 * (k[0] + r2 * (k[1] + r2 * k[4])), dc = k[0] + r2 * (2 * k[1] + 3 * k[4] * r2);
+    double xd = c * xn + 2 * k[2] * xn * yn + k[3] * (r2 + 2 * xn * xn);
+    double yd = c * yn + k[2] * (r2 + 2 * yn * yn) + 2 * k[3] * xn * yn;
+    double fa = K[0] * K[3];
+    *px = K[0] * xd + K[4] * yd + K[1];
+    *py = fa * yd + K[2];
+    if (P) {
+        double j00 = c + 2 * dc * xn * xn + 2 * k[2] * yn + 6 * k[3] * xn, j01 = 2 * dc * xn * yn + 2 * k[2] * xn + 2 * k[3] * yn;
+        double j10 = j01, j11 = c + 2 * dc * yn * yn + 6 * k[2] * yn + 2 * k[3] * xn;
+        double g00 = K[0] * j00 + K[4] * j10, g01 = K[0] * j01 + K[4] * j11, g10 = fa * j10, g11 = fa * j11;
+        P[0][0] = g00 * iz; P[0][1] = g01 * iz; P[0][2] = -(g00 * xn + g01 * yn) * iz;
+        P[1][0] = g10 * iz; P[1][1] = g11 * iz; P[1][2] = -(g10 * xn + g11 * yn) * iz;
+    }
+}
+
 /* compute_exQT.cl:18-71 ; NDRange {o} (sba_func.cpp:115) */
 static void k_exQT(orc_state *s, const double *cams, const double *pts, double *ex)
 {
@@ -57,6 +83,14 @@ static void k_exQT(orc_state *s, const double *cams, const double *pts, double *
         double q[4], Xc[3], inv;
         total_quat(s->initcams + j * 4, cams + j * 6, q);
         transform_point(q, cams + j * 6 + 3, pts + (size_t)i * 3, Xc);
+        if (s->kc || s->wgt) {
+            double px, py, e0, e1;
+            ext_project(K, s->kc ? s->kc + j * 5 : 0, Xc, &px, &py, 0);
+            e0 = s->impts[idx * 2] - px; e1 = s->impts[idx * 2 + 1] - py;
+            if (s->wgt) { const double *w = s->wgt + (size_t)idx * 3; e1 = w[1] * e0 + w[2] * e1; e0 = w[0] * e0; }
+            ex[idx * 2] = e0; ex[idx * 2 + 1] = e1;
+            continue;
+        }
         inv = 1 / Xc[2];
         /* x = (fu*Xc + s*Yc + u0*Zc)/Zc ; y = (fu*ar*Yc + v0*Zc)/Zc  (compute_exQT.cl:68-69) */
         ex[idx * 2] = s->impts[idx * 2] - (K[0] * Xc[0] + K[4] * Xc[1] + K[1] * Xc[2]) * inv;
@@ -97,6 +131,14 @@ static void k_jacobiQT(orc_state *s)
         /* d proj / d Xc */
         P[0][0] = K[0] * iz; P[0][1] = K[4] * iz; P[0][2] = -(K[0] * Xc[0] + K[4] * Xc[1]) * iz2;
         P[1][0] = 0.0;       P[1][1] = K[0] * K[3] * iz; P[1][2] = -(K[0] * K[3] * Xc[1]) * iz2;
+        if (s->kc || s->wgt) {
+            double px, py;
+            ext_project(K, s->kc ? s->kc + j * 5 : 0, Xc, &px, &py, P);
+            if (s->wgt) {       /* rows of the weighted Jacobian: W P */
+                const double *w = s->wgt + (size_t)idx * 3;
+                for (c = 0; c < 3; ++c) { P[1][c] = w[1] * P[0][c] + w[2] * P[1][c]; P[0][c] = w[0] * P[0][c]; }
+            }
+        }
         /* b = X (x) q* */
         qc[0] = q[0]; qc[1] = -q[1]; qc[2] = -q[2]; qc[3] = -q[3];
         qmul(Xq, qc, b);

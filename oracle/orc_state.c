@@ -119,9 +119,17 @@ orc_state *orc_create(int m, int n, int o, const double *K, const double *impts,
 
 void orc_use_ops(orc_state *s, const orc_ops *ops) { s->ops = ops; }
 
+void orc_set_ext(orc_state *s, const double *kc, const double *wgt)
+{
+    free(s->kc); free(s->wgt); s->kc = s->wgt = NULL;
+    if (kc) { s->kc = (double *)xcalloc((size_t)s->m * 5, 8); memcpy(s->kc, kc, (size_t)s->m * 5 * 8); }
+    if (wgt) { s->wgt = (double *)xcalloc((size_t)s->o * 3, 8); memcpy(s->wgt, wgt, (size_t)s->o * 3 * 8); }
+}
+
 void orc_destroy(orc_state *s)
 {
     if (!s) return;
+    free(s->kc); free(s->wgt);
     free(s->K); free(s->impts); free(s->initcams); free(s->cams); free(s->newcams);
     free(s->pts); free(s->newpts); free(s->iidx); free(s->jidx); free(s->pt_ptr);
     free(s->cam_ptr); free(s->cam_obs); free(s->pair_ptr); free(s->pair_oa); free(s->pair_ob);

@@ -93,6 +93,10 @@ typedef struct orc_state {
     double *K;              /* m*5  fu,u0,v0,ar,s */
     double *impts;          /* o*2 */
     double *initcams;       /* m*4 */
+    /* extended camera model (NOT in the reference, whose kernels have neither): fixed
+     * per-camera distortion kc[m*5] of the sba varKD model and a per-observation lower-triangular residual
+     * weight wgt[o*3] = (w00, w10, w11) with W^T W = inverse image-point covariance.  NULL = absent. */
+    double *kc, *wgt;
     double *cams, *newcams; /* m*6 */
     double *pts, *newpts;   /* n*3 */
     /* structure (point-major observation order) */
@@ -137,6 +141,7 @@ void orc_split_motion(const double *motstruct, int origin_cnp, int m,
                       double *Kparas, double *camsEx);
 
 /* ---- orc_state.c ---- */
+void orc_set_ext(orc_state *s, const double *kc /* m*5 or NULL */, const double *wgt /* o*3 or NULL */);
 orc_state *orc_create(int m, int n, int o, const double *K, const double *impts,
                       const double *initcams, const double *camsEx, const double *pts,
                       const int *iidx, const int *jidx, int want_dense_tables);

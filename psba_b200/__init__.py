@@ -107,6 +107,10 @@ def lib():
     L.psba_readInitialSBAEstimate.argtypes = [C.c_char_p, C.c_char_p, i, _dp, _ip, _ip, _ip,
                                               C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp),
                                               C.POINTER(_dp), C.POINTER(_ip), C.POINTER(_ip)]
+    L.psba_readInitialSBAEstimate_ext.argtypes = L.psba_readInitialSBAEstimate.argtypes + [C.POINTER(_dp), C.POINTER(_dp), _ip]
+    L.psba_set_distortion.argtypes = [vp, _dp]
+    L.psba_set_covariances.argtypes = [vp, _dp, i]
+    L.psba_set_covariances.restype = i
     L.psba_quat2vec.argtypes = [_dp, i, _dp, i]
     L.psba_free.argtypes = [vp]
     L.psba_read_bal.argtypes = [C.c_char_p, _ip, _ip, _ip] + [C.POINTER(_dp)] * 5 + [C.POINTER(_ip)] * 2 + [C.POINTER(_dp)]
@@ -129,22 +133,31 @@ def _i(a):
     return None if a is None else a.ctypes.data_as(_ip)
 
 
-def read_sba(cams_path, pts_path, origin_cnp=11, Kdefault=None):
-    """readInitialSBAEstimate + quat2vec + the split of main.cpp:131-149 (host code of the library)."""
+def read_sba(cams_path, pts_path, origin_cnp=11, Kdefault=None, ext=False):
+    """readInitialSBAEstimate + quat2vec + the split of main.cpp:131-149 (host code of the library).
+    ext=True also returns what the reference parses and drops: kc[m,5] (varKD files) and cov[o,covsz] (or None)."""
     L = lib()
     m, n, o = C.c_int(), C.c_int(), C.c_int()
     K, rot, ex, pts, im = _dp(), _dp(), _dp(), _dp(), _dp()
     ii, jj = _ip(), _ip()
+    kc, cov, covsz = _dp(), _dp(), C.c_int()
     kd = None if Kdefault is None else np.ascontiguousarray(Kdefault, dtype=np.float64)
-    rc = L.psba_readInitialSBAEstimate(cams_path.encode(), pts_path.encode(), origin_cnp, _d(kd),
-                                       C.byref(m), C.byref(n), C.byref(o), C.byref(K), C.byref(rot), C.byref(ex),
-                                       C.byref(pts), C.byref(im), C.byref(ii), C.byref(jj))
+    args = [cams_path.encode(), pts_path.encode(), origin_cnp, _d(kd), C.byref(m), C.byref(n), C.byref(o), C.byref(K), C.byref(rot),
+            C.byref(ex), C.byref(pts), C.byref(im), C.byref(ii), C.byref(jj)]
+    rc = (L.psba_readInitialSBAEstimate_ext(*args, C.byref(kc), C.byref(cov), C.byref(covsz)) if ext
+          else L.psba_readInitialSBAEstimate(*args))
     if rc:
         raise RuntimeError("psba_readInitialSBAEstimate failed with code %d" % rc)
     m, n, o = m.value, n.value, o.value
     take = lambda p, k, shp: np.ctypeslib.as_array(p, shape=(k,)).copy().reshape(shp)
     out = dict(m=m, n=n, o=o, K=take(K, m * 5, (m, 5)), initrot=take(rot, m * 4, (m, 4)), cams=take(ex, m * 6, (m, 6)),
                pts=take(pts, n * 3, (n, 3)), impts=take(im, o * 2, (o, 2)), iidx=take(ii, o, (o,)), jidx=take(jj, o, (o,)))
+    if ext:
+        out["kc"] = take(kc, m * 5, (m, 5)) if kc else None
+        out["cov"] = take(cov, o * covsz.value, (o, covsz.value)) if cov else None
+        for p in (kc, cov):
+            if p:
+                L.psba_free(p)
     for p in (K, rot, ex, pts, im, ii, jj):
         L.psba_free(p)
     return out
@@ -246,6 +259,17 @@ class PSBA:
         self.o_loc = int(self.stat("o_local"))
         self.T_loc = self.N + 3 * self.n_loc
         self._dims = (6, 3, 2, self.n, self.m, self.o)
+
+    def set_distortion(self, kc):
+        a = None if kc is None else np.ascontiguousarray(kc, dtype=np.float64)
+        assert a is None or a.shape == (self.m, 5)
+        self.L.psba_set_distortion(self.h, _d(a))
+
+    def set_covariances(self, cov):
+        a = None if cov is None else np.ascontiguousarray(cov, dtype=np.float64)
+        assert a is None or (a.shape[0] == self.o and a.shape[1] in (3, 4))
+        if self.L.psba_set_covariances(self.h, _d(a), 0 if a is None else a.shape[1]):
+            raise ValueError("a covariance is not positive definite")
 
     # ---- operators (names of PSBA/sba_func.h) ------------------------------------------------
     def compute_exQT(self, params=PARAMS_CUR, want=False):

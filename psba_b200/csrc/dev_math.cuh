@@ -123,6 +123,89 @@ __device__ __forceinline__ void residual_jac(const CamReg &c, double X, double Y
 }
 
 // ---------------------------------------------------------------------------------------------
+// Extended camera model (the reference's kernels have neither, F7): fixed per-camera
+// distortion kc[5] = (k1, k2, p1, p2, k3) of Lourakis' sba "varKD" camera (Bouguet model) applied to the normalised
+// image point before the reference's affine K (data/54camsvarKD.txt columns 6-10, PSBA/misc.cpp:27-29 copies them
+// through quat2vec), and a per-observation lower-triangular residual weight (w00, w10, w11) with
+// W^T W = inverse image-point covariance (the covimgpts the reader parses, PSBA/readparams.cpp:272-283, 380-413).
+//   xn = Xc/Zc, yn = Yc/Zc, r2 = xn^2 + yn^2, c = 1 + k1 r2 + k2 r2^2 + k3 r2^3,
+//   xd = c xn + 2 p1 xn yn + p2 (r2 + 2 xn^2),  yd = c yn + p1 (r2 + 2 yn^2) + 2 p2 xn yn,
+//   x = fu xd + s yd + u0,  y = fu ar yd + v0.       kc = 0: compute_exQT.cl:68-69.
+// Kernels take the model as a template flag: the default path (no distortion, no weights) compiles to the code above.
+
+// projection (px, py) and, if P != nullptr, P[6] = d(px, py) / d(xc, yc, zc) row-major
+template <class CAM>
+__device__ __forceinline__ void project_ext(const CAM &c, const double *__restrict__ kc, double xc, double yc, double zc,
+                                            double &px, double &py, double *P)
+{
+    double k0 = 0, k1 = 0, k2 = 0, k3 = 0, k4 = 0;
+    if (kc) { k0 = __ldg(kc); k1 = __ldg(kc + 1); k2 = __ldg(kc + 2); k3 = __ldg(kc + 3); k4 = __ldg(kc + 4); }
+    const double iz = 1.0 / zc, xn = xc * iz, yn = yc * iz, r2 = xn * xn + yn * yn;
+    const double cd = 1.0 + r2 * (k0 + r2 * (k1 + r2 * k4)), dc = k0 + r2 * (2.0 * k1 + 3.0 * k4 * r2);
+    const double xd = cd * xn + 2.0 * k2 * xn * yn + k3 * (r2 + 2.0 * xn * xn);
+    const double yd = cd * yn + k2 * (r2 + 2.0 * yn * yn) + 2.0 * k3 * xn * yn;
+    const double fa = c.K[0] * c.K[3];
+    px = c.K[0] * xd + c.K[4] * yd + c.K[1];
+    py = fa * yd + c.K[2];
+    if (P) {
+        const double j00 = cd + 2.0 * dc * xn * xn + 2.0 * k2 * yn + 6.0 * k3 * xn, j01 = 2.0 * dc * xn * yn + 2.0 * k2 * xn + 2.0 * k3 * yn;
+        const double j11 = cd + 2.0 * dc * yn * yn + 6.0 * k2 * yn + 2.0 * k3 * xn;
+        const double g00 = c.K[0] * j00 + c.K[4] * j01, g01 = c.K[0] * j01 + c.K[4] * j11, g10 = fa * j01, g11 = fa * j11;
+        P[0] = g00 * iz; P[1] = g01 * iz; P[2] = -(g00 * xn + g01 * yn) * iz;
+        P[3] = g10 * iz; P[4] = g11 * iz; P[5] = -(g10 * xn + g11 * yn) * iz;
+    }
+}
+
+// e = W (measured - projected); j = camera, k = observation
+template <class CAM>
+__device__ __forceinline__ void residual_ext(const CAM &c, const psba_ext &x, int j, int k, double X, double Y, double Z,
+                                             double mx, double my, double &e0, double &e1)
+{
+    double b0, b1, b2, b3, xc, yc, zc, px, py;
+    cam_transform(c, X, Y, Z, b0, b1, b2, b3, xc, yc, zc);
+    project_ext(c, x.kc ? x.kc + (size_t)j * 5 : nullptr, xc, yc, zc, px, py, nullptr);
+    e0 = mx - px; e1 = my - py;
+    if (x.wgt) { const double *w = x.wgt + (size_t)k * 3; const double w00 = __ldg(w), w10 = __ldg(w + 1), w11 = __ldg(w + 2); e1 = w10 * e0 + w11 * e1; e0 = w00 * e0; }
+}
+
+// weighted residual + A = W d proj / d(v,t) (2x6) + B = W d proj / dX (2x3)
+__device__ __forceinline__ void residual_jac_ext(const CamReg &c, const psba_ext &x, int j, int k, double X, double Y, double Z,
+                                                 double mx, double my, double &e0, double &e1, double *A, double *B)
+{
+    double b0, b1, b2, b3, xc, yc, zc, px, py, P[6];
+    cam_transform(c, X, Y, Z, b0, b1, b2, b3, xc, yc, zc);
+    project_ext(c, x.kc ? x.kc + (size_t)j * 5 : nullptr, xc, yc, zc, px, py, P);
+    e0 = mx - px; e1 = my - py;
+    if (x.wgt) {
+        const double *w = x.wgt + (size_t)k * 3;
+        const double w00 = __ldg(w), w10 = __ldg(w + 1), w11 = __ldg(w + 2);
+        e1 = w10 * e0 + w11 * e1; e0 = w00 * e0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { P[3 + q] = w10 * P[q] + w11 * P[3 + q]; P[q] = w00 * P[q]; }
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const double ds = c.D[4 * q], dx = c.D[4 * q + 1], dy = c.D[4 * q + 2], dz = c.D[4 * q + 3];
+        const double d0 = 2.0 * (ds * b1 + b0 * dx + dy * b3 - dz * b2);
+        const double d1 = 2.0 * (ds * b2 + b0 * dy + dz * b1 - dx * b3);
+        const double d2 = 2.0 * (ds * b3 + b0 * dz + dx * b2 - dy * b1);
+        A[q] = P[0] * d0 + P[1] * d1 + P[2] * d2;
+        A[6 + q] = P[3] * d0 + P[4] * d1 + P[5] * d2;
+        A[3 + q] = P[q]; A[9 + q] = P[3 + q];
+    }
+    const double s = c.q[0], qx = c.q[1], qy = c.q[2], qz = c.q[3];
+    const double m00 = s * s + qx * qx - qy * qy - qz * qz, m01 = 2 * (qx * qy - s * qz), m02 = 2 * (qx * qz + s * qy);
+    const double m10 = 2 * (qx * qy + s * qz), m11 = s * s - qx * qx + qy * qy - qz * qz, m12 = 2 * (qy * qz - s * qx);
+    const double m20 = 2 * (qx * qz - s * qy), m21 = 2 * (qy * qz + s * qx), m22 = s * s - qx * qx - qy * qy + qz * qz;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        B[r * 3] = P[r * 3] * m00 + P[r * 3 + 1] * m10 + P[r * 3 + 2] * m20;
+        B[r * 3 + 1] = P[r * 3] * m01 + P[r * 3 + 1] * m11 + P[r * 3 + 2] * m21;
+        B[r * 3 + 2] = P[r * 3] * m02 + P[r * 3 + 1] * m12 + P[r * 3 + 2] * m22;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // deterministic block reduction of NV per-thread values (fixed summation order, no atomics):
 // values are staged through shared memory G at a time; 8 lanes sum interleaved slices of each
 // value's column, then a 3-step shuffle tree combines the 8 slices.  sh must hold G*(NT+4) doubles.

@@ -71,11 +71,14 @@ static int count_doubles(const char *s)
     return n;
 }
 
-extern "C" int psba_readInitialSBAEstimate(const char *camsfname, const char *ptsfname, int origin_cnp,
-                                           const double *Kdefault, int *ncams, int *n3Dpts, int *n2Dprojs,
-                                           double **Kparas, double **initrot, double **camsEx, double **pts,
-                                           double **imgpts, int **iidx, int **jidx)
+static int read_sba_impl(const char *camsfname, const char *ptsfname, int origin_cnp,
+                         const double *Kdefault, int *ncams, int *n3Dpts, int *n2Dprojs,
+                         double **Kparas, double **initrot, double **camsEx, double **pts,
+                         double **imgpts, int **iidx, int **jidx, double **kc_out, double **cov_out, int *covsz_out)
 {
+    if (kc_out) *kc_out = nullptr;
+    if (cov_out) *cov_out = nullptr;
+    if (covsz_out) *covsz_out = 0;
     if (origin_cnp != 6 && origin_cnp != 11 && origin_cnp != 16) {
         fprintf(stderr, "psba_readInitialSBAEstimate: origin_cnp must be 6, 11 or 16\n");
         return 1;
@@ -101,8 +104,9 @@ extern "C" int psba_readInitialSBAEstimate(const char *camsfname, const char *pt
     double *K = (double *)malloc(sizeof(double) * m * 5), *rot = (double *)malloc(sizeof(double) * m * 4);
     double *ex = (double *)malloc(sizeof(double) * m * 6);
     double *P = nullptr;
+    double *kcv = (kc_out && origin_cnp == 16) ? (double *)malloc(sizeof(double) * m * 5) : nullptr;
     // every error return below gives back what was allocated so far (the reference exits instead)
-    auto fail = [&](int code) { free(K); free(rot); free(ex); free(P); return code; };
+    auto fail = [&](int code) { free(K); free(rot); free(ex); free(P); free(kcv); return code; };
     std::vector<double> raw(filecnp), filt(origin_cnp);
     for (int j = 0; j < m; ++j) {
         const char *s = cl[j];
@@ -120,6 +124,7 @@ extern "C" int psba_readInitialSBAEstimate(const char *camsfname, const char *pt
         // main.cpp:131-149: K | (local rotation := 0) | t ; distortion columns (varKD) are dropped,
         // the reference has no distortion model
         for (int k = 0; k < 5; ++k) K[j * 5 + k] = origin_cnp >= 11 ? filt[k] : (Kdefault ? Kdefault[k] : 0.0);
+        if (kcv) for (int k = 0; k < 5; ++k) kcv[j * 5 + k] = filt[5 + k];       // varKD: columns 6-10 (quat2vec copies nin - 7 leading values)
         ex[j * 6] = ex[j * 6 + 1] = ex[j * 6 + 2] = 0.0;
         for (int k = 0; k < 3; ++k) ex[j * 6 + 3 + k] = filt[origin_cnp - 3 + k];
     }
@@ -136,7 +141,7 @@ extern "C" int psba_readInitialSBAEstimate(const char *camsfname, const char *pt
         else if (rest == nframes * (mnp + 1 + mnp * (mnp + 1) / 2)) covvals = mnp * (mnp + 1) / 2;
     }
     P = (double *)malloc(sizeof(double) * (size_t)n * 3);
-    std::vector<double> im; std::vector<int> ii, jj;
+    std::vector<double> im, cv; std::vector<int> ii, jj;
     im.reserve((size_t)n * 10); ii.reserve((size_t)n * 5); jj.reserve((size_t)n * 5);
     bool warned = false;
     for (int i = 0; i < n; ++i) {
@@ -165,7 +170,7 @@ extern "C" int psba_readInitialSBAEstimate(const char *camsfname, const char *pt
                 if (e == s) { fprintf(stderr, "readPointParamsAndProjections(): error reading image projections from line %d\n", i + 1); return fail(11); }
                 im.push_back(v); s = e;
             }
-            for (int k = 0; k < covvals; ++k) { strtod(s, &e); s = e; }   // covariances are parsed and dropped (never used by any kernel)
+            for (int k = 0; k < covvals; ++k) { const double v = strtod(s, &e); s = e; if (cov_out) cv.push_back(v); }   // the reference parses them and no kernel uses them
             ii.push_back(i); jj.push_back((int)frameno);
         }
         // generate_idxs scans the visibility mask with cameras ascending (misc.cpp:191-196) while the reference leaves
@@ -178,9 +183,18 @@ extern "C" int psba_readInitialSBAEstimate(const char *camsfname, const char *pt
             std::vector<size_t> ord(cnt);
             for (size_t q = 0; q < cnt; ++q) ord[q] = q;
             std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) { return jj[first + a] < jj[first + b]; });
-            std::vector<int> js(cnt); std::vector<double> ms(cnt * mnp);
-            for (size_t q = 0; q < cnt; ++q) { js[q] = jj[first + ord[q]]; for (int k = 0; k < mnp; ++k) ms[q * mnp + k] = im[(first + ord[q]) * mnp + k]; }
-            for (size_t q = 0; q < cnt; ++q) { jj[first + q] = js[q]; for (int k = 0; k < mnp; ++k) im[(first + q) * mnp + k] = ms[q * mnp + k]; }
+            std::vector<int> js(cnt); std::vector<double> ms(cnt * mnp), cs(cnt * covvals);
+            const bool hc = cov_out && covvals;
+            for (size_t q = 0; q < cnt; ++q) {
+                js[q] = jj[first + ord[q]];
+                for (int k = 0; k < mnp; ++k) ms[q * mnp + k] = im[(first + ord[q]) * mnp + k];
+                if (hc) for (int k = 0; k < covvals; ++k) cs[q * covvals + k] = cv[(first + ord[q]) * covvals + k];
+            }
+            for (size_t q = 0; q < cnt; ++q) {
+                jj[first + q] = js[q];
+                for (int k = 0; k < mnp; ++k) im[(first + q) * mnp + k] = ms[q * mnp + k];
+                if (hc) for (int k = 0; k < covvals; ++k) cv[(first + q) * covvals + k] = cs[q * covvals + k];
+            }
         }
     }
     const size_t o = jj.size();
@@ -191,7 +205,34 @@ extern "C" int psba_readInitialSBAEstimate(const char *camsfname, const char *pt
     memcpy(J, jj.data(), sizeof(int) * o);
     *ncams = m; *n3Dpts = n; *n2Dprojs = (int)o;
     *Kparas = K; *initrot = rot; *camsEx = ex; *pts = P; *imgpts = IM; *iidx = I; *jidx = J;
+    if (kc_out) *kc_out = kcv;
+    if (cov_out && covvals && cv.size() == o * (size_t)covvals) {
+        double *CV = (double *)malloc(sizeof(double) * cv.size());
+        memcpy(CV, cv.data(), sizeof(double) * cv.size());
+        *cov_out = CV;
+        if (covsz_out) *covsz_out = covvals;
+    }
     return 0;
+}
+
+extern "C" int psba_readInitialSBAEstimate(const char *camsfname, const char *ptsfname, int origin_cnp,
+                                           const double *Kdefault, int *ncams, int *n3Dpts, int *n2Dprojs,
+                                           double **Kparas, double **initrot, double **camsEx, double **pts,
+                                           double **imgpts, int **iidx, int **jidx)
+{
+    return read_sba_impl(camsfname, ptsfname, origin_cnp, Kdefault, ncams, n3Dpts, n2Dprojs, Kparas, initrot, camsEx, pts, imgpts, iidx, jidx,
+                         nullptr, nullptr, nullptr);
+}
+
+// the same reader, also handing out what the reference parses and drops: the distortion coefficients of a varKD camera
+// file (origin_cnp = 16: kc[m*5], else NULL) and the image-point covariances (cov[o*covsz], covsz = 4 or 3, else NULL)
+extern "C" int psba_readInitialSBAEstimate_ext(const char *camsfname, const char *ptsfname, int origin_cnp,
+                                               const double *Kdefault, int *ncams, int *n3Dpts, int *n2Dprojs,
+                                               double **Kparas, double **initrot, double **camsEx, double **pts,
+                                               double **imgpts, int **iidx, int **jidx, double **kc, double **cov, int *covsz)
+{
+    return read_sba_impl(camsfname, ptsfname, origin_cnp, Kdefault, ncams, n3Dpts, n2Dprojs, Kparas, initrot, camsEx, pts, imgpts, iidx, jidx,
+                         kc, cov, covsz);
 }
 
 

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(1024) k_newcams(int N, const double *__restric
 //           observation: residual of the candidate -> ||e||^2
 // EVAL=false stops after phase B (trust region: the step is formed on the host side first).
 #define PROJ_LD 14         // doubles per staged projection entry (12 + pad: conflict-free LDS.128)
-template <bool EVAL>
+template <bool EVAL, bool EXT>
 __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ chunk_list, const int4 *__restrict__ ptdesc, const int *__restrict__ pt_ptr,
                                                       const int *__restrict__ iidx, const int *__restrict__ jidx,
                                                       const double *__restrict__ impts, const double *__restrict__ W,
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ c
                                                       const double *__restrict__ dpa, const double *__restrict__ pts,
                                                       const double *__restrict__ newcache, double mu,
                                                       double *__restrict__ eb, double *__restrict__ dpb, double *__restrict__ newpts,
-                                                      double *__restrict__ part)
+                                                      double *__restrict__ part, psba_ext ext)
 {
     __shared__ __align__(16) double stage[PT_CTA * 18];      // W tile of the wave, then the projection entries (128*14 <= 128*18)
     double *pstage = stage;
@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ c
             CamProj cam;
             load_cam_proj<false>(pstage + tid * PROJ_LD, cam);
             double e0, e1;
-            residual(cam, shx[0][lp1], shx[1][lp1], shx[2][lp1], mm1.x, mm1.y, e0, e1);
+            if (EXT) residual_ext(cam, ext, jidx[k], k, shx[0][lp1], shx[1][lp1], shx[2][lp1], mm1.x, mm1.y, e0, e1);
+            else residual(cam, shx[0][lp1], shx[1][lp1], shx[2][lp1], mm1.x, mm1.y, e0, e1);
             s_e2 += e0 * e0 + e1 * e1;
         }
     } else {
@@ -186,7 +187,8 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ c
                 const int lp = iidx[k] - p0;
                 double2 mm = __ldg(reinterpret_cast<const double2 *>(impts) + k);
                 double e0, e1;
-                residual(cam, shx[0][lp], shx[1][lp], shx[2][lp], mm.x, mm.y, e0, e1);
+                if (EXT) residual_ext(cam, ext, sj[tid], k, shx[0][lp], shx[1][lp], shx[2][lp], mm.x, mm.y, e0, e1);
+                else residual(cam, shx[0][lp], shx[1][lp], shx[2][lp], mm.x, mm.y, e0, e1);
                 s_e2 += e0 * e0 + e1 * e1;
             }
         }
@@ -412,15 +414,20 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
         PROF(c, KID_BACKSUB) {
             const int dyn = 2 * PT_CTA * (18 + PROJ_LD) * (int)sizeof(double);
             psba_set_smem((const void *)k_backsub_pipe<0>, dyn);
-            const int gs = std::min(c->n_small, c->n_sm * 3);      // persistent CTAs: one partial each
-            if (c->n_small > 0)
+            int gs = std::min(c->n_small, c->n_sm * 3);      // persistent CTAs: one partial each
+            if (c->ext_on) {       // extended camera model: the one-shot kernel evaluates the candidate (one partial per chunk)
+                gs = c->n_ptchunk;
+                if (gs > 0)
+                    k_backsub<true, true><<<gs, PT_CTA, 0, c->stream>>>(nullptr, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv, gb, c->dp,
+                                                                       c->pts[cur], c->camcache[nw], mu, ebp, dpbp, c->pts[nw], c->d_part, c->ext);
+            } else if (c->n_small > 0)
                 k_backsub_pipe<0><<<gs, PT_CTA, dyn, c->stream>>>(c->n_small, c->d_small_list, c->ptdesc, c->pt_ptr, c->iidx,
                                                               c->jidx, c->impts, c->W, c->Vinv, gb, c->dp, c->pts[cur],
                                                               c->camcache[nw], mu, ebp, dpbp, c->pts[nw], c->d_part);
-            if (c->n_big > 0)      // points with more observations than one wave: one partial per CTA behind the others
-                k_backsub<true><<<c->n_big, PT_CTA, 0, c->stream>>>(c->d_big_list, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
-                                                                   gb, c->dp, c->pts[cur], c->camcache[nw], mu, ebp, dpbp, c->pts[nw], c->d_part + (size_t)gs * 4);
-            n_part = gs + c->n_big;
+            if (c->n_big > 0 && !c->ext_on)      // points with more observations than one wave: one partial per CTA behind the others
+                k_backsub<true, false><<<c->n_big, PT_CTA, 0, c->stream>>>(c->d_big_list, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
+                                                                   gb, c->dp, c->pts[cur], c->camcache[nw], mu, ebp, dpbp, c->pts[nw], c->d_part + (size_t)gs * 4, c->ext);
+            n_part = c->ext_on ? gs : gs + c->n_big;
         }
         PROF(c, KID_REDUCE) k_final_reduce4<<<1, 1024, 0, c->stream>>>(c->d_part, n_part, c->d_scal);
         c->st_launches += 3; c->st_exqt += 1;
@@ -437,9 +444,9 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
         }
     } else {
         if (c->n_ptchunk > 0)
-            PROF(c, KID_BACKSUB) k_backsub<false><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(nullptr, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
+            PROF(c, KID_BACKSUB) k_backsub<false, false><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(nullptr, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
                                                                     gb, c->dp, c->pts[cur], c->camcache[cur], mu, ebp, dpbp,
-                                                                    c->pts[nw], c->d_part);
+                                                                    c->pts[nw], c->d_part, c->ext);
         c->st_launches += 1;
         LAUNCH_CHECK();
     }

@@ -76,10 +76,11 @@ __global__ void k_final_reduce(const double *__restrict__ part, int nparts, int 
 }
 
 // residual + cost. One thread per observation (coalesced impts / idx loads, cached gathers).
+template <bool EXT>
 __global__ void __launch_bounds__(256) k_cost(int o, const int *__restrict__ iidx, const int *__restrict__ jidx,
                                               const double *__restrict__ impts, const double *__restrict__ cache,
                                               const double *__restrict__ pts, double *__restrict__ ex,
-                                              double *__restrict__ part)
+                                              double *__restrict__ part, psba_ext ext)
 {
     __shared__ double sh[8];
     int k = blockIdx.x * 256 + threadIdx.x;
@@ -90,7 +91,8 @@ __global__ void __launch_bounds__(256) k_cost(int o, const int *__restrict__ iid
         const double *X = pts + (size_t)iidx[k] * 3;
         double2 mm = __ldg(reinterpret_cast<const double2 *>(impts) + k);
         double e0, e1;
-        residual(cam, __ldg(X), __ldg(X + 1), __ldg(X + 2), mm.x, mm.y, e0, e1);
+        if (EXT) residual_ext(cam, ext, jidx[k], k, __ldg(X), __ldg(X + 1), __ldg(X + 2), mm.x, mm.y, e0, e1);
+        else residual(cam, __ldg(X), __ldg(X + 1), __ldg(X + 2), mm.x, mm.y, e0, e1);
         if (ex) reinterpret_cast<double2 *>(ex)[k] = make_double2(e0, e1);
         e2 = e0 * e0 + e1 * e1;
     }
@@ -117,7 +119,10 @@ double psba_launch_cost(psba_ctx *c, int set, double *ex_dev)
     if (!c->cache_valid[set]) psba_launch_cam_prep(c, set);
     int nb = cdiv(c->o, 256);
     if (nb > 0)
-        PROF(c, KID_COST) k_cost<<<nb, 256, 0, c->stream>>>(c->o, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set], ex_dev, c->d_part);
+        PROF(c, KID_COST) {
+            if (c->ext_on) k_cost<true><<<nb, 256, 0, c->stream>>>(c->o, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set], ex_dev, c->d_part, c->ext);
+            else k_cost<false><<<nb, 256, 0, c->stream>>>(c->o, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set], ex_dev, c->d_part, c->ext);
+        }
     PROF(c, KID_REDUCE) k_final_reduce<<<1, 256, 0, c->stream>>>(c->d_part, nb, 1, 1, c->d_scal);
     c->st_launches += 2; c->st_exqt += 1;
     LAUNCH_CHECK();
@@ -136,11 +141,12 @@ double psba_launch_cost(psba_ctx *c, int set, double *ex_dev)
 //      ascending camera order (the order of compute_V.cl:24-31 / compute_g.cl:43-54);
 //   3. the W tile (128 x 144 B, contiguous in HBM because observations are point-major) is written
 //      with fully coalesced 16-byte stores.
+template <bool EXT>
 __global__ void __launch_bounds__(PT_CTA, 4) k_lin_points(const int *__restrict__ chunk_list, const int4 *__restrict__ ptdesc, const int *__restrict__ pt_ptr,
                                                          const int *__restrict__ iidx, const int *__restrict__ jidx,
                                                          const double *__restrict__ impts, const double *__restrict__ cache,
                                                          const double *__restrict__ pts, double coeff, double coeff_g,
-                                                         double *__restrict__ W, double *__restrict__ V, double *__restrict__ gb)
+                                                         double *__restrict__ W, double *__restrict__ V, double *__restrict__ gb, psba_ext ext)
 {
     __shared__ __align__(16) double stage[PT_CTA * CAM_LD];      // camera entries, then the W tile (128*18 <= 128*26)
     __shared__ double sh[9][PT_CTA];
@@ -188,7 +194,8 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_lin_points(const int *__restrict_
             CamReg cam;
             load_cam<false>(stage + tid * CAM_LD, cam);
             double e0, e1, A[12], B[6];
-            residual_jac(cam, X0, X1, X2, mm.x, mm.y, e0, e1, A, B);
+            if (EXT) residual_jac_ext(cam, ext, ji, k, X0, X1, X2, mm.x, mm.y, e0, e1, A, B);
+            else residual_jac(cam, X0, X1, X2, mm.x, mm.y, e0, e1, A, B);
 #pragma unroll
             for (int r = 0; r < 6; ++r)
 #pragma unroll
@@ -361,11 +368,12 @@ __global__ void __launch_bounds__(PT_CTA, 3) k_lin_points_pipe(int n_list, const
 // The camera cache entry is uniform per CTA; points and measurements are gathered (L2-resident).
 // Each thread accumulates A^T A (21 upper entries) and A^T e (6) over its observations, then one
 // deterministic block reduction per chunk writes 27 partials.
+template <bool EXT>
 __global__ void __launch_bounds__(CAM_CTA, 4) k_lin_cams(const int *__restrict__ cchunk_cam, const int *__restrict__ cchunk_beg,
                                                         const int *__restrict__ cchunk_end, const int *__restrict__ cam_pt,
                                                         const double *__restrict__ cam_impts,
                                                         const double *__restrict__ cache, const double *__restrict__ pts,
-                                                        double *__restrict__ part)
+                                                        double *__restrict__ part, const int *__restrict__ cam_obs, psba_ext ext)
 {
     __shared__ double sh[16 * (CAM_CTA + 4)];
     const int ch = blockIdx.x;
@@ -382,7 +390,8 @@ __global__ void __launch_bounds__(CAM_CTA, 4) k_lin_cams(const int *__restrict__
         const double *X = pts + (size_t)__ldg(cam_pt + t) * 3;
         double2 mm = __ldg(reinterpret_cast<const double2 *>(cam_impts) + t);
         double e0, e1, A[12], B[6];
-        residual_jac(cam, __ldg(X), __ldg(X + 1), __ldg(X + 2), mm.x, mm.y, e0, e1, A, B);
+        if (EXT) residual_jac_ext(cam, ext, cchunk_cam[ch], __ldg(cam_obs + t), __ldg(X), __ldg(X + 1), __ldg(X + 2), mm.x, mm.y, e0, e1, A, B);
+        else residual_jac(cam, __ldg(X), __ldg(X + 1), __ldg(X + 2), mm.x, mm.y, e0, e1, A, B);
         int q = 0;
 #pragma unroll
         for (int r = 0; r < 6; ++r)
@@ -427,8 +436,12 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
         cs = c->stream2;
     }
     if (c->n_cchunk > 0)
-        PROF(c, KID_LIN_CAMS) k_lin_cams<<<c->n_cchunk, CAM_CTA, 0, cs>>>(c->cchunk_cam, c->cchunk_beg, c->cchunk_end, c->cam_pt,
-                                                          c->cam_impts, c->camcache[set], c->pts[set], c->cam_part);
+        PROF(c, KID_LIN_CAMS) {
+            if (c->ext_on) k_lin_cams<true><<<c->n_cchunk, CAM_CTA, 0, cs>>>(c->cchunk_cam, c->cchunk_beg, c->cchunk_end, c->cam_pt, c->cam_impts,
+                                                                          c->camcache[set], c->pts[set], c->cam_part, c->cam_obs, c->ext);
+            else k_lin_cams<false><<<c->n_cchunk, CAM_CTA, 0, cs>>>(c->cchunk_cam, c->cchunk_beg, c->cchunk_end, c->cam_pt, c->cam_impts,
+                                                                 c->camcache[set], c->pts[set], c->cam_part, c->cam_obs, c->ext);
+        }
     // N > 1 GPUs: ga goes right behind U so that ONE all-reduce sums both
     double *ga_out = c->nranks > 1 ? c->U + (size_t)c->m * 36 : c->g;
     PROF(c, KID_CAM_REDUCE) k_cam_reduce<<<cdiv(c->m * 27, 128), 128, 0, cs>>>(c->m, c->cam_cchunk_ptr, c->cam_part, coeff_uvw, coeff_g,
@@ -441,17 +454,20 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
             // Venice-52, 2 700 chunks: 57 us against 31 us for the one-shot kernel)
             static const int pipe_env = getenv("PSBA_LIN_PIPE") ? atoi(getenv("PSBA_LIN_PIPE")) : -1;
             const bool pipe = pipe_env >= 0 ? pipe_env != 0 : c->n_small >= 8 * c->n_sm * 3;
-            if (!pipe)
-                k_lin_points<<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(nullptr, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set],
-                                                                    coeff_uvw, coeff_g, c->W, c->V, c->g + c->N);
+            if (c->ext_on)     // extended camera model (distortion / residual weights): the one-shot kernel carries it
+                k_lin_points<true><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(nullptr, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set],
+                                                                          coeff_uvw, coeff_g, c->W, c->V, c->g + c->N, c->ext);
+            else if (!pipe)
+                k_lin_points<false><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(nullptr, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set],
+                                                                    coeff_uvw, coeff_g, c->W, c->V, c->g + c->N, c->ext);
             else {
                 if (c->n_small > 0)
                     k_lin_points_pipe<0><<<std::min(c->n_small, c->n_sm * 3), PT_CTA, dyn, c->stream>>>(c->n_small, c->d_small_list, c->ptdesc, c->pt_ptr, c->iidx, c->jidx,
                                                                                                      c->impts, c->camcache[set], c->pts[set], coeff_uvw, coeff_g,
                                                                                                      c->W, c->V, c->g + c->N);
                 if (c->n_big > 0)      // points with more observations than one wave
-                    k_lin_points<<<c->n_big, PT_CTA, 0, c->stream>>>(c->d_big_list, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set],
-                                                                    coeff_uvw, coeff_g, c->W, c->V, c->g + c->N);
+                    k_lin_points<false><<<c->n_big, PT_CTA, 0, c->stream>>>(c->d_big_list, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set],
+                                                                    coeff_uvw, coeff_g, c->W, c->V, c->g + c->N, c->ext);
             }
         }
     if (fork) {
@@ -472,7 +488,7 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
 // compat only: materialise JA (o x 2 x 6) and JB (o x 2 x 3) in the reference's layout
 __global__ void k_jac_materialize(int o, const int *__restrict__ iidx, const int *__restrict__ jidx,
                                   const double *__restrict__ impts, const double *__restrict__ cache,
-                                  const double *__restrict__ pts, double *__restrict__ JA, double *__restrict__ JB)
+                                  const double *__restrict__ pts, double *__restrict__ JA, double *__restrict__ JB, psba_ext ext)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= o) return;
@@ -480,7 +496,8 @@ __global__ void k_jac_materialize(int o, const int *__restrict__ iidx, const int
     load_cam<true>(cache + (size_t)jidx[k] * CAMC, cam);
     const double *X = pts + (size_t)iidx[k] * 3;
     double e0, e1, A[12], B[6];
-    residual_jac(cam, X[0], X[1], X[2], impts[2 * k], impts[2 * k + 1], e0, e1, A, B);
+    if (ext.kc || ext.wgt) residual_jac_ext(cam, ext, jidx[k], k, X[0], X[1], X[2], impts[2 * k], impts[2 * k + 1], e0, e1, A, B);
+    else residual_jac(cam, X[0], X[1], X[2], impts[2 * k], impts[2 * k + 1], e0, e1, A, B);
     for (int q = 0; q < 12; ++q) JA[(size_t)k * 12 + q] = A[q];
     for (int q = 0; q < 6; ++q) JB[(size_t)k * 6 + q] = B[q];
 }
@@ -491,7 +508,7 @@ void psba_launch_jac_materialize(psba_ctx *c, double *JA, double *JB)
     if (!c->cache_valid[set]) psba_launch_cam_prep(c, set);
     if (c->o > 0)
         k_jac_materialize<<<cdiv(c->o, 128), 128, 0, c->stream>>>(c->o, c->iidx, c->jidx, c->impts, c->camcache[set],
-                                                                 c->pts[set], JA, JB);
+                                                                 c->pts[set], JA, JB, c->ext);
     c->st_launches += 1;
     LAUNCH_CHECK();
 }
@@ -503,7 +520,7 @@ __global__ void __launch_bounds__(256) k_Jdot(int o, int N, const int *__restric
                                               const double *__restrict__ impts, const double *__restrict__ cache,
                                               const double *__restrict__ pts, const double *__restrict__ x,
                                               const double *__restrict__ y, double *__restrict__ Jx_out,
-                                              double *__restrict__ part)
+                                              double *__restrict__ part, psba_ext ext)
 {
     __shared__ double sh[3][8];
     int k = blockIdx.x * 256 + threadIdx.x;
@@ -514,7 +531,8 @@ __global__ void __launch_bounds__(256) k_Jdot(int o, int N, const int *__restric
         load_cam<true>(cache + (size_t)j * CAMC, cam);
         const double *X = pts + (size_t)i * 3;
         double e0, e1, A[12], B[6];
-        residual_jac(cam, __ldg(X), __ldg(X + 1), __ldg(X + 2), 0.0, 0.0, e0, e1, A, B);
+        if (ext.kc || ext.wgt) residual_jac_ext(cam, ext, j, k, __ldg(X), __ldg(X + 1), __ldg(X + 2), 0.0, 0.0, e0, e1, A, B);
+        else residual_jac(cam, __ldg(X), __ldg(X + 1), __ldg(X + 2), 0.0, 0.0, e0, e1, A, B);
         const double *xa = x + j * 6, *xb = x + N + (size_t)i * 3;
         const double *ya = y + j * 6, *yb = y + N + (size_t)i * 3;
         double jx[2], jy[2];
@@ -555,7 +573,7 @@ void psba_launch_Jdot(psba_ctx *c, const double *x, const double *y, double *Jx_
     int nb = cdiv(c->o, 256);
     if (nb > 0)
         PROF(c, KID_JDOT) k_Jdot<<<nb, 256, 0, c->stream>>>(c->o, c->N, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set],
-                                         x, y, Jx_out, c->d_part);
+                                         x, y, Jx_out, c->d_part, c->ext);
     PROF(c, KID_REDUCE) k_final_reduce<<<1, 256, 0, c->stream>>>(c->d_part, nb, 3, 3, c->d_scal);
     c->st_launches += 2;
     LAUNCH_CHECK();

@@ -136,6 +136,7 @@ __global__ void k_mat_max(int N, const double *__restrict__ mat, double *__restr
 __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ mat, double *__restrict__ aux, double *__restrict__ diagInv,
                                                   double *__restrict__ diag, double beta, double delta, int *__restrict__ nscalar_out)
 {
+    extern __shared__ double rows3[];                    // [3][N]: the finished factor rows j3 .. j3+2 (columns < j3) of the current block
     __shared__ double T[9], L[6], inv[9];
     __shared__ int fail, over, flagged;
     __shared__ double theta_s;
@@ -143,12 +144,17 @@ __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ ma
     int nscalar = 0;
     for (int j = 0; j < nb; ++j) {
         const int j3 = j * 3;
+        // the three pivot rows are read by nine threads running sequential dot products (T_jj) and by every row of the
+        // block column: staged once by the whole CTA (the nine threads alone paid one L2 round trip per term: 24 us per block)
+        for (int e = tid; e < 3 * j3; e += 1024) { const int v = e / j3, cc = e - v * j3; rows3[v * N + cc] = M(j3 + v, cc); }
+        __syncthreads();
         if (tid < 9) {   // back up A_jj, diag; T_jj (cholmod_blk.cl:107-129)
             const int u = tid / 3, v = tid % 3;
             double sum = M(j3 + u, j3 + v);
             aux[j * 9 + tid] = sum;
             if (u == v) diag[j * 3 + u] = sum;
-            for (int k = 0; k < j; ++k) sum -= M(j3 + u, k * 3) * M(j3 + v, k * 3) + M(j3 + u, k * 3 + 1) * M(j3 + v, k * 3 + 1) + M(j3 + u, k * 3 + 2) * M(j3 + v, k * 3 + 2);
+            const double *ru = rows3 + u * N, *rv = rows3 + v * N;
+            for (int k = 0; k < j; ++k) sum -= ru[k * 3] * rv[k * 3] + ru[k * 3 + 1] * rv[k * 3 + 1] + ru[k * 3 + 2] * rv[k * 3 + 2];
             T[tid] = sum;
         }
         if (tid == 0) { fail = 0; over = 0; }
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ ma
                 for (int k = 0; k < j; ++k) {               // per entry the reference's order: ascending k (cholmod_blk.cl:318-331)
                     const double a0 = M(row, k * 3), a1 = M(row, k * 3 + 1), a2 = M(row, k * 3 + 2);
 #pragma unroll
-                    for (int v = 0; v < 3; ++v) Tij[v] -= a0 * M(j3 + v, k * 3) + a1 * M(j3 + v, k * 3 + 1) + a2 * M(j3 + v, k * 3 + 2);
+                    for (int v = 0; v < 3; ++v) Tij[v] -= a0 * rows3[v * N + k * 3] + a1 * rows3[v * N + k * 3 + 1] + a2 * rows3[v * N + k * 3 + 2];
                 }
                 for (int v = 0; v < 3; ++v) {
                     const double sum = Tij[0] * inv[v * 3] + Tij[1] * inv[v * 3 + 1] + Tij[2] * inv[v * 3 + 2];
@@ -296,7 +302,10 @@ double psba_launch_cholmod_dense(psba_ctx *c, int N, double *mat, double *aux, d
     double beta = fmax(gamma, 1e-15);
     beta = fmax(beta, xi / sqrt((double)N * N - 1));
     beta = sqrt(beta);
-    PROF(c, KID_CHOLMOD) k_cholmod<<<1, 1024, 0, c->stream>>>(N, mat, aux, diagInv, E, beta, delta, c->d_status + 2);
+    const int dyn = 3 * N * (int)sizeof(double);
+    if (dyn > 200 * 1024) { fprintf(stderr, "psba_b200: dense modified Cholesky: N = %d is beyond the single-CTA kernel (the tile-pool version handles it)\n", N); exit(EXIT_FAILURE); }
+    psba_set_smem((const void *)k_cholmod, dyn);
+    PROF(c, KID_CHOLMOD) k_cholmod<<<1, 1024, dyn, c->stream>>>(N, mat, aux, diagInv, E, beta, delta, c->d_status + 2);
     k_cholmod_E<<<cdiv(N, 128), 128, 0, c->stream>>>(N, mat, E);
     c->st_launches += 3;
     LAUNCH_CHECK();

@@ -78,6 +78,7 @@ extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3D
     CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     c->cur = 0; c->cache_valid[0] = c->cache_valid[1] = false;
+    c->ext.kc = c->ext.wgt = nullptr; c->ext_on = false;
     c->lin_valid = false; c->S_valid = false; c->factor_valid = false; c->chol_graph_ok = false; c->bw_graph_ok = false;
     c->Sdense = c->Sdense_aux = nullptr; c->tmpA = c->tmpB = nullptr;
     c->mu_pending = 0.0; c->coeff_uvw = 1.0; c->coeff_g = 1.0;
@@ -88,9 +89,9 @@ extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3D
     for (int k = 0; k < KID_COUNT; ++k) { c->prof_ms[k] = 0; c->prof_n[k] = 0; }
     c->comm = nullptr;
     { int dev = 0; CUDA_CHECK(cudaGetDevice(&dev)); CUDA_CHECK(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, dev)); }
-    c->d_small_list = c->d_big_list = nullptr; c->n_small = c->n_big = 0; c->rblk_src = nullptr;
-    c->rows_ok = false; c->rchunk_desc = nullptr; c->rchunk_first = nullptr; c->vis_desc = nullptr; c->tri_meta = nullptr; c->rseg_row = nullptr; c->rseg_chunks = nullptr;
-    c->rseg_slot_base = nullptr; c->rseg_runs = nullptr; c->row_pair0 = nullptr; c->row_seg_ptr = nullptr; c->n_rchunk = c->n_rseg = c->n_rpart = 0;
+    c->d_small_list = c->d_big_list = nullptr; c->n_small = c->n_big = 0;
+    c->n_seg = 0; c->seg_desc = nullptr; c->sched_chunk = nullptr; c->sch_beg = c->sch_end = nullptr; c->tri_vr = nullptr;
+    c->pchunk_pair = nullptr; c->pchunk_beg = c->pchunk_end = nullptr;
     c->chol_pdl = !(getenv("PSBA_NO_PDL") && atoi(getenv("PSBA_NO_PDL")));
     c->stage_impts = c->stage_pts = nullptr;
     c->K = dalloc<double>(c, (size_t)nCams * 5);
@@ -176,7 +177,7 @@ extern "C" void psba_fill_idxBuffer(psba_ctx *c, int nCams, int n3Dpts, int n2Dp
     c->g = dalloc<double>(c, Tl); c->dp = dalloc<double>(c, Tl); c->eab = dalloc<double>(c, Tl);
     c->P_U = dalloc<double>(c, Tl); c->P_B = dalloc<double>(c, Tl); c->P = dalloc<double>(c, Tl);
     c->cam_part = dalloc<double>(c, (size_t)c->n_cchunk * 27);
-    c->pair_part = dalloc<double>(c, (size_t)std::max(c->n_pchunk, c->n_rpart) * 42);
+    c->pair_part = dalloc<double>(c, (size_t)c->n_pchunk * 42);
     c->d_part = dalloc<double>(c, ((size_t)cdiv(o, 128) + c->n_ptchunk + 512) * 8);
     c->chol_aux = dalloc<double>(c, (size_t)3 * c->N + 2 * TS);
     c->chol_diag = dalloc<double>(c, (size_t)3 * c->N + 2 * TS);
@@ -200,8 +201,7 @@ extern "C" void psba_release_buffer(psba_ctx *c)
                     c->d_psrc_ptr, c->d_psrc, c->d_b_J, c->d_b_sptr, c->d_b_slot, c->d_def_I, c->d_def_J, c->d_def_sptr, c->d_def_src,
                     c->d_step_panels, c->d_crit_desc, c->d_def_desc, c->d_crit_src, c->d_def_srcs, c->d_bw_order, c->d_xdone, c->contrib, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
                     c->Sdense, c->Sdense_aux, c->chol_aux, c->chol_diag, c->chol_E, c->d_part, c->d_scal, c->P_U, c->P_B, c->P,
-                    c->tmpA, c->tmpB, c->rblk_src, c->rchunk_desc, c->rchunk_first, c->vis_desc, c->tri_meta, c->rseg_row, c->rseg_chunks, c->rseg_slot_base, c->rseg_runs,
-                    c->row_pair0, c->row_seg_ptr};
+                    c->tmpA, c->tmpB, (void *)c->ext.kc, (void *)c->ext.wgt, c->seg_desc, c->sched_chunk, c->sch_beg, c->sch_end, c->tri_vr};
     for (void *p : ptrs) psba_dev_free(c, p);
     psba_dev_free(c, c->stage_impts); psba_dev_free(c, c->stage_pts);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -491,6 +491,60 @@ extern "C" void psba_set_params(psba_ctx *c, const double *cams, const double *p
     c->lin_valid = false; c->S_valid = false; c->factor_valid = false; c->mu_pending = 0.0;
 }
 
+static void ext_changed(psba_ctx *c)
+{
+    const bool force = getenv("PSBA_FORCE_EXT") && atoi(getenv("PSBA_FORCE_EXT"));   // tests: the extended kernels with kc = 0
+    c->ext_on = c->ext.kc || c->ext.wgt || force;
+    c->lin_valid = false; c->S_valid = false; c->factor_valid = false;
+}
+
+// Fixed lens distortion per camera: kc[m*5] = (k1, k2, p1, p2, k3) of the sba "varKD" camera (data/54camsvarKD.txt
+// columns 6-10; PSBA/misc.cpp:27-29 copies them through quat2vec, the reference's kernels then ignore them).
+// NULL or all-zero coefficients switch the model off (the reference's undistorted projection, bit for bit).
+extern "C" void psba_set_distortion(psba_ctx *c, const double *kc)
+{
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    psba_dev_free(c, (void *)c->ext.kc); c->ext.kc = nullptr;
+    bool any = false;
+    if (kc) for (int q = 0; q < c->m * 5; ++q) any |= kc[q] != 0.0;
+    if (any) {
+        double *d = (double *)psba_dev_alloc(c, (size_t)c->m * 5 * 8, false);
+        CUDA_CHECK(cudaMemcpyAsync(d, kc, (size_t)c->m * 5 * 8, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->ext.kc = d;
+    }
+    ext_changed(c);
+}
+
+// Image-point covariances (covimgpts of readInitialSBAEstimate, PSBA/readparams.cpp:272-283, 380-413: parsed, never used
+// by any reference kernel): cov[n2Dprojs * covsz], covsz = 4 (full 2x2, row-major) or 3 (upper triangle s00 s01 s11), for
+// ALL observations (a rank takes its slice).  The residual of observation k becomes W_k e_k with W_k^T W_k = Sigma_k^-1
+// (W = L^-1, Sigma = L L^T), as Lourakis' sba weights its residuals.  NULL switches the weights off.  Call after
+// fill_idxBuffer.  Returns 0, or 1 if a covariance is not positive definite.
+extern "C" int psba_set_covariances(psba_ctx *c, const double *cov, int covsz)
+{
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    psba_dev_free(c, (void *)c->ext.wgt); c->ext.wgt = nullptr;
+    if (cov) {
+        if (covsz != 3 && covsz != 4) die("set_covariances: covsz must be 3 or 4");
+        if (!c->iidx) die("set_covariances before fill_idxBuffer");
+        std::vector<double> w((size_t)c->o * 3);
+        for (int k = 0; k < c->o; ++k) {
+            const double *s = cov + (size_t)(c->o_off + k) * covsz;
+            const double s00 = s[0], s01 = s[1], s11 = covsz == 4 ? s[3] : s[2];
+            if (!(s00 > 0.0) || !(s00 * s11 - s01 * s01 > 0.0)) { fprintf(stderr, "psba_b200: covariance of observation %d is not positive definite\n", c->o_off + k); ext_changed(c); return 1; }
+            const double l00 = std::sqrt(s00), l10 = s01 / l00, l11 = std::sqrt(s11 - l10 * l10);
+            w[(size_t)k * 3] = 1.0 / l00; w[(size_t)k * 3 + 1] = -l10 / (l00 * l11); w[(size_t)k * 3 + 2] = 1.0 / l11;
+        }
+        double *d = (double *)psba_dev_alloc(c, std::max<size_t>(w.size(), 1) * 8, false);
+        if (!w.empty()) CUDA_CHECK(cudaMemcpyAsync(d, w.data(), w.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->ext.wgt = d;
+    }
+    ext_changed(c);
+    return 0;
+}
+
 extern "C" void psba_set_option(psba_ctx *c, const char *name, double v)
 {
     std::string s(name);
@@ -533,9 +587,9 @@ extern "C" double psba_get_stat(psba_ctx *c, const char *name)
     if (s == "n_cchunk") return c->n_cchunk;
     if (s == "n_pchunk") return c->n_pchunk;
     if (s == "pair_G") return c->pair_G;
-    if (s == "rows_ok") return c->rows_ok ? 1 : 0;
-    if (s == "n_rseg") return c->n_rseg;
-    if (s == "n_rchunk") return c->n_rchunk;
+    if (s == "pair_mode") return c->pair_mode;
+    if (s == "n_seg") return c->n_seg;
+    if (s == "seg_v") return c->seg_v;
     if (s == "cholmod_events") return c->n_cholmod_events;
     if (s == "timer_ms") {   // device time since "timer_start" on the engine's stream
         if (!c->timer_init) die("timer_ms before timer_start");
@@ -567,9 +621,14 @@ extern "C" long long psba_get_index(psba_ctx *c, const char *name, void *out, lo
     else if (s == "tri_oa") { src = c->tri_oa; cnt = c->ntri; }
     else if (s == "tri_ob") { src = c->tri_ob; cnt = c->ntri; }
     else if (s == "tri_pt") { src = c->tri_pt; cnt = c->ntri; }
-    else if (s == "pchunk_pair") { src = c->pchunk_pair; cnt = c->n_pchunk; }
-    else if (s == "pchunk_beg") { src = c->pchunk_beg; cnt = c->n_pchunk; esz = 8; }
-    else if (s == "pchunk_end") { src = c->pchunk_end; cnt = c->n_pchunk; esz = 8; }
+    else if (s == "pchunk_pair") { src = c->pchunk_pair; cnt = c->pchunk_pair ? c->n_pchunk : 0; }
+    else if (s == "pchunk_beg") { src = c->pchunk_beg; cnt = c->pchunk_beg ? c->n_pchunk : 0; esz = 8; }
+    else if (s == "pchunk_end") { src = c->pchunk_end; cnt = c->pchunk_end ? c->n_pchunk : 0; esz = 8; }
+    else if (s == "pair_chunk_ptr") { src = c->pair_chunk_ptr; cnt = c->n_pair + 1; }
+    else if (s == "chunk_beg") { src = c->sch_beg; cnt = c->sch_beg ? c->n_pchunk : 0; }
+    else if (s == "chunk_end") { src = c->sch_end; cnt = c->sch_end ? c->n_pchunk : 0; }
+    else if (s == "sched_chunk") { src = c->sched_chunk; cnt = c->sched_chunk ? c->n_pchunk : 0; }
+    else if (s == "seg_desc") { src = c->seg_desc; cnt = (long long)c->n_seg * 6; }
     else if (s == "cam2pos") { src = c->cam2pos; cnt = c->m; }
     else die("get_index: unknown table");
     if (out && cnt > 0) {

@@ -24,9 +24,8 @@
 #define CAM_OPT 4          // observations per thread in the camera-major pass
 #define PAIR_CTA 128       // threads per pair-pass CTA
 #define PAIR_TPL 24        // target triples per lane in the pair pass (lane-per-triple variant)
-#define PAIR_TPQ 64        // target triples per quad (quad-per-triple variant)
-#define ROW_MAXLEN 64      // longest prefix (observations of one point) the row kernel stages
-#define ROW_POOL_BYTES(B) (((B) + ROW_MAXLEN + 2) * 144)   // chunk pool for budget B (cost of a chunk: prefix blocks + 2 per visit)
+#define SEG_V_MAX 1400     // visits per segment: the Y tile (144 B per visit) of two resident CTAs fits one SM
+#define SEG_MAXD 384       // chunk descriptors of a segment prefetched into shared memory
 #define NSCAL 16           // size of the device scalar block
 
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
@@ -48,6 +47,8 @@ static const char *const psba_kid_name[KID_COUNT] = {
     "k_S_finalize", "chol_graph", "k_tri_solve", "k_newcams", "k_backsub", "k_reduce", "k_Jdot", "k_vec", "k_cholmod",
     "allreduce" };
 struct psba_prof_rec { int id; cudaEvent_t e0, e1; };
+// extended camera model (dev_math.cuh): per-camera distortion kc[m*5], per-observation residual weights wgt[o*3]; null = absent
+struct psba_ext { const double *kc; const double *wgt; };
 
 struct psba_ctx {
     // global sizes
@@ -62,6 +63,7 @@ struct psba_ctx {
     double *K, *initcams, *impts;
     double *stage_impts, *stage_pts;  // whole-problem uploads of fill_initBuffer2 until fill_idxBuffer slices them
     double *cams[2], *pts[2], *camcache[2];
+    psba_ext ext; bool ext_on;      // extended camera model (psba_set_distortion / psba_set_covariances); off by default
     int cur;                        // index of the "current" parameter set
     bool cache_valid[2];
     // ---- structure
@@ -80,20 +82,15 @@ struct psba_ctx {
     int n_pair; int *pair_k, *pair_l;          // pair blocks present GLOBALLY (all ranks agree)
     int *pair_chunk_ptr;                        // n_pair+1
     int pair_G;                                 // lanes per chunk in the pair pass (1..32)
-    int pair_mode;                              // 0: lane per triple (default), 1: quad per triple, 2: row sweep, 3: staged fetch, 4: row sweep without CTA barriers
-    int n_pchunk; int *pchunk_pair; long long *pchunk_beg, *pchunk_end;
-    // ---- row-sweep pair pass (k_schur_rows): CTA = segment of one camera row, thread = pair of that row
-    bool rows_ok;                   // false: a prefix or a row exceeds the kernel's caps, the pair-major kernel runs
-    int row_budget;                 // chunk budget: 304 (two CTAs per SM) or 640
-    int rows_nt;                    // threads per CTA (288: <= 128 off-diagonal pairs per row, else 544)
-    int n_rchunk, n_rseg, n_rpart;  // chunks, segments (CTAs), partial slots (sum of pairs-per-row over segments)
-    int *rchunk_first;              // n_rchunk+1: first visit (camera-major position) of every chunk
-    int *rblk_src;                  // flow kernel: observation behind every staged block, staging order
-    int4 *rchunk_desc;              // per chunk: first visit, visits, staged blocks
-    int4 *vis_desc;                 // per visit: first observation of the point, prefix length, stage slot in the chunk, point
-    unsigned *tri_meta;             // per triple: chunk in segment << 18 | visit in chunk << 10 | stage slot
-    int *rseg_row; int2 *rseg_chunks; int *rseg_slot_base; int2 *rseg_runs;
-    int *row_pair0, *row_seg_ptr;   // m+1: first pair / first segment of every camera row
+    int pair_mode;                              // 5: segment kernel (default), 0: pair-major gather kernel of round 1
+    int n_pchunk; int *pchunk_pair; long long *pchunk_beg, *pchunk_end;      // mode 0: fixed-size chunks of the pair runs
+    // ---- segment kernel (k_schur_segs): CTA = <= seg_v consecutive visits of one camera row; chunk = the triples of one
+    // camera pair inside one segment (pair-major ids: the partial slots k_S_finalize sums per pair, in segment order)
+    int seg_v, n_seg, seg_cfg;
+    void *seg_desc;                 // n_seg x {row, v0, v1, diag chunk, first / last+1 position in sched_chunk}
+    int *sched_chunk;               // off-diagonal chunk ids segment by segment, largest first
+    int *sch_beg, *sch_end;         // triple range of every chunk
+    unsigned short *tri_vr;         // per triple: rank of the visit (observation of camera k) inside its segment
     // ---- linearisation products
     double *W, *V, *Vinv, *U, *g, *UVdiag_scr;
     double coeff_uvw, coeff_g;
@@ -216,15 +213,17 @@ struct psba_prof_scope {
 #define PROF(c, id) if (psba_prof_scope prof_scope_##id{c, id})
 void psba_prof_collect(psba_ctx *c);
 
-// opt-in dynamic shared memory is an attribute per (function, device): remembered per pair, set once
-#include <set>
+// opt-in dynamic shared memory is an attribute per (function, device); it is also a LIMIT (a launch that asks for more
+// than the value set fails with "invalid argument"), so the largest request seen so far is what is set
+#include <map>
 #include <utility>
 static inline void psba_set_smem(const void *fn, int bytes)
 {
-    static std::set<std::pair<const void *, int>> done;
+    static std::map<std::pair<const void *, int>, int> done;
     int dev = 0;
     CUDA_CHECK(cudaGetDevice(&dev));
-    if (done.insert({fn, dev}).second) CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    int &cur = done[{fn, dev}];
+    if (bytes > cur) { CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); cur = bytes; }
 }
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -139,121 +139,87 @@ __global__ void k_camera_major_copy(int o, const int *__restrict__ cam_obs, cons
 }
 
 
-// ---- row-sweep pair pass (kernels_schur.cu: k_schur_rows) -----------------------------------------
-// A "visit" is an observation in camera-major order: camera k looks at point i.  The blocks a visit needs are
-// the observations of point i with camera <= k: a contiguous prefix of the point's observations (cameras
-// ascend inside a point).  Visits of one camera are cut into chunks by a running cost (prefix length + 2 per
-// visit): chunk = floor(cost_prefix / ROW_BUDGET), computable per visit without a sequential pass.
-__global__ void k_visit_len(int o, const int *__restrict__ cam_obs, const int *__restrict__ iidx, const int *__restrict__ pt_ptr,
-                            int *__restrict__ len, int *__restrict__ cam_pos, int *__restrict__ maxlen)
+// ---- segment kernel of the pair pass (kernels_schur.cu: k_schur_segs) --------------------------------------
+// A "visit" is an observation in camera-major order: camera k looks at point i.  The visits of a camera are cut into
+// segments of equal length (<= seg_v); a chunk is the set of triples of ONE camera pair whose visit (the observation of
+// camera k) lies in ONE segment -- a contiguous piece of the pair's run in the pair-sorted triple list.
+struct seg_desc_h { int row, v0, v1, diag_chunk, sched0, sched1; };
+
+__global__ void k_inverse_perm(int o, const int *__restrict__ perm, int *__restrict__ inv)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= o) return;
-    const int a = cam_obs[v];
-    const int l = a - pt_ptr[iidx[a]] + 1;
-    len[v] = l; cam_pos[a] = v;
-    atomicMax(maxlen, l);
+    if (v < o) inv[perm[v]] = v;
 }
 
-__device__ __forceinline__ int row_chunk_of(int v, int row_first, const int *__restrict__ vis_off, int budget)
-{
-    return ((vis_off[v] + 2 * v) - (vis_off[row_first] + 2 * row_first)) / budget;
-}
-
-__global__ void k_row_chunks(int RB, int m, const int *__restrict__ cam_ptr, const int *__restrict__ vis_off, int *__restrict__ nch)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= m) return;
-    const int b = cam_ptr[k], e = cam_ptr[k + 1];
-    nch[k] = e > b ? row_chunk_of(e - 1, b, vis_off, RB) + 1 : 0;
-}
-
-__global__ void k_chunk_first(int RB, int o, const int *__restrict__ cam_obs, const int *__restrict__ jidx, const int *__restrict__ cam_ptr,
-                              const int *__restrict__ vis_off, const int *__restrict__ row_chunk_base, int n_rchunk, int *__restrict__ chunk_first)
-{
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= o) return;
-    const int k = jidx[cam_obs[v]], b = cam_ptr[k];
-    const int c = row_chunk_of(v, b, vis_off, RB);
-    if (v == b || row_chunk_of(v - 1, b, vis_off, RB) != c) chunk_first[row_chunk_base[k] + c] = v;
-    if (v == o - 1) chunk_first[n_rchunk] = o;
-}
-
-__global__ void k_vis_desc(int RB, int o, const int *__restrict__ cam_obs, const int *__restrict__ iidx, const int *__restrict__ jidx,
-                           const int *__restrict__ pt_ptr, const int *__restrict__ cam_ptr, const int *__restrict__ vis_off,
-                           const int *__restrict__ row_chunk_base, const int *__restrict__ chunk_first, int4 *__restrict__ desc)
-{
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= o) return;
-    const int a = cam_obs[v], i = iidx[a], k = jidx[a], b = cam_ptr[k];
-    const int vf = chunk_first[row_chunk_base[k] + row_chunk_of(v, b, vis_off, RB)];
-    desc[v] = make_int4(pt_ptr[i], vis_off[v + 1] - vis_off[v], vis_off[v] - vis_off[vf], i);
-}
-
-// observation behind every staged block, in staging order (visit-major; the blocks of a visit are the observations
-// pt_ptr[i] .. own observation of its point)
-__global__ void k_block_src(int o, const int4 *__restrict__ desc, const int *__restrict__ vis_off, int *__restrict__ src)
-{
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= o) return;
-    const int4 d = desc[v];
-    const int b0 = vis_off[v];
-    for (int j = 0; j < d.y; ++j) src[b0 + j] = d.x + j;
-}
-
-// one 16-byte record per chunk: first visit, visits, staged blocks
-__global__ void k_chunk_desc(int n_rchunk, const int *__restrict__ chunk_first, const int4 *__restrict__ desc, const int *__restrict__ vis_off, int4 *__restrict__ cdesc)
-{
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_rchunk) return;
-    const int v0 = chunk_first[c], v1 = chunk_first[c + 1];
-    const int4 l = desc[v1 - 1];
-    cdesc[c] = make_int4(v0, v1 - v0, l.z + l.y, vis_off[v0]);       // first visit, visits, staged blocks, rank of the first staged block
-}
-
-// per triple (pair-sorted): where the row kernel finds its operands
-__global__ void k_tri_meta(int packing, int RB, long long ntri, int SC, const int *__restrict__ tri_oa, const int *__restrict__ tri_ob, const int *__restrict__ cam_pos,
-                           const int *__restrict__ jidx, const int *__restrict__ cam_ptr, const int *__restrict__ vis_off,
-                           const int *__restrict__ row_chunk_base, const int *__restrict__ chunk_first, const int4 *__restrict__ desc,
-                           unsigned *__restrict__ meta)
+// per triple: global segment id, rank of its visit in the segment, head flag of its (pair, segment) chunk
+__global__ void k_tri_segment(long long ntri, const int *__restrict__ tri_oa, const int *__restrict__ tri_ob, const int *__restrict__ jidx,
+                              const int *__restrict__ cam_pos, const int *__restrict__ cam_ptr, const int *__restrict__ seglen,
+                              const int *__restrict__ row_seg_ptr, int *__restrict__ tri_seg, unsigned short *__restrict__ tri_vr,
+                              int *__restrict__ head)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntri) return;
-    const int a = tri_oa[t], bo = tri_ob[t];
-    const int v = cam_pos[a], k = jidx[a], rb = cam_ptr[k];
-    const int cir = row_chunk_of(v, rb, vis_off, RB);
-    const int vf = chunk_first[row_chunk_base[k] + cir];
-    const int4 d = desc[v];
-    if (packing == 0) meta[t] = ((unsigned)(cir % SC) << 18) | ((unsigned)(v - vf) << 10) | (unsigned)(d.z + (bo - d.x));
-    else               // flow kernel: chunk in segment (6) | visit in chunk (8) | stage slot of W_il (9) | stage slot of the visit's own block (9)
-        meta[t] = ((unsigned)(cir % SC) << 26) | ((unsigned)(v - vf) << 18) | ((unsigned)(d.z + (bo - d.x)) << 9) | (unsigned)(d.z + d.y - 1);
+    auto seg_of = [&](long long u, int &k, int &l, int &rank) {
+        const int a = tri_oa[u];
+        k = jidx[a]; l = jidx[tri_ob[u]];
+        const int rel = cam_pos[a] - cam_ptr[k], sl = seglen[k];
+        rank = rel % sl;
+        return row_seg_ptr[k] + rel / sl;
+    };
+    int k, l, rank, kp, lp, rp;
+    const int sg = seg_of(t, k, l, rank);
+    tri_seg[t] = sg; tri_vr[t] = (unsigned short)rank;
+    int h = 1;
+    if (t > 0) { const int sp = seg_of(t - 1, kp, lp, rp); h = (sp != sg || kp != k || lp != l) ? 1 : 0; }
+    head[t] = h;
 }
 
-// triple range of every (segment, off-diagonal slot): the triples of the pair whose visit lies in the segment
-__global__ void k_seg_runs(int RB, int SC, const int *__restrict__ seg_row, const int *__restrict__ seg_slot_base, const int *__restrict__ row_seg_ptr,
-                           const int *__restrict__ row_pair0, const long long *__restrict__ tptr, const int *__restrict__ tri_oa,
-                           const int *__restrict__ cam_pos, const int *__restrict__ cam_ptr, const int *__restrict__ vis_off,
-                           int2 *__restrict__ runs)
+// chunk records at the head triples: first triple, segment, diagonal flag; the end of the previous chunk
+__global__ void k_chunk_heads(long long ntri, const int *__restrict__ head, const int *__restrict__ cid, const int *__restrict__ tri_seg,
+                              const int *__restrict__ tri_oa, const int *__restrict__ tri_ob, int n_pair, const long long *__restrict__ tptr,
+                              int *__restrict__ ch_beg, int *__restrict__ ch_end, int *__restrict__ ch_seg, int *__restrict__ ch_pair,
+                              int *__restrict__ ch_diag)
 {
-    const int s = blockIdx.x;
-    const int k = seg_row[s], j = s - row_seg_ptr[k], nseg = row_seg_ptr[k + 1] - row_seg_ptr[k];
-    const int pair0 = row_pair0[k], noff = row_pair0[k + 1] - pair0 - 1, rb = cam_ptr[k];
-    for (int slot = threadIdx.x; slot < noff; slot += blockDim.x) {
-        const long long t0 = tptr[pair0 + slot], t1 = tptr[pair0 + slot + 1];
-        long long be = t0, en = t1;
-        if (nseg > 1) {
-            auto lower = [&](int want) {         // first triple of the pair whose segment is >= want
-                long long lo = t0, hi = t1;
-                while (lo < hi) {
-                    const long long mid = (lo + hi) >> 1;
-                    if (row_chunk_of(cam_pos[tri_oa[mid]], rb, vis_off, RB) / SC < want) lo = mid + 1; else hi = mid;
-                }
-                return lo;
-            };
-            be = lower(j); en = lower(j + 1);
-        }
-        runs[seg_slot_base[s] + slot] = make_int2((int)be, (int)en);
-    }
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntri) return;
+    if (t == ntri - 1) ch_end[cid[t] - 1] = (int)ntri;
+    if (!head[t]) return;
+    const int c = cid[t] - 1;                               // cid is the inclusive scan of the head flags
+    ch_beg[c] = (int)t;
+    if (c > 0) ch_end[c - 1] = (int)t;
+    ch_seg[c] = tri_seg[t];
+    ch_diag[c] = tri_oa[t] == tri_ob[t] ? 1 : 0;
+    int lo = 0, hi = n_pair;                                // pair p with tptr[p] <= t < tptr[p + 1]
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tptr[mid] <= t) lo = mid; else hi = mid; }
+    ch_pair[c] = lo;
+}
+
+// schedule key: off-diagonal chunks segment by segment, largest first; diagonal chunks (handled by phase 1 of their
+// segment) behind everything else
+__global__ void k_chunk_keys(int n_chunk, int n_seg, const int *__restrict__ ch_beg, const int *__restrict__ ch_end, const int *__restrict__ ch_seg,
+                             const int *__restrict__ ch_diag, u64 *__restrict__ key, int *__restrict__ val, int *__restrict__ seg_diag)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunk) return;
+    val[c] = c;
+    if (ch_diag[c]) { key[c] = ((u64)n_seg << 32); seg_diag[ch_seg[c]] = c; }
+    else key[c] = ((u64)ch_seg[c] << 32) | (u64)(0x7fffffff - (ch_end[c] - ch_beg[c]));
+}
+
+// ptr[s] = first position whose key belongs to segment >= s (s = 0..n_seg; keys sorted)
+__global__ void k_sched_ptr(int n_chunk, int n_seg, const u64 *__restrict__ key, int *__restrict__ ptr)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > n_chunk) return;
+    const int cur = j < n_chunk ? (int)(key[j] >> 32) : n_seg, prev = j > 0 ? (int)(key[j - 1] >> 32) : -1;
+    for (int v = prev + 1; v <= cur; ++v) ptr[v] = j;
+}
+
+__global__ void k_fill_seg_desc(int n_seg, seg_desc_h *__restrict__ d, const int *__restrict__ seg_diag, const int *__restrict__ sptr)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    d[s].diag_chunk = seg_diag[s]; d[s].sched0 = sptr[s]; d[s].sched1 = sptr[s + 1];
 }
 
 // ---- helpers ---------------------------------------------------------------------------------------
@@ -319,102 +285,85 @@ static void sorted_triples(psba_ctx *c, int np, int p0, int o0, const int *gptr,
 }
 
 
-// tables of the row-sweep pair pass; falls back (rows_ok = false) when a prefix or a row exceeds the kernel's caps
-static void build_row_sweep(psba_ctx *c, const long long *tptr, const std::vector<int> &cptr, const std::vector<int> &pk)
+// tables of the segment kernel: segments of every camera row, (pair, segment) chunks, schedule
+static void build_segments(psba_ctx *c, const long long *tptr, const std::vector<int> &cptr)
 {
     cudaStream_t st = c->stream;
     const int m = c->m, o = c->o;
-    c->rows_ok = false; c->n_rchunk = c->n_rseg = c->n_rpart = 0;
-    if (c->pair_mode != 2 && c->pair_mode != 4) return;
-    // pairs of a row are contiguous (sorted by k, then l; the diagonal is the last one)
-    std::vector<int> row_pair0((size_t)m + 1, 0);
-    {
-        size_t q = 0;
-        for (int k = 0; k <= m; ++k) { while (q < pk.size() && pk[q] < k) ++q; row_pair0[k] = (int)q; }
+    c->n_seg = 0; c->n_pchunk = 0;
+    c->seg_cfg = getenv("PSBA_SEG_CFG") ? atoi(getenv("PSBA_SEG_CFG")) : 2;    // measured on the headline workload: 384 x 1, 1280 visits, G = 8 is the fastest shape
+    c->seg_v = c->seg_cfg >= 2 ? 1280 : 640;                 // Y tile: 144 B per visit; two resident CTAs (one for cfg 2) share the SM's 227 KB
+    if (getenv("PSBA_SEG_V")) c->seg_v = std::max(32, std::min(c->seg_cfg >= 2 ? SEG_V_MAX : 700, atoi(getenv("PSBA_SEG_V"))));
+    // ---- segments (host: m cameras)
+    std::vector<seg_desc_h> segs;
+    std::vector<int> row_seg_ptr((size_t)m + 1, 0), seglen(m, 1);
+    for (int k = 0; k < m; ++k) {
+        const int cnt = cptr[k + 1] - cptr[k];
+        if (cnt > 0) {
+            const int ns = cdiv(cnt, c->seg_v), sl = cdiv(cnt, ns);
+            seglen[k] = sl;
+            for (int b = 0; b < cnt; b += sl) segs.push_back({k, cptr[k] + b, cptr[k] + std::min(b + sl, cnt), -1, 0, 0});
+        }
+        row_seg_ptr[k + 1] = (int)segs.size();
     }
-    int max_off = 0;
-    for (int k = 0; k < m; ++k) max_off = std::max(max_off, row_pair0[k + 1] - row_pair0[k] - 1);
-    if (max_off > 384 || o == 0) return;
-    int RB = 304;
-    if (getenv("PSBA_ROW_BUDGET") && atoi(getenv("PSBA_ROW_BUDGET")) == 640 && c->pair_mode == 2) RB = 640;
-    int maxlen_cap = ROW_MAXLEN;
-    if (c->pair_mode == 4) {                              // flow kernel: (budget, stages, longest prefix) = (304,2,64) (192,3,32) (144,4,32) (112,5,32)
-        RB = 192;
-        if (getenv("PSBA_FLOW_B")) RB = atoi(getenv("PSBA_FLOW_B"));
-        if (RB != 304 && RB != 192 && RB != 144 && RB != 112) RB = 192;
-        maxlen_cap = RB == 304 ? 64 : 32;
+    c->n_seg = (int)segs.size();
+    c->pair_chunk_ptr = salloc<int>(c, (size_t)c->n_pair + 1);
+    CUDA_CHECK(cudaMemsetAsync(c->pair_chunk_ptr, 0, ((size_t)c->n_pair + 1) * 4, st));
+    c->tri_vr = salloc<unsigned short>(c, (size_t)c->ntri + 8);
+    c->seg_desc = supload(c, segs);
+    if (c->ntri == 0 || c->n_seg == 0) {
+        c->sched_chunk = salloc<int>(c, 1); c->sch_beg = salloc<int>(c, 1); c->sch_end = salloc<int>(c, 1);
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        return;
     }
-    c->row_budget = RB;
-    int *len = salloc<int>(c, (size_t)o + 1), *cam_pos = salloc<int>(c, o), *vis_off = salloc<int>(c, (size_t)o + 1);
-    int *maxlen = salloc<int>(c, 1), *cam_ptr = supload(c, cptr);
-    CUDA_CHECK(cudaMemsetAsync(maxlen, 0, sizeof(int), st));
-    CUDA_CHECK(cudaMemsetAsync(len + o, 0, sizeof(int), st));
-    k_visit_len<<<cdiv(o, 256), 256, 0, st>>>(o, c->cam_obs, c->iidx, c->pt_ptr, len, cam_pos, maxlen);
+    int *cam_pos = salloc<int>(c, o), *cam_ptr = supload(c, cptr), *d_seglen = supload(c, seglen), *d_rsp = supload(c, row_seg_ptr);
+    k_inverse_perm<<<cdiv(o, 256), 256, 0, st>>>(o, c->cam_obs, cam_pos);
+    int *tri_seg = salloc<int>(c, (size_t)c->ntri), *head = salloc<int>(c, (size_t)c->ntri), *cid = salloc<int>(c, (size_t)c->ntri);
+    k_tri_segment<<<cdiv(c->ntri, 256), 256, 0, st>>>(c->ntri, c->tri_oa, c->tri_ob, c->jidx, cam_pos, cam_ptr, d_seglen, d_rsp, tri_seg, c->tri_vr, head);
     {
         size_t tb = 0;
-        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tb, len, vis_off, o + 1, st));
+        CUDA_CHECK(cub::DeviceScan::InclusiveSum(nullptr, tb, head, cid, (int)c->ntri, st));
         void *tmp = psba_dev_alloc(c, std::max<size_t>(tb, 16), false);
-        CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tb, len, vis_off, o + 1, st));
+        CUDA_CHECK(cub::DeviceScan::InclusiveSum(tmp, tb, head, cid, (int)c->ntri, st));
         psba_dev_free(c, tmp);
     }
-    int *nch = salloc<int>(c, m);
-    k_row_chunks<<<cdiv(m, 256), 256, 0, st>>>(RB, m, cam_ptr, vis_off, nch);
-    std::vector<int> hnch(m);
-    int hmax = 0;
-    CUDA_CHECK(cudaMemcpyAsync(hnch.data(), nch, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaMemcpyAsync(&hmax, maxlen, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int n_chunk = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n_chunk, cid + (c->ntri - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));                 // also: the host vectors behind the uploads above are done with
+    c->n_pchunk = n_chunk;
+    c->sch_beg = salloc<int>(c, n_chunk); c->sch_end = salloc<int>(c, n_chunk);
+    int *ch_seg = salloc<int>(c, n_chunk), *ch_pair = salloc<int>(c, n_chunk), *ch_diag = salloc<int>(c, n_chunk);
+    k_chunk_heads<<<cdiv(c->ntri, 256), 256, 0, st>>>(c->ntri, head, cid, tri_seg, c->tri_oa, c->tri_ob, c->n_pair, tptr, c->sch_beg, c->sch_end,
+                                                     ch_seg, ch_pair, ch_diag);
+    k_segment_ptr<<<cdiv(n_chunk, 256), 256, 0, st>>>(n_chunk, c->n_pair, ch_pair, c->pair_chunk_ptr);
+    // ---- schedule
+    u64 *key0 = salloc<u64>(c, n_chunk), *key1 = salloc<u64>(c, n_chunk);
+    int *val0 = salloc<int>(c, n_chunk), *seg_diag = salloc<int>(c, c->n_seg), *sptr = salloc<int>(c, (size_t)c->n_seg + 1);
+    c->sched_chunk = salloc<int>(c, n_chunk);
+    k_chunk_keys<<<cdiv(n_chunk, 256), 256, 0, st>>>(n_chunk, c->n_seg, c->sch_beg, c->sch_end, ch_seg, ch_diag, key0, val0, seg_diag);
+    {
+        size_t tb = 0;
+        const int bits = 32 + bits_for((u64)c->n_seg);
+        CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, key0, key1, val0, c->sched_chunk, n_chunk, 0, bits, st));
+        void *tmp = psba_dev_alloc(c, std::max<size_t>(tb, 16), false);
+        CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tb, key0, key1, val0, c->sched_chunk, n_chunk, 0, bits, st));
+        psba_dev_free(c, tmp);
+    }
+    k_sched_ptr<<<cdiv(n_chunk + 1, 256), 256, 0, st>>>(n_chunk, c->n_seg, key1, sptr);
+    k_fill_seg_desc<<<cdiv(c->n_seg, 256), 256, 0, st>>>(c->n_seg, (seg_desc_h *)c->seg_desc, seg_diag, sptr);
+    // lanes per chunk from the mean size of an off-diagonal chunk (a lane should stream ~8 triples before the butterfly)
+    {
+        const double avg = (double)(c->ntri - o) / std::max(1, n_chunk - c->n_seg);
+        int G = 1;
+        while (G < 32 && avg > 5.0 * G) G *= 2;
+        if (getenv("PSBA_SEG_G")) G = std::max(1, std::min(32, atoi(getenv("PSBA_SEG_G"))));
+        while (G & (G - 1)) G &= G - 1;
+        c->pair_G = G;
+    }
     CUDA_CHECK(cudaStreamSynchronize(st));
-    psba_dev_free(c, nch); psba_dev_free(c, maxlen); psba_dev_free(c, len);
-    if (hmax > maxlen_cap) { psba_dev_free(c, cam_pos); psba_dev_free(c, vis_off); psba_dev_free(c, cam_ptr); return; }
-    std::vector<int> chunk_base((size_t)m + 1, 0);
-    for (int k = 0; k < m; ++k) chunk_base[k + 1] = chunk_base[k] + hnch[k];
-    c->n_rchunk = chunk_base[m];
-    // segments (one CTA each): SC consecutive chunks of one row
-    int SC = std::max(1, cdiv(c->n_rchunk, 8 * c->n_sm));
-    if (getenv("PSBA_ROW_SEG")) SC = std::max(1, atoi(getenv("PSBA_ROW_SEG")));
-    SC = std::min(SC, c->pair_mode == 4 ? 63 : (1 << 14));      // mode 4: 6 bits, 63 is the "no triple" mark
-    std::vector<int> seg_row, seg_slot_base, row_seg_ptr((size_t)m + 1, 0);
-    std::vector<int2> seg_chunks;
-    int nslot_total = 0;
-    for (int k = 0; k < m; ++k) {
-        for (int b = 0; b < hnch[k]; b += SC) {
-            seg_row.push_back(k);
-            seg_chunks.push_back(make_int2(chunk_base[k] + b, chunk_base[k] + std::min(b + SC, hnch[k])));
-            seg_slot_base.push_back(nslot_total);
-            nslot_total += row_pair0[k + 1] - row_pair0[k];
-        }
-        row_seg_ptr[k + 1] = (int)seg_row.size();
-    }
-    c->n_rseg = (int)seg_row.size(); c->n_rpart = nslot_total;
-    c->rows_nt = max_off <= 168 ? 256 : 544;
-    // (NT - 32) / 4 groups of four lanes, three pairs per group; the flow kernel (mode 4) exists in the small size only
-    if (c->pair_mode == 4 && max_off > 144) { c->n_rseg = c->n_rpart = 0; psba_dev_free(c, cam_pos); psba_dev_free(c, vis_off); psba_dev_free(c, cam_ptr); return; }
-    int *row_chunk_base = supload(c, chunk_base);
-    c->rchunk_first = salloc<int>(c, (size_t)c->n_rchunk + 1);
-    k_chunk_first<<<cdiv(o, 256), 256, 0, st>>>(RB, o, c->cam_obs, c->jidx, cam_ptr, vis_off, row_chunk_base, c->n_rchunk, c->rchunk_first);
-    c->vis_desc = salloc<int4>(c, o);
-    k_vis_desc<<<cdiv(o, 256), 256, 0, st>>>(RB, o, c->cam_obs, c->iidx, c->jidx, c->pt_ptr, cam_ptr, vis_off, row_chunk_base, c->rchunk_first, c->vis_desc);
-    c->rchunk_desc = salloc<int4>(c, (size_t)c->n_rchunk + 4);
-    CUDA_CHECK(cudaMemsetAsync(c->rchunk_desc, 0, ((size_t)c->n_rchunk + 4) * sizeof(int4), st));
-    if (c->n_rchunk) k_chunk_desc<<<cdiv(c->n_rchunk, 256), 256, 0, st>>>(c->n_rchunk, c->rchunk_first, c->vis_desc, vis_off, c->rchunk_desc);
-    c->rblk_src = nullptr;
-    if (c->pair_mode == 4) {
-        c->rblk_src = salloc<int>(c, (size_t)c->ntri + 512);
-        CUDA_CHECK(cudaMemsetAsync(c->rblk_src, 0, ((size_t)c->ntri + 512) * sizeof(int), st));
-        k_block_src<<<cdiv(o, 256), 256, 0, st>>>(o, c->vis_desc, vis_off, c->rblk_src);
-    }
-    c->tri_meta = salloc<unsigned>(c, (size_t)c->ntri + 4);
-    if (c->ntri) k_tri_meta<<<cdiv(c->ntri, 256), 256, 0, st>>>(c->pair_mode == 4 ? 1 : 0, RB, c->ntri, SC, c->tri_oa, c->tri_ob, cam_pos, c->jidx, cam_ptr, vis_off, row_chunk_base,
-                                                              c->rchunk_first, c->vis_desc, c->tri_meta);
-    c->rseg_row = supload(c, seg_row); c->rseg_chunks = supload(c, seg_chunks); c->rseg_slot_base = supload(c, seg_slot_base);
-    c->row_pair0 = supload(c, row_pair0); c->row_seg_ptr = supload(c, row_seg_ptr);
-    c->rseg_runs = salloc<int2>(c, (size_t)nslot_total);
-    CUDA_CHECK(cudaMemsetAsync(c->rseg_runs, 0, std::max<size_t>(nslot_total, 1) * sizeof(int2), st));
-    if (c->n_rseg) k_seg_runs<<<c->n_rseg, 128, 0, st>>>(RB, SC, c->rseg_row, c->rseg_slot_base, c->row_seg_ptr, c->row_pair0, tptr, c->tri_oa, cam_pos,
-                                                        cam_ptr, vis_off, c->rseg_runs);
-    CUDA_CHECK(cudaStreamSynchronize(st));          // the host vectors above are read by the async uploads
-    psba_dev_free(c, cam_pos); psba_dev_free(c, vis_off); psba_dev_free(c, cam_ptr); psba_dev_free(c, row_chunk_base);
-    c->rows_ok = true;
+    for (void *p : {(void *)cam_pos, (void *)cam_ptr, (void *)d_seglen, (void *)d_rsp, (void *)tri_seg, (void *)head, (void *)cid, (void *)ch_seg,
+                    (void *)ch_pair, (void *)ch_diag, (void *)key0, (void *)key1, (void *)val0, (void *)seg_diag, (void *)sptr})
+        psba_dev_free(c, p);
 }
 
 // ---- the build ---------------------------------------------------------------------------------------
@@ -565,33 +514,24 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
     int h_nonempty = 0;
     CUDA_CHECK(cudaMemcpyAsync(&h_nonempty, nonempty, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    // lane-group size of the pair pass: every group of G lanes owns one chunk of <= G*PAIR_TPL triples of
-    // one camera pair; G follows the mean run length so that a lane streams ~PAIR_TPL triples before the
-    // (shuffle) reduction -- 4..8 for the synthetic ring (117 triples / pair), 32 for BAL (~10^3 / pair)
-    // pair_mode 0 (default): a lane per triple; 1: the lanes of a group work as quads (four lanes per triple, a 3x3
-    // quadrant of the block each), a chunk is <= (G/4)*PAIR_TPQ triples; 2: row sweep; 3: lane per triple with the
-    // operands fetched cooperatively through a per-warp stage.  PSBA_PAIR_MODE selects the measured-and-slower
-    // variants
-    c->pair_mode = 0;
-    if (getenv("PSBA_PAIR_MODE")) c->pair_mode = atoi(getenv("PSBA_PAIR_MODE"));
-    long long PCH;
-    {
+    // pair pass: 5 (default) = segment kernel (k_schur_segs), 0 = the pair-major gather kernel of round 1
+    c->pair_mode = 5;
+    if (getenv("PSBA_PAIR_MODE")) c->pair_mode = atoi(getenv("PSBA_PAIR_MODE")) == 0 ? 0 : 5;
+    c->n_seg = 0; c->seg_desc = nullptr; c->sched_chunk = nullptr; c->sch_beg = c->sch_end = nullptr; c->tri_vr = nullptr;
+    c->pchunk_pair = nullptr; c->pchunk_beg = c->pchunk_end = nullptr;
+    if (c->pair_mode == 5) {
+        build_segments(c, tptr, cptr);
+        T.lap("segments + chunks");
+    } else {
+        // every group of G lanes owns one chunk of <= G*PAIR_TPL triples of one camera pair; G follows the mean run
+        // length so that a lane streams ~PAIR_TPL triples before the (shuffle) reduction
         const double avg = h_nonempty ? (double)c->ntri / (double)h_nonempty : 1.0;
-        if (c->pair_mode == 1) {
-            int G = 4;
-            while (G < 32 && avg > (double)(G / 4) * PAIR_TPQ) G *= 2;
-            c->pair_G = G;
-            PCH = (long long)(G / 4) * PAIR_TPQ;
-        } else {
-            int G = 1;
-            while (G < 32 && avg > (double)G * PAIR_TPL) G *= 2;
-            c->pair_G = G;
-            PCH = (long long)G * PAIR_TPL;
-        }
-    }
-    k_chunk_count<<<cdiv(c->n_pair, 256), 256, 0, st>>>(c->n_pair, PCH, tptr, ccnt, nullptr);
-    c->pair_chunk_ptr = salloc<int>(c, (size_t)c->n_pair + 1);
-    {
+        int G = 1;
+        while (G < 32 && avg > (double)G * PAIR_TPL) G *= 2;
+        c->pair_G = G;
+        const long long PCH = (long long)G * PAIR_TPL;
+        k_chunk_count<<<cdiv(c->n_pair, 256), 256, 0, st>>>(c->n_pair, PCH, tptr, ccnt, nullptr);
+        c->pair_chunk_ptr = salloc<int>(c, (size_t)c->n_pair + 1);
         size_t tb = 0;
         CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tb, ccnt, c->pair_chunk_ptr, c->n_pair + 1, st));
         void *tmp = psba_dev_alloc(c, std::max<size_t>(tb, 16), false);
@@ -599,13 +539,11 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
         CUDA_CHECK(cudaMemcpyAsync(&c->n_pchunk, c->pair_chunk_ptr + c->n_pair, sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         psba_dev_free(c, tmp);
+        c->pchunk_pair = salloc<int>(c, c->n_pchunk);
+        c->pchunk_beg = salloc<long long>(c, c->n_pchunk); c->pchunk_end = salloc<long long>(c, c->n_pchunk);
+        k_chunk_fill<<<cdiv(c->n_pair, 256), 256, 0, st>>>(c->n_pair, PCH, tptr, c->pair_chunk_ptr, c->pchunk_pair, c->pchunk_beg, c->pchunk_end);
+        T.lap("pair set + chunks");
     }
-    c->pchunk_pair = salloc<int>(c, c->n_pchunk);
-    c->pchunk_beg = salloc<long long>(c, c->n_pchunk); c->pchunk_end = salloc<long long>(c, c->n_pchunk);
-    k_chunk_fill<<<cdiv(c->n_pair, 256), 256, 0, st>>>(c->n_pair, PCH, tptr, c->pair_chunk_ptr, c->pchunk_pair, c->pchunk_beg, c->pchunk_end);
-    T.lap("pair set + chunks");
-    build_row_sweep(c, tptr, cptr, pk);
-    T.lap("row-sweep tables");
     psba_dev_free(c, tptr); psba_dev_free(c, ccnt); psba_dev_free(c, nonempty); psba_dev_free(c, lkeys);
     // ---- camera system tiles (symbolic factorisation, host)
     psba_build_tile_structure(c, pairs);

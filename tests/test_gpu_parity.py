@@ -287,10 +287,31 @@ def test_device_built_index_structure_is_bit_exact(key):
     assert list(zip(pk.tolist(), pl.tolist())) == want
     # triples of every pair = the rows of comm3DIdx, with the observation ids blk_idx gives
     oa, ob, pt = G.index("tri_oa"), G.index("tri_ob"), G.index("tri_pt")
-    cp, cb, ce = G.index("pchunk_pair"), G.index("pchunk_beg"), G.index("pchunk_end")
+    # chunks (pair-major ids): the triples of one pair inside one segment of the camera row; contiguous per pair
+    pcp, cb, ce = G.index("pair_chunk_ptr"), G.index("chunk_beg"), G.index("chunk_end")
+    assert np.array_equal(cb[1:], ce[:-1]) and cb[0] == 0 and ce[-1] == len(oa)
     beg = {}; end = {}
-    for q in range(len(cp)):
-        beg.setdefault(int(cp[q]), int(cb[q])); end[int(cp[q])] = int(ce[q])
+    for pid in range(len(want)):
+        if pcp[pid + 1] > pcp[pid]:
+            beg[pid] = int(cb[pcp[pid]]); end[pid] = int(ce[pcp[pid + 1] - 1])
+    # segments: consecutive visits of one camera (camera-major positions); every off-diagonal chunk is scheduled exactly
+    # once, in the segment that holds the visits of its triples, largest first; the diagonal chunk is the segment's own
+    sd = G.index("seg_desc").reshape(-1, 6)
+    sched = G.index("sched_chunk")
+    cam_obs = G.index("cam_obs")
+    cam_pos = np.empty(o, dtype=np.int64); cam_pos[cam_obs] = np.arange(o)
+    seen = np.zeros(len(cb), dtype=int)
+    for row, v0, v1, dchunk, s0, s1 in sd.tolist():
+        assert 0 < v1 - v0 <= int(G.stat("seg_v")) and np.all(prob["jidx"][cam_obs[v0:v1]] == row)
+        sizes = []
+        for cidx in [dchunk] + sched[s0:s1].tolist():
+            pos = cam_pos[oa[cb[cidx]:ce[cidx]]]
+            assert np.all((pos >= v0) & (pos < v1))
+            seen[cidx] += 1
+            sizes.append(int(ce[cidx] - cb[cidx]))
+        assert oa[cb[dchunk]] == ob[cb[dchunk]] and sizes[0] == v1 - v0
+        assert sizes[1:] == sorted(sizes[1:], reverse=True)
+    assert np.all(seen == 1)
     assert len(oa) == sum(int(cnt[k, l]) for k, l in want)
     for pid, (k, l) in enumerate(want):
         c_kl = int(cnt[k, l])
@@ -352,16 +373,24 @@ def _check_try_against_oracle(prob, G):
     return O
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "2", "3", "4"])
-def test_pair_pass_variants_agree_with_oracle(mode, monkeypatch):
-    """PSBA_PAIR_MODE selects the pair pass: lane per triple, quad per triple, row sweep, staged cooperative fetch.  All must
-    give the reference's S and ea (compute_S.cl / compute_ea.cl) and the same LM trajectory."""
+@pytest.mark.parametrize("mode,cfg,segv,G_", [("5", "0", "", ""), ("5", "1", "", ""), ("5", "2", "", ""), ("5", "0", "48", "1"),
+                                              ("5", "0", "100", "8"), ("5", "2", "1400", "32"), ("0", "0", "", "")])
+def test_pair_pass_variants_agree_with_oracle(mode, cfg, segv, G_, monkeypatch):
+    """PSBA_PAIR_MODE selects the pair pass: 5 = segment kernel (Y staged per camera-row segment; launch shapes, segment
+    lengths and lane-group sizes varied here), 0 = the pair-major gather kernel.  All must give the reference's S and
+    ea (compute_S.cl / compute_ea.cl) and the same LM trajectory."""
     from psba_b200 import synth
     monkeypatch.setenv("PSBA_PAIR_MODE", mode)
+    monkeypatch.setenv("PSBA_SEG_CFG", cfg)
+    if segv:
+        monkeypatch.setenv("PSBA_SEG_V", segv)
+    if G_:
+        monkeypatch.setenv("PSBA_SEG_G", G_)
     for prob in (synth.ring_problem(m=160, n=6000, d=4, w=12, seed=7), psba_b200.read_sba(*dataset_paths("54"))):
         G = psba_b200.PSBA(prob)
-        if mode in ("2", "4"):
-            assert int(G.stat("rows_ok")) == 1 and int(G.stat("n_rseg")) > 0
+        assert int(G.stat("pair_mode")) == int(mode)
+        if mode == "5":
+            assert int(G.stat("n_seg")) >= prob["m"] - 1
         O = _check_try_against_oracle(prob, G)
         G.close()
         G = psba_b200.PSBA(prob)
@@ -373,15 +402,13 @@ def test_pair_pass_variants_agree_with_oracle(mode, monkeypatch):
         G.close(); O.close()
 
 
-@pytest.mark.parametrize("mode", ["0", "2"])
+@pytest.mark.parametrize("mode", ["5", "0"])
 def test_points_with_more_observations_than_one_wave(mode, monkeypatch):
     """Tracks of 150 observations (> 128, one CTA wave) next to ordinary ones: the pipelined point-major kernels
-    take the one-wave chunks, the wave-loop kernels the oversize ones; the row sweep (mode 2) must notice that a
-    prefix of 150 blocks exceeds its stage and fall back to the pair-major kernel."""
+    take the one-wave chunks, the wave-loop kernels the oversize ones; the pair pass has no limit on track length."""
     monkeypatch.setenv("PSBA_PAIR_MODE", mode)
     prob = _mixed_track_problem()
     G = psba_b200.PSBA(prob)
-    assert int(G.stat("rows_ok")) == 0
     O = _check_try_against_oracle(prob, G)
     G.close()
     G = psba_b200.PSBA(prob)
@@ -419,7 +446,7 @@ def _ragged_problem():
     return prob
 
 
-@pytest.mark.parametrize("mode", ["0", "2"])
+@pytest.mark.parametrize("mode", ["5", "0"])
 def test_ragged_structure_empty_camera_and_single_observation_points(mode, monkeypatch):
     monkeypatch.setenv("PSBA_PAIR_MODE", mode)
     prob = _ragged_problem()
