@@ -90,17 +90,27 @@ static bool compute_PB(psba_ctx *c, double *lambda)
 {
     c->st_tries += 1;
     psba_launch_schur(c, *lambda);                                // update_UV, Vinv, Yblks, S (+ ea)
-    const double ret = psba_launch_factor(c);
+    double ret;
+    if (c->camera_solver == 1) {                                  // optional PCG camera solve: "not positive definite / no convergence" = failed
+        psba_launch_pcg(c);
+        int st = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        ret = st ? 1.0 : 0.0;
+    } else ret = psba_launch_factor(c);
     if (ret != 0.0) {
         if (*lambda == 0.0) {
             // the failed factorisation overwrote the tile pool: rebuild S (the reference restores
             // it from Saux, trust_region.cpp:345-346), then the modified Cholesky picks lambda
             psba_launch_schur(c, 0.0);
-            const size_t nn = (size_t)c->N * c->N;
-            if (!c->Sdense) c->Sdense = (double *)psba_dev_alloc(c, nn * sizeof(double), true);
-            psba_tiles_to_dense(c, c->Sdense, true);
-            double delta, beta; int nscalar = 0;
-            const double sum = psba_launch_cholmod(c, &delta, &beta, &nscalar);
+            double delta, beta, sum; int nscalar = 0;
+            if (psba_cholmod_use_tiles(c)) sum = psba_launch_cholmod_tiles(c, &delta, &beta, &nscalar, nullptr, nullptr);   // large N: on the tile pool
+            else {
+                const size_t nn = (size_t)c->N * c->N;
+                if (!c->Sdense) c->Sdense = (double *)psba_dev_alloc(c, nn * sizeof(double), true);
+                psba_tiles_to_dense(c, c->Sdense, true);
+                sum = psba_launch_cholmod(c, &delta, &beta, &nscalar);
+            }
             *lambda = fabs(sum) / c->N;                           // trust_region.cpp:358-364
             if ((size_t)c->n_cholmod_events < c->force_lambda.size()) *lambda = c->force_lambda[c->n_cholmod_events];
             c->n_cholmod_events++;
@@ -110,7 +120,7 @@ static bool compute_PB(psba_ctx *c, double *lambda)
         *lambda = 2 * (*lambda);
         return false;
     }
-    psba_launch_solve(c);                                         // dpa
+    if (c->camera_solver != 1) psba_launch_solve(c);              // dpa
     {   // the dataflow backward solve reports a broken schedule (bounded spin) through the status word
         int st = 0;
         CUDA_CHECK(cudaMemcpyAsync(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

@@ -285,6 +285,37 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
         up_vec(c, &c->d_crit_desc, cd); up_vec(c, &c->d_crit_src, cs);
         up_vec(c, &c->d_def_desc, dd); up_vec(c, &c->d_def_srcs, dsrc);
     }
+    {
+        // ---- dataflow schedule (k_panel_flow): ONE launch, tasks in step order; a task waits on per-tile write counters
+        //   tver[slot] = completed writes of the tile (its deferred updates in step order, then the factor tile itself)
+        //   bver[J]    = completed right-hand-side updates of panel J
+        // instead of on a kernel boundary.  Everything a task waits for belongs to an earlier step = a smaller block index.
+        std::vector<int> ndef(c->n_tiles, 0), nrhs(nt, 0), task_type, task_idx, b_seq(bJ.size(), 0);
+        for (size_t t = 0; t < defI.size(); ++t) { const int sl = c->h_tile_index[(size_t)defI[t] * nt + defJ[t]]; ndef[sl]++; }
+        std::vector<int> tfinal(c->n_tiles + nt, 0);
+        for (int sl = 0; sl < c->n_tiles; ++sl) tfinal[sl] = ndef[sl] + 1;
+        std::vector<int> seen_def(c->n_tiles, 0), seen_b(nt, 0), def_seq(defI.size(), 0), crit_need(critI.size() * 2, 0);
+        for (int s2 = 0; s2 < n_steps; ++s2) {
+            for (int t = c->step_crit_ptr[s2]; t < c->step_crit_ptr[s2 + 1]; ++t) { task_type.push_back(0); task_idx.push_back(t); }
+            for (int t = c->step_def_ptr[s2]; t < c->step_def_ptr[s2 + 1]; ++t) {
+                const int sl = c->h_tile_index[(size_t)defI[t] * nt + defJ[t]];
+                def_seq[t] = seen_def[sl]++;
+                task_type.push_back(1); task_idx.push_back(t);
+            }
+            for (int t = c->step_b_ptr[s2]; t < c->step_b_ptr[s2 + 1]; ++t) { b_seq[t] = seen_b[bJ[t]]++; task_type.push_back(2); task_idx.push_back(t); }
+        }
+        for (int J = 0; J < nt; ++J) { nrhs[J] = seen_b[J]; tfinal[c->n_tiles + J] = nrhs[J]; }
+        for (size_t t = 0; t < critI.size(); ++t) {
+            crit_need[2 * t] = ndef[c->h_tile_index[(size_t)critI[t] * nt + critK[t]]];
+            crit_need[2 * t + 1] = ndef[c->h_tile_index[(size_t)critK[t] * nt + critK[t]]];
+        }
+        std::vector<int2> tasks(task_type.size());
+        for (size_t q = 0; q < tasks.size(); ++q) tasks[q] = make_int2(task_type[q], task_idx[q]);
+        c->n_flow_tasks = (int)tasks.size();
+        up_vec(c, &c->d_flow_tasks, tasks); up_vec(c, &c->d_flow_final, tfinal); up_vec(c, &c->d_flow_defseq, def_seq);
+        up_vec(c, &c->d_flow_bseq, b_seq); up_vec(c, &c->d_flow_critneed, crit_need);
+        c->d_flow_ver = (int *)psba_dev_alloc(c, (size_t)(c->n_tiles + nt) * sizeof(int), true);
+    }
     up_vec(c, &c->d_psrc_ptr, psrc_ptr); up_vec(c, &c->d_psrc, psrc);
     up_vec(c, &c->d_b_J, bJ); up_vec(c, &c->d_b_sptr, b_sptr); up_vec(c, &c->d_b_slot, b_slot);
     up_vec(c, &c->d_def_I, defI); up_vec(c, &c->d_def_J, defJ); up_vec(c, &c->d_def_sptr, def_sptr); up_vec(c, &c->d_def_src, def_src);
@@ -310,15 +341,53 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
 // ---------------------------------------------------------------------------------------------
 // a 48x48 tile travels global -> registers (all loads in flight at once) -> padded shared memory
 template <int NT> struct TileRegs { double2 v[(TS * TS / 2 + NT - 1) / NT]; };
-template <int NT>
-__device__ __forceinline__ void tile_ldg(TileRegs<NT> &t, const double *__restrict__ g)
+// CG: the tile may have been written by another CTA of the SAME launch (dataflow factorisation): read it through L2
+template <int NT, bool CG = false>
+__device__ __forceinline__ void tile_ldg(TileRegs<NT> &t, const double *g)
 {
     constexpr int Q = (TS * TS / 2 + NT - 1) / NT;
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
         const int e = threadIdx.x + q * NT;
-        t.v[q] = e < TS * TS / 2 ? reinterpret_cast<const double2 *>(g)[e] : make_double2(0.0, 0.0);
+        t.v[q] = e < TS * TS / 2 ? (CG ? __ldcg(reinterpret_cast<const double2 *>(g) + e) : reinterpret_cast<const double2 *>(g)[e]) : make_double2(0.0, 0.0);
     }
+}
+template <bool CG> __device__ __forceinline__ double2 ld2c(const double *p) { return CG ? __ldcg(reinterpret_cast<const double2 *>(p)) : *reinterpret_cast<const double2 *>(p); }
+template <bool CG> __device__ __forceinline__ double ld1c(const double *p) { return CG ? __ldcg(p) : *p; }
+
+// ---- flags of the dataflow kernels: release / acquire at GPU scope
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_relaxed(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_add(int *p, int v)
+{
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// one thread waits until counter idx has reached `need`; gives up when the factorisation has failed elsewhere or the
+// bounded spin runs out (status 3: a broken schedule becomes an error, not a hang)
+__device__ __forceinline__ bool flow_wait(const int *ver, int idx, int need, int *status)
+{
+    int spins = 0;
+    while (ld_acquire(ver + idx) < need) {
+        if ((++spins & 255) == 0) {
+            if (ld_relaxed(status) != 0) return false;
+            if (spins > (1 << 23)) { atomicMax(status, 3); return false; }
+        }
+    }
+    return true;
 }
 template <int NT>
 __device__ __forceinline__ void tile_sts(double *sm, const TileRegs<NT> &t)
@@ -484,11 +553,21 @@ __device__ __forceinline__ long long global_ns() { long long t; asm volatile("mo
 //  through shared memory (double-buffered, one barrier per column); the loop body is branch-free (dead
 //  entries are updated too, a non-positive pivot poisons the panel with NaN and is reported once at the end).
 //  deferred CTAs: A_IJ -= sum_P L_IP L_JP^T for trailing tiles whose panel J runs in a later step.
+// MOD: the MODIFIED factorisation of the trust-region fallback (cholmod_blk.cl:446-475 on the tile pool): a pivot that is not
+// positive and finite is replaced by max(|pivot|, delta) instead of failing, and the 3-column blocks that needed it are counted.
+// FLOW: ONE launch for the whole factorisation.  Block b runs task tasks[b] (step order); instead of a kernel boundary it
+// waits -- one thread per dependency, acquire loads -- until the write counters of the tiles it reads have reached the
+// values the static schedule prescribes (flow tables of psba_build_tile_structure), reads everything another CTA of
+// the launch may have written through L2 (ld.cg), and bumps the counter of what it wrote with a release.  A panel's
+// critical chain then runs ahead of the bulk of the trailing updates of its step, and nothing pays a launch gap.
+struct flow_args { const int2 *tasks; const int *tfinal, *defseq, *bseq, *critneed; int *ver; int n_tiles; };
+template <bool MOD, bool FLOW>
 __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *__restrict__ crit_desc, const int2 *__restrict__ crit_src,
                                                          int ndef, const int4 *__restrict__ def_desc, const int2 *__restrict__ def_srcs,
                                                          const int *__restrict__ bJ, const int *__restrict__ b_sptr, const int *__restrict__ b_slot,
-                                                         double *__restrict__ Stiles, double *__restrict__ Ldiag, double *__restrict__ bwork,
-                                                         double *__restrict__ ywork, double *__restrict__ contrib, int *__restrict__ status)
+                                                         double *Stiles, double *__restrict__ Ldiag, double *bwork,
+                                                         double *__restrict__ ywork, double *contrib, int *status,
+                                                         double delta, int *__restrict__ nmod, flow_args fl)
 {
     extern __shared__ double smem[];
     __shared__ __align__(16) double colbuf[2][2 * TS + 4];
@@ -497,40 +576,82 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     int4 cd0 = make_int4(0, 0, 0, 0), cd1 = cd0;
     int2 sl0 = make_int2(-1, -1);                              // first source of the task: static data, fetched before the wait too
-    if ((int)blockIdx.x < ncrit) {
-        cd0 = __ldg(crit_desc + 2 * blockIdx.x); cd1 = __ldg(crit_desc + 2 * blockIdx.x + 1);
+    int role, li;                                             // 0 critical, 1 deferred, 2 right-hand side; index in the task arrays
+    if (FLOW) { const int2 tk = __ldg(fl.tasks + blockIdx.x); role = tk.x; li = tk.y; }
+    else { role = (int)blockIdx.x < ncrit ? 0 : ((int)blockIdx.x < ncrit + ndef ? 1 : 2); li = role == 0 ? blockIdx.x : (role == 1 ? blockIdx.x - ncrit : blockIdx.x - ncrit - ndef); }
+    if (role == 0) {
+        cd0 = __ldg(crit_desc + 2 * li); cd1 = __ldg(crit_desc + 2 * li + 1);
         if (cd1.x < cd1.y) sl0 = __ldg(crit_src + cd1.x);
-    } else if ((int)blockIdx.x < ncrit + ndef) {
-        cd0 = __ldg(def_desc + (blockIdx.x - ncrit));
+    } else if (role == 1) {
+        cd0 = __ldg(def_desc + li);
         sl0 = __ldg(def_srcs + cd0.y);
     }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!FLOW) asm volatile("griddepcontrol.wait;" ::: "memory");
     // the status word of the earlier steps is loaded here and tested after the first tile loads have been issued:
     // one L2 round trip less in front of every step
-    const int failed = *reinterpret_cast<volatile int *>(status);
+    int failed = FLOW ? 0 : *reinterpret_cast<volatile int *>(status);
     const int tid = threadIdx.x;
     double *B0 = smem, *B1 = smem + TILE_SM;
+    int sig = -1;                                             // FLOW: the counter this task bumps when it is done
+    if (FLOW) {
+        // one thread per dependency
+        bool ok = true;
+        if (role == 0) {
+            const int nsrc = cd1.y - cd1.x, K_ = cd0.y;
+            if (cd0.x != cd0.y) sig = cd0.z;
+            for (int d = tid; d < 3 + 2 * nsrc; d += PANEL_NT) {
+                int idx, need;
+                if (d == 0) { idx = cd0.z; need = __ldg(fl.critneed + 2 * li); }
+                else if (d == 1) { idx = cd0.w; need = __ldg(fl.critneed + 2 * li + 1); }
+                else if (d == 2) { idx = fl.n_tiles + K_; need = __ldg(fl.tfinal + idx); }
+                else { const int2 sl = __ldg(crit_src + cd1.x + (d - 3) / 2); idx = ((d - 3) & 1) ? sl.y : sl.x; need = idx >= 0 ? __ldg(fl.tfinal + idx) : 0; }
+                if (idx >= 0) ok = flow_wait(fl.ver, idx, need, status) && ok;
+            }
+        } else if (role == 1) {
+            const int nsrc = cd0.z - cd0.y;
+            sig = cd0.x;
+            for (int d = tid; d < 1 + 2 * nsrc; d += PANEL_NT) {
+                int idx, need;
+                if (d == 0) { idx = cd0.x; need = __ldg(fl.defseq + li); }
+                else { const int2 sl = __ldg(def_srcs + cd0.y + (d - 1) / 2); idx = ((d - 1) & 1) ? sl.y : sl.x; need = __ldg(fl.tfinal + idx); }
+                ok = flow_wait(fl.ver, idx, need, status) && ok;
+            }
+        } else {
+            const int q0 = b_sptr[li], q1 = b_sptr[li + 1], J_ = bJ[li];
+            sig = fl.n_tiles + J_;
+            for (int d = tid; d < 1 + (q1 - q0); d += PANEL_NT) {
+                int idx, need;
+                if (d == 0) { idx = fl.n_tiles + J_; need = __ldg(fl.bseq + li); }
+                else { idx = b_slot[q0 + d - 1]; need = __ldg(fl.tfinal + idx); }
+                ok = flow_wait(fl.ver, idx, need, status) && ok;
+            }
+        }
+        failed = __syncthreads_and(ok) ? 0 : 1;
+    }
+    // FLOW: whatever happens, the task's counter is bumped (a failed factorisation must drain, not hang)
+#define FLOW_DONE() do { if (FLOW && sig >= 0) { __syncthreads(); if (tid == 0) red_release_add(fl.ver + sig, 1); } } while (0)
 
-    if ((int)blockIdx.x >= ncrit + ndef) {
+    if (role == 2) {
         // ---- right-hand side of a later panel:  b_J -= sum_P L_JP y_P  (ascending P)
-        if (failed) return;
-        const int t = blockIdx.x - ncrit - ndef;
+        if (failed) { FLOW_DONE(); return; }
+        const int t = li;
         if (tid < TS) {
             double sum = 0.0;
-            for (int q = b_sptr[t]; q < b_sptr[t + 1]; ++q) sum += contrib[(size_t)b_slot[q] * TS + tid];
-            bwork[bJ[t] * TS + tid] -= sum;
+            for (int q = b_sptr[t]; q < b_sptr[t + 1]; ++q) sum += ld1c<FLOW>(contrib + (size_t)b_slot[q] * TS + tid);
+            bwork[bJ[t] * TS + tid] = ld1c<FLOW>(bwork + bJ[t] * TS + tid) - sum;
         }
+        FLOW_DONE();
         return;
     }
-    if ((int)blockIdx.x >= ncrit) {
+    if (role == 1) {
         // ---- deferred trailing update:  A_IJ -= sum_P L_IP L_JP^T
         const int4 dd = cd0;
         const int sb = dd.y, se = dd.z;
         double *tij = Stiles + (size_t)dd.x * TS * TS;
         TileRegs<PANEL_NT> ra, rb_;
-        tile_ldg(ra, Stiles + (size_t)sl0.x * TS * TS);
-        tile_ldg(rb_, Stiles + (size_t)sl0.y * TS * TS);
-        if (failed) return;
+        tile_ldg<PANEL_NT, FLOW>(ra, Stiles + (size_t)sl0.x * TS * TS);
+        tile_ldg<PANEL_NT, FLOW>(rb_, Stiles + (size_t)sl0.y * TS * TS);
+        if (failed) { FLOW_DONE(); return; }
         // warp w owns the 24x24 block (w / 2, w % 2) of the target: 3x3 DMMA fragments, two doubles per lane each
         const int wrp = tid >> 5, lane = tid & 31, rb = (wrp >> 1) * 24, cb = (wrp & 1) * 24;
         double cf[3][3][2];
@@ -538,7 +659,7 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
         for (int ti = 0; ti < 3; ++ti)
 #pragma unroll
             for (int tj = 0; tj < 3; ++tj) {
-                const double2 v = *reinterpret_cast<const double2 *>(tij + (rb + ti * 8 + (lane >> 2)) * TS + cb + tj * 8 + 2 * (lane & 3));
+                const double2 v = ld2c<FLOW>(tij + (rb + ti * 8 + (lane >> 2)) * TS + cb + tj * 8 + 2 * (lane & 3));
                 cf[ti][tj][0] = v.x; cf[ti][tj][1] = v.y;
             }
         double *D0 = smem, *D1 = smem + TS * LDD;
@@ -548,8 +669,8 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
             __syncthreads();
             if (s + 1 < se) {                                  // next source's tiles fly during the product
                 const int2 sl = __ldg(def_srcs + s + 1);
-                tile_ldg(ra, Stiles + (size_t)sl.x * TS * TS);
-                tile_ldg(rb_, Stiles + (size_t)sl.y * TS * TS);
+                tile_ldg<PANEL_NT, FLOW>(ra, Stiles + (size_t)sl.x * TS * TS);
+                tile_ldg<PANEL_NT, FLOW>(rb_, Stiles + (size_t)sl.y * TS * TS);
             }
             tile_abt_dmma_sub(D0, D1, rb, cb, cf);
         }
@@ -558,13 +679,14 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
 #pragma unroll
             for (int tj = 0; tj < 3; ++tj)
                 *reinterpret_cast<double2 *>(tij + (rb + ti * 8 + (lane >> 2)) * TS + cb + tj * 8 + 2 * (lane & 3)) = make_double2(cf[ti][tj][0], cf[ti][tj][1]);
+        FLOW_DONE();
         return;
     }
 
     // ---- critical path of panel K for tile row I
     const int I = cd0.x, K = cd0.y;
     const bool diagcta = I == K;
-    long long *dbg = (g_panel_dbg && blockIdx.x == 0) ? g_panel_dbg + (size_t)K * 8 : nullptr;
+    long long *dbg = (g_panel_dbg && (FLOW ? diagcta : blockIdx.x == 0)) ? g_panel_dbg + (size_t)K * 8 : nullptr;
     PANEL_STAMP(0); PANEL_WALL(6);
     const int sb = cd1.x, se = cd1.y;
     const int slot_ik = cd0.z;
@@ -574,9 +696,9 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
     TileRegs<PANEL_NT> rp, ri;
     bool upd = false;
     if (sb < se) {
-        tile_ldg(rp, Stiles + (size_t)sl0.x * TS * TS);                                           // L_KP
+        tile_ldg<PANEL_NT, FLOW>(rp, Stiles + (size_t)sl0.x * TS * TS);                           // L_KP
         upd = sl0.y >= 0;
-        if (upd) tile_ldg(ri, Stiles + (size_t)sl0.y * TS * TS);                                  // L_IP
+        if (upd) tile_ldg<PANEL_NT, FLOW>(ri, Stiles + (size_t)sl0.y * TS * TS);                  // L_IP
     }
     // D and A_IK as DMMA accumulator fragments: warp w owns the 24x24 block (w / 2, w % 2), 3x3 fragments of 8x8,
     // lane l holds the entries (l / 4, 2 (l % 4) + {0, 1}) of each
@@ -587,29 +709,29 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
 #pragma unroll
         for (int tj = 0; tj < 3; ++tj) {
             const int off = (rb + ti * 8 + (lane >> 2)) * TS + cb + tj * 8 + 2 * (lane & 3);
-            const double2 dv = *reinterpret_cast<const double2 *>(tkk + off);
+            const double2 dv = ld2c<FLOW>(tkk + off);
             d[ti][tj][0] = dv.x; d[ti][tj][1] = dv.y;
             double2 av = make_double2(0.0, 0.0);
-            if (!diagcta) av = *reinterpret_cast<const double2 *>(tik + off);
+            if (!diagcta) av = ld2c<FLOW>(tik + off);
             a[ti][tj][0] = av.x; a[ti][tj][1] = av.y;
         }
-    if (failed) return;
+    if (failed) { FLOW_DONE(); return; }
     // right-hand side of the panel: what the rhs tasks of earlier steps left in bwork minus the
     // contributions of the source panels (ascending P)
     PANEL_STAMP(1);
     double bk = 0.0;
     if (tid < TS) {
         double sum = 0.0;
-        for (int s = sb; s < se; ++s) sum += contrib[(size_t)__ldg(crit_src + s).x * TS + tid];
-        bk = bwork[K * TS + tid] - sum;
+        for (int s = sb; s < se; ++s) sum += ld1c<FLOW>(contrib + (size_t)__ldg(crit_src + s).x * TS + tid);
+        bk = ld1c<FLOW>(bwork + K * TS + tid) - sum;
     }
     for (int s = sb; s < se; ++s) {
         if (s > sb) {                                          // further sources (first panel of a separator)
             __syncthreads();
             const int2 sl = __ldg(crit_src + s);
-            tile_ldg(rp, Stiles + (size_t)sl.x * TS * TS);
+            tile_ldg<PANEL_NT, FLOW>(rp, Stiles + (size_t)sl.x * TS * TS);
             upd = sl.y >= 0;
-            if (upd) tile_ldg(ri, Stiles + (size_t)sl.y * TS * TS);
+            if (upd) tile_ldg<PANEL_NT, FLOW>(ri, Stiles + (size_t)sl.y * TS * TS);
         }
         tile_sts_ldd(B0, rp);
         if (upd) tile_sts_ldd(B0 + TS * LDD, ri);
@@ -658,6 +780,7 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
     double *pubD = colbuf[0];                                  // [2][SB*SB]
     double *pubL = smem;                                       // [2][TS*SB]  (the tiles in B0 are consumed)
     bool bad = false;
+    unsigned modmask = 0;                                      // MOD: 3-column blocks of this panel with a replaced pivot
     if (tid < SB) {
 #pragma unroll
         for (int k = 0; k < SB; ++k) pubD[tid * SB + k] = row[k];
@@ -693,8 +816,16 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
                         row[c] = r;
                     }
                 }
-                bad |= !(piv > 0.0 && piv < 1e300);
-                const double inv = rsqrt(piv);
+                double pv = piv;
+                if (MOD) {
+                    if (!(piv > 0.0 && piv < 1e300)) {           // cholmod_blk.cl:465-475: d = max(|d|, delta); NaN -> delta
+                        pv = fmax(fabs(piv), delta);
+                        if (!(pv < 1e300)) pv = delta;
+                        modmask |= 1u << ((b * SB + j) / 3);
+                        if (tid == b * SB + j) x[j] = pv;      // the row of D that holds this diagonal entry
+                    }
+                } else bad |= !(piv > 0.0 && piv < 1e300);
+                const double inv = rsqrt(pv);
                 x[j] *= inv;
 #pragma unroll
                 for (int i = j + 1; i < SB; ++i) dd[i][j] *= inv;
@@ -734,7 +865,8 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
         }
     }
     PANEL_STAMP(4);
-    if (__syncthreads_or(bad)) { if (tid == 0) *status = 1; return; }
+    if (__syncthreads_or(bad)) { if (tid == 0) atomicMax(status, 1); FLOW_DONE(); return; }
+    if (MOD && diagcta && tid == 0 && modmask) atomicAdd(nmod, __popc(modmask));
     // ---- results: factor rows to global, y_K to shared, then the contribution L_IK y_K of this tile
     double *ysh = colbuf[0];
     if (tid == 2 * TS) {
@@ -762,7 +894,9 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
         for (int c = 0; c < TS; c += 2) { dst[c / 2] = make_double2(row[c], row[c + 1]); s += row[c] * ysh[c] + row[c + 1] * ysh[c + 1]; }
         contrib[(size_t)slot_ik * TS + (tid - TS)] = s;
     }
+    FLOW_DONE();
 }
+#undef FLOW_DONE
 // L_KK^-1 for every diagonal tile (needed by the backward substitution only): one CTA per tile,
 // all tiles in parallel, off the critical path of the factorisation
 __global__ void __launch_bounds__(256) k_diag_inverse(const double *__restrict__ Ldiag, double *__restrict__ Linv, const int *__restrict__ status)
@@ -787,10 +921,22 @@ __global__ void k_init_rhs(int npad, const int *__restrict__ pos2cam, const doub
     b[k] = cam >= 0 ? ea[cam * 6 + k % 6] : 0.0;
 }
 
-static void enqueue_factor(psba_ctx *c, std::vector<cudaEvent_t> *ev = nullptr)
+static void enqueue_factor(psba_ctx *c, std::vector<cudaEvent_t> *ev = nullptr, bool mod = false, double delta = 0.0)
 {
     const int npad = c->nt * TS;
     k_init_rhs<<<cdiv(npad, 256), 256, 0, c->stream>>>(npad, c->pos2cam, c->eab, c->chol_aux);
+    flow_args fl = {c->d_flow_tasks, c->d_flow_final, c->d_flow_defseq, c->d_flow_bseq, c->d_flow_critneed, c->d_flow_ver, c->n_tiles};
+    if (c->chol_flow && !ev) {
+        // dataflow: one launch for every step; the write counters start from zero
+        CUDA_CHECK(cudaMemsetAsync(c->d_flow_ver, 0, (size_t)(c->n_tiles + c->nt) * sizeof(int), c->stream));
+        auto kern = mod ? k_panel_step<true, true> : k_panel_step<false, true>;
+        psba_set_smem((const void *)kern, (int)CHOL_SMEM);
+        kern<<<c->n_flow_tasks, PANEL_NT, CHOL_SMEM, c->stream>>>(0, (const int4 *)c->d_crit_desc, (const int2 *)c->d_crit_src, 0, (const int4 *)c->d_def_desc,
+                                                              (const int2 *)c->d_def_srcs, (const int *)c->d_b_J, (const int *)c->d_b_sptr, (const int *)c->d_b_slot,
+                                                              c->Stiles, c->Ldiag, c->chol_aux, c->chol_diag, c->contrib, c->d_status, delta, c->d_status + 2, fl);
+        k_diag_inverse<<<c->nt, 256, 2 * TILE_SM * sizeof(double), c->stream>>>(c->Ldiag, c->Linv, c->d_status);
+        return;
+    }
     for (int s = 0; s < c->n_steps; ++s) {
         if (ev) CUDA_CHECK(cudaEventRecord((*ev)[s], c->stream));
         const int cb = c->step_crit_ptr[s], ncrit = c->step_crit_ptr[s + 1] - cb;
@@ -802,10 +948,11 @@ static void enqueue_factor(psba_ctx *c, std::vector<cudaEvent_t> *ev = nullptr)
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = c->chol_pdl ? 1 : 0;
-        CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_panel_step, ncrit, (const int4 *)(c->d_crit_desc + 2 * cb), (const int2 *)c->d_crit_src, ndef,
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, mod ? k_panel_step<true, false> : k_panel_step<false, false>, ncrit, (const int4 *)(c->d_crit_desc + 2 * cb),
+                                      (const int2 *)c->d_crit_src, ndef,
                                       (const int4 *)(c->d_def_desc + db), (const int2 *)c->d_def_srcs, (const int *)(c->d_b_J + bb),
                                       (const int *)(c->d_b_sptr + bb), (const int *)c->d_b_slot, c->Stiles, c->Ldiag, c->chol_aux,
-                                      c->chol_diag, c->contrib, c->d_status));
+                                      c->chol_diag, c->contrib, c->d_status, delta, c->d_status + 2, fl));
     }
     if (ev) CUDA_CHECK(cudaEventRecord((*ev)[c->n_steps], c->stream));
     k_diag_inverse<<<c->nt, 256, 2 * TILE_SM * sizeof(double), c->stream>>>(c->Ldiag, c->Linv, c->d_status);
@@ -818,7 +965,7 @@ double psba_launch_factor(psba_ctx *c, bool defer_status)
 {
     CUDA_CHECK(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream));
     if (!c->chol_graph_ok) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_panel_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CHOL_SMEM));
+        psba_set_smem((const void *)k_panel_step<false, false>, (int)CHOL_SMEM);
         cudaGraph_t graph;
         CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         enqueue_factor(c);
@@ -874,6 +1021,126 @@ double psba_launch_factor(psba_ctx *c, bool defer_status)
     c->factor_valid = (st == 0);
     c->S_valid = false;      // the factor overwrote the tile pool
     return st ? 1.0 : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Modified Cholesky of the trust-region fallback ON THE TILE POOL (cholmod_blk / get_delta_beta / compute_cholmod_E,
+// PSBA/cl_cholmod.cpp:25-202 -> CL_files/cholmod_blk.cl:87-847) for camera systems that are too large for the dense
+// single-CTA kernel of kernels_solve.cu.  Same quantities -- xi, gamma -> delta, beta; L L^T = S + diag(E);
+// E_i = sum_k L_ik^2 - S_ii; the number of 3-column blocks that took the modified path -- computed by the tiled,
+// multi-CTA step schedule above, with two documented differences from the reference's kernel:
+//   * the elimination runs in the solver's nested-dissection ORDER (P S P^T), not in the callers' camera order.  E
+//     is nonzero only where a pivot was replaced or at rounding level elsewhere, and lambda = |sum E| / N is a
+//     rounding-noise quantity by construction, so the value differs like it differs between two builds
+//     of the reference itself;
+//   * the `L_ij > beta` rescue (cholmod_blk.cl:534-611: theta / beta) is not applied; the largest factor entry is
+//     measured instead and reported (stat "cholmod_max_l_over_beta" > 1 means the reference would have rescaled).
+__global__ void k_tile_maxabs(int n_tiles_S, int nt, const int *__restrict__ tile_index, const int *__restrict__ pos2cam,
+                              const double *__restrict__ Stiles, double *__restrict__ diag_out, double *__restrict__ part2)
+{
+    // one CTA per tile slot (I, J) looked up from the index: |offdiag| and |diag| maxima, diagonal saved for E
+    __shared__ double sx[256], sg[256];
+    const int I = blockIdx.x / nt, J = blockIdx.x % nt;
+    double xi = 0.0, ga = 0.0;
+    const int slot = J <= I ? tile_index[I * nt + J] : -1;
+    if (slot >= 0 && slot < n_tiles_S) {
+        const double *t = Stiles + (size_t)slot * TS * TS;
+        for (int e = threadIdx.x; e < TS * TS; e += 256) {
+            const int r = e / TS, cc = e % TS;
+            const bool real = pos2cam[(I * TS + r) / 6] >= 0 && pos2cam[(J * TS + cc) / 6] >= 0;
+            if (!real || (I == J && cc > r)) continue;
+            const double v = fabs(t[e]);
+            if (I == J && r == cc) { ga = fmax(ga, v); diag_out[I * TS + r] = t[e]; } else xi = fmax(xi, v);
+        }
+    }
+    sx[threadIdx.x] = xi; sg[threadIdx.x] = ga;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) { sx[threadIdx.x] = fmax(sx[threadIdx.x], sx[threadIdx.x + w]); sg[threadIdx.x] = fmax(sg[threadIdx.x], sg[threadIdx.x + w]); }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part2[2 * blockIdx.x] = sx[0]; part2[2 * blockIdx.x + 1] = sg[0]; }
+}
+__global__ void k_max_pairs(int n, const double *__restrict__ part2, double *__restrict__ out2)
+{
+    __shared__ double sx[256], sg[256];
+    double xi = 0.0, ga = 0.0;
+    for (int q = threadIdx.x; q < n; q += 256) { xi = fmax(xi, part2[2 * q]); ga = fmax(ga, part2[2 * q + 1]); }
+    sx[threadIdx.x] = xi; sg[threadIdx.x] = ga;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) { sx[threadIdx.x] = fmax(sx[threadIdx.x], sx[threadIdx.x + w]); sg[threadIdx.x] = fmax(sg[threadIdx.x], sg[threadIdx.x + w]); }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out2[0] = sx[0]; out2[1] = sg[0]; }
+}
+// E of row r (solver's ordering) = sum of the squares of row r of the factor - S_rr; also max |L_rc| off the diagonal
+__global__ void k_tile_E(int nt, const int *__restrict__ tile_index, const int *__restrict__ pos2cam, const double *__restrict__ Stiles,
+                         const double *__restrict__ Ldiag, const double *__restrict__ Sdiag, double *__restrict__ E_cam, double *__restrict__ rowmax)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nt * TS) return;
+    const int I = r / TS, rr = r % TS, cam = pos2cam[r / 6];
+    if (cam < 0) { rowmax[r] = 0.0; return; }
+    double sum = 0.0, mx = 0.0;
+    for (int J = 0; J < I; ++J) {
+        const int slot = tile_index[I * nt + J];
+        if (slot < 0) continue;
+        const double *t = Stiles + (size_t)slot * TS * TS + rr * TS;
+        for (int cc = 0; cc < TS; ++cc) { const double v = t[cc]; sum += v * v; mx = fmax(mx, v); }
+    }
+    const double *d = Ldiag + (size_t)I * TS * TS + rr * TS;
+    for (int cc = 0; cc <= rr; ++cc) { const double v = d[cc]; sum += v * v; if (cc < rr) mx = fmax(mx, v); }
+    E_cam[cam * 6 + r % 6] = sum - Sdiag[r];
+    rowmax[r] = mx;                                            // signed maximum, as the reference's test `L_ij > beta`
+}
+
+// the dense single-CTA kernel (exact reference order) up to N = 1536, the tile pool beyond; PSBA_CHOLMOD_TILES=0/1 forces either
+bool psba_cholmod_use_tiles(psba_ctx *c)
+{
+    const char *e = getenv("PSBA_CHOLMOD_TILES");
+    if (e) return atoi(e) != 0;
+    return c->N > 1536;
+}
+
+double psba_launch_cholmod_tiles(psba_ctx *c, double *delta_out, double *beta_out, int *nmod_out, double *E_host, double *max_l_over_beta)
+{
+    const int nt = c->nt, npad = nt * TS, N = c->N;
+    double *Sdiag = (double *)psba_dev_alloc(c, (size_t)npad * 8, true), *part2 = (double *)psba_dev_alloc(c, (size_t)nt * nt * 16, true);
+    double *rowmax = (double *)psba_dev_alloc(c, (size_t)npad * 8, true);
+    k_tile_maxabs<<<nt * nt, 256, 0, c->stream>>>(c->n_tiles_S, nt, c->tile_index, c->pos2cam, c->Stiles, Sdiag, part2);
+    k_max_pairs<<<1, 256, 0, c->stream>>>(nt * nt, part2, c->d_scal + 8);
+    LAUNCH_CHECK();
+    CUDA_CHECK(cudaMemcpyAsync(c->h_scal + 8, c->d_scal + 8, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    const double xi = c->h_scal[8], gamma = c->h_scal[9];
+    const double delta = 1e-15 * fmax(xi + gamma, 1.0);           // cl_cholmod.cpp:161-164
+    double beta = fmax(gamma, 1e-15);
+    beta = sqrt(fmax(beta, xi / sqrt((double)N * N - 1)));
+    CUDA_CHECK(cudaMemsetAsync(c->d_status, 0, 4 * sizeof(int), c->stream));
+    psba_set_smem((const void *)k_panel_step<true, false>, (int)CHOL_SMEM);
+    PROF(c, KID_CHOLMOD) enqueue_factor(c, nullptr, true, delta);  // once per trust-region phase: launched step by step, no graph
+    k_tile_E<<<cdiv(npad, 128), 128, 0, c->stream>>>(nt, c->tile_index, c->pos2cam, c->Stiles, c->Ldiag, Sdiag, c->chol_E, rowmax);
+    c->st_launches += c->n_steps + 5;
+    LAUNCH_CHECK();
+    std::vector<double> E(N), rm(npad);
+    int st[4] = {0, 0, 0, 0};
+    CUDA_CHECK(cudaMemcpyAsync(E.data(), c->chol_E, (size_t)N * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(rm.data(), rowmax, (size_t)npad * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(st, c->d_status, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    psba_dev_free(c, Sdiag); psba_dev_free(c, part2); psba_dev_free(c, rowmax);
+    double sum = 0.0, lmax = 0.0;
+    for (int i = 0; i < N; ++i) sum += E[i];                      // trust_region.cpp:358-362 (callers' camera order)
+    for (int r = 0; r < npad; ++r) lmax = fmax(lmax, rm[r]);
+    if (E_host) for (int i = 0; i < N; ++i) E_host[i] = E[i];
+    if (delta_out) *delta_out = delta;
+    if (beta_out) *beta_out = beta;
+    if (nmod_out) *nmod_out = st[2];
+    if (max_l_over_beta) *max_l_over_beta = lmax / beta;
+    c->cholmod_max_l_over_beta = lmax / beta;
+    c->S_valid = false; c->factor_valid = false;                 // the modified factor overwrote the tile pool
+    return sum;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -967,22 +1234,6 @@ __global__ void __launch_bounds__(TS * BW_SLOTS) k_backward(int nt, const int *_
 __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define BW_STAMP(i) do { if (dbg && threadIdx.x == 0) dbg[i] = gtimer(); } while (0)
 #define FLAG_STRIDE 32        // ints between two flags (128 bytes)
-__device__ __forceinline__ int ld_acquire(const int *p)
-{
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ int ld_relaxed(const int *p)
-{
-    int v;
-    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(int *p, int v)
-{
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 __global__ void __launch_bounds__(TS * BWD_SLOTS, 1) k_backward_flow(const int *__restrict__ order, const int *__restrict__ cptr,
                                                                     const int *__restrict__ crow, const int *__restrict__ cslot,

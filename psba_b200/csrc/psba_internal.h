@@ -121,6 +121,10 @@ struct psba_ctx {
     int *d_crit_I, *d_crit_K, *d_psrc_ptr, *d_psrc, *d_b_J, *d_b_sptr, *d_b_slot;
     int *d_def_I, *d_def_J, *d_def_sptr, *d_def_src, *d_step_panels;
     int4 *d_crit_desc, *d_def_desc; int2 *d_crit_src, *d_def_srcs;   // flat task descriptors (one load per CTA)
+    // dataflow factorisation (k_panel_flow): task table in step order, per-tile write counters and what a task waits for
+    int n_flow_tasks; int2 *d_flow_tasks; int *d_flow_final, *d_flow_defseq, *d_flow_bseq, *d_flow_critneed, *d_flow_ver;
+    int camera_solver; double *pcg_work; double pcg_tol; int pcg_max_iter, pcg_last_iters;   // optional PCG camera solve (kernels_pcg.cu)
+    bool chol_flow;                 // one flag-driven launch instead of one kernel per step (PSBA_CHOL_FLOW=0 restores the step kernels)
     double *contrib;                // n_tiles * TS: L_IK y_K per factor tile
     double *Ldiag;                  // nt * TS*TS   factor of the diagonal tiles (kept out of the tile pool)
     int *d_coltile_ptr, *d_coltile_row, *d_coltile_slot;   // CSC of the factor tiles (backward solve)
@@ -144,6 +148,7 @@ struct psba_ctx {
     double initErr;
     std::vector<psba_trace_rec> trace;
     std::vector<double> force_lambda; int n_cholmod_events;
+    double cholmod_max_l_over_beta;   // tile-pool modified Cholesky: largest factor entry / beta of the last run
     // stats
     double st_tries, st_exqt, st_lin, st_launches;
     bool profile;
@@ -177,8 +182,12 @@ void psba_launch_solve(psba_ctx *c);         // dp[0..N) = S^-1 eab[0..N)
 void psba_tiles_to_dense(psba_ctx *c, double *dense_dev, bool mirror);
 void psba_launch_explicit_inverse(psba_ctx *c, double *out_dev);
 double psba_launch_cholmod(psba_ctx *c, double *delta, double *beta, int *nscalar);
+double psba_launch_cholmod_tiles(psba_ctx *c, double *delta, double *beta, int *nmod, double *E_host, double *max_l_over_beta);
+bool psba_cholmod_use_tiles(psba_ctx *c);
 double psba_launch_cholmod_dense(psba_ctx *c, int N, double *mat, double *aux, double *diagInv, double *E,
                                  double *delta, double *beta, int *nscalar);
+// ---- kernels_pcg.cu
+int psba_launch_pcg(psba_ctx *c);            // dp[0..N) = S^-1 eab[0..N) by block-Jacobi PCG; status word as the factorisation
 // ---- kernels_backsub.cu
 void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result *res);
 void psba_launch_newp(psba_ctx *c);
