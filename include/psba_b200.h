@@ -112,6 +112,16 @@ void psba_compute_ea(psba_ctx *ctx, int cnp, int pnp, int mnp, int n3Dpts, int n
  * Factorises S in place (blocked Cholesky); the explicit inverse is formed only when outMat is
  * non-NULL.  Returns 0.0, or 1.0 when S is not positive definite. */
 double psba_SPDinv(psba_ctx *ctx, int matSize, double *outMat);
+/* cholesky / trigMat_inv / trigMat_mul, PSBA/cl_spdinv.h:10-18 (cl_spdinv.cpp:57-103, 120-162, 169-204): the three stages of
+ * SPDinv.  outMat (N x N, may be NULL) in the callers' camera order: M with M M^T = S (the lower-triangular factor whenever the
+ * solver kept the natural camera order: every dense system), M^-1, S^-1.  cholesky returns 0.0 / 1.0 like SPDinv. */
+double psba_cholesky(psba_ctx *ctx, int matSize, double *outMat);
+double psba_trigMat_inv(psba_ctx *ctx, int matSize, double *outMat);
+void psba_trigMat_mul(psba_ctx *ctx, int matSize, double *outMat);
+/* get_delta_beta / compute_cholmod_E, PSBA/cl_cholmod.h:14-19 (cl_cholmod.cpp:109-167, 176-202): delta and beta of the S of the
+ * last compute_S; E of the last cholmod_blk */
+void psba_get_delta_beta(psba_ctx *ctx, int matSize, double *delta, double *beta);
+void psba_compute_cholmod_E(psba_ctx *ctx, int matSize, double *Eout);
 /* matVec_mul, PSBA/cl_linearalg.cpp:19-55: dp[0..N) = S^-1 * eab[0..N) (two triangular solves) */
 void psba_matVec_mul(psba_ctx *ctx, int mat_rsize, int mat_csize, double *out);
 /* compute_eb / compute_dpb, sba_func.cpp:1001-1062, 1067-1117 */

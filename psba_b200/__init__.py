@@ -78,6 +78,13 @@ def lib():
     L.psba_SPDinv.restype = d
     L.psba_SPDinv.argtypes = [vp, i, _dp]
     L.psba_matVec_mul.argtypes = [vp, i, i, _dp]
+    L.psba_cholesky.restype = d
+    L.psba_cholesky.argtypes = [vp, i, _dp]
+    L.psba_trigMat_inv.restype = d
+    L.psba_trigMat_inv.argtypes = [vp, i, _dp]
+    L.psba_trigMat_mul.argtypes = [vp, i, _dp]
+    L.psba_get_delta_beta.argtypes = [vp, i, _dp, _dp]
+    L.psba_compute_cholmod_E.argtypes = [vp, i, _dp]
     L.psba_compute_eb.argtypes = dims + [_dp]
     L.psba_compute_dpb.argtypes = [vp, i, i, i, i, _dp]
     L.psba_compute_newp.argtypes = [vp, i, i, _dp]
@@ -338,6 +345,30 @@ class PSBA:
         out = np.zeros((self.N, self.N)) if want else None
         ret = self.L.psba_SPDinv(self.h, self.N, _d(out))
         return (ret, out) if want else ret
+
+    def cholesky(self):
+        out = np.zeros((self.N, self.N))
+        return self.L.psba_cholesky(self.h, self.N, _d(out)), out
+
+    def trigMat_inv(self):
+        out = np.zeros((self.N, self.N))
+        self.L.psba_trigMat_inv(self.h, self.N, _d(out))
+        return out
+
+    def trigMat_mul(self):
+        out = np.zeros((self.N, self.N))
+        self.L.psba_trigMat_mul(self.h, self.N, _d(out))
+        return out
+
+    def get_delta_beta(self):
+        dl, bt = C.c_double(), C.c_double()
+        self.L.psba_get_delta_beta(self.h, self.N, C.byref(dl), C.byref(bt))
+        return dl.value, bt.value
+
+    def compute_cholmod_E(self):
+        out = np.zeros(self.N)
+        self.L.psba_compute_cholmod_E(self.h, self.N, _d(out))
+        return out
 
     def matVec_mul(self):
         out = np.zeros(self.N)

@@ -104,8 +104,14 @@ static bool compute_PB(psba_ctx *c, double *lambda)
             // it from Saux, trust_region.cpp:345-346), then the modified Cholesky picks lambda
             psba_launch_schur(c, 0.0);
             double delta, beta, sum; int nscalar = 0;
-            if (psba_cholmod_use_tiles(c)) sum = psba_launch_cholmod_tiles(c, &delta, &beta, &nscalar, nullptr, nullptr);   // large N: on the tile pool
-            else {
+            bool dense = !psba_cholmod_use_tiles(c);
+            if (!dense) {
+                double ratio = 0.0;
+                sum = psba_launch_cholmod_tiles(c, &delta, &beta, &nscalar, nullptr, &ratio);
+                const char *e = getenv("PSBA_CHOLMOD_TILES");
+                if (ratio > 1.0 && psba_cholmod_dense_possible(c) && !(e && atoi(e))) { dense = true; psba_launch_schur(c, 0.0); }   // the `> beta` rescue lives in the dense kernel
+            }
+            if (dense) {
                 const size_t nn = (size_t)c->N * c->N;
                 if (!c->Sdense) c->Sdense = (double *)psba_dev_alloc(c, nn * sizeof(double), true);
                 psba_tiles_to_dense(c, c->Sdense, true);

@@ -1095,12 +1095,35 @@ __global__ void k_tile_E(int nt, const int *__restrict__ tile_index, const int *
     rowmax[r] = mx;                                            // signed maximum, as the reference's test `L_ij > beta`
 }
 
-// the dense single-CTA kernel (exact reference order) up to N = 1536, the tile pool beyond; PSBA_CHOLMOD_TILES=0/1 forces either
+// The dense single-CTA kernel of kernels_solve.cu implements the reference's kernel in full (3x3 block path, `> beta`
+// roll-back, scalar Gill-Murray path with the theta / beta rescue) and is used up to N = 1536; the tile pool takes over
+// beyond (a 1.15 GB dense copy and O(N^3) on one SM at N = 12 000).  The null-space pivots of a gauge-free camera system
+// are rounding noise of either sign, and the beta / theta logic decides what replaces them: on the 7-camera set the
+// per-pivot rule of the tile version flags 2 block columns where the reference flags 1.  lambda = |sum E| / N is noise in
+// both.  PSBA_CHOLMOD_TILES=0/1 forces either.
 bool psba_cholmod_use_tiles(psba_ctx *c)
 {
     const char *e = getenv("PSBA_CHOLMOD_TILES");
     if (e) return atoi(e) != 0;
     return c->N > 1536;
+}
+bool psba_cholmod_dense_possible(psba_ctx *c) { return c->N <= 1536; }
+
+// get_delta_beta (PSBA/cl_cholmod.cpp:109-167) on the S of the tile pool
+void psba_tile_delta_beta(psba_ctx *c, double *delta, double *beta)
+{
+    const int nt = c->nt, npad = nt * TS, N = c->N;
+    double *Sdiag = (double *)psba_dev_alloc(c, (size_t)npad * 8, true), *part2 = (double *)psba_dev_alloc(c, (size_t)nt * nt * 16, true);
+    k_tile_maxabs<<<nt * nt, 256, 0, c->stream>>>(c->n_tiles_S, nt, c->tile_index, c->pos2cam, c->Stiles, Sdiag, part2);
+    k_max_pairs<<<1, 256, 0, c->stream>>>(nt * nt, part2, c->d_scal + 8);
+    LAUNCH_CHECK();
+    CUDA_CHECK(cudaMemcpyAsync(c->h_scal + 8, c->d_scal + 8, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    psba_dev_free(c, Sdiag); psba_dev_free(c, part2);
+    const double xi = c->h_scal[8], gamma = c->h_scal[9];
+    *delta = 1e-15 * fmax(xi + gamma, 1.0);
+    double b = fmax(gamma, 1e-15);
+    *beta = sqrt(fmax(b, xi / sqrt((double)N * N - 1)));
 }
 
 double psba_launch_cholmod_tiles(psba_ctx *c, double *delta_out, double *beta_out, int *nmod_out, double *E_host, double *max_l_over_beta)

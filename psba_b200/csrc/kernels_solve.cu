@@ -60,8 +60,9 @@ static void psba_factor_to_dense(psba_ctx *c, double *dense_dev)
 // ABI parity only (SPDinv's explicit inverse, cl_spdinv.cpp:18-40): column of S^-1 for (camera, component)
 // cidx by one forward and one backward substitution on the dense factor (solver's ordering, padded size
 // NP), written back in the callers' camera order.  O(NP^2) per thread; small N only.
+// half = 1: only the forward substitution, i.e. the column of L^-1 (trigMat_inv, cl_spdinv.cpp:120-162)
 __global__ void k_explicit_inverse(int N, int NP, const int *__restrict__ cam2pos, const double *__restrict__ L,
-                                   double *__restrict__ work, double *__restrict__ out)
+                                   double *__restrict__ work, double *__restrict__ out, int half)
 {
     int cidx = blockIdx.x * blockDim.x + threadIdx.x;
     if (cidx >= N) return;
@@ -72,6 +73,10 @@ __global__ void k_explicit_inverse(int N, int NP, const int *__restrict__ cam2po
         for (int k = 0; k < r; ++k) s -= L[(size_t)r * NP + k] * x[k];
         x[r] = s / L[(size_t)r * NP + r];
     }
+    if (half) {
+        for (int r = 0; r < N; ++r) out[(size_t)r * N + cidx] = x[cam2pos[r / 6] * 6 + r % 6];
+        return;
+    }
     for (int r = NP - 1; r >= 0; --r) {
         double s = x[r];
         for (int k = r + 1; k < NP; ++k) s -= L[(size_t)k * NP + r] * x[k];
@@ -80,18 +85,37 @@ __global__ void k_explicit_inverse(int N, int NP, const int *__restrict__ cam2po
     for (int r = 0; r < N; ++r) out[(size_t)r * N + cidx] = x[cam2pos[r / 6] * 6 + r % 6];
 }
 
-void psba_launch_explicit_inverse(psba_ctx *c, double *out_dev)
+// the factor itself in the callers' camera order: M = P^T L P (M M^T = S; lower triangular when the solver kept the natural order)
+__global__ void k_factor_callers_order(int N, int NP, const int *__restrict__ cam2pos, const double *__restrict__ L, double *__restrict__ out)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)N * N) return;
+    const int r = (int)(e / N), cc = (int)(e % N);
+    out[e] = L[(size_t)(cam2pos[r / 6] * 6 + r % 6) * NP + cam2pos[cc / 6] * 6 + cc % 6];
+}
+
+// what = 0: S^-1 (trigMat_mul after trigMat_inv), 1: L^-1 (trigMat_inv), 2: L (cholesky); all in the callers' camera order
+void psba_launch_factor_products(psba_ctx *c, double *out_dev, int what)
 {
     const size_t NP = (size_t)c->nt * TS;
-    double *Ld = nullptr, *work = nullptr;
-    Ld = (double *)psba_dev_alloc(c, NP * NP * sizeof(double), false);
-    work = (double *)psba_dev_alloc(c, NP * NP * sizeof(double), false);
+    double *Ld = (double *)psba_dev_alloc(c, NP * NP * sizeof(double), false);
     psba_factor_to_dense(c, Ld);
-    k_explicit_inverse<<<cdiv(c->N, 64), 64, 0, c->stream>>>(c->N, (int)NP, c->cam2pos, Ld, work, out_dev);
-    c->st_launches += 1;
+    if (what == 2) k_factor_callers_order<<<cdiv((long long)c->N * c->N, 256), 256, 0, c->stream>>>(c->N, (int)NP, c->cam2pos, Ld, out_dev);
+    else {
+        double *work = (double *)psba_dev_alloc(c, NP * NP * sizeof(double), false);
+        k_explicit_inverse<<<cdiv(c->N, 64), 64, 0, c->stream>>>(c->N, (int)NP, c->cam2pos, Ld, work, out_dev, what == 1 ? 1 : 0);
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        psba_dev_free(c, work);
+    }
+    c->st_launches += 2;
     LAUNCH_CHECK();
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    psba_dev_free(c, Ld); psba_dev_free(c, work);
+    psba_dev_free(c, Ld);
+}
+
+void psba_launch_explicit_inverse(psba_ctx *c, double *out_dev)
+{
+    psba_launch_factor_products(c, out_dev, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -133,7 +157,8 @@ __global__ void k_mat_max(int N, const double *__restrict__ mat, double *__restr
 // coalesced (row-major addressing made each lane pull its own 32-byte sector: 2.5 ms on N = 312).  Only E and the
 // number of scalar blocks leave this file.
 #define M(r, c) mat[(size_t)(c) * N + (r)]
-__global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ mat, double *__restrict__ aux, double *__restrict__ diagInv,
+#define CHM_NT 512
+__global__ void __launch_bounds__(CHM_NT) k_cholmod(int N, double *__restrict__ mat, double *__restrict__ aux, double *__restrict__ diagInv,
                                                   double *__restrict__ diag, double beta, double delta, int *__restrict__ nscalar_out)
 {
     extern __shared__ double rows3[];                    // [3][N]: the finished factor rows j3 .. j3+2 (columns < j3) of the current block
@@ -146,7 +171,7 @@ __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ ma
         const int j3 = j * 3;
         // the three pivot rows are read by nine threads running sequential dot products (T_jj) and by every row of the
         // block column: staged once by the whole CTA (the nine threads alone paid one L2 round trip per term: 24 us per block)
-        for (int e = tid; e < 3 * j3; e += 1024) { const int v = e / j3, cc = e - v * j3; rows3[v * N + cc] = M(j3 + v, cc); }
+        for (int e = tid; e < 3 * j3; e += CHM_NT) { const int v = e / j3, cc = e - v * j3; rows3[v * N + cc] = M(j3 + v, cc); }
         __syncthreads();
         if (tid < 9) {   // back up A_jj, diag; T_jj (cholmod_blk.cl:107-129)
             const int u = tid / 3, v = tid % 3;
@@ -193,12 +218,13 @@ __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ ma
         else if (N - (j + 1) * 3 >= 3) {
             // step 2 (cholmod_blk.cl:290-360): one thread per row (i,u) of the block column
             const int nrows = N - (j + 1) * 3;
-            for (int rr = tid; rr < nrows; rr += 1024) {
+            for (int rr = tid; rr < nrows; rr += CHM_NT) {
                 const int row = (j + 1) * 3 + rr;
                 const int i = row / 3, u = row % 3;
                 double Tij[3];
                 for (int v = 0; v < 3; ++v) { Tij[v] = M(row, j3 + v); aux[i * 9 + u * 3 + v] = Tij[v]; }
-                for (int k = 0; k < j; ++k) {               // per entry the reference's order: ascending k (cholmod_blk.cl:318-331)
+#pragma unroll 8
+                for (int k = 0; k < j; ++k) {               // per entry the reference's order: ascending k (cholmod_blk.cl:318-331); eight steps of loads in flight
                     const double a0 = M(row, k * 3), a1 = M(row, k * 3 + 1), a2 = M(row, k * 3 + 2);
 #pragma unroll
                     for (int v = 0; v < 3; ++v) Tij[v] -= a0 * rows3[v * N + k * 3] + a1 * rows3[v * N + k * 3 + 1] + a2 * rows3[v * N + k * 3 + 2];
@@ -212,7 +238,7 @@ __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ ma
             }
             __syncthreads();
             if (over) {   // step 3 failure branch (cholmod_blk.cl:386-414)
-                for (int rr = tid; rr < nrows; rr += 1024) {
+                for (int rr = tid; rr < nrows; rr += CHM_NT) {
                     const int row = (j + 1) * 3 + rr;
                     const int i = row / 3, u = row % 3;
                     for (int v = 0; v < 3; ++v) M(row, j3 + v) = aux[i * 9 + u * 3 + v];
@@ -243,8 +269,9 @@ __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ ma
                 }
                 __syncthreads();
                 const double ljj = mat[jj];
-                for (int i = x + 1 + tid; i < N; i += 1024) {
+                for (int i = x + 1 + tid; i < N; i += CHM_NT) {
                     double C = M(i, x);
+#pragma unroll 8
                     for (int k = 0; k < x; ++k) C = C - (M(i, k) * M(x, k));
                     aux[N + i] = C;
                     const double lij = C / ljj;
@@ -262,7 +289,7 @@ __global__ void __launch_bounds__(1024) k_cholmod(int N, double *__restrict__ ma
                         aux[x] = theta_s * theta_s;
                     }
                     __syncthreads();
-                    for (int i = x + 1 + tid; i < N; i += 1024) M(i, x) = aux[N + i] / theta_s;
+                    for (int i = x + 1 + tid; i < N; i += CHM_NT) M(i, x) = aux[N + i] / theta_s;
                 }
                 __syncthreads();
             }
@@ -305,7 +332,7 @@ double psba_launch_cholmod_dense(psba_ctx *c, int N, double *mat, double *aux, d
     const int dyn = 3 * N * (int)sizeof(double);
     if (dyn > 200 * 1024) { fprintf(stderr, "psba_b200: dense modified Cholesky: N = %d is beyond the single-CTA kernel (the tile-pool version handles it)\n", N); exit(EXIT_FAILURE); }
     psba_set_smem((const void *)k_cholmod, dyn);
-    PROF(c, KID_CHOLMOD) k_cholmod<<<1, 1024, dyn, c->stream>>>(N, mat, aux, diagInv, E, beta, delta, c->d_status + 2);
+    PROF(c, KID_CHOLMOD) k_cholmod<<<1, CHM_NT, dyn, c->stream>>>(N, mat, aux, diagInv, E, beta, delta, c->d_status + 2);
     k_cholmod_E<<<cdiv(N, 128), 128, 0, c->stream>>>(N, mat, E);
     c->st_launches += 3;
     LAUNCH_CHECK();

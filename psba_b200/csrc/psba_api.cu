@@ -394,6 +394,50 @@ extern "C" double psba_SPDinv(psba_ctx *c, int matSize, double *outMat)
     return ret;
 }
 
+// the three stages of SPDinv as the reference exports them (PSBA/cl_spdinv.h:10-18).  The engine factorises once; each entry
+// hands out its product in the CALLERS' camera order: cholesky -> M with M M^T = S (M = P^T L P: the lower-triangular factor
+// itself whenever the solver kept the natural camera order, i.e. for every dense system), trigMat_inv -> M^-1, trigMat_mul ->
+// S^-1.  Dense N x N outputs: small systems only.
+extern "C" double psba_cholesky(psba_ctx *c, int matSize, double *outMat)
+{
+    if (matSize != c->N) die("cholesky: matSize != 6*nCams");
+    if (!c->S_valid) die("cholesky before compute_S");
+    const double ret = psba_launch_factor(c);
+    if (ret == 0.0 && outMat) {
+        double *tmp = dalloc<double>(c, (size_t)c->N * c->N);
+        psba_launch_factor_products(c, tmp, 2);
+        d2h(c, outMat, tmp, (size_t)c->N * c->N);
+        psba_dev_free(c, tmp);
+    }
+    return ret;
+}
+static double factor_product(psba_ctx *c, int matSize, double *outMat, int what, const char *who)
+{
+    if (matSize != c->N) die("trigMat_*: matSize != 6*nCams");
+    if (!c->factor_valid) { fprintf(stderr, "psba_b200: %s before a successful cholesky / SPDinv\n", who); exit(EXIT_FAILURE); }
+    if (outMat) {
+        double *tmp = dalloc<double>(c, (size_t)c->N * c->N);
+        psba_launch_factor_products(c, tmp, what);
+        d2h(c, outMat, tmp, (size_t)c->N * c->N);
+        psba_dev_free(c, tmp);
+    }
+    return 0.0;
+}
+extern "C" double psba_trigMat_inv(psba_ctx *c, int matSize, double *outMat) { return factor_product(c, matSize, outMat, 1, "trigMat_inv"); }
+extern "C" void psba_trigMat_mul(psba_ctx *c, int matSize, double *outMat) { factor_product(c, matSize, outMat, 0, "trigMat_mul"); }
+// get_delta_beta / compute_cholmod_E (PSBA/cl_cholmod.h:14-19) on the S of the last compute_S / the E of the last cholmod_blk
+extern "C" void psba_get_delta_beta(psba_ctx *c, int matSize, double *delta, double *beta)
+{
+    if (matSize != c->N) die("get_delta_beta: matSize != 6*nCams");
+    if (!c->S_valid) die("get_delta_beta before compute_S");
+    psba_tile_delta_beta(c, delta, beta);
+}
+extern "C" void psba_compute_cholmod_E(psba_ctx *c, int matSize, double *Eout)
+{
+    if (matSize != c->N) die("compute_cholmod_E: matSize != 6*nCams");
+    if (Eout) d2h(c, Eout, c->chol_E, (size_t)c->N);
+}
+
 extern "C" void psba_matVec_mul(psba_ctx *c, int mat_rsize, int mat_csize, double *out)
 {
     (void)mat_rsize; (void)mat_csize;
@@ -454,7 +498,13 @@ extern "C" double psba_cholmod_blk(psba_ctx *c, int matSize, double *E, double *
 {
     if (matSize != c->N) die("cholmod_blk: matSize != 6*nCams");
     if (!c->S_valid) die("cholmod_blk needs the S of the last compute_S (call it again after a failed SPDinv)");
-    if (psba_cholmod_use_tiles(c)) return psba_launch_cholmod_tiles(c, delta, beta, n_scalar_blocks, E, nullptr);
+    if (psba_cholmod_use_tiles(c)) {
+        double ratio = 0.0;
+        const double sum = psba_launch_cholmod_tiles(c, delta, beta, n_scalar_blocks, E, &ratio);
+        const char *e = getenv("PSBA_CHOLMOD_TILES");
+        if (!(ratio > 1.0 && psba_cholmod_dense_possible(c) && !(e && atoi(e)))) return sum;
+        psba_launch_schur(c, c->mu_pending);          // the `> beta` rescue lives in the dense kernel: rebuild S for it
+    }
     ensure_dense(c);
     psba_tiles_to_dense(c, c->Sdense, true);
     const double sum = psba_launch_cholmod(c, delta, beta, n_scalar_blocks);

@@ -181,9 +181,12 @@ double psba_launch_factor(psba_ctx *c, bool defer_status = false);      // retur
 void psba_launch_solve(psba_ctx *c);         // dp[0..N) = S^-1 eab[0..N)
 void psba_tiles_to_dense(psba_ctx *c, double *dense_dev, bool mirror);
 void psba_launch_explicit_inverse(psba_ctx *c, double *out_dev);
+void psba_launch_factor_products(psba_ctx *c, double *out_dev, int what);   // 0 S^-1, 1 L^-1, 2 L (callers' camera order)
+void psba_tile_delta_beta(psba_ctx *c, double *delta, double *beta);
 double psba_launch_cholmod(psba_ctx *c, double *delta, double *beta, int *nscalar);
 double psba_launch_cholmod_tiles(psba_ctx *c, double *delta, double *beta, int *nmod, double *E_host, double *max_l_over_beta);
 bool psba_cholmod_use_tiles(psba_ctx *c);
+bool psba_cholmod_dense_possible(psba_ctx *c);
 double psba_launch_cholmod_dense(psba_ctx *c, int N, double *mat, double *aux, double *diagInv, double *E,
                                  double *delta, double *beta, int *nscalar);
 // ---- kernels_pcg.cu

@@ -57,6 +57,13 @@ def ring_problem(m=2000, n=1_000_000, d=5, w=64, seed=20262000, cam_noise=0.0, c
         depth = Xc[:, 2].reshape(c, d).mean(axis=1)
         pts0[a:b] = X + rng.normal(size=(c, 3)) * (0.01 * depth)[:, None]
     iidx = np.repeat(np.arange(n, dtype=np.int32), d)
+    import os
+    if os.environ.get("PSBA_SYNTH_SORT"):
+        # EXPERIMENT ONLY (memory-locality probe, never the bench default): points ordered by their first camera
+        order = np.argsort(jidx.reshape(n, d)[:, 0], kind="stable")
+        pts_true, pts0 = pts_true[order], pts0[order]
+        jidx = jidx.reshape(n, d)[order].ravel()
+        impts = impts.reshape(n, d, 2)[order].reshape(n * d, 2)
     return dict(m=m, n=n, o=n * d, K=K, initrot=initrot, cams=cams, pts=pts0, impts=impts, iidx=iidx, jidx=jidx,
                 pts_true=pts_true, name="ring-m%d-n%d-o%d-w%d" % (m, n, n * d, w), window=w, seed=seed)
 
