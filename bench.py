@@ -227,6 +227,7 @@ def main():
     ap.add_argument("--workload", default="ring-2000-1M-5M-w64", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-full-solve", action="store_true")
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -383,6 +384,28 @@ def main():
         e2e = {"value": e_tries * o / e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K),
                "seconds": round(e_s, 3), "host_memory": "page-locked (psba_host_alloc)", "includes": "setup_cl + fill_initBuffer2 (H2D) + fill_idxBuffer (H2D + device-built index structure) + K LM iterations + get_params (D2H)"}
 
+    # ---- informational: the WHOLE solve of the reference's main loop on the headline workload (levmar <-> trust_region until
+    # convergence, PSBA/main.cpp:192-209; the trust-region fallback runs the modified Cholesky on the tile pool), device-timed
+    full = None
+    if not args.no_full_solve:
+        G.set_params(cams0, pts0)
+        G.set_option("stats_reset", 0); G.set_option("lm_only", 0); G.set_option("max_iter", 50)
+        barrier()
+        G.set_option("timer_start", 0)
+        r = G.solve()
+        fms = G.stat("timer_ms")
+        barrier()
+        if world > 1:
+            t = torch.tensor([fms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            fms = float(t.item())
+        tr = G.trace()
+        nex = int(G.stat("exqt"))
+        full = {"ms": round(fms, 3), "outer_iterations": r["itno"], "tries": int(G.stat("tries")), "exit_flag": psba_b200.ITER_NAMES.get(r["flag"], r["flag"]),
+                "initial_cost": r["initErr"], "final_cost": r["finalErr"], "reprojections_per_s": nex * o / (fms * 1e-3),
+                "modified_cholesky_events": int(G.stat("cholmod_events")),
+                "pattern": "".join("C" if q["phase"] == 2 else ("A" if q["accepted"] else "x") for q in tr)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         run_cpu("port", cores, CPU_SAMPLE, 1)
@@ -402,7 +425,7 @@ def main():
                 "lm_iters_per_sec": its / (ms * 1e-3), "tries": tries, "lm_iterations": its, "final_cost": final_cost,
                 "gpu_launches": launches, "setup_seconds": round(setup_s, 3), "parity_vs_1gpu": parity,
                 "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "kernels": ktab,
-                "bal_full_solves": bal}
+                "full_solve": full, "bal_full_solves": bal}
         emit(line)
     G.close()
     if world > 1:

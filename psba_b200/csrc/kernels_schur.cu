@@ -233,9 +233,7 @@ struct seg_desc { int row, v0, v1, diag_chunk, sched0, sched1; };
 //           to groups of G lanes, largest first, a warp's worth at a time (shared counter; which group computes a
 //           chunk does not change its sum).  Per triple: Y_ik from shared memory, W_il by 256-bit gathers, 108 FMA.
 // Partial per chunk; k_S_finalize sums the partials of a pair in segment order.
-// PF: software pipelining in registers -- phase 1 keeps the blocks of TWO visits in flight, phase 2 fetches the W block of the
-// next triple before it multiplies the current one (36 more registers: used with one CTA of <= 320 threads per SM).
-template <int G, int NT, int MINB, bool PF>
+template <int G, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_schur_segs(const seg_desc *__restrict__ segs, const int *__restrict__ cam_obs,
                                                           const int *__restrict__ cam_pt, const int *__restrict__ sched,
                                                           const int *__restrict__ ch_beg, const int *__restrict__ ch_end,
@@ -261,31 +259,14 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_segs(const seg_desc *__restr
     for (int q = 0; q < 32; ++q) acc[q] = 0.0;
     int q_n = 0, i_n = 0;
     if (tid < nv) { q_n = __ldg(cam_obs + sd.v0 + tid); i_n = __ldg(cam_pt + sd.v0 + tid); }
-    double w_n[18], vi_n[6], g_n[3];
-    if (PF && tid < nv) {
-        load_blk18(W + (size_t)q_n * 18, w_n); load_sym6(Vinv + (size_t)i_n * 6, vi_n); load_vec3(gb + (size_t)i_n * 3, g_n[0], g_n[1], g_n[2]);
-        if (tid + NT < nv) { q_n = __ldg(cam_obs + sd.v0 + tid + NT); i_n = __ldg(cam_pt + sd.v0 + tid + NT); }
-    }
 #pragma unroll 1
     for (int r = tid; r < nv; r += NT) {
         double w[18], vi[6], g0, g1, g2;
-        if (PF) {
-#pragma unroll
-            for (int h = 0; h < 18; ++h) w[h] = w_n[h];
-#pragma unroll
-            for (int h = 0; h < 6; ++h) vi[h] = vi_n[h];
-            g0 = g_n[0]; g1 = g_n[1]; g2 = g_n[2];
-            if (r + NT < nv) {                                    // the next visit's blocks fly while this one is multiplied
-                load_blk18(W + (size_t)q_n * 18, w_n); load_sym6(Vinv + (size_t)i_n * 6, vi_n); load_vec3(gb + (size_t)i_n * 3, g_n[0], g_n[1], g_n[2]);
-                if (r + 2 * NT < nv) { q_n = __ldg(cam_obs + sd.v0 + r + 2 * NT); i_n = __ldg(cam_pt + sd.v0 + r + 2 * NT); }
-            }
-        } else {
-            const int q = q_n, i = i_n;
-            if (r + NT < nv) { q_n = __ldg(cam_obs + sd.v0 + r + NT); i_n = __ldg(cam_pt + sd.v0 + r + NT); }
-            load_blk18(W + (size_t)q * 18, w);
-            load_sym6(Vinv + (size_t)i * 6, vi);
-            load_vec3(gb + (size_t)i * 3, g0, g1, g2);
-        }
+        const int q = q_n, i = i_n;
+        if (r + NT < nv) { q_n = __ldg(cam_obs + sd.v0 + r + NT); i_n = __ldg(cam_pt + sd.v0 + r + NT); }
+        load_blk18(W + (size_t)q * 18, w);
+        load_sym6(Vinv + (size_t)i * 6, vi);
+        load_vec3(gb + (size_t)i * 3, g0, g1, g2);
         const double i00 = vi[0], i10 = vi[1], i20 = vi[2], i11 = vi[3], i21 = vi[4], i22 = vi[5];
         double2 *yd = reinterpret_cast<double2 *>(Ysm + (size_t)r * 18);
 #pragma unroll
@@ -347,28 +328,12 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_segs(const seg_desc *__restr
         int t = beg + gl;
         int r_n = 0, b_n = 0;
         if (t < end) { r_n = __ldg(tri_vr + t); b_n = __ldg(tri_ob + t); }
-        double wb_n[18];
-        if (PF && t < end) {
-            load_blk18(W + (size_t)b_n * 18, wb_n);
-            if (t + G < end) b_n = __ldg(tri_ob + t + G);
-        }
 #pragma unroll 1
         for (; t < end; t += G) {
-            const int r = r_n;
+            const int r = r_n, b = b_n;
+            if (t + G < end) { r_n = __ldg(tri_vr + t + G); b_n = __ldg(tri_ob + t + G); }
             double wb[18];
-            if (PF) {
-#pragma unroll
-                for (int h = 0; h < 18; ++h) wb[h] = wb_n[h];
-                if (t + G < end) {
-                    r_n = __ldg(tri_vr + t + G);
-                    load_blk18(W + (size_t)b_n * 18, wb_n);          // next triple's block flies under this triple's 108 FMA
-                    if (t + 2 * G < end) b_n = __ldg(tri_ob + t + 2 * G);
-                }
-            } else {
-                const int b = b_n;
-                if (t + G < end) { r_n = __ldg(tri_vr + t + G); b_n = __ldg(tri_ob + t + G); }
-                load_blk18(W + (size_t)b * 18, wb);
-            }
+            load_blk18(W + (size_t)b * 18, wb);
             const double2 *yp = reinterpret_cast<const double2 *>(Ysm + (size_t)r * 18);
 #pragma unroll
             for (int rp = 0; rp < 3; ++rp) {                     // two rows of Y_ik (three double2) at a time
@@ -395,28 +360,23 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_segs(const seg_desc *__restr
     }
 }
 
-template <int G, int NT, int MINB, bool PF>
-static void launch_segs_t(psba_ctx *c)
-{
-    const int dyn = c->seg_v * 144;
-    psba_set_smem((const void *)k_schur_segs<G, NT, MINB, PF>, dyn);
-    k_schur_segs<G, NT, MINB, PF><<<c->n_seg, NT, dyn, c->stream>>>((const seg_desc *)c->seg_desc, c->cam_obs, c->cam_pt, c->sched_chunk, c->sch_beg,
-                                                              c->sch_end, c->tri_vr, c->tri_ob, c->W, c->Vinv, c->g + c->N, c->pair_part);
-}
-// launch shapes (PSBA_SEG_CFG): 0 = 256 threads x 2 CTAs per SM (128 registers), 1 = 192 x 2 (168 registers, no spills),
-// 2 = 384 x 1 (168 registers; the Y tile may then take up to 1400 visits), 3 = 512 x 1 (128 registers),
-// 4 = 320 x 1 and 5 = 256 x 1 with the register pipelining PF
+// Launch shape: 384 threads, ONE CTA per SM (the kernel needs 162 registers), Y tile of up to 1 280 visits (180 KB).  Measured
+// on the headline workload (15 M triples; profiles/pair_pass_r02.md): 256 x 2 at 128 registers (spills) 1.49 ms, 192 x 2
+// 1.30, 512 x 1 at 128 registers 1.11, 384 x 1 0.83; lanes per chunk G = 2 / 4 / 8 / 16 / 32: 1.28 / 0.95 / 0.83 / 1.00 / 1.34;
+// segments of 640 instead of 1 280 visits 0.88; the W block of the next triple prefetched into registers (224 registers,
+// 256 x 1) 0.84 -- no gain: the kernel is bound by the gather rate of the memory system, not by a lane's latency chain.
+#define SEG_NT 384
 template <int G>
 static void launch_segs(psba_ctx *c)
 {
-    if (c->seg_cfg == 1) launch_segs_t<G, 192, 2, false>(c);
-    else if (c->seg_cfg == 2) launch_segs_t<G, 384, 1, false>(c);
-    else if (c->seg_cfg == 3) launch_segs_t<G, 512, 1, false>(c);
-    else if (c->seg_cfg == 4) launch_segs_t<G, 320, 1, true>(c);
-    else if (c->seg_cfg == 5) launch_segs_t<G, 256, 1, true>(c);
-    else launch_segs_t<G, 256, 2, false>(c);
+    const int dyn = c->seg_v * 144;
+    psba_set_smem((const void *)k_schur_segs<G, SEG_NT, 1>, dyn);
+    k_schur_segs<G, SEG_NT, 1><<<c->n_seg, SEG_NT, dyn, c->stream>>>((const seg_desc *)c->seg_desc, c->cam_obs, c->cam_pt, c->sched_chunk, c->sch_beg,
+                                                                   c->sch_end, c->tri_vr, c->tri_ob, c->W, c->Vinv, c->g + c->N, c->pair_part);
 }
 
+// position of entry (r,cc) of the camera block (k,l) inside the tile pool: the camera system is stored in
+// the solver's camera ordering (cam2pos); a block that lands above the diagonal is stored transposed
 __device__ __forceinline__ double *s_entry(double *Stiles, const int *__restrict__ tile_index, int nt, int pk, int pl, int r, int cc)
 {
     if (pk < pl) { int t = pk; pk = pl; pl = t; t = r; r = cc; cc = t; }

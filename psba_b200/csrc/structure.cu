@@ -291,12 +291,12 @@ static void build_segments(psba_ctx *c, const long long *tptr, const std::vector
     cudaStream_t st = c->stream;
     const int m = c->m, o = c->o;
     c->n_seg = 0; c->n_pchunk = 0;
-    c->seg_cfg = getenv("PSBA_SEG_CFG") ? atoi(getenv("PSBA_SEG_CFG")) : 2;    // measured on the headline workload: 384 x 1, 1280 visits, G = 8 is the fastest shape
-    c->seg_v = c->seg_cfg >= 2 ? 1280 : 640;                 // Y tile: 144 B per visit; two resident CTAs (one for cfg 2) share the SM's 227 KB
+    c->seg_cfg = 2;
+    c->seg_v = 1280;                                         // Y tile: 144 B per visit, one resident CTA per SM (kernels_schur.cu: launch shape)
     // small problems: enough segments to fill the machine four times over (Venice-52: 312 segments of 1 280 visits were three
     // uneven waves of one CTA per SM)
     if ((long long)o < (long long)c->seg_v * 4 * c->n_sm) c->seg_v = std::max(128, std::min(c->seg_v, cdiv(o, 4 * c->n_sm)));
-    if (getenv("PSBA_SEG_V")) c->seg_v = std::max(32, std::min(c->seg_cfg >= 2 ? SEG_V_MAX : 700, atoi(getenv("PSBA_SEG_V"))));
+    if (getenv("PSBA_SEG_V")) c->seg_v = std::max(32, std::min(SEG_V_MAX, atoi(getenv("PSBA_SEG_V"))));
     // ---- segments (host: m cameras)
     std::vector<seg_desc_h> segs;
     std::vector<int> row_seg_ptr((size_t)m + 1, 0), seglen(m, 1);
