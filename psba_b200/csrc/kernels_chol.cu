@@ -323,8 +323,7 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
     {
         std::vector<int> order(step_panels.rbegin(), step_panels.rend());        // last step first
         up_vec(c, &c->d_bw_order, order);
-        c->d_xdone = (int *)psba_dev_alloc(c, (size_t)nt * 32 * sizeof(int), true);
-        c->bw_epoch = 0;
+        c->bw_xbuf = (double *)psba_dev_alloc(c, (size_t)nt * TS * sizeof(double), true);
     }
     up_vec(c, &c->d_coltile_ptr, cptr); up_vec(c, &c->d_coltile_row, crow); up_vec(c, &c->d_coltile_slot, cslot);
     c->Stiles = (double *)psba_dev_alloc(c, (size_t)c->n_tiles * TS * TS * sizeof(double), true);
@@ -372,6 +371,17 @@ __device__ __forceinline__ void st_release(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const double *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_f64(double *p, double v)
+{
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+#define X_SENTINEL 0xFFFFFFFFFFFFFFFFull      // "not there yet" in the solution buffer of the dataflow backward solve (a NaN no solve produces)
 __device__ __forceinline__ void red_release_add(int *p, int v)
 {
     asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -913,18 +923,19 @@ __global__ void __launch_bounds__(256) k_diag_inverse(const double *__restrict__
 }
 
 // b0 = ea in the camera ordering of S (zero on the padding)
-__global__ void k_init_rhs(int npad, const int *__restrict__ pos2cam, const double *__restrict__ ea, double *__restrict__ b)
+__global__ void k_init_rhs(int npad, const int *__restrict__ pos2cam, const double *__restrict__ ea, double *__restrict__ b, double *__restrict__ xbuf)
 {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= npad) return;
     const int cam = pos2cam[k / 6];
     b[k] = cam >= 0 ? ea[cam * 6 + k % 6] : 0.0;
+    if (xbuf) reinterpret_cast<unsigned long long *>(xbuf)[k] = X_SENTINEL;   // the backward solve of this factorisation starts from "nothing known"
 }
 
 static void enqueue_factor(psba_ctx *c, std::vector<cudaEvent_t> *ev = nullptr, bool mod = false, double delta = 0.0)
 {
     const int npad = c->nt * TS;
-    k_init_rhs<<<cdiv(npad, 256), 256, 0, c->stream>>>(npad, c->pos2cam, c->eab, c->chol_aux);
+    k_init_rhs<<<cdiv(npad, 256), 256, 0, c->stream>>>(npad, c->pos2cam, c->eab, c->chol_aux, c->bw_xbuf);
     flow_args fl = {c->d_flow_tasks, c->d_flow_final, c->d_flow_defseq, c->d_flow_bseq, c->d_flow_critneed, c->d_flow_ver, c->n_tiles};
     if (c->chol_flow && !ev) {
         // dataflow: one launch for every step; the write counters start from zero
@@ -1261,8 +1272,8 @@ __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u
 __global__ void __launch_bounds__(TS * BWD_SLOTS, 1) k_backward_flow(const int *__restrict__ order, const int *__restrict__ cptr,
                                                                     const int *__restrict__ crow, const int *__restrict__ cslot,
                                                                     const double *__restrict__ Stiles, const double *__restrict__ Linv,
-                                                                    double *ywork, const int *__restrict__ pos2cam, double *__restrict__ sol,
-                                                                    int *xdone, int epoch, int *__restrict__ status)
+                                                                    const double *__restrict__ ywork, const int *__restrict__ pos2cam, double *__restrict__ sol,
+                                                                    double *xbuf, int *__restrict__ status)
 {
     __shared__ double part[BWD_SLOTS][TS];
     __shared__ double xs[BWD_SLOTS][TS];
@@ -1284,29 +1295,24 @@ __global__ void __launch_bounds__(TS * BWD_SLOTS, 1) k_backward_flow(const int *
         for (int r = 0; r < TS; ++r) lv[r] = __ldg(L + r * TS);
     }
     for (int e = tid; e < TS * TS; e += TS * BWD_SLOTS) invs[e] = __ldg(Linv + (size_t)I * TS * TS + e);
-    const double yI = tid < TS ? __ldcg(ywork + I * TS + tid) : 0.0;
+    const double yI = tid < TS ? __ldg(ywork + I * TS + tid) : 0.0;
     BW_STAMP(1);
-    // wait for the x_J of this column: ONE lane per dependency polls (relaxed load + back-off; flags are 128
-    // bytes apart so that the pollers of the whole grid do not queue up on one L2 slice), then the CTA
-    // synchronises and a single fence orders the x loads behind the flags
-    for (int t = beg + tid; t < end; t += TS * BWD_SLOTS) {
-        const int *f = xdone + (size_t)crow[t] * FLAG_STRIDE;
-        int spins = 0;
-        while (ld_acquire(f) != epoch) {              // acquire by the polling lane + the barrier below order the x loads of every thread
-            if (++spins > (1 << 22)) { *status = 3; break; }
-        }
-    }
-    BW_STAMP(2);
-    __syncthreads();
-    BW_STAMP(3);
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     for (int t0 = beg; t0 < end; t0 += BWD_SLOTS) {
-        // x_J of this slot's tile: ONE coherent load per thread into shared memory (L2-coherent loads are
-        // not pipelined by the hardware: 48 of them in a row cost 48 round trips)
+        // x_J of this slot's tile: every thread polls ITS element of the solution buffer until the producer's value has
+        // replaced the sentinel -- the data is its own flag (one L2 round trip after the store instead of flag poll +
+        // barrier + coherent load); a bounded spin turns a broken schedule into status 3
         const int t = t0 + slotid;
         if (t < end) {
             const int J = t0 == beg ? myrow : crow[t];
-            xs[slotid][col] = __ldcg(ywork + J * TS + col);
+            const double *src = xbuf + J * TS + col;
+            unsigned long long bits = ld_relaxed_u64(src);
+            int spins = 0;
+            while (bits == X_SENTINEL) {
+                if (++spins > (1 << 22)) { atomicMax(status, 3); bits = 0; break; }
+                bits = ld_relaxed_u64(src);
+            }
+            xs[slotid][col] = __longlong_as_double((long long)bits);
             if (t0 != beg) {
                 const double *L = Stiles + (size_t)cslot[t] * TS * TS + col;
 #pragma unroll
@@ -1321,6 +1327,7 @@ __global__ void __launch_bounds__(TS * BWD_SLOTS, 1) k_backward_flow(const int *
         }
         __syncthreads();
     }
+    BW_STAMP(3);
     part[slotid][col] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (tid < TS) {
@@ -1338,14 +1345,13 @@ __global__ void __launch_bounds__(TS * BWD_SLOTS, 1) k_backward_flow(const int *
     }
     __syncthreads();
     if (tid < TS) {
-        const double a = (mv[0][tid] + mv[1][tid]) + (mv[2][tid] + mv[3][tid]);
-        __stcg(ywork + I * TS + tid, a);
+        double a = (mv[0][tid] + mv[1][tid]) + (mv[2][tid] + mv[3][tid]);
+        if (__double_as_longlong(a) == (long long)X_SENTINEL) a = __longlong_as_double(0x7FF8000000000000ll);   // a NaN solution must not look like "not there yet"
+        st_relaxed_f64(xbuf + I * TS + tid, a);
         const int pos = I * TS + tid, cam = pos2cam[pos / 6];
         if (cam >= 0) sol[cam * 6 + pos % 6] = a;
     }
-    __syncthreads();
     BW_STAMP(4);
-    if (tid == 0) st_release(xdone + (size_t)I * FLAG_STRIDE, epoch);
     BW_STAMP(5);
 }
 
@@ -1358,7 +1364,6 @@ void psba_launch_solve(psba_ctx *c)
         LAUNCH_CHECK();
         return;
     }
-    c->bw_epoch += 1;
     static int dbg_runs = getenv("PSBA_BW_DEBUG") ? 3 : 0;
     long long *dbg_dev = nullptr;
     if (dbg_runs > 0) {
@@ -1367,8 +1372,7 @@ void psba_launch_solve(psba_ctx *c)
         CUDA_CHECK(cudaMemcpyToSymbol(g_panel_dbg, &dbg_dev, sizeof(dbg_dev)));
     }
     PROF(c, KID_TRI_SOLVE) k_backward_flow<<<c->nt, TS * BWD_SLOTS, 0, c->stream>>>(c->d_bw_order, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
-                                                                        c->Stiles, c->Linv, c->chol_diag, c->pos2cam, c->dp, c->d_xdone, c->bw_epoch,
-                                                                        c->d_status);
+                                                                        c->Stiles, c->Linv, c->chol_diag, c->pos2cam, c->dp, c->bw_xbuf, c->d_status);
     c->st_launches += 1;
     LAUNCH_CHECK();
     if (dbg_dev) {

@@ -204,7 +204,7 @@ extern "C" void psba_release_buffer(psba_ctx *c)
                     c->pchunk_beg, c->pchunk_end, c->W, c->V, c->Vinv, c->U, c->g, c->UVdiag_scr, c->cam_part, c->pair_part,
                     c->tile_index, c->Stiles, c->Linv, c->eab, c->dp, c->d_status, c->Ldiag, c->cam2pos, c->pos2cam, c->d_crit_I, c->d_crit_K,
                     c->d_psrc_ptr, c->d_psrc, c->d_b_J, c->d_b_sptr, c->d_b_slot, c->d_def_I, c->d_def_J, c->d_def_sptr, c->d_def_src,
-                    c->d_step_panels, c->d_crit_desc, c->d_def_desc, c->d_crit_src, c->d_def_srcs, c->d_bw_order, c->d_xdone, c->contrib, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
+                    c->d_step_panels, c->d_crit_desc, c->d_def_desc, c->d_crit_src, c->d_def_srcs, c->d_bw_order, c->bw_xbuf, c->contrib, c->d_coltile_ptr, c->d_coltile_row, c->d_coltile_slot,
                     c->Sdense, c->Sdense_aux, c->chol_aux, c->chol_diag, c->chol_E, c->d_part, c->d_scal, c->P_U, c->P_B, c->P,
                     c->pcg_work, c->d_flow_tasks, c->d_flow_final, c->d_flow_defseq, c->d_flow_bseq, c->d_flow_critneed, c->d_flow_ver,
                     c->tmpA, c->tmpB, (void *)c->ext.kc, (void *)c->ext.wgt, c->seg_desc, c->sched_chunk, c->sch_beg, c->sch_end, c->tri_vr};

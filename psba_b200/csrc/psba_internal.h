@@ -129,7 +129,7 @@ struct psba_ctx {
     double *Ldiag;                  // nt * TS*TS   factor of the diagonal tiles (kept out of the tile pool)
     int *d_coltile_ptr, *d_coltile_row, *d_coltile_slot;   // CSC of the factor tiles (backward solve)
     cudaGraphExec_t bw_graph; bool bw_graph_ok;
-    int *d_bw_order, *d_xdone; int bw_epoch;   // dataflow backward solve: panel order, per-panel flags, epoch
+    int *d_bw_order; double *bw_xbuf;           // dataflow backward solve: panel order, solution buffer in the solver's ordering (sentinel = not there yet)
     cudaGraphExec_t chol_graph; bool chol_graph_ok;
     bool S_valid, factor_valid;
     double *Sdense, *Sdense_aux;    // N*N, only allocated on demand (compat / cholmod)
