@@ -375,142 +375,6 @@ static void launch_segs(psba_ctx *c)
                                                                    c->sch_end, c->tri_vr, c->tri_ob, c->W, c->Vinv, c->g + c->N, c->pair_part);
 }
 
-// ---- Segment kernel on the FP64 tensor cores -----------------------------------------------------------
-// Same segments, chunks and schedule as k_schur_segs; what changes is who holds what.  A WARP owns a whole 6x3 block:
-// lane (fr, fk) = (lane / 4, lane % 4) holds entry (fr, fk) of it (18 of the 32 lanes; rows 6-7 and column 3 are the zero
-// padding of the 8x4 fragment of mma.m8n8k4.f64).  The lanes of a warp therefore read ONE contiguous 144-byte block per
-// load instruction -- two cache lines per request instead of thirty-two for a lane-per-triple gather -- and the sum over
-// the triples of a chunk happens inside the accumulator fragment of the tensor core: no cross-lane reduction at all.
-//  phase 1  warp per visit: A = W_ik (6x3), B = Vinv_i (3x3)  ->  Y_ik = W_ik Vinv_i in the accumulator layout, two shuffles
-//           turn it into the A layout, it goes to the shared tile, and ONE more DMMA adds Y_ik [W_ik ; gb_i]^T (columns
-//           0-5: the diagonal block, compute_S.cl:44-52; column 6: Y_ik gb_i, compute_ea.cl:27-33);
-//  phase 2  warp per chunk: per triple A = Y_ik from the shared tile, B = W_il straight from global memory, one DMMA.
-// Four accumulators per warp (triple t goes to t mod 4, summed at the end in a fixed order) keep four DMMA in flight.
-__device__ __forceinline__ void dmma_acc(double &c0, double &c1, double a, double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-template <int NT, int UNR>
-__global__ void __launch_bounds__(NT, 1) k_schur_mma(const seg_desc *__restrict__ segs, const int *__restrict__ cam_obs,
-                                                      const int *__restrict__ cam_pt, const int *__restrict__ sched,
-                                                      const int *__restrict__ ch_beg, const int *__restrict__ ch_end,
-                                                      const unsigned short *__restrict__ tri_vr, const int *__restrict__ tri_ob,
-                                                      const double *__restrict__ W, const double *__restrict__ Vinv,
-                                                      const double *__restrict__ gb, double *__restrict__ part)
-{
-    extern __shared__ __align__(16) double Ysm[];                 // [visits of the segment][18]
-    constexpr int NW = NT / 32;
-    __shared__ double red[NW][64];
-    __shared__ int4 sdesc[SEG_MAXD];
-    __shared__ int next;
-    const seg_desc sd = segs[blockIdx.x];
-    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    const int fr = lane >> 2, fk = lane & 3;
-    const bool act = fr < 6 && fk < 3;                            // this lane holds an entry of a 6x3 block
-    const int eoff = act ? fr * 3 + fk : 0;
-    const int nv = sd.v1 - sd.v0, nch = sd.sched1 - sd.sched0;
-    if (tid == 0) next = 0;
-    for (int j = tid; j < min(nch, SEG_MAXD); j += NT) {          // chunk descriptors of phase 2 fly under phase 1
-        const int c = __ldg(sched + sd.sched0 + j);
-        sdesc[j] = make_int4(__ldg(ch_beg + c), __ldg(ch_end + c), c, 0);
-    }
-    // ---- phase 1: warp w owns the visits [w * per, (w + 1) * per) of the segment
-    {
-        const int per = (nv + NW - 1) / NW;
-        const int r0 = wrp * per, r1 = min(nv, r0 + per);
-        // Vinv_i as the B fragment: B[k = fk][col = fr] = Vinv[fk][fr], packed (i00,i10,i20,i11,i21,i22)
-        const bool vact = fr < 3 && fk < 3;
-        const int hi = max(fr, fk), lo = min(fr, fk);
-        const int voff = lo == 0 ? hi : (lo == 1 ? hi + 2 : 5);
-        const bool gact = fr == 6 && fk < 3;
-        double d0[4] = {0.0, 0.0, 0.0, 0.0}, d1[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int rb = r0; rb < r1; rb += 32) {
-            const int cnt = min(32, r1 - rb);
-            int q_l = 0, i_l = 0;
-            if (lane < cnt) { q_l = __ldg(cam_obs + sd.v0 + rb + lane); i_l = __ldg(cam_pt + sd.v0 + rb + lane); }
-#pragma unroll 1
-            for (int u0 = 0; u0 < cnt; u0 += 4) {
-                double wv[4], vb[4], gv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int q = __shfl_sync(0xffffffffu, q_l, (u0 + u) & 31), i = __shfl_sync(0xffffffffu, i_l, (u0 + u) & 31);
-                    const bool ok = u0 + u < cnt;
-                    wv[u] = ok && act ? __ldg(W + (size_t)q * 18 + eoff) : 0.0;
-                    vb[u] = ok && vact ? __ldg(Vinv + (size_t)i * 6 + voff) : 0.0;
-                    gv[u] = ok && gact ? __ldg(gb + (size_t)i * 3 + fk) : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    double y0 = 0.0, y1 = 0.0;
-                    dmma_acc(y0, y1, wv[u], vb[u]);               // Y = W Vinv: lane holds Y[fr][2 fk], Y[fr][2 fk + 1]
-                    const int src = (lane & ~3) | (fk >> 1);
-                    const double v0 = __shfl_sync(0xffffffffu, y0, src), v1 = __shfl_sync(0xffffffffu, y1, src);
-                    const double ya = fk == 3 ? 0.0 : ((fk & 1) ? v1 : v0);      // A layout: Y[fr][fk]
-                    if (act && u0 + u < cnt) Ysm[(size_t)(rb + u0 + u) * 18 + eoff] = ya;
-                    dmma_acc(d0[u], d1[u], ya, fr < 6 ? wv[u] : gv[u]);          // [Y W^T | Y gb]
-                }
-            }
-        }
-        red[wrp][fr * 8 + 2 * fk] = (d0[0] + d0[1]) + (d0[2] + d0[3]);
-        red[wrp][fr * 8 + 2 * fk + 1] = (d1[0] + d1[1]) + (d1[2] + d1[3]);
-    }
-    __syncthreads();                                              // Y tile complete, warp sums published, `next` and sdesc visible
-    if (tid < 64) {
-        const int r = tid >> 3, cc = tid & 7;
-        if (r < 6 && cc <= 6 && (cc <= r || cc == 6)) {           // lower triangle of the (symmetric) diagonal block + the ea column
-            double sum = 0.0;
-#pragma unroll
-            for (int w8 = 0; w8 < NW; ++w8) sum += red[w8][tid];
-            double *out = part + (size_t)sd.diag_chunk * 42;
-            if (cc == 6) out[36 + r] = sum;
-            else { out[r * 6 + cc] = sum; out[cc * 6 + r] = sum; }
-        }
-    }
-    // ---- phase 2: warp per chunk, largest first
-    for (;;) {
-        int j = 0;
-        if (lane == 0) j = atomicAdd(&next, 1);
-        j = __shfl_sync(0xffffffffu, j, 0);
-        if (j >= nch) break;
-        int beg, end, c;
-        if (j < SEG_MAXD) { const int4 d = sdesc[j]; beg = d.x; end = d.y; c = d.z; }
-        else { c = __ldg(sched + sd.sched0 + j); beg = __ldg(ch_beg + c); end = __ldg(ch_end + c); }
-        double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int tb = beg; tb < end; tb += 32) {
-            const int cnt = min(32, end - tb);
-            int r_l = 0, b_l = 0;
-            if (lane < cnt) { r_l = __ldg(tri_vr + tb + lane); b_l = __ldg(tri_ob + tb + lane); }
-#pragma unroll 1
-            for (int u0 = 0; u0 < cnt; u0 += UNR) {
-                double wv[UNR], yv[UNR];
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    const int r = __shfl_sync(0xffffffffu, r_l, (u0 + u) & 31), b = __shfl_sync(0xffffffffu, b_l, (u0 + u) & 31);
-                    const bool ok = act && u0 + u < cnt;
-                    wv[u] = ok ? __ldg(W + (size_t)b * 18 + eoff) : 0.0;
-                    yv[u] = ok ? Ysm[(size_t)r * 18 + eoff] : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) dmma_acc(a0[u & 3], a1[u & 3], yv[u], wv[u]);
-            }
-        }
-        if (act) {
-            const double s0 = (a0[0] + a0[1]) + (a0[2] + a0[3]), s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
-            *reinterpret_cast<double2 *>(part + (size_t)c * 42 + fr * 6 + 2 * fk) = make_double2(s0, s1);
-        }
-    }
-}
-
-template <int NT, int UNR>
-static void launch_mma(psba_ctx *c)
-{
-    const int dyn = c->seg_v * 144;
-    psba_set_smem((const void *)k_schur_mma<NT, UNR>, dyn);
-    k_schur_mma<NT, UNR><<<c->n_seg, NT, dyn, c->stream>>>((const seg_desc *)c->seg_desc, c->cam_obs, c->cam_pt, c->sched_chunk, c->sch_beg, c->sch_end,
-                                                           c->tri_vr, c->tri_ob, c->W, c->Vinv, c->g + c->N, c->pair_part);
-}
-
 // position of entry (r,cc) of the camera block (k,l) inside the tile pool: the camera system is stored in
 // the solver's camera ordering (cam2pos); a block that lands above the diagonal is stored transposed
 __device__ __forceinline__ double *s_entry(double *Stiles, const int *__restrict__ tile_index, int nt, int pk, int pl, int r, int cc)
@@ -582,16 +446,7 @@ void psba_launch_schur(psba_ctx *c, double mu)
     // N > 1 GPUs: the local sums of ea go right behind the S tiles of the pool so that ONE all-reduce moves both
     double *ea_red = c->Stiles + (size_t)c->n_tiles_S * TS * TS;
     double *ea_out = single ? c->eab : ea_red;
-    if (c->pair_mode == 6) {
-        static const int nt = getenv("PSBA_MMA_NT") ? atoi(getenv("PSBA_MMA_NT")) : 768;
-        static const int unr = getenv("PSBA_MMA_UNR") ? atoi(getenv("PSBA_MMA_UNR")) : 8;
-        if (c->n_seg > 0)
-            PROF(c, KID_SCHUR_PAIRS) {
-                if (nt == 1024) { if (unr == 16) launch_mma<1024, 16>(c); else launch_mma<1024, 8>(c); }
-                else if (nt == 512) { if (unr == 16) launch_mma<512, 16>(c); else launch_mma<512, 8>(c); }
-                else { if (unr == 16) launch_mma<768, 16>(c); else if (unr == 4) launch_mma<768, 4>(c); else launch_mma<768, 8>(c); }
-            }
-    } else if (c->pair_mode == 5) {
+    if (c->pair_mode == 5) {
         if (c->n_seg > 0)
             PROF(c, KID_SCHUR_PAIRS) {
                 switch (c->pair_G) {

@@ -519,10 +519,10 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
     CUDA_CHECK(cudaStreamSynchronize(st));
     // pair pass: 5 (default) = segment kernel (k_schur_segs), 0 = the pair-major gather kernel of round 1
     c->pair_mode = 5;
-    if (getenv("PSBA_PAIR_MODE")) { const int pm = atoi(getenv("PSBA_PAIR_MODE")); c->pair_mode = pm == 0 ? 0 : (pm == 6 ? 6 : 5); }
+    if (getenv("PSBA_PAIR_MODE")) c->pair_mode = atoi(getenv("PSBA_PAIR_MODE")) == 0 ? 0 : 5;
     c->n_seg = 0; c->seg_desc = nullptr; c->sched_chunk = nullptr; c->sch_beg = c->sch_end = nullptr; c->tri_vr = nullptr;
     c->pchunk_pair = nullptr; c->pchunk_beg = c->pchunk_end = nullptr;
-    if (c->pair_mode >= 5) {
+    if (c->pair_mode == 5) {
         build_segments(c, tptr, cptr);
         T.lap("segments + chunks");
     } else {
