@@ -43,6 +43,9 @@ struct nd_ctx {
     int tag;
     int min_size;
     std::vector<int> order;
+    std::vector<int> front;     // front[p]: id of the leaf / separator the tile at position p belongs to (consecutive positions)
+    int n_front = 0;
+    void append(const std::vector<int> &nodes) { order.insert(order.end(), nodes.begin(), nodes.end()); front.insert(front.end(), nodes.size(), n_front++); }
 };
 
 static void nd_bfs(nd_ctx &x, int root, int tag, std::vector<int> &visit, int &nlev)
@@ -62,7 +65,7 @@ static void nd_bfs(nd_ctx &x, int root, int tag, std::vector<int> &visit, int &n
 static void nd_recurse(nd_ctx &x, std::vector<int> nodes)
 {
     std::sort(nodes.begin(), nodes.end());
-    if ((int)nodes.size() <= x.min_size) { x.order.insert(x.order.end(), nodes.begin(), nodes.end()); return; }
+    if ((int)nodes.size() <= x.min_size) { x.append(nodes); return; }
     const int tag = ++x.tag;
     for (int v : nodes) { x.mark[v] = tag; x.dist[v] = -1; }
     std::vector<int> visit;
@@ -92,7 +95,7 @@ static void nd_recurse(nd_ctx &x, std::vector<int> nodes)
         if (!grew) break;
     }
     (void)root;
-    if (nlev < 3) { x.order.insert(x.order.end(), nodes.begin(), nodes.end()); return; }
+    if (nlev < 3) { x.append(nodes); return; }
     std::vector<int> cnt(nlev, 0);
     for (int v : nodes) cnt[x.dist[v]]++;
     int best_l = 1;
@@ -111,7 +114,7 @@ static void nd_recurse(nd_ctx &x, std::vector<int> nodes)
     nd_recurse(x, A);
     nd_recurse(x, B);
     std::sort(S.begin(), S.end());
-    x.order.insert(x.order.end(), S.begin(), S.end());
+    x.append(S);
 }
 
 template <class T> static void up_vec(psba_ctx *c, T **d, const std::vector<T> &h)
@@ -133,6 +136,7 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
             if (a != b && nat[(size_t)a * nt + b]) adj[a].push_back(b);
     // ---- ordering
     std::vector<int> tpos(nt);                       // natural tile -> position
+    std::vector<int> front(nt, 0);                   // position -> front (leaf or separator of the dissection)
     {
         const char *e = getenv("PSBA_ND_MIN");
         int min_size = e ? atoi(e) : 12;
@@ -140,10 +144,11 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
         x.adj = &adj; x.mark.assign(nt, 0); x.dist.assign(nt, -1); x.tag = 0; x.min_size = std::max(1, min_size);
         std::vector<int> all(nt);
         for (int t = 0; t < nt; ++t) all[t] = t;
-        if (min_size <= 0 || min_size >= nt) x.order = all;      // natural order
+        if (min_size <= 0 || min_size >= nt) x.append(all);      // natural order
         else nd_recurse(x, all);
         if ((int)x.order.size() != nt) { fprintf(stderr, "psba_b200: internal error in the tile ordering\n"); exit(EXIT_FAILURE); }
         for (int p = 0; p < nt; ++p) tpos[x.order[p]] = p;
+        front = x.front;
     }
     c->h_cam2pos.resize(c->m);
     std::vector<int> pos2cam((size_t)nt * 8, -1);
@@ -190,7 +195,7 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
     for (auto &v : by_step) if (v.size() != 1) c->chain_schedule = false;
     // ---- task lists
     std::vector<int> critI, critK, psrc_ptr(1, 0), psrc;
-    std::vector<int> defI, defJ, def_sptr(1, 0), def_src, def_cnt, step_panels;
+    std::vector<int> defI, defJ, def_sptr(1, 0), def_src, step_panels;
     std::vector<int> bJ, b_sptr(1, 0), b_slot;
     std::vector<std::vector<int>> psrc_of(nt);
     for (int K = 0; K < nt; ++K) {
@@ -200,7 +205,51 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
         psrc_ptr.push_back((int)psrc.size());
     }
     c->step_crit_ptr.assign(1, 0); c->step_def_ptr.assign(1, 0); c->step_panel_ptr.assign(1, 0); c->step_b_ptr.assign(1, 0);
-    std::vector<int> stamp((size_t)nt * nt, -1), def_of((size_t)nt * nt, -1);
+    // ---- plan of the deferred trailing updates.  Panel P updates every tile (I,J), I >= J in rows[P].  When J runs in the step
+    // right after P the critical CTAs of panel J apply the update themselves; every other update is deferred to a step e with
+    //     step[P] < e < step[J]:   e = min(step[J] - 1, last step of P's front + 1)
+    // i.e. a tile collects the updates of a whole front (a leaf or separator of the dissection: its panels follow each other)
+    // in ONE task with several sources -- one read-modify-write of the target per front instead of one per panel, the source
+    // tiles streaming under the tensor-core products -- and tiles of the front itself are updated just in time, one step
+    // before their panel.  PSBA_DEF_MERGE=0 restores the step-by-step schedule (every update in the step after its panel).
+    struct def_item { int e; size_t key; int P; };
+    std::vector<def_item> def_plan;
+    {
+        const int mode = getenv("PSBA_DEF_MERGE") ? atoi(getenv("PSBA_DEF_MERGE")) : 2;
+        std::vector<int> front_end(nt, 0);               // last step of the front of panel P
+        {
+            int nf = 0;
+            for (int P = 0; P < nt; ++P) nf = std::max(nf, front[P] + 1);
+            std::vector<int> fe(nf, 0);
+            for (int P = 0; P < nt; ++P) fe[front[P]] = std::max(fe[front[P]], step[P]);
+            for (int P = 0; P < nt; ++P) front_end[P] = fe[front[P]];
+        }
+        for (int P = 0; P < nt; ++P)
+            for (size_t a = 0; a < rows[P].size(); ++a)
+                for (size_t b = 0; b <= a; ++b) {
+                    const int I = rows[P][a], J = rows[P][b];
+                    if (step[J] == step[P] + 1) continue;        // handled by the critical CTAs of panel J
+                    const int e = mode == 1 ? std::min(step[J] - 1, front_end[P] + 1) : step[P] + 1;
+                    def_plan.push_back({e, (size_t)I * nt + J, P});
+                }
+        const int cap = std::max(1, getenv("PSBA_DEF_CAP") ? atoi(getenv("PSBA_DEF_CAP")) : 3);
+        if (mode == 2) {
+            // as late as possible, `cap` sources per target and step: the m deferred sources of a target (ascending step) run in
+            // the steps D-m+1 .. D before its panel (D = step[J] - 1), never before their own panel is done
+            std::sort(def_plan.begin(), def_plan.end(), [&](const def_item &x, const def_item &y) {
+                return x.key != y.key ? x.key < y.key : (step[x.P] != step[y.P] ? step[x.P] < step[y.P] : x.P < y.P); });
+            for (size_t q0 = 0; q0 < def_plan.size();) {
+                size_t q1 = q0;
+                while (q1 < def_plan.size() && def_plan[q1].key == def_plan[q0].key) ++q1;
+                const int D = step[(int)(def_plan[q0].key % nt)] - 1, mm = (int)(q1 - q0);
+                for (size_t q = q0; q < q1; ++q) def_plan[q].e = std::max(step[def_plan[q].P] + 1, D - (mm - 1 - (int)(q - q0)) / cap);
+                q0 = q1;
+            }
+        }
+        std::sort(def_plan.begin(), def_plan.end(), [](const def_item &x, const def_item &y) {
+            return x.e != y.e ? x.e < y.e : (x.key != y.key ? x.key < y.key : x.P < y.P); });
+    }
+    size_t dq = 0;
     for (int s = 0; s < n_steps; ++s) {
         for (int K : by_step[s]) {
             critI.push_back(K); critK.push_back(K);
@@ -209,31 +258,12 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
         }
         c->step_crit_ptr.push_back((int)critI.size());
         c->step_panel_ptr.push_back((int)step_panels.size());
-        // deferred targets of the panels of step s-1: tiles (I,J) with J in a later step than s
-        if (s > 0) {
-            // two passes over the same loops (count, then fill) into flat arrays: no per-target allocation
-            const int t0 = (int)defI.size();
-            for (int P : by_step[s - 1])
-                for (size_t a = 0; a < rows[P].size(); ++a)
-                    for (size_t b = 0; b <= a; ++b) {
-                        const int I = rows[P][a], J = rows[P][b];
-                        if (step[J] == s) continue;              // handled by the critical CTAs of panel J
-                        const size_t key = (size_t)I * nt + J;
-                        if (stamp[key] != s) { stamp[key] = s; def_of[key] = (int)defI.size(); defI.push_back(I); defJ.push_back(J); def_cnt.push_back(0); }
-                        def_cnt[def_of[key]] += 1;
-                    }
-            const int t1 = (int)defI.size();
-            for (int t = t0; t < t1; ++t) def_sptr.push_back(def_sptr.back() + def_cnt[t]);
-            def_src.resize(def_sptr.back());
-            for (int t = t0; t < t1; ++t) def_cnt[t] = 0;
-            for (int P : by_step[s - 1])
-                for (size_t a = 0; a < rows[P].size(); ++a)
-                    for (size_t b = 0; b <= a; ++b) {
-                        const int I = rows[P][a], J = rows[P][b];
-                        if (step[J] == s) continue;
-                        const int t = def_of[(size_t)I * nt + J];
-                        def_src[def_sptr[t] + def_cnt[t]++] = P;
-                    }
+        // deferred updates that run in step s (see def_plan above): one task per target tile, sources in ascending panel order
+        while (dq < def_plan.size() && def_plan[dq].e == s) {
+            const size_t key = def_plan[dq].key;
+            defI.push_back((int)(key / nt)); defJ.push_back((int)(key % nt));
+            while (dq < def_plan.size() && def_plan[dq].e == s && def_plan[dq].key == key) def_src.push_back(def_plan[dq++].P);
+            def_sptr.push_back((int)def_src.size());
         }
         c->step_def_ptr.push_back((int)defI.size());
         // right-hand-side tasks: b_J -= sum_P L_JP y_P for the panels P of step s-1 and rows J of later steps

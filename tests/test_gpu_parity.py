@@ -373,7 +373,7 @@ def _check_try_against_oracle(prob, G):
     return O
 
 
-@pytest.mark.parametrize("mode,segv,G_", [("5", "", ""), ("5", "48", "1"), ("5", "100", "2"), ("5", "100", "8"), ("5", "1400", "32"), ("0", "", ""))])
+@pytest.mark.parametrize("mode,segv,G_", [("5", "", ""), ("5", "48", "1"), ("5", "100", "2"), ("5", "100", "8"), ("5", "1400", "32"), ("0", "", "")])
 def test_pair_pass_variants_agree_with_oracle(mode, segv, G_, monkeypatch):
     """PSBA_PAIR_MODE selects the pair pass: 5 = segment kernel (Y staged per camera-row segment; segment lengths and lane-group sizes varied here), 0 = the pair-major gather kernel.  All must give the reference's S and
     ea (compute_S.cl / compute_ea.cl) and the same LM trajectory."""
