@@ -96,6 +96,9 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+FP64_PEAK_TFLOPS = 36.74          # 63.2 FMA/clk/SM x 148 SMs x 1965 MHz x 2 (profiles/fp64_bench_r01.txt)
+
+
 def kernel_bytes(G, prob_sizes):
     """Algorithmic bytes per launch of the memory-bound kernels (DESIGN.md 'Kernels and rooflines'):
     every distinct global array a kernel must read or write, counted once."""
@@ -357,6 +360,19 @@ def main():
                 "frac": ktab[dom]["frac_hbm"], "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": ktab[dom]["alg_bytes"], "ms_per_launch": ktab[dom]["ms_avg"]}
 
+    # camera solve (factorisation graph + backward solve): FP64-bound.  Flops from the symbolic factor (stat chol_flops:
+    # potrf + trsm + trailing updates of every panel + both triangular solves); peak = the FP64 FMA rate measured with
+    # tools/microbench/fp64_bench.cu on this pool's B200 (profiles/fp64_bench_r01.txt: MEASURED_PEAKS.json has no FP64 entry)
+    roofline_fp64 = None
+    if "chol_graph" in ktab:
+        fl = G.stat("chol_flops")
+        ms_solve = ktab["chol_graph"]["ms_avg"] + ktab.get("k_tri_solve", {"ms_avg": 0.0})["ms_avg"]
+        tf = fl / (ms_solve * 1e-3) / 1e12
+        roofline_fp64 = {"bound": "fp64", "kernel": "chol_graph + k_tri_solve", "achieved": round(tf, 2), "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": round(tf / FP64_PEAK_TFLOPS, 4), "flops_per_solve": fl, "ms_per_solve": round(ms_solve, 4),
+                         "dependent_panel_steps": int(G.stat("n_steps")),
+                         "peak_source": "builder-measured DFMA rate (tools/microbench/fp64_bench.cu, profiles/fp64_bench_r01.txt)"}
+
     # ---- end to end through the C ABI with HOST buffers: upload + structure build + K iterations + download
     e2e = None
     if not args.no_e2e:
@@ -424,7 +440,7 @@ def main():
                 "dtype": "f64", "data": "synthetic", "config": config,
                 "lm_iters_per_sec": its / (ms * 1e-3), "tries": tries, "lm_iterations": its, "final_cost": final_cost,
                 "gpu_launches": launches, "setup_seconds": round(setup_s, 3), "parity_vs_1gpu": parity,
-                "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "kernels": ktab,
+                "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu, "kernels": ktab,
                 "full_solve": full, "bal_full_solves": bal}
         emit(line)
     G.close()

@@ -189,6 +189,14 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
         n_steps = std::max(n_steps, s + 1);
     }
     c->n_steps = n_steps;
+    // algorithmic flops of the factorisation from the symbolic factor (bench.py: roofline_fp64): per panel with R tile rows
+    // below the diagonal  potrf TS^3/3 + trsm R TS^3 + trailing updates R (R + 1) / 2 * 2 TS^3; forward and backward solve 4 TS^2 per tile
+    {
+        double fl = 0.0;
+        const double t3 = (double)TS * TS * TS;
+        for (int K = 0; K < nt; ++K) { const double R = (double)rows[K].size(); fl += t3 / 3.0 + R * t3 + R * (R + 1.0) * t3 + 4.0 * (R + 1.0) * TS * TS; }
+        c->chol_flops = fl;
+    }
     std::vector<std::vector<int>> by_step(n_steps);
     for (int K = 0; K < nt; ++K) by_step[step[K]].push_back(K);
     c->chain_schedule = true;

@@ -643,6 +643,7 @@ extern "C" double psba_get_stat(psba_ctx *c, const char *name)
     if (s == "n_tiles_S") return c->n_tiles_S;
     if (s == "nt") return c->nt;
     if (s == "n_steps") return c->n_steps;
+    if (s == "chol_flops") return c->chol_flops;
     if (s == "n_ptchunk") return c->n_ptchunk;
     if (s == "n_cchunk") return c->n_cchunk;
     if (s == "n_pchunk") return c->n_pchunk;

@@ -117,6 +117,7 @@ struct psba_ctx {
     //   deferred task (I,J): trailing tile touched by panels of the previous step, J in a later step
     bool chol_pdl;                             // programmatic dependent launch between the step kernels
     int n_steps; bool chain_schedule;          // chain: one panel per step (dense S)
+    double chol_flops;                         // algorithmic FP64 flops of one factorisation + solves (symbolic factor)
     std::vector<int> step_crit_ptr, step_def_ptr, step_panel_ptr, step_b_ptr;
     int *d_crit_I, *d_crit_K, *d_psrc_ptr, *d_psrc, *d_b_J, *d_b_sptr, *d_b_slot;
     int *d_def_I, *d_def_J, *d_def_sptr, *d_def_src, *d_step_panels;
