@@ -21,6 +21,7 @@
 // the panels (48 wide) are latency-, not throughput-bound.
 #include "dev_math.cuh"
 #include <algorithm>
+#include <chrono>
 
 #define LDT (TS + 1)            // padded leading dimension in shared memory
 #define TILE_SM (TS * LDT)      // doubles per shared tile
@@ -127,6 +128,14 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
 {
     const int nt = (c->m + 7) / 8;
     c->nt = nt;
+    const bool lapon = getenv("PSBA_SETUP_TIMING") != nullptr;
+    auto lap_t = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!lapon) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "psba setup:   tiles: %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - lap_t).count());
+        lap_t = now;
+    };
     // ---- tile graph in natural numbering
     std::vector<char> nat((size_t)nt * nt, 0);
     for (auto &p : pairs) { const int a = p.first / 8, b = p.second / 8; nat[(size_t)a * nt + b] = 1; nat[(size_t)b * nt + a] = 1; }
@@ -155,6 +164,7 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
     for (int j = 0; j < c->m; ++j) { c->h_cam2pos[j] = tpos[j / 8] * 8 + j % 8; pos2cam[c->h_cam2pos[j]] = j; }
     up_vec(c, &c->cam2pos, c->h_cam2pos);
     up_vec(c, &c->pos2cam, pos2cam);
+    lap("tile graph + ordering");
     // ---- pattern in permuted numbering + symbolic factorisation at tile granularity
     std::vector<char> present((size_t)nt * nt, 0);
     for (int I = 0; I < nt; ++I) present[(size_t)I * nt + I] = 1;
@@ -177,6 +187,7 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
         if (pass == 0) { c->n_tiles_S = slot; slot += (c->N + TS * TS - 1) / (TS * TS); }   // room for ea behind the S tiles: one all-reduce for both
     }
     c->n_tiles = slot;
+    lap("symbolic factor");
     // ---- steps: a panel runs one step after the last panel it depends on
     std::vector<int> step(nt, 0);
     std::vector<std::vector<int>> cols(nt);          // cols[K]: panels P < K with a factor tile (K,P), ascending
@@ -215,48 +226,56 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
     c->step_crit_ptr.assign(1, 0); c->step_def_ptr.assign(1, 0); c->step_panel_ptr.assign(1, 0); c->step_b_ptr.assign(1, 0);
     // ---- plan of the deferred trailing updates.  Panel P updates every tile (I,J), I >= J in rows[P].  When J runs in the step
     // right after P the critical CTAs of panel J apply the update themselves; every other update is deferred to a step e with
-    //     step[P] < e < step[J]:   e = min(step[J] - 1, last step of P's front + 1)
-    // i.e. a tile collects the updates of a whole front (a leaf or separator of the dissection: its panels follow each other)
-    // in ONE task with several sources -- one read-modify-write of the target per front instead of one per panel, the source
-    // tiles streaming under the tensor-core products -- and tiles of the front itself are updated just in time, one step
-    // before their panel.  PSBA_DEF_MERGE=0 restores the step-by-step schedule (every update in the step after its panel).
-    struct def_item { int e; size_t key; int P; };
-    std::vector<def_item> def_plan;
+    // step[P] < e < step[J].  Updates of one target that fall into the same step form ONE task with several sources (one
+    // read-modify-write of the target, the source tiles streaming under the tensor-core products).  Measured on the headline
+    // system (profiles/notes_r02_experiments.md): right after the source panel 1.083 ms; a whole front per task 1.32 ms (the thin
+    // upper steps wait for their 8-source tasks); as late as possible with 3 sources per target and step 1.030 ms (default).
+    // PSBA_DEF_MERGE=0 restores the step-by-step schedule, PSBA_DEF_CAP sets the sources per target and step.
+    lap("steps + sources");
+    struct def_item { int e; int key; int P; };
+    std::vector<def_item> def_plan;                  // ordered by step, target, source
     {
         const int mode = getenv("PSBA_DEF_MERGE") ? atoi(getenv("PSBA_DEF_MERGE")) : 2;
-        std::vector<int> front_end(nt, 0);               // last step of the front of panel P
-        {
-            int nf = 0;
-            for (int P = 0; P < nt; ++P) nf = std::max(nf, front[P] + 1);
-            std::vector<int> fe(nf, 0);
-            for (int P = 0; P < nt; ++P) fe[front[P]] = std::max(fe[front[P]], step[P]);
-            for (int P = 0; P < nt; ++P) front_end[P] = fe[front[P]];
-        }
+        const int cap = std::max(1, getenv("PSBA_DEF_CAP") ? atoi(getenv("PSBA_DEF_CAP")) : 3);
+        // sources of every target, grouped by target without a sort: count, prefix sum, fill (P ascending)
+        std::vector<int> kcnt((size_t)nt * nt + 1, 0);
         for (int P = 0; P < nt; ++P)
             for (size_t a = 0; a < rows[P].size(); ++a)
                 for (size_t b = 0; b <= a; ++b) {
                     const int I = rows[P][a], J = rows[P][b];
-                    if (step[J] == step[P] + 1) continue;        // handled by the critical CTAs of panel J
-                    const int e = mode == 1 ? std::min(step[J] - 1, front_end[P] + 1) : step[P] + 1;
-                    def_plan.push_back({e, (size_t)I * nt + J, P});
+                    if (step[J] != step[P] + 1) kcnt[(size_t)I * nt + J + 1]++;      // else: handled by the critical CTAs of panel J
                 }
-        const int cap = std::max(1, getenv("PSBA_DEF_CAP") ? atoi(getenv("PSBA_DEF_CAP")) : 3);
-        if (mode == 2) {
-            // as late as possible, `cap` sources per target and step: the m deferred sources of a target (ascending step) run in
-            // the steps D-m+1 .. D before its panel (D = step[J] - 1), never before their own panel is done
-            std::sort(def_plan.begin(), def_plan.end(), [&](const def_item &x, const def_item &y) {
-                return x.key != y.key ? x.key < y.key : (step[x.P] != step[y.P] ? step[x.P] < step[y.P] : x.P < y.P); });
-            for (size_t q0 = 0; q0 < def_plan.size();) {
-                size_t q1 = q0;
-                while (q1 < def_plan.size() && def_plan[q1].key == def_plan[q0].key) ++q1;
-                const int D = step[(int)(def_plan[q0].key % nt)] - 1, mm = (int)(q1 - q0);
-                for (size_t q = q0; q < q1; ++q) def_plan[q].e = std::max(step[def_plan[q].P] + 1, D - (mm - 1 - (int)(q - q0)) / cap);
-                q0 = q1;
+        for (size_t q = 0; q < (size_t)nt * nt; ++q) kcnt[q + 1] += kcnt[q];
+        std::vector<int> ksrc(kcnt.back()), kfill(kcnt.begin(), kcnt.end() - 1);
+        for (int P = 0; P < nt; ++P)
+            for (size_t a = 0; a < rows[P].size(); ++a)
+                for (size_t b = 0; b <= a; ++b) {
+                    const int I = rows[P][a], J = rows[P][b];
+                    if (step[J] != step[P] + 1) ksrc[kfill[(size_t)I * nt + J]++] = P;
+                }
+        // step of every (target, source): mode 0 right after the source panel; mode 2 (default) as late as possible, `cap`
+        // sources per target and step: the m deferred sources of a target (ascending step) run in the last ceil(m / cap)
+        // steps before its panel, never before their own panel is done
+        std::vector<int> kstep(ksrc.size());
+        std::vector<int> per_step(n_steps + 1, 0);
+        for (int key = 0; key < nt * nt; ++key) {
+            const int q0 = kcnt[key], q1 = kcnt[key + 1], mm = q1 - q0;
+            if (mm == 0) continue;
+            std::sort(ksrc.begin() + q0, ksrc.begin() + q1, [&](int x, int y) { return step[x] != step[y] ? step[x] < step[y] : x < y; });
+            const int D = step[key % nt] - 1;
+            for (int q = q0; q < q1; ++q) {
+                const int P = ksrc[q];
+                kstep[q] = mode == 2 ? std::max(step[P] + 1, D - (mm - 1 - (q - q0)) / cap) : step[P] + 1;
+                per_step[kstep[q] + 1]++;
             }
         }
-        std::sort(def_plan.begin(), def_plan.end(), [](const def_item &x, const def_item &y) {
-            return x.e != y.e ? x.e < y.e : (x.key != y.key ? x.key < y.key : x.P < y.P); });
+        // bucket by step (stable: targets ascending, sources in the order above)
+        for (int e = 0; e < n_steps; ++e) per_step[e + 1] += per_step[e];
+        def_plan.resize(ksrc.size());
+        for (int key = 0; key < nt * nt; ++key)
+            for (int q = kcnt[key]; q < kcnt[key + 1]; ++q) def_plan[per_step[kstep[q]]++] = {kstep[q], key, ksrc[q]};
     }
+    lap("deferred plan");
     size_t dq = 0;
     for (int s = 0; s < n_steps; ++s) {
         for (int K : by_step[s]) {
@@ -268,7 +287,7 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
         c->step_panel_ptr.push_back((int)step_panels.size());
         // deferred updates that run in step s (see def_plan above): one task per target tile, sources in ascending panel order
         while (dq < def_plan.size() && def_plan[dq].e == s) {
-            const size_t key = def_plan[dq].key;
+            const int key = def_plan[dq].key;
             defI.push_back((int)(key / nt)); defJ.push_back((int)(key % nt));
             while (dq < def_plan.size() && def_plan[dq].e == s && def_plan[dq].key == key) def_src.push_back(def_plan[dq++].P);
             def_sptr.push_back((int)def_src.size());
@@ -293,6 +312,7 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
         }
         c->step_b_ptr.push_back((int)bJ.size());
     }
+    lap("task lists");
     std::vector<int> cptr(1, 0), crow, cslot;
     for (int J = 0; J < nt; ++J) {
         for (int I : rows[J]) { crow.push_back(I); cslot.push_back(c->h_tile_index[(size_t)I * nt + J]); }
@@ -323,7 +343,7 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
         up_vec(c, &c->d_crit_desc, cd); up_vec(c, &c->d_crit_src, cs);
         up_vec(c, &c->d_def_desc, dd); up_vec(c, &c->d_def_srcs, dsrc);
     }
-    {
+    if (c->chol_flow) {
         // ---- dataflow schedule (k_panel_flow): ONE launch, tasks in step order; a task waits on per-tile write counters
         //   tver[slot] = completed writes of the tile (its deferred updates in step order, then the factor tile itself)
         //   bver[J]    = completed right-hand-side updates of panel J
@@ -368,7 +388,9 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
     c->contrib = (double *)psba_dev_alloc(c, (size_t)c->n_tiles * TS * sizeof(double), true);
     c->Linv = (double *)psba_dev_alloc(c, (size_t)nt * TS * TS * sizeof(double), true);
     c->Ldiag = (double *)psba_dev_alloc(c, (size_t)nt * TS * TS * sizeof(double), true);
+    lap("descriptors + uploads");
     CUDA_CHECK(cudaStreamSynchronize(c->stream));            // the host vectors above go out of scope
+    lap("sync");
     c->chol_graph_ok = false; c->bw_graph_ok = false;
     if (getenv("PSBA_SETUP_TIMING"))
         fprintf(stderr, "psba setup: camera system %d tiles/edge, %d factor tiles, %d steps, %zu critical + %zu deferred + %zu rhs tasks\n",
