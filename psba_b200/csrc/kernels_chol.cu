@@ -947,21 +947,29 @@ __global__ void __launch_bounds__(PANEL_NT) k_panel_step(int ncrit, const int4 *
             for (int c = 0; c < TS; ++c) ywork[K * TS + c] = row[c];
         }
     }
+    // the rows leave through shared memory so that the stores are coalesced (a thread that writes its own 384-byte row issues
+    // 24 stores that each touch 32 different lines across the warp)
+    double *stg = smem + TILE_SM;                              // the sweep's publication buffers live in the first tile
     if (diagcta) {
         if (tid < TS) {
-            double2 *dst = reinterpret_cast<double2 *>(Ldiag + (size_t)K * TS * TS + tid * TS);
 #pragma unroll
-            for (int c = 0; c < TS; c += 2) dst[c / 2] = make_double2(c <= tid ? row[c] : 0.0, c + 1 <= tid ? row[c + 1] : 0.0);
+            for (int c = 0; c < TS; ++c) stg[tid * LDT + c] = row[c];
         }
+        __syncthreads();
+        tile_stg<PANEL_NT>(Ldiag + (size_t)K * TS * TS, stg, true);
         PANEL_STAMP(5); PANEL_WALL(7);
         return;
     }
-    __syncthreads();
     if (tid >= TS && tid < 2 * TS) {
-        double2 *dst = reinterpret_cast<double2 *>(tik + (tid - TS) * TS);
+#pragma unroll
+        for (int c = 0; c < TS; ++c) stg[(tid - TS) * LDT + c] = row[c];
+    }
+    __syncthreads();
+    tile_stg<PANEL_NT>(tik, stg);
+    if (tid >= TS && tid < 2 * TS) {
         double s = 0.0;
 #pragma unroll
-        for (int c = 0; c < TS; c += 2) { dst[c / 2] = make_double2(row[c], row[c + 1]); s += row[c] * ysh[c] + row[c + 1] * ysh[c + 1]; }
+        for (int c = 0; c < TS; c += 2) s += row[c] * ysh[c] + row[c + 1] * ysh[c + 1];
         contrib[(size_t)slot_ik * TS + (tid - TS)] = s;
     }
     FLOW_DONE();
