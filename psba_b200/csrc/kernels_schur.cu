@@ -375,6 +375,256 @@ static void launch_segs(psba_ctx *c)
                                                                    c->sch_end, c->tri_vr, c->tri_ob, c->W, c->Vinv, c->g + c->N, c->pair_part);
 }
 
+
+// ---- Ring kernel --------------------------------------------------------------------------------------
+// Same segments, same chunks and the same partial slots as the segment kernel; what changes is how phase 2 gets its W_il
+// blocks.  The off-diagonal triples of the segment are laid out as ROWS of 32 lane slots (structure.cu: k_ring_plan /
+// k_ring_rows), the rows of a warp contiguous.  A warp copies the 32 blocks of a row COOPERATIVELY (nine consecutive lanes
+// read the 144 bytes of one block: whole lines instead of one 32-byte sector per lane -- the segment kernel is bound by
+// the wavefronts of its divergent loads in the L1 data pipe, profiles/ncu_full_r02.md) with cp.async into its own ring of
+// `STAGES` row buffers, `STAGES` rows ahead of the row it multiplies; no CTA-wide barrier after phase 1.  Sums: the G
+// lanes of a chunk by recursive halving (36 -> 18 -> 9 values) and a butterfly of the last nine: fixed order.
+// the warp copies the blocks W[b] of its 32 lanes (b < 0: no block) into stage[lane * 18 ...]
+__device__ __forceinline__ void ring_issue(double *stage, const double *__restrict__ W, int b, int lane)
+{
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        const int p = q * 32 + lane, sl = p / 9, part = p - sl * 9;
+        const int bs = __shfl_sync(0xffffffffu, b, sl);
+        if (bs >= 0) cp_async16(stage + p * 2, W + (size_t)bs * 18 + part * 2);
+    }
+}
+// record of one row: 32 lane slots {observation of camera l, rank of the visit} + {task word, schedule position}
+__device__ __forceinline__ void ring_issue_rec(int2 *slot, const int2 *__restrict__ rows, const int2 *__restrict__ info, int row, int lane)
+{
+    cp_async8(slot + lane, rows + (size_t)row * 32 + lane);
+    if (lane == 0) cp_async8(slot + 32, info + row);
+}
+
+template <int NT, int STAGES, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restrict__ segs, const int *__restrict__ cam_obs,
+                                                          const int *__restrict__ cam_pt, const int *__restrict__ wrow_ptr,
+                                                          const int2 *__restrict__ rows, const int2 *__restrict__ info,
+                                                          const int *__restrict__ sched, const double *__restrict__ W,
+                                                          const double *__restrict__ Vinv, const double *__restrict__ gb,
+                                                          double *__restrict__ part, int seg_v)
+{
+    constexpr int NW = NT / 32, RS = 2 * STAGES + 1;
+    extern __shared__ __align__(16) double sm[];   // [seg_v][18] Y tile | [NW][STAGES][32][18] copy rings | [NW][RS][33] row records
+    __shared__ double red[NW][32];
+    const seg_desc sd = segs[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int nv = sd.v1 - sd.v0;
+    double *Ysm = sm;
+    double *ring = sm + (size_t)seg_v * 18 + (size_t)wrp * STAGES * 576;
+    int2 *recs = reinterpret_cast<int2 *>(sm + (size_t)seg_v * 18 + (size_t)NW * STAGES * 576) + (size_t)wrp * RS * 33;
+    const int r0 = __ldg(wrow_ptr + (size_t)blockIdx.x * NW + wrp), r1 = __ldg(wrow_ptr + (size_t)blockIdx.x * NW + wrp + 1);
+    // records of the first 2 STAGES rows of this warp: they land under phase 1
+#pragma unroll
+    for (int s = 0; s < 2 * STAGES; ++s)
+        if (r0 + s < r1) ring_issue_rec(recs + ((r0 + s) % RS) * 33, rows, info, r0 + s, lane);
+    cp_async_commit();
+    // ---- phase 1: Y tile, diagonal block and ea of the segment.  A warp owns the visit rows wrp, wrp + NW, ... (32
+    // consecutive visits each).  W_ik goes straight to its place in the Y tile, Vinv_i and gb_i into the (still idle) copy
+    // ring of the warp, all by cooperative cp.async; then lane = visit: Y_ik = W_ik Vinv_i overwrites W_ik in place
+    // (compute_Yblks.cl:26-37), the lower triangle of Y_ik W_ik^T and Y_ik gb_i are summed per lane in ascending visit order.
+    double acc[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) acc[q] = 0.0;
+    constexpr int RB = STAGES * 2;                                  // visit rows per batch: 2 304 B of Vinv | gb each
+    const int nvr = (nv + 31) >> 5;
+#pragma unroll 1
+    for (int vb = wrp; vb < nvr; vb += NW * RB) {
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            const int r = (vb + j * NW) * 32 + lane;
+            int q = -1, i = 0;
+            if (r < nv) { q = __ldg(cam_obs + sd.v0 + r); i = __ldg(cam_pt + sd.v0 + r); }
+            double *dstW = Ysm + (size_t)(vb + j * NW) * 32 * 18, *stg = ring + j * 288;
+            ring_issue(dstW, W, q, lane);
+#pragma unroll
+            for (int qq = 0; qq < 3; ++qq) {
+                const int p = qq * 32 + lane, sl = p / 3, part = p - sl * 3;
+                const int qs = __shfl_sync(0xffffffffu, q, sl), is = __shfl_sync(0xffffffffu, i, sl);
+                if (qs >= 0) {
+                    cp_async16(stg + p * 2, Vinv + (size_t)is * 6 + part * 2);
+                    cp_async8(stg + 192 + p, gb + (size_t)is * 3 + part);
+                }
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            const int r = (vb + j * NW) * 32 + lane;
+            if (r < nv) {
+                double w[18];
+                double2 *yd = reinterpret_cast<double2 *>(Ysm + (size_t)r * 18);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { const double2 v = yd[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+                const double *stg = ring + j * 288;
+                const double2 *vp = reinterpret_cast<const double2 *>(stg + lane * 6);
+                const double2 v0 = vp[0], v1 = vp[1], v2 = vp[2];
+                const double i00 = v0.x, i10 = v0.y, i20 = v1.x, i11 = v1.y, i21 = v2.x, i22 = v2.y;
+                const double g0 = stg[192 + lane * 3], g1 = stg[192 + lane * 3 + 1], g2 = stg[192 + lane * 3 + 2];
+#pragma unroll
+                for (int rp = 0; rp < 3; ++rp) {                     // two rows of Y at a time: three 16-byte stores
+                    double y[6];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const double w0 = w[(rp * 2 + h) * 3], w1 = w[(rp * 2 + h) * 3 + 1], w2 = w[(rp * 2 + h) * 3 + 2];
+                        y[h * 3] = w0 * i00 + w1 * i10 + w2 * i20;
+                        y[h * 3 + 1] = w0 * i10 + w1 * i11 + w2 * i21;
+                        y[h * 3 + 2] = w0 * i20 + w1 * i21 + w2 * i22;
+                    }
+                    yd[rp * 3] = make_double2(y[0], y[1]); yd[rp * 3 + 1] = make_double2(y[2], y[3]); yd[rp * 3 + 2] = make_double2(y[4], y[5]);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int rr = rp * 2 + h;
+#pragma unroll
+                        for (int cc = 0; cc <= rr; ++cc) {
+                            double &a = acc[rr * (rr + 1) / 2 + cc];
+                            a = fma(y[h * 3], w[cc * 3], a); a = fma(y[h * 3 + 1], w[cc * 3 + 1], a); a = fma(y[h * 3 + 2], w[cc * 3 + 2], a);
+                        }
+                        double &e = acc[21 + rr];
+                        e = fma(y[h * 3], g0, e); e = fma(y[h * 3 + 1], g1, e); e = fma(y[h * 3 + 2], g2, e);
+                    }
+                }
+            }
+        }
+        __syncwarp();                                               // the staging area is reused by the next batch / by phase 2
+    }
+    {
+        const double tot = warp_reduce_scatter32(acc);
+        red[wrp][lane] = tot;
+    }
+    // ---- the first rows of phase 2 start their way before the barrier: group j carries the blocks of row j + STAGES and the
+    // record of row j + 2 STAGES
+    cp_async_wait<0>();
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+        int b = -1;
+        if (r0 + s < r1) b = recs[((r0 + s) % RS) * 33 + lane].x;
+        ring_issue(ring + s * 576, W, b, lane);
+        cp_async_commit();
+    }
+    __syncthreads();                                                // Y tile complete, warp sums published
+    if (tid < 27) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < NW; ++w8) sum += red[w8][tid];
+        double *out = part + (size_t)sd.diag_chunk * 42;
+        if (tid < 21) {
+            int rr = 0, base = 0;
+            while (base + rr + 1 <= tid) { base += rr + 1; ++rr; }
+            const int cc = tid - base;
+            out[rr * 6 + cc] = sum;
+            out[cc * 6 + rr] = sum;
+        } else out[36 + (tid - 21)] = sum;
+    }
+    // ---- phase 2: the rows of this warp
+    double a36[36];
+#pragma unroll
+    for (int q = 0; q < 36; ++q) a36[q] = 0.0;
+    int st = 0, sl_cur = r0 % RS, sl_far = (r0 + STAGES) % RS, sl_new = (r0 + 2 * STAGES) % RS;
+#pragma unroll 1
+    for (int row = r0; row < r1; ++row) {
+        cp_async_wait<STAGES - 1>();
+        __syncwarp();
+        const int2 cur = recs[sl_cur * 33 + lane], ci = recs[sl_cur * 33 + 32];
+        const int b_far = row + STAGES < r1 ? recs[sl_far * 33 + lane].x : -1;
+        double *stage = ring + st * 576;
+        if (cur.x >= 0) {
+            double wb[18];
+            const double2 *wp = reinterpret_cast<const double2 *>(stage + lane * 18);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) { const double2 v = wp[j]; wb[2 * j] = v.x; wb[2 * j + 1] = v.y; }
+            const double2 *yp = reinterpret_cast<const double2 *>(Ysm + (size_t)cur.y * 18);
+#pragma unroll
+            for (int rp = 0; rp < 3; ++rp) {
+                const double2 p0 = yp[rp * 3], p1 = yp[rp * 3 + 1], p2 = yp[rp * 3 + 2];
+                const double ya[6] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y};
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int cc = 0; cc < 6; ++cc) {
+                        double &a = a36[(rp * 2 + h) * 6 + cc];
+                        a = fma(ya[h * 3], wb[cc * 3], a); a = fma(ya[h * 3 + 1], wb[cc * 3 + 1], a); a = fma(ya[h * 3 + 2], wb[cc * 3 + 2], a);
+                    }
+            }
+        }
+        __syncwarp();                                               // every lane has read its block: the stage can be refilled
+        ring_issue(stage, W, b_far, lane);
+        if (row + 2 * STAGES < r1) ring_issue_rec(recs + sl_new * 33, rows, info, row + 2 * STAGES, lane);
+        cp_async_commit();
+        st = st + 1 == STAGES ? 0 : st + 1;
+        sl_cur = sl_cur + 1 == RS ? 0 : sl_cur + 1; sl_far = sl_far + 1 == RS ? 0 : sl_far + 1; sl_new = sl_new + 1 == RS ? 0 : sl_new + 1;
+        if (ci.x & 256) {                                           // last row of a task: sum over the G lanes of every chunk, partials out
+            const int lg = ci.x & 255, G = 1 << lg, gl = lane & (G - 1), nch = ci.x >> 16;
+            int start = 0;
+            if (G >= 2) {
+                const int h = G >> 1;
+                const bool up = (gl & h) != 0;
+                if (up) start += 18;
+#pragma unroll
+                for (int j = 0; j < 18; ++j) {
+                    const double send = up ? a36[j] : a36[j + 18], keep = up ? a36[j + 18] : a36[j];
+                    a36[j] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+                }
+            }
+            if (G >= 4) {
+                const int h = G >> 2;
+                const bool up = (gl & h) != 0;
+                if (up) start += 9;
+#pragma unroll
+                for (int j = 0; j < 9; ++j) {
+                    const double send = up ? a36[j] : a36[j + 9], keep = up ? a36[j + 9] : a36[j];
+                    a36[j] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+                }
+            }
+            for (int h = G >> 3; h >= 1; h >>= 1) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) a36[j] += __shfl_xor_sync(0xffffffffu, a36[j], h);
+            }
+            const int cnt = G >= 4 ? 9 : (G == 2 ? 18 : 36);
+            const int q = lane >> lg;
+            const bool writer = q < nch && (G < 8 || (gl & ((G >> 2) - 1)) == 0);
+            if (writer) {
+                const int c = __ldg(sched + ci.y + q);
+                double *out = part + (size_t)c * 42 + start;
+#pragma unroll
+                for (int j = 0; j < 36; ++j)
+                    if (j < cnt) out[j] = a36[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 36; ++j) a36[j] = 0.0;
+        }
+    }
+    cp_async_wait<0>();
+}
+
+template <int NT, int STAGES, int MINB>
+static void launch_ring_shape(psba_ctx *c)
+{
+    const int dyn = (int)psba_ring_smem(c->ring_cfg, c->seg_v);
+    psba_set_smem((const void *)k_schur_ring<NT, STAGES, MINB>, dyn);
+    k_schur_ring<NT, STAGES, MINB><<<c->n_seg, NT, dyn, c->stream>>>((const seg_desc *)c->seg_desc, c->cam_obs, c->cam_pt, c->ring_wrow_ptr, c->ring_rows,
+                                                                    c->ring_info, c->sched_chunk, c->W, c->Vinv, c->g + c->N, c->pair_part, c->seg_v);
+}
+static void launch_ring(psba_ctx *c)
+{
+    switch (c->ring_cfg) {
+    case 0: launch_ring_shape<384, 2, 1>(c); break;
+    case 1: launch_ring_shape<256, 2, 1>(c); break;
+    case 2: launch_ring_shape<256, 3, 1>(c); break;
+    case 3: launch_ring_shape<128, 2, 2>(c); break;
+    case 4: launch_ring_shape<128, 3, 2>(c); break;
+    default: launch_ring_shape<192, 2, 1>(c); break;
+    }
+}
+
 // position of entry (r,cc) of the camera block (k,l) inside the tile pool: the camera system is stored in
 // the solver's camera ordering (cam2pos); a block that lands above the diagonal is stored transposed
 __device__ __forceinline__ double *s_entry(double *Stiles, const int *__restrict__ tile_index, int nt, int pk, int pl, int r, int cc)
@@ -446,7 +696,9 @@ void psba_launch_schur(psba_ctx *c, double mu)
     // N > 1 GPUs: the local sums of ea go right behind the S tiles of the pool so that ONE all-reduce moves both
     double *ea_red = c->Stiles + (size_t)c->n_tiles_S * TS * TS;
     double *ea_out = single ? c->eab : ea_red;
-    if (c->pair_mode == 5) {
+    if (c->pair_mode == 6) {
+        if (c->n_seg > 0) PROF(c, KID_SCHUR_PAIRS) launch_ring(c);
+    } else if (c->pair_mode == 5) {
         if (c->n_seg > 0)
             PROF(c, KID_SCHUR_PAIRS) {
                 switch (c->pair_G) {

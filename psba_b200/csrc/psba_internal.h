@@ -82,7 +82,7 @@ struct psba_ctx {
     int n_pair; int *pair_k, *pair_l;          // pair blocks present GLOBALLY (all ranks agree)
     int *pair_chunk_ptr;                        // n_pair+1
     int pair_G;                                 // lanes per chunk in the pair pass (1..32)
-    int pair_mode;                              // 5: segment kernel (default), 0: pair-major gather kernel of round 1
+    int pair_mode;                              // 6: ring kernel, 5: segment kernel, 0: pair-major gather kernel of round 1
     int n_pchunk; int *pchunk_pair; long long *pchunk_beg, *pchunk_end;      // mode 0: fixed-size chunks of the pair runs
     // ---- segment kernel (k_schur_segs): CTA = <= seg_v consecutive visits of one camera row; chunk = the triples of one
     // camera pair inside one segment (pair-major ids: the partial slots k_S_finalize sums per pair, in segment order)
@@ -91,6 +91,13 @@ struct psba_ctx {
     int *sched_chunk;               // off-diagonal chunk ids segment by segment, largest first
     int *sch_beg, *sch_end;         // triple range of every chunk
     unsigned short *tri_vr;         // per triple: rank of the visit (observation of camera k) inside its segment
+    // ---- ring kernel (k_schur_ring, pair_mode 6): the off-diagonal triples of a segment as ROWS of 32 lane slots, the rows of
+    // one warp contiguous; a task = consecutive rows that sum the chunks of 32/G pairs with G lanes each
+    int ring_nw, ring_stages, ring_rt, ring_cfg;   // warps per CTA, stages per warp, target rows per task, launch shape
+    long long ring_n_rows;
+    int *ring_wrow_ptr;             // n_seg * ring_nw + 1: first row of (segment, warp)
+    int2 *ring_rows;                // n_rows * 32: {observation of camera l (-1: empty slot), rank of the visit in the segment}
+    int2 *ring_info;                // n_rows: {log2 G | last row of its task << 8 | chunks of the task << 16, position of the task's first chunk in sched_chunk}
     // ---- linearisation products
     double *W, *V, *Vinv, *U, *g, *UVdiag_scr;
     double coeff_uvw, coeff_g;
@@ -175,6 +182,7 @@ void psba_launch_Jdot(psba_ctx *c, const double *x, const double *y, double *Jx_
 // ---- kernels_schur.cu
 double psba_launch_vinv(psba_ctx *c, double mu);
 void psba_launch_schur(psba_ctx *c, double mu);
+size_t psba_ring_smem(int cfg, int seg_v);   // dynamic shared memory of k_schur_ring (structure.cu)
 void psba_launch_Y_materialize(psba_ctx *c, double *Y);
 // ---- kernels_solve.cu
 void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int,int>> &camera_pairs);

@@ -222,6 +222,67 @@ __global__ void k_fill_seg_desc(int n_seg, seg_desc_h *__restrict__ d, const int
     d[s].diag_chunk = seg_diag[s]; d[s].sched0 = sptr[s]; d[s].sched1 = sptr[s + 1];
 }
 
+
+// ---- ring kernel of the pair pass (kernels_schur.cu: k_schur_ring) -----------------------------------------
+// The off-diagonal chunks of a segment (sorted largest first) become TASKS: the next 32/G chunks share a warp, G lanes
+// each (G = the power of two that brings the largest chunk of the task down to ~rt rows), one ROW = 32 lane slots = one
+// triple per lane.  Tasks are dealt to the nw warps of the CTA, largest first to the least loaded warp; the rows of a warp
+// are contiguous so that the warp streams them through its copy ring without looking at task boundaries.
+__device__ __forceinline__ int ring_lanes(int len, int rt)
+{
+    const int want = (len + rt - 1) / rt;
+    int G = 1;
+    while (G < 32 && G < want) G *= 2;
+    return G;
+}
+
+// thread per segment.  fill = 0: rows of every (segment, warp) -> wrows;  fill = 1: task records at the position of the
+// task's first chunk in the schedule: {first row, rows, chunks, log2 G} (rows = 0 at the other chunks of a task)
+__global__ void k_ring_plan(int n_seg, const seg_desc_h *__restrict__ segs, const int *__restrict__ sched, const int *__restrict__ ch_beg,
+                            const int *__restrict__ ch_end, int nw, int rt, int fill, int *__restrict__ wrows,
+                            const int *__restrict__ wrow_ptr, int4 *__restrict__ task)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    int load[16];
+    for (int w = 0; w < 16; ++w) load[w] = 0;
+    const int j0 = segs[s].sched0, j1 = segs[s].sched1;
+    for (int j = j0; j < j1;) {
+        const int c = sched[j], len = ch_end[c] - ch_beg[c];
+        const int G = ring_lanes(len, rt), nch = min(32 / G, j1 - j), nrows = (len + G - 1) / G;
+        int w = 0;
+        for (int q = 1; q < nw; ++q) if (load[q] < load[w]) w = q;
+        if (fill) {
+            int lg = 0;
+            while ((1 << lg) < G) ++lg;
+            task[j] = make_int4(wrow_ptr[(size_t)s * nw + w] + load[w], nrows, nch, lg);
+            for (int q = 1; q < nch; ++q) task[j + q] = make_int4(0, 0, 0, 0);
+        }
+        load[w] += nrows;
+        j += nch;
+    }
+    if (!fill) for (int w = 0; w < nw; ++w) wrows[(size_t)s * nw + w] = load[w];
+}
+
+// warp per schedule position that starts a task: the rows of the task
+__global__ void k_ring_rows(int n_sched, const int4 *__restrict__ task, const int *__restrict__ sched, const int *__restrict__ ch_beg,
+                            const int *__restrict__ ch_end, const unsigned short *__restrict__ tri_vr, const int *__restrict__ tri_ob,
+                            int2 *__restrict__ rows, int2 *__restrict__ info)
+{
+    const int j = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (j >= n_sched) return;
+    const int4 tk = task[j];
+    if (tk.y == 0) return;
+    const int G = 1 << tk.w, q = lane >> tk.w, gl = lane & (G - 1);
+    int beg = 0, end = 0;
+    if (q < tk.z) { const int c = sched[j + q]; beg = ch_beg[c]; end = ch_end[c]; }
+    for (int it = 0; it < tk.y; ++it) {
+        const int t = beg + gl + it * G;
+        rows[((size_t)tk.x + it) * 32 + lane] = t < end ? make_int2(tri_ob[t], (int)tri_vr[t]) : make_int2(-1, 0);
+        if (lane == 0) info[(size_t)tk.x + it] = make_int2(tk.w | ((it == tk.y - 1) ? 256 : 0) | (tk.z << 16), j);
+    }
+}
+
 // ---- helpers ---------------------------------------------------------------------------------------
 template <class T> static T *salloc(psba_ctx *c, size_t n)
 {
@@ -285,6 +346,7 @@ static void sorted_triples(psba_ctx *c, int np, int p0, int o0, const int *gptr,
 }
 
 
+static int ring_seg_v(const psba_ctx *c);
 // tables of the segment kernel: segments of every camera row, (pair, segment) chunks, schedule
 static void build_segments(psba_ctx *c, const long long *tptr, const std::vector<int> &cptr)
 {
@@ -293,6 +355,7 @@ static void build_segments(psba_ctx *c, const long long *tptr, const std::vector
     c->n_seg = 0; c->n_pchunk = 0;
     c->seg_cfg = 2;
     c->seg_v = 1280;                                         // Y tile: 144 B per visit, one resident CTA per SM (kernels_schur.cu: launch shape)
+    if (c->pair_mode == 6) c->seg_v = ring_seg_v(c);
     // small problems: enough segments to fill the machine four times over (Venice-52: 312 segments of 1 280 visits were three
     // uneven waves of one CTA per SM)
     if ((long long)o < (long long)c->seg_v * 4 * c->n_sm) c->seg_v = std::max(128, std::min(c->seg_v, cdiv(o, 4 * c->n_sm)));
@@ -367,6 +430,71 @@ static void build_segments(psba_ctx *c, const long long *tptr, const std::vector
     for (void *p : {(void *)cam_pos, (void *)cam_ptr, (void *)d_seglen, (void *)d_rsp, (void *)tri_seg, (void *)head, (void *)cid, (void *)ch_seg,
                     (void *)ch_pair, (void *)ch_diag, (void *)key0, (void *)key1, (void *)val0, (void *)seg_diag, (void *)sptr})
         psba_dev_free(c, p);
+}
+
+
+// launch shapes of the ring kernel: {threads, stages per warp, CTAs per SM}; the Y tile takes what the copy rings and the row
+// records leave of the SM's shared memory
+static const int RING_SHAPES[6][3] = {{384, 2, 1}, {256, 2, 1}, {256, 3, 1}, {128, 2, 2}, {128, 3, 2}, {192, 2, 1}};
+static size_t ring_fixed_smem(int cfg)
+{
+    const int nw = RING_SHAPES[cfg][0] / 32, st = RING_SHAPES[cfg][1];
+    return (size_t)nw * st * 4608 + (size_t)nw * (2 * st + 1) * 264;
+}
+size_t psba_ring_smem(int cfg, int seg_v) { return (size_t)seg_v * 144 + ring_fixed_smem(cfg); }
+
+static void ring_config(psba_ctx *c)
+{
+    c->ring_cfg = 3;                                         // measured on the headline workload: 2 x 128 threads per SM 0.73 ms, 256 x 1 0.75-0.77, 384 x 1 0.87
+    if (getenv("PSBA_RING_CFG")) c->ring_cfg = std::max(0, std::min(5, atoi(getenv("PSBA_RING_CFG"))));
+    c->ring_nw = RING_SHAPES[c->ring_cfg][0] / 32; c->ring_stages = RING_SHAPES[c->ring_cfg][1];
+    c->ring_rt = 5;
+    if (getenv("PSBA_RING_RT")) c->ring_rt = std::max(1, std::min(64, atoi(getenv("PSBA_RING_RT"))));
+}
+// visits per segment: the Y tile beside the copy rings (227 KB per CTA, 228 KB per SM less 1 KB per resident CTA; 4 KB kept
+// for the static arrays)
+static int ring_seg_v(const psba_ctx *c)
+{
+    const int per_sm = RING_SHAPES[c->ring_cfg][2];
+    const long long cta = per_sm == 1 ? 227ll * 1024 : (228ll * 1024) / per_sm - 1024;
+    const long long avail = cta - 4096 - (long long)ring_fixed_smem(c->ring_cfg);
+    return (int)std::min<long long>(SEG_V_MAX, avail / 144);
+}
+
+static void build_ring_tables(psba_ctx *c)
+{
+    cudaStream_t st = c->stream;
+    const int nw = c->ring_nw, n_sched = c->n_pchunk;
+    c->ring_n_rows = 0;
+    c->ring_wrow_ptr = salloc<int>(c, (size_t)c->n_seg * nw + 1);
+    if (c->n_seg == 0 || c->ntri == 0) {
+        CUDA_CHECK(cudaMemsetAsync(c->ring_wrow_ptr, 0, ((size_t)c->n_seg * nw + 1) * 4, st));
+        c->ring_rows = salloc<int2>(c, 32); c->ring_info = salloc<int2>(c, 1);
+        return;
+    }
+    const size_t nwr = (size_t)c->n_seg * nw + 1;
+    int *wrows = salloc<int>(c, nwr);
+    CUDA_CHECK(cudaMemsetAsync(wrows, 0, nwr * 4, st));
+    int4 *task = salloc<int4>(c, (size_t)n_sched);
+    CUDA_CHECK(cudaMemsetAsync(task, 0, (size_t)n_sched * sizeof(int4), st));     // positions of the diagonal chunks start no task
+    k_ring_plan<<<cdiv(c->n_seg, 128), 128, 0, st>>>(c->n_seg, (const seg_desc_h *)c->seg_desc, c->sched_chunk, c->sch_beg, c->sch_end, nw, c->ring_rt, 0,
+                                                     wrows, nullptr, nullptr);
+    size_t tb = 0;
+    CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tb, wrows, c->ring_wrow_ptr, (int)nwr, st));
+    void *tmp = psba_dev_alloc(c, std::max<size_t>(tb, 16), false);
+    CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tb, wrows, c->ring_wrow_ptr, (int)nwr, st));
+    int n_rows = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&n_rows, c->ring_wrow_ptr + (nwr - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    psba_dev_free(c, tmp);
+    c->ring_n_rows = n_rows;
+    c->ring_rows = salloc<int2>(c, (size_t)n_rows * 32 + 32); c->ring_info = salloc<int2>(c, (size_t)n_rows + 1);
+    k_ring_plan<<<cdiv(c->n_seg, 128), 128, 0, st>>>(c->n_seg, (const seg_desc_h *)c->seg_desc, c->sched_chunk, c->sch_beg, c->sch_end, nw, c->ring_rt, 1,
+                                                     nullptr, c->ring_wrow_ptr, task);
+    k_ring_rows<<<cdiv((long long)n_sched * 32, 256), 256, 0, st>>>(n_sched, task, c->sched_chunk, c->sch_beg, c->sch_end, c->tri_vr, c->tri_ob,
+                                                                   c->ring_rows, c->ring_info);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    psba_dev_free(c, wrows); psba_dev_free(c, task);
 }
 
 // ---- the build ---------------------------------------------------------------------------------------
@@ -518,13 +646,15 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
     CUDA_CHECK(cudaMemcpyAsync(&h_nonempty, nonempty, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     // pair pass: 5 (default) = segment kernel (k_schur_segs), 0 = the pair-major gather kernel of round 1
-    c->pair_mode = 5;
-    if (getenv("PSBA_PAIR_MODE")) c->pair_mode = atoi(getenv("PSBA_PAIR_MODE")) == 0 ? 0 : 5;
+    c->pair_mode = 6;
+    if (getenv("PSBA_PAIR_MODE")) { const int pm = atoi(getenv("PSBA_PAIR_MODE")); c->pair_mode = pm == 0 ? 0 : (pm == 5 ? 5 : 6); }
+    if (c->pair_mode == 6) ring_config(c);
     c->n_seg = 0; c->seg_desc = nullptr; c->sched_chunk = nullptr; c->sch_beg = c->sch_end = nullptr; c->tri_vr = nullptr;
     c->pchunk_pair = nullptr; c->pchunk_beg = c->pchunk_end = nullptr;
-    if (c->pair_mode == 5) {
+    if (c->pair_mode == 5 || c->pair_mode == 6) {
         build_segments(c, tptr, cptr);
         T.lap("segments + chunks");
+        if (c->pair_mode == 6) { build_ring_tables(c); T.lap("ring rows"); }
     } else {
         // every group of G lanes owns one chunk of <= G*PAIR_TPL triples of one camera pair; G follows the mean run
         // length so that a lane streams ~PAIR_TPL triples before the (shuffle) reduction
