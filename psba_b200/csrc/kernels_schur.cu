@@ -384,7 +384,9 @@ static void launch_segs(psba_ctx *c)
 // the wavefronts of its divergent loads in the L1 data pipe, profiles/ncu_full_r02.md) with cp.async into its own ring of
 // `STAGES` row buffers, `STAGES` rows ahead of the row it multiplies; no CTA-wide barrier after phase 1.  Sums: the G
 // lanes of a chunk by recursive halving (36 -> 18 -> 9 values) and a butterfly of the last nine: fixed order.
-// the warp copies the blocks W[b] of its 32 lanes (b < 0: no block) into stage[lane * 18 ...]
+// the warp copies the blocks W[b] of its 32 lanes (b < 0: no block) into stage[lane * 18 ...]: nine consecutive lanes per
+// block.  Measured and not kept: three whole blocks per instruction (27 lanes, no block straddles two instructions) 0.728
+// against 0.731 ms; cp.async.ca (through L1) instead of .cg 0.99 ms
 __device__ __forceinline__ void ring_issue(double *stage, const double *__restrict__ W, int b, int lane)
 {
 #pragma unroll
@@ -407,9 +409,11 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
                                                           const int2 *__restrict__ rows, const int2 *__restrict__ info,
                                                           const int *__restrict__ sched, const double *__restrict__ W,
                                                           const double *__restrict__ Vinv, const double *__restrict__ gb,
-                                                          double *__restrict__ part, int seg_v)
+                                                          double *__restrict__ part, int seg_v, long long *__restrict__ dbg)
 {
     constexpr int NW = NT / 32, RS = 2 * STAGES + 1;
+    long long stamp[6];
+    stamp[0] = clock64(); stamp[1] = stamp[0];
     extern __shared__ __align__(16) double sm[];   // [seg_v][18] Y tile | [NW][STAGES][32][18] copy rings | [NW][RS][33] row records
     __shared__ double red[NW][32];
     const seg_desc sd = segs[blockIdx.x];
@@ -455,6 +459,7 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
         cp_async_commit();
         cp_async_wait<0>();
         __syncwarp();
+        stamp[1] = clock64();
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
             const int r = (vb + j * NW) * 32 + lane;
@@ -499,6 +504,7 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
         const double tot = warp_reduce_scatter32(acc);
         red[wrp][lane] = tot;
     }
+    stamp[2] = clock64();
     // ---- the first rows of phase 2 start their way before the barrier: group j carries the blocks of row j + STAGES and the
     // record of row j + 2 STAGES
     cp_async_wait<0>();
@@ -511,6 +517,7 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
         cp_async_commit();
     }
     __syncthreads();                                                // Y tile complete, warp sums published
+    stamp[3] = clock64();
     if (tid < 27) {
         double sum = 0.0;
 #pragma unroll
@@ -603,6 +610,16 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
         }
     }
     cp_async_wait<0>();
+    if (dbg && lane == 0) {
+        stamp[4] = clock64();
+        long long *d = dbg + ((size_t)blockIdx.x * NW + wrp) * 8;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) d[k] = stamp[k];
+        d[5] = r1 - r0; d[6] = nv;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        d[7] = smid;
+    }
 }
 
 template <int NT, int STAGES, int MINB>
@@ -610,8 +627,34 @@ static void launch_ring_shape(psba_ctx *c)
 {
     const int dyn = (int)psba_ring_smem(c->ring_cfg, c->seg_v);
     psba_set_smem((const void *)k_schur_ring<NT, STAGES, MINB>, dyn);
+    static int dbg_runs = getenv("PSBA_RING_DEBUG") ? 3 : 0;       // third launch: clock stamps of every warp (phase times)
+    long long *dbg = nullptr;
+    const size_t nd = (size_t)c->n_seg * (NT / 32) * 8;
+    if (dbg_runs > 0 && --dbg_runs == 0) { dbg = (long long *)psba_dev_alloc(c, nd * 8, true); }
     k_schur_ring<NT, STAGES, MINB><<<c->n_seg, NT, dyn, c->stream>>>((const seg_desc *)c->seg_desc, c->cam_obs, c->cam_pt, c->ring_wrow_ptr, c->ring_rows,
-                                                                    c->ring_info, c->sched_chunk, c->W, c->Vinv, c->g + c->N, c->pair_part, c->seg_v);
+                                                                    c->ring_info, c->sched_chunk, c->W, c->Vinv, c->g + c->N, c->pair_part, c->seg_v, dbg);
+    if (dbg) {
+        std::vector<long long> h(nd);
+        CUDA_CHECK(cudaMemcpyAsync(h.data(), dbg, nd * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        const int NW = NT / 32;
+        double s_p1wait = 0, s_p1comp = 0, s_bar = 0, s_p2 = 0, s_cta = 0, s_rows = 0, s_maxrows = 0, s_p2max = 0, s_p2min = 0;
+        for (int b = 0; b < c->n_seg; ++b) {
+            long long t0 = h[(size_t)b * NW * 8], tend = 0, p2max = 0, p2min = 1ll << 60; int maxr = 0;
+            for (int w = 0; w < NW; ++w) {
+                const long long *d = &h[((size_t)b * NW + w) * 8];
+                t0 = std::min(t0, d[0]); tend = std::max(tend, d[4]);
+                s_p1wait += (double)(d[1] - d[0]) / NW; s_p1comp += (double)(d[2] - d[1]) / NW; s_bar += (double)(d[3] - d[2]) / NW; s_p2 += (double)(d[4] - d[3]) / NW;
+                s_rows += (double)d[5] / NW; maxr = std::max(maxr, (int)d[5]);
+                p2max = std::max(p2max, d[4] - d[3]); p2min = std::min(p2min, d[4] - d[3]);
+            }
+            s_cta += (double)(tend - t0); s_maxrows += maxr; s_p2max += (double)p2max; s_p2min += (double)p2min;
+        }
+        const double n = c->n_seg;
+        fprintf(stderr, "ring debug: %d CTAs x %d warps, per CTA (cycles): life %.0f | start->phase-1 data %.0f, phase-1 compute %.0f, reduce+prologue+barrier %.0f, phase 2 mean %.0f (min %.0f max %.0f) | rows/warp mean %.1f max %.1f\n",
+                c->n_seg, NW, s_cta / n, s_p1wait / n, s_p1comp / n, s_bar / n, s_p2 / n, s_p2min / n, s_p2max / n, s_rows / n, s_maxrows / n);
+        psba_dev_free(c, dbg);
+    }
 }
 static void launch_ring(psba_ctx *c)
 {

@@ -653,6 +653,9 @@ extern "C" double psba_get_stat(psba_ctx *c, const char *name)
     if (s == "pair_mode") return c->pair_mode;
     if (s == "n_seg") return c->n_seg;
     if (s == "seg_v") return c->seg_v;
+    if (s == "ring_rows") return (double)c->ring_n_rows;
+    if (s == "ring_cfg") return c->pair_mode == 6 ? c->ring_cfg : -1;
+    if (s == "ring_rt") return c->pair_mode == 6 ? c->ring_rt : -1;
     if (s == "cholmod_events") return c->n_cholmod_events;
     if (s == "pcg_iterations") return c->pcg_last_iters;
     if (s == "cholmod_max_l_over_beta") return c->cholmod_max_l_over_beta;

@@ -359,7 +359,7 @@ static void build_segments(psba_ctx *c, const long long *tptr, const std::vector
     // small problems: enough segments to fill the machine four times over (Venice-52: 312 segments of 1 280 visits were three
     // uneven waves of one CTA per SM)
     if ((long long)o < (long long)c->seg_v * 4 * c->n_sm) c->seg_v = std::max(128, std::min(c->seg_v, cdiv(o, 4 * c->n_sm)));
-    if (getenv("PSBA_SEG_V")) c->seg_v = std::max(32, std::min(SEG_V_MAX, atoi(getenv("PSBA_SEG_V"))));
+    if (getenv("PSBA_SEG_V")) c->seg_v = std::max(32, std::min(c->pair_mode == 6 ? ring_seg_v(c) : SEG_V_MAX, atoi(getenv("PSBA_SEG_V"))));
     // ---- segments (host: m cameras)
     std::vector<seg_desc_h> segs;
     std::vector<int> row_seg_ptr((size_t)m + 1, 0), seglen(m, 1);

@@ -373,20 +373,25 @@ def _check_try_against_oracle(prob, G):
     return O
 
 
-@pytest.mark.parametrize("mode,segv,G_", [("5", "", ""), ("5", "48", "1"), ("5", "100", "2"), ("5", "100", "8"), ("5", "1400", "32"), ("0", "", "")])
+@pytest.mark.parametrize("mode,segv,G_", [("6", "", ""), ("6", "40", "0:1"), ("6", "100", "1:2"), ("6", "1400", "2:64"), ("6", "33", "4:3"), ("6", "200", "5:5"),
+                                          ("5", "", ""), ("5", "48", "1"), ("5", "100", "2"), ("5", "100", "8"), ("5", "1400", "32"), ("0", "", "")])
 def test_pair_pass_variants_agree_with_oracle(mode, segv, G_, monkeypatch):
-    """PSBA_PAIR_MODE selects the pair pass: 5 = segment kernel (Y staged per camera-row segment; segment lengths and lane-group sizes varied here), 0 = the pair-major gather kernel.  All must give the reference's S and
-    ea (compute_S.cl / compute_ea.cl) and the same LM trajectory."""
+    """PSBA_PAIR_MODE selects the pair pass: 6 = ring kernel (default; launch shape `cfg` and rows per task `rt` varied here as
+    "cfg:rt", segment lengths too), 5 = segment kernel (Y staged per camera-row segment; segment lengths and lane-group sizes
+    varied here), 0 = the pair-major gather kernel.  All must give the reference's S and ea (compute_S.cl / compute_ea.cl)
+    and the same LM trajectory."""
     from psba_b200 import synth
     monkeypatch.setenv("PSBA_PAIR_MODE", mode)
     if segv:
         monkeypatch.setenv("PSBA_SEG_V", segv)
-    if G_:
+    if G_ and mode == "6":
+        monkeypatch.setenv("PSBA_RING_CFG", G_.split(":")[0]); monkeypatch.setenv("PSBA_RING_RT", G_.split(":")[1])
+    elif G_:
         monkeypatch.setenv("PSBA_SEG_G", G_)
     for prob in (synth.ring_problem(m=160, n=6000, d=4, w=12, seed=7), psba_b200.read_sba(*dataset_paths("54"))):
         G = psba_b200.PSBA(prob)
         assert int(G.stat("pair_mode")) == int(mode)
-        if mode == "5":
+        if mode in ("5", "6"):
             assert int(G.stat("n_seg")) >= prob["m"] - 1
         O = _check_try_against_oracle(prob, G)
         G.close()
@@ -399,7 +404,7 @@ def test_pair_pass_variants_agree_with_oracle(mode, segv, G_, monkeypatch):
         G.close(); O.close()
 
 
-@pytest.mark.parametrize("mode", ["5", "0"])
+@pytest.mark.parametrize("mode", ["6", "5", "0"])
 def test_points_with_more_observations_than_one_wave(mode, monkeypatch):
     """Tracks of 150 observations (> 128, one CTA wave) next to ordinary ones: the pipelined point-major kernels
     take the one-wave chunks, the wave-loop kernels the oversize ones; the pair pass has no limit on track length."""
@@ -443,7 +448,7 @@ def _ragged_problem():
     return prob
 
 
-@pytest.mark.parametrize("mode", ["5", "0"])
+@pytest.mark.parametrize("mode", ["6", "5", "0"])
 def test_ragged_structure_empty_camera_and_single_observation_points(mode, monkeypatch):
     monkeypatch.setenv("PSBA_PAIR_MODE", mode)
     prob = _ragged_problem()
