@@ -22,6 +22,8 @@
 #include "dev_math.cuh"
 #include <algorithm>
 #include <chrono>
+#include <map>
+#include <mutex>
 
 #define LDT (TS + 1)            // padded leading dimension in shared memory
 #define TILE_SM (TS * LDT)      // doubles per shared tile
@@ -118,10 +120,50 @@ static void nd_recurse(nd_ctx &x, std::vector<int> nodes)
     x.append(S);
 }
 
+// The symbolic part below runs on a helper thread under device work of the set-up (structure.cu); it issues no CUDA call:
+// every upload / zero-filled allocation is recorded here and carried out by psba_flush_tile_uploads on the calling thread
+struct pending_upload { void **dst; std::vector<char> bytes; size_t zero_bytes; };
+static std::vector<pending_upload> &pending(psba_ctx *c)
+{
+    static std::map<psba_ctx *, std::vector<pending_upload>> q;   // one set-up at a time per context
+    static std::mutex mu;
+    std::lock_guard<std::mutex> l(mu);
+    return q[c];
+}
 template <class T> static void up_vec(psba_ctx *c, T **d, const std::vector<T> &h)
 {
-    *d = (T *)psba_dev_alloc(c, std::max<size_t>(1, h.size()) * sizeof(T), false);
-    if (!h.empty()) CUDA_CHECK(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    pending_upload u;
+    u.dst = (void **)d; u.zero_bytes = 0;
+    u.bytes.assign((const char *)h.data(), (const char *)h.data() + h.size() * sizeof(T));
+    pending(c).push_back(std::move(u));
+}
+template <class T> static void zero_alloc(psba_ctx *c, T **d, size_t bytes)
+{
+    pending_upload u;
+    u.dst = (void **)d; u.zero_bytes = std::max<size_t>(bytes, 16);
+    pending(c).push_back(std::move(u));
+}
+void psba_flush_tile_uploads(psba_ctx *c)
+{
+    // ONE device block and ONE host-to-device copy for all tables (forty separate pageable copies cost 1.3 ms at 2 000
+    // cameras); the zero-filled work arrays (tile pool, ...) stay separate allocations
+    std::vector<pending_upload> &q = pending(c);
+    size_t total = 0;
+    auto room = [](const pending_upload &u) { return std::max<size_t>(256, (u.bytes.size() + 255) & ~(size_t)255); };   // distinct addresses for empty tables
+    for (pending_upload &u : q) if (!u.zero_bytes) total += room(u);
+    std::vector<char> stage(std::max<size_t>(total, 256));
+    c->tile_block = psba_dev_alloc(c, stage.size(), false);
+    c->tile_block_bytes = stage.size();
+    size_t off = 0;
+    for (pending_upload &u : q) {
+        if (u.zero_bytes) { *u.dst = psba_dev_alloc(c, u.zero_bytes, true); continue; }
+        if (!u.bytes.empty()) memcpy(stage.data() + off, u.bytes.data(), u.bytes.size());
+        *u.dst = (char *)c->tile_block + off;
+        off += room(u);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(c->tile_block, stage.data(), std::min(stage.size(), std::max<size_t>(off, 1)), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));            // the staged bytes go out of scope
+    q.clear();
 }
 
 void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int>> &pairs)
@@ -372,7 +414,7 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
         c->n_flow_tasks = (int)tasks.size();
         up_vec(c, &c->d_flow_tasks, tasks); up_vec(c, &c->d_flow_final, tfinal); up_vec(c, &c->d_flow_defseq, def_seq);
         up_vec(c, &c->d_flow_bseq, b_seq); up_vec(c, &c->d_flow_critneed, crit_need);
-        c->d_flow_ver = (int *)psba_dev_alloc(c, (size_t)(c->n_tiles + nt) * sizeof(int), true);
+        zero_alloc(c, &c->d_flow_ver, (size_t)(c->n_tiles + nt) * sizeof(int));
     }
     up_vec(c, &c->d_psrc_ptr, psrc_ptr); up_vec(c, &c->d_psrc, psrc);
     up_vec(c, &c->d_b_J, bJ); up_vec(c, &c->d_b_sptr, b_sptr); up_vec(c, &c->d_b_slot, b_slot);
@@ -381,16 +423,14 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
     {
         std::vector<int> order(step_panels.rbegin(), step_panels.rend());        // last step first
         up_vec(c, &c->d_bw_order, order);
-        c->bw_xbuf = (double *)psba_dev_alloc(c, (size_t)nt * TS * sizeof(double), true);
+        zero_alloc(c, &c->bw_xbuf, (size_t)nt * TS * sizeof(double));
     }
     up_vec(c, &c->d_coltile_ptr, cptr); up_vec(c, &c->d_coltile_row, crow); up_vec(c, &c->d_coltile_slot, cslot);
-    c->Stiles = (double *)psba_dev_alloc(c, (size_t)c->n_tiles * TS * TS * sizeof(double), true);
-    c->contrib = (double *)psba_dev_alloc(c, (size_t)c->n_tiles * TS * sizeof(double), true);
-    c->Linv = (double *)psba_dev_alloc(c, (size_t)nt * TS * TS * sizeof(double), true);
-    c->Ldiag = (double *)psba_dev_alloc(c, (size_t)nt * TS * TS * sizeof(double), true);
-    lap("descriptors + uploads");
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));            // the host vectors above go out of scope
-    lap("sync");
+    zero_alloc(c, &c->Stiles, (size_t)c->n_tiles * TS * TS * sizeof(double));
+    zero_alloc(c, &c->contrib, (size_t)c->n_tiles * TS * sizeof(double));
+    zero_alloc(c, &c->Linv, (size_t)nt * TS * TS * sizeof(double));
+    zero_alloc(c, &c->Ldiag, (size_t)nt * TS * TS * sizeof(double));
+    lap("descriptors");
     c->chol_graph_ok = false; c->bw_graph_ok = false;
     if (getenv("PSBA_SETUP_TIMING"))
         fprintf(stderr, "psba setup: camera system %d tiles/edge, %d factor tiles, %d steps, %zu critical + %zu deferred + %zu rhs tasks\n",

@@ -92,6 +92,7 @@ extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3D
     c->d_small_list = c->d_big_list = nullptr; c->n_small = c->n_big = 0;
     c->n_seg = 0; c->seg_desc = nullptr; c->sched_chunk = nullptr; c->sch_beg = c->sch_end = nullptr; c->tri_vr = nullptr;
     c->ring_wrow_ptr = nullptr; c->ring_rows = nullptr; c->ring_info = nullptr; c->ring_n_rows = 0;
+    c->tile_block = nullptr; c->tile_block_bytes = 0;
     c->pchunk_pair = nullptr; c->pchunk_beg = c->pchunk_end = nullptr;
     c->chol_pdl = !(getenv("PSBA_NO_PDL") && atoi(getenv("PSBA_NO_PDL")));
     // dataflow factorisation (one flag-driven launch): measured 1.148 ms against 1.079 ms for the step kernels on the headline
@@ -210,7 +211,12 @@ extern "C" void psba_release_buffer(psba_ctx *c)
                     c->pcg_work, c->d_flow_tasks, c->d_flow_final, c->d_flow_defseq, c->d_flow_bseq, c->d_flow_critneed, c->d_flow_ver,
                     c->tmpA, c->tmpB, (void *)c->ext.kc, (void *)c->ext.wgt, c->seg_desc, c->sched_chunk, c->sch_beg, c->sch_end, c->tri_vr,
                     c->ring_wrow_ptr, c->ring_rows, c->ring_info};
-    for (void *p : ptrs) psba_dev_free(c, p);
+    for (void *p : ptrs) {
+        const char *q = (const char *)p, *b = (const char *)c->tile_block;   // tables inside the schedule block are not allocations
+        if (b && q >= b && q < b + c->tile_block_bytes) continue;
+        psba_dev_free(c, p);
+    }
+    psba_dev_free(c, c->tile_block);
     psba_dev_free(c, c->stage_impts); psba_dev_free(c, c->stage_pts);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (c->chol_graph_ok) cudaGraphExecDestroy(c->chol_graph);

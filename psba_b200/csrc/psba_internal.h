@@ -129,6 +129,7 @@ struct psba_ctx {
     int *d_crit_I, *d_crit_K, *d_psrc_ptr, *d_psrc, *d_b_J, *d_b_sptr, *d_b_slot;
     int *d_def_I, *d_def_J, *d_def_sptr, *d_def_src, *d_step_panels;
     int4 *d_crit_desc, *d_def_desc; int2 *d_crit_src, *d_def_srcs;   // flat task descriptors (one load per CTA)
+    void *tile_block; size_t tile_block_bytes;   // the schedule tables above live in ONE device block (psba_flush_tile_uploads)
     // dataflow factorisation (k_panel_flow): task table in step order, per-tile write counters and what a task waits for
     int n_flow_tasks; int2 *d_flow_tasks; int *d_flow_final, *d_flow_defseq, *d_flow_bseq, *d_flow_critneed, *d_flow_ver;
     int camera_solver; double *pcg_work; double pcg_tol; int pcg_max_iter, pcg_last_iters;   // optional PCG camera solve (kernels_pcg.cu)
@@ -185,7 +186,8 @@ void psba_launch_schur(psba_ctx *c, double mu);
 size_t psba_ring_smem(int cfg, int seg_v);   // dynamic shared memory of k_schur_ring (structure.cu)
 void psba_launch_Y_materialize(psba_ctx *c, double *Y);
 // ---- kernels_solve.cu
-void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int,int>> &camera_pairs);
+void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int,int>> &camera_pairs);   // host only; then:
+void psba_flush_tile_uploads(psba_ctx *c);       // uploads / allocations the symbolic part recorded
 double psba_launch_factor(psba_ctx *c, bool defer_status = false);      // returns 0.0 / 1.0 (syncs unless deferred)
 void psba_launch_solve(psba_ctx *c);         // dp[0..N) = S^-1 eab[0..N)
 void psba_tiles_to_dense(psba_ctx *c, double *dense_dev, bool mirror);

@@ -14,6 +14,10 @@
 #include <cub/cub.cuh>
 #include <algorithm>
 #include <chrono>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <functional>
 #include <cstdint>
 
 typedef unsigned long long u64;
@@ -497,6 +501,30 @@ static void build_ring_tables(psba_ctx *c)
     psba_dev_free(c, wrows); psba_dev_free(c, task);
 }
 
+
+// one helper thread per process for host work that can run under device work of the same set-up (created once; the jobs it
+// gets issue no CUDA calls -- two threads feeding one stream serialise on each other's blocking copies)
+struct host_worker {
+    std::thread th; std::mutex mu; std::condition_variable cv;
+    std::function<void()> job; bool busy = false, quit = false;
+    static host_worker &get() { static host_worker w; return w; }
+    host_worker() { th = std::thread([this] { loop(); }); }
+    ~host_worker() { { std::lock_guard<std::mutex> l(mu); quit = true; } cv.notify_all(); th.join(); }
+    void loop()
+    {
+        std::unique_lock<std::mutex> l(mu);
+        for (;;) {
+            cv.wait(l, [this] { return quit || (busy && job); });
+            if (quit) return;
+            std::function<void()> j = std::move(job); job = nullptr;
+            l.unlock(); j(); l.lock();
+            busy = false; cv.notify_all();
+        }
+    }
+    void run(std::function<void()> j) { { std::lock_guard<std::mutex> l(mu); job = std::move(j); busy = true; } cv.notify_all(); }
+    void wait() { std::unique_lock<std::mutex> l(mu); cv.wait(l, [this] { return !busy; }); }
+};
+
 // ---- the build ---------------------------------------------------------------------------------------
 void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
 {
@@ -535,6 +563,23 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
     int *iota = salloc<int>(c, o);
     if (o) k_local_idx<<<cdiv(o, 256), 256, 0, st>>>(o, o0, p0, gi, gj, c->iidx, c->jidx, iota);
     k_local_ptr<<<cdiv(n + 1, 256), 256, 0, st>>>(n + 1, p0, o0, gptr, c->pt_ptr);
+    // ---- camera-major order: stable radix sort of the local observations by camera (enqueued first: the host loop over the
+    // points below runs under it)
+    c->cam_obs = salloc<int>(c, o);
+    std::vector<int> cptr((size_t)m + 1, 0);
+    int *skey = salloc<int>(c, o), *cp = salloc<int>(c, (size_t)m + 1);
+    void *sort_tmp = nullptr;
+    {
+        CUDA_CHECK(cudaMemsetAsync(cp, 0, ((size_t)m + 1) * 4, st));
+        size_t tb = 0;
+        const int bits = bits_for((u64)m);
+        CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, c->jidx, skey, iota, c->cam_obs, o, 0, bits, st));
+        sort_tmp = psba_dev_alloc(c, std::max<size_t>(tb, 16), false);
+        if (o) {
+            CUDA_CHECK(cub::DeviceRadixSort::SortPairs(sort_tmp, tb, c->jidx, skey, iota, c->cam_obs, o, 0, bits, st));
+            k_segment_ptr<<<cdiv(o, 256), 256, 0, st>>>(o, m, skey, cp);
+        }
+    }
     // point chunks: whole points, <= PT_CTA observations and <= PT_CTA points per CTA (greedy, host)
     std::vector<int> pch(1, 0);
     {
@@ -561,23 +606,10 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
         c->d_small_list = big.empty() ? nullptr : supload(c, small);
         c->d_big_list = big.empty() ? nullptr : supload(c, big);
     }
-    // ---- camera-major order: stable radix sort of the local observations by camera
-    c->cam_obs = salloc<int>(c, o);
-    std::vector<int> cptr((size_t)m + 1, 0);
     {
-        int *skey = salloc<int>(c, o), *cp = salloc<int>(c, (size_t)m + 1);
-        CUDA_CHECK(cudaMemsetAsync(cp, 0, ((size_t)m + 1) * 4, st));
-        size_t tb = 0;
-        const int bits = bits_for((u64)m);
-        CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tb, c->jidx, skey, iota, c->cam_obs, o, 0, bits, st));
-        void *tmp = psba_dev_alloc(c, std::max<size_t>(tb, 16), false);
-        if (o) {
-            CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tb, c->jidx, skey, iota, c->cam_obs, o, 0, bits, st));
-            k_segment_ptr<<<cdiv(o, 256), 256, 0, st>>>(o, m, skey, cp);
-        }
         CUDA_CHECK(cudaMemcpyAsync(cptr.data(), cp, ((size_t)m + 1) * 4, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
-        psba_dev_free(c, tmp); psba_dev_free(c, skey); psba_dev_free(c, cp); psba_dev_free(c, iota);
+        psba_dev_free(c, sort_tmp); psba_dev_free(c, skey); psba_dev_free(c, cp); psba_dev_free(c, iota);
     }
     std::vector<int> cc_cam, cc_beg, cc_end, cc_ptr(1, 0);
     const int CCH = CAM_CTA * CAM_OPT;
@@ -635,6 +667,9 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
     }
     c->n_pair = (int)pk.size();
     c->pair_k = supload(c, pk); c->pair_l = supload(c, pl);
+    // ---- camera system tiles (symbolic factorisation, 2 ms of host work at 2 000 cameras) on a helper thread, under the device
+    // work and the host round trips of the segment / ring tables below (disjoint fields of the context, same stream)
+    host_worker::get().run([c, &pairs]() { psba_build_tile_structure(c, pairs); });     // no CUDA call inside: uploads are flushed below
     // ---- triple range of every pair, chunks of the pair pass
     long long *tptr = salloc<long long>(c, (size_t)c->n_pair + 1);
     k_pair_ptr<<<cdiv(c->n_pair + 1, 256), 256, 0, st>>>(c->n_pair, m, c->pair_k, c->pair_l, c->ntri, lkeys, tptr);
@@ -678,9 +713,10 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
         T.lap("pair set + chunks");
     }
     psba_dev_free(c, tptr); psba_dev_free(c, ccnt); psba_dev_free(c, nonempty); psba_dev_free(c, lkeys);
-    // ---- camera system tiles (symbolic factorisation, host)
-    psba_build_tile_structure(c, pairs);
-    T.lap("tile structure");
+    host_worker::get().wait();
+    T.lap("tile structure (wait)");
+    psba_flush_tile_uploads(c);
+    T.lap("tile structure (uploads)");
 }
 
 // camera-major copies of the per-observation constants the camera pass reads (point index, measurement)
