@@ -168,6 +168,9 @@ void psba_trace_get(psba_ctx *ctx, int k, psba_trace_rec *rec);
 /* options: "verbose" (0/1), "max_iter" (50), "itno", "lm_only" (stop instead of handing to TR),
  * "camera_solver" (0: tiled Cholesky, the default and the path compared with the reference; 1: block-Jacobi preconditioned
  * conjugate gradients on the tiles of S) with "pcg_tol" (1e-10, relative residual) and "pcg_max_iter" (1000),
+ * "tr_fused" (1: psba_trust_region takes the scalars of a step -- pUpU, pUg, pBpB, pBg, |P|, the dog-leg quadratic, g.P, |JP|^2,
+ * PSBA/trust_region.cpp:125-130,166-176,208-212,520-595 -- from six inner products of g and P_B computed once per step, one host
+ * round trip per step and one per radius try; 0: every scalar from the explicit vectors, as the reference does),
  * "trace_reset" (forget the run log), "stats_reset", "profile" (per-kernel CUDA-event timing), "timer_start"; unknown names abort. */
 void psba_set_option(psba_ctx *ctx, const char *name, double value);
 double psba_get_stat(psba_ctx *ctx, const char *name);

@@ -138,10 +138,169 @@ static bool compute_PB(psba_ctx *c, double *lambda)
     return true;
 }
 
+
+// ---- trust region with ONE device round trip per Gauss-Newton step and ONE per radius try -----------------------------
+// Same iteration as psba_trust_region_explicit below (trust_region.cpp:112-272, compute_p_2 :520-595); what changes is where the
+// scalars come from.  P_U = -(g gtg)/gtBg is a multiple of g, P = eta1 P_U + eta2 P_B (or one of the three dog-leg forms) is a
+// combination of g and P_B, and every scalar the reference forms from those vectors -- pUpU, pUg, pBpB, pBg, |P|, the
+// dog-leg quadratic, g.P, |J P|^2 -- is a function of the six numbers  g.g, g.P_B, P_B.P_B, |J g|^2, Jg.JP_B, |J P_B|^2.
+// They are computed ONCE per step, behind the camera solve and without a host round trip in between (the status word
+// of the solve travels with them); a radius try is then  dp = a g + b P_B, candidate parameters, candidate cost.
+// The reference needs 4 J-products, 5-6 triple dot products and 3-6 vector updates with a read-back each per step; here:
+// 1 J-product, 1 triple dot product, 1 vector update per radius try, 2 read-backs.  Values agree with the explicit
+// evaluation to rounding (the explicit path stays available: psba_set_option "tr_fused" = 0).
+static int enqueue_PB(psba_ctx *c, double lambda)
+{
+    c->st_tries += 1;
+    psba_launch_schur(c, lambda);
+    psba_launch_factor(c, true);                                  // status word read later, with the scalars
+    psba_launch_solve(c);
+    psba_launch_backsub(c, lambda, false, nullptr);               // eb, dpb
+    psba_launch_axpby(c, -1.0, c->dp, 0.0, c->dp, c->P_B);        // P_B = -dp
+    return 0;
+}
+
+static int psba_trust_region_fused(psba_ctx *c, double *finalErr)
+{
+    int iter_flag, notgood_cnt = 0, good_iters = 0, nu = 2;
+    double ex_L2, pred_ex_L2, act_ex_L2, dk = 1, lambda = 0, p_norm, origin_lambda = 0.0;
+
+    ex_L2 = psba_launch_cost(c, c->cur, nullptr);                 // trust_region.cpp:106-107
+    iter_flag = PSBA_ITER_CONTINUE;
+    for (; c->itno < c->max_iter; c->itno++) {
+        psba_launch_linearize(c, 2.0, -2.0);                      // :117-122, 133-137
+        double JgJg = 0, JgJB = 0, JBJB = 0, gg = 0, gB = 0, BB = 0;
+        bool solved = false;
+        while (!solved) {                                         // :141-163 with compute_PB (:292-405) inlined
+            enqueue_PB(c, lambda);
+            psba_enqueue_Jdot(c, c->g, c->P_B, nullptr, 16);      // |J g|^2, Jg.JP_B, |J P_B|^2
+            psba_enqueue_dots(c, c->g, c->P_B, c->g, 20);         // g.g, g.P_B, ., P_B.P_B (camera part, point part)
+            CUDA_CHECK(cudaMemcpyAsync(c->h_scal + 16, c->d_scal + 16, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            const int st = c->h_status[0];
+            if (st > 1) { fprintf(stderr, "psba_b200: camera solve failed with status %d (broken dataflow schedule)\n", st); exit(EXIT_FAILURE); }
+            if (st == 0) {
+                c->factor_valid = true;
+                JgJg = c->h_scal[16]; JgJB = c->h_scal[17]; JBJB = c->h_scal[18];
+                gg = c->h_scal[20] + c->h_scal[26]; gB = c->h_scal[21] + c->h_scal[27]; BB = c->h_scal[23] + c->h_scal[29];
+                solved = true; nu = 2; origin_lambda = lambda;
+                break;
+            }
+            c->factor_valid = false;
+            if (lambda == 0.0) {
+                // the failed factorisation overwrote the tile pool: rebuild S, then the modified Cholesky picks lambda
+                // (trust_region.cpp:345-364)
+                psba_launch_schur(c, 0.0);
+                double delta, beta, sum; int nscalar = 0;
+                bool dense = !psba_cholmod_use_tiles(c);
+                if (!dense) {
+                    double ratio = 0.0;
+                    sum = psba_launch_cholmod_tiles(c, &delta, &beta, &nscalar, nullptr, &ratio);
+                    const char *e = getenv("PSBA_CHOLMOD_TILES");
+                    if (ratio > 1.0 && psba_cholmod_dense_possible(c) && !(e && atoi(e))) { dense = true; psba_launch_schur(c, 0.0); }
+                }
+                if (dense) {
+                    const size_t nn = (size_t)c->N * c->N;
+                    if (!c->Sdense) c->Sdense = (double *)psba_dev_alloc(c, nn * sizeof(double), true);
+                    psba_tiles_to_dense(c, c->Sdense, true);
+                    sum = psba_launch_cholmod(c, &delta, &beta, &nscalar);
+                }
+                lambda = fabs(sum) / c->N;
+                if ((size_t)c->n_cholmod_events < c->force_lambda.size()) lambda = c->force_lambda[c->n_cholmod_events];
+                c->n_cholmod_events++;
+                {
+                    psba_trace_rec r;
+                    r.phase = 2; r.itno = c->itno; r.err = (double)nscalar; r.rho = sum; r.mu = lambda; r.delta = 0; r.pnorm = 0; r.accepted = 0;
+                    c->trace.push_back(r);
+                }
+            } else lambda = 2 * lambda;
+            if (c->verbose) printf("chol failed.\n");
+            if (origin_lambda != 0.0) {
+                if (nu > 4) { *finalErr = ex_L2; return PSBA_ITER_TURN_TO_LM; }
+                lambda = lambda * nu; nu = nu * 2;
+            }
+        }
+        // ---- the scalars of trust_region.cpp:125-130, 166-176 from the six numbers
+        const double gtBg = 2 * JgJg, gtg = gg;
+        const double alpha = -gtg / gtBg;                          // P_U = alpha g
+        const double pUtBpU = alpha * alpha * gtBg, pUtBpB = 2 * alpha * JgJB, pBtBpB = 2 * JBJB;
+        const double pUpU = alpha * alpha * gtg, pUg = alpha * gtg, pBpB = BB, pBg = gB, pUpB = alpha * gB;
+
+        iter_flag = PSBA_ITER_CONTINUE;
+        while (iter_flag == PSBA_ITER_CONTINUE) {                 // :180
+            // ---- compute_p_2 (:520-595): P = cU P_U + cB P_B
+            const double den = -pUtBpB * pUtBpB + pBtBpB * pUtBpU;
+            const double eta1 = (pBg * pUtBpB) / den - (pBtBpB * pUg) / den;
+            const double eta2 = (pUg * pUtBpB) / den - (pBg * pUtBpU) / den;
+            double cU = eta1, cB = eta2;
+            p_norm = sqrt(eta1 * eta1 * pUpU + 2 * eta1 * eta2 * pUpB + eta2 * eta2 * pBpB);
+            if (p_norm > dk) {
+                const double pU_norm = sqrt(pUpU), pB_norm = sqrt(pBpB);
+                if (pU_norm > dk) { cU = dk / pU_norm; cB = 0.0; p_norm = dk; }
+                else if (pB_norm <= dk) { cU = 0.0; cB = 1.0; p_norm = sqrt(p_norm + pBpB); }   // printed value only
+                else {
+                    // dog-leg: A = P_B - P_U, B = 2 P_U - P_B
+                    const double a = pBpB - 2 * pUpB + pUpU;
+                    double b = 3 * pUpB - pBpB - 2 * pUpU, cc = 4 * pUpU - 4 * pUpB + pBpB;
+                    b = 2 * b; cc = cc - dk * dk;
+                    double b2_4ac = b * b - 4 * a * cc; if (fabs(b2_4ac) < 1e-12) b2_4ac = 0;
+                    const double tau = (-b + sqrt(b2_4ac)) / (2 * a);
+                    cU = 2 - tau; cB = tau - 1;                    // P_U + (tau - 1)(P_B - P_U)
+                    p_norm = dk;
+                }
+            }
+            // ---- candidate = p + P, actual cost (:184-194)
+            psba_launch_axpby(c, cU * alpha, c->g, cB, c->P_B, c->dp);
+            psba_launch_newp(c);
+            act_ex_L2 = psba_launch_cost(c, 1 - c->cur, nullptr);
+            if (fabs((ex_L2 - act_ex_L2) / ex_L2) < PSBA_EPSILON2) { iter_flag = PSBA_ITER_DP_NO_CHANGE; break; }
+            // ---- predicted cost (:208-212)
+            const double Jx_norm = cU * cU * pUtBpU + 2 * cU * cB * pUtBpB + cB * cB * pBtBpB;
+            pred_ex_L2 = cU * pUg + cB * pBg;
+            pred_ex_L2 += ex_L2 + Jx_norm / 2;
+            const double rho = (ex_L2 - act_ex_L2) / (ex_L2 - pred_ex_L2);
+            int acc = 0;
+            if (rho < (1.0 / 4.0) || act_ex_L2 > ex_L2) {
+                dk = dk / 4;
+                if (c->verbose) printf("iter %d reduce region\n", c->itno);
+            } else if (rho >= (3.0 / 4.0) && act_ex_L2 < ex_L2) {
+                iter_flag = PSBA_ITER_PASS; acc = 1;
+                c->cur = 1 - c->cur; c->lin_valid = false;        // update_p
+                *finalErr = act_ex_L2;
+                dk = fmin(2 * dk, PSBA_MAX_DELTA);
+            } else if (rho >= (1.0 / 4.0) && rho < (3.0 / 4.0) && act_ex_L2 < ex_L2) {
+                iter_flag = PSBA_ITER_PASS; acc = 1;
+                c->cur = 1 - c->cur; c->lin_valid = false;
+                *finalErr = act_ex_L2;
+            } else if (std::isnan(rho)) {
+                *finalErr = ex_L2;
+                return PSBA_ITER_TURN_TO_LM;
+            }
+            if (c->verbose)
+                printf("itno=%d\tErr:%.15E\tDelta=%f\tRho=%f\tnorm_p=%f\tLambda=%E\n", c->itno, act_ex_L2, dk, rho, p_norm, lambda);
+            trace(c, 1, act_ex_L2, rho, lambda, dk, p_norm, acc);
+            if (fabs((act_ex_L2 - ex_L2) / ex_L2) <= PSBA_EPSILON2) { iter_flag = PSBA_ITER_ERR_SMALL_ENOUGH; break; }
+            if (rho < 1.0 / 4) {
+                notgood_cnt++;
+                if (notgood_cnt >= 5) { iter_flag = PSBA_ITER_TURN_TO_LM; break; }
+            } else notgood_cnt = 0;
+            if (rho > 3.0 / 4 && act_ex_L2 < ex_L2) {
+                good_iters++;
+                if (good_iters >= 10) { lambda = 0.0; origin_lambda = 0.0; good_iters = 0; }
+            } else good_iters = 0;
+            if (rho > (1.0 / 4) && act_ex_L2 < ex_L2) ex_L2 = act_ex_L2;
+        }
+        if (iter_flag != PSBA_ITER_PASS) break;
+    }
+    return iter_flag;
+}
+
 extern "C" int psba_trust_region(psba_ctx *c, int cnp, int pnp, int mnp, int n3Dpts, int nCams, int n2Dprojs,
                                  int *blk_idx, double *finalErr)
 {
     (void)cnp; (void)pnp; (void)mnp; (void)n3Dpts; (void)nCams; (void)n2Dprojs; (void)blk_idx;
+    if (c->tr_fused && c->camera_solver != 1) return psba_trust_region_fused(c, finalErr);
     int iter_flag, notgood_cnt = 0, good_iters = 0, nu = 2;
     double ex_L2, pred_ex_L2, act_ex_L2, gtBg, gtg, dk = 1, lambda = 0, p_norm, origin_lambda = 0.0;
     const size_t Tl = (size_t)c->N + 3 * (size_t)c->n;

@@ -489,23 +489,29 @@ __global__ void k_final_reduce6(const double *__restrict__ part, int nparts, dou
     int v = threadIdx.x;
     if (v >= 6) return;
     double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += part[(size_t)p * 6 + v];
+#pragma unroll 8
+    for (int p = 0; p < nparts; ++p) s += part[(size_t)p * 6 + v];      // same order; the loads of eight partials fly together
     out[v] = s;
 }
 
-void psba_launch_dots(psba_ctx *c, const double *x, const double *y, const double *z, double out[6])
+void psba_enqueue_dots(psba_ctx *c, const double *x, const double *y, const double *z, int off)
 {
     // camera part
     k_dots<<<1, 256, 0, c->stream>>>(c->N, x, y, z, c->d_part);
-    k_final_reduce6<<<1, 32, 0, c->stream>>>(c->d_part, 1, c->d_scal);
+    k_final_reduce6<<<1, 32, 0, c->stream>>>(c->d_part, 1, c->d_scal + off);
     // point part
     const int np = 3 * c->n;
     int nb = np > 0 ? std::min(cdiv(np, 256), 296) : 0;
     if (nb > 0) k_dots<<<nb, 256, 0, c->stream>>>(np, x + c->N, y + c->N, z + c->N, c->d_part + 8);
-    k_final_reduce6<<<1, 32, 0, c->stream>>>(c->d_part + 8, nb, c->d_scal + 6);
+    k_final_reduce6<<<1, 32, 0, c->stream>>>(c->d_part + 8, nb, c->d_scal + off + 6);
     c->st_launches += 4;
     LAUNCH_CHECK();
-    if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal + 6, 6);
+    if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal + off + 6, 6);
+}
+
+void psba_launch_dots(psba_ctx *c, const double *x, const double *y, const double *z, double out[6])
+{
+    psba_enqueue_dots(c, x, y, z, 0);
     CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, 12 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     for (int v = 0; v < 6; ++v) out[v] = c->h_scal[v] + c->h_scal[6 + v];

@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(256) k_Jdot(int o, int N, const int *__restric
     }
 }
 
-void psba_launch_Jdot(psba_ctx *c, const double *x, const double *y, double *Jx_out, double res[3])
+void psba_enqueue_Jdot(psba_ctx *c, const double *x, const double *y, double *Jx_out, int off)
 {
     const int set = c->cur;
     if (!c->cache_valid[set]) psba_launch_cam_prep(c, set);
@@ -574,10 +574,15 @@ void psba_launch_Jdot(psba_ctx *c, const double *x, const double *y, double *Jx_
     if (nb > 0)
         PROF(c, KID_JDOT) k_Jdot<<<nb, 256, 0, c->stream>>>(c->o, c->N, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set],
                                          x, y, Jx_out, c->d_part, c->ext);
-    PROF(c, KID_REDUCE) k_final_reduce<<<1, 256, 0, c->stream>>>(c->d_part, nb, 3, 3, c->d_scal);
+    PROF(c, KID_REDUCE) k_final_reduce<<<1, 256, 0, c->stream>>>(c->d_part, nb, 3, 3, c->d_scal + off);
     c->st_launches += 2;
     LAUNCH_CHECK();
-    if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal, 3);
+    if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal + off, 3);
+}
+
+void psba_launch_Jdot(psba_ctx *c, const double *x, const double *y, double *Jx_out, double res[3])
+{
+    psba_enqueue_Jdot(c, x, y, Jx_out, 0);
     read_scalars(c, 0, 3);
     res[0] = c->h_scal[0]; res[1] = c->h_scal[1]; res[2] = c->h_scal[2];
 }

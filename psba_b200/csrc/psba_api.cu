@@ -82,7 +82,7 @@ extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3D
     c->lin_valid = false; c->S_valid = false; c->factor_valid = false; c->chol_graph_ok = false; c->bw_graph_ok = false;
     c->Sdense = c->Sdense_aux = nullptr; c->tmpA = c->tmpB = nullptr;
     c->mu_pending = 0.0; c->coeff_uvw = 1.0; c->coeff_g = 1.0;
-    c->itno = 0; c->max_iter = 50; c->verbose = 0; c->lm_only = 0; c->initErr = 0.0;
+    c->itno = 0; c->max_iter = 50; c->verbose = 0; c->lm_only = 0; c->initErr = 0.0; c->tr_fused = 1;
     c->n_cholmod_events = 0; c->cholmod_max_l_over_beta = 0.0;
     c->st_tries = c->st_exqt = c->st_lin = c->st_launches = 0;
     c->profile = false; c->timer_init = false;
@@ -617,6 +617,7 @@ extern "C" void psba_set_option(psba_ctx *c, const char *name, double v)
     else if (s == "max_iter") c->max_iter = (int)v;
     else if (s == "itno") c->itno = (int)v;
     else if (s == "lm_only") c->lm_only = (int)v;
+    else if (s == "tr_fused") c->tr_fused = (int)v;
     else if (s == "camera_solver") { c->camera_solver = (int)v; c->factor_valid = false; }      // 0 tiled Cholesky (default), 1 block-Jacobi PCG
     else if (s == "pcg_tol") c->pcg_tol = v;
     else if (s == "pcg_max_iter") c->pcg_max_iter = (int)v;

@@ -26,7 +26,7 @@
 #define PAIR_TPL 24        // target triples per lane in the pair pass (lane-per-triple variant)
 #define SEG_V_MAX 1400     // visits per segment: the Y tile (144 B per visit) of two resident CTAs fits one SM
 #define SEG_MAXD 384       // chunk descriptors of a segment prefetched into shared memory
-#define NSCAL 16           // size of the device scalar block
+#define NSCAL 48           // size of the device scalar block ([16..) : the scalars of a fused trust-region step)
 
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
     fprintf(stderr, "psba_b200: CUDA error %d (%s) at %s(%d)\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); \
@@ -146,6 +146,7 @@ struct psba_ctx {
     // ---- scalars
     double *d_part;                 // per-chunk partial sums (n_ptchunk * 4)
     double *d_scal; double *h_scal; // NSCAL doubles (h_scal pinned)
+    int tr_fused;                   // trust region: scalars of a step from six inner products, one read-back (host_drivers.cpp); 0: explicit vectors
     int *h_status;                  // pinned copy of d_status[0] read with the step scalars
     // ---- TR vectors (local layout [N | 3n])
     double *P_U, *P_B, *P;
@@ -207,6 +208,9 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
 void psba_launch_newp(psba_ctx *c);
 // ---- vector helpers (kernels_backsub.cu)
 void psba_launch_dots(psba_ctx *c, const double *x, const double *y, const double *z, double out[6]);
+// the same sums left in d_scal[off..off+12) (camera part, point part) / d_scal[off..off+3): no read-back, no host round trip
+void psba_enqueue_dots(psba_ctx *c, const double *x, const double *y, const double *z, int off);
+void psba_enqueue_Jdot(psba_ctx *c, const double *x, const double *y, double *Jx_out, int off);
 void psba_launch_axpby(psba_ctx *c, double a, const double *x, double b, const double *y, double *out);
 double psba_launch_maxdiag(psba_ctx *c);
 // ---- comm.cu
