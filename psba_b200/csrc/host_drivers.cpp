@@ -251,8 +251,7 @@ static int psba_trust_region_fused(psba_ctx *c, double *finalErr)
                 }
             }
             // ---- candidate = p + P, actual cost (:184-194)
-            psba_launch_axpby(c, cU * alpha, c->g, cB, c->P_B, c->dp);
-            psba_launch_newp(c);
+            psba_launch_step_newp(c, cU * alpha, c->g, cB, c->P_B);
             act_ex_L2 = psba_launch_cost(c, 1 - c->cur, nullptr);
             if (fabs((ex_L2 - act_ex_L2) / ex_L2) < PSBA_EPSILON2) { iter_flag = PSBA_ITER_DP_NO_CHANGE; break; }
             // ---- predicted cost (:208-212)

@@ -459,6 +459,27 @@ __global__ void k_newp(int n, const double *__restrict__ a, const double *__rest
     if (k < n) out[k] = a[k] + d[k];
 }
 
+// dp = a x + b y over [N | 3n] and the candidate parameters p + dp in the same pass (trust-region radius try: one launch
+// instead of k_axpby + two k_newp); the products are formed exactly as k_axpby and k_newp form them
+__global__ void k_step_newp(int N, int n3, double a, const double *__restrict__ x, double b, const double *__restrict__ y, double *__restrict__ dp,
+                            const double *__restrict__ cams, const double *__restrict__ pts, double *__restrict__ cams_new, double *__restrict__ pts_new)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= N + n3) return;
+    const double d = a * x[k] + b * y[k];
+    dp[k] = d;
+    if (k < N) cams_new[k] = cams[k] + d; else pts_new[k - N] = pts[k - N] + d;
+}
+
+void psba_launch_step_newp(psba_ctx *c, double a, const double *x, double b, const double *y)
+{
+    const int cur = c->cur, nw = 1 - cur, tot = c->N + 3 * c->n;
+    PROF(c, KID_VEC) k_step_newp<<<cdiv(tot, 256), 256, 0, c->stream>>>(c->N, 3 * c->n, a, x, b, y, c->dp, c->cams[cur], c->pts[cur], c->cams[nw], c->pts[nw]);
+    c->cache_valid[nw] = false;
+    c->st_launches += 1;
+    LAUNCH_CHECK();
+}
+
 void psba_launch_newp(psba_ctx *c)
 {
     const int cur = c->cur, nw = 1 - cur;
@@ -472,39 +493,48 @@ void psba_launch_newp(psba_ctx *c)
 // ---------------------------------------------------------------------------------------------
 // all pairwise dot products of up to three [N | 3n] vectors: out = {xx, xy, xz, yy, yz, zz}.
 // Camera part (replicated across ranks) and point part (sharded) are reduced separately.
-__global__ void __launch_bounds__(256) k_dots(int n, const double *__restrict__ x, const double *__restrict__ y,
-                                              const double *__restrict__ z, double *__restrict__ part)
+// camera part (block 0: the first N entries) and point part (the other blocks) of the three vectors in ONE launch;
+// partials: part[0..6) camera, part[8 + 6 b ..) point block b
+__global__ void __launch_bounds__(256) k_dots2(int N, int np, const double *__restrict__ x, const double *__restrict__ y,
+                                               const double *__restrict__ z, double *__restrict__ part)
 {
     __shared__ double sh[16 * (256 + 4)];
     double v[6] = {0, 0, 0, 0, 0, 0};
-    for (int k = blockIdx.x * 256 + threadIdx.x; k < n; k += gridDim.x * 256) {
-        const double a = x[k], b = y[k], cc = z[k];
-        v[0] += a * a; v[1] += a * b; v[2] += a * cc; v[3] += b * b; v[4] += b * cc; v[5] += cc * cc;
+    if (blockIdx.x == 0) {
+        for (int k = threadIdx.x; k < N; k += 256) {
+            const double a = x[k], b = y[k], cc = z[k];
+            v[0] += a * a; v[1] += a * b; v[2] += a * cc; v[3] += b * b; v[4] += b * cc; v[5] += cc * cc;
+        }
+        block_reduce_to<6, 256, 16>(v, sh, part);
+    } else {
+        const int nb = gridDim.x - 1;
+        for (int k = (blockIdx.x - 1) * 256 + threadIdx.x; k < np; k += nb * 256) {
+            const double a = x[N + k], b = y[N + k], cc = z[N + k];
+            v[0] += a * a; v[1] += a * b; v[2] += a * cc; v[3] += b * b; v[4] += b * cc; v[5] += cc * cc;
+        }
+        block_reduce_to<6, 256, 16>(v, sh, part + 8 + (size_t)(blockIdx.x - 1) * 6);
     }
-    block_reduce_to<6, 256, 16>(v, sh, part + (size_t)blockIdx.x * 6);
 }
-
-__global__ void k_final_reduce6(const double *__restrict__ part, int nparts, double *__restrict__ out)
+// out[0..6) = camera partial, out[6..12) = fixed-order sum of the point partials
+__global__ void k_final_reduce6x2(const double *__restrict__ part, int nparts, double *__restrict__ out)
 {
-    int v = threadIdx.x;
-    if (v >= 6) return;
-    double s = 0.0;
+    const int v = threadIdx.x;
+    if (v < 6) out[v] = part[v];
+    else if (v < 12) {
+        double s = 0.0;
 #pragma unroll 8
-    for (int p = 0; p < nparts; ++p) s += part[(size_t)p * 6 + v];      // same order; the loads of eight partials fly together
-    out[v] = s;
+        for (int p = 0; p < nparts; ++p) s += part[8 + (size_t)p * 6 + (v - 6)];
+        out[v] = s;
+    }
 }
 
 void psba_enqueue_dots(psba_ctx *c, const double *x, const double *y, const double *z, int off)
 {
-    // camera part
-    k_dots<<<1, 256, 0, c->stream>>>(c->N, x, y, z, c->d_part);
-    k_final_reduce6<<<1, 32, 0, c->stream>>>(c->d_part, 1, c->d_scal + off);
-    // point part
     const int np = 3 * c->n;
-    int nb = np > 0 ? std::min(cdiv(np, 256), 296) : 0;
-    if (nb > 0) k_dots<<<nb, 256, 0, c->stream>>>(np, x + c->N, y + c->N, z + c->N, c->d_part + 8);
-    k_final_reduce6<<<1, 32, 0, c->stream>>>(c->d_part + 8, nb, c->d_scal + off + 6);
-    c->st_launches += 4;
+    const int nb = np > 0 ? std::min(cdiv(np, 256), 296) : 0;
+    k_dots2<<<1 + nb, 256, 0, c->stream>>>(c->N, np, x, y, z, c->d_part);
+    k_final_reduce6x2<<<1, 32, 0, c->stream>>>(c->d_part, nb, c->d_scal + off);
+    c->st_launches += 2;
     LAUNCH_CHECK();
     if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal + off + 6, 6);
 }

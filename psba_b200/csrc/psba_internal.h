@@ -206,6 +206,7 @@ int psba_launch_pcg(psba_ctx *c);            // dp[0..N) = S^-1 eab[0..N) by blo
 // ---- kernels_backsub.cu
 void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result *res);
 void psba_launch_newp(psba_ctx *c);
+void psba_launch_step_newp(psba_ctx *c, double a, const double *x, double b, const double *y);   // dp = a x + b y and p + dp -> candidate set
 // ---- vector helpers (kernels_backsub.cu)
 void psba_launch_dots(psba_ctx *c, const double *x, const double *y, const double *z, double out[6]);
 // the same sums left in d_scal[off..off+12) (camera part, point part) / d_scal[off..off+3): no read-back, no host round trip
