@@ -171,6 +171,8 @@ void psba_trace_get(psba_ctx *ctx, int k, psba_trace_rec *rec);
  * "tr_fused" (1: psba_trust_region takes the scalars of a step -- pUpU, pUg, pBpB, pBg, |P|, the dog-leg quadratic, g.P, |JP|^2,
  * PSBA/trust_region.cpp:125-130,166-176,208-212,520-595 -- from six inner products of g and P_B computed once per step, one host
  * round trip per step and one per radius try; 0: every scalar from the explicit vectors, as the reference does),
+ * "seq_graphs" (-1 auto: on one GPU and up to 2 M observations; 0 / 1: an LM try, a linearisation, a trust-region step and a radius try --
+ * chains of launches without a host round trip -- run as CUDA graphs from their third use on; the damping term travels in device memory),
  * "trace_reset" (forget the run log), "stats_reset", "profile" (per-kernel CUDA-event timing), "timer_start"; unknown names abort. */
 void psba_set_option(psba_ctx *ctx, const char *name, double value);
 double psba_get_stat(psba_ctx *ctx, const char *name);

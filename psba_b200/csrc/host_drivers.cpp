@@ -36,7 +36,7 @@ extern "C" int psba_levmar(psba_ctx *c, int cnp, int pnp, int mnp, int n3Dpts, i
     c->initErr = ex_L2;
     iter_flag = PSBA_ITER_CONTINUE;
     for (; c->itno < c->max_iter && iter_flag == PSBA_ITER_CONTINUE; c->itno++) {
-        psba_launch_linearize(c, 1.0, 1.0);                       // levmar.cpp:103-108
+        if (psba_seq_begin(c, SEQ_LIN_LM, 0.0, 0.0, 0.0)) { psba_launch_linearize(c, 1.0, 1.0); psba_seq_end(c); }   // levmar.cpp:103-108
         if (first) {                                              // levmar.cpp:114-120
             mu = tau * psba_launch_maxdiag(c);
             first = false; p_L2 = 1e+3; nu = 2;
@@ -168,15 +168,18 @@ static int psba_trust_region_fused(psba_ctx *c, double *finalErr)
     ex_L2 = psba_launch_cost(c, c->cur, nullptr);                 // trust_region.cpp:106-107
     iter_flag = PSBA_ITER_CONTINUE;
     for (; c->itno < c->max_iter; c->itno++) {
-        psba_launch_linearize(c, 2.0, -2.0);                      // :117-122, 133-137
+        if (psba_seq_begin(c, SEQ_LIN_TR, 0.0, 0.0, 0.0)) { psba_launch_linearize(c, 2.0, -2.0); psba_seq_end(c); }   // :117-122, 133-137
         double JgJg = 0, JgJB = 0, JBJB = 0, gg = 0, gB = 0, BB = 0;
         bool solved = false;
         while (!solved) {                                         // :141-163 with compute_PB (:292-405) inlined
-            enqueue_PB(c, lambda);
-            psba_enqueue_Jdot(c, c->g, c->P_B, nullptr, 16);      // |J g|^2, Jg.JP_B, |J P_B|^2
-            psba_enqueue_dots(c, c->g, c->P_B, c->g, 20);         // g.g, g.P_B, ., P_B.P_B (camera part, point part)
-            CUDA_CHECK(cudaMemcpyAsync(c->h_scal + 16, c->d_scal + 16, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-            CUDA_CHECK(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            if (psba_seq_begin(c, SEQ_TR_STEP, lambda, 0.0, 0.0)) {   // one chain; a CUDA graph from its third use on (small problems)
+                enqueue_PB(c, lambda);
+                psba_enqueue_Jdot(c, c->g, c->P_B, nullptr, 16);  // |J g|^2, Jg.JP_B, |J P_B|^2
+                psba_enqueue_dots(c, c->g, c->P_B, c->g, 20);     // g.g, g.P_B, ., P_B.P_B (camera part, point part)
+                CUDA_CHECK(cudaMemcpyAsync(c->h_scal + 16, c->d_scal + 16, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                CUDA_CHECK(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+                psba_seq_end(c);
+            }
             CUDA_CHECK(cudaStreamSynchronize(c->stream));
             const int st = c->h_status[0];
             if (st > 1) { fprintf(stderr, "psba_b200: camera solve failed with status %d (broken dataflow schedule)\n", st); exit(EXIT_FAILURE); }
@@ -251,8 +254,14 @@ static int psba_trust_region_fused(psba_ctx *c, double *finalErr)
                 }
             }
             // ---- candidate = p + P, actual cost (:184-194)
-            psba_launch_step_newp(c, cU * alpha, c->g, cB, c->P_B);
-            act_ex_L2 = psba_launch_cost(c, 1 - c->cur, nullptr);
+            if (psba_seq_begin(c, SEQ_TR_RADIUS, 0.0, cU * alpha, cB)) {
+                psba_launch_step_newp(c, cU * alpha, c->g, cB, c->P_B);
+                psba_enqueue_cost(c, 1 - c->cur, nullptr);
+                CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                psba_seq_end(c);
+            }
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            act_ex_L2 = c->h_scal[0];
             if (fabs((ex_L2 - act_ex_L2) / ex_L2) < PSBA_EPSILON2) { iter_flag = PSBA_ITER_DP_NO_CHANGE; break; }
             // ---- predicted cost (:208-212)
             const double Jx_norm = cU * cU * pUtBpU + 2 * cU * cB * pUtBpB + cB * cB * pBtBpB;

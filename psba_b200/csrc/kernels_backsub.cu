@@ -11,8 +11,9 @@
 
 // candidate cameras = cams + dpa, plus the camera part of the step scalars
 __global__ void __launch_bounds__(1024) k_newcams(int N, const double *__restrict__ cams, const double *__restrict__ dpa, const double *__restrict__ ga,
-                                                  double mu, double *__restrict__ newcams, double *__restrict__ scal3)
+                                                  const double *__restrict__ mu_p, double *__restrict__ newcams, double *__restrict__ scal3)
 {
+    const double mu = __ldg(mu_p);                               // damping term of this solve (device-resident: psba_set_scalars)
     // one CTA on the critical path of every try: 1024 threads so that the N = 6m entries are a dozen independent
     // loads per thread (25 us with 256 threads on 2 000 cameras); fixed-order tree
     __shared__ double s0[1024], s1[1024], s2[1024];
@@ -48,10 +49,11 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ c
                                                       const double *__restrict__ impts, const double *__restrict__ W,
                                                       const double *__restrict__ Vinv, const double *__restrict__ gb,
                                                       const double *__restrict__ dpa, const double *__restrict__ pts,
-                                                      const double *__restrict__ newcache, double mu,
+                                                      const double *__restrict__ newcache, const double *__restrict__ mu_p,
                                                       double *__restrict__ eb, double *__restrict__ dpb, double *__restrict__ newpts,
                                                       double *__restrict__ part, psba_ext ext)
 {
+    const double mu = __ldg(mu_p);
     __shared__ __align__(16) double stage[PT_CTA * 18];      // W tile of the wave, then the projection entries (128*14 <= 128*18)
     double *pstage = stage;
     __shared__ double sh[3][PT_CTA];
@@ -226,10 +228,11 @@ __global__ void __launch_bounds__(PT_CTA, 3) k_backsub_pipe(int n_list, const in
                                                            const int *__restrict__ jidx, const double *__restrict__ impts,
                                                            const double *__restrict__ W, const double *__restrict__ Vinv,
                                                            const double *__restrict__ gb, const double *__restrict__ dpa,
-                                                           const double *__restrict__ pts, const double *__restrict__ newcache, double mu,
+                                                           const double *__restrict__ pts, const double *__restrict__ newcache, const double *__restrict__ mu_p,
                                                            double *__restrict__ eb, double *__restrict__ dpb, double *__restrict__ newpts,
                                                            double *__restrict__ part)
 {
+    const double mu = __ldg(mu_p);
     extern __shared__ __align__(128) double dyn[];             // two W tiles (TMA destinations), then two entry stages
     double *wtile = dyn, *pstage = dyn + 2 * PT_CTA * 18;
     __shared__ __align__(8) unsigned long long bar[2];
@@ -403,8 +406,12 @@ __global__ void __launch_bounds__(1024) k_final_reduce4(const double *__restrict
 
 // evaluate=true : dp (cams+points), candidate parameters, candidate cost, step scalars (LM try)
 // evaluate=false: eb and dpb only (trust region / compat)
-void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result *res)
+// everything of the back-substitution up to (and with) the copies of the step scalars and the status word to the host:
+// no host round trip (the caller synchronises; psba_finish_try reads)
+void psba_enqueue_backsub(psba_ctx *c, double mu_value, bool evaluate)
 {
+    psba_set_scalars(c, mu_value, 0.0, 0.0);
+    const double *mu = c->d_mu;
     const int cur = c->cur, nw = 1 - cur;
     double *gb = c->g + c->N, *ebp = c->eab + c->N, *dpbp = c->dp + c->N;
     if (evaluate) {
@@ -435,13 +442,6 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
         if (c->nranks > 1) psba_allreduce_sum(c, c->d_scal, 4);
         CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        if (res) {
-            res->cost_new = c->h_scal[0];
-            res->dp_L2 = c->h_scal[4] + c->h_scal[1];      // cameras first, then points (misc.cpp:151-157 order)
-            res->dp_dot = c->h_scal[5] + c->h_scal[2];
-            res->p_new_L2 = c->h_scal[6] + c->h_scal[3];   // ||candidate parameters||^2
-        }
     } else {
         if (c->n_ptchunk > 0)
             PROF(c, KID_BACKSUB) k_backsub<false, false><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(nullptr, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->W, c->Vinv,
@@ -450,6 +450,23 @@ void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result 
         c->st_launches += 1;
         LAUNCH_CHECK();
     }
+}
+
+void psba_finish_try(psba_ctx *c, psba_try_result *res)
+{
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (res) {
+        res->cost_new = c->h_scal[0];
+        res->dp_L2 = c->h_scal[4] + c->h_scal[1];      // cameras first, then points (misc.cpp:151-157 order)
+        res->dp_dot = c->h_scal[5] + c->h_scal[2];
+        res->p_new_L2 = c->h_scal[6] + c->h_scal[3];   // ||candidate parameters||^2
+    }
+}
+
+void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result *res)
+{
+    psba_enqueue_backsub(c, mu, evaluate);
+    if (evaluate) psba_finish_try(c, res);
 }
 
 // new = cur + dp for an externally supplied step in c->dp (compute_newp.cl:6-26)
@@ -461,11 +478,12 @@ __global__ void k_newp(int n, const double *__restrict__ a, const double *__rest
 
 // dp = a x + b y over [N | 3n] and the candidate parameters p + dp in the same pass (trust-region radius try: one launch
 // instead of k_axpby + two k_newp); the products are formed exactly as k_axpby and k_newp form them
-__global__ void k_step_newp(int N, int n3, double a, const double *__restrict__ x, double b, const double *__restrict__ y, double *__restrict__ dp,
+__global__ void k_step_newp(int N, int n3, const double *__restrict__ coef, const double *__restrict__ x, const double *__restrict__ y, double *__restrict__ dp,
                             const double *__restrict__ cams, const double *__restrict__ pts, double *__restrict__ cams_new, double *__restrict__ pts_new)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= N + n3) return;
+    const double a = __ldg(coef + 1), b = __ldg(coef + 2);       // device-resident step coefficients (psba_set_scalars)
     const double d = a * x[k] + b * y[k];
     dp[k] = d;
     if (k < N) cams_new[k] = cams[k] + d; else pts_new[k - N] = pts[k - N] + d;
@@ -474,7 +492,8 @@ __global__ void k_step_newp(int N, int n3, double a, const double *__restrict__ 
 void psba_launch_step_newp(psba_ctx *c, double a, const double *x, double b, const double *y)
 {
     const int cur = c->cur, nw = 1 - cur, tot = c->N + 3 * c->n;
-    PROF(c, KID_VEC) k_step_newp<<<cdiv(tot, 256), 256, 0, c->stream>>>(c->N, 3 * c->n, a, x, b, y, c->dp, c->cams[cur], c->pts[cur], c->cams[nw], c->pts[nw]);
+    psba_set_scalars(c, 0.0, a, b);
+    PROF(c, KID_VEC) k_step_newp<<<cdiv(tot, 256), 256, 0, c->stream>>>(c->N, 3 * c->n, c->d_mu, x, y, c->dp, c->cams[cur], c->pts[cur], c->cams[nw], c->pts[nw]);
     c->cache_valid[nw] = false;
     c->st_launches += 1;
     LAUNCH_CHECK();

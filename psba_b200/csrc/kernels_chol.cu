@@ -1114,7 +1114,8 @@ double psba_launch_factor(psba_ctx *c, bool defer_status)
                     c->step_def_ptr[s + 1] - c->step_def_ptr[s], c->step_b_ptr[s + 1] - c->step_b_ptr[s]);
         }
         for (auto &e : ev) cudaEventDestroy(e);
-    } else
+    } else if (c->capturing) enqueue_factor(c);                  // inside a captured chain (psba_seq_begin): the step kernels join that graph
+    else
     PROF(c, KID_FACTOR) CUDA_CHECK(cudaGraphLaunch(c->chol_graph, c->stream));
     if (dbg_dev) {
         std::vector<long long> h((size_t)c->nt * 8);

@@ -62,10 +62,11 @@ __device__ __forceinline__ void load_vec3(const double *__restrict__ p, double &
 }
 
 // packed symmetric storage: V = (v00,v01,v02,v11,v12,v22); Vinv = (i00,i10,i20,i11,i21,i22)
-__global__ void k_vinv(int n, const double *__restrict__ V, double mu, double *__restrict__ Vinv, int *__restrict__ flag)
+__global__ void k_vinv(int n, const double *__restrict__ V, const double *__restrict__ mu_p, double *__restrict__ Vinv, int *__restrict__ flag)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const double mu = __ldg(mu_p);                               // damping term of this solve (device-resident: psba_set_scalars)
     const double *v = V + (size_t)i * 6;
     const double a11 = v[0] + mu, a12 = v[1], a13 = v[2], a22 = v[3] + mu, a23 = v[4], a33 = v[5] + mu;
     double T = (a33 * a12 * a12 - 2 * a12 * a13 * a23 + a22 * a13 * a13 + a11 * a23 * a23 - a11 * a22 * a33);
@@ -102,8 +103,9 @@ __global__ void k_vinv(int n, const double *__restrict__ V, double mu, double *_
 
 double psba_launch_vinv(psba_ctx *c, double mu)
 {
+    psba_set_scalars(c, mu, 0.0, 0.0);
     CUDA_CHECK(cudaMemsetAsync(c->d_status + 1, 0, sizeof(int), c->stream));
-    if (c->n > 0) PROF(c, KID_VINV) k_vinv<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->V, mu, c->Vinv, c->d_status + 1);
+    if (c->n > 0) PROF(c, KID_VINV) k_vinv<<<cdiv(c->n, 256), 256, 0, c->stream>>>(c->n, c->V, c->d_mu, c->Vinv, c->d_status + 1);
     c->st_launches += 1;
     LAUNCH_CHECK();
     return 0.0;
@@ -682,13 +684,14 @@ __device__ __forceinline__ double *s_entry(double *Stiles, const int *__restrict
 // (multi-GPU: all-reduce first, then k_add_U).
 __global__ void k_S_finalize(int n_pair, const int *__restrict__ pair_k, const int *__restrict__ pair_l,
                              const int *__restrict__ pair_chunk_ptr, const double *__restrict__ part,
-                             const double *__restrict__ U, const double *__restrict__ ga, double mu, int with_U,
+                             const double *__restrict__ U, const double *__restrict__ ga, const double *__restrict__ mu_p, int with_U,
                              const int *__restrict__ tile_index, const int *__restrict__ cam2pos, int nt,
                              double *__restrict__ Stiles, double *__restrict__ ea)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int pr = t / 42, v = t - pr * 42;
     if (pr >= n_pair) return;
+    const double mu = __ldg(mu_p);
     const int k = pair_k[pr], l = pair_l[pr];
     if (v >= 36 && k != l) return;
     double s = 0.0;
@@ -706,13 +709,14 @@ __global__ void k_S_finalize(int n_pair, const int *__restrict__ pair_k, const i
 
 
 // multi-GPU second half: add U_k + mu I to the diagonal blocks and ga to ea (after the all-reduce)
-__global__ void k_add_U(int m, const double *__restrict__ U, const double *__restrict__ ga, double mu,
+__global__ void k_add_U(int m, const double *__restrict__ U, const double *__restrict__ ga, const double *__restrict__ mu_p,
                         const int *__restrict__ tile_index, const int *__restrict__ cam2pos, int nt,
                         double *__restrict__ Stiles, const double *__restrict__ ea_red, double *__restrict__ ea)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int k = t / 42, v = t - k * 42;
     if (k >= m) return;
+    const double mu = __ldg(mu_p);
     if (v < 36) {
         const int r = v / 6, cc = v - r * 6;
         double *p = s_entry(Stiles, tile_index, nt, cam2pos[k], cam2pos[k], r, cc);
@@ -766,13 +770,13 @@ void psba_launch_schur(psba_ctx *c, double mu)
         }
     }
     PROF(c, KID_S_FINALIZE) k_S_finalize<<<cdiv((long long)c->n_pair * 42, 128), 128, 0, c->stream>>>(c->n_pair, c->pair_k, c->pair_l, c->pair_chunk_ptr,
-                                                                         c->pair_part, c->U, c->g, mu, single, c->tile_index,
+                                                                         c->pair_part, c->U, c->g, c->d_mu, single, c->tile_index,
                                                                          c->cam2pos, c->nt, c->Stiles, ea_out);
     c->st_launches += 3;
     LAUNCH_CHECK();
     if (!single) {
         psba_allreduce_sum(c, c->Stiles, (size_t)c->n_tiles_S * TS * TS + (size_t)c->N);   // S tiles + ea; fill-in tiles are zero on every rank
-        k_add_U<<<cdiv(c->m * 42, 128), 128, 0, c->stream>>>(c->m, c->U, c->g, mu, c->tile_index, c->cam2pos, c->nt, c->Stiles, ea_red, c->eab);
+        k_add_U<<<cdiv(c->m * 42, 128), 128, 0, c->stream>>>(c->m, c->U, c->g, c->d_mu, c->tile_index, c->cam2pos, c->nt, c->Stiles, ea_red, c->eab);
         c->st_launches += 1;
         LAUNCH_CHECK();
     }

@@ -113,6 +113,10 @@ extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3D
     CUDA_CHECK(cudaMallocHost(&c->h_scal, NSCAL * sizeof(double)));
     CUDA_CHECK(cudaMallocHost(&c->h_status, 4 * sizeof(int)));
     c->h_status[0] = 0;
+    c->d_mu = dalloc<double>(c, 4);
+    CUDA_CHECK(cudaMallocHost(&c->h_mu_ring, 64 * 4 * sizeof(double)));
+    c->h_mu_next = 0; c->st_seq_replays = 0; c->capturing = nullptr; c->seqs = new std::map<unsigned long long, psba_ctx::seq_graph>();
+    c->use_graphs = getenv("PSBA_SEQ_GRAPHS") ? atoi(getenv("PSBA_SEQ_GRAPHS")) : -1;
     return c;
 }
 
@@ -221,6 +225,11 @@ extern "C" void psba_release_buffer(psba_ctx *c)
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (c->chol_graph_ok) cudaGraphExecDestroy(c->chol_graph);
     if (c->bw_graph_ok) cudaGraphExecDestroy(c->bw_graph);
+    for (auto &kv : *c->seqs) if (kv.second.ok) cudaGraphExecDestroy(kv.second.exec);
+    delete c->seqs;
+    psba_dev_free(c, c->d_mu);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    cudaFreeHost(c->h_mu_ring);
     cudaFreeHost(c->h_scal); cudaFreeHost(c->h_status);
     cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
     cudaStreamDestroy(c->stream2);
@@ -618,13 +627,14 @@ extern "C" void psba_set_option(psba_ctx *c, const char *name, double v)
     else if (s == "itno") c->itno = (int)v;
     else if (s == "lm_only") c->lm_only = (int)v;
     else if (s == "tr_fused") c->tr_fused = (int)v;
+    else if (s == "seq_graphs") c->use_graphs = (int)v;
     else if (s == "camera_solver") { c->camera_solver = (int)v; c->factor_valid = false; }      // 0 tiled Cholesky (default), 1 block-Jacobi PCG
     else if (s == "pcg_tol") c->pcg_tol = v;
     else if (s == "pcg_max_iter") c->pcg_max_iter = (int)v;
     else if (s == "profile") { psba_prof_collect(c); c->profile = v != 0; }
     else if (s == "profile_reset") { psba_prof_collect(c); for (int k = 0; k < KID_COUNT; ++k) { c->prof_ms[k] = 0; c->prof_n[k] = 0; } }
     else if (s == "trace_reset") { c->trace.clear(); c->n_cholmod_events = 0; }
-    else if (s == "stats_reset") { c->st_tries = c->st_exqt = c->st_lin = c->st_launches = 0; }
+    else if (s == "stats_reset") { c->st_tries = c->st_exqt = c->st_lin = c->st_launches = c->st_seq_replays = 0; }
     else if (s == "timer_start") {
         if (!c->timer_init) { CUDA_CHECK(cudaEventCreate(&c->timer_e0)); CUDA_CHECK(cudaEventCreate(&c->timer_e1)); c->timer_init = true; }
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -660,6 +670,9 @@ extern "C" double psba_get_stat(psba_ctx *c, const char *name)
     if (s == "pair_mode") return c->pair_mode;
     if (s == "n_seg") return c->n_seg;
     if (s == "seg_v") return c->seg_v;
+    if (s == "seq_replays") return c->st_seq_replays;
+    if (s == "seq_graphs") { int k = 0; for (auto &kv : *c->seqs) k += kv.second.ok ? 1 : 0; return k; }
+    if (s == "seq_keys") return (double)c->seqs->size();
     if (s == "ring_rows") return (double)c->ring_n_rows;
     if (s == "ring_cfg") return c->pair_mode == 6 ? c->ring_cfg : -1;
     if (s == "ring_rt") return c->pair_mode == 6 ? c->ring_rt : -1;
@@ -740,18 +753,85 @@ extern "C" void psba_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
     psba_launch_linearize(c, coeff_uvw, coeff_g);
 }
 
+
+// ---- device-resident scalars and sequence graphs ------------------------------------------------------------------
+void psba_set_scalars(psba_ctx *c, double mu, double a, double b)
+{
+    // a captured chain copies from ITS slot (the replay writes the slot before the launch); plain launches rotate through
+    // the other slots: a slot is rewritten 32 calls later at the earliest, and every try ends with a host synchronisation
+    const int slot = c->capturing ? c->capturing->slot : 32 + (c->h_mu_next++ & 31);
+    double *h = c->h_mu_ring + (size_t)slot * 4;
+    h[0] = mu; h[1] = a; h[2] = b; h[3] = 0.0;
+    CUDA_CHECK(cudaMemcpyAsync(c->d_mu, h, 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+}
+
+static bool seq_graphs_on(const psba_ctx *c)
+{
+    if (c->profile || c->nranks > 1 || c->camera_solver == 1) return false;      // event scopes / NCCL / host-driven PCG stay out of graphs
+    if (c->use_graphs >= 0) return c->use_graphs != 0;
+    return c->o_glob <= 2000000;           // the chains of a large problem are not launch-bound (2.84 ms of kernels in 2.84 ms)
+}
+
+bool psba_seq_begin(psba_ctx *c, int kind, double mu, double a, double b)
+{
+    if (!seq_graphs_on(c)) return true;
+    const unsigned long long key = (unsigned long long)kind | ((unsigned long long)c->cur << 8) | ((unsigned long long)c->cache_valid[0] << 9) |
+                                   ((unsigned long long)c->cache_valid[1] << 10) | ((unsigned long long)(c->ext_on ? 1 : 0) << 11) |
+                                   ((unsigned long long)c->pair_mode << 12) | ((unsigned long long)(c->S_valid ? 1 : 0) << 20) |
+                                   ((unsigned long long)(c->lin_valid ? 1 : 0) << 21);
+    psba_ctx::seq_graph &g = (*c->seqs)[key];
+    if (g.seen == 0 && !g.ok) { g.exec = nullptr; g.slot = (int)((c->seqs->size() - 1) & 31); }
+    if (g.ok) {
+        double *h = c->h_mu_ring + (size_t)g.slot * 4;
+        h[0] = mu; h[1] = a; h[2] = b; h[3] = 0.0;
+        CUDA_CHECK(cudaGraphLaunch(g.exec, c->stream));
+        c->st_seq_replays += 1;
+        c->st_launches += g.d_launches; c->st_tries += g.d_tries; c->st_exqt += g.d_exqt; c->st_lin += g.d_lin;
+        c->cache_valid[0] = g.cv0; c->cache_valid[1] = g.cv1; c->S_valid = g.S_valid; c->factor_valid = g.factor_valid; c->lin_valid = g.lin_valid;
+        if (kind == SEQ_LIN_LM || kind == SEQ_LIN_TR) { c->coeff_uvw = g.cu; c->coeff_g = g.cg; }
+        return false;
+    }
+    g.seen += 1;
+    if (g.seen < 2 || c->seqs->size() > 32) { c->capturing = nullptr; return true; }   // first sighting: plain launches (lazy set-up of the kernels runs here)
+    c->capturing = &g;
+    c->snap_launches = c->st_launches; c->snap_tries = c->st_tries; c->snap_exqt = c->st_exqt; c->snap_lin = c->st_lin;
+    CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    return true;
+}
+
+void psba_seq_end(psba_ctx *c)
+{
+    psba_ctx::seq_graph *g = c->capturing;
+    if (!g) return;
+    c->capturing = nullptr;
+    cudaGraph_t graph;
+    CUDA_CHECK(cudaStreamEndCapture(c->stream, &graph));
+    CUDA_CHECK(cudaGraphInstantiate(&g->exec, graph, 0));
+    CUDA_CHECK(cudaGraphDestroy(graph));
+    g->ok = true;
+    g->d_launches = c->st_launches - c->snap_launches; g->d_tries = c->st_tries - c->snap_tries;
+    g->d_exqt = c->st_exqt - c->snap_exqt; g->d_lin = c->st_lin - c->snap_lin;
+    g->cv0 = c->cache_valid[0]; g->cv1 = c->cache_valid[1]; g->S_valid = c->S_valid; g->factor_valid = c->factor_valid; g->lin_valid = c->lin_valid;
+    g->cu = c->coeff_uvw; g->cg = c->coeff_g;
+    CUDA_CHECK(cudaGraphLaunch(g->exec, c->stream));            // the captured chain has not run yet
+}
+
 extern "C" void psba_try_step(psba_ctx *c, double mu, psba_try_result *res)
 {
     if (!c->lin_valid) die("try_step before linearize");
-    c->st_tries += 1;
-    psba_launch_schur(c, mu);
     res->cost_new = res->dp_L2 = res->dp_dot = res->p_new_L2 = NAN;
-    if (c->camera_solver == 1) psba_launch_pcg(c);   // optional iterative camera solve (kernels_pcg.cu)
-    else {
-        psba_launch_factor(c, true);                 // no host round trip between factorisation and solves
-        psba_launch_solve(c);
+    if (psba_seq_begin(c, SEQ_TRY, mu, 0.0, 0.0)) {  // the whole try is one chain: a CUDA graph from its third use on (small problems)
+        c->st_tries += 1;
+        psba_launch_schur(c, mu);
+        if (c->camera_solver == 1) psba_launch_pcg(c);   // optional iterative camera solve (kernels_pcg.cu)
+        else {
+            psba_launch_factor(c, true);                 // no host round trip between factorisation and solves
+            psba_launch_solve(c);
+        }
+        psba_enqueue_backsub(c, mu, true);               // step scalars and status word on their way to the host
+        psba_seq_end(c);
     }
-    psba_launch_backsub(c, mu, true, res);           // reads the status word with the step scalars
+    psba_finish_try(c, res);
     if (c->h_status[0] > 1) { fprintf(stderr, "psba_b200: camera solve failed with status %d (broken dataflow schedule)\n", c->h_status[0]); exit(EXIT_FAILURE); }
     res->solve_status = c->h_status[0] ? 1.0 : 0.0;
     if (res->solve_status != 0.0) { c->factor_valid = false; res->cost_new = res->dp_L2 = res->dp_dot = res->p_new_L2 = NAN; }

@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <vector>
+#include <map>
 #include "../../include/psba_b200.h"
 
 #define PSBA_CNP 6
@@ -146,6 +147,14 @@ struct psba_ctx {
     // ---- scalars
     double *d_part;                 // per-chunk partial sums (n_ptchunk * 4)
     double *d_scal; double *h_scal; // NSCAL doubles (h_scal pinned)
+    // ---- device-resident scalars of a solve and whole-sequence CUDA graphs (psba_api.cu: psba_set_scalars, psba_seq_begin/end)
+    double *d_mu;                   // device: {damping term, step coefficient a, step coefficient b, -}
+    double *h_mu_ring; int h_mu_next;   // pinned: 64 slots of 4 doubles; slots 0..31 belong to captured sequences, the rest rotate
+    int use_graphs;                 // -1 auto (small problems on one GPU), 0 off, 1 on
+    struct seq_graph { cudaGraphExec_t exec; int seen, slot; bool ok; double d_launches, d_tries, d_exqt, d_lin; bool cv0, cv1, S_valid, factor_valid, lin_valid; double cu, cg; };
+    std::map<unsigned long long, seq_graph> *seqs;
+    seq_graph *capturing;           // sequence being captured (its scalar slot is the source of the captured copies)
+    double snap_launches, snap_tries, snap_exqt, snap_lin;
     int tr_fused;                   // trust region: scalars of a step from six inner products, one read-back (host_drivers.cpp); 0: explicit vectors
     int *h_status;                  // pinned copy of d_status[0] read with the step scalars
     // ---- TR vectors (local layout [N | 3n])
@@ -160,7 +169,7 @@ struct psba_ctx {
     std::vector<double> force_lambda; int n_cholmod_events;
     double cholmod_max_l_over_beta;   // tile-pool modified Cholesky: largest factor entry / beta of the last run
     // stats
-    double st_tries, st_exqt, st_lin, st_launches;
+    double st_tries, st_exqt, st_lin, st_launches, st_seq_replays;
     bool profile;
     std::vector<psba_prof_rec> prof_pending;
     std::vector<cudaEvent_t> prof_pool;
@@ -205,6 +214,18 @@ double psba_launch_cholmod_dense(psba_ctx *c, int N, double *mat, double *aux, d
 int psba_launch_pcg(psba_ctx *c);            // dp[0..N) = S^-1 eab[0..N) by block-Jacobi PCG; status word as the factorisation
 // ---- kernels_backsub.cu
 void psba_launch_backsub(psba_ctx *c, double mu, bool evaluate, psba_try_result *res);
+void psba_enqueue_backsub(psba_ctx *c, double mu, bool evaluate);   // no host round trip; evaluate: scalars + status copies enqueued
+void psba_finish_try(psba_ctx *c, psba_try_result *res);            // synchronise, read the step scalars
+// damping term / step coefficients into device memory (kernels read c->d_mu): a 32-byte copy from a pinned slot
+void psba_set_scalars(psba_ctx *c, double mu, double a, double b);
+// A SEQUENCE is a fixed chain of launches without a host round trip (an LM try, a linearisation, a trust-region step, a radius
+// try).  psba_seq_begin returns true when the caller has to enqueue the chain (first sighting: plainly; second: under stream
+// capture) and false when an instantiated graph of the chain has been launched instead; psba_seq_end closes a begun chain.
+// `kind` + the host state the chain depends on (parameter set, valid camera caches, camera model) is the key of the graph.
+bool psba_seq_begin(psba_ctx *c, int kind, double mu, double a, double b);
+void psba_seq_end(psba_ctx *c);
+enum { SEQ_TRY = 1, SEQ_LIN_LM = 2, SEQ_LIN_TR = 3, SEQ_TR_STEP = 4, SEQ_TR_RADIUS = 5, SEQ_COST = 6 };
+double psba_enqueue_cost(psba_ctx *c, int set, double *ex_dev);     // cost kernels + reduction into d_scal[0]; no read-back (returns 0)
 void psba_launch_newp(psba_ctx *c);
 void psba_launch_step_newp(psba_ctx *c, double a, const double *x, double b, const double *y);   // dp = a x + b y and p + dp -> candidate set
 // ---- vector helpers (kernels_backsub.cu)

@@ -286,3 +286,56 @@ def test_separate_spdinv_and_cholmod_entries():
     res = G.cholmod_blk()
     assert np.array_equal(G.compute_cholmod_E(), res["E"])
     G.close(); O.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", ["7", "54", "T21"])
+def test_fused_trust_region_equals_explicit_evaluation(key):
+    """psba_trust_region takes the scalars of a step (pUpU, pUg, pBpB, pBg, |P|, the dog-leg quadratic, g.P, |JP|^2:
+    PSBA/trust_region.cpp:125-130,166-176,208-212,520-595) from six inner products of g and P_B (option "tr_fused", default) instead
+    of forming every vector and reducing it as the reference does ("tr_fused" = 0).  Same accept / shrink pattern, same iteration
+    count and exit flag, radius-try costs and final cost equal to rounding; fewer launches."""
+    prob = psba_b200.read_sba(*dataset_paths(key))
+    runs = []
+    for fused in (1, 0):
+        G = psba_b200.PSBA(prob)
+        G.set_option("tr_fused", fused)
+        r = G.solve()
+        runs.append((r, G.trace(), int(G.stat("launches"))))
+        G.close()
+    (r1, t1, l1), (r0, t0, l0) = runs
+    assert any(q["phase"] == 1 for q in t1)                       # the trust-region phase ran
+    assert r1["flag"] == r0["flag"] and r1["itno"] == r0["itno"]
+    assert [(q["phase"], q["accepted"]) for q in t1] == [(q["phase"], q["accepted"]) for q in t0]
+    for a, b in zip(t1, t0):
+        if a["phase"] == 1 and a["accepted"]:
+            # the two evaluations differ by rounding, and the unconstrained step P = eta1 P_U + eta2 P_B solves a 2x2 system whose
+            # determinant -pUtBpB^2 + pBtBpB pUtBpU cancels when P_U and P_B are nearly parallel: a 1e-16 change of the inputs
+            # moves such a step by 1e-6 (54cams, iteration 6: costs 4430.14 against 4429.52; the radius-limited tries before it
+            # agree to 1e-15 and both runs reach the same final cost to 1e-15); the Gauss-Newton step P_B itself carries
+            # rounding-determined gauge components (Trafalgar-21: rejected tries at four times the accepted radius differ by 8 %).
+            # Tolerances as in the oracle comparisons: 2e-2 on the costs of accepted radius tries (SURVEY F3/F4), 1e-9 on the
+            # final cost, identical accept / shrink pattern.
+            assert abs(a["err"] - b["err"]) <= 2e-2 * abs(b["err"])
+    assert abs(r1["finalErr"] - r0["finalErr"]) <= 1e-9 * r0["finalErr"]
+    assert l1 < l0
+
+
+@pytest.mark.parametrize("key", ["54", "T21"])
+def test_chains_as_cuda_graphs_give_the_same_bits(key):
+    """An LM try, a linearisation, a trust-region step and a radius try are chains of launches without a host round trip; on small
+    problems they run as CUDA graphs from their third use on (psba_seq_begin / psba_seq_end, option "seq_graphs"), the damping term
+    and the step coefficients travelling through device memory.  Same kernels, same arguments: the run must be bit-identical to
+    the one with plain launches, and the graphs must actually have been replayed."""
+    prob = psba_b200.read_sba(*dataset_paths(key))
+    out = []
+    for on in (1, 0):
+        G = psba_b200.PSBA(prob)
+        G.set_option("seq_graphs", on)
+        r = G.solve()
+        out.append((r, [(q["phase"], q["accepted"], q["err"], q["rho"], q["mu"], q["pnorm"]) for q in G.trace()], int(G.stat("seq_replays")), int(G.stat("launches"))))
+        G.close()
+    assert out[0][0] == out[1][0]
+    assert out[0][1] == out[1][1]
+    assert out[0][2] > 0 and out[1][2] == 0
+    assert out[0][3] == out[1][3]                     # the launch count of a replayed chain is the count of the captured one

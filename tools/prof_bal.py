@@ -22,8 +22,9 @@ for prof in (0, 1):
     r = G.solve()
     ms = G.stat("timer_ms")
     wall = (time.perf_counter() - t0) * 1e3
-    print("profile=%d: device span %.3f ms, wall %.3f ms, itno %d, tries %d, exqt %d, launches %d, final %.9e" %
-          (prof, ms, wall, r["itno"], int(G.stat("tries")), int(G.stat("exqt")), int(G.stat("launches")), r["finalErr"]))
+    print("profile=%d: device span %.3f ms, wall %.3f ms, itno %d, tries %d, exqt %d, launches %d, final %.9e | chains as graphs: %d keys, %d graphs, %d replays" %
+          (prof, ms, wall, r["itno"], int(G.stat("tries")), int(G.stat("exqt")), int(G.stat("launches")), r["finalErr"],
+           int(G.stat("seq_keys")), int(G.stat("seq_graphs")), int(G.stat("seq_replays"))))
 tot = 0.0
 for k in KN:
     n = G.stat("n." + k)
