@@ -223,7 +223,10 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ c
 //                       (6 x 16 B per observation) by asynchronous copies (LDGSTS) into a double-buffered stage,
 //                       the dpa rows and the per-point data (gb, Vinv, point) in registers.
 template <int DUMMY>
-__global__ void __launch_bounds__(PT_CTA, 3) k_backsub_pipe(int n_list, const int *__restrict__ chunk_list, const int4 *__restrict__ ptdesc,
+#ifndef BSUB_MINB
+#define BSUB_MINB 3
+#endif
+__global__ void __launch_bounds__(PT_CTA, BSUB_MINB) k_backsub_pipe(int n_list, const int *__restrict__ chunk_list, const int4 *__restrict__ ptdesc,
                                                            const int *__restrict__ pt_ptr, const int *__restrict__ iidx,
                                                            const int *__restrict__ jidx, const double *__restrict__ impts,
                                                            const double *__restrict__ W, const double *__restrict__ Vinv,
@@ -421,7 +424,7 @@ void psba_enqueue_backsub(psba_ctx *c, double mu_value, bool evaluate)
         PROF(c, KID_BACKSUB) {
             const int dyn = 2 * PT_CTA * (18 + PROJ_LD) * (int)sizeof(double);
             psba_set_smem((const void *)k_backsub_pipe<0>, dyn);
-            int gs = std::min(c->n_small, c->n_sm * 3);      // persistent CTAs: one partial each
+            int gs = std::min(c->n_small, c->n_sm * BSUB_MINB);      // persistent CTAs: one partial each
             if (c->ext_on) {       // extended camera model: the one-shot kernel evaluates the candidate (one partial per chunk)
                 gs = c->n_ptchunk;
                 if (gs > 0)

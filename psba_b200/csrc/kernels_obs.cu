@@ -257,7 +257,10 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_lin_points(const int *__restrict_
 // and the W tile (contiguous in HBM: observations are point-major) leaves with ONE bulk store (TMA) out of the
 // stage half its camera entries came in, instead of a copy-out loop through the load/store unit.
 template <int DUMMY>
-__global__ void __launch_bounds__(PT_CTA, 3) k_lin_points_pipe(int n_list, const int *__restrict__ chunk_list, const int4 *__restrict__ ptdesc,
+#ifndef LINP_MINB
+#define LINP_MINB 3
+#endif
+__global__ void __launch_bounds__(PT_CTA, LINP_MINB) k_lin_points_pipe(int n_list, const int *__restrict__ chunk_list, const int4 *__restrict__ ptdesc,
                                                               const int *__restrict__ pt_ptr, const int *__restrict__ iidx,
                                                               const int *__restrict__ jidx, const double *__restrict__ impts,
                                                               const double *__restrict__ cache, const double *__restrict__ pts,
@@ -468,7 +471,7 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
                                                                     coeff_uvw, coeff_g, c->W, c->V, c->g + c->N, c->ext);
             else {
                 if (c->n_small > 0)
-                    k_lin_points_pipe<0><<<std::min(c->n_small, c->n_sm * 3), PT_CTA, dyn, c->stream>>>(c->n_small, c->d_small_list, c->ptdesc, c->pt_ptr, c->iidx, c->jidx,
+                    k_lin_points_pipe<0><<<std::min(c->n_small, c->n_sm * LINP_MINB), PT_CTA, dyn, c->stream>>>(c->n_small, c->d_small_list, c->ptdesc, c->pt_ptr, c->iidx, c->jidx,
                                                                                                      c->impts, c->camcache[set], c->pts[set], coeff_uvw, coeff_g,
                                                                                                      c->W, c->V, c->g + c->N);
                 if (c->n_big > 0)      // points with more observations than one wave
