@@ -377,8 +377,11 @@ __global__ void __launch_bounds__(PT_CTA, LINP_MINB) k_lin_points_pipe(int n_lis
 // The camera cache entry is uniform per CTA; points and measurements are gathered (L2-resident).
 // Each thread accumulates A^T A (21 upper entries) and A^T e (6) over its observations, then one
 // deterministic block reduction per chunk writes 27 partials.
+#ifndef LINC_MINB
+#define LINC_MINB 4
+#endif
 template <bool EXT>
-__global__ void __launch_bounds__(CAM_CTA, 4) k_lin_cams(const int *__restrict__ cchunk_cam, const int *__restrict__ cchunk_beg,
+__global__ void __launch_bounds__(CAM_CTA, LINC_MINB) k_lin_cams(const int *__restrict__ cchunk_cam, const int *__restrict__ cchunk_beg,
                                                         const int *__restrict__ cchunk_end, const int *__restrict__ cam_pt,
                                                         const double *__restrict__ cam_impts,
                                                         const double *__restrict__ cache, const double *__restrict__ pts,
@@ -393,14 +396,30 @@ __global__ void __launch_bounds__(CAM_CTA, 4) k_lin_cams(const int *__restrict__
 #pragma unroll
     for (int q = 0; q < 27; ++q) acc[q] = 0.0;
     // point index and measurement come from camera-major copies made at set-up (coalesced streams); only the
-    // point itself, which changes every iteration, is gathered
-#pragma unroll 1
-    for (int t = beg + threadIdx.x; t < end; t += CAM_CTA) {
-        const double *X = pts + (size_t)__ldg(cam_pt + t) * 3;
-        double2 mm = __ldg(reinterpret_cast<const double2 *>(cam_impts) + t);
+    // point itself, which changes every iteration, is gathered.  A chunk holds at most CAM_OPT observations per thread: all
+    // their indices, then all their points are requested before the first Jacobian is formed (the pass is bound by the
+    // latency of these gathers: one observation at a time 0.154 ms; four in flight 0.167 / 0.123 / 0.116 ms at 2 / 3 / 4 CTAs per SM)
+    int pi[CAM_OPT];
+    double2 mm[CAM_OPT];
+    double X[CAM_OPT][3];
+#pragma unroll
+    for (int u = 0; u < CAM_OPT; ++u) {
+        const int t = beg + threadIdx.x + u * CAM_CTA;
+        pi[u] = t < end ? __ldg(cam_pt + t) : -1;
+        mm[u] = t < end ? __ldg(reinterpret_cast<const double2 *>(cam_impts) + t) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < CAM_OPT; ++u) {
+        const double *P = pts + (size_t)(pi[u] < 0 ? 0 : pi[u]) * 3;
+        X[u][0] = __ldg(P); X[u][1] = __ldg(P + 1); X[u][2] = __ldg(P + 2);
+    }
+#pragma unroll
+    for (int u = 0; u < CAM_OPT; ++u) {
+        if (pi[u] < 0) continue;
+        const int t = beg + threadIdx.x + u * CAM_CTA;
         double e0, e1, A[12], B[6];
-        if (EXT) residual_jac_ext(cam, ext, cchunk_cam[ch], __ldg(cam_obs + t), __ldg(X), __ldg(X + 1), __ldg(X + 2), mm.x, mm.y, e0, e1, A, B);
-        else residual_jac(cam, __ldg(X), __ldg(X + 1), __ldg(X + 2), mm.x, mm.y, e0, e1, A, B);
+        if (EXT) residual_jac_ext(cam, ext, cchunk_cam[ch], __ldg(cam_obs + t), X[u][0], X[u][1], X[u][2], mm[u].x, mm[u].y, e0, e1, A, B);
+        else residual_jac(cam, X[u][0], X[u][1], X[u][2], mm[u].x, mm[u].y, e0, e1, A, B);
         int q = 0;
 #pragma unroll
         for (int r = 0; r < 6; ++r)
