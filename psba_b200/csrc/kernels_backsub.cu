@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_backsub(const int *__restrict__ c
 //                       the dpa rows and the per-point data (gb, Vinv, point) in registers.
 template <int DUMMY>
 #ifndef BSUB_MINB
-#define BSUB_MINB 3
+#define BSUB_MINB (384 / PT_CTA)   // resident CTAs per SM: twelve warps (168 registers per thread)
 #endif
 __global__ void __launch_bounds__(PT_CTA, BSUB_MINB) k_backsub_pipe(int n_list, const int *__restrict__ chunk_list, const int4 *__restrict__ ptdesc,
                                                            const int *__restrict__ pt_ptr, const int *__restrict__ iidx,

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_lin_points(const int *__restrict_
 // stage half its camera entries came in, instead of a copy-out loop through the load/store unit.
 template <int DUMMY>
 #ifndef LINP_MINB
-#define LINP_MINB 3
+#define LINP_MINB (384 / PT_CTA)   // resident CTAs per SM: twelve warps (168 registers per thread)
 #endif
 __global__ void __launch_bounds__(PT_CTA, LINP_MINB) k_lin_points_pipe(int n_list, const int *__restrict__ chunk_list, const int4 *__restrict__ ptdesc,
                                                               const int *__restrict__ pt_ptr, const int *__restrict__ iidx,
@@ -481,7 +481,7 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
             // the persistent kernel pays for its three-stage prologue only when a CTA sees enough chunks (measured on
             // Venice-52, 2 700 chunks: 57 us against 31 us for the one-shot kernel)
             static const int pipe_env = getenv("PSBA_LIN_PIPE") ? atoi(getenv("PSBA_LIN_PIPE")) : -1;
-            const bool pipe = pipe_env >= 0 ? pipe_env != 0 : c->n_small >= 8 * c->n_sm * 3;
+            const bool pipe = pipe_env >= 0 ? pipe_env != 0 : c->n_small >= 8 * c->n_sm * LINP_MINB;
             if (c->ext_on)     // extended camera model (distortion / residual weights): the one-shot kernel carries it
                 k_lin_points<true><<<c->n_ptchunk, PT_CTA, 0, c->stream>>>(nullptr, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set],
                                                                           coeff_uvw, coeff_g, c->W, c->V, c->g + c->N, c->ext);

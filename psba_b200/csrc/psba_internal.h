@@ -20,7 +20,10 @@
 #define PSBA_MNP 2
 #define CAMC 24            // doubles per camera-cache entry: q(4) t(3) K(5) dq/dv(12) = 192 B
 #define TS 48              // tile size of the camera system (8 cameras)
-#define PT_CTA 128         // observations per point-major CTA wave
+#ifndef PT_CTA
+#define PT_CTA 64          // observations per point-major CTA wave (measured 128 / 96 / 64 / 32: point pass 0.297 / 0.290 / 0.287 / 0.286 ms,
+                           // back-substitution 0.283 / 0.263 / 0.259 / 0.271 ms: smaller CTAs, cheaper barriers, same warps per SM)
+#endif
 #define CAM_CTA 128        // threads per camera-major CTA
 #define CAM_OPT 4          // observations per thread in the camera-major pass
 #define PAIR_CTA 128       // threads per pair-pass CTA
