@@ -24,7 +24,7 @@
 #define PT_CTA 64          // observations per point-major CTA wave (measured 128 / 96 / 64 / 32: point pass 0.297 / 0.290 / 0.287 / 0.286 ms,
                            // back-substitution 0.283 / 0.263 / 0.259 / 0.271 ms: smaller CTAs, cheaper barriers, same warps per SM)
 #endif
-#define CAM_CTA 128        // threads per camera-major CTA
+#define CAM_CTA 128        // threads per camera-major CTA (the block reduction of the pass assumes four warps)
 #define CAM_OPT 4          // observations per thread in the camera-major pass
 #define PAIR_CTA 128       // threads per pair-pass CTA
 #define PAIR_TPL 24        // target triples per lane in the pair pass (lane-per-triple variant)
