@@ -575,9 +575,18 @@ static void ext_changed(psba_ctx *c)
 // Fixed lens distortion per camera: kc[m*5] = (k1, k2, p1, p2, k3) of the sba "varKD" camera (data/54camsvarKD.txt
 // columns 6-10; PSBA/misc.cpp:27-29 copies them through quat2vec, the reference's kernels then ignore them).
 // NULL or all-zero coefficients switch the model off (the reference's undistorted projection, bit for bit).
+// captured chains hold kernel arguments by value: anything that replaces a device array they name drops them
+static void seq_invalidate(psba_ctx *c)
+{
+    for (auto &kv : *c->seqs) if (kv.second.ok) cudaGraphExecDestroy(kv.second.exec);
+    c->seqs->clear();
+    c->capturing = nullptr;
+}
+
 extern "C" void psba_set_distortion(psba_ctx *c, const double *kc)
 {
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    seq_invalidate(c);
     psba_dev_free(c, (void *)c->ext.kc); c->ext.kc = nullptr;
     bool any = false;
     if (kc) for (int q = 0; q < c->m * 5; ++q) any |= kc[q] != 0.0;
@@ -598,6 +607,7 @@ extern "C" void psba_set_distortion(psba_ctx *c, const double *kc)
 extern "C" int psba_set_covariances(psba_ctx *c, const double *cov, int covsz)
 {
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    seq_invalidate(c);
     psba_dev_free(c, (void *)c->ext.wgt); c->ext.wgt = nullptr;
     if (cov) {
         if (covsz != 3 && covsz != 4) die("set_covariances: covsz must be 3 or 4");
