@@ -41,6 +41,35 @@ __device__ __forceinline__ void load_cam(const double *__restrict__ cc, CamReg &
 #pragma unroll
     for (int i = 0; i < 12; ++i) c.D[i] = buf[CC_D + i];
 }
+// COMPACT record (16 doubles = 128 B = four sectors instead of six): q0 (4), ds = -v / sl (3), sl = sqrt(1 - |v|^2), t (3), K (5).
+// v = -ds sl (no division per observation), then q and the D_k with the expressions of k_cam_prep (kernels_obs.cu) -- the pipelined point pass fetches one record per
+// observation, and what bounds it is the L2 -> SM traffic of these fetches (profiles/ncu_full_r02b.md)
+#define CAMC2 16
+__device__ __forceinline__ void load_cam_compact(const double *cc, CamReg &c)
+{
+    const double2 *p = reinterpret_cast<const double2 *>(cc);
+    double b[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const double2 v = p[i]; b[2 * i] = v.x; b[2 * i + 1] = v.y; }
+    const double s0 = b[0], a1 = b[1], a2 = b[2], a3 = b[3], sl = b[7];
+    const double v1 = -b[4] * sl, v2 = -b[5] * sl, v3 = -b[6] * sl;
+    c.q[0] = sl * s0 - (a1 * v1 + a2 * v2 + a3 * v3);
+    c.q[1] = s0 * v1 + sl * a1 + a3 * v2 - a2 * v3;
+    c.q[2] = s0 * v2 + sl * a2 + a1 * v3 - a3 * v1;
+    c.q[3] = s0 * v3 + sl * a3 + a2 * v1 - a1 * v2;
+    c.t[0] = b[8]; c.t[1] = b[9]; c.t[2] = b[10];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) c.K[k] = b[11 + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double ds_l = b[4 + k];
+        const double e1 = (k == 0), e2 = (k == 1), e3 = (k == 2);
+        c.D[4 * k + 0] = ds_l * s0 - (a1 * e1 + a2 * e2 + a3 * e3);
+        c.D[4 * k + 1] = s0 * e1 + ds_l * a1 + a3 * e2 - a2 * e3;
+        c.D[4 * k + 2] = s0 * e2 + ds_l * a2 + a1 * e3 - a3 * e1;
+        c.D[4 * k + 3] = s0 * e3 + ds_l * a3 + a2 * e1 - a1 * e2;
+    }
+}
 template <bool GLOBAL>
 __device__ __forceinline__ void load_cam_proj(const double *__restrict__ cc, CamProj &c)
 {

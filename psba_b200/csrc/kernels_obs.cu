@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #define CAM_LD 26          // doubles per staged camera entry in shared memory (24 + pad: conflict-free LDS.128)
+#define CAM_LD2 18         // pipelined point pass: compact records (16 doubles + pad; the W tile of the chunk, 18 doubles per observation, takes the place)
 
 // ------------------------------------------------------------------------------------------------
 // per-camera cache: q = ql (x) q0, t, K, D_k = d q / d v_k
@@ -27,6 +28,13 @@ __global__ void k_cam_prep(int m, const double *__restrict__ K, const double *__
     const double v1 = cams[j * 6], v2 = cams[j * 6 + 1], v3 = cams[j * 6 + 2];
     const double sl = sqrt(1 - v1 * v1 - v2 * v2 - v3 * v3);
     double *c = cache + (size_t)j * CAMC;
+    {   // compact record behind the m full entries (load_cam_compact, dev_math.cuh)
+        double *r = cache + (size_t)m * CAMC + (size_t)j * CAMC2;
+        r[0] = s0; r[1] = a1; r[2] = a2; r[3] = a3; r[4] = -v1 / sl; r[5] = -v2 / sl; r[6] = -v3 / sl; r[7] = sl;
+        r[8] = cams[j * 6 + 3]; r[9] = cams[j * 6 + 4]; r[10] = cams[j * 6 + 5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) r[11 + k] = K[j * 5 + k];
+    }
     // q = ql (x) q0, same operation order as compute_exQT.cl:46-49
     c[CC_Q + 0] = sl * s0 - (a1 * v1 + a2 * v2 + a3 * v3);
     c[CC_Q + 1] = s0 * v1 + sl * a1 + a3 * v2 - a2 * v3;
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(PT_CTA, 4) k_lin_points(const int *__restrict_
 // stage half its camera entries came in, instead of a copy-out loop through the load/store unit.
 template <int DUMMY>
 #ifndef LINP_MINB
-#define LINP_MINB (384 / PT_CTA)   // resident CTAs per SM: twelve warps (168 registers per thread)
+#define LINP_MINB (512 / PT_CTA)   // resident CTAs per SM: sixteen warps (128 registers per thread, 26 KB of shared memory per CTA)
 #endif
 __global__ void __launch_bounds__(PT_CTA, LINP_MINB) k_lin_points_pipe(int n_list, const int *__restrict__ chunk_list, const int4 *__restrict__ ptdesc,
                                                               const int *__restrict__ pt_ptr, const int *__restrict__ iidx,
@@ -267,7 +275,7 @@ __global__ void __launch_bounds__(PT_CTA, LINP_MINB) k_lin_points_pipe(int n_lis
                                                               double coeff, double coeff_g, double *__restrict__ W,
                                                               double *__restrict__ V, double *__restrict__ gb)
 {
-    extern __shared__ __align__(128) double stage_dyn[];       // 2 x PT_CTA*CAM_LD: camera entries, then the W tile
+    extern __shared__ __align__(128) double stage_dyn[];       // 2 x PT_CTA*CAM_LD2: compact camera records, then the W tile
     __shared__ double sh[9][PT_CTA];
     __shared__ double px[2][3][PT_CTA];
     __shared__ int sj[2][PT_CTA];
@@ -283,11 +291,11 @@ __global__ void __launch_bounds__(PT_CTA, LINP_MINB) k_lin_points_pipe(int n_lis
     };
     auto issue = [&](const int4 &d, int buf) {               // camera entries (sj[buf] is visible) and points of a chunk
         const int cnt = d.w - d.z, np = d.y - d.x;
-        double *st = stage_dyn + buf * PT_CTA * CAM_LD;
+        double *st = stage_dyn + buf * PT_CTA * CAM_LD2;
 #pragma unroll
-        for (int q = 0; q < 12; ++q) {
-            const int p = tid + q * PT_CTA, ob = p / 12, part = p - ob * 12;
-            if (p < cnt * 12) cp_async16(st + ob * CAM_LD + part * 2, cache + (size_t)sj[buf][ob] * CAMC + part * 2);
+        for (int q = 0; q < 8; ++q) {
+            const int p = tid + q * PT_CTA, ob = p >> 3, part = p & 7;
+            if (p < cnt * 8) cp_async16(st + ob * CAM_LD2 + part * 2, cache + (size_t)sj[buf][ob] * CAMC2 + part * 2);
         }
         if (tid < np) {
             const double *X = pts + (size_t)(d.x + tid) * 3;
@@ -321,9 +329,9 @@ __global__ void __launch_bounds__(PT_CTA, LINP_MINB) k_lin_points_pipe(int n_lis
         __syncthreads();                                     // entries and points of this chunk have landed
         const int p0 = ds.x, o0 = ds.z, o1 = ds.w, np = ds.y - ds.x, cnt = o1 - o0;
         const int k = o0 + tid;
-        double *st = stage_dyn + buf * PT_CTA * CAM_LD;
+        double *st = stage_dyn + buf * PT_CTA * CAM_LD2;
         CamReg cam;
-        load_cam<false>(st + tid * CAM_LD, cam);
+        load_cam_compact(st + tid * CAM_LD2, cam);
         const double X0 = px[buf][0][cur.lp], X1 = px[buf][1][cur.lp], X2 = px[buf][2][cur.lp];
         __syncthreads();                                     // every thread holds its entry: the half is free for the W tile
         if (k < o1) {
@@ -476,7 +484,7 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
                                                              c->U, ga_out);
     if (c->n_ptchunk > 0)
         PROF(c, KID_LIN_POINTS) {
-            const int dyn = 2 * PT_CTA * CAM_LD * (int)sizeof(double);
+            const int dyn = 2 * PT_CTA * CAM_LD2 * (int)sizeof(double);
             psba_set_smem((const void *)k_lin_points_pipe<0>, dyn);
             // the persistent kernel pays for its three-stage prologue only when a CTA sees enough chunks (measured on
             // Venice-52, 2 700 chunks: 57 us against 31 us for the one-shot kernel)
@@ -491,7 +499,7 @@ void psba_launch_linearize(psba_ctx *c, double coeff_uvw, double coeff_g)
             else {
                 if (c->n_small > 0)
                     k_lin_points_pipe<0><<<std::min(c->n_small, c->n_sm * LINP_MINB), PT_CTA, dyn, c->stream>>>(c->n_small, c->d_small_list, c->ptdesc, c->pt_ptr, c->iidx, c->jidx,
-                                                                                                     c->impts, c->camcache[set], c->pts[set], coeff_uvw, coeff_g,
+                                                                                                     c->impts, c->camcache[set] + (size_t)c->m * CAMC, c->pts[set], coeff_uvw, coeff_g,
                                                                                                      c->W, c->V, c->g + c->N);
                 if (c->n_big > 0)      // points with more observations than one wave
                     k_lin_points<false><<<c->n_big, PT_CTA, 0, c->stream>>>(c->d_big_list, c->ptdesc, c->pt_ptr, c->iidx, c->jidx, c->impts, c->camcache[set], c->pts[set],

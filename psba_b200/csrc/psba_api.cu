@@ -105,7 +105,7 @@ extern "C" psba_ctx *psba_setup_cl(int cnp, int pnp, int mnp, int nCams, int n3D
     c->initcams = dalloc<double>(c, (size_t)nCams * 4);
     for (int s = 0; s < 2; ++s) {
         c->cams[s] = dalloc<double>(c, (size_t)nCams * 6);
-        c->camcache[s] = dalloc<double>(c, (size_t)nCams * CAMC);
+        c->camcache[s] = dalloc<double>(c, (size_t)nCams * (CAMC + 16));   // full entries, then the compact records of the pipelined point pass
     }
     c->U = dalloc<double>(c, (size_t)nCams * 42);          // [U | 6m doubles: ga as it comes out of the camera pass on N > 1 GPUs (one all-reduce for both)]
     c->d_status = dalloc<int>(c, 4);
