@@ -110,7 +110,7 @@ def kernel_bytes(G, prob_sizes):
         "k_lin_cams": 20 * o + 24 * n + 192 * m + 216 * ncch,  # R cam_pt4 cam_impts16 P C | W partials
         # ring kernel (pair_mode 6): R W144 cam_obs4 cam_pt4 Vinv48n gb24n, row records 8 B per lane slot + 8 B per row | W partials;
         # the older kernels read 8 B of triple indices per triple instead of the row records
-        "k_schur_pairs": (152 * o + 72 * n + 264 * st("ring_rows") + 336 * npch) if st("pair_mode") == 6 else (148 * o + 72 * n + 8 * ntri + 336 * npch),
+        "k_schur_pairs": (152 * o + 72 * n + 272 * st("ring_rows") + 336 * npch) if st("pair_mode") == 6 else (148 * o + 72 * n + 8 * ntri + 336 * npch),
         "k_backsub": 168 * o + 168 * n + 96 * m + 48 * m,     # R W144 jidx4 iidx4 impts16 Vinv gb pts dpa C' | W eb dpb newpts
         "k_cost": 24 * o + 24 * n + 96 * m,
         "k_Jdot": 8 * o + 24 * n + 192 * m + 16 * (6 * m + 3 * n),

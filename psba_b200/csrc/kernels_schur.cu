@@ -398,17 +398,27 @@ __device__ __forceinline__ void ring_issue(double *stage, const double *__restri
         if (bs >= 0) cp_async16(stage + p * 2, W + (size_t)bs * 18 + part * 2);
     }
 }
-// record of one row: 32 lane slots {observation of camera l, rank of the visit} + {task word, schedule position}
-__device__ __forceinline__ void ring_issue_rec(int2 *slot, const int2 *__restrict__ rows, const int2 *__restrict__ info, int row, int lane)
+// record of one row: 32 lane slots {observation of camera l, rank of the visit} + {task word, schedule position} + pad = 272 bytes,
+// copied as seventeen 16-byte pieces that bypass L1 (an L1-allocating 8-byte copy per lane fetched 2.25 sectors per sector asked for)
+#define RING_REC 34
+#ifndef RING_GB
+#define RING_GB 0
+#endif
+#ifndef RING_CG
+#define RING_CG 0
+#endif
+// measured on the headline workload: records as 16-byte pieces past L1 0.731 -> 0.699 ms; indices by ld.global.cg too (RING_CG) 0.706;
+// gb by three 8-byte loads per lane past L1 instead of 8-byte copies through L1 (RING_GB) 0.90 ms
+__device__ __forceinline__ void ring_issue_rec(int2 *slot, const int2 *__restrict__ rows, int row, int lane)
 {
-    cp_async8(slot + lane, rows + (size_t)row * 32 + lane);
-    if (lane == 0) cp_async8(slot + 32, info + row);
+    if (lane < 17) cp_async16(slot + 2 * lane, rows + (size_t)row * RING_REC + 2 * lane);
 }
+__device__ __forceinline__ int ldcg_int(const int *p) { return RING_CG ? __ldcg(p) : __ldg(p); }
 
 template <int NT, int STAGES, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restrict__ segs, const int *__restrict__ cam_obs,
                                                           const int *__restrict__ cam_pt, const int *__restrict__ wrow_ptr,
-                                                          const int2 *__restrict__ rows, const int2 *__restrict__ info,
+                                                          const int2 *__restrict__ rows,
                                                           const int *__restrict__ sched, const double *__restrict__ W,
                                                           const double *__restrict__ Vinv, const double *__restrict__ gb,
                                                           double *__restrict__ part, int seg_v, long long *__restrict__ dbg)
@@ -416,19 +426,19 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
     constexpr int NW = NT / 32, RS = 2 * STAGES + 1;
     long long stamp[6];
     stamp[0] = clock64(); stamp[1] = stamp[0];
-    extern __shared__ __align__(16) double sm[];   // [seg_v][18] Y tile | [NW][STAGES][32][18] copy rings | [NW][RS][33] row records
+    extern __shared__ __align__(16) double sm[];   // [seg_v][18] Y tile | [NW][STAGES][32][18] copy rings | [NW][RS][34] row records
     __shared__ double red[NW][32];
     const seg_desc sd = segs[blockIdx.x];
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int nv = sd.v1 - sd.v0;
     double *Ysm = sm;
     double *ring = sm + (size_t)seg_v * 18 + (size_t)wrp * STAGES * 576;
-    int2 *recs = reinterpret_cast<int2 *>(sm + (size_t)seg_v * 18 + (size_t)NW * STAGES * 576) + (size_t)wrp * RS * 33;
-    const int r0 = __ldg(wrow_ptr + (size_t)blockIdx.x * NW + wrp), r1 = __ldg(wrow_ptr + (size_t)blockIdx.x * NW + wrp + 1);
+    int2 *recs = reinterpret_cast<int2 *>(sm + (size_t)seg_v * 18 + (size_t)NW * STAGES * 576) + (size_t)wrp * RS * RING_REC;
+    const int r0 = ldcg_int(wrow_ptr + (size_t)blockIdx.x * NW + wrp), r1 = ldcg_int(wrow_ptr + (size_t)blockIdx.x * NW + wrp + 1);
     // records of the first 2 STAGES rows of this warp: they land under phase 1
 #pragma unroll
     for (int s = 0; s < 2 * STAGES; ++s)
-        if (r0 + s < r1) ring_issue_rec(recs + ((r0 + s) % RS) * 33, rows, info, r0 + s, lane);
+        if (r0 + s < r1) ring_issue_rec(recs + ((r0 + s) % RS) * RING_REC, rows, r0 + s, lane);
     cp_async_commit();
     // ---- phase 1: Y tile, diagonal block and ea of the segment.  A warp owns the visit rows wrp, wrp + NW, ... (32
     // consecutive visits each).  W_ik goes straight to its place in the Y tile, Vinv_i and gb_i into the (still idle) copy
@@ -441,20 +451,30 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
     const int nvr = (nv + 31) >> 5;
 #pragma unroll 1
     for (int vb = wrp; vb < nvr; vb += NW * RB) {
+#if RING_GB
+        double gq[RB][3];
+#endif
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
             const int r = (vb + j * NW) * 32 + lane;
             int q = -1, i = 0;
-            if (r < nv) { q = __ldg(cam_obs + sd.v0 + r); i = __ldg(cam_pt + sd.v0 + r); }
+            if (r < nv) { q = ldcg_int(cam_obs + sd.v0 + r); i = ldcg_int(cam_pt + sd.v0 + r); }
             double *dstW = Ysm + (size_t)(vb + j * NW) * 32 * 18, *stg = ring + j * 288;
             ring_issue(dstW, W, q, lane);
+            // gb_i: three 8-byte loads per lane past L1 (24 bytes at an 8-byte aligned address: no 16-byte copy fits)
+#if RING_GB
+            gq[j][0] = gq[j][1] = gq[j][2] = 0.0;
+            if (r < nv) { const double *gp = gb + (size_t)i * 3; gq[j][0] = __ldcg(gp); gq[j][1] = __ldcg(gp + 1); gq[j][2] = __ldcg(gp + 2); }
+#endif
 #pragma unroll
             for (int qq = 0; qq < 3; ++qq) {
                 const int p = qq * 32 + lane, sl = p / 3, part = p - sl * 3;
                 const int qs = __shfl_sync(0xffffffffu, q, sl), is = __shfl_sync(0xffffffffu, i, sl);
                 if (qs >= 0) {
                     cp_async16(stg + p * 2, Vinv + (size_t)is * 6 + part * 2);
+#if !RING_GB
                     cp_async8(stg + 192 + p, gb + (size_t)is * 3 + part);
+#endif
                 }
             }
         }
@@ -474,7 +494,11 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
                 const double2 *vp = reinterpret_cast<const double2 *>(stg + lane * 6);
                 const double2 v0 = vp[0], v1 = vp[1], v2 = vp[2];
                 const double i00 = v0.x, i10 = v0.y, i20 = v1.x, i11 = v1.y, i21 = v2.x, i22 = v2.y;
+#if RING_GB
+                const double g0 = gq[j][0], g1 = gq[j][1], g2 = gq[j][2];
+#else
                 const double g0 = stg[192 + lane * 3], g1 = stg[192 + lane * 3 + 1], g2 = stg[192 + lane * 3 + 2];
+#endif
 #pragma unroll
                 for (int rp = 0; rp < 3; ++rp) {                     // two rows of Y at a time: three 16-byte stores
                     double y[6];
@@ -514,7 +538,7 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
         int b = -1;
-        if (r0 + s < r1) b = recs[((r0 + s) % RS) * 33 + lane].x;
+        if (r0 + s < r1) b = recs[((r0 + s) % RS) * RING_REC + lane].x;
         ring_issue(ring + s * 576, W, b, lane);
         cp_async_commit();
     }
@@ -542,8 +566,8 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
     for (int row = r0; row < r1; ++row) {
         cp_async_wait<STAGES - 1>();
         __syncwarp();
-        const int2 cur = recs[sl_cur * 33 + lane], ci = recs[sl_cur * 33 + 32];
-        const int b_far = row + STAGES < r1 ? recs[sl_far * 33 + lane].x : -1;
+        const int2 cur = recs[sl_cur * RING_REC + lane], ci = recs[sl_cur * RING_REC + 32];
+        const int b_far = row + STAGES < r1 ? recs[sl_far * RING_REC + lane].x : -1;
         double *stage = ring + st * 576;
         if (cur.x >= 0) {
             double wb[18];
@@ -566,7 +590,7 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
         }
         __syncwarp();                                               // every lane has read its block: the stage can be refilled
         ring_issue(stage, W, b_far, lane);
-        if (row + 2 * STAGES < r1) ring_issue_rec(recs + sl_new * 33, rows, info, row + 2 * STAGES, lane);
+        if (row + 2 * STAGES < r1) ring_issue_rec(recs + sl_new * RING_REC, rows, row + 2 * STAGES, lane);
         cp_async_commit();
         st = st + 1 == STAGES ? 0 : st + 1;
         sl_cur = sl_cur + 1 == RS ? 0 : sl_cur + 1; sl_far = sl_far + 1 == RS ? 0 : sl_far + 1; sl_new = sl_new + 1 == RS ? 0 : sl_new + 1;
@@ -601,7 +625,7 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
             const int q = lane >> lg;
             const bool writer = q < nch && (G < 8 || (gl & ((G >> 2) - 1)) == 0);
             if (writer) {
-                const int c = __ldg(sched + ci.y + q);
+                const int c = ldcg_int(sched + ci.y + q);
                 double *out = part + (size_t)c * 42 + start;
 #pragma unroll
                 for (int j = 0; j < 36; ++j)
@@ -634,7 +658,7 @@ static void launch_ring_shape(psba_ctx *c)
     const size_t nd = (size_t)c->n_seg * (NT / 32) * 8;
     if (dbg_runs > 0 && --dbg_runs == 0) { dbg = (long long *)psba_dev_alloc(c, nd * 8, true); }
     k_schur_ring<NT, STAGES, MINB><<<c->n_seg, NT, dyn, c->stream>>>((const seg_desc *)c->seg_desc, c->cam_obs, c->cam_pt, c->ring_wrow_ptr, c->ring_rows,
-                                                                    c->ring_info, c->sched_chunk, c->W, c->Vinv, c->g + c->N, c->pair_part, c->seg_v, dbg);
+                                                                    c->sched_chunk, c->W, c->Vinv, c->g + c->N, c->pair_part, c->seg_v, dbg);
     if (dbg) {
         std::vector<long long> h(nd);
         CUDA_CHECK(cudaMemcpyAsync(h.data(), dbg, nd * 8, cudaMemcpyDeviceToHost, c->stream));

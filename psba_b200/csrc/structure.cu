@@ -271,7 +271,7 @@ __global__ void k_ring_plan(int n_seg, const seg_desc_h *__restrict__ segs, cons
 // warp per schedule position that starts a task: the rows of the task
 __global__ void k_ring_rows(int n_sched, const int4 *__restrict__ task, const int *__restrict__ sched, const int *__restrict__ ch_beg,
                             const int *__restrict__ ch_end, const unsigned short *__restrict__ tri_vr, const int *__restrict__ tri_ob,
-                            int2 *__restrict__ rows, int2 *__restrict__ info)
+                            int2 *__restrict__ rows)
 {
     const int j = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (j >= n_sched) return;
@@ -282,8 +282,11 @@ __global__ void k_ring_rows(int n_sched, const int4 *__restrict__ task, const in
     if (q < tk.z) { const int c = sched[j + q]; beg = ch_beg[c]; end = ch_end[c]; }
     for (int it = 0; it < tk.y; ++it) {
         const int t = beg + gl + it * G;
-        rows[((size_t)tk.x + it) * 32 + lane] = t < end ? make_int2(tri_ob[t], (int)tri_vr[t]) : make_int2(-1, 0);
-        if (lane == 0) info[(size_t)tk.x + it] = make_int2(tk.w | ((it == tk.y - 1) ? 256 : 0) | (tk.z << 16), j);
+        rows[((size_t)tk.x + it) * 34 + lane] = t < end ? make_int2(tri_ob[t], (int)tri_vr[t]) : make_int2(-1, 0);
+        if (lane == 0) {       // slot 32: the task word of the row; slot 33: pad (a row record is seventeen 16-byte pieces)
+            rows[((size_t)tk.x + it) * 34 + 32] = make_int2(tk.w | ((it == tk.y - 1) ? 256 : 0) | (tk.z << 16), j);
+            rows[((size_t)tk.x + it) * 34 + 33] = make_int2(0, 0);
+        }
     }
 }
 
@@ -443,7 +446,7 @@ static const int RING_SHAPES[6][3] = {{384, 2, 1}, {256, 2, 1}, {256, 3, 1}, {12
 static size_t ring_fixed_smem(int cfg)
 {
     const int nw = RING_SHAPES[cfg][0] / 32, st = RING_SHAPES[cfg][1];
-    return (size_t)nw * st * 4608 + (size_t)nw * (2 * st + 1) * 264;
+    return (size_t)nw * st * 4608 + (size_t)nw * (2 * st + 1) * 272;
 }
 size_t psba_ring_smem(int cfg, int seg_v) { return (size_t)seg_v * 144 + ring_fixed_smem(cfg); }
 
@@ -473,7 +476,7 @@ static void build_ring_tables(psba_ctx *c)
     c->ring_wrow_ptr = salloc<int>(c, (size_t)c->n_seg * nw + 1);
     if (c->n_seg == 0 || c->ntri == 0) {
         CUDA_CHECK(cudaMemsetAsync(c->ring_wrow_ptr, 0, ((size_t)c->n_seg * nw + 1) * 4, st));
-        c->ring_rows = salloc<int2>(c, 32); c->ring_info = salloc<int2>(c, 1);
+        c->ring_rows = salloc<int2>(c, 34); c->ring_info = nullptr;
         return;
     }
     const size_t nwr = (size_t)c->n_seg * nw + 1;
@@ -492,11 +495,11 @@ static void build_ring_tables(psba_ctx *c)
     CUDA_CHECK(cudaStreamSynchronize(st));
     psba_dev_free(c, tmp);
     c->ring_n_rows = n_rows;
-    c->ring_rows = salloc<int2>(c, (size_t)n_rows * 32 + 32); c->ring_info = salloc<int2>(c, (size_t)n_rows + 1);
+    c->ring_rows = salloc<int2>(c, (size_t)n_rows * 34 + 34); c->ring_info = nullptr;
     k_ring_plan<<<cdiv(c->n_seg, 128), 128, 0, st>>>(c->n_seg, (const seg_desc_h *)c->seg_desc, c->sched_chunk, c->sch_beg, c->sch_end, nw, c->ring_rt, 1,
                                                      nullptr, c->ring_wrow_ptr, task);
     k_ring_rows<<<cdiv((long long)n_sched * 32, 256), 256, 0, st>>>(n_sched, task, c->sched_chunk, c->sch_beg, c->sch_end, c->tri_vr, c->tri_ob,
-                                                                   c->ring_rows, c->ring_info);
+                                                                   c->ring_rows);
     CUDA_CHECK(cudaStreamSynchronize(st));
     psba_dev_free(c, wrows); psba_dev_free(c, task);
 }
