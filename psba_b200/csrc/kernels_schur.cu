@@ -401,19 +401,12 @@ __device__ __forceinline__ void ring_issue(double *stage, const double *__restri
 // record of one row: 32 lane slots {observation of camera l, rank of the visit} + {task word, schedule position} + pad = 272 bytes,
 // copied as seventeen 16-byte pieces that bypass L1 (an L1-allocating 8-byte copy per lane fetched 2.25 sectors per sector asked for)
 #define RING_REC 34
-#ifndef RING_GB
-#define RING_GB 0
-#endif
-#ifndef RING_CG
-#define RING_CG 0
-#endif
-// measured on the headline workload: records as 16-byte pieces past L1 0.731 -> 0.699 ms; indices by ld.global.cg too (RING_CG) 0.706;
-// gb by three 8-byte loads per lane past L1 instead of 8-byte copies through L1 (RING_GB) 0.90 ms
+// measured on the headline workload: records as 16-byte pieces past L1 0.731 -> 0.699 ms; not kept: the index loads by ld.global.cg
+// too (0.706), gb by three 8-byte loads per lane past L1 instead of 8-byte copies through L1 (0.90 ms)
 __device__ __forceinline__ void ring_issue_rec(int2 *slot, const int2 *__restrict__ rows, int row, int lane)
 {
     if (lane < 17) cp_async16(slot + 2 * lane, rows + (size_t)row * RING_REC + 2 * lane);
 }
-__device__ __forceinline__ int ldcg_int(const int *p) { return RING_CG ? __ldcg(p) : __ldg(p); }
 
 template <int NT, int STAGES, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restrict__ segs, const int *__restrict__ cam_obs,
@@ -434,7 +427,7 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
     double *Ysm = sm;
     double *ring = sm + (size_t)seg_v * 18 + (size_t)wrp * STAGES * 576;
     int2 *recs = reinterpret_cast<int2 *>(sm + (size_t)seg_v * 18 + (size_t)NW * STAGES * 576) + (size_t)wrp * RS * RING_REC;
-    const int r0 = ldcg_int(wrow_ptr + (size_t)blockIdx.x * NW + wrp), r1 = ldcg_int(wrow_ptr + (size_t)blockIdx.x * NW + wrp + 1);
+    const int r0 = __ldg(wrow_ptr + (size_t)blockIdx.x * NW + wrp), r1 = __ldg(wrow_ptr + (size_t)blockIdx.x * NW + wrp + 1);
     // records of the first 2 STAGES rows of this warp: they land under phase 1
 #pragma unroll
     for (int s = 0; s < 2 * STAGES; ++s)
@@ -451,30 +444,20 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
     const int nvr = (nv + 31) >> 5;
 #pragma unroll 1
     for (int vb = wrp; vb < nvr; vb += NW * RB) {
-#if RING_GB
-        double gq[RB][3];
-#endif
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
             const int r = (vb + j * NW) * 32 + lane;
             int q = -1, i = 0;
-            if (r < nv) { q = ldcg_int(cam_obs + sd.v0 + r); i = ldcg_int(cam_pt + sd.v0 + r); }
+            if (r < nv) { q = __ldg(cam_obs + sd.v0 + r); i = __ldg(cam_pt + sd.v0 + r); }
             double *dstW = Ysm + (size_t)(vb + j * NW) * 32 * 18, *stg = ring + j * 288;
             ring_issue(dstW, W, q, lane);
-            // gb_i: three 8-byte loads per lane past L1 (24 bytes at an 8-byte aligned address: no 16-byte copy fits)
-#if RING_GB
-            gq[j][0] = gq[j][1] = gq[j][2] = 0.0;
-            if (r < nv) { const double *gp = gb + (size_t)i * 3; gq[j][0] = __ldcg(gp); gq[j][1] = __ldcg(gp + 1); gq[j][2] = __ldcg(gp + 2); }
-#endif
 #pragma unroll
             for (int qq = 0; qq < 3; ++qq) {
                 const int p = qq * 32 + lane, sl = p / 3, part = p - sl * 3;
                 const int qs = __shfl_sync(0xffffffffu, q, sl), is = __shfl_sync(0xffffffffu, i, sl);
                 if (qs >= 0) {
                     cp_async16(stg + p * 2, Vinv + (size_t)is * 6 + part * 2);
-#if !RING_GB
                     cp_async8(stg + 192 + p, gb + (size_t)is * 3 + part);
-#endif
                 }
             }
         }
@@ -494,11 +477,7 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
                 const double2 *vp = reinterpret_cast<const double2 *>(stg + lane * 6);
                 const double2 v0 = vp[0], v1 = vp[1], v2 = vp[2];
                 const double i00 = v0.x, i10 = v0.y, i20 = v1.x, i11 = v1.y, i21 = v2.x, i22 = v2.y;
-#if RING_GB
-                const double g0 = gq[j][0], g1 = gq[j][1], g2 = gq[j][2];
-#else
                 const double g0 = stg[192 + lane * 3], g1 = stg[192 + lane * 3 + 1], g2 = stg[192 + lane * 3 + 2];
-#endif
 #pragma unroll
                 for (int rp = 0; rp < 3; ++rp) {                     // two rows of Y at a time: three 16-byte stores
                     double y[6];
@@ -625,7 +604,7 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
             const int q = lane >> lg;
             const bool writer = q < nch && (G < 8 || (gl & ((G >> 2) - 1)) == 0);
             if (writer) {
-                const int c = ldcg_int(sched + ci.y + q);
+                const int c = __ldg(sched + ci.y + q);
                 double *out = part + (size_t)c * 42 + start;
 #pragma unroll
                 for (int j = 0; j < 36; ++j)
