@@ -361,6 +361,12 @@ def main():
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ktab[dom]["GBps"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": ktab[dom]["frac_hbm"], "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": ktab[dom]["alg_bytes"], "ms_per_launch": ktab[dom]["ms_avg"]}
+    if dom == "k_schur_pairs":
+        # what bounds this kernel is not the HBM stream rate: it GATHERS 2.5 GB of 144-byte blocks per launch, and this memory system
+        # delivers such gathers at ~4 TB/s at best (tools/microbench/gather_bench.cu)
+        roofline["note"] = ("gather-bound: 216 B per observation + 144 B per off-diagonal triple are gathered in 144-byte blocks; measured gather rate "
+                            "of this memory system for such blocks ~4.0 TB/s (tools/microbench/gather_bench.cu), L2->SM traffic of the launch 4.2 GB at 5.7 TB/s "
+                            "(profiles/ncu_full_r02b.md)")
 
     # camera solve (factorisation graph + backward solve): FP64-bound.  Flops from the symbolic factor (stat chol_flops:
     # potrf + trsm + trailing updates of every panel + both triangular solves); peak = the FP64 FMA rate measured with
