@@ -408,6 +408,50 @@ __device__ __forceinline__ void ring_issue_rec(int2 *slot, const int2 *__restric
     if (lane < 17) cp_async16(slot + 2 * lane, rows + (size_t)row * RING_REC + 2 * lane);
 }
 
+// sum of the 36 block entries over the G = 2^LG lanes of every chunk of a task, partials out: recursive halving 36 -> 18 -> 9
+// (the lane with the group bit set keeps the upper half), then a butterfly of the last nine; lanes whose low bits are zero write
+template <int LG>
+__device__ __forceinline__ void ring_task_reduce(double (&a36)[36], int lane, int nch, const int *__restrict__ sched_task, double *__restrict__ part)
+{
+    constexpr int G = 1 << LG;
+    const int gl = lane & (G - 1);
+    int start = 0;
+    if (G >= 2) {
+        constexpr int h = G >> 1;
+        const bool up = (gl & h) != 0;
+        if (up) start += 18;
+#pragma unroll
+        for (int j = 0; j < 18; ++j) {
+            const double send = up ? a36[j] : a36[j + 18], keep = up ? a36[j + 18] : a36[j];
+            a36[j] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    if (G >= 4) {
+        constexpr int h = G >> 2;
+        const bool up = (gl & h) != 0;
+        if (up) start += 9;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const double send = up ? a36[j] : a36[j + 9], keep = up ? a36[j + 9] : a36[j];
+            a36[j] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+#pragma unroll
+    for (int h = G >> 3; h >= 1; h >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) a36[j] += __shfl_xor_sync(0xffffffffu, a36[j], h);
+    }
+    constexpr int cnt = G >= 4 ? 9 : (G == 2 ? 18 : 36);
+    const int q = lane >> LG;
+    const bool writer = q < nch && (G < 8 || (gl & ((G >> 2) - 1)) == 0);
+    if (writer) {
+        const int c = __ldg(sched_task + q);
+        double *out = part + (size_t)c * 42 + start;
+#pragma unroll
+        for (int j = 0; j < cnt; ++j) out[j] = a36[j];
+    }
+}
+
 template <int NT, int STAGES, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restrict__ segs, const int *__restrict__ cam_obs,
                                                           const int *__restrict__ cam_pt, const int *__restrict__ wrow_ptr,
@@ -574,41 +618,14 @@ __global__ void __launch_bounds__(NT, MINB) k_schur_ring(const seg_desc *__restr
         st = st + 1 == STAGES ? 0 : st + 1;
         sl_cur = sl_cur + 1 == RS ? 0 : sl_cur + 1; sl_far = sl_far + 1 == RS ? 0 : sl_far + 1; sl_new = sl_new + 1 == RS ? 0 : sl_new + 1;
         if (ci.x & 256) {                                           // last row of a task: sum over the G lanes of every chunk, partials out
-            const int lg = ci.x & 255, G = 1 << lg, gl = lane & (G - 1), nch = ci.x >> 16;
-            int start = 0;
-            if (G >= 2) {
-                const int h = G >> 1;
-                const bool up = (gl & h) != 0;
-                if (up) start += 18;
-#pragma unroll
-                for (int j = 0; j < 18; ++j) {
-                    const double send = up ? a36[j] : a36[j + 18], keep = up ? a36[j + 18] : a36[j];
-                    a36[j] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-                }
-            }
-            if (G >= 4) {
-                const int h = G >> 2;
-                const bool up = (gl & h) != 0;
-                if (up) start += 9;
-#pragma unroll
-                for (int j = 0; j < 9; ++j) {
-                    const double send = up ? a36[j] : a36[j + 9], keep = up ? a36[j + 9] : a36[j];
-                    a36[j] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-                }
-            }
-            for (int h = G >> 3; h >= 1; h >>= 1) {
-#pragma unroll
-                for (int j = 0; j < 9; ++j) a36[j] += __shfl_xor_sync(0xffffffffu, a36[j], h);
-            }
-            const int cnt = G >= 4 ? 9 : (G == 2 ? 18 : 36);
-            const int q = lane >> lg;
-            const bool writer = q < nch && (G < 8 || (gl & ((G >> 2) - 1)) == 0);
-            if (writer) {
-                const int c = __ldg(sched + ci.y + q);
-                double *out = part + (size_t)c * 42 + start;
-#pragma unroll
-                for (int j = 0; j < 36; ++j)
-                    if (j < cnt) out[j] = a36[j];
+            const int nch = ci.x >> 16;
+            switch (ci.x & 255) {                                   // one straight-line reduction per group size (no register shuffling at merges)
+            case 0: ring_task_reduce<0>(a36, lane, nch, sched + ci.y, part); break;
+            case 1: ring_task_reduce<1>(a36, lane, nch, sched + ci.y, part); break;
+            case 2: ring_task_reduce<2>(a36, lane, nch, sched + ci.y, part); break;
+            case 3: ring_task_reduce<3>(a36, lane, nch, sched + ci.y, part); break;
+            case 4: ring_task_reduce<4>(a36, lane, nch, sched + ci.y, part); break;
+            default: ring_task_reduce<5>(a36, lane, nch, sched + ci.y, part); break;
             }
 #pragma unroll
             for (int j = 0; j < 36; ++j) a36[j] = 0.0;
