@@ -583,9 +583,11 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
             k_segment_ptr<<<cdiv(o, 256), 256, 0, st>>>(o, m, skey, cp);
         }
     }
-    // point chunks: whole points, <= PT_CTA observations and <= PT_CTA points per CTA (greedy, host)
-    std::vector<int> pch(1, 0);
-    {
+    // point chunks: whole points, <= PT_CTA observations and <= PT_CTA points per CTA (greedy over the n points: a millisecond of
+    // host work at 1 M points) -- on the helper thread, under the sorts below; uploaded where the worker is joined
+    std::vector<int> pch(1, 0), small_chunks, big_chunks;
+    std::vector<int4> ptdesc_h;
+    host_worker::get().run([&pch, &small_chunks, &big_chunks, &ptdesc_h, &hptr, n, p0, o0]() {
         int cnt_o = 0, cnt_p = 0;
         for (int i = 0; i < n; ++i) {
             const int d = hptr[p0 + i + 1] - hptr[p0 + i];
@@ -593,22 +595,14 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
             cnt_o += d; cnt_p++;
         }
         if (n > 0) pch.push_back(n);
-    }
-    c->n_ptchunk = (int)pch.size() - 1;
-    c->ptchunk = supload(c, pch);
-    {
-        std::vector<int4> desc(c->n_ptchunk);            // {p0, p1, o0, o1}: one 16-byte load per CTA
-        for (int q = 0; q < c->n_ptchunk; ++q)
-            desc[q] = make_int4(pch[q], pch[q + 1], hptr[p0 + pch[q]] - o0, hptr[p0 + pch[q + 1]] - o0);
-        c->ptdesc = supload(c, desc);
+        const int nch = (int)pch.size() - 1;
+        ptdesc_h.resize(nch);                                  // {p0, p1, o0, o1}: one 16-byte load per CTA
+        for (int q = 0; q < nch; ++q)
+            ptdesc_h[q] = make_int4(pch[q], pch[q + 1], hptr[p0 + pch[q]] - o0, hptr[p0 + pch[q + 1]] - o0);
         // chunks that fit one wave go through the pipelined kernels; a chunk that is one point with more than
         // PT_CTA observations keeps the wave loop
-        std::vector<int> small, big;
-        for (int q = 0; q < c->n_ptchunk; ++q) (desc[q].w - desc[q].z <= PT_CTA ? small : big).push_back(q);
-        c->n_small = (int)small.size(); c->n_big = (int)big.size();
-        c->d_small_list = big.empty() ? nullptr : supload(c, small);
-        c->d_big_list = big.empty() ? nullptr : supload(c, big);
-    }
+        for (int q = 0; q < nch; ++q) (ptdesc_h[q].w - ptdesc_h[q].z <= PT_CTA ? small_chunks : big_chunks).push_back(q);
+    });
     {
         CUDA_CHECK(cudaMemcpyAsync(cptr.data(), cp, ((size_t)m + 1) * 4, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
@@ -672,6 +666,13 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
     c->pair_k = supload(c, pk); c->pair_l = supload(c, pl);
     // ---- camera system tiles (symbolic factorisation, 2 ms of host work at 2 000 cameras) on a helper thread, under the device
     // work and the host round trips of the segment / ring tables below (disjoint fields of the context, same stream)
+    host_worker::get().wait();                                // the point chunks
+    c->n_ptchunk = (int)pch.size() - 1;
+    c->ptchunk = supload(c, pch);
+    c->ptdesc = supload(c, ptdesc_h);
+    c->n_small = (int)small_chunks.size(); c->n_big = (int)big_chunks.size();
+    c->d_small_list = big_chunks.empty() ? nullptr : supload(c, small_chunks);
+    c->d_big_list = big_chunks.empty() ? nullptr : supload(c, big_chunks);
     host_worker::get().run([c, &pairs]() { psba_build_tile_structure(c, pairs); });     // no CUDA call inside: uploads are flushed below
     // ---- triple range of every pair, chunks of the pair pass
     long long *tptr = salloc<long long>(c, (size_t)c->n_pair + 1);
