@@ -666,14 +666,14 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
     c->pair_k = supload(c, pk); c->pair_l = supload(c, pl);
     // ---- camera system tiles (symbolic factorisation, 2 ms of host work at 2 000 cameras) on a helper thread, under the device
     // work and the host round trips of the segment / ring tables below (disjoint fields of the context, same stream)
-    host_worker::get().wait();                                // the point chunks
+    host_worker::get().wait();                                // the point chunks are done (uploaded below, under the next job)
+    host_worker::get().run([c, &pairs]() { psba_build_tile_structure(c, pairs); });     // no CUDA call inside: uploads are flushed below
     c->n_ptchunk = (int)pch.size() - 1;
     c->ptchunk = supload(c, pch);
     c->ptdesc = supload(c, ptdesc_h);
     c->n_small = (int)small_chunks.size(); c->n_big = (int)big_chunks.size();
     c->d_small_list = big_chunks.empty() ? nullptr : supload(c, small_chunks);
     c->d_big_list = big_chunks.empty() ? nullptr : supload(c, big_chunks);
-    host_worker::get().run([c, &pairs]() { psba_build_tile_structure(c, pairs); });     // no CUDA call inside: uploads are flushed below
     // ---- triple range of every pair, chunks of the pair pass
     long long *tptr = salloc<long long>(c, (size_t)c->n_pair + 1);
     k_pair_ptr<<<cdiv(c->n_pair + 1, 256), 256, 0, st>>>(c->n_pair, m, c->pair_k, c->pair_l, c->ntri, lkeys, tptr);
