@@ -667,7 +667,14 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
     // ---- camera system tiles (symbolic factorisation, 2 ms of host work at 2 000 cameras) on a helper thread, under the device
     // work and the host round trips of the segment / ring tables below (disjoint fields of the context, same stream)
     host_worker::get().wait();                                // the point chunks are done (uploaded below, under the next job)
-    host_worker::get().run([c, &pairs]() { psba_build_tile_structure(c, pairs); });     // no CUDA call inside: uploads are flushed below
+    const auto t_job = std::chrono::steady_clock::now();
+    host_worker::get().run([c, &pairs, t_job]() {          // no CUDA call inside: uploads are flushed below
+        const auto t_in = std::chrono::steady_clock::now();
+        psba_build_tile_structure(c, pairs);
+        if (getenv("PSBA_SETUP_TIMING"))
+            fprintf(stderr, "psba setup:   tiles: job picked up after %.2f ms, ran %.2f ms\n", std::chrono::duration<double, std::milli>(t_in - t_job).count(),
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_in).count());
+    });
     c->n_ptchunk = (int)pch.size() - 1;
     c->ptchunk = supload(c, pch);
     c->ptdesc = supload(c, ptdesc_h);
