@@ -769,7 +769,8 @@ void psba_set_scalars(psba_ctx *c, double mu, double a, double b)
 {
     // a captured chain copies from ITS slot (the replay writes the slot before the launch); plain launches rotate through
     // the other slots: a slot is rewritten 32 calls later at the earliest, and every try ends with a host synchronisation
-    const int slot = c->capturing ? c->capturing->slot : 32 + (c->h_mu_next++ & 31);
+    const int slot = c->capturing ? c->capturing->slot : 32 + c->h_mu_next;
+    if (!c->capturing) c->h_mu_next = (c->h_mu_next + 1) & 31;
     double *h = c->h_mu_ring + (size_t)slot * 4;
     h[0] = mu; h[1] = a; h[2] = b; h[3] = 0.0;
     CUDA_CHECK(cudaMemcpyAsync(c->d_mu, h, 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));

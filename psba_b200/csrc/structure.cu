@@ -433,7 +433,7 @@ static void build_segments(psba_ctx *c, const long long *tptr, const std::vector
         while (G & (G - 1)) G &= G - 1;
         c->pair_G = G;
     }
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    // the temporaries are freed in stream order (cudaFreeAsync): no host round trip here
     for (void *p : {(void *)cam_pos, (void *)cam_ptr, (void *)d_seglen, (void *)d_rsp, (void *)tri_seg, (void *)head, (void *)cid, (void *)ch_seg,
                     (void *)ch_pair, (void *)ch_diag, (void *)key0, (void *)key1, (void *)val0, (void *)seg_diag, (void *)sptr})
         psba_dev_free(c, p);
@@ -500,8 +500,7 @@ static void build_ring_tables(psba_ctx *c)
                                                      nullptr, c->ring_wrow_ptr, task);
     k_ring_rows<<<cdiv((long long)n_sched * 32, 256), 256, 0, st>>>(n_sched, task, c->sched_chunk, c->sch_beg, c->sch_end, c->tri_vr, c->tri_ob,
                                                                    c->ring_rows);
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    psba_dev_free(c, wrows); psba_dev_free(c, task);
+    psba_dev_free(c, wrows); psba_dev_free(c, task);       // stream-ordered frees: no host round trip
 }
 
 
@@ -684,17 +683,19 @@ void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
     // ---- triple range of every pair, chunks of the pair pass
     long long *tptr = salloc<long long>(c, (size_t)c->n_pair + 1);
     k_pair_ptr<<<cdiv(c->n_pair + 1, 256), 256, 0, st>>>(c->n_pair, m, c->pair_k, c->pair_l, c->ntri, lkeys, tptr);
-    int *ccnt = salloc<int>(c, (size_t)c->n_pair + 1), *nonempty = salloc<int>(c, 1);
-    CUDA_CHECK(cudaMemsetAsync(nonempty, 0, sizeof(int), st));
-    CUDA_CHECK(cudaMemsetAsync(ccnt, 0, ((size_t)c->n_pair + 1) * 4, st));
-    k_chunk_count<<<cdiv(c->n_pair, 256), 256, 0, st>>>(c->n_pair, 1, tptr, ccnt, nonempty);   // pch = 1: counts triples; only `nonempty` is used
-    int h_nonempty = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&h_nonempty, nonempty, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    // pair pass: 5 (default) = segment kernel (k_schur_segs), 0 = the pair-major gather kernel of round 1
+    // pair pass: 6 (default) = ring kernel, 5 = segment kernel, 0 = the pair-major gather kernel of round 1
     c->pair_mode = 6;
     if (getenv("PSBA_PAIR_MODE")) { const int pm = atoi(getenv("PSBA_PAIR_MODE")); c->pair_mode = pm == 0 ? 0 : (pm == 5 ? 5 : 6); }
     if (c->pair_mode == 6) ring_config(c);
+    int *ccnt = salloc<int>(c, (size_t)c->n_pair + 1), *nonempty = salloc<int>(c, 1);
+    int h_nonempty = 0;
+    if (c->pair_mode == 0) {                                  // mean run length of a pair (the other kernels do not need it: no round trip)
+        CUDA_CHECK(cudaMemsetAsync(nonempty, 0, sizeof(int), st));
+        CUDA_CHECK(cudaMemsetAsync(ccnt, 0, ((size_t)c->n_pair + 1) * 4, st));
+        k_chunk_count<<<cdiv(c->n_pair, 256), 256, 0, st>>>(c->n_pair, 1, tptr, ccnt, nonempty);   // pch = 1: counts triples; only `nonempty` is used
+        CUDA_CHECK(cudaMemcpyAsync(&h_nonempty, nonempty, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
     c->n_seg = 0; c->seg_desc = nullptr; c->sched_chunk = nullptr; c->sch_beg = c->sch_end = nullptr; c->tri_vr = nullptr;
     c->pchunk_pair = nullptr; c->pchunk_beg = c->pchunk_end = nullptr;
     if (c->pair_mode == 5 || c->pair_mode == 6) {
