@@ -151,18 +151,38 @@ void psba_flush_tile_uploads(psba_ctx *c)
     size_t total = 0;
     auto room = [](const pending_upload &u) { return std::max<size_t>(256, (u.bytes.size() + 255) & ~(size_t)255); };   // distinct addresses for empty tables
     for (pending_upload &u : q) if (!u.zero_bytes) total += room(u);
-    std::vector<char> stage(std::max<size_t>(total, 256));
-    c->tile_block = psba_dev_alloc(c, stage.size(), false);
-    c->tile_block_bytes = stage.size();
+    // the block is assembled in page-locked memory kept by the process (one set-up at a time; pageable memory otherwise)
+    static std::mutex pin_mu;
+    static char *pin_buf = nullptr; static size_t pin_cap = 0; static bool pin_busy = false;
+    const size_t need = std::max<size_t>(total, 256);
+    std::vector<char> pageable;
+    char *stage = nullptr;
+    {
+        std::lock_guard<std::mutex> l(pin_mu);
+        if (!pin_busy) {
+            if (pin_cap < need) {
+                if (pin_buf) cudaFreeHost(pin_buf);
+                pin_buf = nullptr; pin_cap = 0;
+                if (cudaHostAlloc((void **)&pin_buf, need + need / 2, cudaHostAllocDefault) == cudaSuccess) pin_cap = need + need / 2;
+                else { cudaGetLastError(); pin_buf = nullptr; }
+            }
+            if (pin_buf) { stage = pin_buf; pin_busy = true; }
+        }
+    }
+    const bool pinned = stage != nullptr;
+    if (!pinned) { pageable.resize(need); stage = pageable.data(); }
+    c->tile_block = psba_dev_alloc(c, need, false);
+    c->tile_block_bytes = need;
     size_t off = 0;
     for (pending_upload &u : q) {
         if (u.zero_bytes) { *u.dst = psba_dev_alloc(c, u.zero_bytes, true); continue; }
-        if (!u.bytes.empty()) memcpy(stage.data() + off, u.bytes.data(), u.bytes.size());
+        if (!u.bytes.empty()) memcpy(stage + off, u.bytes.data(), u.bytes.size());
         *u.dst = (char *)c->tile_block + off;
         off += room(u);
     }
-    CUDA_CHECK(cudaMemcpyAsync(c->tile_block, stage.data(), std::min(stage.size(), std::max<size_t>(off, 1)), cudaMemcpyHostToDevice, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));            // the staged bytes go out of scope
+    CUDA_CHECK(cudaMemcpyAsync(c->tile_block, stage, std::min(need, std::max<size_t>(off, 1)), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));            // the staged bytes are free again
+    if (pinned) { std::lock_guard<std::mutex> l(pin_mu); pin_busy = false; }
     q.clear();
 }
 
