@@ -123,12 +123,12 @@ static void nd_recurse(nd_ctx &x, std::vector<int> nodes)
 // The symbolic part below runs on a helper thread under device work of the set-up (structure.cu); it issues no CUDA call:
 // every upload / zero-filled allocation is recorded here and carried out by psba_flush_tile_uploads on the calling thread
 struct pending_upload { void **dst; std::vector<char> bytes; size_t zero_bytes; };
+static std::map<psba_ctx *, std::vector<pending_upload>> g_pending;   // one set-up at a time per context
+static std::mutex g_pending_mu;
 static std::vector<pending_upload> &pending(psba_ctx *c)
 {
-    static std::map<psba_ctx *, std::vector<pending_upload>> q;   // one set-up at a time per context
-    static std::mutex mu;
-    std::lock_guard<std::mutex> l(mu);
-    return q[c];
+    std::lock_guard<std::mutex> l(g_pending_mu);
+    return g_pending[c];
 }
 template <class T> static void up_vec(psba_ctx *c, T **d, const std::vector<T> &h)
 {
@@ -183,7 +183,7 @@ void psba_flush_tile_uploads(psba_ctx *c)
     CUDA_CHECK(cudaMemcpyAsync(c->tile_block, stage, std::min(need, std::max<size_t>(off, 1)), cudaMemcpyHostToDevice, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));            // the staged bytes are free again
     if (pinned) { std::lock_guard<std::mutex> l(pin_mu); pin_busy = false; }
-    q.clear();
+    { std::lock_guard<std::mutex> l(g_pending_mu); g_pending.erase(c); }   // `q` is gone from here on
 }
 
 void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int>> &pairs)

@@ -554,6 +554,10 @@ struct pinned_scratch {
 // ---- the build ---------------------------------------------------------------------------------------
 void psba_build_structure(psba_ctx *c, const int *iidx, const int *jidx)
 {
+    // one set-up at a time per process: the helper thread has ONE job slot (host_worker) and the page-locked scratch blocks are
+    // shared; two contexts set up from two host threads take turns here (the solves themselves run concurrently)
+    static std::mutex setup_mu;
+    std::lock_guard<std::mutex> setup_lock(setup_mu);
     cudaStream_t st = c->stream;
     const int m = c->m, ng = c->n_glob, og = c->o_glob;
     lap_timer T(c);
