@@ -182,6 +182,20 @@ double psba_get_stat(psba_ctx *ctx, const char *name);
  * "pchunk_pair" (n_pchunk), "cam2pos" (m); int64: "pchunk_beg"/"pchunk_end" (n_pchunk).  These replace
  * blk_idx / comm3DIdx / comm3DIdxCnt of generate_idxs (PSBA/misc.cpp:178-218). */
 long long psba_get_index(psba_ctx *ctx, const char *name, void *out, long long max_count);
+/* camera-system plan readback (test hook; HOST ONLY -- needs no GPU and no context).  Runs the set-up's host stage for the
+ * camera system of `nCams` cameras whose coupled pairs are (pair_k[q], pair_l[q]), q < npairs (either triangle; the diagonal
+ * is implied): nested-dissection ordering of the 8-camera tiles, symbolic factorisation, step schedule and task lists of the
+ * tiled factorisation that replaces SPDinv / cholmod_blk (PSBA/cl_spdinv.cpp:57-103, CL_files/SPD_inv.cl:20-239) -- exactly
+ * the tables fill_idxBuffer uploads.  psba_plan_get copies the named int32 table to `out` (at most max_count elements; out may be
+ * NULL) and returns its length, -1 for an unknown name:
+ *   "stats" = {nt, n_steps, n_tiles_S, n_tiles, one panel per step?}, "cam2pos" (m), "tile_index" (nt*nt, slot of factor tile
+ *   (I,J), I >= J in the solver's order, -1 = structurally zero), "step_panels" + "step_panel_ptr" (panels of every step),
+ *   "crit_I"/"crit_K" + "step_crit_ptr" (panel CTAs), "psrc_ptr"/"psrc" (source panels a panel's own CTAs apply),
+ *   "def_I"/"def_J"/"def_sptr"/"def_src" + "step_def_ptr" (deferred trailing updates: target tile, source panels, step),
+ *   "b_J"/"b_sptr"/"b_slot" + "step_b_ptr" (right-hand-side tasks).  tests/test_tile_plan_cpu.py replays the plan in numpy. */
+void *psba_plan_open(int nCams, long long npairs, const int *pair_k, const int *pair_l);
+long long psba_plan_get(void *plan, const char *name, int *out, long long max_count);
+void psba_plan_close(void *plan);
 /* lambda-follow hook for parity runs: the k-th modified-Cholesky event uses lam[k] */
 void psba_force_lambda(psba_ctx *ctx, const double *lam, int n);
 /* copy current parameters to the host: cams[m*6], pts[n*3] (either may be NULL) */

@@ -127,6 +127,11 @@ def lib():
     L.psba_comm_unique_id.argtypes = [C.c_char_p]
     L.psba_comm_init.argtypes = [i, i, C.c_char_p]
     L.psba_local_range.argtypes = [i, i, _ip, i, i, _ip, _ip, _ip, _ip]
+    L.psba_plan_open.restype = vp
+    L.psba_plan_open.argtypes = [i, C.c_longlong, _ip, _ip]
+    L.psba_plan_get.restype = C.c_longlong
+    L.psba_plan_get.argtypes = [vp, C.c_char_p, _ip, C.c_longlong]
+    L.psba_plan_close.argtypes = [vp]
     L.psba_version.restype = C.c_char_p
     _lib = L
     return L
@@ -211,6 +216,31 @@ def local_range(n, o, iidx, rank, nranks):
     a = np.ascontiguousarray(iidx, dtype=np.int32)
     L.psba_local_range(n, o, _i(a), rank, nranks, *[C.byref(x) for x in v])
     return tuple(x.value for x in v)
+
+
+PLAN_TABLES = ("stats", "cam2pos", "tile_index", "step_panels", "step_panel_ptr", "crit_I", "crit_K", "step_crit_ptr", "psrc_ptr", "psrc",
+               "def_I", "def_J", "def_sptr", "def_src", "step_def_ptr", "b_J", "b_sptr", "b_slot", "step_b_ptr")
+
+
+def plan_tiles(m, pair_k, pair_l):
+    """Host stage of the camera-system set-up (ordering, symbolic factor, step schedule, task lists) as numpy tables; no GPU needed
+    (psba_plan_open / psba_plan_get in include/psba_b200.h)."""
+    L = lib()
+    k = np.ascontiguousarray(pair_k, dtype=np.int32)
+    l = np.ascontiguousarray(pair_l, dtype=np.int32)
+    h = L.psba_plan_open(int(m), len(k), _i(k), _i(l))
+    if not h:
+        raise ValueError("psba_plan_open refused the pair list")
+    try:
+        out = {}
+        for name in PLAN_TABLES:
+            n = L.psba_plan_get(h, name.encode(), None, 0)
+            a = np.zeros(max(int(n), 1), dtype=np.int32)
+            L.psba_plan_get(h, name.encode(), _i(a), n)
+            out[name] = a[:n]
+        return out
+    finally:
+        L.psba_plan_close(h)
 
 
 class _Pinned(np.ndarray):

@@ -24,6 +24,8 @@
 #include <chrono>
 #include <map>
 #include <mutex>
+#include <string>
+#include <cstring>
 
 #define LDT (TS + 1)            // padded leading dimension in shared memory
 #define TILE_SM (TS * LDT)      // doubles per shared tile
@@ -459,6 +461,58 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
 
 // ---------------------------------------------------------------------------------------------
 // a 48x48 tile travels global -> registers (all loads in flight at once) -> padded shared memory
+// ---- host-only readback of the plan (include/psba_b200.h: psba_plan_open / _get / _close; tests/test_tile_plan_cpu.py) --------
+// psba_build_tile_structure issues no CUDA call and records its uploads in g_pending: run it on a throwaway context and keep the
+// tables as host arrays.
+struct psba_plan { std::map<std::string, std::vector<int>> arr; };
+extern "C" void *psba_plan_open(int nCams, long long npairs, const int *pair_k, const int *pair_l)
+{
+    if (nCams <= 0 || npairs < 0 || (npairs > 0 && (!pair_k || !pair_l))) return nullptr;
+    std::vector<std::pair<int, int>> pairs;
+    pairs.reserve((size_t)npairs);
+    for (long long q = 0; q < npairs; ++q) {
+        if (pair_k[q] < 0 || pair_k[q] >= nCams || pair_l[q] < 0 || pair_l[q] >= nCams) return nullptr;
+        pairs.push_back({pair_k[q], pair_l[q]});
+    }
+    psba_ctx *c = new psba_ctx();                      // value-initialised: no stream, no device memory
+    c->m = nCams; c->N = 6 * nCams;
+    c->chol_flow = getenv("PSBA_CHOL_FLOW") && atoi(getenv("PSBA_CHOL_FLOW")) != 0;
+    psba_build_tile_structure(c, pairs);
+    psba_plan *pl = new psba_plan();
+    pl->arr["stats"] = {c->nt, c->n_steps, c->n_tiles_S, c->n_tiles, c->chain_schedule ? 1 : 0};
+    pl->arr["cam2pos"] = c->h_cam2pos;
+    pl->arr["tile_index"] = c->h_tile_index;
+    pl->arr["step_crit_ptr"] = c->step_crit_ptr; pl->arr["step_def_ptr"] = c->step_def_ptr;
+    pl->arr["step_b_ptr"] = c->step_b_ptr; pl->arr["step_panel_ptr"] = c->step_panel_ptr;
+    const std::pair<const char *, void **> named[] = {
+        {"crit_I", (void **)&c->d_crit_I}, {"crit_K", (void **)&c->d_crit_K}, {"psrc_ptr", (void **)&c->d_psrc_ptr}, {"psrc", (void **)&c->d_psrc},
+        {"def_I", (void **)&c->d_def_I}, {"def_J", (void **)&c->d_def_J}, {"def_sptr", (void **)&c->d_def_sptr}, {"def_src", (void **)&c->d_def_src},
+        {"b_J", (void **)&c->d_b_J}, {"b_sptr", (void **)&c->d_b_sptr}, {"b_slot", (void **)&c->d_b_slot}, {"step_panels", (void **)&c->d_step_panels}};
+    {
+        std::lock_guard<std::mutex> l(g_pending_mu);
+        for (const pending_upload &u : g_pending[c])
+            for (const auto &nm : named)
+                if (u.dst == nm.second) {
+                    const int *b = (const int *)u.bytes.data();
+                    pl->arr[nm.first].assign(b, b + u.bytes.size() / sizeof(int));
+                }
+        g_pending.erase(c);
+    }
+    delete c;
+    return pl;
+}
+extern "C" long long psba_plan_get(void *plan, const char *name, int *out, long long max_count)
+{
+    if (!plan || !name) return -1;
+    const psba_plan *pl = (const psba_plan *)plan;
+    const auto it = pl->arr.find(name);
+    if (it == pl->arr.end()) return -1;
+    const long long len = (long long)it->second.size();
+    if (out && max_count > 0 && len > 0) memcpy(out, it->second.data(), (size_t)std::min(len, max_count) * sizeof(int));
+    return len;
+}
+extern "C" void psba_plan_close(void *plan) { delete (psba_plan *)plan; }
+
 template <int NT> struct TileRegs { double2 v[(TS * TS / 2 + NT - 1) / NT]; };
 // CG: the tile may have been written by another CTA of the SAME launch (dataflow factorisation): read it through L2
 template <int NT, bool CG = false>
