@@ -47,6 +47,13 @@ struct nd_ctx {
     std::vector<int> mark, dist;
     int tag;
     int min_size;
+    // degree of a root candidate counted inside the subgraph (PSBA_ND_ROOT=1) instead of in the whole tile graph (default, what
+    // every GPU measurement of rounds 1-2 ran with).  In a band every tile has the same degree in the whole graph, so the default
+    // takes the FIRST tile of the last level, not the end of the band: the level structure then starts [1, 15, 8, ...] and a 23-tile
+    // segment splits into 1 + 13..15 (separator) + 9.  Counted inside the subgraph the root is the end of the band, every separator
+    // of the headline ring is 8 tiles and the schedule has 49 steps instead of 56 (same 4 506 factor tiles; CPU-checked plan,
+    // tests/test_tile_plan_cpu.py) -- found after the GPU budget of round 2 was spent, hence not yet the default.
+    bool subset_degree = false;
     std::vector<int> order;
     std::vector<int> front;     // front[p]: id of the leaf / separator the tile at position p belongs to (consecutive positions)
     int n_front = 0;
@@ -90,8 +97,12 @@ static void nd_recurse(nd_ctx &x, std::vector<int> nodes)
     for (int it = 0; it < 4; ++it) {
         int best = -1;
         size_t bdeg = (size_t)-1;
-        for (int v : visit)
-            if (x.dist[v] == nlev - 1 && (*x.adj)[v].size() < bdeg) { bdeg = (*x.adj)[v].size(); best = v; }
+        for (int v : visit) {
+            if (x.dist[v] != nlev - 1) continue;
+            size_t deg = (*x.adj)[v].size();
+            if (x.subset_degree) { deg = 0; for (int w : (*x.adj)[v]) deg += x.mark[w] == tag; }
+            if (deg < bdeg) { bdeg = deg; best = v; }
+        }
         for (int v : nodes) x.dist[v] = -1;
         int nl2 = 0;
         nd_bfs(x, best, tag, visit, nl2);
@@ -215,6 +226,7 @@ void psba_build_tile_structure(psba_ctx *c, const std::vector<std::pair<int, int
         int min_size = e ? atoi(e) : 12;
         nd_ctx x;
         x.adj = &adj; x.mark.assign(nt, 0); x.dist.assign(nt, -1); x.tag = 0; x.min_size = std::max(1, min_size);
+        x.subset_degree = getenv("PSBA_ND_ROOT") && atoi(getenv("PSBA_ND_ROOT")) != 0;
         std::vector<int> all(nt);
         for (int t = 0; t < nt; ++t) all[t] = t;
         if (min_size <= 0 || min_size >= nt) x.append(all);      // natural order

@@ -277,6 +277,26 @@ def test_leaf_size_switch_gives_valid_plans(nd_min, monkeypatch):
         assert info["n_steps"] < info["nt"]
 
 
+@pytest.mark.parametrize("case", ["headline ring 2000 / 64", "ring 500 / 64", "open band 400 / 30", "two disjoint rings", "random sparse 600"])
+def test_root_by_degree_inside_the_subgraph(case, monkeypatch):
+    """PSBA_ND_ROOT=1 (opt-in): the pseudo-peripheral root is the lowest-degree tile of the last level with the degree counted INSIDE
+    the subgraph, i.e. the end of a band; the headline ring then has 8-tile separators throughout and 49 steps instead of 56, with
+    the same factor tiles and no larger task lists than the default plan the GPU runs were made with."""
+    m, k, l = CASES[case]()
+    P0, i0 = check_plan(m, k, l)
+    monkeypatch.setenv("PSBA_ND_ROOT", "1")
+    P1, i1 = check_plan(m, k, l)
+    replay(P1, i1, seed=11)
+    if "random" not in case:                      # a heuristic: on band-shaped graphs it never lengthens the chain
+        assert i1["n_steps"] <= i0["n_steps"]
+    if case.startswith("headline"):
+        assert (i0["n_steps"], i1["n_steps"]) == (56, 49) and len(i1["present"]) == len(i0["present"]) == 4506
+        assert max(len(r) for r in i1["rows"]) <= max(len(r) for r in i0["rows"])
+        assert max(len(x) for x in i1["psrc_of"]) <= max(len(x) for x in i0["psrc_of"])
+        assert int(np.diff(P1["def_sptr"]).max()) <= int(np.diff(P0["def_sptr"]).max())
+        assert int(np.diff(P1["b_sptr"]).max()) <= int(np.diff(P0["b_sptr"]).max())
+
+
 @pytest.mark.parametrize("knobs", [("0", "3"), ("2", "1"), ("2", "8")])
 def test_deferral_switches_give_valid_plans(knobs, monkeypatch):
     monkeypatch.setenv("PSBA_DEF_MERGE", knobs[0])
