@@ -438,17 +438,25 @@ def main():
                 "modified_cholesky_events": int(G.stat("cholmod_events")),
                 "pattern": "".join("C" if q["phase"] == 2 else ("A" if q["accepted"] else "x") for q in tr)}
 
+    # the two legs below are reported beside the measurement; a failure in one of them (oracle not buildable on this box, a data file
+    # missing) is recorded in its entry and must not cost the line
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        run_cpu("port", cores, CPU_SAMPLE, 1)
-        v, cits, secs, kind, desc, o_s = run_cpu("port", cores, CPU_SAMPLE, 3)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc,
-               "lm_iters_per_sec_scaled_to_workload": cits * o_s / o}
+        try:
+            run_cpu("port", cores, CPU_SAMPLE, 1)
+            v, cits, secs, kind, desc, o_s = run_cpu("port", cores, CPU_SAMPLE, 3)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc,
+                   "lm_iters_per_sec_scaled_to_workload": cits * o_s / o}
+        except Exception as e:                                # noqa: BLE001
+            cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": CPU_SAMPLE, "error": repr(e)[:300]}
 
     # ---- informational: FULL LM + trust-region solves (the reference's main loop) on BAL-size problems
     bal = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        bal = bal_full_solves(cores)
+        try:
+            bal = bal_full_solves(cores)
+        except Exception as e:                                # noqa: BLE001
+            bal = {"error": repr(e)[:300]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
