@@ -188,6 +188,25 @@ def bal_full_solves(cores):
     return out
 
 
+def run_experiment(env, steps, workload):
+    """An opt-in switch of the library measured beside the headline number: the same LM iterations in a CHILD process (its own CUDA
+    context; a crash or a hang there costs only this entry), never the reported value.  Returns what the child's line says."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--steps", str(steps), "--warmup", "3", "--workload", workload,
+           "--no-e2e", "--no-cpu-baseline", "--no-full-solve", "--no-experiments"]
+    try:
+        r = subprocess.run(cmd, env=dict(os.environ, **env), capture_output=True, text=True, timeout=240)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"env": env, "error": "rc=%d %s" % (r.returncode, r.stderr.strip()[-200:])}
+        d = json.loads(lines[-1])
+        kt = d.get("kernels", {})
+        return {"env": env, "ms_per_step": d["ms_per_step"], "value": d["value"], "steps": d["steps"], "parity_vs_1gpu": d.get("parity_vs_1gpu"),
+                "chol_graph_ms": kt.get("chol_graph", {}).get("ms_avg"), "k_tri_solve_ms": kt.get("k_tri_solve", {}).get("ms_avg"),
+                "dependent_panel_steps": (d.get("roofline_fp64") or {}).get("dependent_panel_steps")}
+    except Exception as e:                                    # noqa: BLE001  (timeout, unparsable output)
+        return {"env": env, "error": repr(e)[:300]}
+
+
 def lm_parity(workload, costs):
     """per-iteration LM costs of the timed run against the 1-GPU values stored in tests/golden/headline_lm_costs.json
     (tools/make_headline_golden.py wrote them from a single-GPU run): every rank count must walk the same trajectory"""
@@ -233,6 +252,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-full-solve", action="store_true")
+    ap.add_argument("--no-experiments", action="store_true")
     args = ap.parse_args()
     K, W = args.steps, max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -458,6 +478,14 @@ def main():
         except Exception as e:                                # noqa: BLE001
             bal = {"error": repr(e)[:300]}
 
+    # ---- informational: opt-in switches that were found after the last GPU measurement of the round, each in a child process;
+    # `value` above is the default path.  PSBA_ND_ROOT=1: root of the dissection's level structures by its degree inside the
+    # subgraph -- 49 instead of 56 dependent factorisation steps on this workload (plan checked on the CPU, tests/test_tile_plan_cpu.py)
+    experiments = None
+    if rank == 0 and world == 1 and not args.no_experiments and not args.no_cpu_baseline:
+        experiments = {"note": "opt-in switches measured in child processes beside the default path; not part of `value`",
+                       "nd_root_by_subgraph_degree": run_experiment({"PSBA_ND_ROOT": "1"}, K, args.workload)}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / max(its, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -465,7 +493,7 @@ def main():
                 "lm_iters_per_sec": its / (ms * 1e-3), "tries": tries, "lm_iterations": its, "final_cost": final_cost,
                 "gpu_launches": launches, "setup_seconds": round(setup_s, 3), "parity_vs_1gpu": parity,
                 "clocks": clocks, "e2e": e2e, "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu, "kernels": ktab,
-                "full_solve": full, "bal_full_solves": bal}
+                "full_solve": full, "bal_full_solves": bal, "experiments": experiments}
         emit(line)
     G.close()
     if world > 1:
