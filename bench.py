@@ -192,7 +192,7 @@ def run_experiment(env, steps, workload):
     """An opt-in switch of the library measured beside the headline number: the same LM iterations in a CHILD process (its own CUDA
     context; a crash or a hang there costs only this entry), never the reported value.  Returns what the child's line says."""
     cmd = [sys.executable, os.path.abspath(__file__), "--steps", str(steps), "--warmup", "3", "--workload", workload,
-           "--no-e2e", "--no-cpu-baseline", "--no-full-solve", "--no-experiments"]
+           "--no-e2e", "--no-cpu-baseline", "--no-experiments"]
     try:
         r = subprocess.run(cmd, env=dict(os.environ, **env), capture_output=True, text=True, timeout=240)
         lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
@@ -202,7 +202,9 @@ def run_experiment(env, steps, workload):
         kt = d.get("kernels", {})
         return {"env": env, "ms_per_step": d["ms_per_step"], "value": d["value"], "steps": d["steps"], "parity_vs_1gpu": d.get("parity_vs_1gpu"),
                 "chol_graph_ms": kt.get("chol_graph", {}).get("ms_avg"), "k_tri_solve_ms": kt.get("k_tri_solve", {}).get("ms_avg"),
-                "dependent_panel_steps": (d.get("roofline_fp64") or {}).get("dependent_panel_steps")}
+                "dependent_panel_steps": (d.get("roofline_fp64") or {}).get("dependent_panel_steps"),
+                "full_solve": {k: (d.get("full_solve") or {}).get(k) for k in ("ms", "outer_iterations", "tries", "exit_flag", "final_cost",
+                                                                                "modified_cholesky_events")}}
     except Exception as e:                                    # noqa: BLE001  (timeout, unparsable output)
         return {"env": env, "error": repr(e)[:300]}
 
