@@ -486,7 +486,9 @@ def main():
     experiments = None
     if rank == 0 and world == 1 and not args.no_experiments and not args.no_cpu_baseline:
         experiments = {"note": "opt-in switches measured in child processes beside the default path; not part of `value`",
-                       "nd_root_by_subgraph_degree": run_experiment({"PSBA_ND_ROOT": "1"}, K, args.workload)}
+                       "nd_root_by_subgraph_degree": run_experiment({"PSBA_ND_ROOT": "1"}, K, args.workload),
+                       # leaf size 24 with the default root rule: measured once at the end of round 2 (factorisation 1.02 -> 0.98 ms)
+                       "nd_min_24": run_experiment({"PSBA_ND_MIN": "24"}, K, args.workload)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
