@@ -339,3 +339,13 @@ def test_chains_as_cuda_graphs_give_the_same_bits(key):
     assert out[0][1] == out[1][1]
     assert out[0][2] > 0 and out[1][2] == 0
     assert out[0][3] == out[1][3]                     # the launch count of a replayed chain is the count of the captured one
+
+
+@pytest.mark.xfail(strict=False, reason="PSBA_ND_ROOT=1 is an opt-in found after the GPU budget of round 2 was spent: its plan is checked on the "
+                                        "CPU (tests/test_tile_plan_cpu.py) but no GPU run had seen it when the round ended; this records the first one")
+def test_opt_in_root_rule_of_the_tile_ordering_on_the_gpu():
+    """tools/nd_root_check.py in its own process (a time limit, its own CUDA context): S^-1, dpa, LM trajectory and a whole
+    LM + trust-region solve on banded rings under PSBA_ND_ROOT=1 against the oracle."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "nd_root_check.py")], env=dict(os.environ, PSBA_ND_ROOT="1"),
+                       capture_output=True, text=True, timeout=900)
+    assert "ND_ROOT_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
