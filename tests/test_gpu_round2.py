@@ -347,5 +347,5 @@ def test_opt_in_root_rule_of_the_tile_ordering_on_the_gpu():
     """tools/nd_root_check.py in its own process (a time limit, its own CUDA context): S^-1, dpa, LM trajectory and a whole
     LM + trust-region solve on banded rings under PSBA_ND_ROOT=1 against the oracle."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "nd_root_check.py")], env=dict(os.environ, PSBA_ND_ROOT="1"),
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=300)
     assert "ND_ROOT_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
