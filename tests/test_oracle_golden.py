@@ -158,6 +158,43 @@ def test_cholmod_on_spd_matrix_is_plain_cholesky():
     assert np.max(np.abs(diag)) < 1e-9 * np.max(np.diag(S))
 
 
+@pytest.mark.parametrize("kind,N", [("indefinite", 12), ("indefinite", 30), ("rank-deficient", 42), ("negative definite", 24), ("one bad pivot", 36)])
+def test_cholmod_defining_properties_on_non_positive_matrices(kind, N):
+    """cholmod_blk.cl cannot be compiled here, so its restatement (orc_chol.c) is pinned by what the algorithm DEFINES (SURVEY App. A.4,
+    PSBA/cl_cholmod.cpp:25-202): L L^T = S + diag(E) with the off-diagonal part reproduced to rounding, E >= 0, S + diag(E) positive
+    (semi)definite, the modified path taken exactly when S is not safely positive definite, and E = what compute_cholmod_E returns."""
+    rng = np.random.default_rng(N)
+    M = rng.normal(size=(N, N))
+    if kind == "indefinite":
+        S = M + M.T
+    elif kind == "rank-deficient":
+        B = rng.normal(size=(N, N - 7))                   # 7 = the gauge null space of a bundle-adjustment camera system
+        S = B @ B.T
+    elif kind == "negative definite":
+        S = -(M @ M.T) - np.eye(N)
+    else:
+        S = M @ M.T + 1e-12 * np.eye(N)
+        S[3, 3] -= 1.5 * S[3, 3]
+    L = oracle.lib()
+    mat = S.copy(); aux = np.zeros(3 * N); dinv = np.zeros(3 * N); E = np.zeros(N)
+    delta, beta = oracle.C.c_double(), oracle.C.c_double()
+    L.orc_get_delta_beta(oracle._d(mat), N, oracle.C.byref(delta), oracle.C.byref(beta))
+    assert delta.value > 0 and beta.value > 0
+    ns = oracle.C.c_int()
+    L.orc_cholmod_blk(oracle._d(mat), oracle._d(aux), oracle._d(dinv), oracle._d(E), N, beta.value, delta.value, oracle.C.byref(ns))
+    Lf = np.tril(mat)
+    L.orc_cholmod_E(oracle._d(mat), oracle._d(E), N)
+    assert ns.value >= 1                                    # at least one 3-column block left the fast path
+    scale = np.abs(S).max()
+    R = Lf @ Lf.T - S
+    assert np.abs(R - np.diag(np.diag(R))).max() < 1e-13 * scale
+    assert np.abs(np.diag(R) - E).max() < 1e-12 * max(scale, np.abs(E).max())
+    assert E.min() > -1e-12 * scale
+    assert np.linalg.eigvalsh(S + np.diag(E)).min() > -1e-12 * max(scale, np.abs(E).max())
+    if kind != "rank-deficient":
+        assert E.max() > 0.1 * abs(np.linalg.eigvalsh(S).min())      # a real shift, not rounding
+
+
 @pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("key", ["7", "54"])
 def test_restatement_vs_reference_kernels_stagewise(key):
