@@ -16,6 +16,7 @@ place, else the C restatement) on a bounded sample of the same workload, all hos
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -233,7 +234,15 @@ _REAL_STDOUT = None
 
 def emit(line):
     """the ONE JSON line goes to the process's original stdout; everything else any library prints was sent to stderr"""
-    data = (json.dumps(line) + "\n").encode()
+    def finite(x):                                      # strict JSON: a NaN / inf (a failed solve in an informational leg) becomes null
+        if isinstance(x, float) and not math.isfinite(x):
+            return None
+        if isinstance(x, dict):
+            return {k: finite(v) for k, v in x.items()}
+        if isinstance(x, (list, tuple)):
+            return [finite(v) for v in x]
+        return x
+    data = (json.dumps(finite(line), allow_nan=False) + "\n").encode()
     if _REAL_STDOUT is None:
         sys.stdout.write(data.decode()); sys.stdout.flush()
     else:
