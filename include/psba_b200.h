@@ -192,7 +192,10 @@ long long psba_get_index(psba_ctx *ctx, const char *name, void *out, long long m
  *   (I,J), I >= J in the solver's order, -1 = structurally zero), "step_panels" + "step_panel_ptr" (panels of every step),
  *   "crit_I"/"crit_K" + "step_crit_ptr" (panel CTAs), "psrc_ptr"/"psrc" (source panels a panel's own CTAs apply),
  *   "def_I"/"def_J"/"def_sptr"/"def_src" + "step_def_ptr" (deferred trailing updates: target tile, source panels, step),
- *   "b_J"/"b_sptr"/"b_slot" + "step_b_ptr" (right-hand-side tasks).  tests/test_tile_plan_cpu.py replays the plan in numpy. */
+ *   "b_J"/"b_sptr"/"b_slot" + "step_b_ptr" (right-hand-side tasks), and the flat records the step kernels load, as consecutive ints:
+ *   "crit_desc" (8 per panel CTA: I, K, slot(I,K), slot(K,K), first source, end source, 0, 0), "crit_src" (2 per source: slot(K,P),
+ *   slot(I,P) or -1), "def_desc" (4 per deferred task: slot(I,J), first source, end source, 0), "def_srcs" (2 per source: slot(I,P),
+ *   slot(J,P)).  tests/test_tile_plan_cpu.py replays the plan in numpy. */
 void *psba_plan_open(int nCams, long long npairs, const int *pair_k, const int *pair_l);
 long long psba_plan_get(void *plan, const char *name, int *out, long long max_count);
 void psba_plan_close(void *plan);

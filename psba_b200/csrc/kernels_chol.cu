@@ -499,7 +499,9 @@ extern "C" void *psba_plan_open(int nCams, long long npairs, const int *pair_k, 
     const std::pair<const char *, void **> named[] = {
         {"crit_I", (void **)&c->d_crit_I}, {"crit_K", (void **)&c->d_crit_K}, {"psrc_ptr", (void **)&c->d_psrc_ptr}, {"psrc", (void **)&c->d_psrc},
         {"def_I", (void **)&c->d_def_I}, {"def_J", (void **)&c->d_def_J}, {"def_sptr", (void **)&c->d_def_sptr}, {"def_src", (void **)&c->d_def_src},
-        {"b_J", (void **)&c->d_b_J}, {"b_sptr", (void **)&c->d_b_sptr}, {"b_slot", (void **)&c->d_b_slot}, {"step_panels", (void **)&c->d_step_panels}};
+        {"b_J", (void **)&c->d_b_J}, {"b_sptr", (void **)&c->d_b_sptr}, {"b_slot", (void **)&c->d_b_slot}, {"step_panels", (void **)&c->d_step_panels},
+        // the flat descriptors the step kernels read (int4 / int2 records as consecutive ints)
+        {"crit_desc", (void **)&c->d_crit_desc}, {"crit_src", (void **)&c->d_crit_src}, {"def_desc", (void **)&c->d_def_desc}, {"def_srcs", (void **)&c->d_def_srcs}};
     {
         std::lock_guard<std::mutex> l(g_pending_mu);
         for (const pending_upload &u : g_pending[c])

@@ -167,6 +167,22 @@ def check_plan(m, k, l):
                 got_b.setdefault(J, []).append(p)
     for J in range(nt):
         assert sorted(got_b.get(J, [])) == sorted(p for p in cols[J] if step[p] != step[J] - 1)
+    # ---- the flat records the step kernels load say the same as the lists
+    cd, cs = P["crit_desc"].reshape(-1, 8), P["crit_src"].reshape(-1, 2)
+    assert len(cd) == len(cI)
+    for t in range(len(cI)):
+        I, K = int(cI[t]), int(cK[t])
+        assert cd[t, :4].tolist() == [I, K, ti[I, K], ti[K, K]]
+        src = cs[cd[t, 4]:cd[t, 5]].tolist()
+        assert src == [[int(ti[K, p]), -1 if I == K else int(ti[I, p])] for p in psrc_of[K]]
+        assert all(a >= 0 for a, _ in src)
+    dd, ds = P["def_desc"].reshape(-1, 4), P["def_srcs"].reshape(-1, 2)
+    assert len(dd) == len(dI)
+    for t in range(len(dI)):
+        I, J = int(dI[t]), int(dJ[t])
+        assert dd[t, 0] == ti[I, J]
+        want = [[int(ti[I, p]), int(ti[J, p])] for p in dsrc[dsp[t]:dsp[t + 1]].tolist()]
+        assert ds[dd[t, 1]:dd[t, 2]].tolist() == want and all(a >= 0 and b >= 0 for a, b in want)
     return P, dict(nt=nt, n_steps=n_steps, rows=rows, cols=cols, step=step, present=present, psrc_of=psrc_of, n_updates=n_updates,
                    slot2tile=slot2tile)
 
