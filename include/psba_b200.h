@@ -195,7 +195,8 @@ long long psba_get_index(psba_ctx *ctx, const char *name, void *out, long long m
  *   "b_J"/"b_sptr"/"b_slot" + "step_b_ptr" (right-hand-side tasks), and the flat records the step kernels load, as consecutive ints:
  *   "crit_desc" (8 per panel CTA: I, K, slot(I,K), slot(K,K), first source, end source, 0, 0), "crit_src" (2 per source: slot(K,P),
  *   slot(I,P) or -1), "def_desc" (4 per deferred task: slot(I,J), first source, end source, 0), "def_srcs" (2 per source: slot(I,P),
- *   slot(J,P)).  tests/test_tile_plan_cpu.py replays the plan in numpy. */
+ *   slot(J,P)); "bw_order" (panel of every CTA of the backward solve) with "coltile_ptr"/"coltile_row"/"coltile_slot" (tile column of a
+ *   panel).  tests/test_tile_plan_cpu.py replays the plan in numpy. */
 void *psba_plan_open(int nCams, long long npairs, const int *pair_k, const int *pair_l);
 long long psba_plan_get(void *plan, const char *name, int *out, long long max_count);
 void psba_plan_close(void *plan);

@@ -220,7 +220,7 @@ def local_range(n, o, iidx, rank, nranks):
 
 PLAN_TABLES = ("stats", "cam2pos", "tile_index", "step_panels", "step_panel_ptr", "crit_I", "crit_K", "step_crit_ptr", "psrc_ptr", "psrc",
                "def_I", "def_J", "def_sptr", "def_src", "step_def_ptr", "b_J", "b_sptr", "b_slot", "step_b_ptr",
-               "crit_desc", "crit_src", "def_desc", "def_srcs")
+               "crit_desc", "crit_src", "def_desc", "def_srcs", "bw_order", "coltile_ptr", "coltile_row", "coltile_slot")
 
 
 def plan_tiles(m, pair_k, pair_l):

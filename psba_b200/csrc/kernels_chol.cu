@@ -501,7 +501,8 @@ extern "C" void *psba_plan_open(int nCams, long long npairs, const int *pair_k, 
         {"def_I", (void **)&c->d_def_I}, {"def_J", (void **)&c->d_def_J}, {"def_sptr", (void **)&c->d_def_sptr}, {"def_src", (void **)&c->d_def_src},
         {"b_J", (void **)&c->d_b_J}, {"b_sptr", (void **)&c->d_b_sptr}, {"b_slot", (void **)&c->d_b_slot}, {"step_panels", (void **)&c->d_step_panels},
         // the flat descriptors the step kernels read (int4 / int2 records as consecutive ints)
-        {"crit_desc", (void **)&c->d_crit_desc}, {"crit_src", (void **)&c->d_crit_src}, {"def_desc", (void **)&c->d_def_desc}, {"def_srcs", (void **)&c->d_def_srcs}};
+        {"bw_order", (void **)&c->d_bw_order}, {"coltile_ptr", (void **)&c->d_coltile_ptr}, {"coltile_row", (void **)&c->d_coltile_row},
+        {"coltile_slot", (void **)&c->d_coltile_slot}, {"crit_desc", (void **)&c->d_crit_desc}, {"crit_src", (void **)&c->d_crit_src}, {"def_desc", (void **)&c->d_def_desc}, {"def_srcs", (void **)&c->d_def_srcs}};
     {
         std::lock_guard<std::mutex> l(g_pending_mu);
         for (const pending_upload &u : g_pending[c])

@@ -183,6 +183,16 @@ def check_plan(m, k, l):
         assert dd[t, 0] == ti[I, J]
         want = [[int(ti[I, p]), int(ti[J, p])] for p in dsrc[dsp[t]:dsp[t + 1]].tolist()]
         assert ds[dd[t, 1]:dd[t, 2]].tolist() == want and all(a >= 0 and b >= 0 for a, b in want)
+    # ---- backward solve: one CTA per panel; a CTA only waits for CTAs with a smaller block index (forward progress without
+    # co-residency), and its tile column is the factor column of its panel
+    order = P["bw_order"].tolist()
+    assert sorted(order) == list(range(nt))
+    at = {K: b for b, K in enumerate(order)}
+    ctp, ctr, cts = P["coltile_ptr"], P["coltile_row"], P["coltile_slot"]
+    for K in range(nt):
+        assert ctr[ctp[K]:ctp[K + 1]].tolist() == rows[K]
+        assert cts[ctp[K]:ctp[K + 1]].tolist() == [int(ti[I, K]) for I in rows[K]]
+        assert all(at[I] < at[K] for I in rows[K])
     return P, dict(nt=nt, n_steps=n_steps, rows=rows, cols=cols, step=step, present=present, psrc_of=psrc_of, n_updates=n_updates,
                    slot2tile=slot2tile)
 
@@ -252,6 +262,16 @@ def replay(P, info, seed=0, bs=2):
     assert np.abs(L - Lref).max() < 1e-10 * np.abs(Lref).max()
     yref = np.linalg.solve(Lref, b)
     assert np.abs(np.concatenate(y) - yref).max() < 1e-10 * max(1.0, np.abs(yref).max())
+    # backward solve in the order of its CTAs: x_K = L_KK^-T (y_K - sum_I L_IK^T x_I), every x_I already known
+    xs = [None] * nt
+    for K in P["bw_order"].tolist():
+        acc = y[K].copy()
+        for I in rows[K]:
+            assert xs[I] is not None
+            acc -= T[(I, K)].T @ xs[I]
+        xs[K] = np.linalg.solve(T[(K, K)].T, acc)
+    xref = np.linalg.solve(A, b)
+    assert np.abs(np.concatenate(xs) - xref).max() < 1e-9 * max(1.0, np.abs(xref).max())
 
 
 @pytest.mark.parametrize("case", sorted(CASES))
